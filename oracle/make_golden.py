@@ -1,0 +1,172 @@
+"""Generates tests/golden/*.npz by RUNNING THE UNMODIFIED REFERENCE.
+
+TEST INFRASTRUCTURE.  Runs only in the authoring container (needs
+/root/reference); the fixtures it writes are committed, so the GPU box and the
+CPU test-suite never need the reference tree.
+
+  python -m oracle.make_golden            # rewrites tests/golden/
+
+Every fixture stores the inputs (so a test can replay the same history through the
+port / the CUDA library) and the reference's outputs.
+"""
+import os
+import random
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refshim  # pylint: disable=g-import-not-at-top
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def synth_history(rng, num, obs_shape, terminal_p, num_actions=18):
+  obs = rng.randint(0, 256, size=(num,) + obs_shape).astype(np.uint8)
+  act = rng.randint(0, num_actions, size=num).astype(np.int32)
+  rew = np.clip(rng.randn(num), -1, 1).astype(np.float32)
+  term = (rng.rand(num) < terminal_p).astype(np.uint8)
+  return obs, act, rew, term
+
+
+def golden_sum_tree(sum_tree):
+  out = {}
+  for cap in (1, 2, 100, 1000):
+    rng = np.random.RandomState(100 + cap)
+    tree = sum_tree.SumTree(cap)
+    n = 400
+    idx = rng.randint(0, cap, size=n).astype(np.int64)
+    # f32-valued priorities (what set_priority receives) + some exact dups/zeros
+    val = np.sqrt(np.abs(rng.randn(n)) + 1e-10).astype(np.float32).astype(
+        np.float64)
+    val[rng.rand(n) < 0.05] = 0.0
+    val[7] = 12.5
+    for i, v in zip(idx, val):
+      tree.set(int(i), float(v))
+    queries = np.concatenate([[0.0, 1.0], rng.rand(64)])
+    picks = np.array([tree.sample(query_value=float(q)) for q in queries],
+                     dtype=np.int64)
+    random.seed(cap)
+    strat = np.array(tree.stratified_sample(32), dtype=np.int64)
+    out['cap%d_idx' % cap] = idx
+    out['cap%d_val' % cap] = val
+    out['cap%d_queries' % cap] = queries
+    out['cap%d_picks' % cap] = picks
+    out['cap%d_strat_seed%d' % (cap, cap)] = strat
+    out['cap%d_max' % cap] = np.float64(tree.max_recorded_priority)
+    for l, level in enumerate(tree.nodes):
+      out['cap%d_level%d' % (cap, l)] = level.copy()
+  np.savez_compressed(os.path.join(OUT, 'sum_tree.npz'), **out)
+
+
+def golden_uniform(crb):
+  out = {}
+  cases = {
+      # name: (obs_shape, stack, capacity, horizon, gamma, num_adds, term_p)
+      'small_wrap': ((6, 8), 4, 50, 3, 0.99, 137, 0.08),
+      'not_full': ((6, 8), 4, 64, 1, 0.99, 40, 0.1),
+      'atari_tiny': ((84, 84), 4, 24, 3, 0.99, 40, 0.1),
+      'long_horizon': ((4, 4), 2, 64, 10, 0.9, 150, 0.04),
+      'stack1': ((5, 3), 1, 20, 2, 1.0, 55, 0.2),
+  }
+  for name, (shape, stack, cap, n, gamma, adds, tp) in cases.items():
+    rng = np.random.RandomState(len(name))
+    obs, act, rew, term = synth_history(rng, adds, shape, tp)
+    mem = crb.OutOfGraphReplayBuffer(shape, stack, cap, 8, update_horizon=n,
+                                     gamma=gamma)
+    for k in range(adds):
+      mem.add(obs[k], act[k], rew[k], term[k])
+    valid = np.array([mem.is_valid_transition(i) for i in range(-2, cap + 2)],
+                     dtype=np.uint8)
+    good = [i for i in range(cap) if mem.is_valid_transition(i)]
+    batch = mem.sample_transition_batch(batch_size=len(good), indices=good)
+    np.random.seed(11)
+    drawn = np.array(mem.sample_index_batch(16), dtype=np.int64)
+    after = np.random.randint(0, 1 << 30)  # pins how many draws were consumed
+    p = name + '_'
+    out[p + 'cfg'] = np.array([stack, cap, n, adds], dtype=np.int64)
+    out[p + 'shape'] = np.array(shape, dtype=np.int64)
+    out[p + 'gamma'] = np.float64(gamma)
+    out[p + 'obs'], out[p + 'act'] = obs, act
+    out[p + 'rew'], out[p + 'term'] = rew, term
+    out[p + 'add_count'] = np.int64(mem.add_count)
+    out[p + 'invalid_range'] = np.asarray(mem.invalid_range, dtype=np.int64)
+    out[p + 'valid_m2_to_cap_p2'] = valid
+    out[p + 'good'] = np.array(good, dtype=np.int32)
+    for e, arr in zip(mem.get_transition_elements(len(good)), batch):
+      out[p + 'out_' + e.name] = arr
+    out[p + 'uniform_seed11'] = drawn
+    out[p + 'np_next_randint'] = np.int64(after)
+  np.savez_compressed(os.path.join(OUT, 'uniform_replay.npz'), **out)
+
+
+def golden_prioritized(prb):
+  out = {}
+  cases = {
+      'per_wrap': ((6, 8), 4, 100, 3, 0.99, 260, 0.05, 1000),
+      'per_not_full': ((6, 8), 4, 128, 3, 0.99, 90, 0.05, 1000),
+      'per_tight_budget': ((4, 4), 4, 32, 1, 0.99, 70, 0.45, 2),
+  }
+  for name, (shape, stack, cap, n, gamma, adds, tp, attempts) in cases.items():
+    rng = np.random.RandomState(len(name) * 7)
+    obs, act, rew, term = synth_history(rng, adds, shape, tp)
+    mem = prb.OutOfGraphPrioritizedReplayBuffer(
+        shape, stack, cap, 8, update_horizon=n, gamma=gamma,
+        max_sample_attempts=attempts)
+    add_prio = np.zeros(adds, dtype=np.float64)
+    for k in range(adds):
+      add_prio[k] = mem.sum_tree.max_recorded_priority
+      mem.add(obs[k], act[k], rew[k], term[k], add_prio[k])
+      if k % 17 == 5:  # interleave priority write-backs (with duplicates)
+        ids = rng.randint(0, min(cap, int(mem.add_count)), size=6).astype(
+            np.int32)
+        ids[1] = ids[0]
+        pr = np.sqrt(np.abs(rng.randn(6)) + 1e-10).astype(np.float32)
+        mem.set_priority(ids, pr)
+        out['%s_set%d_ids' % (name, k)] = ids
+        out['%s_set%d_pr' % (name, k)] = pr
+    p = name + '_'
+    results, errors, states = [], [], []
+    for rep in range(24):
+      random.seed(1000 + rep)
+      try:
+        results.append(np.array(mem.sample_index_batch(8), dtype=np.int64))
+        errors.append('')
+      except RuntimeError as e:
+        results.append(np.full(8, -1, dtype=np.int64))
+        errors.append(str(e))
+      states.append(random.random())  # pins how many draws were consumed
+    out[p + 'sample_idx'] = np.stack(results)
+    out[p + 'sample_err'] = np.array(errors)
+    out[p + 'sample_next_u'] = np.array(states)
+    good = [i for i in range(cap) if mem.is_valid_transition(i)][:40]
+    batch = mem.sample_transition_batch(batch_size=len(good), indices=good)
+    out[p + 'cfg'] = np.array([stack, cap, n, adds, attempts], dtype=np.int64)
+    out[p + 'shape'] = np.array(shape, dtype=np.int64)
+    out[p + 'gamma'] = np.float64(gamma)
+    out[p + 'obs'], out[p + 'act'] = obs, act
+    out[p + 'rew'], out[p + 'term'] = rew, term
+    out[p + 'add_prio'] = add_prio
+    out[p + 'add_count'] = np.int64(mem.add_count)
+    out[p + 'good'] = np.array(good, dtype=np.int32)
+    for e, arr in zip(mem.get_transition_elements(len(good)), batch):
+      out[p + 'out_' + e.name] = arr
+    out[p + 'max_recorded'] = np.float64(mem.sum_tree.max_recorded_priority)
+    for l, level in enumerate(mem.sum_tree.nodes):
+      out[p + 'level%d' % l] = level.copy()
+  np.savez_compressed(os.path.join(OUT, 'prioritized_replay.npz'), **out)
+
+
+def main():
+  st, crb, prb = refshim.load_reference()
+  os.makedirs(OUT, exist_ok=True)
+  golden_sum_tree(st)
+  golden_uniform(crb)
+  golden_prioritized(prb)
+  for f in sorted(os.listdir(OUT)):
+    print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == '__main__':
+  main()
