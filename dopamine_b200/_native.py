@@ -1,0 +1,220 @@
+"""ctypes binding of libb200replay.so (the C ABI declared in include/b200_replay.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc, and if
+there is no CUDA device every create call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'libb200replay.so')
+
+MAX_EXTRAS = 8
+OK = 0
+ERR_INVALID_ARGUMENT = 1
+ERR_CUDA = 2
+ERR_NEGATIVE_PRIORITY = 3
+ERR_EMPTY_TREE = 4
+ERR_SAMPLE_ATTEMPTS = 5
+ERR_TOO_FEW_TRANSITIONS = 6
+ERR_INDEX_RANGE = 7
+ERR_UNSUPPORTED = 8
+
+PRIORITY_EXPLICIT = 0
+PRIORITY_MAX_RECORDED = 1
+
+COL_OBSERVATION, COL_ACTION, COL_REWARD, COL_TERMINAL, COL_EXTRA0 = 0, 1, 2, 3, 4
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_int32 = ctypes.c_int32
+c_int64 = ctypes.c_int64
+c_uint64 = ctypes.c_uint64
+c_double = ctypes.c_double
+c_float = ctypes.c_float
+
+
+class Config(ctypes.Structure):
+  _fields_ = [
+      ('capacity', c_int64),
+      ('stack_size', c_int32),
+      ('update_horizon', c_int32),
+      ('gamma', c_double),
+      ('max_sample_attempts', c_int32),
+      ('prioritized', c_int32),
+      ('obs_bytes', c_int64),
+      ('obs_itemsize', c_int32),
+      ('action_bytes', c_int32),
+      ('reward_itemsize', c_int32),
+      ('terminal_itemsize', c_int32),
+      ('num_extras', c_int32),
+      ('extra_bytes', c_int32 * MAX_EXTRAS),
+      ('add_queue_rows', c_int32),
+  ]
+
+
+class Batch(ctypes.Structure):
+  _fields_ = [
+      ('state', c_void_p),
+      ('action', c_void_p),
+      ('reward', c_void_p),
+      ('next_state', c_void_p),
+      ('next_action', c_void_p),
+      ('next_reward', c_void_p),
+      ('terminal', c_void_p),
+      ('indices', c_void_p),
+      ('extras', c_void_p * MAX_EXTRAS),
+      ('sampling_probabilities', c_void_p),
+  ]
+
+
+class C51Args(ctypes.Structure):
+  _fields_ = [
+      ('batch', c_int32),
+      ('num_actions', c_int32),
+      ('num_atoms', c_int32),
+      ('cumulative_gamma', c_float),
+      ('support', c_void_p),
+      ('target_logits', c_void_p),
+      ('online_logits', c_void_p),
+      ('actions', c_void_p),
+      ('rewards', c_void_p),
+      ('terminals', c_void_p),
+      ('sampling_probabilities', c_void_p),
+      ('target', c_void_p),
+      ('loss', c_void_p),
+      ('priorities', c_void_p),
+      ('weights', c_void_p),
+      ('mean_weighted_loss', c_void_p),
+      ('grad_logits', c_void_p),
+  ]
+
+
+P = ctypes.POINTER
+
+# name -> (restype, argtypes); must list every symbol of include/b200_replay.h.
+SIGNATURES = {
+    'b2r_last_error': (ctypes.c_char_p, []),
+    'b2r_abi_version': (c_int, []),
+    'b2r_launch_count': (c_int64, []),
+    'b2r_tree_create': (c_int, [c_int64, P(c_void_p)]),
+    'b2r_tree_destroy': (c_int, [c_void_p]),
+    'b2r_tree_depth': (c_int, [c_void_p]),
+    'b2r_tree_set': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, P(c_int64),
+                             c_void_p]),
+    'b2r_tree_set_device': (c_int, [c_void_p, c_int64, c_void_p, c_void_p,
+                                    c_void_p]),
+    'b2r_tree_check': (c_int, [c_void_p, c_void_p]),
+    'b2r_tree_get': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    'b2r_tree_total': (c_int, [c_void_p, P(c_double), c_void_p]),
+    'b2r_tree_max_recorded': (c_int, [c_void_p, P(c_double), c_void_p]),
+    'b2r_tree_set_max_recorded': (c_int, [c_void_p, c_double, c_void_p]),
+    'b2r_tree_sample': (c_int, [c_void_p, c_int64, c_void_p, c_void_p,
+                                c_void_p]),
+    'b2r_tree_read_level': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    'b2r_tree_write_level': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    'b2r_create': (c_int, [P(Config), P(c_void_p)]),
+    'b2r_destroy': (c_int, [c_void_p]),
+    'b2r_buffer_tree': (c_void_p, [c_void_p]),
+    'b2r_add': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                        P(c_void_p), c_double, c_int, c_void_p]),
+    'b2r_flush': (c_int, [c_void_p, c_void_p]),
+    'b2r_add_count': (c_int64, [c_void_p]),
+    'b2r_cursor': (c_int64, [c_void_p]),
+    'b2r_get_invalid_range': (c_int, [c_void_p, c_void_p, P(c_int32)]),
+    'b2r_set_state': (c_int, [c_void_p, c_int64, c_void_p, c_int32]),
+    'b2r_valid_mask': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    'b2r_uniform_bounds': (c_int, [c_void_p, P(c_int64), P(c_int64)]),
+    'b2r_sample_indices_uniform': (c_int, [
+        c_void_p, c_int32, c_int32, c_void_p, c_void_p, P(c_int32), P(c_int32),
+        P(c_int32), c_void_p]),
+    'b2r_sample_indices_prioritized': (c_int, [
+        c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, P(c_int32),
+        P(c_int32), c_void_p]),
+    'b2r_sample_indices_device': (c_int, [c_void_p, c_int32, c_uint64, c_uint64,
+                                          c_void_p, c_void_p]),
+    'b2r_check': (c_int, [c_void_p, c_void_p]),
+    'b2r_gather_device': (c_int, [c_void_p, c_int32, c_void_p, P(Batch),
+                                  c_void_p]),
+    'b2r_gather': (c_int, [c_void_p, c_int32, c_void_p, P(Batch), c_void_p]),
+    'b2r_sample_transition_batch_device': (c_int, [
+        c_void_p, c_int32, c_uint64, c_uint64, P(Batch), c_void_p]),
+    'b2r_set_priority': (c_int, [c_void_p, c_int64, c_void_p, c_void_p,
+                                 P(c_int64), c_void_p]),
+    'b2r_set_priority_device': (c_int, [c_void_p, c_int64, c_void_p, c_void_p,
+                                        c_void_p]),
+    'b2r_get_priority': (c_int, [c_void_p, c_int64, c_void_p, c_void_p,
+                                 c_void_p]),
+    'b2r_get_priority_device': (c_int, [c_void_p, c_int64, c_void_p, c_void_p,
+                                        c_void_p]),
+    'b2r_store_read': (c_int, [c_void_p, c_int32, c_int64, c_int64, c_void_p,
+                               c_void_p]),
+    'b2r_store_write': (c_int, [c_void_p, c_int32, c_int64, c_int64, c_void_p,
+                                c_void_p]),
+    'b2r_store_device_ptr': (c_void_p, [c_void_p, c_int32]),
+    'b2r_sample_indices_sharded_device': (c_int, [
+        c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
+        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'b2r_total_device_ptr': (c_void_p, [c_void_p]),
+    'b2r_c51_project': (c_int, [c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    'b2r_c51_loss': (c_int, [P(C51Args), c_void_p]),
+}
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+  """A libb200replay call failed; `.code` is the b2r_status."""
+
+  def __init__(self, code, message):
+    super().__init__(message)
+    self.code = code
+
+
+def build():
+  from dopamine_b200.csrc import build as _build  # pylint: disable=g-import-not-at-top
+  return _build.build()
+
+
+def lib():
+  """Loads (building first if needed) the shared library. Never falls back."""
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      build()
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+      fn = getattr(handle, name)  # AttributeError if the ABI is incomplete
+      fn.restype = restype
+      fn.argtypes = argtypes
+    _lib = handle
+  return _lib
+
+
+def last_error():
+  return lib().b2r_last_error().decode('utf-8', 'replace')
+
+
+def check(status):
+  """Raises NativeError for a non-zero status."""
+  if status != OK:
+    raise NativeError(status, last_error())
+
+
+def ptr(array):
+  """Address of a C-contiguous numpy array."""
+  assert array.flags['C_CONTIGUOUS']
+  return array.ctypes.data
+
+
+def current_stream():
+  """torch's current CUDA stream as an integer handle (plumbing only)."""
+  import torch  # pylint: disable=g-import-not-at-top
+  return torch.cuda.current_stream().cuda_stream
+
+
+def as_i64(values):
+  return np.ascontiguousarray(values, dtype=np.int64)

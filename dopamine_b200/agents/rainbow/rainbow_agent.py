@@ -1,0 +1,223 @@
+"""Rainbow's C51 target / loss math as fused CUDA kernels.
+
+Drop-in for the hot-path pieces of `dopamine/agents/rainbow/rainbow_agent.py`:
+  * `project_distribution(supports, weights, target_support, validate_args)`
+    (rainbow_agent.py:340-494) — same argument meaning and validation errors,
+    over torch CUDA tensors (numpy arrays are accepted and round-tripped);
+  * `build_target_distribution` / `c51_loss` — the n-step distributional Bellman
+    target, projection, softmax cross-entropy, `sqrt(loss + 1e-10)` priorities
+    and `1/sqrt(p + 1e-10) / max` importance weights of
+    `_build_target_distribution` (rainbow_agent.py:200-251) and `_build_train_op`
+    (rainbow_agent.py:253-305), in one launch (+ a one-CTA finalize);
+  * `C51Loss` — the same as a differentiable torch op, so the conv Q-network
+    (cuDNN through PyTorch, the only dense contraction on the path) trains on it.
+
+The agent class `RainbowAgent` (host glue: epsilon-greedy acting, update cadence,
+target sync) lives in `dopamine_b200/agents/rainbow/agent.py`.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from dopamine_b200 import _native
+
+
+def _torch():
+  import torch  # pylint: disable=g-import-not-at-top
+  return torch
+
+
+def make_support(vmax, num_atoms, device='cuda'):
+  """`tf.linspace(-vmax, vmax, num_atoms)` in f32 (rainbow_agent.py:124-126).
+
+  TF-1.x evaluates `start + i * step` in f32.
+  """
+  torch = _torch()
+  vmax = np.float32(float(vmax))
+  if num_atoms == 1:
+    host = np.array([-vmax], dtype=np.float32)
+  else:
+    step = (vmax - (-vmax)) / np.float32(num_atoms - 1)
+    host = (-vmax + np.arange(num_atoms, dtype=np.float32) * step).astype(
+        np.float32)
+  return torch.as_tensor(host, device=device)
+
+
+def _as_cuda_f32(x):
+  torch = _torch()
+  if isinstance(x, torch.Tensor):
+    return x.to(device='cuda', dtype=torch.float32).contiguous(), False
+  return torch.as_tensor(np.asarray(x, dtype=np.float32), device='cuda'), True
+
+
+def project_distribution(supports, weights, target_support,
+                         validate_args=False):
+  """Projects a batch of (support, weights) onto target_support (Eq. 7 of C51).
+
+  Args:
+    supports: (batch_size, num_dims) supports of the source distributions.
+    weights: (batch_size, num_dims) weights on those supports.
+    target_support: (num_dims,) equally spaced, increasing target support.
+    validate_args: also check monotonicity / equal spacing of target_support
+      (a device->host read), as the reference's tf.Assert ops do.
+
+  Returns:
+    (batch_size, num_dims) projection; a CUDA tensor, or a numpy array if the
+    inputs were numpy.
+
+  Raises:
+    ValueError: on incompatible shapes or an invalid target_support.
+  """
+  torch = _torch()
+  supports, from_numpy = _as_cuda_f32(supports)
+  weights, _ = _as_cuda_f32(weights)
+  target_support, _ = _as_cuda_f32(target_support)
+  if target_support.dim() == 0:
+    raise ValueError('Index out of range: target_support has no dimensions')
+  if target_support.dim() != 1:
+    raise ValueError('target_support must have rank 1, index out of bounds '
+                     'for rank {}'.format(target_support.dim()))
+  if supports.dim() != 2 or tuple(supports.shape) != tuple(weights.shape):
+    raise ValueError('Shapes {} and {} are incompatible'.format(
+        tuple(supports.shape), tuple(weights.shape)))
+  if supports.shape[1] != target_support.shape[0]:
+    raise ValueError('Shapes {} and {} are incompatible'.format(
+        tuple(supports.shape[1:]), tuple(target_support.shape)))
+  if target_support.shape[0] < 2:
+    raise ValueError('target_support needs at least two atoms')
+  if validate_args:
+    deltas = (target_support[1:] - target_support[:-1]).cpu()
+    if not bool((deltas > 0).all()):
+      raise ValueError('assertion failed: target_support must be increasing')
+    if not bool((deltas == deltas[0]).all()):
+      raise ValueError('assertion failed: target_support must be equally spaced')
+  out = torch.empty_like(supports)
+  _native.check(_native.lib().b2r_c51_project(
+      supports.shape[0], supports.shape[1], supports.data_ptr(),
+      weights.data_ptr(), target_support.data_ptr(), out.data_ptr(),
+      _native.current_stream()))
+  return out.cpu().numpy() if from_numpy else out
+
+
+def c51_loss(online_logits, target_logits, actions, rewards, terminals,
+             sampling_probabilities, support, cumulative_gamma,
+             want_target=False, want_grad=False):
+  """Fused Rainbow update math for one batch, all on the device.
+
+  Args:
+    online_logits: (B, A, N) f32, online network on `state`.
+    target_logits: (B, A, N) f32, target network on `next_state`.
+    actions: (B,) int32; rewards: (B,) f32 n-step returns; terminals: (B,) uint8.
+    sampling_probabilities: (B,) f32 raw priorities from the replay batch, or
+      None for the 'uniform' replay scheme (rainbow_agent.py:273-295).
+    support: (N,) f32 (see make_support); cumulative_gamma: gamma ** n.
+  Returns:
+    dict with 'loss' (B,), 'priorities' (B,) = sqrt(loss + 1e-10), 'weights'
+    (B,), 'mean_weighted_loss' (scalar tensor) and optionally 'target' (B, N),
+    'grad_logits' (B, A, N) = d mean_weighted_loss / d online_logits.
+  """
+  torch = _torch()
+  b, a, n = online_logits.shape
+  assert tuple(target_logits.shape) == (b, a, n)
+  assert online_logits.dtype == torch.float32 and online_logits.is_cuda
+  assert target_logits.dtype == torch.float32 and target_logits.is_cuda
+  assert actions.dtype == torch.int32 and rewards.dtype == torch.float32
+  assert terminals.dtype == torch.uint8 and support.dtype == torch.float32
+  online_logits = online_logits.contiguous()
+  target_logits = target_logits.contiguous()
+  dev = online_logits.device
+  out = {
+      'loss': torch.empty(b, dtype=torch.float32, device=dev),
+      'priorities': torch.empty(b, dtype=torch.float32, device=dev),
+      'weights': torch.empty(b, dtype=torch.float32, device=dev),
+      'mean_weighted_loss': torch.empty((), dtype=torch.float32, device=dev),
+  }
+  if want_target:
+    out['target'] = torch.empty(b, n, dtype=torch.float32, device=dev)
+  if want_grad:
+    out['grad_logits'] = torch.empty(b, a, n, dtype=torch.float32, device=dev)
+  args = _native.C51Args()
+  args.batch, args.num_actions, args.num_atoms = b, a, n
+  args.cumulative_gamma = float(np.float32(cumulative_gamma))
+  args.support = support.data_ptr()
+  args.target_logits = target_logits.data_ptr()
+  args.online_logits = online_logits.data_ptr()
+  args.actions = actions.contiguous().data_ptr()
+  args.rewards = rewards.contiguous().data_ptr()
+  args.terminals = terminals.contiguous().data_ptr()
+  args.sampling_probabilities = (
+      sampling_probabilities.contiguous().data_ptr()
+      if sampling_probabilities is not None else None)
+  args.target = out['target'].data_ptr() if want_target else None
+  args.loss = out['loss'].data_ptr()
+  args.priorities = out['priorities'].data_ptr()
+  args.weights = out['weights'].data_ptr()
+  args.mean_weighted_loss = out['mean_weighted_loss'].data_ptr()
+  args.grad_logits = out['grad_logits'].data_ptr() if want_grad else None
+  _native.check(_native.lib().b2r_c51_loss(ctypes.byref(args),
+                                           _native.current_stream()))
+  return out
+
+
+def build_target_distribution(rewards, terminals, target_logits, support,
+                              cumulative_gamma):
+  """The projected C51 target of `_build_target_distribution`
+  (rainbow_agent.py:200-251) for a batch, given the target net's logits."""
+  torch = _torch()
+  b, a, _ = target_logits.shape
+  zeros_i = torch.zeros(b, dtype=torch.int32, device=target_logits.device)
+  out = c51_loss(target_logits, target_logits, zeros_i, rewards, terminals, None,
+                 support, cumulative_gamma, want_target=True)
+  del a
+  return out['target']
+
+
+def cumulative_gamma(gamma, update_horizon):
+  """dqn_agent.py:175."""
+  return math.pow(gamma, update_horizon)
+
+
+class C51Loss(object):
+  """Differentiable wrapper: `loss, aux = C51Loss.apply(online_logits, ...)`.
+
+  Forward runs the fused kernel once (it also produces the gradient w.r.t. the
+  online logits); backward scales that gradient by the upstream scalar.
+  """
+
+  _fn = None
+
+  @classmethod
+  def _function(cls):
+    if cls._fn is None:
+      torch = _torch()
+
+      class _Fn(torch.autograd.Function):
+
+        @staticmethod
+        def forward(ctx, online_logits, target_logits, actions, rewards,
+                    terminals, probs, support, gamma_n):
+          out = c51_loss(online_logits.detach(), target_logits.detach(), actions,
+                         rewards, terminals, probs, support, gamma_n,
+                         want_grad=True)
+          ctx.save_for_backward(out['grad_logits'])
+          ctx.mark_non_differentiable(out['priorities'], out['loss'],
+                                      out['weights'])
+          return (out['mean_weighted_loss'], out['priorities'], out['loss'],
+                  out['weights'])
+
+        @staticmethod
+        def backward(ctx, grad_mean, *unused):
+          (grad_logits,) = ctx.saved_tensors
+          return (grad_logits * grad_mean, None, None, None, None, None, None,
+                  None)
+
+      cls._fn = _Fn
+    return cls._fn
+
+  @classmethod
+  def apply(cls, online_logits, target_logits, actions, rewards, terminals,
+            sampling_probabilities, support, gamma_n):
+    return cls._function().apply(online_logits, target_logits, actions, rewards,
+                                 terminals, sampling_probabilities, support,
+                                 gamma_n)

@@ -1,0 +1,64 @@
+"""Builds libb200replay.so in-tree with nvcc for sm_100a (no JIT cache)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+ROOT = os.path.dirname(PKG)
+LIB = os.path.join(PKG, 'libb200replay.so')
+SOURCES = ['common.cu', 'tree.cu', 'replay.cu', 'sample.cu', 'gather.cu',
+           'c51.cu']
+HEADERS = ['common.cuh', 'tree.cuh', 'replay.cuh',
+           os.path.join(ROOT, 'include', 'b200_replay.h')]
+
+NVCC_FLAGS = [
+    '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17',
+    '-lineinfo', '-Xcompiler', '-fPIC',
+    '-I', os.path.join(ROOT, 'include'), '-I', HERE,
+]
+
+
+def _nvcc():
+  for cand in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', 'nvcc'):
+    if cand and (os.path.isabs(cand) and os.path.exists(cand) or
+                 not os.path.isabs(cand)):
+      return cand
+  raise RuntimeError('nvcc not found')
+
+
+def _stale(target, deps):
+  if not os.path.exists(target):
+    return True
+  t = os.path.getmtime(target)
+  return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False, extra_flags=()):
+  """Compiles every .cu for sm_100a and links the C-ABI shared library."""
+  nvcc = _nvcc()
+  obj_dir = os.path.join(HERE, '_obj')
+  os.makedirs(obj_dir, exist_ok=True)
+  headers = [h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS]
+  objects = []
+  for src in SOURCES:
+    src_path = os.path.join(HERE, src)
+    obj = os.path.join(obj_dir, src.replace('.cu', '.o'))
+    objects.append(obj)
+    if force or _stale(obj, [src_path] + headers + [__file__]):
+      cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ['-c', src_path, '-o', obj]
+      if verbose:
+        print(' '.join(cmd), file=sys.stderr)
+      subprocess.check_call(cmd)
+  if force or _stale(LIB, objects):
+    cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a',
+           '-o', LIB] + objects + ['-lcudart_static', '-lpthread', '-ldl', '-lrt']
+    if verbose:
+      print(' '.join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
+  return LIB
+
+
+if __name__ == '__main__':
+  print(build(force='--force' in sys.argv, verbose=True,
+              extra_flags=('-Xptxas', '-v') if '--ptxas' in sys.argv else ()))

@@ -1,0 +1,53 @@
+// Error plumbing and the pinned bounce buffer.
+#include "common.cuh"
+
+namespace b2r {
+
+std::atomic<int64_t> g_launches{0};
+
+std::string &last_error_slot() {
+  static thread_local std::string slot;
+  return slot;
+}
+
+int fail(int code, const char *fmt, ...) {
+  char text[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(text, sizeof(text), fmt, ap);
+  va_end(ap);
+  last_error_slot() = text;
+  return code;
+}
+
+int Bounce::reserve(size_t bytes) {
+  if (bytes <= cap) return B2R_OK;
+  size_t want = cap ? cap : 4096;
+  while (want < bytes) want *= 2;
+  release();
+  B2R_CUDA(cudaMallocHost(reinterpret_cast<void **>(&host), want));
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&dev), want));
+  cap = want;
+  return B2R_OK;
+}
+
+void Bounce::release() {
+  if (host) cudaFreeHost(host);
+  if (dev) cudaFree(dev);
+  host = dev = nullptr;
+  cap = 0;
+}
+
+}  // namespace b2r
+
+extern "C" {
+
+const char *b2r_last_error(void) { return b2r::last_error_slot().c_str(); }
+
+int b2r_abi_version(void) { return 1; }
+
+int64_t b2r_launch_count(void) {
+  return b2r::g_launches.load(std::memory_order_relaxed);
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// Shared helpers for libb200replay (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "b200_replay.h"
+
+namespace b2r {
+
+// ---- error plumbing ---------------------------------------------------------
+std::string &last_error_slot();
+int fail(int code, const char *fmt, ...);
+extern std::atomic<int64_t> g_launches;
+
+#define B2R_CUDA(expr)                                                        \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess)                                                    \
+      return ::b2r::fail(B2R_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,        \
+                         cudaGetErrorString(_e), __FILE__, __LINE__);         \
+  } while (0)
+
+#define B2R_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != B2R_OK) return _s; \
+  } while (0)
+
+// Counts the launch and surfaces launch-configuration errors immediately.
+#define B2R_LAUNCHED()                                                        \
+  do {                                                                        \
+    ::b2r::g_launches.fetch_add(1, std::memory_order_relaxed);                \
+    B2R_CUDA(cudaGetLastError());                                             \
+  } while (0)
+
+static inline cudaStream_t as_stream(b2r_stream s) {
+  return reinterpret_cast<cudaStream_t>(s);
+}
+
+// Pinned host <-> device bounce buffer that grows on demand.
+struct Bounce {
+  uint8_t *host = nullptr;
+  uint8_t *dev = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes);
+  void release();
+};
+
+// ---- device helpers ----------------------------------------------------------
+__device__ __forceinline__ int64_t wrap_index(int64_t i, int64_t cap) {
+  int64_t r = i % cap;
+  return r < 0 ? r + cap : r;
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter = (lo, hi, stream, 0), key = seed.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
+                                              uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1,
+                                              uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 53-bit uniform in [0,1) from draw number `n` of stream (seed, offset).
+__device__ __forceinline__ double philox_uniform53(uint64_t seed, uint64_t offset,
+                                                   uint64_t n) {
+  uint32_t o[4];
+  philox4x32_10((uint32_t)n, (uint32_t)(n >> 32), (uint32_t)offset,
+                (uint32_t)(offset >> 32), (uint32_t)seed, (uint32_t)(seed >> 32),
+                o);
+  uint64_t a = o[0] >> 5, b = o[1] >> 6;  // 27 + 26 bits
+  return (double)((a << 26) | b) * (1.0 / 9007199254740992.0);
+}
+
+}  // namespace b2r

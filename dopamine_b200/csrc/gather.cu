@@ -1,0 +1,439 @@
+// Fused batch assembly: replaces the per-index Python loop of
+// OutOfGraphReplayBuffer.sample_transition_batch (circular_replay_buffer.py:516-556,
+// stacks via 338-375) and the sampling_probabilities fill of the prioritized
+// buffer (prioritized_replay_buffer.py:193-200).
+//
+// Per sampled index i (one launch for the whole batch):
+//   L         = 1 + offset of the first non-zero terminal in slots i..i+n-1, else n
+//   state     = frames i-S+1..i,      stack axis innermost  (np.moveaxis, CRB:375)
+//   next_state= frames i+L-S+1..i+L   (deterministic even when terminal, Q14)
+//   reward    = np.sum(f32(gamma^k) * r[i+k], k < L)  in numpy's f32 order
+//   next_action / next_reward = rows at (i+L) mod C; action/extras = rows at i
+//   terminal  = any terminal in the trajectory; indices = i; priorities = leaf(i)
+//
+// HBM-bound byte movement: per transition (S=4, n=3, 84x84 u8) 7 unique frames are
+// read (49 392 B, one contiguous span of the ring unless it wraps) and 2 x 28 224 B
+// written.  Fast path (S=4, 1-byte pixels, frame % 16 == 0): each thread moves one
+// 16-pixel column of the span — up to 7 x LDG.128, a PRMT byte-transpose into the
+// [pixel][stack] interleave, 8 x STG.128 — with frames shared between state and
+// next_state read once.
+#include "replay.cuh"
+
+namespace b2r {
+namespace {
+
+constexpr int kMaxRowCopies = 3 + B2R_MAX_EXTRAS;
+
+struct RowCopy {
+  const uint8_t *src;
+  uint8_t *dst;
+  int32_t row_bytes;
+  int32_t at_next;  // 0: row i, 1: row (i + L) mod C
+};
+
+struct GatherArgs {
+  int64_t capacity;
+  int32_t stack, horizon, batch;
+  int64_t obs_bytes;
+  int32_t obs_itemsize;
+  const uint8_t *obs;
+  const uint8_t *term_flag;
+  const void *reward;   // f32 or f64 column
+  int32_t reward_itemsize;
+  const float *discounts;
+  const int32_t *indices;
+  uint8_t *state, *next_state;
+  void *ret;            // n-step return, reward dtype
+  uint8_t *terminal_out;
+  int32_t terminal_itemsize;
+  int32_t *indices_out;
+  int32_t n_copies;
+  RowCopy copies[kMaxRowCopies];
+  const double *leaves;  // tree leaf level (nullable)
+  float *prio_out;
+};
+
+// Trajectory length and terminal flag (circular_replay_buffer.py:517-527).
+__device__ __forceinline__ int trajectory_length(const uint8_t *__restrict__ term,
+                                                 int64_t i, int horizon,
+                                                 int64_t cap, bool *ends) {
+  for (int k = 0; k < horizon; ++k) {
+    int64_t s = i + k;
+    if (s >= cap) s -= cap;
+    if (term[s]) {
+      *ends = true;
+      return k + 1;
+    }
+  }
+  *ends = false;
+  return horizon;
+}
+
+// np.sum(discount[:L] * reward[i:i+L]) in numpy's evaluation order (probed on
+// numpy 2.3.5; DESIGN.md "n-step return"): L < 8: +0.0f then left to right;
+// 8 <= L <= 128: 8-lane unrolled block, pairwise combine, sequential tail.
+template <typename R>
+__device__ __forceinline__ R mul_rn(float d, R r);
+template <>
+__device__ __forceinline__ float mul_rn<float>(float d, float r) { return __fmul_rn(d, r); }
+template <>
+__device__ __forceinline__ double mul_rn<double>(float d, double r) { return __dmul_rn((double)d, r); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
+template <typename R>
+__device__ R nstep_return(const R *__restrict__ reward,
+                          const float *__restrict__ disc, int64_t i, int length,
+                          int64_t cap) {
+  auto term = [&](int k) {
+    int64_t s = i + k;
+    if (s >= cap) s -= cap;
+    return mul_rn<R>(disc[k], reward[s]);
+  };
+  if (length < 8) {
+    R acc = (R)0;
+    for (int k = 0; k < length; ++k) acc = add_rn(acc, term(k));
+    return acc;
+  }
+  R r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = term(j);
+  int k = 8;
+  for (; k < length - (length % 8); k += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = add_rn(r[j], term(k + j));
+  }
+  R acc = add_rn(add_rn(add_rn(r[0], r[1]), add_rn(r[2], r[3])),
+                 add_rn(add_rn(r[4], r[5]), add_rn(r[6], r[7])));
+  for (; k < length; ++k) acc = add_rn(acc, term(k));
+  return acc;
+}
+
+// Scalar outputs of one transition; run by one warp (lane-strided byte copies).
+__device__ void write_scalars(const GatherArgs &a, int b, int64_t i, int length,
+                              bool ends, int lane) {
+  int64_t nxt = i + length;
+  if (nxt >= a.capacity) nxt -= a.capacity;
+  if (lane == 0) {
+    if (a.ret) {
+      if (a.reward_itemsize == 4)
+        static_cast<float *>(a.ret)[b] = nstep_return<float>(
+            static_cast<const float *>(a.reward), a.discounts, i, length, a.capacity);
+      else
+        static_cast<double *>(a.ret)[b] = nstep_return<double>(
+            static_cast<const double *>(a.reward), a.discounts, i, length, a.capacity);
+    }
+    if (a.terminal_out) {
+      uint8_t *t = a.terminal_out + (int64_t)b * a.terminal_itemsize;
+      t[0] = ends ? 1 : 0;
+      for (int k = 1; k < a.terminal_itemsize; ++k) t[k] = 0;
+    }
+    if (a.indices_out) a.indices_out[b] = (int32_t)i;
+    if (a.prio_out) a.prio_out[b] = (float)a.leaves[i];  // PRB:231-235
+  }
+  for (int c = 0; c < a.n_copies; ++c) {
+    const RowCopy rc = a.copies[c];
+    const uint8_t *s = rc.src + (rc.at_next ? nxt : i) * (int64_t)rc.row_bytes;
+    uint8_t *d = rc.dst + (int64_t)b * rc.row_bytes;
+    for (int k = lane; k < rc.row_bytes; k += 32) d[k] = s[k];
+  }
+}
+
+// [a0 a1 a2 a3] x4 frames -> 4 words [a_p b_p c_p d_p], p = 0..3.
+__device__ __forceinline__ uint4 interleave4(uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+  const uint32_t ab_lo = __byte_perm(a, b, 0x5140);  // a0 b0 a1 b1
+  const uint32_t ab_hi = __byte_perm(a, b, 0x7362);  // a2 b2 a3 b3
+  const uint32_t cd_lo = __byte_perm(c, d, 0x5140);
+  const uint32_t cd_hi = __byte_perm(c, d, 0x7362);
+  uint4 o;
+  o.x = __byte_perm(ab_lo, cd_lo, 0x5410);  // a0 b0 c0 d0
+  o.y = __byte_perm(ab_lo, cd_lo, 0x7632);  // a1 b1 c1 d1
+  o.z = __byte_perm(ab_hi, cd_hi, 0x5410);
+  o.w = __byte_perm(ab_hi, cd_hi, 0x7632);
+  return o;
+}
+
+__device__ __forceinline__ void store_stack16(uint8_t *dst, const uint4 f0,
+                                              const uint4 f1, const uint4 f2,
+                                              const uint4 f3) {
+  uint4 *d = reinterpret_cast<uint4 *>(dst);
+  d[0] = interleave4(f0.x, f1.x, f2.x, f3.x);
+  d[1] = interleave4(f0.y, f1.y, f2.y, f3.y);
+  d[2] = interleave4(f0.z, f1.z, f2.z, f3.z);
+  d[3] = interleave4(f0.w, f1.w, f2.w, f3.w);
+}
+
+__device__ __forceinline__ uint4 load_frame16(const uint8_t *__restrict__ obs,
+                                              int64_t slot, int64_t cap,
+                                              int64_t obs_bytes, int chunk) {
+  if (slot < 0) slot += cap;
+  if (slot >= cap) slot -= cap;
+  return __ldg(reinterpret_cast<const uint4 *>(obs + slot * obs_bytes) + chunk);
+}
+
+// Fast path: stack 4, 1-byte pixels, obs_bytes % 16 == 0.
+// grid = (ceil(chunks / blockDim), batch); thread = one 16-pixel column.
+__global__ void __launch_bounds__(128) gather_stack4_u8_kernel(GatherArgs a) {
+  const int b = blockIdx.y;
+  const int64_t i = a.indices[b];
+  bool ends;
+  const int length = trajectory_length(a.term_flag, i, a.horizon, a.capacity, &ends);
+  if (blockIdx.x == 0 && threadIdx.x < 32)
+    write_scalars(a, b, i, length, ends, threadIdx.x);
+
+  const int chunks = (int)(a.obs_bytes >> 4);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= chunks) return;
+
+  // frames i-3 .. i
+  const uint4 s0 = load_frame16(a.obs, i - 3, a.capacity, a.obs_bytes, c);
+  const uint4 s1 = load_frame16(a.obs, i - 2, a.capacity, a.obs_bytes, c);
+  const uint4 s2 = load_frame16(a.obs, i - 1, a.capacity, a.obs_bytes, c);
+  const uint4 s3 = load_frame16(a.obs, i, a.capacity, a.obs_bytes, c);
+  // frames i+L-3 .. i+L: the first 4-L of them are state frames already loaded.
+  uint4 n0, n1, n2, n3;
+  const int64_t j = i + length;  // < 2 * capacity
+  if (length == 1) {
+    n0 = s1; n1 = s2; n2 = s3;
+    n3 = load_frame16(a.obs, j, a.capacity, a.obs_bytes, c);
+  } else if (length == 2) {
+    n0 = s2; n1 = s3;
+    n2 = load_frame16(a.obs, j - 1, a.capacity, a.obs_bytes, c);
+    n3 = load_frame16(a.obs, j, a.capacity, a.obs_bytes, c);
+  } else if (length == 3) {
+    n0 = s3;
+    n1 = load_frame16(a.obs, j - 2, a.capacity, a.obs_bytes, c);
+    n2 = load_frame16(a.obs, j - 1, a.capacity, a.obs_bytes, c);
+    n3 = load_frame16(a.obs, j, a.capacity, a.obs_bytes, c);
+  } else {
+    n0 = load_frame16(a.obs, j - 3, a.capacity, a.obs_bytes, c);
+    n1 = load_frame16(a.obs, j - 2, a.capacity, a.obs_bytes, c);
+    n2 = load_frame16(a.obs, j - 1, a.capacity, a.obs_bytes, c);
+    n3 = load_frame16(a.obs, j, a.capacity, a.obs_bytes, c);
+  }
+  const int64_t out_off = (int64_t)b * a.obs_bytes * 4 + (int64_t)c * 64;
+  if (a.state) store_stack16(a.state + out_off, s0, s1, s2, s3);
+  if (a.next_state) store_stack16(a.next_state + out_off, n0, n1, n2, n3);
+}
+
+// General path: any stack size / element size. thread = one observation element.
+__global__ void __launch_bounds__(256) gather_generic_kernel(GatherArgs a) {
+  const int b = blockIdx.y;
+  const int64_t i = a.indices[b];
+  bool ends;
+  const int length = trajectory_length(a.term_flag, i, a.horizon, a.capacity, &ends);
+  if (blockIdx.x == 0 && threadIdx.x < 32)
+    write_scalars(a, b, i, length, ends, threadIdx.x);
+
+  const int es = a.obs_itemsize;
+  const int64_t elems = a.obs_bytes / es;
+  const int64_t j = i + length;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < elems;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    for (int k = 0; k < a.stack; ++k) {
+      const int64_t fs = wrap_index(i - a.stack + 1 + k, a.capacity);
+      const int64_t fn = wrap_index(j - a.stack + 1 + k, a.capacity);
+      const uint8_t *ps = a.obs + fs * a.obs_bytes + e * es;
+      const uint8_t *pn = a.obs + fn * a.obs_bytes + e * es;
+      const int64_t o = ((int64_t)b * elems * a.stack + e * a.stack + k) * es;
+      for (int q = 0; q < es; ++q) {
+        if (a.state) a.state[o + q] = ps[q];
+        if (a.next_state) a.next_state[o + q] = pn[q];
+      }
+    }
+  }
+}
+
+__global__ void get_priority_kernel(const double *__restrict__ leaves, int64_t n,
+                                    const int32_t *__restrict__ indices,
+                                    float *__restrict__ out) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < n) out[k] = (float)leaves[indices[k]];
+}
+
+}  // namespace
+
+int launch_gather(b2r_buffer *b, int32_t batch, const int32_t *indices_dev,
+                  const b2r_batch *out, cudaStream_t stream) {
+  GatherArgs a;
+  a.capacity = b->cfg.capacity;
+  a.stack = b->cfg.stack_size;
+  a.horizon = b->cfg.update_horizon;
+  a.batch = batch;
+  a.obs_bytes = b->cfg.obs_bytes;
+  a.obs_itemsize = b->cfg.obs_itemsize;
+  a.obs = b->col[0].dev;
+  a.term_flag = b->term_flag;
+  a.reward = b->col[2].dev;
+  a.reward_itemsize = b->cfg.reward_itemsize;
+  a.discounts = b->discounts;
+  a.indices = indices_dev;
+  a.state = static_cast<uint8_t *>(out->state);
+  a.next_state = static_cast<uint8_t *>(out->next_state);
+  a.ret = out->reward;
+  a.terminal_out = static_cast<uint8_t *>(out->terminal);
+  a.terminal_itemsize = b->cfg.terminal_itemsize;
+  a.indices_out = out->indices;
+  a.n_copies = 0;
+  auto add_copy = [&](int column, void *dst, int at_next) {
+    if (!dst) return;
+    RowCopy &rc = a.copies[a.n_copies++];
+    rc.src = b->col[column].dev;
+    rc.dst = static_cast<uint8_t *>(dst);
+    rc.row_bytes = (int32_t)b->col[column].row_bytes;
+    rc.at_next = at_next;
+  };
+  add_copy(B2R_COL_ACTION, out->action, 0);
+  add_copy(B2R_COL_ACTION, out->next_action, 1);
+  add_copy(B2R_COL_REWARD, out->next_reward, 1);
+  for (int e = 0; e < b->cfg.num_extras; ++e)
+    add_copy(B2R_COL_EXTRA0 + e, out->extras[e], 0);
+  a.leaves = nullptr;
+  a.prio_out = nullptr;
+  if (b->tree && out->sampling_probabilities) {
+    a.leaves = b->tree->heap + (b->tree->leaves - 1);
+    a.prio_out = out->sampling_probabilities;
+  }
+  const bool fast = a.stack == 4 && a.obs_itemsize == 1 && (a.obs_bytes & 15) == 0;
+  if (fast) {
+    const int chunks = (int)(a.obs_bytes >> 4);
+    dim3 grid((chunks + 127) / 128, batch);
+    gather_stack4_u8_kernel<<<grid, 128, 0, stream>>>(a);
+  } else {
+    const int64_t elems = a.obs_bytes / a.obs_itemsize;
+    int gx = (int)((elems + 255) / 256);
+    if (gx > 32) gx = 32;
+    dim3 grid(gx, batch);
+    gather_generic_kernel<<<grid, 256, 0, stream>>>(a);
+  }
+  B2R_LAUNCHED();
+  return B2R_OK;
+}
+
+}  // namespace b2r
+
+using b2r::as_stream;
+using b2r::fail;
+
+extern "C" {
+
+int b2r_gather_device(b2r_buffer *b, int32_t batch, const int32_t *indices,
+                      const b2r_batch *out, b2r_stream stream) {
+  if (batch <= 0 || batch > 65535)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "batch must be in [1, 65535]");
+  B2R_TRY(b2r::flush_queue(b, as_stream(stream)));
+  return b2r::launch_gather(b, batch, indices, out, as_stream(stream));
+}
+
+int b2r_gather(b2r_buffer *b, int32_t batch, const int32_t *indices,
+               const b2r_batch *out, b2r_stream stream) {
+  if (batch <= 0 || batch > 65535)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "batch must be in [1, 65535]");
+  cudaStream_t s = as_stream(stream);
+  B2R_TRY(b2r::flush_queue(b, s));
+  // Device scratch for every requested output, 256-byte aligned segments.
+  struct Seg { void *host; size_t bytes; size_t off; };
+  Seg segs[8 + B2R_MAX_EXTRAS + 2];
+  int nseg = 0;
+  size_t total = 0;
+  auto seg = [&](void *host, size_t bytes) -> size_t {
+    segs[nseg] = {host, bytes, total};
+    total += (bytes + 255) & ~(size_t)255;
+    return segs[nseg++].off;
+  };
+  const size_t B = (size_t)batch;
+  const size_t stack_bytes = (size_t)b->cfg.obs_bytes * b->cfg.stack_size;
+  const size_t off_idx = seg(nullptr, B * 4);
+  b2r_batch d;
+  memset(&d, 0, sizeof(d));
+  size_t o_state = out->state ? seg(out->state, B * stack_bytes) : 0;
+  size_t o_action = out->action ? seg(out->action, B * b->cfg.action_bytes) : 0;
+  size_t o_reward = out->reward ? seg(out->reward, B * b->cfg.reward_itemsize) : 0;
+  size_t o_nstate = out->next_state ? seg(out->next_state, B * stack_bytes) : 0;
+  size_t o_naction = out->next_action ? seg(out->next_action, B * b->cfg.action_bytes) : 0;
+  size_t o_nreward = out->next_reward ? seg(out->next_reward, B * b->cfg.reward_itemsize) : 0;
+  size_t o_term = out->terminal ? seg(out->terminal, B * b->cfg.terminal_itemsize) : 0;
+  size_t o_ind = out->indices ? seg(out->indices, B * 4) : 0;
+  size_t o_extra[B2R_MAX_EXTRAS] = {0};
+  for (int e = 0; e < b->cfg.num_extras; ++e)
+    if (out->extras[e]) o_extra[e] = seg(out->extras[e], B * b->cfg.extra_bytes[e]);
+  size_t o_prio = out->sampling_probabilities ? seg(out->sampling_probabilities, B * 4) : 0;
+  if (total > b->out_scratch_cap) {
+    if (b->out_scratch) cudaFree(b->out_scratch);
+    b->out_scratch = nullptr;
+    b->out_scratch_cap = 0;
+    B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->out_scratch), total));
+    b->out_scratch_cap = total;
+  }
+  uint8_t *base = b->out_scratch;
+  if (out->state) d.state = base + o_state;
+  if (out->action) d.action = base + o_action;
+  if (out->reward) d.reward = base + o_reward;
+  if (out->next_state) d.next_state = base + o_nstate;
+  if (out->next_action) d.next_action = base + o_naction;
+  if (out->next_reward) d.next_reward = base + o_nreward;
+  if (out->terminal) d.terminal = base + o_term;
+  if (out->indices) d.indices = reinterpret_cast<int32_t *>(base + o_ind);
+  for (int e = 0; e < b->cfg.num_extras; ++e)
+    if (out->extras[e]) d.extras[e] = base + o_extra[e];
+  if (out->sampling_probabilities)
+    d.sampling_probabilities = reinterpret_cast<float *>(base + o_prio);
+  B2R_CUDA(cudaMemcpyAsync(base + off_idx, indices, B * 4, cudaMemcpyHostToDevice, s));
+  B2R_TRY(b2r::launch_gather(b, batch,
+                             reinterpret_cast<const int32_t *>(base + off_idx), &d, s));
+  for (int k = 1; k < nseg; ++k)
+    B2R_CUDA(cudaMemcpyAsync(segs[k].host, base + segs[k].off, segs[k].bytes,
+                             cudaMemcpyDeviceToHost, s));
+  B2R_CUDA(cudaStreamSynchronize(s));
+  return B2R_OK;
+}
+
+int b2r_sample_transition_batch_device(b2r_buffer *b, int32_t batch,
+                                       uint64_t seed, uint64_t offset,
+                                       const b2r_batch *out, b2r_stream stream) {
+  if (!out->indices)
+    return fail(B2R_ERR_INVALID_ARGUMENT,
+                "out->indices is required (the sampled indices live there)");
+  B2R_TRY(b2r_sample_indices_device(b, batch, seed, offset, out->indices, stream));
+  return b2r::launch_gather(b, batch, out->indices, out, as_stream(stream));
+}
+
+int b2r_get_priority_device(b2r_buffer *b, int64_t n, const int32_t *indices,
+                            float *out, b2r_stream stream) {
+  if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
+  if (n <= 0) return B2R_OK;
+  cudaStream_t s = as_stream(stream);
+  B2R_TRY(b2r::flush_queue(b, s));
+  b2r::get_priority_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+      b->tree->heap + (b->tree->leaves - 1), n, indices, out);
+  B2R_LAUNCHED();
+  return B2R_OK;
+}
+
+int b2r_get_priority(b2r_buffer *b, int64_t n, const int32_t *indices, float *out,
+                     b2r_stream stream) {
+  if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
+  if (n <= 0) return B2R_OK;
+  for (int64_t k = 0; k < n; ++k)
+    if (indices[k] < 0 || indices[k] >= b->tree->leaves)
+      return fail(B2R_ERR_INDEX_RANGE, "index %d is out of bounds", indices[k]);
+  cudaStream_t s = as_stream(stream);
+  B2R_TRY(b2r::flush_queue(b, s));
+  B2R_TRY(b->bounce.reserve((size_t)n * 8 + 16));
+  memcpy(b->bounce.host, indices, (size_t)n * 4);
+  B2R_CUDA(cudaMemcpyAsync(b->bounce.dev, b->bounce.host, (size_t)n * 4,
+                           cudaMemcpyHostToDevice, s));
+  float *dout = reinterpret_cast<float *>(b->bounce.dev + (size_t)n * 4);
+  b2r::get_priority_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
+      b->tree->heap + (b->tree->leaves - 1), n,
+      reinterpret_cast<const int32_t *>(b->bounce.dev), dout);
+  B2R_LAUNCHED();
+  B2R_CUDA(cudaMemcpyAsync(b->bounce.host + (size_t)n * 4, dout, (size_t)n * 4,
+                           cudaMemcpyDeviceToHost, s));
+  B2R_CUDA(cudaStreamSynchronize(s));
+  memcpy(out, b->bounce.host + (size_t)n * 4, (size_t)n * 4);
+  return B2R_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,474 @@
+// Index sampling: replaces sample_index_batch of OutOfGraphReplayBuffer
+// (circular_replay_buffer.py:436-477) and OutOfGraphPrioritizedReplayBuffer
+// (prioritized_replay_buffer.py:142-171), incl. SumTree.stratified_sample
+// (sum_tree.py:143-166).
+//
+// Both kernels are one CTA: the batch is at most a few thousand independent
+// root-to-leaf descents (20 dependent fp64 loads each at capacity 1M), and the
+// sequential parts of the reference — "the j-th invalid slot takes the j-th valid
+// retry draw", "stop after max_sample_attempts failures" — become block-wide
+// prefix scans (warp ballots + shuffles) over windows evaluated speculatively in
+// parallel.  Levels 0..10 of the tree are staged in shared memory first.
+#include "replay.cuh"
+
+namespace b2r {
+namespace {
+
+struct PerSampleArgs {
+  const double *heap;
+  int depth;
+  ValidCtx valid;
+  int batch;          // strata (global batch when sharded)
+  int max_attempts;
+  // uniforms: host-provided (reference RNG stream) or Philox (throughput mode)
+  int use_philox;
+  uint64_t seed, offset;
+  const double *strat_query01;  // [batch]  final query values in [0,1]
+  const double *retry_u01;      // [max_attempts]
+  // outputs
+  int32_t *out_idx;
+  int32_t *inv_slots;  // scratch [batch]
+  int32_t *info;       // [0] status, [1] fail slot, [2] retry draws used, [3] count
+  int64_t *latched;    // nullable: asynchronous error latch
+  // sharding (num_shards == 1: plain buffer)
+  int num_shards, rank;
+  const double *shard_totals;
+  int32_t *out_slots;  // nullable
+};
+
+__global__ void __launch_bounds__(1024) per_sample_kernel(PerSampleArgs a) {
+  __shared__ double top[2 << kTopLevels];
+  __shared__ int warp_counts[32];
+  __shared__ int s_draws_used, s_last_idx, s_last_valid;
+
+  const int top_depth = stage_top_levels(a.heap, a.depth, top);
+  const double local_total = top[0];
+  // Mass the strata are spread over: the root, or all shards' roots summed in
+  // rank order (fp64, left to right).
+  double grand_total = local_total;
+  if (a.num_shards > 1) {
+    grand_total = 0.0;
+    for (int g = 0; g < a.num_shards; ++g)
+      grand_total = __dadd_rn(grand_total, a.shard_totals[g]);
+  }
+  if (grand_total == 0.0 || (a.num_shards == 1 && local_total == 0.0)) {
+    // sum_tree.py:159-160
+    if (threadIdx.x == 0) {
+      a.info[0] = B2R_ERR_EMPTY_TREE;
+      a.info[1] = 0; a.info[2] = 0; a.info[3] = 0;
+      if (a.latched && a.latched[0] == 0) a.latched[0] = B2R_ERR_EMPTY_TREE;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+    s_draws_used = 0;
+    s_last_idx = -1;
+    s_last_valid = 0;
+  }
+
+  // ---- stratified pass (sum_tree.py:162-166 + prioritized_replay_buffer.py:155)
+  const double step = 1.0 / (double)a.batch;  // np.linspace(0, 1, batch + 1)
+  int mine_base = 0, inv_base = 0;
+  for (int tile = 0; tile < a.batch; tile += blockDim.x) {
+    const int i = tile + threadIdx.x;
+    bool mine = false, valid = true;
+    int64_t idx = 0;
+    if (i < a.batch) {
+      double q01;
+      if (a.use_philox) {
+        const double lo = __dmul_rn((double)i, step);
+        const double hi = (i + 1 == a.batch) ? 1.0 : __dmul_rn((double)(i + 1), step);
+        const double u = philox_uniform53(a.seed, a.offset, (uint64_t)i);
+        q01 = __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), u));  // random.uniform
+      } else {
+        q01 = a.strat_query01[i];
+      }
+      double mass = __dmul_rn(q01, grand_total);
+      int owner = 0;
+      for (; owner < a.num_shards - 1; ++owner) {
+        const double left = a.shard_totals[owner];
+        if (mass < left) break;
+        mass = __dsub_rn(mass, left);
+      }
+      mine = (owner == a.rank);
+      if (mine) {
+        idx = tree_descend_staged(a.heap, top, top_depth, a.depth, mass);
+        valid = is_valid_transition(a.valid, idx);
+      }
+    }
+    int tile_mine, tile_inv;
+    const int pos = mine_base + block_scan_flag(mine, warp_counts, &tile_mine);
+    const int ipos = inv_base + block_scan_flag(mine && !valid, warp_counts, &tile_inv);
+    if (mine) {
+      a.out_idx[pos] = (int32_t)idx;
+      if (a.out_slots) a.out_slots[pos] = i;
+      if (!valid) a.inv_slots[ipos] = pos;
+    }
+    mine_base += tile_mine;
+    inv_base += tile_inv;
+  }
+  const int count = mine_base;
+  const int num_invalid = inv_base;
+
+  // ---- in-order replacement of invalid slots (prioritized_replay_buffer.py:156-170)
+  int found = 0, drawn = 0;
+  const int budget = a.max_attempts;
+  __syncthreads();
+  while (num_invalid > 0 && found < num_invalid && drawn < budget) {
+    const int r = drawn + threadIdx.x;
+    const bool active = r < budget;
+    bool valid = false;
+    int64_t idx = 0;
+    if (active) {
+      const double u = a.use_philox
+                           ? philox_uniform53(a.seed, a.offset,
+                                              (uint64_t)a.batch + (uint64_t)r)
+                           : a.retry_u01[r];
+      // sum_tree.py:123-124: query = random.random() * total
+      idx = tree_descend_staged(a.heap, top, top_depth, a.depth,
+                                __dmul_rn(u, local_total));
+      valid = is_valid_transition(a.valid, idx);
+    }
+    int tile_valid;
+    const int ord = found + block_scan_flag(active && valid, warp_counts, &tile_valid);
+    if (active && valid && ord < num_invalid) {
+      __syncwarp(__activemask());
+      a.out_idx[a.inv_slots[ord]] = (int32_t)idx;
+      if (ord == num_invalid - 1) s_draws_used = r + 1;
+    }
+    if (active && r == budget - 1) {
+      s_last_idx = (int)idx;
+      s_last_valid = valid ? 1 : 0;
+    }
+    found += tile_valid;
+    drawn += blockDim.x;
+    __syncthreads();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int status = B2R_OK, fail_slot = 0, used = 0;
+    if (num_invalid > 0) {
+      if (found >= num_invalid) {
+        used = s_draws_used;
+      } else {
+        // Every one of the `budget` draws was consumed; `found` slots were fixed.
+        used = budget;
+        const int next = found;  // first invalid slot still unresolved
+        if (budget == 0 || s_last_valid) {
+          // budget already 0 when this slot is reached -> PRB:159-163
+          status = B2R_ERR_SAMPLE_ATTEMPTS;
+          fail_slot = a.inv_slots[next];
+        } else {
+          // the slot burnt the rest of the budget and keeps its last (invalid)
+          // draw; only a FURTHER invalid slot raises.
+          a.out_idx[a.inv_slots[next]] = s_last_idx;
+          if (num_invalid > next + 1) {
+            status = B2R_ERR_SAMPLE_ATTEMPTS;
+            fail_slot = a.inv_slots[next + 1];
+          }
+        }
+      }
+    }
+    a.info[0] = status;
+    a.info[1] = a.out_slots ? (status ? a.out_slots[fail_slot] : 0) : fail_slot;
+    a.info[2] = used;
+    a.info[3] = count;
+    if (status != B2R_OK && a.latched && a.latched[0] == 0) {
+      a.latched[0] = status;
+      a.latched[1] = fail_slot;
+    }
+  }
+}
+
+struct UniformSampleArgs {
+  ValidCtx valid;
+  int batch;
+  int max_attempts;
+  int use_philox;
+  uint64_t seed, offset;
+  int64_t min_id, max_id;      // Philox mode: candidates in [min_id, max_id)
+  int n_cand;                  // host mode: number of supplied candidates
+  const int64_t *candidates;   // np.random.randint(min_id, max_id) draws
+  int32_t *out_idx;
+  int32_t *counters;           // in/out: [0] accepted, [1] rejected; out: [2] draws used
+  int64_t *latched;
+};
+
+// circular_replay_buffer.py:462-470 over a window of candidate draws.
+__global__ void __launch_bounds__(1024) uniform_sample_kernel(UniformSampleArgs a) {
+  __shared__ int warp_counts[32];
+  int accepted = a.counters[0], rejected = a.counters[1], used = 0;
+  __syncthreads();
+  const int64_t span = a.max_id - a.min_id;
+  int base = 0;
+  while (accepted < a.batch && rejected < a.max_attempts &&
+         (a.use_philox || base < a.n_cand)) {
+    const int p = base + threadIdx.x;
+    const bool active = a.use_philox || p < a.n_cand;
+    bool valid = false;
+    int64_t idx = 0;
+    if (active) {
+      int64_t cand;
+      if (a.use_philox) {
+        const double u = philox_uniform53(a.seed, a.offset, (uint64_t)p);
+        int64_t off = (int64_t)(u * (double)span);
+        if (off >= span) off = span - 1;
+        cand = a.min_id + off;
+      } else {
+        cand = a.candidates[p];
+      }
+      idx = wrap_index(cand, a.valid.capacity);  // `% replay_capacity`, CRB:466
+      valid = is_valid_transition(a.valid, idx);
+    }
+    int tile_acc, tile_rej, tile_done;
+    const int acc_before = accepted + block_scan_flag(active && valid, warp_counts, &tile_acc);
+    const int rej_before = rejected + block_scan_flag(active && !valid, warp_counts, &tile_rej);
+    // A draw happens only while both loop conditions still hold (CRB:464-465).
+    const bool processed =
+        active && acc_before < a.batch && rej_before < a.max_attempts;
+    if (processed && valid) a.out_idx[acc_before] = (int32_t)idx;
+    block_scan_flag(processed, warp_counts, &tile_done);
+    int done_acc, done_rej;
+    block_scan_flag(processed && valid, warp_counts, &done_acc);
+    block_scan_flag(processed && !valid, warp_counts, &done_rej);
+    accepted += done_acc;
+    rejected += done_rej;
+    used += tile_done;
+    base += blockDim.x;
+  }
+  if (threadIdx.x == 0) {
+    a.counters[0] = accepted;
+    a.counters[1] = rejected;
+    a.counters[2] = used;
+    if (a.use_philox && accepted < a.batch && a.latched && a.latched[0] == 0) {
+      a.latched[0] = B2R_ERR_SAMPLE_ATTEMPTS;
+      a.latched[1] = accepted;
+    }
+  }
+}
+
+int uniform_bounds(const b2r_buffer *b, int64_t *lo, int64_t *hi) {
+  // circular_replay_buffer.py:449-460
+  const int64_t cap = b->cfg.capacity;
+  const int64_t cursor = b->add_count % cap;
+  if (b->add_count >= cap) {
+    *lo = cursor - cap + b->cfg.stack_size - 1;
+    *hi = cursor - b->cfg.update_horizon;
+  } else {
+    *lo = b->cfg.stack_size - 1;
+    *hi = cursor - b->cfg.update_horizon;
+    if (*hi <= *lo)
+      return fail(B2R_ERR_TOO_FEW_TRANSITIONS,
+                  "Cannot sample a batch with fewer than stack size (%d) + "
+                  "update_horizon (%d) transitions.",
+                  b->cfg.stack_size, b->cfg.update_horizon);
+  }
+  return B2R_OK;
+}
+
+int sample_threads(int n) {
+  int t = 32;
+  while (t < n && t < 1024) t <<= 1;
+  return t;
+}
+
+}  // namespace
+
+int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
+                  uint64_t offset, const double *strat_dev,
+                  const double *retry_dev, int32_t n_retry, int32_t *out_idx_dev,
+                  int32_t *info_dev, cudaStream_t stream) {
+  B2R_TRY(ensure_inv_slots(b, batch));
+  PerSampleArgs a;
+  a.heap = b->tree->heap;
+  a.depth = b->tree->depth;
+  fill_valid_ctx(b, &a.valid);
+  a.batch = batch;
+  a.max_attempts = philox ? b->cfg.max_sample_attempts : n_retry;
+  a.use_philox = philox ? 1 : 0;
+  a.seed = seed;
+  a.offset = offset;
+  a.strat_query01 = strat_dev;
+  a.retry_u01 = retry_dev;
+  a.out_idx = out_idx_dev;
+  a.inv_slots = b->inv_slots;
+  a.info = info_dev;
+  a.latched = philox ? b->status : nullptr;
+  a.num_shards = 1;
+  a.rank = 0;
+  a.shard_totals = nullptr;
+  a.out_slots = nullptr;
+  // At least 128 threads so staging the top levels is one pass of wide loads.
+  int threads = sample_threads(batch);
+  if (threads < 128) threads = 128;
+  per_sample_kernel<<<1, threads, 0, stream>>>(a);
+  B2R_LAUNCHED();
+  return B2R_OK;
+}
+
+}  // namespace b2r
+
+using b2r::as_stream;
+using b2r::fail;
+
+extern "C" {
+
+int b2r_uniform_bounds(const b2r_buffer *b, int64_t *min_id, int64_t *max_id) {
+  return b2r::uniform_bounds(b, min_id, max_id);
+}
+
+int b2r_sample_indices_uniform(b2r_buffer *b, int32_t batch, int32_t n_cand,
+                               const int64_t *candidates, int32_t *out_indices,
+                               int32_t *accepted, int32_t *rejected,
+                               int32_t *draws_used, b2r_stream stream) {
+  if (batch <= 0 || n_cand < 0)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "bad batch / candidate count");
+  cudaStream_t s = as_stream(stream);
+  B2R_TRY(b2r::flush_queue(b, s));
+  // bounce layout: [candidates n_cand*8][out batch*4][counters 16]
+  const size_t off_out = (size_t)n_cand * 8;
+  const size_t off_cnt = off_out + (((size_t)batch * 4 + 15) & ~(size_t)15);
+  B2R_TRY(b->bounce.reserve(off_cnt + 16));
+  memcpy(b->bounce.host, candidates, (size_t)n_cand * 8);
+  // Earlier windows already filled out_indices[0 .. *accepted).
+  memcpy(b->bounce.host + off_out, out_indices, (size_t)batch * 4);
+  int32_t cnt[4] = {*accepted, *rejected, 0, 0};
+  memcpy(b->bounce.host + off_cnt, cnt, 16);
+  B2R_CUDA(cudaMemcpyAsync(b->bounce.dev, b->bounce.host, off_cnt + 16,
+                           cudaMemcpyHostToDevice, s));
+  b2r::UniformSampleArgs a;
+  b2r::fill_valid_ctx(b, &a.valid);
+  a.batch = batch;
+  a.max_attempts = b->cfg.max_sample_attempts;
+  a.use_philox = 0;
+  a.seed = a.offset = 0;
+  a.min_id = a.max_id = 0;
+  a.n_cand = n_cand;
+  a.candidates = reinterpret_cast<const int64_t *>(b->bounce.dev);
+  a.out_idx = reinterpret_cast<int32_t *>(b->bounce.dev + off_out);
+  a.counters = reinterpret_cast<int32_t *>(b->bounce.dev + off_cnt);
+  a.latched = nullptr;
+  b2r::uniform_sample_kernel<<<1, b2r::sample_threads(n_cand), 0, s>>>(a);
+  B2R_LAUNCHED();
+  B2R_CUDA(cudaMemcpyAsync(b->bounce.host + off_out, b->bounce.dev + off_out,
+                           off_cnt + 16 - off_out, cudaMemcpyDeviceToHost, s));
+  B2R_CUDA(cudaStreamSynchronize(s));
+  memcpy(out_indices, b->bounce.host + off_out, (size_t)batch * 4);
+  memcpy(cnt, b->bounce.host + off_cnt, 16);
+  *accepted = cnt[0];
+  *rejected = cnt[1];
+  *draws_used = cnt[2];
+  return B2R_OK;
+}
+
+int b2r_sample_indices_prioritized(b2r_buffer *b, int32_t batch,
+                                   const double *strat_query01, int32_t n_retry,
+                                   const double *retry_u01,
+                                   int32_t *out_indices, int32_t *draws_used,
+                                   int32_t *fail_slot, b2r_stream stream) {
+  if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
+  if (batch <= 0 || n_retry < 0)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "bad batch / retry count");
+  cudaStream_t s = as_stream(stream);
+  B2R_TRY(b2r::flush_queue(b, s));
+  // bounce layout: [strat batch*8][retry n_retry*8][out batch*4][info 16]
+  const size_t off_retry = (size_t)batch * 8;
+  const size_t off_out = off_retry + (size_t)n_retry * 8;
+  const size_t off_info = off_out + (((size_t)batch * 4 + 15) & ~(size_t)15);
+  B2R_TRY(b->bounce.reserve(off_info + 16));
+  memcpy(b->bounce.host, strat_query01, (size_t)batch * 8);
+  if (n_retry) memcpy(b->bounce.host + off_retry, retry_u01, (size_t)n_retry * 8);
+  B2R_CUDA(cudaMemcpyAsync(b->bounce.dev, b->bounce.host, off_out,
+                           cudaMemcpyHostToDevice, s));
+  int32_t *dinfo = reinterpret_cast<int32_t *>(b->bounce.dev + off_info);
+  B2R_TRY(b2r::launch_sample(
+      b, batch, false, 0, 0, reinterpret_cast<const double *>(b->bounce.dev),
+      reinterpret_cast<const double *>(b->bounce.dev + off_retry), n_retry,
+      reinterpret_cast<int32_t *>(b->bounce.dev + off_out), dinfo, s));
+  B2R_CUDA(cudaMemcpyAsync(b->bounce.host + off_out, b->bounce.dev + off_out,
+                           off_info + 16 - off_out, cudaMemcpyDeviceToHost, s));
+  B2R_CUDA(cudaStreamSynchronize(s));
+  int32_t info[4];
+  memcpy(info, b->bounce.host + off_info, 16);
+  memcpy(out_indices, b->bounce.host + off_out, (size_t)batch * 4);
+  *draws_used = info[2];
+  *fail_slot = info[1];
+  if (info[0] == B2R_ERR_EMPTY_TREE)
+    return fail(B2R_ERR_EMPTY_TREE, "Cannot sample from an empty sum tree.");
+  if (info[0] == B2R_ERR_SAMPLE_ATTEMPTS)
+    return fail(B2R_ERR_SAMPLE_ATTEMPTS,
+                "Max sample attempts: Tried %d times but only sampled %d valid "
+                "indices. Batch size is %d",
+                b->cfg.max_sample_attempts, info[1], batch);
+  return B2R_OK;
+}
+
+int b2r_sample_indices_device(b2r_buffer *b, int32_t batch, uint64_t seed,
+                              uint64_t offset, int32_t *out_indices,
+                              b2r_stream stream) {
+  if (batch <= 0) return fail(B2R_ERR_INVALID_ARGUMENT, "bad batch");
+  cudaStream_t s = as_stream(stream);
+  B2R_TRY(b2r::flush_queue(b, s));
+  if (b->tree)
+    return b2r::launch_sample(b, batch, true, seed, offset, nullptr, nullptr, 0,
+                              out_indices, b->info, s);
+  b2r::UniformSampleArgs a;
+  b2r::fill_valid_ctx(b, &a.valid);
+  B2R_TRY(b2r::uniform_bounds(b, &a.min_id, &a.max_id));
+  a.batch = batch;
+  a.max_attempts = b->cfg.max_sample_attempts;
+  a.use_philox = 1;
+  a.seed = seed;
+  a.offset = offset;
+  a.n_cand = 0;
+  a.candidates = nullptr;
+  a.out_idx = out_indices;
+  a.counters = b->info;
+  a.latched = b->status;
+  B2R_CUDA(cudaMemsetAsync(b->info, 0, 16, s));
+  b2r::uniform_sample_kernel<<<1, b2r::sample_threads(batch), 0, s>>>(a);
+  B2R_LAUNCHED();
+  return B2R_OK;
+}
+
+int b2r_sample_indices_sharded_device(b2r_buffer *b, int32_t global_batch,
+                                      int32_t num_shards, int32_t rank,
+                                      const double *shard_totals,
+                                      const double *query01, int32_t n_retry,
+                                      const double *retry_u01,
+                                      int32_t *out_slots, int32_t *out_indices,
+                                      int32_t *out_count, b2r_stream stream) {
+  if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
+  if (global_batch <= 0 || num_shards <= 0 || rank < 0 || rank >= num_shards)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "bad sharding arguments");
+  cudaStream_t s = as_stream(stream);
+  B2R_TRY(b2r::flush_queue(b, s));
+  B2R_TRY(b2r::ensure_inv_slots(b, global_batch));
+  b2r::PerSampleArgs a;
+  a.heap = b->tree->heap;
+  a.depth = b->tree->depth;
+  b2r::fill_valid_ctx(b, &a.valid);
+  a.batch = global_batch;
+  a.max_attempts = n_retry;
+  a.use_philox = 0;
+  a.seed = a.offset = 0;
+  a.strat_query01 = query01;
+  a.retry_u01 = retry_u01;
+  a.out_idx = out_indices;
+  a.inv_slots = b->inv_slots;
+  a.info = b->info;
+  a.latched = b->status;
+  a.num_shards = num_shards;
+  a.rank = rank;
+  a.shard_totals = shard_totals;
+  a.out_slots = out_slots;
+  int threads = b2r::sample_threads(global_batch);
+  if (threads < 128) threads = 128;
+  b2r::per_sample_kernel<<<1, threads, 0, s>>>(a);
+  B2R_LAUNCHED();
+  if (out_count)
+    B2R_CUDA(cudaMemcpyAsync(out_count, b->info + 3, 4, cudaMemcpyDeviceToDevice, s));
+  return B2R_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,309 @@
+/*
+ * b200_replay.h — C ABI of libb200replay.so: Dopamine's replay-and-update hot path
+ * on one B200 (sm_100a).  Plain pointers and sizes only; no torch types.
+ *
+ * The reference (K-Kielak/dopamine) is pure Python and has no FFI; the entry points
+ * below are what a binding for its hot path would call.  Each one names the
+ * reference interface it replaces (paths relative to the reference root):
+ *   ST  = dopamine/replay_memory/sum_tree.py
+ *   CRB = dopamine/replay_memory/circular_replay_buffer.py
+ *   PRB = dopamine/replay_memory/prioritized_replay_buffer.py
+ *   RA  = dopamine/agents/rainbow/rainbow_agent.py
+ *
+ * Conventions
+ *   - every function returns a b2r_status; b2r_last_error() gives the text of the
+ *     last failure on the calling thread.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Work is
+ *     stream-ordered; a call synchronises the stream only when it has to hand a
+ *     result back in HOST memory (documented per function).
+ *   - "_device" variants take/return DEVICE pointers owned by the caller and never
+ *     synchronise.  The others take HOST pointers.
+ *   - handles are not thread-safe (neither is the reference: one host thread per
+ *     buffer).
+ *   - there is no CPU fallback: without a CUDA device every create call fails.
+ */
+#ifndef B200_REPLAY_H_
+#define B200_REPLAY_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2r_tree b2r_tree;     /* GPU sum tree            (ST:30)  */
+typedef struct b2r_buffer b2r_buffer; /* GPU circular replay     (CRB:80, PRB:36) */
+typedef void *b2r_stream;             /* cudaStream_t */
+
+typedef enum {
+  B2R_OK = 0,
+  B2R_ERR_INVALID_ARGUMENT = 1,
+  B2R_ERR_CUDA = 2,
+  B2R_ERR_NEGATIVE_PRIORITY = 3, /* ST:191-193 ValueError                     */
+  B2R_ERR_EMPTY_TREE = 4,        /* ST:116-117, 159-160 Exception             */
+  B2R_ERR_SAMPLE_ATTEMPTS = 5,   /* CRB:471-475 / PRB:160-163 RuntimeError    */
+  B2R_ERR_TOO_FEW_TRANSITIONS = 6, /* CRB:457-460 RuntimeError                */
+  B2R_ERR_INDEX_RANGE = 7,
+  B2R_ERR_UNSUPPORTED = 8
+} b2r_status;
+
+const char *b2r_last_error(void);
+int b2r_abi_version(void);
+/* Number of kernels this library has launched in this process (for bench.py's
+ * gpu_launches claim). */
+int64_t b2r_launch_count(void);
+
+/* ------------------------------------------------------------------------- */
+/* Sum tree — replaces sum_tree.SumTree (ST:30-205).                          */
+/* fp64 nodes, one heap array: node (level l, position i) at 2^l - 1 + i.     */
+/* ------------------------------------------------------------------------- */
+
+/* SumTree.__init__ (ST:65-89). capacity <= 0 -> B2R_ERR_INVALID_ARGUMENT. */
+int b2r_tree_create(int64_t capacity, b2r_tree **out);
+int b2r_tree_destroy(b2r_tree *tree);
+/* len(SumTree.nodes) - 1 (ST:81). */
+int b2r_tree_depth(const b2r_tree *tree);
+
+/* n x SumTree.set applied IN ARRAY ORDER (ST:178-205 as looped by PRB:213-214):
+ * duplicates chain, every ancestor receives the deltas in order, so all fp64 nodes
+ * are bit-identical to the reference's.  A negative value at position k applies
+ * elements [0,k) and returns B2R_ERR_NEGATIVE_PRIORITY (*bad_pos = k).
+ * HOST arrays; synchronises. */
+int b2r_tree_set(b2r_tree *tree, int64_t n, const int64_t *indices,
+                 const double *values, int64_t *bad_pos, b2r_stream stream);
+/* Same, DEVICE arrays (int32 indices, f32 values: what the loss kernel emits).
+ * Asynchronous; a negative value latches an error reported by b2r_tree_check. */
+int b2r_tree_set_device(b2r_tree *tree, int64_t n, const int32_t *indices,
+                        const float *values, b2r_stream stream);
+/* Returns (and clears) a latched asynchronous error. Synchronises. */
+int b2r_tree_check(b2r_tree *tree, b2r_stream stream);
+
+/* SumTree.get (ST:168-176). HOST arrays; synchronises. */
+int b2r_tree_get(b2r_tree *tree, int64_t n, const int64_t *indices, double *out,
+                 b2r_stream stream);
+/* SumTree._total_priority (ST:91-97) and .max_recorded_priority (ST:89, 194). */
+int b2r_tree_total(b2r_tree *tree, double *out, b2r_stream stream);
+int b2r_tree_max_recorded(b2r_tree *tree, double *out, b2r_stream stream);
+int b2r_tree_set_max_recorded(b2r_tree *tree, double value, b2r_stream stream);
+
+/* SumTree.sample (ST:99-141) for n explicit query values in [0,1] (the caller
+ * draws them, so the reference's RNG stream can be reproduced):
+ * out[k] = leaf reached by descending with query01[k] * root.
+ * Empty tree -> B2R_ERR_EMPTY_TREE. HOST arrays; synchronises. */
+int b2r_tree_sample(b2r_tree *tree, int64_t n, const double *query01,
+                    int64_t *out, b2r_stream stream);
+
+/* SumTree.nodes[level] (ST:79-87): 2^level doubles. HOST; synchronises. */
+int b2r_tree_read_level(b2r_tree *tree, int level, double *out,
+                        b2r_stream stream);
+int b2r_tree_write_level(b2r_tree *tree, int level, const double *in,
+                         b2r_stream stream);
+
+/* ------------------------------------------------------------------------- */
+/* Replay buffer — replaces OutOfGraphReplayBuffer (CRB:80-687) and            */
+/* OutOfGraphPrioritizedReplayBuffer (PRB:36-252).                             */
+/* ------------------------------------------------------------------------- */
+
+#define B2R_MAX_EXTRAS 8
+#define B2R_COL_OBSERVATION 0
+#define B2R_COL_ACTION 1
+#define B2R_COL_REWARD 2
+#define B2R_COL_TERMINAL 3
+#define B2R_COL_EXTRA0 4
+
+typedef struct {
+  int64_t capacity;            /* replay_capacity                    CRB:101 */
+  int32_t stack_size;          /* CRB:100                                    */
+  int32_t update_horizon;      /* CRB:103                                    */
+  double gamma;                /* CRB:104 (discounts = f32(pow(gamma,k)) CRB:181) */
+  int32_t max_sample_attempts; /* CRB:105                                    */
+  int32_t prioritized;         /* 0: CRB:80, 1: PRB:36 (owns a b2r_tree)     */
+  int64_t obs_bytes;           /* bytes of one observation                   */
+  int32_t obs_itemsize;        /* bytes of one observation element           */
+  int32_t action_bytes;        /* bytes of one action row                    */
+  int32_t reward_itemsize;     /* 4 = float32, 8 = float64 (scalar rewards)  */
+  int32_t terminal_itemsize;   /* 1/2/4/8-byte integer                       */
+  int32_t num_extras;          /* extra_storage_types               CRB:106  */
+  int32_t extra_bytes[B2R_MAX_EXTRAS]; /* bytes of one row of each extra     */
+  int32_t add_queue_rows;      /* rows staged on the host before an automatic
+                                  flush; 0 = library default                 */
+} b2r_config;
+
+int b2r_create(const b2r_config *config, b2r_buffer **out);
+int b2r_destroy(b2r_buffer *buf);
+/* The PER buffer's tree (`memory.sum_tree`, PRB:98); NULL for the uniform buffer. */
+b2r_tree *b2r_buffer_tree(b2r_buffer *buf);
+
+/* Priority argument of add(): an explicit value, or "whatever
+ * sum_tree.max_recorded_priority is when the row is applied" (RA:330-334),
+ * resolved on the device so the caller never has to read it back. */
+#define B2R_PRIORITY_EXPLICIT 0
+#define B2R_PRIORITY_MAX_RECORDED 1
+
+/* OutOfGraphReplayBuffer.add (CRB:234-260) incl. the stack_size-1 zero
+ * transitions at episode starts (CRB:255-259), and for PER the
+ * sum_tree.set(cursor, priority) that precedes each row (PRB:139-140).
+ * All pointers are HOST rows already cast to the storage dtypes.  Rows are staged
+ * in pinned memory and applied by one kernel at the next flush; every call below
+ * that reads buffer state flushes first, so the deferral is not observable. */
+int b2r_add(b2r_buffer *buf, const void *observation, const void *action,
+            const void *reward, const void *terminal,
+            const void *const *extras, double priority, int priority_mode,
+            b2r_stream stream);
+int b2r_flush(b2r_buffer *buf, b2r_stream stream);
+
+/* add_count (CRB:177), cursor() (CRB:334-336), invalid_range (CRB:53-77, 285-287). */
+int64_t b2r_add_count(const b2r_buffer *buf);
+int64_t b2r_cursor(const b2r_buffer *buf);
+int b2r_get_invalid_range(const b2r_buffer *buf, int64_t *out, int32_t *n);
+/* For load() (CRB:656-687): overwrite the bookkeeping after the stores. */
+int b2r_set_state(b2r_buffer *buf, int64_t add_count,
+                  const int64_t *invalid_range, int32_t n);
+
+/* is_valid_transition (CRB:381-414) evaluated on the device for n indices.
+ * HOST arrays; synchronises. */
+int b2r_valid_mask(b2r_buffer *buf, int64_t n, const int64_t *indices,
+                   uint8_t *out, b2r_stream stream);
+
+/* Uniform sample_index_batch (CRB:436-477).
+ * b2r_uniform_bounds: min_id/max_id of CRB:449-460 (TOO_FEW_TRANSITIONS as there).
+ * b2r_sample_indices_uniform consumes, in order, `candidates` =
+ * np.random.randint(min_id, max_id) draws made by the caller: each is reduced
+ * mod capacity, accepted if valid, otherwise counted as a failed attempt, until
+ * `batch` are accepted or max_sample_attempts failed (CRB:464-470).  The counters
+ * are in/out so a caller can feed several windows.  HOST arrays; synchronises. */
+int b2r_uniform_bounds(const b2r_buffer *buf, int64_t *min_id, int64_t *max_id);
+int b2r_sample_indices_uniform(b2r_buffer *buf, int32_t batch, int32_t n_cand,
+                               const int64_t *candidates, int32_t *out_indices,
+                               int32_t *accepted, int32_t *rejected,
+                               int32_t *draws_used, b2r_stream stream);
+
+/* Prioritized sample_index_batch (PRB:142-171) with the caller's uniforms:
+ * strat_query01[i] = random.uniform(bounds[i], bounds[i+1]) (ST:162-165);
+ * retry_u01[r] = the r-th random.random() a retry would draw (ST:123), n_retry
+ * should be max_sample_attempts.  Reproduces the shared attempt budget, the
+ * in-order replacement of invalid slots and the "last slot may stay invalid"
+ * quirk.  *draws_used = retry draws the reference would have consumed.
+ * On B2R_ERR_SAMPLE_ATTEMPTS *fail_slot is the `i` of PRB:160-163.
+ * HOST arrays; synchronises. */
+int b2r_sample_indices_prioritized(b2r_buffer *buf, int32_t batch,
+                                   const double *strat_query01, int32_t n_retry,
+                                   const double *retry_u01,
+                                   int32_t *out_indices, int32_t *draws_used,
+                                   int32_t *fail_slot, b2r_stream stream);
+
+/* Throughput mode: indices drawn on the device with Philox4x32-10 keyed by
+ * (seed, offset); same sampling rules, not stream-compatible with Python's RNG.
+ * Uniform or prioritized according to the buffer.  DEVICE output; asynchronous;
+ * attempt exhaustion latches an error reported by b2r_check. */
+int b2r_sample_indices_device(b2r_buffer *buf, int32_t batch, uint64_t seed,
+                              uint64_t offset, int32_t *out_indices,
+                              b2r_stream stream);
+int b2r_check(b2r_buffer *buf, b2r_stream stream);
+
+/* Outputs of sample_transition_batch in get_transition_elements order
+ * (CRB:571-590, PRB:246-252).  Any pointer may be NULL to skip that output. */
+typedef struct {
+  void *state;          /* (B, obs..., stack)  observation dtype */
+  void *action;         /* (B, action...)                        */
+  void *reward;         /* (B,) n-step discounted return         */
+  void *next_state;     /* (B, obs..., stack)                    */
+  void *next_action;    /* (B, action...)                        */
+  void *next_reward;    /* (B,)                                  */
+  void *terminal;       /* (B,) terminal dtype, 0/1              */
+  int32_t *indices;     /* (B,)                                  */
+  void *extras[B2R_MAX_EXTRAS];
+  float *sampling_probabilities; /* (B,) PER only: f32(leaf)  PRB:193-200 */
+} b2r_batch;
+
+/* The per-index body of sample_transition_batch (CRB:516-556): frame stacks with
+ * the stack axis innermost, n-step return cut at the first terminal, next_* taken
+ * at (i + L) mod capacity, terminal mask, indices, extras, raw leaf priorities.
+ * DEVICE pointers; asynchronous. */
+int b2r_gather_device(b2r_buffer *buf, int32_t batch, const int32_t *indices,
+                      const b2r_batch *out, b2r_stream stream);
+/* Same with HOST indices and HOST outputs (copies inside); synchronises. */
+int b2r_gather(b2r_buffer *buf, int32_t batch, const int32_t *indices,
+               const b2r_batch *out, b2r_stream stream);
+/* Device-RNG sampling + gather in one call (two launches). DEVICE; asynchronous. */
+int b2r_sample_transition_batch_device(b2r_buffer *buf, int32_t batch,
+                                       uint64_t seed, uint64_t offset,
+                                       const b2r_batch *out, b2r_stream stream);
+
+/* set_priority / get_priority (PRB:203-235) — b2r_tree_set/get on the buffer's
+ * tree after flushing pending adds. */
+int b2r_set_priority(b2r_buffer *buf, int64_t n, const int32_t *indices,
+                     const double *priorities, int64_t *bad_pos,
+                     b2r_stream stream);
+int b2r_set_priority_device(b2r_buffer *buf, int64_t n, const int32_t *indices,
+                            const float *priorities, b2r_stream stream);
+int b2r_get_priority(b2r_buffer *buf, int64_t n, const int32_t *indices,
+                     float *out, b2r_stream stream);
+int b2r_get_priority_device(b2r_buffer *buf, int64_t n, const int32_t *indices,
+                            float *out, b2r_stream stream);
+
+/* Raw access to `_store[name]` rows for save()/load() (CRB:596-687) and tests.
+ * HOST memory; synchronises. */
+int b2r_store_read(b2r_buffer *buf, int32_t column, int64_t row0, int64_t nrows,
+                   void *out, b2r_stream stream);
+int b2r_store_write(b2r_buffer *buf, int32_t column, int64_t row0,
+                    int64_t nrows, const void *in, b2r_stream stream);
+/* Device address of a column (read-only use by callers that stay on the GPU). */
+const void *b2r_store_device_ptr(b2r_buffer *buf, int32_t column);
+
+/* Sharded replay: one buffer per GPU; shard_totals[g] is
+ * rank g's root priority (device array, e.g. straight out of an NCCL all-gather).
+ * For each of the global_batch strata i (query01[i] in [0,1], DEVICE), mass =
+ * query01[i] * (sum of totals, rank order); the owner is found by the same
+ * "q < left ? left : (q -= left, right)" rule as ST:128-139 applied to the G
+ * totals in rank order, and only the owning rank descends its tree with the
+ * residual.  out_slots/out_indices receive this rank's strata (ascending i) and
+ * *out_count their number.  Invalid picks are redrawn locally from retry_u01
+ * exactly as in PRB:156-170.  DEVICE pointers; asynchronous. */
+int b2r_sample_indices_sharded_device(b2r_buffer *buf, int32_t global_batch,
+                                      int32_t num_shards, int32_t rank,
+                                      const double *shard_totals,
+                                      const double *query01, int32_t n_retry,
+                                      const double *retry_u01,
+                                      int32_t *out_slots, int32_t *out_indices,
+                                      int32_t *out_count, b2r_stream stream);
+/* Device address of the buffer's root total (input of the all-gather). */
+const double *b2r_total_device_ptr(b2r_buffer *buf);
+
+/* ------------------------------------------------------------------------- */
+/* C51 — replaces the TF graph of RA:200-305 and project_distribution          */
+/* (RA:340-494).  f32, DEVICE pointers, asynchronous.                          */
+/* ------------------------------------------------------------------------- */
+
+/* project_distribution(supports, weights, target_support) (RA:340-494):
+ * out[b,i] = sum_j clip(1 - |clip(s[b,j], z0, zN-1) - z_i| / (z1 - z0), 0, 1) * w[b,j] */
+int b2r_c51_project(int32_t batch, int32_t num_atoms, const float *supports,
+                    const float *weights, const float *target_support,
+                    float *out, b2r_stream stream);
+
+typedef struct {
+  int32_t batch, num_actions, num_atoms;
+  float cumulative_gamma;       /* f32(pow(gamma, n))               DQ:175, RA:232 */
+  const float *support;         /* (N,)                             RA:126 */
+  const float *target_logits;   /* (B, A, N) target net on next_state  RA:238-248 */
+  const float *online_logits;   /* (B, A, N) online net on state       RA:262-267 */
+  const int32_t *actions;       /* (B,)                                          */
+  const float *rewards;         /* (B,) n-step returns                 RA:221 */
+  const uint8_t *terminals;     /* (B,)                                RA:229 */
+  const float *sampling_probabilities; /* (B,) or NULL (uniform scheme) RA:278 */
+  float *target;                /* (B, N) projected target or NULL     RA:250 */
+  float *loss;                  /* (B,) cross entropy                  RA:269 */
+  float *priorities;            /* (B,) sqrt(loss + 1e-10)             RA:290 */
+  float *weights;               /* (B,) IS weights / max or NULL       RA:279-280 */
+  float *mean_weighted_loss;    /* scalar or NULL                      RA:293, 305 */
+  float *grad_logits;           /* (B, A, N) d mean(w*loss)/d online_logits or NULL */
+} b2r_c51_args;
+
+/* Bellman target + projection + softmax cross-entropy + new priorities + IS
+ * weights in one launch (RA:200-293). */
+int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_REPLAY_H_ */

@@ -1,0 +1,74 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol the
+header declares, fails loudly without a GPU, and the host-side logic that needs no
+device behaves like the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from dopamine_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+  text = open(os.path.join(ROOT, 'include', 'b200_replay.h')).read()
+  text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+  return sorted(set(re.findall(r'\b(b2r_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+  lib = _native.lib()
+  names = _declared_symbols()
+  assert len(names) >= 40
+  for name in names:
+    assert hasattr(lib, name), name
+  assert sorted(_native.SIGNATURES) == names
+  assert lib.b2r_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header():
+  # sizes the C compiler produces for the by-pointer structs
+  assert ctypes.sizeof(_native.Config) == 96
+  assert ctypes.sizeof(_native.Batch) == 8 * 8 + 8 * _native.MAX_EXTRAS + 8
+  assert ctypes.sizeof(_native.C51Args) == 16 + 13 * 8
+
+
+def test_no_cpu_fallback_without_a_device():
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip('a CUDA device is present')
+  handle = ctypes.c_void_p()
+  status = _native.lib().b2r_tree_create(16, ctypes.byref(handle))
+  assert status == _native.ERR_CUDA
+  assert 'no CPU fallback' in _native.last_error()
+  from dopamine_b200.replay_memory import sum_tree
+  with pytest.raises(_native.NativeError, match='no CPU fallback'):
+    sum_tree.SumTree(16)
+
+
+def test_argument_validation_needs_no_device():
+  from dopamine_b200.replay_memory import circular_replay_buffer as crb
+  from dopamine_b200.replay_memory import sum_tree
+  with pytest.raises(ValueError, match='Sum tree capacity should be positive'):
+    sum_tree.SumTree(-1)
+  with pytest.raises(AssertionError):
+    crb.OutOfGraphReplayBuffer(84, 4, 5, 32)
+  with pytest.raises(ValueError, match='There is not enough capacity'):
+    crb.OutOfGraphReplayBuffer((84, 84), 10, 10, 32)
+  assert list(crb.invalid_range(6, 10, 4, 1)) == [5, 6, 7, 8, 9]
+  assert list(crb.invalid_range(9, 10, 4, 1)) == [8, 9, 0, 1, 2]
+  assert list(crb.invalid_range(0, 10, 4, 1)) == [9, 0, 1, 2, 3]
+  assert list(crb.invalid_range(6, 10, 4, 3)) == [3, 4, 5, 6, 7, 8, 9]
+
+
+def test_product_never_imports_the_oracle():
+  pkg = os.path.join(ROOT, 'dopamine_b200')
+  for base, _, files in os.walk(pkg):
+    for f in files:
+      if f.endswith(('.py', '.cu', '.cuh')):
+        text = open(os.path.join(base, f)).read()
+        assert 'import oracle' not in text and 'from oracle' not in text, f
+        assert 'fast_oracle' not in text, f

@@ -1,0 +1,441 @@
+"""Parity of the CUDA path (through the C ABI) against the pinned oracle.
+
+Everything here needs a B200: run with `pytest -m gpu`.  Nothing reads
+/root/reference; the checker is `oracle/` plus the committed fixtures.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import c51_port
+from oracle import fast
+from oracle.replay_port import PortPrioritizedReplay, PortReplay
+from oracle.sumtree_port import PortSumTree
+from tests import golden_cases
+from tests import reference_kats
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def gpu():
+  import torch
+  if not torch.cuda.is_available():
+    pytest.fail('-m gpu tests need a CUDA device (no CPU fallback exists)')
+  from dopamine_b200.agents.rainbow import rainbow_agent
+  from dopamine_b200.replay_memory import circular_replay_buffer as crb
+  from dopamine_b200.replay_memory import prioritized_replay_buffer as prb
+  from dopamine_b200.replay_memory import sum_tree as st
+
+  class Mods(object):
+    pass
+
+  m = Mods()
+  m.torch, m.crb, m.prb, m.st, m.ra = torch, crb, prb, st, rainbow_agent
+  return m
+
+
+def _nodes(tree):
+  return tree.nodes
+
+
+# ---------------------------------------------------------------- sum tree ----
+def test_tree_reference_known_answers(gpu):
+  reference_kats.tree_kats(gpu.st.SumTree, _nodes)
+
+
+@pytest.mark.parametrize('cap', golden_cases.TREE_CAPS)
+def test_tree_reference_fixture(gpu, cap):
+  golden_cases.check_tree(gpu.st.SumTree, cap, _nodes)
+
+
+@pytest.mark.parametrize('cap,batch', [(1, 7), (2, 33), (100, 32), (1000, 256),
+                                       (4096, 1024), (100000, 4096),
+                                       (1 << 20, 4096), (50000, 10000)])
+def test_tree_batched_sets_bit_exact(gpu, cap, batch):
+  """Long mixed history of batched sets (duplicates, zeros) == sequential oracle."""
+  rng = np.random.RandomState(cap % 1000 + batch)
+  tree = gpu.st.SumTree(cap)
+  want = fast.FastTree(cap)
+  for rep in range(6):
+    idx = rng.randint(0, cap, size=batch).astype(np.int64)
+    if batch > 4:
+      idx[rng.randint(0, batch, size=max(2, batch // 8))] = idx[0]  # duplicates
+    val = np.sqrt(np.abs(rng.randn(batch)) + 1e-10).astype(np.float32).astype(
+        np.float64) * (10.0 ** rng.randint(-3, 3))
+    val[rng.rand(batch) < 0.05] = 0.0
+    tree.set_batch(idx, val)
+    assert want.set_seq(idx, val) == 0
+  for l, level in enumerate(tree.nodes):
+    assert np.array_equal(level.view(np.uint64), want.level(l).view(np.uint64)), (
+        'level %d differs' % l)
+  assert tree.max_recorded_priority == float(want.max_recorded[0])
+  # descent parity on the drifted tree
+  q = rng.rand(2000)
+  got = tree._descend(q)
+  assert got.tolist() == want.descend(q * want.heap[0]).tolist()
+
+
+def test_tree_negative_value_stops_the_batch(gpu):
+  tree = gpu.st.SumTree(64)
+  with pytest.raises(ValueError, match='nonnegative. Got -2.0'):
+    tree.set_batch([1, 2, 3, 4], [1.0, 3.0, -2.0, 5.0])
+  leaves = tree.nodes[-1]
+  assert leaves[1] == 1.0 and leaves[2] == 3.0 and leaves[3] == 0 and leaves[4] == 0
+  assert tree.max_recorded_priority == 3.0
+  assert tree._total_priority() == 4.0
+  tree.set(9, 2.0)  # the error latch is cleared
+  assert tree._total_priority() == 6.0
+
+
+def test_tree_device_set_matches_host_set(gpu):
+  torch = gpu.torch
+  rng = np.random.RandomState(4)
+  a, b = gpu.st.SumTree(5000), gpu.st.SumTree(5000)
+  idx = rng.randint(0, 5000, size=3000).astype(np.int32)
+  val = np.abs(rng.randn(3000)).astype(np.float32)
+  a.set_batch(idx, val)
+  from dopamine_b200 import _native
+  _native.check(_native.lib().b2r_tree_set_device(
+      b._h, 3000, torch.as_tensor(idx, device='cuda').data_ptr(),
+      torch.as_tensor(val, device='cuda').data_ptr(), _native.current_stream()))
+  for la, lb in zip(a.nodes, b.nodes):
+    assert np.array_equal(la.view(np.uint64), lb.view(np.uint64))
+
+
+# ---------------------------------------------------------- uniform buffer ----
+def test_uniform_reference_known_answers(gpu):
+  reference_kats.uniform_kats(gpu.crb.OutOfGraphReplayBuffer,
+                              gpu.crb.invalid_range, gpu.crb.ReplayElement)
+
+
+@pytest.mark.parametrize('name', golden_cases.UNIFORM_CASES)
+def test_uniform_reference_fixture(gpu, name):
+  golden_cases.check_uniform(gpu.crb.OutOfGraphReplayBuffer, name)
+
+
+@pytest.mark.parametrize('name', golden_cases.UNIFORM_CASES)
+def test_uniform_reference_fixture_device_outputs(gpu, name):
+  def make(*a, **k):
+    return gpu.crb.OutOfGraphReplayBuffer(*a, output='torch', **k)
+  golden_cases.check_uniform(make, name)
+
+
+def _fill_pair(rng, ours, port, steps, shape, prioritized, term_p=0.03):
+  for _ in range(steps):
+    row = (rng.randint(0, 256, size=shape).astype(np.uint8), rng.randint(18),
+           np.float32(np.clip(rng.randn(), -1, 1)), int(rng.rand() < term_p))
+    if prioritized:
+      p = port.sum_tree.max_recorded_priority
+      ours.add(*row, p)
+      port.add(*row, p)
+    else:
+      ours.add(*row)
+      port.add(*row)
+
+
+def test_uniform_sampling_stream_matches_port(gpu):
+  rng = np.random.RandomState(2)
+  args = ((8, 8), 4, 500, 32)
+  kw = dict(update_horizon=3, gamma=0.99, max_sample_attempts=50)
+  ours = gpu.crb.OutOfGraphReplayBuffer(*args, **kw)
+  port = PortReplay(*args, **kw)
+  for rounds in range(6):
+    _fill_pair(rng, ours, port, 173, (8, 8), False, term_p=0.2)
+    for bs in (1, 32, 300):
+      np.random.seed(rounds * 10 + bs)
+      try:
+        want = port.sample_transition_batch(bs)
+        err = None
+      except RuntimeError as e:
+        want, err = None, str(e)
+      after = np.random.randint(1 << 30)
+      np.random.seed(rounds * 10 + bs)
+      if err:
+        with pytest.raises(RuntimeError) as info:
+          ours.sample_transition_batch(bs)
+        assert str(info.value) == err
+      else:
+        got = ours.sample_transition_batch(bs)
+        for w, g in zip(want, got):
+          assert w.tobytes() == g.tobytes()
+      assert np.random.randint(1 << 30) == after
+
+
+# ------------------------------------------------------ prioritized buffer ----
+def test_prioritized_reference_known_answers(gpu):
+  reference_kats.prioritized_kats(gpu.prb.OutOfGraphPrioritizedReplayBuffer)
+
+
+@pytest.mark.parametrize('name', golden_cases.PER_CASES)
+def test_prioritized_reference_fixture(gpu, name):
+  golden_cases.check_prioritized(gpu.prb.OutOfGraphPrioritizedReplayBuffer, name,
+                                 _nodes)
+
+
+@pytest.mark.parametrize('attempts', [0, 1, 3, 1000])
+def test_prioritized_train_loop_matches_port(gpu, attempts):
+  """add / sample / set_priority interleaved like the agent does, incl. retries,
+  budget exhaustion (Q10) and duplicate indices in the write-back."""
+  rng = np.random.RandomState(attempts)
+  args = ((6, 6), 4, 300, 16)
+  kw = dict(update_horizon=3, gamma=0.99, max_sample_attempts=attempts)
+  ours = gpu.prb.OutOfGraphPrioritizedReplayBuffer(*args, **kw)
+  port = PortPrioritizedReplay(*args, **kw)
+  errors = 0
+  silent_invalid = 0
+  for step in range(160):
+    _fill_pair(rng, ours, port, 4, (6, 6), True, term_p=0.15)
+    if step < 5:
+      continue
+    random.seed(step)
+    try:
+      want_idx = port.sample_index_batch(16)
+      err = None
+    except RuntimeError as e:
+      want_idx, err = None, str(e)
+    after = random.random()
+    random.seed(step)
+    if err:
+      errors += 1
+      with pytest.raises(RuntimeError) as info:
+        ours.sample_index_batch(16)
+      assert str(info.value) == err
+    else:
+      got_idx = ours.sample_index_batch(16)
+      assert got_idx == [int(i) for i in want_idx]
+    assert random.random() == after, 'retry draws consumed differ at %d' % step
+    if err:
+      continue
+    if not all(port.is_valid_transition(i) for i in want_idx):
+      silent_invalid += 1  # Q10: the last slot kept an invalid draw
+      continue
+    want = port.sample_transition_batch(16, want_idx)
+    got = ours.sample_transition_batch(16, got_idx)
+    for w, g in zip(want, got):
+      assert w.tobytes() == g.tobytes()
+    pr = np.sqrt(np.abs(rng.randn(16)) + 1e-10).astype(np.float32)
+    port.set_priority(want[7], pr)
+    ours.set_priority(got[7], pr)
+  for lo, lp in zip(ours.sum_tree.nodes, port.sum_tree.nodes):
+    assert np.array_equal(lo.view(np.uint64), lp.view(np.uint64))
+  assert ours.sum_tree.max_recorded_priority == port.sum_tree.max_recorded_priority
+  if attempts in (0, 1):
+    assert errors > 0  # the tight budgets must actually exercise the error path
+
+
+def test_max_recorded_priority_sentinel(gpu):
+  prb = gpu.prb
+  ours = prb.OutOfGraphPrioritizedReplayBuffer((4, 4), 4, 64, 8)
+  port = PortPrioritizedReplay((4, 4), 4, 64, 8)
+  rng = np.random.RandomState(0)
+  for k in range(40):
+    row = (rng.randint(0, 256, size=(4, 4)).astype(np.uint8), 1, 0.5, k % 9 == 8)
+    port.add(*row, port.sum_tree.max_recorded_priority)
+    ours.add(*row, prb.MAX_RECORDED_PRIORITY)
+    if k % 7 == 3:
+      ids = np.array([k, max(k - 1, 0)], dtype=np.int32)
+      pr = np.array([2.0 + k, 0.25], dtype=np.float32)
+      port.set_priority(ids, pr)
+      ours.set_priority(ids, pr)
+    if k == 20:  # an explicit priority above the running max, same flush
+      port.add(*row, 99.0)
+      ours.add(*row, 99.0)
+  for lo, lp in zip(ours.sum_tree.nodes, port.sum_tree.nodes):
+    assert np.array_equal(lo.view(np.uint64), lp.view(np.uint64))
+  assert ours.sum_tree.max_recorded_priority == port.sum_tree.max_recorded_priority
+
+
+# ------------------------------------------------------------- big gathers ----
+def _stamp_fill(mem, cap, frame_bytes, rng, term_p=0.001):
+  """Fills the HBM stores directly (store_write) with stamped pseudo-random frames."""
+  pattern = rng.randint(0, 256, size=(4099, frame_bytes)).astype(np.uint8)
+  obs = np.empty((cap, frame_bytes), dtype=np.uint8)
+  for start in range(0, cap, 4099):
+    n = min(4099, cap - start)
+    obs[start:start + n] = pattern[:n]
+  obs[:, :8] = np.arange(cap, dtype=np.int64).view(np.uint8).reshape(cap, 8)
+  action = rng.randint(0, 18, size=cap).astype(np.int32)
+  reward = np.clip(rng.randn(cap), -1, 1).astype(np.float32)
+  terminal = (rng.rand(cap) < term_p).astype(np.uint8)
+  mem._store['observation'] = obs.reshape((cap,) + mem._observation_shape)
+  mem._store['action'] = action
+  mem._store['reward'] = reward
+  mem._store['terminal'] = terminal
+  return obs, action, reward, terminal
+
+
+@pytest.mark.parametrize('cap,batch,horizon', [(100000, 32, 1), (100000, 4096, 3),
+                                               (1000000, 4096, 3)])
+def test_gather_full_size_matches_c_oracle(gpu, cap, batch, horizon):
+  """BASELINE configs 1-3 at full size: Atari frames, bit-exact against the C
+  restatement, wrap-around and terminals inside the trajectory included."""
+  rng = np.random.RandomState(cap // 1000 + batch)
+  mem = gpu.crb.OutOfGraphReplayBuffer((84, 84), 4, cap, batch,
+                                       update_horizon=horizon, gamma=0.99,
+                                       output='torch')
+  obs, action, reward, terminal = _stamp_fill(mem, cap, 7056, rng, term_p=0.01)
+  mem.add_count = cap + 12345  # full and wrapped; cursor = 12345
+  idx = rng.randint(0, cap, size=batch).astype(np.int32)
+  idx[:8] = [0, 1, 2, 3, cap - 1, cap - 2, cap - 3, cap - 4]  # wrap both ways
+  got = mem.sample_transition_batch(batch, indices=idx.tolist())
+  want = fast.gather_u8(cap, 7056, 4, horizon, mem._cumulative_discount_vector,
+                        obs, action, reward, terminal, idx)
+  names = ['state', 'action', 'reward', 'next_state', 'next_action',
+           'next_reward', 'terminal', 'indices']
+  for nm, w, g in zip(names, want, got):
+    g = g.cpu().numpy().reshape(w.shape)
+    assert w.tobytes() == g.tobytes(), nm
+  assert want[6].any() and not want[6].all()  # both kinds of trajectories seen
+
+
+def test_validity_mask_full_size(gpu):
+  cap = 100000
+  rng = np.random.RandomState(1)
+  mem = gpu.crb.OutOfGraphReplayBuffer((84, 84), 4, cap, 32, update_horizon=3)
+  _, _, _, terminal = _stamp_fill(mem, cap, 7056, rng, term_p=0.01)
+  for add_count in (cap + 777, 5000, cap, 2 * cap - 1):
+    mem.add_count = add_count
+    cursor = add_count % cap
+    inv = [(cursor - 3 + i) % cap for i in range(7)]
+    mem.invalid_range = inv
+    probe = np.concatenate([rng.randint(-5, cap + 5, size=3000),
+                            np.array(inv), np.arange(cursor - 10, cursor + 10)])
+    from dopamine_b200 import _native
+    out = np.zeros(len(probe), dtype=np.uint8)
+    p64 = np.ascontiguousarray(probe, dtype=np.int64)
+    _native.check(_native.lib().b2r_valid_mask(
+        mem._h, len(p64), _native.ptr(p64), _native.ptr(out),
+        _native.current_stream()))
+    want = [fast.is_valid(int(i), cap, add_count, 4, 3, np.array(inv), terminal)
+            for i in probe]
+    assert out.astype(bool).tolist() == want
+
+
+def test_prioritized_full_size_step_matches_oracles(gpu):
+  """Config 2/3 shape: capacity 1M tree + sampling + gather + write-back, checked
+  against the C tree/gather restatement with the same injected uniforms."""
+  cap, batch = 1000000, 1024
+  rng = np.random.RandomState(7)
+  mem = gpu.prb.OutOfGraphPrioritizedReplayBuffer(
+      (84, 84), 4, cap, batch, update_horizon=3, gamma=0.99, output='torch')
+  obs, action, reward, terminal = _stamp_fill(mem, cap, 7056, rng)
+  add_count = cap + 4242
+  mem.add_count = add_count
+  inv = np.array([(4242 - 3 + i) % cap for i in range(7)])
+  mem.invalid_range = inv
+  want_tree = fast.FastTree(cap)
+  for lo in range(0, cap, 50000):  # non-uniform priorities over the whole ring
+    ids = np.arange(lo, lo + 50000, dtype=np.int32)
+    pr = np.sqrt(np.abs(rng.randn(50000)) + 1e-10).astype(np.float32)
+    mem.set_priority(ids, pr)
+    want_tree.set_seq(ids, pr.astype(np.float64))
+  # make sure retries happen: a run of high-priority slots right at the cursor
+  hot = np.array(inv[:4], dtype=np.int32)
+  mem.set_priority(hot, np.full(4, 3000.0, dtype=np.float32))
+  want_tree.set_seq(hot, np.full(4, 3000.0))
+  retried = 0
+  for step in range(3):
+    random.seed(step)
+    got = mem.sample_transition_batch()
+    ours_next = random.random()
+    random.seed(step)
+    bounds = np.linspace(0., 1., batch + 1)
+    q = np.array([random.uniform(bounds[i], bounds[i + 1]) for i in range(batch)])
+    picks = want_tree.descend(q * want_tree.heap[0])
+    fixed = []
+    for i in picks:
+      while not fast.is_valid(int(i), cap, add_count, 4, 3, inv, terminal):
+        retried += 1
+        i = int(want_tree.descend(np.array([random.random()]) *
+                                  want_tree.heap[0])[0])
+      fixed.append(int(i))
+    assert ours_next == random.random(), 'retry draws consumed differ'
+    idx = got[7].cpu().numpy()
+    assert idx.tolist() == fixed
+    want = fast.gather_u8(cap, 7056, 4, 3, mem._cumulative_discount_vector, obs,
+                          action, reward, terminal, idx)
+    for w, g in zip(want, got[:8]):
+      assert w.tobytes() == g.cpu().numpy().reshape(w.shape).tobytes()
+    leaves = want_tree.level(want_tree.depth)
+    assert got[8].cpu().numpy().tobytes() == leaves[idx].astype(np.float32).tobytes()
+    pr = np.sqrt(np.abs(rng.randn(batch)) + 1e-10).astype(np.float32)
+    mem.set_priority(got[7], gpu.torch.as_tensor(pr, device='cuda'))
+    want_tree.set_seq(idx, pr.astype(np.float64))
+  assert retried > 0
+  for l, level in enumerate(mem.sum_tree.nodes):
+    assert np.array_equal(level.view(np.uint64), want_tree.level(l).view(np.uint64))
+
+
+# ------------------------------------------------------------------- C51 ----
+def test_projection_reference_known_answers(gpu):
+  reference_kats.projection_kats(gpu.ra.project_distribution)
+
+
+def test_projection_shape_errors(gpu):
+  pd = gpu.ra.project_distribution
+  s = np.array([[0, 2, 4, 6, 8], [3, 4, 5, 6, 7]], np.float32)
+  w4 = np.array([[0.1, 0.2, 0.3, 0.2]] * 2, np.float32)
+  w5 = np.array([[0.1, 0.2, 0.3, 0.2, 0.2]] * 2, np.float32)
+  with pytest.raises(ValueError, match='are incompatible'):
+    pd(s, w4, np.array([4, 5, 6, 7, 8], np.float32))
+  with pytest.raises(ValueError, match='are incompatible'):
+    pd(s, w5, np.array([4, 5, 6], np.float32))
+  with pytest.raises(ValueError, match='Index out of range'):
+    pd(s, w5, np.float32(3))
+  with pytest.raises(ValueError, match='out of bounds'):
+    pd(s, w5, np.array([[3]], np.float32))
+  with pytest.raises(ValueError, match='assertion failed'):
+    pd(s, w5, np.array([8, 7, 6, 5, 4], np.float32), validate_args=True)
+  with pytest.raises(ValueError, match='assertion failed'):
+    pd(s, w5, np.array([3, 4, 6, 7, 8], np.float32), validate_args=True)
+
+
+@pytest.mark.parametrize('batch,actions,atoms', [(32, 18, 51), (256, 4, 51),
+                                                 (1024, 18, 51), (7, 3, 5),
+                                                 (4096, 18, 51), (33, 6, 101)])
+def test_c51_loss_matches_numpy_restatement(gpu, batch, actions, atoms):
+  """Projection, loss, new priorities and IS weights within 1e-6 relative of the
+  f32 numpy restatement (north_star tolerance; TF's own assertAllClose default)."""
+  torch = gpu.torch
+  rng = np.random.RandomState(7)
+  online = rng.randn(batch, actions, atoms).astype(np.float32)
+  target = rng.randn(batch, actions, atoms).astype(np.float32)
+  act = rng.randint(0, actions, size=batch).astype(np.int32)
+  rew = np.clip(rng.randn(batch), -1, 1).astype(np.float32)
+  term = (rng.rand(batch) < 0.2).astype(np.uint8)
+  probs = np.sqrt(np.abs(rng.randn(batch)) + 1e-10).astype(np.float32)
+  want = c51_port.rainbow_update(rew, term, act, probs, online, target,
+                                 vmax=10., num_atoms=atoms, gamma=0.99,
+                                 update_horizon=3)
+  support = gpu.ra.make_support(10., atoms)
+  assert support.cpu().numpy().tobytes() == want['support'].tobytes()
+  dev = lambda x: torch.as_tensor(x, device='cuda')
+  got = gpu.ra.c51_loss(dev(online), dev(target), dev(act), dev(rew), dev(term),
+                        dev(probs), support, 0.99 ** 3, want_target=True,
+                        want_grad=True)
+  tol = dict(rtol=1e-6, atol=1e-6)
+  np.testing.assert_allclose(got['target'].cpu().numpy(), want['target'], **tol)
+  np.testing.assert_allclose(got['loss'].cpu().numpy(), want['loss'], rtol=2e-6,
+                             atol=1e-6)
+  np.testing.assert_allclose(got['priorities'].cpu().numpy(),
+                             want['priorities'], rtol=2e-6, atol=1e-6)
+  np.testing.assert_allclose(got['weights'].cpu().numpy(), want['weights'], **tol)
+  np.testing.assert_allclose(float(got['mean_weighted_loss']),
+                             want['weighted_loss'].mean(), rtol=1e-5)
+  # gradient of mean(w * ce) w.r.t. the online logits, against torch autograd
+  x = torch.tensor(online, device='cuda', dtype=torch.float64, requires_grad=True)
+  t = torch.tensor(want['target'], device='cuda', dtype=torch.float64)
+  w = torch.tensor(want['weights'], device='cuda', dtype=torch.float64)
+  chosen = x[torch.arange(batch), torch.as_tensor(act, device='cuda').long()]
+  ce = -(t * torch.log_softmax(chosen, dim=1)).sum(1)
+  (w * ce).mean().backward()
+  np.testing.assert_allclose(got['grad_logits'].cpu().numpy(),
+                             x.grad.cpu().numpy(), rtol=1e-4, atol=1e-7)
+  # uniform scheme: weights are all ones
+  uni = gpu.ra.c51_loss(dev(online), dev(target), dev(act), dev(rew), dev(term),
+                        None, support, 0.99 ** 3)
+  assert (uni['weights'].cpu().numpy() == 1.0).all()
+  np.testing.assert_allclose(uni['loss'].cpu().numpy(), want['loss'], rtol=2e-6,
+                             atol=1e-6)
