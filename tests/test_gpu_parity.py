@@ -97,9 +97,10 @@ def test_tree_device_set_matches_host_set(gpu):
   val = np.abs(rng.randn(3000)).astype(np.float32)
   a.set_batch(idx, val)
   from dopamine_b200 import _native
+  d_idx = torch.as_tensor(idx, device='cuda')  # keep alive across the launch
+  d_val = torch.as_tensor(val, device='cuda')
   _native.check(_native.lib().b2r_tree_set_device(
-      b._h, 3000, torch.as_tensor(idx, device='cuda').data_ptr(),
-      torch.as_tensor(val, device='cuda').data_ptr(), _native.current_stream()))
+      b._h, 3000, d_idx.data_ptr(), d_val.data_ptr(), _native.current_stream()))
   for la, lb in zip(a.nodes, b.nodes):
     assert np.array_equal(la.view(np.uint64), lb.view(np.uint64))
 
