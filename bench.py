@@ -1,0 +1,569 @@
+"""Benchmark of the replay-and-update hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of the hot path over one batch: prioritized stratified sample
+-> fused frame-stack / n-step gather -> fused C51 target + cross-entropy + new
+priorities -> batched priority write-back, on synthetic Atari-shaped transitions
+(SURVEY.md section 8d).  Workload at N=1: BASELINE.json configs[1] — prioritized
+replay capacity 1M, update_horizon 3, gamma 0.99, batch 32, 51 atoms, 18 actions.
+With N>1 (torchrun) every rank owns a 1M shard and the global batch is 32*N
+(weak scaling); the only collective is the all-gather of shard totals.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU
+algorithm (oracle port, Python) on the host cores for the same workload.
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+FRAME = 84 * 84
+NUM_ACTIONS = 18
+NUM_ATOMS = 51
+VMAX = 10.0
+GAMMA = 0.99
+HORIZON = 3
+STACK = 4
+METRIC = ('sampled transitions/sec (PER sample+gather+C51 target+priority '
+          'update)')
+UNIT = 'transitions/s'
+
+
+def parse_args():
+  p = argparse.ArgumentParser()
+  p.add_argument('--gpus', type=int, default=1)
+  p.add_argument('--steps', type=int, default=2000)
+  p.add_argument('--warmup', type=int, default=50)
+  p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  p.add_argument('--batch', type=int, default=32)
+  p.add_argument('--capacity', type=int, default=1000000)
+  p.add_argument('--no-graph', action='store_true',
+                 help='launch eagerly instead of replaying a CUDA graph')
+  p.add_argument('--no-sweep', action='store_true')
+  p.add_argument('--no-cpu-baseline', action='store_true')
+  p.add_argument('--no-e2e', action='store_true')
+  return p.parse_args()
+
+
+def workload_name(batch, capacity, n_gpus):
+  name = ('Rainbow prioritized replay capacity {}, update_horizon 3, gamma 0.99, '
+          'batch {}, 51-atom C51 projection'.format(capacity, batch))
+  if n_gpus > 1:
+    name += ', {} shards (one per GPU), global batch {}'.format(
+        n_gpus, batch * n_gpus)
+  return name
+
+
+# --------------------------------------------------------------------------- #
+# clocks sampling (B200_PROFILING.md)
+# --------------------------------------------------------------------------- #
+class ClockSampler(object):
+
+  def __init__(self, index):
+    self.index = index
+    self.rows = []
+    self._stop = threading.Event()
+    self._thread = threading.Thread(target=self._run, daemon=True)
+
+  def _run(self):
+    q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+    while not self._stop.is_set():
+      try:
+        out = subprocess.run(
+            ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+             '--format=csv,noheader,nounits'], capture_output=True, text=True,
+            timeout=5).stdout.strip()
+        if out:
+          self.rows.append([x.strip() for x in out.split(',')])
+      except Exception:  # pylint: disable=broad-except
+        pass
+      self._stop.wait(0.2)
+
+  def __enter__(self):
+    self._thread.start()
+    return self
+
+  def __exit__(self, *exc):
+    self._stop.set()
+    self._thread.join(timeout=6)
+
+  def summary(self):
+    sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+    mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+             'sw_power_cap']
+    reasons = []
+    for k, name in enumerate(names):
+      if any(len(r) > 2 + k and r[2 + k].lower().startswith('active')
+             for r in self.rows):
+        reasons.append(name)
+    return {'sm_mhz': sm[len(sm) // 2] if sm else None,
+            'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+            'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------- #
+# our arm
+# --------------------------------------------------------------------------- #
+class GpuWorkload(object):
+  """Capacity-`capacity` prioritized buffer filled with synthetic transitions on
+  the device, plus resident network outputs for the C51 step."""
+
+  def __init__(self, capacity, max_batch, rank, seed=1234):
+    import torch
+    from dopamine_b200 import _native
+    from dopamine_b200.agents.rainbow import rainbow_agent
+    from dopamine_b200.replay_memory import prioritized_replay_buffer as prb
+    self.torch, self.native, self.ra = torch, _native, rainbow_agent
+    self.lib = _native.lib()
+    self.capacity = capacity
+    self.mem = prb.OutOfGraphPrioritizedReplayBuffer(
+        (84, 84), STACK, capacity, 32, update_horizon=HORIZON, gamma=GAMMA,
+        output='numpy', rng='device', seed=seed + rank)
+    self.h = self.mem._h  # pylint: disable=protected-access
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(seed + rank)
+    stream = _native.current_stream()
+    chunk = 65536
+    terminal_host = np.zeros(capacity, dtype=np.uint8)
+    for lo in range(0, capacity, chunk):
+      n = min(chunk, capacity - lo)
+      frames = torch.randint(0, 256, (n, FRAME), dtype=torch.uint8,
+                             device='cuda', generator=gen)
+      actions = torch.randint(0, NUM_ACTIONS, (n,), dtype=torch.int32,
+                              device='cuda', generator=gen)
+      rewards = torch.randn(n, device='cuda', generator=gen).clamp_(-1, 1)
+      terms = (torch.rand(n, device='cuda', generator=gen) < 1e-3).to(
+          torch.uint8)
+      for col, t in ((0, frames), (1, actions), (2, rewards), (3, terms)):
+        _native.check(self.lib.b2r_store_write(self.h, col, lo, n, t.data_ptr(),
+                                               stream))
+      terminal_host[lo:lo + n] = terms.cpu().numpy()
+    self.terminal_host = terminal_host
+    add_count = capacity + 500  # full and wrapped
+    self.mem.add_count = add_count
+    cursor = add_count % capacity
+    self.mem.invalid_range = [(cursor - HORIZON + i) % capacity
+                              for i in range(STACK + HORIZON)]
+    for lo in range(0, capacity, chunk):  # non-uniform priorities
+      n = min(chunk, capacity - lo)
+      idx = torch.arange(lo, lo + n, dtype=torch.int32, device='cuda')
+      pr = (torch.randn(n, device='cuda', generator=gen).abs() + 1e-10).sqrt()
+      self.mem.set_priority(idx, pr)
+    torch.cuda.synchronize()
+    _native.check(self.lib.b2r_check(self.h, stream))
+    gen.manual_seed(7)
+    self.online = torch.randn(max_batch, NUM_ACTIONS, NUM_ATOMS, device='cuda',
+                              generator=gen)
+    self.target = torch.randn(max_batch, NUM_ACTIONS, NUM_ATOMS, device='cuda',
+                              generator=gen)
+    self.support = rainbow_agent.make_support(VMAX, NUM_ATOMS)
+    self.gamma_n = float(np.float32(math.pow(GAMMA, HORIZON)))
+    self.seed = seed + rank
+    self._plans = {}
+
+  def plan(self, batch):
+    """Preallocated outputs + argument structs for a batch size (reused across
+    steps, like the reference's optional output reuse for benchmarks)."""
+    if batch in self._plans:
+      return self._plans[batch]
+    torch, nat = self.torch, self.native
+    t = {
+        'state': torch.empty(batch, 84, 84, STACK, dtype=torch.uint8, device='cuda'),
+        'action': torch.empty(batch, dtype=torch.int32, device='cuda'),
+        'reward': torch.empty(batch, dtype=torch.float32, device='cuda'),
+        'next_state': torch.empty(batch, 84, 84, STACK, dtype=torch.uint8, device='cuda'),
+        'next_action': torch.empty(batch, dtype=torch.int32, device='cuda'),
+        'next_reward': torch.empty(batch, dtype=torch.float32, device='cuda'),
+        'terminal': torch.empty(batch, dtype=torch.uint8, device='cuda'),
+        'indices': torch.empty(batch, dtype=torch.int32, device='cuda'),
+        'sampling_probabilities': torch.empty(batch, dtype=torch.float32, device='cuda'),
+        'loss': torch.empty(batch, dtype=torch.float32, device='cuda'),
+        'priorities': torch.empty(batch, dtype=torch.float32, device='cuda'),
+        'weights': torch.empty(batch, dtype=torch.float32, device='cuda'),
+        'mean': torch.empty((), dtype=torch.float32, device='cuda'),
+    }
+    b = nat.Batch()
+    for name in ('state', 'action', 'reward', 'next_state', 'next_action',
+                 'next_reward', 'terminal', 'indices', 'sampling_probabilities'):
+      setattr(b, name, t[name].data_ptr())
+    c = nat.C51Args()
+    c.batch, c.num_actions, c.num_atoms = batch, NUM_ACTIONS, NUM_ATOMS
+    c.cumulative_gamma = self.gamma_n
+    c.support = self.support.data_ptr()
+    c.target_logits = self.target.data_ptr()
+    c.online_logits = self.online.data_ptr()
+    c.actions = t['action'].data_ptr()
+    c.rewards = t['reward'].data_ptr()
+    c.terminals = t['terminal'].data_ptr()
+    c.sampling_probabilities = t['sampling_probabilities'].data_ptr()
+    c.target = None
+    c.loss = t['loss'].data_ptr()
+    c.priorities = t['priorities'].data_ptr()
+    c.weights = t['weights'].data_ptr()
+    c.mean_weighted_loss = t['mean'].data_ptr()
+    c.grad_logits = None
+    self._plans[batch] = (t, b, c)
+    return self._plans[batch]
+
+  def step(self, batch):
+    """sample -> gather -> C51 loss/priorities -> write-back, all in HBM."""
+    t, b, c = self.plan(batch)
+    nat, lib = self.native, self.lib
+    stream = nat.current_stream()
+    nat.check(lib.b2r_sample_transition_batch_device(
+        self.h, batch, self.seed, 0, ctypes.byref(b), stream))
+    nat.check(lib.b2r_c51_loss(ctypes.byref(c), stream))
+    nat.check(lib.b2r_set_priority_device(
+        self.h, batch, t['indices'].data_ptr(), t['priorities'].data_ptr(),
+        stream))
+
+  def gather_only(self, batch, idx_tensor):
+    _, b, _ = self.plan(batch)
+    self.native.check(self.lib.b2r_gather_device(
+        self.h, batch, idx_tensor.data_ptr(), ctypes.byref(b),
+        self.native.current_stream()))
+
+  def algorithmic_bytes(self, idx_host):
+    """unique frames read once + outputs written once, per index."""
+    cap = self.capacity
+    total = 0
+    for i in idx_host:
+      length = HORIZON
+      for k in range(HORIZON):
+        if self.terminal_host[(int(i) + k) % cap]:
+          length = k + 1
+          break
+      frames_read = STACK + min(length, STACK)
+      total += FRAME * (frames_read + 2 * STACK)
+      total += 64 + 25  # scalar columns in, scalar outputs
+    return total
+
+
+def time_graph_or_eager(torch, fn, steps, warmup, use_graph, dist=None):
+  """Times `steps` calls of fn with CUDA events on the launching stream."""
+  side = torch.cuda.Stream()
+  side.wait_stream(torch.cuda.current_stream())
+  with torch.cuda.stream(side):
+    for _ in range(max(3, warmup)):
+      fn()
+    side.synchronize()
+    runner = fn
+    if use_graph:
+      graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(graph, stream=side):
+        fn()
+      runner = graph.replay
+      for _ in range(3):
+        runner()
+      side.synchronize()
+    if dist is not None:
+      dist.barrier()
+    torch.cuda.synchronize()
+    start = torch.cuda.Event(enable_timing=True)
+    end = torch.cuda.Event(enable_timing=True)
+    start.record(side)
+    for _ in range(steps):
+      runner()
+    end.record(side)
+    end.synchronize()
+    torch.cuda.synchronize()
+    if dist is not None:
+      dist.barrier()
+    ms = start.elapsed_time(end)
+  torch.cuda.current_stream().wait_stream(side)
+  return ms
+
+
+def measure_gather_roofline(torch, wl, batch, peak_gbs, launches=200):
+  """Average duration of the gather kernel alone over pre-sampled index batches
+  (distinct every launch: the 7 GB ring defeats L2) -> achieved algorithmic GB/s."""
+  nat = wl.native
+  nbuf = 20
+  idx_bufs = []
+  for k in range(nbuf):
+    idx = torch.empty(batch, dtype=torch.int32, device='cuda')
+    nat.check(wl.lib.b2r_sample_indices_device(
+        wl.h, batch, wl.seed, 1000 + k, idx.data_ptr(), nat.current_stream()))
+    idx_bufs.append(idx)
+  torch.cuda.synchronize()
+  bytes_per_launch = np.mean(
+      [wl.algorithmic_bytes(i.cpu().numpy()) for i in idx_bufs])
+
+  def body():
+    for idx in idx_bufs:
+      wl.gather_only(batch, idx)
+
+  reps = max(1, launches // nbuf)
+  ms = time_graph_or_eager(torch, body, reps, 3, True)
+  sec_per_launch = ms * 1e-3 / (reps * nbuf)
+  achieved = bytes_per_launch / sec_per_launch / 1e9
+  return {
+      'bound': 'hbm', 'kernel': 'gather_stack4_u8_kernel',
+      'achieved': round(achieved, 1), 'peak': peak_gbs, 'unit': 'GB/s',
+      'frac': round(achieved / peak_gbs, 4), 'traffic': None,
+      'us_per_launch': round(sec_per_launch * 1e6, 3),
+      'algorithmic_bytes_per_launch': int(bytes_per_launch),
+      'peak_source': 'MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)',
+  }
+
+
+def measure_e2e(torch, wl, batch, steps):
+  """Same step through the reference-facing API with HOST buffers: numpy batch
+  out (D2H), logits in from pinned host memory (H2D), priorities back (D2H),
+  host-array set_priority."""
+  mem, ra = wl.mem, wl.ra
+  online_h = wl.online[:batch].cpu().pin_memory()
+  target_h = wl.target[:batch].cpu().pin_memory()
+  online_d = torch.empty_like(wl.online[:batch])
+  target_d = torch.empty_like(wl.target[:batch])
+
+  def one():
+    batch_np = mem.sample_transition_batch(batch)  # host numpy tuple
+    online_d.copy_(online_h, non_blocking=True)
+    target_d.copy_(target_h, non_blocking=True)
+    dev = lambda a: torch.as_tensor(a).cuda(non_blocking=True)
+    out = ra.c51_loss(online_d, target_d, dev(batch_np[1]), dev(batch_np[2]),
+                      dev(batch_np[6]), dev(batch_np[8]), wl.support, wl.gamma_n)
+    prio = out['priorities'].cpu().numpy()
+    mem.set_priority(batch_np[7], prio)
+    return batch_np
+
+  for _ in range(5):
+    sample = one()
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    one()
+  torch.cuda.synchronize()
+  dt = time.perf_counter() - t0
+  d2h = sum(a.nbytes for a in sample) + batch * 4
+  h2d = (online_h.numel() + target_h.numel()) * 4 + batch * (4 + 4 + 1 + 4 + 4 + 8)
+  return {'value': round(batch * steps / dt, 1), 'unit': UNIT,
+          'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+          'ms_per_step': round(dt * 1e3 / steps, 4), 'steps': steps}
+
+
+# --------------------------------------------------------------------------- #
+# CPU arm: the oracle port (the reference's algorithm, Python/numpy)
+# --------------------------------------------------------------------------- #
+def build_cpu_port(capacity, batch, seed=1234):
+  from oracle.replay_port import PortPrioritizedReplay
+  rng = np.random.RandomState(seed)
+  port = PortPrioritizedReplay((84, 84), STACK, capacity, batch,
+                               update_horizon=HORIZON, gamma=GAMMA)
+  pattern = rng.randint(0, 256, size=(4096, 84, 84)).astype(np.uint8)
+  obs = port.store['observation']
+  for lo in range(0, capacity, 4096):
+    n = min(4096, capacity - lo)
+    obs[lo:lo + n] = pattern[:n]
+  port.store['action'][:] = rng.randint(0, NUM_ACTIONS, size=capacity)
+  port.store['reward'][:] = np.clip(rng.randn(capacity), -1, 1)
+  port.store['terminal'][:] = rng.rand(capacity) < 1e-3
+  port.add_count = np.array(capacity + 500)
+  from oracle.replay_port import cursor_window
+  port.invalid_range = cursor_window(500, capacity, STACK, HORIZON)
+  # tree: leaves = priorities, parents = child sums (timing only needs the shape)
+  tree = port.sum_tree
+  leaves = np.zeros(1 << tree.depth)
+  leaves[:capacity] = np.sqrt(np.abs(rng.randn(capacity)) + 1e-10).astype(
+      np.float32)
+  level = leaves
+  for l in range(tree.depth, -1, -1):
+    tree.level(l)[:] = level
+    level = level.reshape(-1, 2).sum(axis=1) if l else level
+  tree.max_recorded_priority = float(leaves.max())
+  return port
+
+
+def cpu_steps(port, batch, budget_s, max_steps, seed=7):
+  from oracle import c51_port
+  rng = np.random.RandomState(seed)
+  online = rng.randn(batch, NUM_ACTIONS, NUM_ATOMS).astype(np.float32)
+  target = rng.randn(batch, NUM_ACTIONS, NUM_ATOMS).astype(np.float32)
+  random.seed(0)
+  done = 0
+  t0 = time.perf_counter()
+  while done < max_steps and (time.perf_counter() - t0 < budget_s or done < 3):
+    b = port.sample_transition_batch(batch)
+    out = c51_port.rainbow_update(b[2], b[6], b[1], b[8], online, target,
+                                  vmax=VMAX, num_atoms=NUM_ATOMS, gamma=GAMMA,
+                                  update_horizon=HORIZON)
+    port.set_priority(b[7], out['priorities'])
+    done += 1
+  return done, time.perf_counter() - t0
+
+
+def cpu_baseline(batch, capacity, budget_s=12.0):
+  port = build_cpu_port(capacity, batch)
+  cpu_steps(port, batch, 0.0, 3)  # warm-up
+  steps, dt = cpu_steps(port, batch, budget_s, 100000)
+  return {
+      'value': round(batch * steps / dt, 1), 'unit': UNIT, 'cores': 1,
+      'kind': 'port',
+      'sample': '{} steps of batch {} in {:.1f} s, capacity {} (oracle port of the '
+                'reference: Python/numpy, single thread as the reference is)'
+                .format(steps, batch, dt, capacity),
+  }
+
+
+def _replica(args):
+  batch, capacity, budget_s, seed = args
+  port = build_cpu_port(capacity, batch, seed=seed)
+  cpu_steps(port, batch, 0.0, 2)
+  steps, dt = cpu_steps(port, batch, budget_s, 100000, seed=seed)
+  return steps, dt
+
+
+def run_reference(args):
+  """--impl reference: the reference's CPU implementation of the path (oracle
+  port; the reference itself is TF-1.x Python and cannot travel) on all host
+  cores, as independent single-threaded replicas (it has no threading)."""
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  import multiprocessing as mp
+  cores = os.cpu_count() or 1
+  replicas = max(1, min(cores, 16))
+  per_cap = max(65536, args.capacity // replicas)
+  budget = 10.0
+  t0 = time.perf_counter()
+  with mp.get_context('fork').Pool(replicas) as pool:
+    res = pool.map(_replica, [(args.batch, per_cap, budget, 100 + r)
+                              for r in range(replicas)])
+  wall = time.perf_counter() - t0
+  rate = sum(args.batch * s / dt for s, dt in res)
+  steps_total = sum(s for s, _ in res)
+  line = {
+      'impl': 'reference', 'metric': METRIC, 'value': round(rate, 1),
+      'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+      'warmup': args.warmup,
+      'ms_per_step': round(1e3 * args.batch / rate, 4),
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+      'dtype': 'u8', 'data': 'synthetic',
+      'config': {'workload': workload_name(args.batch, args.capacity, 1)},
+      'cpu_baseline': {
+          'value': round(rate, 1), 'unit': UNIT, 'cores': replicas,
+          'kind': 'port',
+          'sample': '{} replica processes x ~{:.0f} s, {} steps of batch {} in '
+                    'total, capacity {} each (wall {:.0f} s)'.format(
+                        replicas, budget, steps_total, args.batch, per_cap, wall),
+      },
+      'e2e': {'value': round(rate, 1), 'unit': UNIT, 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+  }
+  print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- #
+def main():
+  args = parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+    return
+  import torch
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a CUDA device: there is no CPU fallback')
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local_rank)
+  dist = None
+  if world > 1:
+    import torch.distributed as dist_mod
+    dist_mod.init_process_group('nccl')
+    dist = dist_mod
+  from dopamine_b200 import _native
+  peaks = {}
+  try:
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+  except Exception:  # pylint: disable=broad-except
+    pass
+  peak_gbs = float(peaks.get('hbm_gbs', 6650.0))
+
+  sweep_batches = [] if args.no_sweep else [256, 1024, 4096]
+  wl = GpuWorkload(args.capacity, max([args.batch] + sweep_batches), rank)
+  launches_before = _native.lib().b2r_launch_count()
+  wl.step(args.batch)
+  launches_per_step = _native.lib().b2r_launch_count() - launches_before
+  torch.cuda.synchronize()
+
+  if world > 1:
+    from dopamine_b200.replay_memory import sharded_replay
+    sharded = sharded_replay.ShardedStep(wl, args.batch * world, world, rank, dist)
+    step_fn = sharded.step
+    launches_per_step = sharded.launches_per_step()
+    use_graph = False
+  else:
+    step_fn = lambda: wl.step(args.batch)
+    use_graph = not args.no_graph
+
+  with ClockSampler(local_rank) as clocks:
+    ms = time_graph_or_eager(torch, step_fn, args.steps, args.warmup, use_graph,
+                             dist)
+  if dist is not None:
+    t = torch.tensor([ms], device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+  _native.check(_native.lib().b2r_check(wl.h, _native.current_stream()))
+  transitions = args.batch * world * args.steps
+  value = transitions / (ms * 1e-3)
+
+  line = {
+      'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'n_gpus': world,
+      'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': round(ms / args.steps, 6), 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8',
+      'data': 'synthetic',
+      'config': {
+          'workload': workload_name(args.batch, args.capacity, world),
+          'l2': 'inputs larger than L2: 7.06 GB frame ring per GPU, fresh random '
+                'indices every step (device Philox); no flush needed',
+          'launch': 'CUDA graph replay' if use_graph else 'eager launches',
+          'rng': 'device Philox4x32-10',
+      },
+      'gpu_launches': int(launches_per_step * args.steps),
+      'clocks': clocks.summary(),
+  }
+  if rank == 0:
+    line['roofline'] = measure_gather_roofline(torch, wl, args.batch, peak_gbs)
+    if sweep_batches and world == 1:
+      sweep = {}
+      for b in sweep_batches:
+        k = max(20, min(args.steps, 400))
+        ms_b = time_graph_or_eager(torch, lambda: wl.step(b), k, 5, use_graph)
+        roof = measure_gather_roofline(torch, wl, b, peak_gbs, launches=60)
+        sweep[str(b)] = {'value': round(b * k / (ms_b * 1e-3), 1),
+                         'ms_per_step': round(ms_b / k, 5),
+                         'gather_GBps': roof['achieved'],
+                         'gather_frac': roof['frac'],
+                         'gather_us': roof['us_per_launch']}
+      line['sweep'] = sweep
+    if not args.no_e2e and world == 1:
+      line['e2e'] = measure_e2e(torch, wl, args.batch, max(50, min(args.steps, 500)))
+    if not args.no_cpu_baseline and world == 1:
+      line['cpu_baseline'] = cpu_baseline(args.batch, args.capacity)
+    print(json.dumps(line))
+  if dist is not None:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

@@ -336,6 +336,8 @@ int b2r_create(const b2r_config *cfg, b2r_buffer **out) {
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->info), 64));
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->status), 16));
   B2R_CUDA(cudaMemset(b->status, 0, 16));
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->draw_counter), 8));
+  B2R_CUDA(cudaMemset(b->draw_counter, 0, 8));
   *out = b;
   return B2R_OK;
 }
@@ -355,6 +357,7 @@ int b2r_destroy(b2r_buffer *b) {
   if (b->inv_slots) cudaFree(b->inv_slots);
   cudaFree(b->info);
   cudaFree(b->status);
+  cudaFree(b->draw_counter);
   if (b->out_scratch) cudaFree(b->out_scratch);
   b->bounce.release();
   delete b;
@@ -445,7 +448,7 @@ int b2r_store_read(b2r_buffer *b, int32_t column, int64_t row0, int64_t nrows,
   B2R_TRY(b2r::flush_queue(b, s));
   const int64_t rb = b->col[column].row_bytes;
   B2R_CUDA(cudaMemcpyAsync(out, b->col[column].dev + row0 * rb,
-                           (size_t)(nrows * rb), cudaMemcpyDeviceToHost, s));
+                           (size_t)(nrows * rb), cudaMemcpyDefault, s));
   B2R_CUDA(cudaStreamSynchronize(s));
   return B2R_OK;
 }
@@ -459,12 +462,17 @@ int b2r_store_write(b2r_buffer *b, int32_t column, int64_t row0, int64_t nrows,
   B2R_TRY(b2r::flush_queue(b, s));
   const int64_t rb = b->col[column].row_bytes;
   B2R_CUDA(cudaMemcpyAsync(b->col[column].dev + row0 * rb, in,
-                           (size_t)(nrows * rb), cudaMemcpyHostToDevice, s));
+                           (size_t)(nrows * rb), cudaMemcpyDefault, s));
   if (column == B2R_COL_TERMINAL) {
-    const uint8_t *src = static_cast<const uint8_t *>(in);
+    // keep the host mirror of `terminal == 1` (CRB:255) in step; `in` may be a
+    // device pointer, so read the rows back from the store itself.
+    std::vector<uint8_t> rows((size_t)(nrows * rb));
+    B2R_CUDA(cudaMemcpyAsync(rows.data(), b->col[column].dev + row0 * rb,
+                             rows.size(), cudaMemcpyDeviceToHost, s));
+    B2R_CUDA(cudaStreamSynchronize(s));
     for (int64_t k = 0; k < nrows; ++k)
-      b->term_is_one[row0 + k] =
-          b2r::terminal_equals_one(src + k * rb, b->cfg.terminal_itemsize);
+      b->term_is_one[row0 + k] = b2r::terminal_equals_one(
+          rows.data() + k * rb, b->cfg.terminal_itemsize);
     if (b->term_flag_owned && nrows > 0) {
       b2r::term_flag_rebuild_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0,
                                       s>>>(b->col[3].dev,

@@ -104,6 +104,8 @@ struct b2r_buffer {
   int64_t inv_slots_cap = 0;
   int32_t *info = nullptr;      // device [4]: status, fail slot, draws used, count
   int64_t *status = nullptr;    // device [2]: latched asynchronous error
+  uint64_t *draw_counter = nullptr;  // device: bumps per Philox sample launch, so a
+                                     // replayed CUDA graph draws fresh uniforms
   b2r::Bounce bounce;           // HOST-array calls
   uint8_t *out_scratch = nullptr;  // device outputs of b2r_gather (HOST variant)
   size_t out_scratch_cap = 0;

@@ -23,6 +23,7 @@ struct PerSampleArgs {
   // uniforms: host-provided (reference RNG stream) or Philox (throughput mode)
   int use_philox;
   uint64_t seed, offset;
+  uint64_t *counter;            // nullable: device draw counter added to offset
   const double *strat_query01;  // [batch]  final query values in [0,1]
   const double *retry_u01;      // [max_attempts]
   // outputs
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(1024) per_sample_kernel(PerSampleArgs a) {
   __shared__ int warp_counts[32];
   __shared__ int s_draws_used, s_last_idx, s_last_valid;
 
+  const uint64_t draw_offset = a.offset + (a.counter ? *a.counter : 0ull);
   const int top_depth = stage_top_levels(a.heap, a.depth, top);
   const double local_total = top[0];
   // Mass the strata are spread over: the root, or all shards' roots summed in
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(1024) per_sample_kernel(PerSampleArgs a) {
       if (a.use_philox) {
         const double lo = __dmul_rn((double)i, step);
         const double hi = (i + 1 == a.batch) ? 1.0 : __dmul_rn((double)(i + 1), step);
-        const double u = philox_uniform53(a.seed, a.offset, (uint64_t)i);
+        const double u = philox_uniform53(a.seed, draw_offset, (uint64_t)i);
         q01 = __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), u));  // random.uniform
       } else {
         q01 = a.strat_query01[i];
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(1024) per_sample_kernel(PerSampleArgs a) {
     int64_t idx = 0;
     if (active) {
       const double u = a.use_philox
-                           ? philox_uniform53(a.seed, a.offset,
+                           ? philox_uniform53(a.seed, draw_offset,
                                               (uint64_t)a.batch + (uint64_t)r)
                            : a.retry_u01[r];
       // sum_tree.py:123-124: query = random.random() * total
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__(1024) per_sample_kernel(PerSampleArgs a) {
         }
       }
     }
+    if (a.counter) *a.counter += 1;
     a.info[0] = status;
     a.info[1] = a.out_slots ? (status ? a.out_slots[fail_slot] : 0) : fail_slot;
     a.info[2] = used;
@@ -186,6 +189,7 @@ struct UniformSampleArgs {
   int max_attempts;
   int use_philox;
   uint64_t seed, offset;
+  uint64_t *counter;
   int64_t min_id, max_id;      // Philox mode: candidates in [min_id, max_id)
   int n_cand;                  // host mode: number of supplied candidates
   const int64_t *candidates;   // np.random.randint(min_id, max_id) draws
@@ -198,6 +202,7 @@ struct UniformSampleArgs {
 __global__ void __launch_bounds__(1024) uniform_sample_kernel(UniformSampleArgs a) {
   __shared__ int warp_counts[32];
   int accepted = a.counters[0], rejected = a.counters[1], used = 0;
+  const uint64_t draw_offset = a.offset + (a.counter ? *a.counter : 0ull);
   __syncthreads();
   const int64_t span = a.max_id - a.min_id;
   int base = 0;
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(1024) uniform_sample_kernel(UniformSampleArgs 
     if (active) {
       int64_t cand;
       if (a.use_philox) {
-        const double u = philox_uniform53(a.seed, a.offset, (uint64_t)p);
+        const double u = philox_uniform53(a.seed, draw_offset, (uint64_t)p);
         int64_t off = (int64_t)(u * (double)span);
         if (off >= span) off = span - 1;
         cand = a.min_id + off;
@@ -240,6 +245,7 @@ __global__ void __launch_bounds__(1024) uniform_sample_kernel(UniformSampleArgs 
     a.counters[0] = accepted;
     a.counters[1] = rejected;
     a.counters[2] = used;
+    if (a.counter) *a.counter += 1;
     if (a.use_philox && accepted < a.batch && a.latched && a.latched[0] == 0) {
       a.latched[0] = B2R_ERR_SAMPLE_ATTEMPTS;
       a.latched[1] = accepted;
@@ -288,6 +294,7 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   a.use_philox = philox ? 1 : 0;
   a.seed = seed;
   a.offset = offset;
+  a.counter = philox ? b->draw_counter : nullptr;
   a.strat_query01 = strat_dev;
   a.retry_u01 = retry_dev;
   a.out_idx = out_idx_dev;
@@ -342,6 +349,7 @@ int b2r_sample_indices_uniform(b2r_buffer *b, int32_t batch, int32_t n_cand,
   a.max_attempts = b->cfg.max_sample_attempts;
   a.use_philox = 0;
   a.seed = a.offset = 0;
+  a.counter = nullptr;
   a.min_id = a.max_id = 0;
   a.n_cand = n_cand;
   a.candidates = reinterpret_cast<const int64_t *>(b->bounce.dev);
@@ -420,6 +428,7 @@ int b2r_sample_indices_device(b2r_buffer *b, int32_t batch, uint64_t seed,
   a.use_philox = 1;
   a.seed = seed;
   a.offset = offset;
+  a.counter = b->draw_counter;
   a.n_cand = 0;
   a.candidates = nullptr;
   a.out_idx = out_indices;
@@ -452,6 +461,7 @@ int b2r_sample_indices_sharded_device(b2r_buffer *b, int32_t global_batch,
   a.max_attempts = n_retry;
   a.use_philox = 0;
   a.seed = a.offset = 0;
+  a.counter = nullptr;
   a.strat_query01 = query01;
   a.retry_u01 = retry_u01;
   a.out_idx = out_indices;
