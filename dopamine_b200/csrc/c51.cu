@@ -66,36 +66,54 @@ c51_project_kernel(int batch, int n, const float *__restrict__ supports,
 
 struct LossArgs {
   b2r_c51_args u;
-  float *raw_weights;  // scratch (B,)
+  float *weighted;        // scratch (B,): w_b * loss_b, reduced by the last CTA
+  unsigned int *ticket;   // scratch: CTAs finished (self-resetting)
+  int warps;              // warps per CTA = min(num_actions, 32)
+  int parts;              // threads cooperating on one projected atom
 };
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) c51_loss_kernel(LossArgs a) {
+// One CTA per batch row, one warp per action (rainbow_agent.py:200-293):
+//   A. every warp: softmax of its action's target logits, q = sum z*p
+//      (atari_lib.py:141-143); meanwhile the CTA finds min(sampling_probabilities)
+//      for the IS-weight normalisation.
+//   B. first argmax over actions (RA:238-248); Bellman support r + g^n(1-t) z
+//      (RA:229-235); projection, `parts` threads per output atom (RA:381-494).
+//   C. warp 0: cross-entropy vs the chosen online logits (RA:262-271), priority
+//      sqrt(loss + 1e-10) (RA:290), weight 1/sqrt(p + 1e-10) / max (RA:279-280).
+//   D. all threads: gradient row; the last CTA to finish sums w*loss in a fixed
+//      order for mean_weighted_loss (RA:293, 305).
+__global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kWarpsPerBlock + warp;
-  const int N = a.u.num_atoms, A = a.u.num_actions;
-  if (b >= a.u.batch) return;
-  float *cur = smem + (size_t)warp * 3 * N;  // exp(x - max) of the action scanned
-  float *best_p = cur + N;                   // probabilities of the argmax action
-  float *sup = cur + 2 * N;                  // Bellman support r + g*z_j
+  const int b = blockIdx.x;
+  const int N = a.u.num_atoms, A = a.u.num_actions, W = a.warps;
+  float *cur = smem + (size_t)warp * N;          // [W][N] scratch per warp
+  float *bestp = smem + (size_t)(W + warp) * N;  // [W][N] best action's probs
+  float *sup = smem + (size_t)2 * W * N;         // [N] Bellman support
+  float *part = sup + N;                         // [parts][N] projection partials
+  float *tgt = part + (size_t)a.parts * N;       // [N] projected target
+  __shared__ float s_q[32];
+  __shared__ int s_a[32];
+  __shared__ float s_red[32];
+  __shared__ float s_scalar[4];  // tsum, w_b, m, denom
+  __shared__ bool s_last;
   const float *z = a.u.support;
 
-  // ---- target network head: softmax, q = sum z*p, first argmax
-  //      (atari_lib.py:141-143, rainbow_agent.py:238-248)
+  // ---- A. per-action softmax + q-value
   float best_q = 0.f;
   int best_a = -1;
-  for (int act = 0; act < A; ++act) {
+  for (int act = warp; act < A; act += W) {
     const float *x = a.u.target_logits + ((size_t)b * A + act) * N;
     float m = -INFINITY;
     for (int i = lane; i < N; i += 32) m = fmaxf(m, x[i]);
     m = warp_max(m);
-    float part = 0.f;
+    float psum = 0.f;
     for (int i = lane; i < N; i += 32) {
       const float e = expf(__fsub_rn(x[i], m));
       cur[i] = e;
-      part = __fadd_rn(part, e);
+      psum = __fadd_rn(psum, e);
     }
-    const float denom = warp_sum(part);
+    const float denom = warp_sum(psum);
     float qpart = 0.f;
     for (int i = lane; i < N; i += 32) {
       const float p = __fdiv_rn(cur[i], denom);
@@ -106,117 +124,145 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) c51_loss_kernel(LossArgs 
     if (best_a < 0 || q > best_q) {  // strict > keeps the first maximum
       best_q = q;
       best_a = act;
-      for (int i = lane; i < N; i += 32) best_p[i] = cur[i];
+      for (int i = lane; i < N; i += 32) bestp[i] = cur[i];
     }
     __syncwarp();
   }
+  if (lane == 0) {
+    s_q[warp] = best_q;
+    s_a[warp] = best_a;
+  }
+  // min over the batch of the sampling probabilities: 1/sqrt(p + 1e-10) is
+  // monotone under round-to-nearest, so max_b w_b == w(min_b p_b) exactly.
+  float pmin = INFINITY;
+  if (a.u.sampling_probabilities) {
+    for (int k = threadIdx.x; k < a.u.batch; k += blockDim.x)
+      pmin = fminf(pmin, a.u.sampling_probabilities[k]);
+    pmin = -warp_max(-pmin);
+    if (lane == 0) s_red[warp] = pmin;
+  }
+  __syncthreads();
 
-  // ---- Bellman support (rainbow_agent.py:229-235)
+  // ---- B. argmax action (first maximum), Bellman support, projection
+  int win = 0;
+  for (int w = 1; w < W; ++w) {
+    if (s_a[w] < 0) continue;
+    if (s_q[w] > s_q[win] || (s_q[w] == s_q[win] && s_a[w] < s_a[win])) win = w;
+  }
+  const float *next_p = smem + (size_t)(W + win) * N;
   const float live = __fsub_rn(1.0f, (float)a.u.terminals[b]);
   const float gwt = __fmul_rn(a.u.cumulative_gamma, live);
   const float r = a.u.rewards[b];
-  for (int j = lane; j < N; j += 32) sup[j] = __fadd_rn(r, __fmul_rn(gwt, z[j]));
-  __syncwarp();
-
-  // ---- projection + cross entropy against the chosen online logits
-  //      (rainbow_agent.py:250, 262-271)
+  for (int j = threadIdx.x; j < N; j += blockDim.x)
+    sup[j] = __fadd_rn(r, __fmul_rn(gwt, z[j]));
+  __syncthreads();
   const float z0 = z[0], zlast = z[N - 1];
   const float dz = __fsub_rn(z[1], z[0]);
+  const int per = (N + a.parts - 1) / a.parts;
+  for (int t = threadIdx.x; t < a.parts * N; t += blockDim.x) {
+    const int i = t % N, pt = t / N;
+    const int j0 = pt * per, j1 = min(N, j0 + per);
+    const float zi = z[i];
+    float acc = 0.f;
+    for (int j = j0; j < j1; ++j) {
+      const float clipped = fminf(fmaxf(sup[j], z0), zlast);
+      const float gap = fabsf(__fsub_rn(clipped, zi));
+      float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
+      hat = fminf(fmaxf(hat, 0.f), 1.f);
+      acc = __fadd_rn(acc, __fmul_rn(hat, next_p[j]));
+    }
+    part[(size_t)pt * N + i] = acc;
+  }
+  __syncthreads();
+
+  // ---- C. cross entropy, priority, weight (warp 0)
   const int chosen = a.u.actions[b];
   const float *x = a.u.online_logits + ((size_t)b * A + chosen) * N;
-  float m = -INFINITY;
-  for (int i = lane; i < N; i += 32) m = fmaxf(m, x[i]);
-  m = warp_max(m);
-  float part = 0.f;
-  for (int i = lane; i < N; i += 32) part = __fadd_rn(part, expf(__fsub_rn(x[i], m)));
-  const float denom = warp_sum(part);
-  const float lse = logf(denom);
-  float ce_part = 0.f, tsum_part = 0.f;
-  for (int i = lane; i < N; i += 32) {
-    const float t = project_atom(sup, best_p, N, z[i], z0, zlast, dz);
-    cur[i] = t;  // `cur` is free again: keep the target for the gradient pass
-    if (a.u.target) a.u.target[(size_t)b * N + i] = t;
-    const float logp = __fsub_rn(__fsub_rn(x[i], m), lse);
-    ce_part = __fadd_rn(ce_part, __fmul_rn(t, logp));
-    tsum_part = __fadd_rn(tsum_part, t);
+  if (warp == 0) {
+    float m = -INFINITY;
+    for (int i = lane; i < N; i += 32) m = fmaxf(m, x[i]);
+    m = warp_max(m);
+    float psum = 0.f;
+    for (int i = lane; i < N; i += 32) psum = __fadd_rn(psum, expf(__fsub_rn(x[i], m)));
+    const float denom = warp_sum(psum);
+    const float lse = logf(denom);
+    float ce_part = 0.f, tsum_part = 0.f;
+    for (int i = lane; i < N; i += 32) {
+      float t = part[i];
+      for (int pt = 1; pt < a.parts; ++pt) t = __fadd_rn(t, part[(size_t)pt * N + i]);
+      tgt[i] = t;
+      if (a.u.target) a.u.target[(size_t)b * N + i] = t;
+      const float logp = __fsub_rn(__fsub_rn(x[i], m), lse);
+      ce_part = __fadd_rn(ce_part, __fmul_rn(t, logp));
+      tsum_part = __fadd_rn(tsum_part, t);
+    }
+    const float ce = -warp_sum(ce_part);
+    const float tsum = warp_sum(tsum_part);
+    if (lane == 0) {
+      float w = 1.f;
+      if (a.u.sampling_probabilities) {
+        float mn = s_red[0];
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) mn = fminf(mn, s_red[k]);
+        const float wmax = __fdiv_rn(1.0f, sqrtf(__fadd_rn(mn, 1e-10f)));
+        const float raw = __fdiv_rn(
+            1.0f, sqrtf(__fadd_rn(a.u.sampling_probabilities[b], 1e-10f)));
+        w = __fdiv_rn(raw, wmax);
+      }
+      a.u.loss[b] = ce;
+      a.u.priorities[b] = sqrtf(__fadd_rn(ce, 1e-10f));
+      if (a.u.weights) a.u.weights[b] = w;
+      a.weighted[b] = __fmul_rn(w, ce);
+      s_scalar[0] = tsum;
+      s_scalar[1] = w;
+      s_scalar[2] = m;
+      s_scalar[3] = denom;
+    }
   }
-  const float ce = -warp_sum(ce_part);
-  const float tsum = warp_sum(tsum_part);
-  if (lane == 0) {
-    a.u.loss[b] = ce;
-    a.u.priorities[b] = sqrtf(__fadd_rn(ce, 1e-10f));  // rainbow_agent.py:290
-    if (a.u.sampling_probabilities)  // rainbow_agent.py:279
-      a.raw_weights[b] =
-          __fdiv_rn(1.0f, sqrtf(__fadd_rn(a.u.sampling_probabilities[b], 1e-10f)));
-  }
+  __syncthreads();
+
+  // ---- D. gradient of mean(w * ce) w.r.t. the online logits
   if (a.u.grad_logits) {
-    // d ce / d x_i = softmax(x)_i * sum(t) - t_i ; other actions get zero.
-    // Scaled by w_b / B in c51_finalize_kernel once max(w) is known.
-    __syncwarp();
+    const float tsum = s_scalar[0], w = s_scalar[1], m = s_scalar[2], denom = s_scalar[3];
+    const float scale = __fmul_rn(w, __fdiv_rn(1.0f, (float)a.u.batch));
     float *g = a.u.grad_logits + (size_t)b * A * N;
-    for (int k = lane; k < A * N; k += 32) {
+    for (int k = threadIdx.x; k < A * N; k += blockDim.x) {
       const int act = k / N, i = k - act * N;
       float v = 0.f;
       if (act == chosen) {
         const float p = __fdiv_rn(expf(__fsub_rn(x[i], m)), denom);
-        v = __fsub_rn(__fmul_rn(p, tsum), cur[i]);
+        v = __fmul_rn(__fsub_rn(__fmul_rn(p, tsum), tgt[i]), scale);
       }
       g[k] = v;
     }
   }
-}
 
-// One CTA: IS weights / max, mean weighted loss, gradient scaling
-// (rainbow_agent.py:279-280, 293, 305).
-__global__ void __launch_bounds__(1024) c51_finalize_kernel(LossArgs a) {
-  __shared__ float red[32];
-  __shared__ float s_max;
-  const int B = a.u.batch, N = a.u.num_atoms, A = a.u.num_actions;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool weighted = a.u.sampling_probabilities != nullptr;
-  float wmax = 1.f;
-  if (weighted) {
-    float m = 0.f;
-    for (int b = threadIdx.x; b < B; b += blockDim.x) m = fmaxf(m, a.raw_weights[b]);
-    m = warp_max(m);
-    if (lane == 0) red[warp] = m;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float mm = 0.f;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mm = fmaxf(mm, red[w]);
-      s_max = mm;
-    }
-    __syncthreads();
-    wmax = s_max;
+  // ---- mean weighted loss: the last CTA to finish reduces in a fixed order.
+  if (a.u.mean_weighted_loss == nullptr) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(a.ticket, 1u);
+    s_last = (done == gridDim.x - 1);
   }
-  float part = 0.f;
-  for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const float w = weighted ? __fdiv_rn(a.raw_weights[b], wmax) : 1.f;
-    if (a.u.weights) a.u.weights[b] = w;
-    part = __fadd_rn(part, __fmul_rn(w, a.u.loss[b]));
-  }
-  part = warp_sum(part);
   __syncthreads();
-  if (lane == 0) red[warp] = part;
+  if (!s_last) return;
+  __threadfence();
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < a.u.batch; k += blockDim.x)
+    acc = __fadd_rn(acc, __ldcg(a.weighted + k));
+  acc = warp_sum(acc);
+  if (lane == 0) s_red[warp] = acc;
   __syncthreads();
-  if (threadIdx.x == 0 && a.u.mean_weighted_loss) {
+  if (threadIdx.x == 0) {
     float total = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total = __fadd_rn(total, red[w]);
-    *a.u.mean_weighted_loss = __fdiv_rn(total, (float)B);
-  }
-  if (a.u.grad_logits) {
-    const float inv_b = __fdiv_rn(1.0f, (float)B);
-    for (int k = threadIdx.x; k < B * N; k += blockDim.x) {
-      const int b = k / N, i = k - b * N;
-      const float w = weighted ? __fdiv_rn(a.raw_weights[b], wmax) : 1.f;
-      float *g = a.u.grad_logits + ((size_t)b * A + a.u.actions[b]) * N + i;
-      *g = __fmul_rn(*g, __fmul_rn(w, inv_b));
-    }
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total = __fadd_rn(total, s_red[w]);
+    *a.u.mean_weighted_loss = __fdiv_rn(total, (float)a.u.batch);
+    *a.ticket = 0u;  // ready for the next launch
   }
 }
 
-float *g_raw_weights = nullptr;
-int g_raw_weights_cap = 0;
+float *g_weighted = nullptr;
+unsigned int *g_ticket = nullptr;
+int g_weighted_cap = 0;
 
 }  // namespace
 }  // namespace b2r
@@ -250,29 +296,33 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
       !args->actions || !args->rewards || !args->terminals || !args->loss ||
       !args->priorities)
     return fail(B2R_ERR_INVALID_ARGUMENT, "a required C51 pointer is NULL");
-  const size_t smem = (size_t)b2r::kWarpsPerBlock * 3 * args->num_atoms * 4;
-  if (smem > 48 * 1024) return fail(B2R_ERR_UNSUPPORTED, "num_atoms too large");
   cudaStream_t s = as_stream(stream);
-  if (args->batch > b2r::g_raw_weights_cap) {
-    if (b2r::g_raw_weights) cudaFree(b2r::g_raw_weights);
-    b2r::g_raw_weights = nullptr;
-    int cap = 4096;
-    while (cap < args->batch) cap *= 2;
-    B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b2r::g_raw_weights), (size_t)cap * 4));
-    b2r::g_raw_weights_cap = cap;
-  }
   b2r::LossArgs a;
   a.u = *args;
-  a.raw_weights = b2r::g_raw_weights;
-  const int blocks = (args->batch + b2r::kWarpsPerBlock - 1) / b2r::kWarpsPerBlock;
-  b2r::c51_loss_kernel<<<blocks, b2r::kWarpsPerBlock * 32, smem, s>>>(a);
-  B2R_LAUNCHED();
-  if (args->weights || args->mean_weighted_loss || args->grad_logits) {
-    int threads = 32;
-    while (threads < args->batch && threads < 1024) threads <<= 1;
-    b2r::c51_finalize_kernel<<<1, threads, 0, s>>>(a);
-    B2R_LAUNCHED();
+  a.warps = args->num_actions < 32 ? args->num_actions : 32;
+  const int threads = a.warps * 32;
+  a.parts = threads / args->num_atoms;
+  if (a.parts < 1) a.parts = 1;
+  if (a.parts > 4) a.parts = 4;
+  const size_t smem =
+      ((size_t)2 * a.warps + 2 + a.parts) * args->num_atoms * sizeof(float);
+  if (smem > 48 * 1024) return fail(B2R_ERR_UNSUPPORTED, "num_atoms too large");
+  if (args->batch > b2r::g_weighted_cap) {
+    if (b2r::g_weighted) cudaFree(b2r::g_weighted);
+    b2r::g_weighted = nullptr;
+    int cap = 4096;
+    while (cap < args->batch) cap *= 2;
+    B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b2r::g_weighted), (size_t)cap * 4));
+    b2r::g_weighted_cap = cap;
   }
+  if (!b2r::g_ticket) {
+    B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b2r::g_ticket), 4));
+    B2R_CUDA(cudaMemset(b2r::g_ticket, 0, 4));
+  }
+  a.weighted = b2r::g_weighted;
+  a.ticket = b2r::g_ticket;
+  b2r::c51_loss_kernel<<<args->batch, threads, smem, s>>>(a);
+  B2R_LAUNCHED();
   return B2R_OK;
 }
 

@@ -292,7 +292,7 @@ int launch_gather(b2r_buffer *b, int32_t batch, const int32_t *indices_dev,
   a.leaves = nullptr;
   a.prio_out = nullptr;
   if (b->tree && out->sampling_probabilities) {
-    a.leaves = b->tree->heap + (b->tree->leaves - 1);
+    a.leaves = b->tree->heap + b->tree->leaves;
     a.prio_out = out->sampling_probabilities;
   }
   const bool fast = a.stack == 4 && a.obs_itemsize == 1 && (a.obs_bytes & 15) == 0;
@@ -406,7 +406,7 @@ int b2r_get_priority_device(b2r_buffer *b, int64_t n, const int32_t *indices,
   cudaStream_t s = as_stream(stream);
   B2R_TRY(b2r::flush_queue(b, s));
   b2r::get_priority_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
-      b->tree->heap + (b->tree->leaves - 1), n, indices, out);
+      b->tree->heap + b->tree->leaves, n, indices, out);
   B2R_LAUNCHED();
   return B2R_OK;
 }
@@ -426,7 +426,7 @@ int b2r_get_priority(b2r_buffer *b, int64_t n, const int32_t *indices, float *ou
                            cudaMemcpyHostToDevice, s));
   float *dout = reinterpret_cast<float *>(b->bounce.dev + (size_t)n * 4);
   b2r::get_priority_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(
-      b->tree->heap + (b->tree->leaves - 1), n,
+      b->tree->heap + b->tree->leaves, n,
       reinterpret_cast<const int32_t *>(b->bounce.dev), dout);
   B2R_LAUNCHED();
   B2R_CUDA(cudaMemcpyAsync(b->bounce.host + (size_t)n * 4, dout, (size_t)n * 4,

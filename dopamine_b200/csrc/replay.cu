@@ -491,7 +491,7 @@ const void *b2r_store_device_ptr(b2r_buffer *b, int32_t column) {
 }
 
 const double *b2r_total_device_ptr(b2r_buffer *b) {
-  return b->tree ? b->tree->heap : nullptr;
+  return b->tree ? b->tree->heap + 1 : nullptr;  // root of the 1-based heap
 }
 
 int b2r_check(b2r_buffer *b, b2r_stream stream) {

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(1024) per_sample_kernel(PerSampleArgs a) {
 
   const uint64_t draw_offset = a.offset + (a.counter ? *a.counter : 0ull);
   const int top_depth = stage_top_levels(a.heap, a.depth, top);
-  const double local_total = top[0];
+  const double local_total = top[1];  // root of the 1-based heap
   // Mass the strata are spread over: the root, or all shards' roots summed in
   // rank order (fp64, left to right).
   double grand_total = local_total;
@@ -134,7 +134,6 @@ __global__ void __launch_bounds__(1024) per_sample_kernel(PerSampleArgs a) {
     int tile_valid;
     const int ord = found + block_scan_flag(active && valid, warp_counts, &tile_valid);
     if (active && valid && ord < num_invalid) {
-      __syncwarp(__activemask());
       a.out_idx[a.inv_slots[ord]] = (int32_t)idx;
       if (ord == num_invalid - 1) s_draws_used = r + 1;
     }

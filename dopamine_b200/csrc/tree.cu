@@ -6,18 +6,20 @@
 // (prioritized_replay_buffer.py:213-214) is a sequential loop, so for every node
 // the deltas of the batch elements below it must be added IN BATCH ORDER.
 //
-//   kernel 1  tree_leaf_pass      one CTA: sorts (leaf, k) in shared memory,
-//                                 resolves duplicate leaves as chains, emits
-//                                 delta[k], updates leaves + max_recorded.
-//   kernel 2  tree_internal_pass  one CTA per internal level, all levels
-//                                 concurrently: sorts (node, k) and runs one
-//                                 ordered fp64 add-chain per touched node.
+// ONE cooperative launch per chunk of <= 4096 sets, one CTA per tree level (see
+// tree_update_kernel): every CTA sorts its (node, k) keys in shared memory, the
+// leaf CTA resolves duplicate leaves as chains and publishes delta[k], a grid
+// barrier, then each internal CTA runs one ordered fp64 add-chain per touched node.
 //
 // The critical path is the root's chain of n dependent DADDs; everything else
 // overlaps with it.  Bandwidth is irrelevant here (n * depth * 16 bytes).
 #include "tree.cuh"
 
+#include <cooperative_groups.h>
+
 #include <new>
+
+namespace cg = cooperative_groups;
 
 namespace b2r {
 namespace {
@@ -44,24 +46,41 @@ __device__ __forceinline__ void bitonic_sort(uint64_t *keys, int padded) {
 }
 
 template <typename I, typename V>
-__global__ void __launch_bounds__(1024)
-tree_leaf_pass(double *__restrict__ heap, int depth, int64_t leaves, int n,
-               int padded, const I *__restrict__ indices,
-               const V *__restrict__ values, const uint8_t *__restrict__ mode,
-               int64_t k_base, double *__restrict__ delta_out,
-               int32_t *__restrict__ n_eff_out, double *__restrict__ max_rec,
-               int64_t *__restrict__ status) {
+struct UpdateArgs {
+  double *heap;
+  int depth;
+  int64_t leaves;
+  int n, padded;
+  const I *indices;
+  const V *values;
+  const uint8_t *mode;
+  int64_t k_base;
+  double *delta;      // global scratch [n]: leaf deltas, produced by the leaf CTA
+  double *max_rec;
+  int64_t *status;
+};
+
+// ONE cooperative launch, grid = depth + 1 CTAs (CTA l owns level l, CTA `depth`
+// the leaves).  Every CTA sorts its own (node, k) keys concurrently; the leaf CTA
+// then resolves the per-leaf chains and publishes delta[k]; after one grid-wide
+// barrier each internal CTA adds the deltas that fall under each of its nodes in
+// batch order.  Critical path: one sort + the root's chain of n dependent DADDs.
+template <typename I, typename V>
+__global__ void __launch_bounds__(1024) tree_update_kernel(UpdateArgs<I, V> a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);
-  double *vals = reinterpret_cast<double *>(smem_raw) + padded;
+  double *vals = reinterpret_cast<double *>(smem_raw) + a.padded;
   __shared__ int s_stop;       // first position that must not be applied
   __shared__ int s_stop_code;
   __shared__ double s_max[32];
 
-  if (status[0] != 0) {  // an earlier chunk failed: the sequence stopped there
-    if (threadIdx.x == 0) *n_eff_out = 0;
-    return;
-  }
+  cg::grid_group grid = cg::this_grid();
+  const int level = blockIdx.x;
+  const bool is_leaf = level == a.depth;
+  const int n = a.n;
+  // An earlier chunk failed: the reference's loop stopped there.  The latch is
+  // only written after the grid barrier, so every CTA takes the same branch.
+  if (a.status[0] != 0) return;
   if (threadIdx.x == 0) {
     s_stop = n;
     s_stop_code = 0;
@@ -69,117 +88,108 @@ tree_leaf_pass(double *__restrict__ heap, int depth, int64_t leaves, int n,
   __syncthreads();
 
   // 1. stage values; find the first element the reference would have raised on.
-  if (mode != nullptr) {
+  //    (Redundant in every CTA: cheaper than a second barrier.)
+  if (a.mode != nullptr) {
     // add-path batches may ask for "current max_recorded_priority": needs the
     // running maximum in order.  These batches are tiny; one thread walks them.
     if (threadIdx.x == 0) {
-      double running = *max_rec;
+      double running = *a.max_rec;
       for (int k = 0; k < n; ++k) {
-        double v = mode[k] ? running : (double)values[k];
-        const int64_t idx = (int64_t)indices[k];
+        double v = a.mode[k] ? running : (double)a.values[k];
+        const int64_t idx = (int64_t)a.indices[k];
         if (v < 0.0) { s_stop = k; s_stop_code = B2R_ERR_NEGATIVE_PRIORITY; break; }
-        if (idx < 0 || idx >= leaves) { s_stop = k; s_stop_code = B2R_ERR_INDEX_RANGE; break; }
+        if (idx < 0 || idx >= a.leaves) { s_stop = k; s_stop_code = B2R_ERR_INDEX_RANGE; break; }
         if (v > running) running = v;
         vals[k] = v;
       }
     }
   } else {
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
-      const double v = (double)values[k];
-      const int64_t idx = (int64_t)indices[k];
+      const double v = (double)a.values[k];
+      const int64_t idx = (int64_t)a.indices[k];
       vals[k] = v;
-      if (v < 0.0 || idx < 0 || idx >= leaves) atomicMin(&s_stop, k);
+      if (v < 0.0 || idx < 0 || idx >= a.leaves) atomicMin(&s_stop, k);
     }
   }
   __syncthreads();
   const int n_eff = s_stop;
-  if (mode == nullptr && n_eff < n && threadIdx.x == 0) {
+  if (a.mode == nullptr && n_eff < n && threadIdx.x == 0)
     s_stop_code = (vals[n_eff] < 0.0) ? B2R_ERR_NEGATIVE_PRIORITY
                                       : B2R_ERR_INDEX_RANGE;
-  }
 
-  // 2. max_recorded_priority = max(value, current) over the applied prefix.
-  double local_max = 0.0;
-  for (int k = threadIdx.x; k < n_eff; k += blockDim.x)
-    local_max = fmax(local_max, vals[k]);
-  for (int off = 16; off > 0; off >>= 1)
-    local_max = fmax(local_max, __shfl_xor_sync(0xffffffffu, local_max, off));
-  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = local_max;
-
-  // 3. keys = (leaf, k): sorting groups duplicates and keeps batch order inside.
-  for (int k = threadIdx.x; k < padded; k += blockDim.x)
-    keys[k] = k < n_eff ? (((uint64_t)(int64_t)indices[k]) << 32) | (uint32_t)k
-                        : kPadKey;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double m = *max_rec;
-    for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w)
-      if (s_max[w] > m) m = s_max[w];
-    if (n_eff > 0) *max_rec = m;
-    *n_eff_out = n_eff;
-    if (n_eff < n) {
-      status[0] = s_stop_code;
-      status[1] = k_base + n_eff;
-    }
-  }
-  bitonic_sort(keys, padded);
-
-  // 4. one thread per distinct leaf walks its chain in batch order:
-  //    delta = value - leaf; leaf += delta   (sum_tree.py:196-202, last level).
-  const int64_t leaf_base = leaves - 1;
-  for (int p = threadIdx.x; p < n_eff; p += blockDim.x) {
-    const uint32_t node = (uint32_t)(keys[p] >> 32);
-    if (p > 0 && (uint32_t)(keys[p - 1] >> 32) == node) continue;
-    double leaf = heap[leaf_base + node];
-    for (int q = p; q < n_eff && (uint32_t)(keys[q] >> 32) == node; ++q) {
-      const uint32_t k = (uint32_t)keys[q];
-      const double d = __dsub_rn(vals[k], leaf);
-      leaf = __dadd_rn(leaf, d);
-      vals[k] = d;
-    }
-    heap[leaf_base + node] = leaf;
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < n_eff; k += blockDim.x) delta_out[k] = vals[k];
-}
-
-template <typename I>
-__global__ void __launch_bounds__(1024)
-tree_internal_pass(double *__restrict__ heap, int depth, int padded,
-                   const I *__restrict__ indices,
-                   const double *__restrict__ delta_in,
-                   const int32_t *__restrict__ n_eff_in) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);
-  double *delta = reinterpret_cast<double *>(smem_raw) + padded;
-
-  const int n_eff = *n_eff_in;
-  if (n_eff == 0) return;
-  const int level = blockIdx.x;  // 0 .. depth-1
-  const int shift = depth - level;
-  // Shrink the sort to the next power of two >= n_eff.
+  // 2. keys = (node at this level, k): sorting groups the elements under one node
+  //    and keeps batch order inside the group.  The root needs no sort.
+  const int shift = a.depth - level;
   int p2 = 32;
   while (p2 < n_eff) p2 <<= 1;
-  if (p2 > padded) p2 = padded;
-  for (int k = threadIdx.x; k < p2; k += blockDim.x) {
-    if (k < n_eff) {
-      keys[k] = (((uint64_t)((int64_t)indices[k] >> shift)) << 32) | (uint32_t)k;
-      delta[k] = delta_in[k];
-    } else {
-      keys[k] = kPadKey;
-    }
-  }
+  for (int k = threadIdx.x; k < p2; k += blockDim.x)
+    keys[k] = k < n_eff
+                  ? (((uint64_t)((int64_t)a.indices[k] >> shift)) << 32) | (uint32_t)k
+                  : kPadKey;
   __syncthreads();
-  bitonic_sort(keys, p2);
+  if (level != 0) bitonic_sort(keys, p2);
 
-  const int64_t base = (((int64_t)1) << level) - 1;
+  if (is_leaf) {
+    // max_recorded_priority = max(value, current) over the applied prefix.
+    double local_max = 0.0;
+    for (int k = threadIdx.x; k < n_eff; k += blockDim.x)
+      local_max = fmax(local_max, vals[k]);
+    for (int off = 16; off > 0; off >>= 1)
+      local_max = fmax(local_max, __shfl_xor_sync(0xffffffffu, local_max, off));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = local_max;
+    // one thread per distinct leaf walks its chain in batch order:
+    //   delta = value - leaf; leaf += delta   (sum_tree.py:196-202, last level).
+    for (int p = threadIdx.x; p < n_eff; p += blockDim.x) {
+      const uint32_t node = (uint32_t)(keys[p] >> 32);
+      if (p > 0 && (uint32_t)(keys[p - 1] >> 32) == node) continue;
+      double leaf = a.heap[a.leaves + node];
+      for (int q = p; q < n_eff && (uint32_t)(keys[q] >> 32) == node; ++q) {
+        const uint32_t k = (uint32_t)keys[q];
+        const double d = __dsub_rn(vals[k], leaf);
+        leaf = __dadd_rn(leaf, d);
+        vals[k] = d;
+      }
+      a.heap[a.leaves + node] = leaf;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_eff; k += blockDim.x) a.delta[k] = vals[k];
+  }
+
+  grid.sync();
+
+  if (is_leaf) {
+    if (threadIdx.x == 0) {
+      double m = *a.max_rec;
+      for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w)
+        if (s_max[w] > m) m = s_max[w];
+      if (n_eff > 0) *a.max_rec = m;
+      if (n_eff < n) {
+        a.status[0] = s_stop_code;
+        a.status[1] = a.k_base + n_eff;
+      }
+    }
+    return;
+  }
+
+  // 3. internal level: deltas in sorted order, then one ordered chain per node.
+  double *sorted_delta = vals;
+  for (int p = threadIdx.x; p < n_eff; p += blockDim.x)
+    sorted_delta[p] = a.delta[(uint32_t)keys[p]];
+  __syncthreads();
+  const int64_t base = ((int64_t)1) << level;
   for (int p = threadIdx.x; p < n_eff; p += blockDim.x) {
     const uint32_t node = (uint32_t)(keys[p] >> 32);
     if (p > 0 && (uint32_t)(keys[p - 1] >> 32) == node) continue;
-    double acc = heap[base + node];
-    for (int q = p; q < n_eff && (uint32_t)(keys[q] >> 32) == node; ++q)
-      acc = __dadd_rn(acc, delta[(uint32_t)keys[q]]);
-    heap[base + node] = acc;
+    // end of the segment: first position whose node is larger (binary search).
+    int lo = p + 1, hi = n_eff;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((uint32_t)(keys[mid] >> 32) > node) hi = mid; else lo = mid + 1;
+    }
+    double acc = a.heap[base + node];
+#pragma unroll 8
+    for (int q = p; q < lo; ++q) acc = __dadd_rn(acc, sorted_delta[q]);
+    a.heap[base + node] = acc;
   }
 }
 
@@ -189,7 +199,7 @@ __global__ void tree_get_kernel(const double *__restrict__ heap, int64_t leaves,
   const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int64_t i = indices[k];
-  out[k] = (i >= 0 && i < leaves) ? heap[leaves - 1 + i] : 0.0;
+  out[k] = (i >= 0 && i < leaves) ? heap[leaves + i] : 0.0;
 }
 
 __global__ void tree_query_kernel(const double *__restrict__ heap, int depth,
@@ -198,7 +208,7 @@ __global__ void tree_query_kernel(const double *__restrict__ heap, int depth,
                                   double *__restrict__ total_out) {
   extern __shared__ double top[];
   const int top_depth = stage_top_levels(heap, depth, top);
-  const double total = top[0];
+  const double total = top[1];
   if (blockIdx.x == 0 && threadIdx.x == 0) *total_out = total;
   const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -232,8 +242,7 @@ int allow_big_smem(K kernel) {
 template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
                const uint8_t *mode, cudaStream_t stream) {
-  B2R_TRY(allow_big_smem(tree_leaf_pass<I, V>));
-  B2R_TRY(allow_big_smem(tree_internal_pass<I>));
+  B2R_TRY(allow_big_smem(tree_update_kernel<I, V>));
   for (int64_t base = 0; base < n; base += kTreeChunk) {
     const int len = (int)((n - base) < kTreeChunk ? (n - base) : kTreeChunk);
     const int padded = padded_size(len);
@@ -241,16 +250,24 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     if (threads < 32) threads = 32;
     if (threads > 1024) threads = 1024;
     const size_t smem = (size_t)padded * 16;
-    tree_leaf_pass<I, V><<<1, threads, smem, stream>>>(
-        t->heap, t->depth, t->leaves, len, padded, indices + base,
-        values + base, mode ? mode + base : nullptr, base, t->delta, t->n_eff,
-        t->max_rec, t->status);
+    UpdateArgs<I, V> a;
+    a.heap = t->heap;
+    a.depth = t->depth;
+    a.leaves = t->leaves;
+    a.n = len;
+    a.padded = padded;
+    a.indices = indices + base;
+    a.values = values + base;
+    a.mode = mode ? mode + base : nullptr;
+    a.k_base = base;
+    a.delta = t->delta;
+    a.max_rec = t->max_rec;
+    a.status = t->status;
+    void *params[] = {&a};
+    B2R_CUDA(cudaLaunchCooperativeKernel(
+        reinterpret_cast<const void *>(&tree_update_kernel<I, V>),
+        dim3(t->depth + 1), dim3(threads), params, smem, stream));
     B2R_LAUNCHED();
-    if (t->depth > 0) {
-      tree_internal_pass<I><<<t->depth, threads, smem, stream>>>(
-          t->heap, t->depth, padded, indices + base, t->delta, t->n_eff);
-      B2R_LAUNCHED();
-    }
   }
   return B2R_OK;
 }
@@ -292,14 +309,13 @@ int b2r_tree_create(int64_t capacity, b2r_tree **out) {
   while ((1ll << depth) < capacity) ++depth;  // ceil(log2(capacity)), ST:81
   t->depth = depth;
   t->leaves = 1ll << depth;
-  const size_t nodes = (size_t)(2 * t->leaves - 1);
+  const size_t nodes = (size_t)(2 * t->leaves);  // 1-based heap, element 0 unused
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->heap), nodes * 8));
   B2R_CUDA(cudaMemset(t->heap, 0, nodes * 8));
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->max_rec), 8));
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->status), 16));
   B2R_CUDA(cudaMemset(t->status, 0, 16));
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->delta), b2r::kTreeChunk * 8));
-  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->n_eff), 4));
   const double one = 1.0;  // ST:89
   B2R_CUDA(cudaMemcpy(t->max_rec, &one, 8, cudaMemcpyHostToDevice));
   *out = t;
@@ -312,7 +328,6 @@ int b2r_tree_destroy(b2r_tree *t) {
   cudaFree(t->max_rec);
   cudaFree(t->status);
   cudaFree(t->delta);
-  cudaFree(t->n_eff);
   t->bounce.release();
   delete t;
   return B2R_OK;
@@ -398,7 +413,7 @@ int b2r_tree_get(b2r_tree *t, int64_t n, const int64_t *indices, double *out,
 }
 
 int b2r_tree_total(b2r_tree *t, double *out, b2r_stream stream) {
-  B2R_CUDA(cudaMemcpyAsync(out, t->heap, 8, cudaMemcpyDeviceToHost,
+  B2R_CUDA(cudaMemcpyAsync(out, t->heap + 1, 8, cudaMemcpyDeviceToHost,
                            as_stream(stream)));
   B2R_CUDA(cudaStreamSynchronize(as_stream(stream)));
   return B2R_OK;
@@ -447,7 +462,7 @@ int b2r_tree_read_level(b2r_tree *t, int level, double *out, b2r_stream stream) 
   if (level < 0 || level > t->depth)
     return fail(B2R_ERR_INVALID_ARGUMENT, "level %d out of range", level);
   const size_t count = (size_t)1 << level;
-  B2R_CUDA(cudaMemcpyAsync(out, t->heap + (count - 1), count * 8,
+  B2R_CUDA(cudaMemcpyAsync(out, t->heap + count, count * 8,
                            cudaMemcpyDeviceToHost, as_stream(stream)));
   B2R_CUDA(cudaStreamSynchronize(as_stream(stream)));
   return B2R_OK;
@@ -458,7 +473,7 @@ int b2r_tree_write_level(b2r_tree *t, int level, const double *in,
   if (level < 0 || level > t->depth)
     return fail(B2R_ERR_INVALID_ARGUMENT, "level %d out of range", level);
   const size_t count = (size_t)1 << level;
-  B2R_CUDA(cudaMemcpyAsync(t->heap + (count - 1), in, count * 8,
+  B2R_CUDA(cudaMemcpyAsync(t->heap + count, in, count * 8,
                            cudaMemcpyHostToDevice, as_stream(stream)));
   B2R_CUDA(cudaStreamSynchronize(as_stream(stream)));
   return B2R_OK;
