@@ -2,12 +2,12 @@
 // weights: replaces the TensorFlow graph built by RainbowAgent
 // (rainbow_agent.py:200-305) and project_distribution (rainbow_agent.py:340-494).
 //
-// One warp per batch row; atoms are strided over lanes, reductions are warp
-// shuffles, the (source support, probability) pairs of a row sit in shared memory
-// so that lane i accumulates output atom i over all j exactly as the dense
-// [B, N, N] form does — without ever materialising it.  All arithmetic is f32
-// with explicit round-to-nearest intrinsics where TF evaluates separate ops
-// (no FMA contraction), true division and IEEE sqrt.
+// One CTA per batch row, one warp per action; atoms are strided over lanes,
+// reductions are warp shuffles, the (Bellman support, probability) pairs of a row
+// sit in shared memory so that each output atom is accumulated over all j exactly
+// as the dense [B, N, N] form does — without ever materialising it.  All
+// arithmetic is f32 with explicit round-to-nearest intrinsics where TF evaluates
+// separate ops (no FMA contraction), true division and IEEE sqrt.
 //
 // Traffic per row (A=18, N=51): 3 672 B of target logits + 204 B of online logits
 // read, <= 204 B target + 12 B scalars written (+3 672 B if grad_logits is asked).
@@ -82,6 +82,8 @@ struct LossArgs {
 //      sqrt(loss + 1e-10) (RA:290), weight 1/sqrt(p + 1e-10) / max (RA:279-280).
 //   D. all threads: gradient row; the last CTA to finish sums w*loss in a fixed
 //      order for mean_weighted_loss (RA:293, 305).
+constexpr int kMaxAtomsPerLane = 4;  // num_atoms <= 128
+
 __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   float *sup = smem + (size_t)2 * W * N;         // [N] Bellman support
   float *part = sup + N;                         // [parts][N] projection partials
   float *tgt = part + (size_t)a.parts * N;       // [N] projected target
+  float *onl = tgt + N;                          // [N] chosen online logits
   __shared__ float s_q[32];
   __shared__ int s_a[32];
   __shared__ float s_red[32];
@@ -99,63 +102,99 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   __shared__ bool s_last;
   const float *z = a.u.support;
 
-  // ---- A. per-action softmax + q-value
+  // ---- every global load the row needs is issued here, before the first use:
+  // the kernel is latency-bound at batch 32 and this keeps it to one round trip.
+  const int chosen = a.u.actions[b];
+  const float r = a.u.rewards[b];
+  const float term = (float)a.u.terminals[b];
+  const float my_prob = a.u.sampling_probabilities ? a.u.sampling_probabilities[b] : 1.f;
+  float pmin = INFINITY;
+  if (a.u.sampling_probabilities)
+    for (int k = threadIdx.x; k < a.u.batch; k += blockDim.x)
+      pmin = fminf(pmin, a.u.sampling_probabilities[k]);
+  float zl[kMaxAtomsPerLane], xt[kMaxAtomsPerLane], xo[kMaxAtomsPerLane];
+  const int act0 = warp;  // first (usually only) action of this warp
+#pragma unroll
+  for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+    const int i = lane + 32 * t;
+    const bool ok = i < N && act0 < A;
+    zl[t] = i < N ? z[i] : 0.f;
+    xt[t] = ok ? a.u.target_logits[((size_t)b * A + act0) * N + i] : -INFINITY;
+    xo[t] = ok ? a.u.online_logits[((size_t)b * A + act0) * N + i] : 0.f;
+  }
+
+  // ---- A. per-action softmax + q-value (atari_lib.py:141-143)
   float best_q = 0.f;
   int best_a = -1;
   for (int act = warp; act < A; act += W) {
-    const float *x = a.u.target_logits + ((size_t)b * A + act) * N;
+    if (act != act0) {  // more actions than warps: later rounds load as they go
+#pragma unroll
+      for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+        const int i = lane + 32 * t;
+        xt[t] = i < N ? a.u.target_logits[((size_t)b * A + act) * N + i] : -INFINITY;
+        xo[t] = i < N ? a.u.online_logits[((size_t)b * A + act) * N + i] : 0.f;
+      }
+    }
+    if (act == chosen) {
+#pragma unroll
+      for (int t = 0; t < kMaxAtomsPerLane; ++t)
+        if (lane + 32 * t < N) onl[lane + 32 * t] = xo[t];
+    }
     float m = -INFINITY;
-    for (int i = lane; i < N; i += 32) m = fmaxf(m, x[i]);
+#pragma unroll
+    for (int t = 0; t < kMaxAtomsPerLane; ++t) m = fmaxf(m, xt[t]);
     m = warp_max(m);
+    float e[kMaxAtomsPerLane];
     float psum = 0.f;
-    for (int i = lane; i < N; i += 32) {
-      const float e = expf(__fsub_rn(x[i], m));
-      cur[i] = e;
-      psum = __fadd_rn(psum, e);
+#pragma unroll
+    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+      const bool ok = lane + 32 * t < N;
+      e[t] = ok ? expf(__fsub_rn(xt[t], m)) : 0.f;
+      if (ok) psum = __fadd_rn(psum, e[t]);
     }
     const float denom = warp_sum(psum);
     float qpart = 0.f;
-    for (int i = lane; i < N; i += 32) {
-      const float p = __fdiv_rn(cur[i], denom);
-      cur[i] = p;
-      qpart = __fadd_rn(qpart, __fmul_rn(z[i], p));
+#pragma unroll
+    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+      if (lane + 32 * t < N) {
+        e[t] = __fdiv_rn(e[t], denom);
+        qpart = __fadd_rn(qpart, __fmul_rn(zl[t], e[t]));
+      }
     }
     const float q = warp_sum(qpart);
     if (best_a < 0 || q > best_q) {  // strict > keeps the first maximum
       best_q = q;
       best_a = act;
-      for (int i = lane; i < N; i += 32) bestp[i] = cur[i];
+#pragma unroll
+      for (int t = 0; t < kMaxAtomsPerLane; ++t)
+        if (lane + 32 * t < N) bestp[lane + 32 * t] = e[t];
     }
-    __syncwarp();
   }
+  (void)cur;
   if (lane == 0) {
     s_q[warp] = best_q;
     s_a[warp] = best_a;
   }
   // min over the batch of the sampling probabilities: 1/sqrt(p + 1e-10) is
   // monotone under round-to-nearest, so max_b w_b == w(min_b p_b) exactly.
-  float pmin = INFINITY;
   if (a.u.sampling_probabilities) {
-    for (int k = threadIdx.x; k < a.u.batch; k += blockDim.x)
-      pmin = fminf(pmin, a.u.sampling_probabilities[k]);
     pmin = -warp_max(-pmin);
     if (lane == 0) s_red[warp] = pmin;
   }
+  // Bellman support (rainbow_agent.py:229-235)
+  const float live = __fsub_rn(1.0f, term);
+  const float gwt = __fmul_rn(a.u.cumulative_gamma, live);
+  for (int j = threadIdx.x; j < N; j += blockDim.x)
+    sup[j] = __fadd_rn(r, __fmul_rn(gwt, z[j]));
   __syncthreads();
 
-  // ---- B. argmax action (first maximum), Bellman support, projection
+  // ---- B. argmax action (first maximum, RA:238-248), projection (RA:381-494)
   int win = 0;
   for (int w = 1; w < W; ++w) {
     if (s_a[w] < 0) continue;
     if (s_q[w] > s_q[win] || (s_q[w] == s_q[win] && s_a[w] < s_a[win])) win = w;
   }
   const float *next_p = smem + (size_t)(W + win) * N;
-  const float live = __fsub_rn(1.0f, (float)a.u.terminals[b]);
-  const float gwt = __fmul_rn(a.u.cumulative_gamma, live);
-  const float r = a.u.rewards[b];
-  for (int j = threadIdx.x; j < N; j += blockDim.x)
-    sup[j] = __fadd_rn(r, __fmul_rn(gwt, z[j]));
-  __syncthreads();
   const float z0 = z[0], zlast = z[N - 1];
   const float dz = __fsub_rn(z[1], z[0]);
   const int per = (N + a.parts - 1) / a.parts;
@@ -175,9 +214,8 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   }
   __syncthreads();
 
-  // ---- C. cross entropy, priority, weight (warp 0)
-  const int chosen = a.u.actions[b];
-  const float *x = a.u.online_logits + ((size_t)b * A + chosen) * N;
+  // ---- C. cross entropy (RA:262-271), priority (RA:290), weight (RA:279-280)
+  const float *x = onl;
   if (warp == 0) {
     float m = -INFINITY;
     for (int i = lane; i < N; i += 32) m = fmaxf(m, x[i]);
@@ -204,8 +242,7 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
         float mn = s_red[0];
         for (int k = 1; k < (int)(blockDim.x >> 5); ++k) mn = fminf(mn, s_red[k]);
         const float wmax = __fdiv_rn(1.0f, sqrtf(__fadd_rn(mn, 1e-10f)));
-        const float raw = __fdiv_rn(
-            1.0f, sqrtf(__fadd_rn(a.u.sampling_probabilities[b], 1e-10f)));
+        const float raw = __fdiv_rn(1.0f, sqrtf(__fadd_rn(my_prob, 1e-10f)));
         w = __fdiv_rn(raw, wmax);
       }
       a.u.loss[b] = ce;
@@ -305,8 +342,9 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
   if (a.parts < 1) a.parts = 1;
   if (a.parts > 4) a.parts = 4;
   const size_t smem =
-      ((size_t)2 * a.warps + 2 + a.parts) * args->num_atoms * sizeof(float);
-  if (smem > 48 * 1024) return fail(B2R_ERR_UNSUPPORTED, "num_atoms too large");
+      ((size_t)2 * a.warps + 3 + a.parts) * args->num_atoms * sizeof(float);
+  if (smem > 48 * 1024 || args->num_atoms > 32 * b2r::kMaxAtomsPerLane)
+    return fail(B2R_ERR_UNSUPPORTED, "num_atoms above 128 is not supported");
   if (args->batch > b2r::g_weighted_cap) {
     if (b2r::g_weighted) cudaFree(b2r::g_weighted);
     b2r::g_weighted = nullptr;

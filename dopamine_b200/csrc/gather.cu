@@ -53,16 +53,24 @@ struct GatherArgs {
   float *prio_out;
 };
 
-// Trajectory length and terminal flag (circular_replay_buffer.py:517-527).
+// Trajectory length and terminal flag (circular_replay_buffer.py:517-527).  The
+// flags of up to 8 steps are loaded together (one round trip) before any is tested.
 __device__ __forceinline__ int trajectory_length(const uint8_t *__restrict__ term,
                                                  int64_t i, int horizon,
                                                  int64_t cap, bool *ends) {
-  for (int k = 0; k < horizon; ++k) {
-    int64_t s = i + k;
-    if (s >= cap) s -= cap;
-    if (term[s]) {
+  for (int base = 0; base < horizon; base += 8) {
+    unsigned flags = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (base + k < horizon) {
+        int64_t s = i + base + k;
+        if (s >= cap) s -= cap;
+        flags |= (term[s] ? 1u : 0u) << k;
+      }
+    }
+    if (flags) {
       *ends = true;
-      return k + 1;
+      return base + __ffs(flags);
     }
   }
   *ends = false;

@@ -27,16 +27,19 @@ struct ValidCtx {
 __device__ __forceinline__ bool is_valid_transition(const ValidCtx &c,
                                                     int64_t index) {
   if (index < 0 || index >= c.capacity) return false;
-  if (c.add_count < c.capacity) {  // not full
-    if (index >= c.cursor - c.horizon) return false;
-    if (index < c.stack - 1) return false;
+  bool ok = true;
+  if (c.add_count < c.capacity)  // not full
+    ok = index < c.cursor - c.horizon && index >= c.stack - 1;
+  for (int k = 0; k < c.n_invalid; ++k) ok = ok && c.invalid[k] != index;
+  // get_terminal_stack(index)[:-1].any(): all flags are loaded before any is
+  // tested, so the check costs one memory round trip.
+  unsigned any = 0;
+  for (int k = 1; k < c.stack; ++k) {
+    int64_t s = index - k;
+    if (s < 0) s += c.capacity;
+    any |= c.term_flag[s];
   }
-  for (int k = 0; k < c.n_invalid; ++k)
-    if (c.invalid[k] == index) return false;
-  // get_terminal_stack(index)[:-1].any()
-  for (int k = 1; k < c.stack; ++k)
-    if (c.term_flag[wrap_index(index - k, c.capacity)]) return false;
-  return true;
+  return ok && any == 0;
 }
 
 // Block-wide exclusive scan of a 0/1 flag (warp ballots + one shared array).

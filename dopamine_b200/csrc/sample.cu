@@ -24,6 +24,7 @@ struct PerSampleArgs {
   int use_philox;
   uint64_t seed, offset;
   uint64_t *counter;            // nullable: device draw counter added to offset
+  uint32_t zero;                // always 0 (see descend_levels)
   const double *strat_query01;  // [batch]  final query values in [0,1]
   const double *retry_u01;      // [max_attempts]
   // outputs
@@ -37,12 +38,14 @@ struct PerSampleArgs {
   int32_t *out_slots;  // nullable
 };
 
-__global__ void __launch_bounds__(1024) per_sample_kernel(PerSampleArgs a) {
+template <int K, int MAX_THREADS>
+__global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a) {
   __shared__ double top[2 << kTopLevels];
   __shared__ int warp_counts[32];
   __shared__ int s_draws_used, s_last_idx, s_last_valid;
 
-  const uint64_t draw_offset = a.offset + (a.counter ? *a.counter : 0ull);
+  const uint64_t draws_before = a.counter ? *a.counter : 0ull;
+  const uint64_t draw_offset = a.offset + draws_before;
   const int top_depth = stage_top_levels(a.heap, a.depth, top);
   const double local_total = top[1];  // root of the 1-based heap
   // Mass the strata are spread over: the root, or all shards' roots summed in
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(1024) per_sample_kernel(PerSampleArgs a) {
       }
       mine = (owner == a.rank);
       if (mine) {
-        idx = tree_descend_staged(a.heap, top, top_depth, a.depth, mass);
+        idx = tree_descend_staged<K>(a.heap, top, top_depth, a.depth, mass, a.zero);
         valid = is_valid_transition(a.valid, idx);
       }
     }
@@ -127,8 +130,8 @@ __global__ void __launch_bounds__(1024) per_sample_kernel(PerSampleArgs a) {
                                               (uint64_t)a.batch + (uint64_t)r)
                            : a.retry_u01[r];
       // sum_tree.py:123-124: query = random.random() * total
-      idx = tree_descend_staged(a.heap, top, top_depth, a.depth,
-                                __dmul_rn(u, local_total));
+      idx = tree_descend_staged<K>(a.heap, top, top_depth, a.depth,
+                                   __dmul_rn(u, local_total), a.zero);
       valid = is_valid_transition(a.valid, idx);
     }
     int tile_valid;
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(1024) per_sample_kernel(PerSampleArgs a) {
         }
       }
     }
-    if (a.counter) *a.counter += 1;
+    if (a.counter) *a.counter = draws_before + 1;
     a.info[0] = status;
     a.info[1] = a.out_slots ? (status ? a.out_slots[fail_slot] : 0) : fail_slot;
     a.info[2] = used;
@@ -201,7 +204,8 @@ struct UniformSampleArgs {
 __global__ void __launch_bounds__(1024) uniform_sample_kernel(UniformSampleArgs a) {
   __shared__ int warp_counts[32];
   int accepted = a.counters[0], rejected = a.counters[1], used = 0;
-  const uint64_t draw_offset = a.offset + (a.counter ? *a.counter : 0ull);
+  const uint64_t draws_before = a.counter ? *a.counter : 0ull;
+  const uint64_t draw_offset = a.offset + draws_before;
   __syncthreads();
   const int64_t span = a.max_id - a.min_id;
   int base = 0;
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(1024) uniform_sample_kernel(UniformSampleArgs 
     a.counters[0] = accepted;
     a.counters[1] = rejected;
     a.counters[2] = used;
-    if (a.counter) *a.counter += 1;
+    if (a.counter) *a.counter = draws_before + 1;
     if (a.use_philox && accepted < a.batch && a.latched && a.latched[0] == 0) {
       a.latched[0] = B2R_ERR_SAMPLE_ATTEMPTS;
       a.latched[1] = accepted;
@@ -294,6 +298,7 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   a.seed = seed;
   a.offset = offset;
   a.counter = philox ? b->draw_counter : nullptr;
+  a.zero = 0;
   a.strat_query01 = strat_dev;
   a.retry_u01 = retry_dev;
   a.out_idx = out_idx_dev;
@@ -304,10 +309,15 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   a.rank = 0;
   a.shard_totals = nullptr;
   a.out_slots = nullptr;
-  // At least 128 threads so staging the top levels is one pass of wide loads.
+  // At least 128 threads: staging the top levels is then one round of loads.
   int threads = sample_threads(batch);
   if (threads < 128) threads = 128;
-  per_sample_kernel<<<1, threads, 0, stream>>>(a);
+  // Small batches are latency-bound: 5 tree levels per memory round trip; large
+  // ones have enough loads in flight already.
+  if (batch <= 256)
+    per_sample_kernel<5, 256><<<1, threads, 0, stream>>>(a);
+  else
+    per_sample_kernel<3, 1024><<<1, threads, 0, stream>>>(a);
   B2R_LAUNCHED();
   return B2R_OK;
 }
@@ -461,6 +471,7 @@ int b2r_sample_indices_sharded_device(b2r_buffer *b, int32_t global_batch,
   a.use_philox = 0;
   a.seed = a.offset = 0;
   a.counter = nullptr;
+  a.zero = 0;
   a.strat_query01 = query01;
   a.retry_u01 = retry_u01;
   a.out_idx = out_indices;
@@ -473,7 +484,10 @@ int b2r_sample_indices_sharded_device(b2r_buffer *b, int32_t global_batch,
   a.out_slots = out_slots;
   int threads = b2r::sample_threads(global_batch);
   if (threads < 128) threads = 128;
-  b2r::per_sample_kernel<<<1, threads, 0, s>>>(a);
+  if (global_batch <= 256)
+    b2r::per_sample_kernel<5, 256><<<1, threads, 0, s>>>(a);
+  else
+    b2r::per_sample_kernel<3, 1024><<<1, threads, 0, s>>>(a);
   B2R_LAUNCHED();
   if (out_count)
     B2R_CUDA(cudaMemcpyAsync(out_count, b->info + 3, 4, cudaMemcpyDeviceToDevice, s));

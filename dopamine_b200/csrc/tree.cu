@@ -193,6 +193,160 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(UpdateArgs<I, V> a) {
   }
 }
 
+constexpr int kSmallBatch = 256;  // largest batch the single-CTA kernel takes
+
+// Warp-level bitonic sort of `padded` (<= 256) keys in shared memory.
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t *keys, int padded, int lane) {
+  for (int k = 2; k <= padded; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < padded; t += 32) {
+        const int partner = t ^ j;
+        if (partner > t) {
+          const uint64_t a = keys[t], b = keys[partner];
+          const bool ascending = (t & k) == 0;
+          if ((a > b) == ascending) {
+            keys[t] = b;
+            keys[partner] = a;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// Latency path for small batches (<= 256 sets: the agent's batch 32): ONE CTA,
+// one WARP per tree level, so the only synchronisation between the leaf pass and
+// the internal levels is a __syncthreads.  Each warp sorts its own (node, k) keys
+// with shuffled-free warp-synchronous bitonic steps while the leaf warp resolves
+// the leaf chains; internal warps prefetch their node values before the barrier.
+template <typename I, typename V>
+__global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V> a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int levels = a.depth + 1;
+  double *vals = reinterpret_cast<double *>(smem_raw);            // [padded] value -> delta
+  uint64_t *all_keys = reinterpret_cast<uint64_t *>(smem_raw) + a.padded;
+  uint64_t *keys = all_keys + (size_t)warp * a.padded;            // this level's keys
+  double *all_sorted = reinterpret_cast<double *>(all_keys + (size_t)levels * a.padded);
+  double *sorted_delta = all_sorted + (size_t)warp * a.padded;
+  __shared__ int s_stop, s_stop_code;
+
+  const int n = a.n;
+  const int64_t latched = a.status[0];
+  if (threadIdx.x == 0) {
+    s_stop = n;
+    s_stop_code = 0;
+  }
+  __syncthreads();
+  if (latched != 0) return;  // an earlier chunk failed: the sequence stopped there
+
+  if (a.mode != nullptr) {
+    if (threadIdx.x == 0) {
+      double running = *a.max_rec;
+      for (int k = 0; k < n; ++k) {
+        double v = a.mode[k] ? running : (double)a.values[k];
+        const int64_t idx = (int64_t)a.indices[k];
+        if (v < 0.0) { s_stop = k; s_stop_code = B2R_ERR_NEGATIVE_PRIORITY; break; }
+        if (idx < 0 || idx >= a.leaves) { s_stop = k; s_stop_code = B2R_ERR_INDEX_RANGE; break; }
+        if (v > running) running = v;
+        vals[k] = v;
+      }
+    }
+  } else {
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      const double v = (double)a.values[k];
+      const int64_t idx = (int64_t)a.indices[k];
+      vals[k] = v;
+      if (v < 0.0 || idx < 0 || idx >= a.leaves) atomicMin(&s_stop, k);
+    }
+  }
+  __syncthreads();
+  const int n_eff = s_stop;
+  if (a.mode == nullptr && n_eff < n && threadIdx.x == 0)
+    s_stop_code = (vals[n_eff] < 0.0) ? B2R_ERR_NEGATIVE_PRIORITY
+                                      : B2R_ERR_INDEX_RANGE;
+
+  const int level = warp;
+  const bool is_leaf = level == a.depth;
+  const int shift = a.depth - level;
+  int p2 = 32;
+  while (p2 < n_eff) p2 <<= 1;
+  for (int k = lane; k < p2; k += 32)
+    keys[k] = k < n_eff
+                  ? (((uint64_t)((int64_t)a.indices[k] >> shift)) << 32) | (uint32_t)k
+                  : kPadKey;
+  __syncwarp();
+  if (level != 0) warp_bitonic_sort(keys, p2, lane);
+
+  // Segment heads of this level and (internal levels) their node values, loaded
+  // before the barrier so the round trip overlaps the leaf pass.
+  const int64_t base = ((int64_t)1) << level;
+  constexpr int kHeadsPerLane = kSmallBatch / 32;
+  double node_value[kHeadsPerLane];
+#pragma unroll
+  for (int t = 0; t < kHeadsPerLane; ++t) {
+    const int p = lane + 32 * t;
+    node_value[t] = 0.0;
+    if (p < n_eff) {
+      const uint32_t node = (uint32_t)(keys[p] >> 32);
+      if (p == 0 || (uint32_t)(keys[p - 1] >> 32) != node)
+        node_value[t] = a.heap[base + node];
+    }
+  }
+
+  if (is_leaf) {
+    double local_max = 0.0;
+    for (int k = lane; k < n_eff; k += 32) local_max = fmax(local_max, vals[k]);
+    for (int off = 16; off > 0; off >>= 1)
+      local_max = fmax(local_max, __shfl_xor_sync(0xffffffffu, local_max, off));
+#pragma unroll
+    for (int t = 0; t < kHeadsPerLane; ++t) {
+      const int p = lane + 32 * t;
+      if (p >= n_eff) continue;
+      const uint32_t node = (uint32_t)(keys[p] >> 32);
+      if (p > 0 && (uint32_t)(keys[p - 1] >> 32) == node) continue;
+      double leaf = node_value[t];
+      for (int q = p; q < n_eff && (uint32_t)(keys[q] >> 32) == node; ++q) {
+        const uint32_t k = (uint32_t)keys[q];
+        const double d = __dsub_rn(vals[k], leaf);
+        leaf = __dadd_rn(leaf, d);
+        vals[k] = d;
+      }
+      a.heap[base + node] = leaf;
+    }
+    if (lane == 0) {
+      const double m = *a.max_rec;
+      if (n_eff > 0 && local_max > m) *a.max_rec = local_max;
+      if (n_eff < n) {
+        a.status[0] = s_stop_code;
+        a.status[1] = a.k_base + n_eff;
+      }
+    }
+  }
+  __syncthreads();  // deltas are in vals[]
+  if (is_leaf || warp >= levels) return;
+
+  for (int p = lane; p < n_eff; p += 32) sorted_delta[p] = vals[(uint32_t)keys[p]];
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < kHeadsPerLane; ++t) {
+    const int p = lane + 32 * t;
+    if (p >= n_eff) continue;
+    const uint32_t node = (uint32_t)(keys[p] >> 32);
+    if (p > 0 && (uint32_t)(keys[p - 1] >> 32) == node) continue;
+    int lo = p + 1, hi = n_eff;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((uint32_t)(keys[mid] >> 32) > node) hi = mid; else lo = mid + 1;
+    }
+    double acc = node_value[t];
+#pragma unroll 8
+    for (int q = p; q < lo; ++q) acc = __dadd_rn(acc, sorted_delta[q]);
+    a.heap[base + node] = acc;
+  }
+}
+
 __global__ void tree_get_kernel(const double *__restrict__ heap, int64_t leaves,
                                 int64_t n, const int64_t *__restrict__ indices,
                                 double *__restrict__ out) {
@@ -205,7 +359,7 @@ __global__ void tree_get_kernel(const double *__restrict__ heap, int64_t leaves,
 __global__ void tree_query_kernel(const double *__restrict__ heap, int depth,
                                   int64_t n, const double *__restrict__ query01,
                                   int64_t *__restrict__ out,
-                                  double *__restrict__ total_out) {
+                                  double *__restrict__ total_out, uint32_t zero) {
   extern __shared__ double top[];
   const int top_depth = stage_top_levels(heap, depth, top);
   const double total = top[1];
@@ -213,8 +367,8 @@ __global__ void tree_query_kernel(const double *__restrict__ heap, int depth,
   const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k >= n) return;
   // sum_tree.py:123-124: query_value *= total
-  out[k] = tree_descend_staged(heap, top, top_depth, depth,
-                               __dmul_rn(query01[k], total));
+  out[k] = tree_descend_staged<3>(heap, top, top_depth, depth,
+                               __dmul_rn(query01[k], total), zero);
 }
 
 __global__ void tree_set_scalar_kernel(double *dst, double v) { *dst = v; }
@@ -242,6 +396,35 @@ int allow_big_smem(K kernel) {
 template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
                const uint8_t *mode, cudaStream_t stream) {
+  if (n <= kSmallBatch) {
+    // latency path: one CTA, one warp per level
+    static bool small_ready = false;
+    const int padded = padded_size((int)n);
+    const size_t smem = (size_t)padded * 8 * (1 + 2 * (size_t)(t->depth + 1));
+    if (!small_ready) {
+      B2R_CUDA(cudaFuncSetAttribute(
+          tree_update_small_kernel<I, V>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          kSmallBatch * 8 * (1 + 2 * 32)));
+      small_ready = true;
+    }
+    UpdateArgs<I, V> a;
+    a.heap = t->heap;
+    a.depth = t->depth;
+    a.leaves = t->leaves;
+    a.n = (int)n;
+    a.padded = padded;
+    a.indices = indices;
+    a.values = values;
+    a.mode = mode;
+    a.k_base = 0;
+    a.delta = t->delta;
+    a.max_rec = t->max_rec;
+    a.status = t->status;
+    tree_update_small_kernel<I, V><<<1, 32 * (t->depth + 1), smem, stream>>>(a);
+    B2R_LAUNCHED();
+    return B2R_OK;
+  }
   B2R_TRY(allow_big_smem(tree_update_kernel<I, V>));
   for (int64_t base = 0; base < n; base += kTreeChunk) {
     const int len = (int)((n - base) < kTreeChunk ? (n - base) : kTreeChunk);
@@ -445,7 +628,7 @@ int b2r_tree_sample(b2r_tree *t, int64_t n, const double *query01, int64_t *out,
   const size_t smem = ((size_t)2 << b2r::kTopLevels) * 8;
   b2r::tree_query_kernel<<<(unsigned)((n + 255) / 256), 256, smem, s>>>(
       t->heap, t->depth, n, reinterpret_cast<const double *>(t->bounce.dev),
-      dout, dtotal);
+      dout, dtotal, 0u);
   B2R_LAUNCHED();
   B2R_CUDA(cudaMemcpyAsync(t->bounce.host + (size_t)n * 8, dout,
                            (size_t)n * 8 + 8, cudaMemcpyDeviceToHost, s));

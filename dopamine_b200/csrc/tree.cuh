@@ -36,39 +36,140 @@ __device__ __forceinline__ void descend_step(int64_t &h, double &q, double left)
   }
 }
 
+// K levels in ONE memory round trip: the left-child values of the next K levels
+// (1 + 2 + ... + 2^(K-1) candidates; the 1-based layout keeps each level's
+// candidates inside 2^(K-d) adjacent 32-byte sectors) are fetched together, then the
+// K decisions are taken one after the other exactly as the reference takes them.
+// Candidates are picked with unrolled selects, so everything stays in registers.
+template <int COUNT>
+__device__ __forceinline__ double select_candidate(const double (&c)[COUNT], int w) {
+  double r = c[0];
+#pragma unroll
+  for (int j = 1; j < COUNT; ++j) r = (w == j) ? c[j] : r;
+  return r;
+}
+
+// Loads issued through volatile asm keep their program order and cannot be sunk
+// below the selects by the compiler, which is the whole point: all candidates of a
+// round are in flight before the first decision is taken.
+struct GlobalNodes {
+  const double *base;
+  __device__ __forceinline__ double operator()(int64_t h) const {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(base + h));
+    return v;
+  }
+};
+struct SharedNodes {
+  uint32_t base;  // shared-space address of element 0
+  __device__ __forceinline__ double operator()(int64_t h) const {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + (uint32_t)h * 8u));
+    return v;
+  }
+};
+
+__device__ __forceinline__ uint32_t low_bits(double v) {
+  return (uint32_t)__double2loint(v);
+}
+
+// `zero` is a run-time 0 the compiler cannot see through: q is made to depend on the
+// bits of every candidate (q.lo ^= xor(all) & zero), so neither nvcc nor ptxas can
+// take the first decision - and stall the in-order issue - before all loads of the
+// round have been issued.
+template <int K, typename Nodes>
+__device__ __forceinline__ void descend_levels(const Nodes &nodes, int64_t &h,
+                                               double &q, uint32_t zero) {
+  static_assert(K >= 1 && K <= 5, "K levels per round trip");
+  const int64_t h0 = h;
+  const double c1 = nodes(2 * h0);
+  double c2[2], c3[4], c4[8], c5[16];
+  if (K >= 2) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) c2[j] = nodes(4 * h0 + 2 * j);
+  }
+  if (K >= 3) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c3[j] = nodes(8 * h0 + 2 * j);
+  }
+  if (K >= 4) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c4[j] = nodes(16 * h0 + 2 * j);
+  }
+  if (K >= 5) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) c5[j] = nodes(32 * h0 + 2 * j);
+  }
+  if (K >= 3) {
+    uint32_t g = low_bits(c1);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) g ^= low_bits(c2[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) g ^= low_bits(c3[j]);
+    if (K >= 4) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g ^= low_bits(c4[j]);
+    }
+    if (K >= 5) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) g ^= low_bits(c5[j]);
+    }
+    q = __hiloint2double(__double2hiint(q), __double2loint(q) ^ (int)(g & zero));
+  }
+  descend_step(h, q, c1);
+  if (K >= 2) descend_step(h, q, select_candidate<2>(c2, (int)(h - 2 * h0)));
+  if (K >= 3) descend_step(h, q, select_candidate<4>(c3, (int)(h - 4 * h0)));
+  if (K >= 4) descend_step(h, q, select_candidate<8>(c4, (int)(h - 8 * h0)));
+  if (K >= 5) descend_step(h, q, select_candidate<16>(c5, (int)(h - 16 * h0)));
+}
+
+template <int K, typename Nodes>
+__device__ __forceinline__ void descend_span(const Nodes &nodes, int64_t &h,
+                                             double &q, int levels, uint32_t zero) {
+  while (levels >= K) {
+    descend_levels<K>(nodes, h, q, zero);
+    levels -= K;
+  }
+  if (K > 4 && levels == 4) { descend_levels<4>(nodes, h, q, zero); levels = 0; }
+  if (K > 3 && levels == 3) { descend_levels<3>(nodes, h, q, zero); levels = 0; }
+  if (K > 2 && levels == 2) { descend_levels<2>(nodes, h, q, zero); levels = 0; }
+  if (K > 1 && levels == 1) { descend_levels<1>(nodes, h, q, zero); levels = 0; }
+}
+
 // Root-to-leaf descent (sum_tree.py:126-141).  `top` is a shared-memory copy of
-// heap[0 .. 2^(top_depth+1)).  Below it, the dependent chain of loads is cut by 3:
-// the left-child values of the next three levels (1 + 2 + 4 candidates, three
-// sectors thanks to the 1-based layout) are fetched in ONE round trip and the
-// three decisions are then taken exactly as the reference takes them.
+// heap[0 .. 2^(top_depth+1)): those levels are walked two per shared-memory round
+// trip, the rest K per global-memory round trip.
+template <int K>
 __device__ __forceinline__ int64_t tree_descend_staged(
     const double *__restrict__ heap, const double *top, int top_depth, int depth,
-    double q) {
+    double q, uint32_t zero) {
   int64_t h = 1;
-  int level = 0;
-  for (; level < top_depth; ++level) descend_step(h, q, top[2 * h]);
-  while (depth - level >= 3) {
-    const double c1 = heap[2 * h];
-    const double c2a = heap[4 * h], c2b = heap[4 * h + 2];
-    const double c3a = heap[8 * h], c3b = heap[8 * h + 2];
-    const double c3c = heap[8 * h + 4], c3d = heap[8 * h + 6];
-    const int64_t h0 = h;
-    descend_step(h, q, c1);
-    descend_step(h, q, (h == 2 * h0) ? c2a : c2b);
-    const int which = (int)(h - 4 * h0);
-    descend_step(h, q, which == 0 ? c3a : which == 1 ? c3b : which == 2 ? c3c : c3d);
-    level += 3;
-  }
-  for (; level < depth; ++level) descend_step(h, q, heap[2 * h]);
+  const SharedNodes staged{(uint32_t)__cvta_generic_to_shared(top)};
+  const GlobalNodes global{heap};
+  descend_span<2>(staged, h, q, top_depth, zero);
+  descend_span<K>(global, h, q, depth - top_depth, zero);
   return h - (((int64_t)1) << depth);
 }
 
-// Cooperative copy of heap[0 .. 2^(min(depth, kTopLevels)+1)) into shared memory.
+// Cooperative copy of heap[0 .. 2^(min(depth, kTopLevels)+1)) into shared memory:
+// every thread issues all of its loads before the first store, so staging costs one
+// memory round trip (needs blockDim.x >= 128).
 __device__ __forceinline__ int stage_top_levels(const double *__restrict__ heap,
                                                 int depth, double *top) {
   const int top_depth = depth < kTopLevels ? depth : kTopLevels;
   const int count = 2 << top_depth;
-  for (int i = threadIdx.x; i < count; i += blockDim.x) top[i] = heap[i];
+  constexpr int kPerThread = (2 << kTopLevels) / 128;
+  double r[kPerThread];
+#pragma unroll
+  for (int j = 0; j < kPerThread; ++j) {
+    const int i = threadIdx.x + j * blockDim.x;
+    r[j] = i < count ? heap[i] : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < kPerThread; ++j) {
+    const int i = threadIdx.x + j * blockDim.x;
+    if (i < count) top[i] = r[j];
+  }
   __syncthreads();
   return top_depth;
 }
