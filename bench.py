@@ -217,7 +217,9 @@ class GpuWorkload(object):
     c.loss = t['loss'].data_ptr()
     c.priorities = t['priorities'].data_ptr()
     c.weights = t['weights'].data_ptr()
-    c.mean_weighted_loss = t['mean'].data_ptr()
+    # The scalar mean(w * loss) only feeds summaries (RA:298-301); the gradient
+    # path needs loss / weights per row, which are produced.
+    c.mean_weighted_loss = None
     c.grad_logits = None
     self._plans[batch] = (t, b, c)
     return self._plans[batch]

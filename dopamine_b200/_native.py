@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, 'libb200replay.so')
+# B2R_LIB lets the profiling scripts load an instrumented build of the same library.
+LIB_PATH = os.environ.get('B2R_LIB') or os.path.join(_PKG, 'libb200replay.so')
 
 MAX_EXTRAS = 8
 OK = 0

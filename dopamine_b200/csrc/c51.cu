@@ -16,13 +16,17 @@
 namespace b2r {
 namespace {
 
+B2R_TRACE_DECL
+
 constexpr int kWarpsPerBlock = 4;
 
 __device__ __forceinline__ float warp_max(float v) {
+#pragma unroll 1
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 __device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll 1
   for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
@@ -84,6 +88,9 @@ struct LossArgs {
 //      order for mean_weighted_loss (RA:293, 305).
 constexpr int kMaxAtomsPerLane = 4;  // num_atoms <= 128
 
+// PL = atoms per lane (2 covers C51's 51 atoms; fewer unrolled copies = less
+// straight-line code to fetch on a cold instruction cache).
+template <int PL>
 __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,6 +108,10 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   __shared__ float s_scalar[4];  // tsum, w_b, m, denom
   __shared__ bool s_last;
   const float *z = a.u.support;
+  B2R_MARK(0);
+  pdl_release();
+  pdl_acquire();
+  B2R_MARK(1);
 
   // ---- every global load the row needs is issued here, before the first use:
   // the kernel is latency-bound at batch 32 and this keeps it to one round trip.
@@ -112,10 +123,10 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   if (a.u.sampling_probabilities)
     for (int k = threadIdx.x; k < a.u.batch; k += blockDim.x)
       pmin = fminf(pmin, a.u.sampling_probabilities[k]);
-  float zl[kMaxAtomsPerLane], xt[kMaxAtomsPerLane], xo[kMaxAtomsPerLane];
+  float zl[PL], xt[PL], xo[PL];
   const int act0 = warp;  // first (usually only) action of this warp
 #pragma unroll
-  for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+  for (int t = 0; t < PL; ++t) {
     const int i = lane + 32 * t;
     const bool ok = i < N && act0 < A;
     zl[t] = i < N ? z[i] : 0.f;
@@ -123,13 +134,14 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
     xo[t] = ok ? a.u.online_logits[((size_t)b * A + act0) * N + i] : 0.f;
   }
 
+  B2R_MARK(2);
   // ---- A. per-action softmax + q-value (atari_lib.py:141-143)
   float best_q = 0.f;
   int best_a = -1;
   for (int act = warp; act < A; act += W) {
     if (act != act0) {  // more actions than warps: later rounds load as they go
 #pragma unroll
-      for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+      for (int t = 0; t < PL; ++t) {
         const int i = lane + 32 * t;
         xt[t] = i < N ? a.u.target_logits[((size_t)b * A + act) * N + i] : -INFINITY;
         xo[t] = i < N ? a.u.online_logits[((size_t)b * A + act) * N + i] : 0.f;
@@ -137,17 +149,17 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
     }
     if (act == chosen) {
 #pragma unroll
-      for (int t = 0; t < kMaxAtomsPerLane; ++t)
+      for (int t = 0; t < PL; ++t)
         if (lane + 32 * t < N) onl[lane + 32 * t] = xo[t];
     }
     float m = -INFINITY;
 #pragma unroll
-    for (int t = 0; t < kMaxAtomsPerLane; ++t) m = fmaxf(m, xt[t]);
+    for (int t = 0; t < PL; ++t) m = fmaxf(m, xt[t]);
     m = warp_max(m);
-    float e[kMaxAtomsPerLane];
+    float e[PL];
     float psum = 0.f;
 #pragma unroll
-    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+    for (int t = 0; t < PL; ++t) {
       const bool ok = lane + 32 * t < N;
       e[t] = ok ? expf(__fsub_rn(xt[t], m)) : 0.f;
       if (ok) psum = __fadd_rn(psum, e[t]);
@@ -155,7 +167,7 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
     const float denom = warp_sum(psum);
     float qpart = 0.f;
 #pragma unroll
-    for (int t = 0; t < kMaxAtomsPerLane; ++t) {
+    for (int t = 0; t < PL; ++t) {
       if (lane + 32 * t < N) {
         e[t] = __fdiv_rn(e[t], denom);
         qpart = __fadd_rn(qpart, __fmul_rn(zl[t], e[t]));
@@ -166,11 +178,12 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
       best_q = q;
       best_a = act;
 #pragma unroll
-      for (int t = 0; t < kMaxAtomsPerLane; ++t)
+      for (int t = 0; t < PL; ++t)
         if (lane + 32 * t < N) bestp[lane + 32 * t] = e[t];
     }
   }
   (void)cur;
+  B2R_MARK(3);
   if (lane == 0) {
     s_q[warp] = best_q;
     s_a[warp] = best_a;
@@ -188,8 +201,10 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
     sup[j] = __fadd_rn(r, __fmul_rn(gwt, z[j]));
   __syncthreads();
 
+  B2R_MARK(4);
   // ---- B. argmax action (first maximum, RA:238-248), projection (RA:381-494)
   int win = 0;
+#pragma unroll 1
   for (int w = 1; w < W; ++w) {
     if (s_a[w] < 0) continue;
     if (s_q[w] > s_q[win] || (s_q[w] == s_q[win] && s_a[w] < s_a[win])) win = w;
@@ -198,11 +213,13 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   const float z0 = z[0], zlast = z[N - 1];
   const float dz = __fsub_rn(z[1], z[0]);
   const int per = (N + a.parts - 1) / a.parts;
+#pragma unroll 1
   for (int t = threadIdx.x; t < a.parts * N; t += blockDim.x) {
     const int i = t % N, pt = t / N;
     const int j0 = pt * per, j1 = min(N, j0 + per);
     const float zi = z[i];
     float acc = 0.f;
+#pragma unroll 1
     for (int j = j0; j < j1; ++j) {
       const float clipped = fminf(fmaxf(sup[j], z0), zlast);
       const float gap = fabsf(__fsub_rn(clipped, zi));
@@ -214,19 +231,24 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   }
   __syncthreads();
 
+  B2R_MARK(5);
   // ---- C. cross entropy (RA:262-271), priority (RA:290), weight (RA:279-280)
   const float *x = onl;
   if (warp == 0) {
     float m = -INFINITY;
+#pragma unroll 1
     for (int i = lane; i < N; i += 32) m = fmaxf(m, x[i]);
     m = warp_max(m);
     float psum = 0.f;
+#pragma unroll 1
     for (int i = lane; i < N; i += 32) psum = __fadd_rn(psum, expf(__fsub_rn(x[i], m)));
     const float denom = warp_sum(psum);
     const float lse = logf(denom);
     float ce_part = 0.f, tsum_part = 0.f;
+#pragma unroll 1
     for (int i = lane; i < N; i += 32) {
       float t = part[i];
+#pragma unroll 1
       for (int pt = 1; pt < a.parts; ++pt) t = __fadd_rn(t, part[(size_t)pt * N + i]);
       tgt[i] = t;
       if (a.u.target) a.u.target[(size_t)b * N + i] = t;
@@ -240,6 +262,7 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
       float w = 1.f;
       if (a.u.sampling_probabilities) {
         float mn = s_red[0];
+#pragma unroll 1
         for (int k = 1; k < (int)(blockDim.x >> 5); ++k) mn = fminf(mn, s_red[k]);
         const float wmax = __fdiv_rn(1.0f, sqrtf(__fadd_rn(mn, 1e-10f)));
         const float raw = __fdiv_rn(1.0f, sqrtf(__fadd_rn(my_prob, 1e-10f)));
@@ -257,6 +280,7 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   }
   __syncthreads();
 
+  B2R_MARK(6);
   // ---- D. gradient of mean(w * ce) w.r.t. the online logits
   if (a.u.grad_logits) {
     const float tsum = s_scalar[0], w = s_scalar[1], m = s_scalar[2], denom = s_scalar[3];
@@ -273,6 +297,7 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
     }
   }
 
+  B2R_MARK(7);
   // ---- mean weighted loss: the last CTA to finish reduces in a fixed order.
   if (a.u.mean_weighted_loss == nullptr) return;
   __threadfence();
@@ -336,7 +361,10 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
   cudaStream_t s = as_stream(stream);
   b2r::LossArgs a;
   a.u = *args;
+  // Small batches are latency-bound: one warp per action.  Large batches are
+  // throughput-bound: a third of that, so more rows are resident per SM.
   a.warps = args->num_actions < 32 ? args->num_actions : 32;
+  if (args->batch > 256) a.warps = (a.warps + 2) / 3;
   const int threads = a.warps * 32;
   a.parts = threads / args->num_atoms;
   if (a.parts < 1) a.parts = 1;
@@ -359,9 +387,20 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
   }
   a.weighted = b2r::g_weighted;
   a.ticket = b2r::g_ticket;
-  b2r::c51_loss_kernel<<<args->batch, threads, smem, s>>>(a);
+  if (args->num_atoms <= 64)
+    B2R_CUDA(b2r::launch(b2r::c51_loss_kernel<2>, dim3(args->batch), dim3(threads),
+                         smem, s, a));
+  else
+    B2R_CUDA(b2r::launch(b2r::c51_loss_kernel<4>, dim3(args->batch), dim3(threads),
+                         smem, s, a));
   B2R_LAUNCHED();
   return B2R_OK;
 }
 
 }  // extern "C"
+
+#ifdef B2R_TRACE
+extern "C" int b2r_debug_trace_c51(long long *out) {
+  return (int)cudaMemcpyFromSymbol(out, b2r::g_trace, sizeof(long long) * 32);
+}
+#endif

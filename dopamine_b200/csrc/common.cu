@@ -1,9 +1,16 @@
 // Error plumbing and the pinned bounce buffer.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace b2r {
 
 std::atomic<int64_t> g_launches{0};
+
+bool pdl_enabled() {
+  static const bool on = std::getenv("B2R_NO_PDL") == nullptr;
+  return on;
+}
 
 std::string &last_error_slot() {
   static thread_local std::string slot;

@@ -53,6 +53,52 @@ struct Bounce {
   void release();
 };
 
+// ---- programmatic dependent launch ---------------------------------------------
+// The hot-path kernels of one step form a dependent chain of short launches; each
+// is launched with programmatic stream serialization so that its launch latency
+// overlaps the tail of its predecessor: a kernel lets its successor start
+// launching right away (pdl_release) and touches global memory only after its
+// own predecessor has completed and flushed (pdl_acquire).
+bool pdl_enabled();
+
+template <typename... Params, typename... Args>
+cudaError_t launch(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem,
+                   cudaStream_t stream, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
+__device__ __forceinline__ void pdl_release() {
+  asm volatile("griddepcontrol.launch_dependents;");
+}
+__device__ __forceinline__ void pdl_acquire() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ---- optional phase tracing (build with -DB2R_TRACE; never in the shipped .so) ---
+#ifdef B2R_TRACE
+#define B2R_TRACE_DECL static __device__ long long g_trace[32];
+#define B2R_MARK(i)                                              \
+  do {                                                           \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)  \
+      g_trace[i] = clock64();                                    \
+  } while (0)
+#else
+#define B2R_TRACE_DECL
+#define B2R_MARK(i) \
+  do {              \
+  } while (0)
+#endif
+
 // ---- device helpers ----------------------------------------------------------
 __device__ __forceinline__ int64_t wrap_index(int64_t i, int64_t cap) {
   int64_t r = i % cap;
@@ -64,7 +110,9 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
                                               uint32_t c2, uint32_t c3,
                                               uint32_t k0, uint32_t k1,
                                               uint32_t out[4]) {
-#pragma unroll
+  // Rolled on purpose: these kernels run once per launch on a cold instruction
+  // cache, where every extra 128-byte line of straight-line code costs an L2 trip.
+#pragma unroll 1
   for (int r = 0; r < 10; ++r) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;

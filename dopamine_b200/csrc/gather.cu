@@ -22,6 +22,8 @@
 namespace b2r {
 namespace {
 
+B2R_TRACE_DECL
+
 constexpr int kMaxRowCopies = 3 + B2R_MAX_EXTRAS;
 
 struct RowCopy {
@@ -90,7 +92,7 @@ __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, 
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 
 template <typename R>
-__device__ R nstep_return(const R *__restrict__ reward,
+__device__ __forceinline__ R nstep_return(const R *__restrict__ reward,
                           const float *__restrict__ disc, int64_t i, int length,
                           int64_t cap) {
   auto term = [&](int k) {
@@ -100,6 +102,7 @@ __device__ R nstep_return(const R *__restrict__ reward,
   };
   if (length < 8) {
     R acc = (R)0;
+#pragma unroll 1
     for (int k = 0; k < length; ++k) acc = add_rn(acc, term(k));
     return acc;
   }
@@ -107,6 +110,7 @@ __device__ R nstep_return(const R *__restrict__ reward,
 #pragma unroll
   for (int j = 0; j < 8; ++j) r[j] = term(j);
   int k = 8;
+#pragma unroll 1
   for (; k < length - (length % 8); k += 8) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) r[j] = add_rn(r[j], term(k + j));
@@ -117,33 +121,41 @@ __device__ R nstep_return(const R *__restrict__ reward,
   return acc;
 }
 
-// Scalar outputs of one transition; run by one warp (lane-strided byte copies).
-__device__ void write_scalars(const GatherArgs &a, int b, int64_t i, int length,
-                              bool ends, int lane) {
+// Scalar outputs: one THREAD per transition, in extra CTAs appended to the grid
+// (rows blockIdx.y >= batch), so they run beside the frame copies and every
+// transition's loads are in flight at once.
+__device__ void write_scalars(const GatherArgs &a, int b) {
+  const int64_t i = a.indices[b];
+  bool ends;
+  const int length = trajectory_length(a.term_flag, i, a.horizon, a.capacity, &ends);
   int64_t nxt = i + length;
   if (nxt >= a.capacity) nxt -= a.capacity;
-  if (lane == 0) {
-    if (a.ret) {
-      if (a.reward_itemsize == 4)
-        static_cast<float *>(a.ret)[b] = nstep_return<float>(
-            static_cast<const float *>(a.reward), a.discounts, i, length, a.capacity);
-      else
-        static_cast<double *>(a.ret)[b] = nstep_return<double>(
-            static_cast<const double *>(a.reward), a.discounts, i, length, a.capacity);
-    }
-    if (a.terminal_out) {
-      uint8_t *t = a.terminal_out + (int64_t)b * a.terminal_itemsize;
-      t[0] = ends ? 1 : 0;
-      for (int k = 1; k < a.terminal_itemsize; ++k) t[k] = 0;
-    }
-    if (a.indices_out) a.indices_out[b] = (int32_t)i;
-    if (a.prio_out) a.prio_out[b] = (float)a.leaves[i];  // PRB:231-235
+  if (a.ret) {
+    if (a.reward_itemsize == 4)
+      static_cast<float *>(a.ret)[b] = nstep_return<float>(
+          static_cast<const float *>(a.reward), a.discounts, i, length, a.capacity);
+    else
+      static_cast<double *>(a.ret)[b] = nstep_return<double>(
+          static_cast<const double *>(a.reward), a.discounts, i, length, a.capacity);
   }
+  if (a.prio_out) a.prio_out[b] = (float)a.leaves[i];  // PRB:231-235
+  if (a.indices_out) a.indices_out[b] = (int32_t)i;
+  if (a.terminal_out) {
+    uint8_t *t = a.terminal_out + (int64_t)b * a.terminal_itemsize;
+    t[0] = ends ? 1 : 0;
+    for (int k = 1; k < a.terminal_itemsize; ++k) t[k] = 0;
+  }
+#pragma unroll 1
   for (int c = 0; c < a.n_copies; ++c) {
     const RowCopy rc = a.copies[c];
     const uint8_t *s = rc.src + (rc.at_next ? nxt : i) * (int64_t)rc.row_bytes;
     uint8_t *d = rc.dst + (int64_t)b * rc.row_bytes;
-    for (int k = lane; k < rc.row_bytes; k += 32) d[k] = s[k];
+    if ((rc.row_bytes & 3) == 0) {  // word rows (int32 actions, f32 rewards, ...)
+      for (int k = 0; k < rc.row_bytes; k += 4)
+        *reinterpret_cast<uint32_t *>(d + k) = *reinterpret_cast<const uint32_t *>(s + k);
+    } else {
+      for (int k = 0; k < rc.row_bytes; ++k) d[k] = s[k];
+    }
   }
 }
 
@@ -183,12 +195,21 @@ __device__ __forceinline__ uint4 load_frame16(const uint8_t *__restrict__ obs,
 // Fast path: stack 4, 1-byte pixels, obs_bytes % 16 == 0.
 // grid = (ceil(chunks / blockDim), batch); thread = one 16-pixel column.
 __global__ void __launch_bounds__(128) gather_stack4_u8_kernel(GatherArgs a) {
+  B2R_MARK(0);
+  pdl_release();
+  pdl_acquire();
+  B2R_MARK(1);
+  if (blockIdx.y >= a.batch) {  // appended scalar CTAs: one thread per transition
+    const int b = ((blockIdx.y - a.batch) * gridDim.x + blockIdx.x) * blockDim.x +
+                  threadIdx.x;
+    if (b < a.batch) write_scalars(a, b);
+    return;
+  }
   const int b = blockIdx.y;
   const int64_t i = a.indices[b];
   bool ends;
   const int length = trajectory_length(a.term_flag, i, a.horizon, a.capacity, &ends);
-  if (blockIdx.x == 0 && threadIdx.x < 32)
-    write_scalars(a, b, i, length, ends, threadIdx.x);
+  B2R_MARK(2);
 
   const int chunks = (int)(a.obs_bytes >> 4);
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,18 +242,26 @@ __global__ void __launch_bounds__(128) gather_stack4_u8_kernel(GatherArgs a) {
     n3 = load_frame16(a.obs, j, a.capacity, a.obs_bytes, c);
   }
   const int64_t out_off = (int64_t)b * a.obs_bytes * 4 + (int64_t)c * 64;
+  B2R_MARK(4);
   if (a.state) store_stack16(a.state + out_off, s0, s1, s2, s3);
   if (a.next_state) store_stack16(a.next_state + out_off, n0, n1, n2, n3);
+  B2R_MARK(5);
 }
 
 // General path: any stack size / element size. thread = one observation element.
 __global__ void __launch_bounds__(256) gather_generic_kernel(GatherArgs a) {
+  pdl_release();
+  pdl_acquire();
+  if (blockIdx.y >= a.batch) {  // appended scalar CTAs: one thread per transition
+    const int b = ((blockIdx.y - a.batch) * gridDim.x + blockIdx.x) * blockDim.x +
+                  threadIdx.x;
+    if (b < a.batch) write_scalars(a, b);
+    return;
+  }
   const int b = blockIdx.y;
   const int64_t i = a.indices[b];
   bool ends;
   const int length = trajectory_length(a.term_flag, i, a.horizon, a.capacity, &ends);
-  if (blockIdx.x == 0 && threadIdx.x < 32)
-    write_scalars(a, b, i, length, ends, threadIdx.x);
 
   const int es = a.obs_itemsize;
   const int64_t elems = a.obs_bytes / es;
@@ -306,14 +335,16 @@ int launch_gather(b2r_buffer *b, int32_t batch, const int32_t *indices_dev,
   const bool fast = a.stack == 4 && a.obs_itemsize == 1 && (a.obs_bytes & 15) == 0;
   if (fast) {
     const int chunks = (int)(a.obs_bytes >> 4);
-    dim3 grid((chunks + 127) / 128, batch);
-    gather_stack4_u8_kernel<<<grid, 128, 0, stream>>>(a);
+    const int nx = (chunks + 127) / 128;
+    // + rows of scalar CTAs (one thread per transition)
+    dim3 grid(nx, batch + (batch + nx * 128 - 1) / (nx * 128));
+    B2R_CUDA(launch(gather_stack4_u8_kernel, grid, dim3(128), 0, stream, a));
   } else {
     const int64_t elems = a.obs_bytes / a.obs_itemsize;
     int gx = (int)((elems + 255) / 256);
     if (gx > 32) gx = 32;
-    dim3 grid(gx, batch);
-    gather_generic_kernel<<<grid, 256, 0, stream>>>(a);
+    dim3 grid(gx, batch + (batch + gx * 256 - 1) / (gx * 256));  // + scalar CTAs
+    B2R_CUDA(launch(gather_generic_kernel, grid, dim3(256), 0, stream, a));
   }
   B2R_LAUNCHED();
   return B2R_OK;
@@ -445,3 +476,9 @@ int b2r_get_priority(b2r_buffer *b, int64_t n, const int32_t *indices, float *ou
 }
 
 }  // extern "C"
+
+#ifdef B2R_TRACE
+extern "C" int b2r_debug_trace_gather(long long *out) {
+  return (int)cudaMemcpyFromSymbol(out, b2r::g_trace, sizeof(long long) * 32);
+}
+#endif

@@ -34,6 +34,7 @@ __device__ __forceinline__ bool is_valid_transition(const ValidCtx &c,
   // get_terminal_stack(index)[:-1].any(): all flags are loaded before any is
   // tested, so the check costs one memory round trip.
   unsigned any = 0;
+#pragma unroll 4
   for (int k = 1; k < c.stack; ++k) {
     int64_t s = index - k;
     if (s < 0) s += c.capacity;
@@ -107,6 +108,7 @@ struct b2r_buffer {
   int64_t inv_slots_cap = 0;
   int32_t *info = nullptr;      // device [4]: status, fail slot, draws used, count
   int64_t *status = nullptr;    // device [2]: latched asynchronous error
+  unsigned int *ticket = nullptr;   // device: last-CTA election of the sample kernel
   uint64_t *draw_counter = nullptr;  // device: bumps per Philox sample launch, so a
                                      // replayed CUDA graph draws fresh uniforms
   b2r::Bounce bounce;           // HOST-array calls

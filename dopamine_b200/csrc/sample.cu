@@ -14,6 +14,10 @@
 namespace b2r {
 namespace {
 
+B2R_TRACE_DECL
+
+constexpr int kMaxTiles = 2048;  // batch / tile size (>= 32 strata per tile)
+
 struct PerSampleArgs {
   const double *heap;
   int depth;
@@ -29,7 +33,9 @@ struct PerSampleArgs {
   const double *retry_u01;      // [max_attempts]
   // outputs
   int32_t *out_idx;
-  int32_t *inv_slots;  // scratch [batch]
+  int32_t *inv_slots;  // scratch [n_tiles * tile_size]: per-tile invalid slots
+  int32_t *tile_counts;        // scratch [n_tiles]
+  unsigned int *ticket;        // scratch: CTAs finished (self-resetting)
   int32_t *info;       // [0] status, [1] fail slot, [2] retry draws used, [3] count
   int64_t *latched;    // nullable: asynchronous error latch
   // sharding (num_shards == 1: plain buffer)
@@ -38,15 +44,36 @@ struct PerSampleArgs {
   int32_t *out_slots;  // nullable
 };
 
+// Slot of the ord-th invalid stratum: the per-tile lists are concatenated in tile
+// order (tile_start[] is the exclusive prefix of the per-tile counts).
+__device__ __forceinline__ int invalid_slot(const PerSampleArgs &a, const int *tile_start,
+                                            int n_tiles, int tile_size, int ord) {
+  int t = 0;
+  while (t + 1 < n_tiles && tile_start[t + 1] <= ord) ++t;
+  return a.inv_slots[(size_t)t * tile_size + (ord - tile_start[t])];
+}
+
+// grid = 1 CTA (small batches, sharded sampling) or one CTA per tile of blockDim
+// strata (large batches).  The stratified picks are independent; what the
+// reference does sequentially — the j-th invalid slot takes the j-th valid retry
+// draw out of a shared budget — is done by the last CTA to finish, on per-tile
+// ordered lists of invalid slots, with block-wide prefix scans over windows of
+// retry draws evaluated speculatively in parallel.
 template <int K, int MAX_THREADS>
 __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a) {
   __shared__ double top[2 << kTopLevels];
   __shared__ int warp_counts[32];
-  __shared__ int s_draws_used, s_last_idx, s_last_valid;
+  __shared__ int s_draws_used, s_last_idx, s_last_valid, s_is_last;
+  __shared__ int tile_start[kMaxTiles + 1];
 
+  B2R_MARK(0);
+  pdl_release();
+  pdl_acquire();
+  B2R_MARK(1);
   const uint64_t draws_before = a.counter ? *a.counter : 0ull;
   const uint64_t draw_offset = a.offset + draws_before;
   const int top_depth = stage_top_levels(a.heap, a.depth, top);
+  B2R_MARK(2);
   const double local_total = top[1];  // root of the 1-based heap
   // Mass the strata are spread over: the root, or all shards' roots summed in
   // rank order (fp64, left to right).
@@ -57,8 +84,8 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
       grand_total = __dadd_rn(grand_total, a.shard_totals[g]);
   }
   if (grand_total == 0.0 || (a.num_shards == 1 && local_total == 0.0)) {
-    // sum_tree.py:159-160
-    if (threadIdx.x == 0) {
+    // sum_tree.py:159-160 (every CTA takes this branch together)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
       a.info[0] = B2R_ERR_EMPTY_TREE;
       a.info[1] = 0; a.info[2] = 0; a.info[3] = 0;
       if (a.latched && a.latched[0] == 0) a.latched[0] = B2R_ERR_EMPTY_TREE;
@@ -72,10 +99,12 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
   }
 
   // ---- stratified pass (sum_tree.py:162-166 + prioritized_replay_buffer.py:155)
+  const int tile_size = blockDim.x;
+  const int n_tiles = (a.batch + tile_size - 1) / tile_size;
   const double step = 1.0 / (double)a.batch;  // np.linspace(0, 1, batch + 1)
-  int mine_base = 0, inv_base = 0;
-  for (int tile = 0; tile < a.batch; tile += blockDim.x) {
-    const int i = tile + threadIdx.x;
+  int mine_base = 0;  // running output position (single-CTA / sharded mode)
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int i = tile * tile_size + threadIdx.x;
     bool mine = false, valid = true;
     int64_t idx = 0;
     if (i < a.batch) {
@@ -96,29 +125,58 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
         mass = __dsub_rn(mass, left);
       }
       mine = (owner == a.rank);
+      B2R_MARK(3);
       if (mine) {
         idx = tree_descend_staged<K>(a.heap, top, top_depth, a.depth, mass, a.zero);
+        B2R_MARK(4);
         valid = is_valid_transition(a.valid, idx);
+        B2R_MARK(5);
       }
     }
-    int tile_mine, tile_inv;
-    const int pos = mine_base + block_scan_flag(mine, warp_counts, &tile_mine);
-    const int ipos = inv_base + block_scan_flag(mine && !valid, warp_counts, &tile_inv);
+    int pos = i, tile_mine = 0, tile_inv;
+    if (a.num_shards > 1) {  // compact this rank's strata (grid is 1 CTA here)
+      pos = mine_base + block_scan_flag(mine, warp_counts, &tile_mine);
+      mine_base += tile_mine;
+    }
+    const int ipos = block_scan_flag(mine && !valid, warp_counts, &tile_inv);
     if (mine) {
       a.out_idx[pos] = (int32_t)idx;
       if (a.out_slots) a.out_slots[pos] = i;
-      if (!valid) a.inv_slots[ipos] = pos;
+      if (!valid) a.inv_slots[(size_t)tile * tile_size + ipos] = pos;
     }
-    mine_base += tile_mine;
-    inv_base += tile_inv;
+    if (threadIdx.x == 0) a.tile_counts[tile] = tile_inv;
   }
-  const int count = mine_base;
-  const int num_invalid = inv_base;
+  B2R_MARK(6);
+  const int count = a.num_shards > 1 ? mine_base : a.batch;
+
+  // ---- only the last CTA to finish goes on
+  if (gridDim.x > 1) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      s_is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+  } else {
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+      tile_start[t] = run;
+      run += *(volatile int *)(a.tile_counts + t);
+    }
+    tile_start[n_tiles] = run;
+    if (gridDim.x > 1) *a.ticket = 0u;  // ready for the next launch
+  }
+  __syncthreads();
+  const int num_invalid = tile_start[n_tiles];
+  B2R_MARK(7);
 
   // ---- in-order replacement of invalid slots (prioritized_replay_buffer.py:156-170)
   int found = 0, drawn = 0;
   const int budget = a.max_attempts;
-  __syncthreads();
   while (num_invalid > 0 && found < num_invalid && drawn < budget) {
     const int r = drawn + threadIdx.x;
     const bool active = r < budget;
@@ -137,7 +195,7 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
     int tile_valid;
     const int ord = found + block_scan_flag(active && valid, warp_counts, &tile_valid);
     if (active && valid && ord < num_invalid) {
-      a.out_idx[a.inv_slots[ord]] = (int32_t)idx;
+      a.out_idx[invalid_slot(a, tile_start, n_tiles, tile_size, ord)] = (int32_t)idx;
       if (ord == num_invalid - 1) s_draws_used = r + 1;
     }
     if (active && r == budget - 1) {
@@ -158,17 +216,18 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
         // Every one of the `budget` draws was consumed; `found` slots were fixed.
         used = budget;
         const int next = found;  // first invalid slot still unresolved
+        const int next_slot = invalid_slot(a, tile_start, n_tiles, tile_size, next);
         if (budget == 0 || s_last_valid) {
           // budget already 0 when this slot is reached -> PRB:159-163
           status = B2R_ERR_SAMPLE_ATTEMPTS;
-          fail_slot = a.inv_slots[next];
+          fail_slot = next_slot;
         } else {
           // the slot burnt the rest of the budget and keeps its last (invalid)
           // draw; only a FURTHER invalid slot raises.
-          a.out_idx[a.inv_slots[next]] = s_last_idx;
+          a.out_idx[next_slot] = s_last_idx;
           if (num_invalid > next + 1) {
             status = B2R_ERR_SAMPLE_ATTEMPTS;
-            fail_slot = a.inv_slots[next + 1];
+            fail_slot = invalid_slot(a, tile_start, n_tiles, tile_size, next + 1);
           }
         }
       }
@@ -183,6 +242,7 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
       a.latched[1] = fail_slot;
     }
   }
+  B2R_MARK(8);
 }
 
 struct UniformSampleArgs {
@@ -203,6 +263,8 @@ struct UniformSampleArgs {
 // circular_replay_buffer.py:462-470 over a window of candidate draws.
 __global__ void __launch_bounds__(1024) uniform_sample_kernel(UniformSampleArgs a) {
   __shared__ int warp_counts[32];
+  pdl_release();
+  pdl_acquire();
   int accepted = a.counters[0], rejected = a.counters[1], used = 0;
   const uint64_t draws_before = a.counter ? *a.counter : 0ull;
   const uint64_t draw_offset = a.offset + draws_before;
@@ -287,7 +349,13 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
                   uint64_t offset, const double *strat_dev,
                   const double *retry_dev, int32_t n_retry, int32_t *out_idx_dev,
                   int32_t *info_dev, cudaStream_t stream) {
-  B2R_TRY(ensure_inv_slots(b, batch));
+  if (batch > kMaxTiles * 32)
+    return fail(B2R_ERR_UNSUPPORTED, "batch above %d is not supported", kMaxTiles * 32);
+  // At least 256 threads, so that staging the top levels is two rounds of loads.
+  int threads = sample_threads(batch);
+  if (threads < 256) threads = 256;
+  const int tiles = (batch + threads - 1) / threads;
+  B2R_TRY(ensure_inv_slots(b, (int64_t)tiles * threads + kMaxTiles + 8));
   PerSampleArgs a;
   a.heap = b->tree->heap;
   a.depth = b->tree->depth;
@@ -303,21 +371,21 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   a.retry_u01 = retry_dev;
   a.out_idx = out_idx_dev;
   a.inv_slots = b->inv_slots;
+  a.tile_counts = b->inv_slots + (int64_t)tiles * threads;
+  a.ticket = b->ticket;
   a.info = info_dev;
   a.latched = philox ? b->status : nullptr;
   a.num_shards = 1;
   a.rank = 0;
   a.shard_totals = nullptr;
   a.out_slots = nullptr;
-  // At least 128 threads: staging the top levels is then one round of loads.
-  int threads = sample_threads(batch);
-  if (threads < 128) threads = 128;
-  // Small batches are latency-bound: 5 tree levels per memory round trip; large
-  // ones have enough loads in flight already.
+  // Small batches: one CTA; large ones: one CTA per 1024 strata.  3 tree levels
+  // per memory round trip either way (more would bloat the straight-line code,
+  // and a cold instruction cache costs more than the saved round trips).
   if (batch <= 256)
-    per_sample_kernel<5, 256><<<1, threads, 0, stream>>>(a);
+    B2R_CUDA(launch(per_sample_kernel<3, 256>, dim3(1), dim3(threads), 0, stream, a));
   else
-    per_sample_kernel<3, 1024><<<1, threads, 0, stream>>>(a);
+    B2R_CUDA(launch(per_sample_kernel<3, 1024>, dim3(tiles), dim3(threads), 0, stream, a));
   B2R_LAUNCHED();
   return B2R_OK;
 }
@@ -365,7 +433,8 @@ int b2r_sample_indices_uniform(b2r_buffer *b, int32_t batch, int32_t n_cand,
   a.out_idx = reinterpret_cast<int32_t *>(b->bounce.dev + off_out);
   a.counters = reinterpret_cast<int32_t *>(b->bounce.dev + off_cnt);
   a.latched = nullptr;
-  b2r::uniform_sample_kernel<<<1, b2r::sample_threads(n_cand), 0, s>>>(a);
+  B2R_CUDA(b2r::launch(b2r::uniform_sample_kernel, dim3(1),
+                       dim3(b2r::sample_threads(n_cand)), 0, s, a));
   B2R_LAUNCHED();
   B2R_CUDA(cudaMemcpyAsync(b->bounce.host + off_out, b->bounce.dev + off_out,
                            off_cnt + 16 - off_out, cudaMemcpyDeviceToHost, s));
@@ -444,7 +513,8 @@ int b2r_sample_indices_device(b2r_buffer *b, int32_t batch, uint64_t seed,
   a.counters = b->info;
   a.latched = b->status;
   B2R_CUDA(cudaMemsetAsync(b->info, 0, 16, s));
-  b2r::uniform_sample_kernel<<<1, b2r::sample_threads(batch), 0, s>>>(a);
+  B2R_CUDA(b2r::launch(b2r::uniform_sample_kernel, dim3(1),
+                       dim3(b2r::sample_threads(batch)), 0, s, a));
   B2R_LAUNCHED();
   return B2R_OK;
 }
@@ -461,7 +531,12 @@ int b2r_sample_indices_sharded_device(b2r_buffer *b, int32_t global_batch,
     return fail(B2R_ERR_INVALID_ARGUMENT, "bad sharding arguments");
   cudaStream_t s = as_stream(stream);
   B2R_TRY(b2r::flush_queue(b, s));
-  B2R_TRY(b2r::ensure_inv_slots(b, global_batch));
+  int threads = b2r::sample_threads(global_batch);
+  if (threads < 256) threads = 256;
+  const int tiles = (global_batch + threads - 1) / threads;
+  if (tiles > b2r::kMaxTiles)
+    return fail(B2R_ERR_UNSUPPORTED, "global batch too large");
+  B2R_TRY(b2r::ensure_inv_slots(b, (int64_t)tiles * threads + b2r::kMaxTiles + 8));
   b2r::PerSampleArgs a;
   a.heap = b->tree->heap;
   a.depth = b->tree->depth;
@@ -476,18 +551,18 @@ int b2r_sample_indices_sharded_device(b2r_buffer *b, int32_t global_batch,
   a.retry_u01 = retry_u01;
   a.out_idx = out_indices;
   a.inv_slots = b->inv_slots;
+  a.tile_counts = b->inv_slots + (int64_t)tiles * threads;
+  a.ticket = b->ticket;
   a.info = b->info;
   a.latched = b->status;
   a.num_shards = num_shards;
   a.rank = rank;
   a.shard_totals = shard_totals;
   a.out_slots = out_slots;
-  int threads = b2r::sample_threads(global_batch);
-  if (threads < 128) threads = 128;
   if (global_batch <= 256)
-    b2r::per_sample_kernel<5, 256><<<1, threads, 0, s>>>(a);
+    B2R_CUDA(b2r::launch(b2r::per_sample_kernel<3, 256>, dim3(1), dim3(threads), 0, s, a));
   else
-    b2r::per_sample_kernel<3, 1024><<<1, threads, 0, s>>>(a);
+    B2R_CUDA(b2r::launch(b2r::per_sample_kernel<3, 1024>, dim3(1), dim3(threads), 0, s, a));
   B2R_LAUNCHED();
   if (out_count)
     B2R_CUDA(cudaMemcpyAsync(out_count, b->info + 3, 4, cudaMemcpyDeviceToDevice, s));
@@ -495,3 +570,9 @@ int b2r_sample_indices_sharded_device(b2r_buffer *b, int32_t global_batch,
 }
 
 }  // extern "C"
+
+#ifdef B2R_TRACE
+extern "C" int b2r_debug_trace_sample(long long *out) {
+  return (int)cudaMemcpyFromSymbol(out, b2r::g_trace, sizeof(long long) * 32);
+}
+#endif

@@ -24,6 +24,8 @@ namespace cg = cooperative_groups;
 namespace b2r {
 namespace {
 
+B2R_TRACE_DECL
+
 constexpr uint64_t kPadKey = ~0ull;
 
 __device__ __forceinline__ void bitonic_sort(uint64_t *keys, int padded) {
@@ -197,8 +199,11 @@ constexpr int kSmallBatch = 256;  // largest batch the single-CTA kernel takes
 
 // Warp-level bitonic sort of `padded` (<= 256) keys in shared memory.
 __device__ __forceinline__ void warp_bitonic_sort(uint64_t *keys, int padded, int lane) {
+#pragma unroll 1
   for (int k = 2; k <= padded; k <<= 1) {
+#pragma unroll 1
     for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 1
       for (int t = lane; t < padded; t += 32) {
         const int partner = t ^ j;
         if (partner > t) {
@@ -233,6 +238,10 @@ __global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V
   __shared__ int s_stop, s_stop_code;
 
   const int n = a.n;
+  B2R_MARK(0);
+  pdl_release();
+  pdl_acquire();
+  B2R_MARK(1);
   const int64_t latched = a.status[0];
   if (threadIdx.x == 0) {
     s_stop = n;
@@ -267,6 +276,7 @@ __global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V
     s_stop_code = (vals[n_eff] < 0.0) ? B2R_ERR_NEGATIVE_PRIORITY
                                       : B2R_ERR_INDEX_RANGE;
 
+  B2R_MARK(2);
   const int level = warp;
   const bool is_leaf = level == a.depth;
   const int shift = a.depth - level;
@@ -277,36 +287,26 @@ __global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V
                   ? (((uint64_t)((int64_t)a.indices[k] >> shift)) << 32) | (uint32_t)k
                   : kPadKey;
   __syncwarp();
+  B2R_MARK(3);
   if (level != 0) warp_bitonic_sort(keys, p2, lane);
+  B2R_MARK(4);
 
-  // Segment heads of this level and (internal levels) their node values, loaded
-  // before the barrier so the round trip overlaps the leaf pass.
+  // (Loops below stay rolled: this code runs once per launch on a cold
+  // instruction cache, so compact code beats unrolling.)
   const int64_t base = ((int64_t)1) << level;
-  constexpr int kHeadsPerLane = kSmallBatch / 32;
-  double node_value[kHeadsPerLane];
-#pragma unroll
-  for (int t = 0; t < kHeadsPerLane; ++t) {
-    const int p = lane + 32 * t;
-    node_value[t] = 0.0;
-    if (p < n_eff) {
-      const uint32_t node = (uint32_t)(keys[p] >> 32);
-      if (p == 0 || (uint32_t)(keys[p - 1] >> 32) != node)
-        node_value[t] = a.heap[base + node];
-    }
-  }
-
   if (is_leaf) {
     double local_max = 0.0;
+#pragma unroll 1
     for (int k = lane; k < n_eff; k += 32) local_max = fmax(local_max, vals[k]);
+#pragma unroll 1
     for (int off = 16; off > 0; off >>= 1)
       local_max = fmax(local_max, __shfl_xor_sync(0xffffffffu, local_max, off));
-#pragma unroll
-    for (int t = 0; t < kHeadsPerLane; ++t) {
-      const int p = lane + 32 * t;
-      if (p >= n_eff) continue;
+#pragma unroll 1
+    for (int p = lane; p < n_eff; p += 32) {
       const uint32_t node = (uint32_t)(keys[p] >> 32);
       if (p > 0 && (uint32_t)(keys[p - 1] >> 32) == node) continue;
-      double leaf = node_value[t];
+      double leaf = a.heap[base + node];
+#pragma unroll 1
       for (int q = p; q < n_eff && (uint32_t)(keys[q] >> 32) == node; ++q) {
         const uint32_t k = (uint32_t)keys[q];
         const double d = __dsub_rn(vals[k], leaf);
@@ -324,27 +324,30 @@ __global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V
       }
     }
   }
+  B2R_MARK(5);
   __syncthreads();  // deltas are in vals[]
+  B2R_MARK(6);
   if (is_leaf || warp >= levels) return;
 
+#pragma unroll 1
   for (int p = lane; p < n_eff; p += 32) sorted_delta[p] = vals[(uint32_t)keys[p]];
   __syncwarp();
-#pragma unroll
-  for (int t = 0; t < kHeadsPerLane; ++t) {
-    const int p = lane + 32 * t;
-    if (p >= n_eff) continue;
+#pragma unroll 1
+  for (int p = lane; p < n_eff; p += 32) {
     const uint32_t node = (uint32_t)(keys[p] >> 32);
     if (p > 0 && (uint32_t)(keys[p - 1] >> 32) == node) continue;
+    double acc = a.heap[base + node];  // issued before the search below
     int lo = p + 1, hi = n_eff;
+#pragma unroll 1
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       if ((uint32_t)(keys[mid] >> 32) > node) hi = mid; else lo = mid + 1;
     }
-    double acc = node_value[t];
-#pragma unroll 8
+#pragma unroll 4
     for (int q = p; q < lo; ++q) acc = __dadd_rn(acc, sorted_delta[q]);
     a.heap[base + node] = acc;
   }
+  B2R_MARK(7);
 }
 
 __global__ void tree_get_kernel(const double *__restrict__ heap, int64_t leaves,
@@ -421,7 +424,8 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     a.delta = t->delta;
     a.max_rec = t->max_rec;
     a.status = t->status;
-    tree_update_small_kernel<I, V><<<1, 32 * (t->depth + 1), smem, stream>>>(a);
+    B2R_CUDA(launch(tree_update_small_kernel<I, V>, dim3(1),
+                    dim3(32 * (t->depth + 1)), smem, stream, a));
     B2R_LAUNCHED();
     return B2R_OK;
   }
@@ -663,3 +667,9 @@ int b2r_tree_write_level(b2r_tree *t, int level, const double *in,
 }
 
 }  // extern "C"
+
+#ifdef B2R_TRACE
+extern "C" int b2r_debug_trace_tree(long long *out) {
+  return (int)cudaMemcpyFromSymbol(out, b2r::g_trace, sizeof(long long) * 32);
+}
+#endif

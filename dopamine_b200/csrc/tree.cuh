@@ -126,6 +126,7 @@ __device__ __forceinline__ void descend_levels(const Nodes &nodes, int64_t &h,
 template <int K, typename Nodes>
 __device__ __forceinline__ void descend_span(const Nodes &nodes, int64_t &h,
                                              double &q, int levels, uint32_t zero) {
+#pragma unroll 1
   while (levels >= K) {
     descend_levels<K>(nodes, h, q, zero);
     levels -= K;
@@ -158,17 +159,21 @@ __device__ __forceinline__ int stage_top_levels(const double *__restrict__ heap,
                                                 int depth, double *top) {
   const int top_depth = depth < kTopLevels ? depth : kTopLevels;
   const int count = 2 << top_depth;
-  constexpr int kPerThread = (2 << kTopLevels) / 128;
-  double r[kPerThread];
+  // 4 independent loads in flight per thread and iteration; the loop stays rolled
+  // (compact code matters more than the last bit of memory-level parallelism).
+#pragma unroll 1
+  for (int i0 = threadIdx.x; i0 < count; i0 += 4 * blockDim.x) {
+    double r[4];
 #pragma unroll
-  for (int j = 0; j < kPerThread; ++j) {
-    const int i = threadIdx.x + j * blockDim.x;
-    r[j] = i < count ? heap[i] : 0.0;
-  }
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * blockDim.x;
+      r[j] = i < count ? heap[i] : 0.0;
+    }
 #pragma unroll
-  for (int j = 0; j < kPerThread; ++j) {
-    const int i = threadIdx.x + j * blockDim.x;
-    if (i < count) top[i] = r[j];
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j * blockDim.x;
+      if (i < count) top[i] = r[j];
+    }
   }
   __syncthreads();
   return top_depth;
