@@ -500,7 +500,8 @@ def main():
   peak_gbs = float(peaks.get('hbm_gbs', 6650.0))
 
   sweep_batches = [] if args.no_sweep else [256, 1024, 4096]
-  wl = GpuWorkload(args.capacity, max([args.batch] + sweep_batches), rank)
+  wl = GpuWorkload(args.capacity,
+                   max([args.batch, args.batch * world] + sweep_batches), rank)
   launches_before = _native.lib().b2r_launch_count()
   wl.step(args.batch)
   launches_per_step = _native.lib().b2r_launch_count() - launches_before

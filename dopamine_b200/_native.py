@@ -90,6 +90,7 @@ class C51Args(ctypes.Structure):
       ('weights', c_void_p),
       ('mean_weighted_loss', c_void_p),
       ('grad_logits', c_void_p),
+      ('batch_count', c_void_p),
   ]
 
 
@@ -157,7 +158,12 @@ SIGNATURES = {
     'b2r_store_device_ptr': (c_void_p, [c_void_p, c_int32]),
     'b2r_sample_indices_sharded_device': (c_int, [
         c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
-        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+        c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'b2r_gather_device_counted': (c_int, [c_void_p, c_int32, c_void_p, c_void_p,
+                                          P(Batch), c_void_p]),
+    'b2r_set_priority_device_counted': (c_int, [c_void_p, c_int64, c_void_p,
+                                                c_void_p, c_void_p, c_void_p]),
+    'b2r_copy_total_device': (c_int, [c_void_p, c_void_p, c_void_p]),
     'b2r_total_device_ptr': (c_void_p, [c_void_p]),
     'b2r_c51_project': (c_int, [c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),

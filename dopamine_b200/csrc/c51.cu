@@ -112,6 +112,8 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   pdl_release();
   pdl_acquire();
   B2R_MARK(1);
+  const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
+  if (b >= rows) return;  // (mean_weighted_loss is not supported with batch_count)
 
   // ---- every global load the row needs is issued here, before the first use:
   // the kernel is latency-bound at batch 32 and this keeps it to one round trip.
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   const float my_prob = a.u.sampling_probabilities ? a.u.sampling_probabilities[b] : 1.f;
   float pmin = INFINITY;
   if (a.u.sampling_probabilities)
-    for (int k = threadIdx.x; k < a.u.batch; k += blockDim.x)
+    for (int k = threadIdx.x; k < rows; k += blockDim.x)
       pmin = fminf(pmin, a.u.sampling_probabilities[k]);
   float zl[PL], xt[PL], xo[PL];
   const int act0 = warp;  // first (usually only) action of this warp
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   // ---- D. gradient of mean(w * ce) w.r.t. the online logits
   if (a.u.grad_logits) {
     const float tsum = s_scalar[0], w = s_scalar[1], m = s_scalar[2], denom = s_scalar[3];
-    const float scale = __fmul_rn(w, __fdiv_rn(1.0f, (float)a.u.batch));
+    const float scale = __fmul_rn(w, __fdiv_rn(1.0f, (float)rows));
     float *g = a.u.grad_logits + (size_t)b * A * N;
     for (int k = threadIdx.x; k < A * N; k += blockDim.x) {
       const int act = k / N, i = k - act * N;
@@ -354,6 +356,9 @@ int b2r_c51_project(int32_t batch, int32_t num_atoms, const float *supports,
 int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
   if (!args || args->batch <= 0 || args->num_atoms < 2 || args->num_actions <= 0)
     return fail(B2R_ERR_INVALID_ARGUMENT, "bad C51 shape");
+  if (args->batch_count && args->mean_weighted_loss)
+    return fail(B2R_ERR_UNSUPPORTED,
+                "mean_weighted_loss cannot be combined with batch_count");
   if (!args->support || !args->target_logits || !args->online_logits ||
       !args->actions || !args->rewards || !args->terminals || !args->loss ||
       !args->priorities)

@@ -53,6 +53,7 @@ struct GatherArgs {
   RowCopy copies[kMaxRowCopies];
   const double *leaves;  // tree leaf level (nullable)
   float *prio_out;
+  const int32_t *count;  // nullable: device-side number of rows (<= batch)
 };
 
 // Trajectory length and terminal flag (circular_replay_buffer.py:517-527).  The
@@ -199,13 +200,15 @@ __global__ void __launch_bounds__(128) gather_stack4_u8_kernel(GatherArgs a) {
   pdl_release();
   pdl_acquire();
   B2R_MARK(1);
+  const int rows = a.count ? min(*a.count, a.batch) : a.batch;
   if (blockIdx.y >= a.batch) {  // appended scalar CTAs: one thread per transition
     const int b = ((blockIdx.y - a.batch) * gridDim.x + blockIdx.x) * blockDim.x +
                   threadIdx.x;
-    if (b < a.batch) write_scalars(a, b);
+    if (b < rows) write_scalars(a, b);
     return;
   }
   const int b = blockIdx.y;
+  if (b >= rows) return;
   const int64_t i = a.indices[b];
   bool ends;
   const int length = trajectory_length(a.term_flag, i, a.horizon, a.capacity, &ends);
@@ -252,13 +255,15 @@ __global__ void __launch_bounds__(128) gather_stack4_u8_kernel(GatherArgs a) {
 __global__ void __launch_bounds__(256) gather_generic_kernel(GatherArgs a) {
   pdl_release();
   pdl_acquire();
+  const int rows = a.count ? min(*a.count, a.batch) : a.batch;
   if (blockIdx.y >= a.batch) {  // appended scalar CTAs: one thread per transition
     const int b = ((blockIdx.y - a.batch) * gridDim.x + blockIdx.x) * blockDim.x +
                   threadIdx.x;
-    if (b < a.batch) write_scalars(a, b);
+    if (b < rows) write_scalars(a, b);
     return;
   }
   const int b = blockIdx.y;
+  if (b >= rows) return;
   const int64_t i = a.indices[b];
   bool ends;
   const int length = trajectory_length(a.term_flag, i, a.horizon, a.capacity, &ends);
@@ -292,8 +297,10 @@ __global__ void get_priority_kernel(const double *__restrict__ leaves, int64_t n
 }  // namespace
 
 int launch_gather(b2r_buffer *b, int32_t batch, const int32_t *indices_dev,
-                  const b2r_batch *out, cudaStream_t stream) {
+                  const b2r_batch *out, cudaStream_t stream,
+                  const int32_t *count_dev) {
   GatherArgs a;
+  a.count = count_dev;
   a.capacity = b->cfg.capacity;
   a.stack = b->cfg.stack_size;
   a.horizon = b->cfg.update_horizon;
@@ -359,16 +366,25 @@ extern "C" {
 
 int b2r_gather_device(b2r_buffer *b, int32_t batch, const int32_t *indices,
                       const b2r_batch *out, b2r_stream stream) {
-  if (batch <= 0 || batch > 65535)
-    return fail(B2R_ERR_INVALID_ARGUMENT, "batch must be in [1, 65535]");
+  if (batch <= 0 || batch > 60000)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "batch must be in [1, 60000]");
   B2R_TRY(b2r::flush_queue(b, as_stream(stream)));
   return b2r::launch_gather(b, batch, indices, out, as_stream(stream));
 }
 
+int b2r_gather_device_counted(b2r_buffer *b, int32_t max_batch,
+                              const int32_t *count, const int32_t *indices,
+                              const b2r_batch *out, b2r_stream stream) {
+  if (max_batch <= 0 || max_batch > 60000)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "max_batch must be in [1, 60000]");
+  B2R_TRY(b2r::flush_queue(b, as_stream(stream)));
+  return b2r::launch_gather(b, max_batch, indices, out, as_stream(stream), count);
+}
+
 int b2r_gather(b2r_buffer *b, int32_t batch, const int32_t *indices,
                const b2r_batch *out, b2r_stream stream) {
-  if (batch <= 0 || batch > 65535)
-    return fail(B2R_ERR_INVALID_ARGUMENT, "batch must be in [1, 65535]");
+  if (batch <= 0 || batch > 60000)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "batch must be in [1, 60000]");
   cudaStream_t s = as_stream(stream);
   B2R_TRY(b2r::flush_queue(b, s));
   // Device scratch for every requested output, 256-byte aligned segments.

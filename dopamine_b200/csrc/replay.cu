@@ -554,4 +554,22 @@ int b2r_set_priority_device(b2r_buffer *b, int64_t n, const int32_t *indices,
   return b2r_tree_set_device(b->tree, n, indices, priorities, stream);
 }
 
+int b2r_set_priority_device_counted(b2r_buffer *b, int64_t max_n,
+                                    const int32_t *count, const int32_t *indices,
+                                    const float *priorities, b2r_stream stream) {
+  if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
+  if (max_n <= 0) return B2R_OK;
+  B2R_TRY(b2r::flush_queue(b, as_stream(stream)));
+  return b2r::tree_apply<int32_t, float>(b->tree, max_n, indices, priorities,
+                                         nullptr, as_stream(stream), count);
+}
+
+int b2r_copy_total_device(b2r_buffer *b, double *dst, b2r_stream stream) {
+  if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
+  B2R_TRY(b2r::flush_queue(b, as_stream(stream)));
+  B2R_CUDA(cudaMemcpyAsync(dst, b->tree->heap + 1, 8, cudaMemcpyDeviceToDevice,
+                           as_stream(stream)));
+  return B2R_OK;
+}
+
 }  // extern "C"

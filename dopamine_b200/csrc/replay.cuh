@@ -121,7 +121,8 @@ int flush_queue(b2r_buffer *buf, cudaStream_t stream);
 void fill_valid_ctx(const b2r_buffer *buf, ValidCtx *ctx);
 int ensure_inv_slots(b2r_buffer *buf, int64_t n);
 int launch_gather(b2r_buffer *buf, int32_t batch, const int32_t *indices_dev,
-                  const b2r_batch *out, cudaStream_t stream);
+                  const b2r_batch *out, cudaStream_t stream,
+                  const int32_t *count_dev = nullptr);
 int launch_sample(b2r_buffer *buf, int32_t batch, bool philox, uint64_t seed,
                   uint64_t offset, const double *strat_dev,
                   const double *retry_dev, int32_t n_retry, int32_t *out_idx_dev,

@@ -183,8 +183,10 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
     bool valid = false;
     int64_t idx = 0;
     if (active) {
-      const double u = a.use_philox
-                           ? philox_uniform53(a.seed, draw_offset,
+      // Philox retry stream: rank-private (strata streams are shared by all ranks)
+      const double u = (a.use_philox || a.retry_u01 == nullptr)
+                           ? philox_uniform53(a.seed + 0x9E3779B97F4A7C15ull * (uint64_t)(a.rank + 1),
+                                              draw_offset,
                                               (uint64_t)a.batch + (uint64_t)r)
                            : a.retry_u01[r];
       // sum_tree.py:123-124: query = random.random() * total
@@ -523,9 +525,10 @@ int b2r_sample_indices_sharded_device(b2r_buffer *b, int32_t global_batch,
                                       int32_t num_shards, int32_t rank,
                                       const double *shard_totals,
                                       const double *query01, int32_t n_retry,
-                                      const double *retry_u01,
-                                      int32_t *out_slots, int32_t *out_indices,
-                                      int32_t *out_count, b2r_stream stream) {
+                                      const double *retry_u01, uint64_t seed,
+                                      uint64_t offset, int32_t *out_slots,
+                                      int32_t *out_indices, int32_t *out_count,
+                                      b2r_stream stream) {
   if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
   if (global_batch <= 0 || num_shards <= 0 || rank < 0 || rank >= num_shards)
     return fail(B2R_ERR_INVALID_ARGUMENT, "bad sharding arguments");
@@ -543,8 +546,9 @@ int b2r_sample_indices_sharded_device(b2r_buffer *b, int32_t global_batch,
   b2r::fill_valid_ctx(b, &a.valid);
   a.batch = global_batch;
   a.max_attempts = n_retry;
-  a.use_philox = 0;
-  a.seed = a.offset = 0;
+  a.use_philox = (query01 == nullptr) ? 1 : 0;
+  a.seed = seed;
+  a.offset = offset;
   a.counter = nullptr;
   a.zero = 0;
   a.strat_query01 = query01;

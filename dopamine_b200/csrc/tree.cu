@@ -60,6 +60,7 @@ struct UpdateArgs {
   double *delta;      // global scratch [n]: leaf deltas, produced by the leaf CTA
   double *max_rec;
   int64_t *status;
+  const int32_t *n_dev;  // nullable: device-side element count of the whole batch
 };
 
 // ONE cooperative launch, grid = depth + 1 CTAs (CTA l owns level l, CTA `depth`
@@ -79,7 +80,11 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(UpdateArgs<I, V> a) {
   cg::grid_group grid = cg::this_grid();
   const int level = blockIdx.x;
   const bool is_leaf = level == a.depth;
-  const int n = a.n;
+  int n = a.n;
+  if (a.n_dev) {
+    const int64_t left = (int64_t)*a.n_dev - a.k_base;
+    n = left < n ? (left > 0 ? (int)left : 0) : n;
+  }
   // An earlier chunk failed: the reference's loop stopped there.  The latch is
   // only written after the grid barrier, so every CTA takes the same branch.
   if (a.status[0] != 0) return;
@@ -237,11 +242,12 @@ __global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V
   double *sorted_delta = all_sorted + (size_t)warp * a.padded;
   __shared__ int s_stop, s_stop_code;
 
-  const int n = a.n;
   B2R_MARK(0);
   pdl_release();
   pdl_acquire();
   B2R_MARK(1);
+  int n = a.n;
+  if (a.n_dev) n = min(n, max(*a.n_dev, 0));
   const int64_t latched = a.status[0];
   if (threadIdx.x == 0) {
     s_stop = n;
@@ -398,7 +404,7 @@ int allow_big_smem(K kernel) {
 
 template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
-               const uint8_t *mode, cudaStream_t stream) {
+               const uint8_t *mode, cudaStream_t stream, const int32_t *n_dev) {
   if (n <= kSmallBatch) {
     // latency path: one CTA, one warp per level
     static bool small_ready = false;
@@ -424,6 +430,7 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     a.delta = t->delta;
     a.max_rec = t->max_rec;
     a.status = t->status;
+    a.n_dev = n_dev;
     B2R_CUDA(launch(tree_update_small_kernel<I, V>, dim3(1),
                     dim3(32 * (t->depth + 1)), smem, stream, a));
     B2R_LAUNCHED();
@@ -450,6 +457,7 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     a.delta = t->delta;
     a.max_rec = t->max_rec;
     a.status = t->status;
+    a.n_dev = n_dev;
     void *params[] = {&a};
     B2R_CUDA(cudaLaunchCooperativeKernel(
         reinterpret_cast<const void *>(&tree_update_kernel<I, V>),
@@ -461,13 +469,13 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
 
 template int tree_apply<int64_t, double>(b2r_tree *, int64_t, const int64_t *,
                                          const double *, const uint8_t *,
-                                         cudaStream_t);
+                                         cudaStream_t, const int32_t *);
 template int tree_apply<int32_t, float>(b2r_tree *, int64_t, const int32_t *,
                                         const float *, const uint8_t *,
-                                        cudaStream_t);
+                                        cudaStream_t, const int32_t *);
 template int tree_apply<int32_t, double>(b2r_tree *, int64_t, const int32_t *,
                                          const double *, const uint8_t *,
-                                         cudaStream_t);
+                                         cudaStream_t, const int32_t *);
 
 }  // namespace b2r
 

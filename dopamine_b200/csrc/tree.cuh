@@ -181,8 +181,10 @@ __device__ __forceinline__ int stage_top_levels(const double *__restrict__ heap,
 
 // Applies n sets in array order (device arrays).  mode (nullable): 1 = use the
 // running max_recorded_priority instead of values[k].
+// n_dev (nullable): device count, the effective n is min(n, *n_dev).
 template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
-               const uint8_t *mode, cudaStream_t stream);
+               const uint8_t *mode, cudaStream_t stream,
+               const int32_t *n_dev = nullptr);
 
 }  // namespace b2r

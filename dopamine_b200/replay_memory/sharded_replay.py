@@ -1,0 +1,151 @@
+"""Prioritized replay sharded over the GPUs of one box.
+
+The reference is single-process; this is the only multi-GPU piece of the path.
+Every rank owns a complete `OutOfGraphPrioritizedReplayBuffer` shard (its own
+cursor, validity window and sum tree) fed by its own actors.  A GLOBAL stratified
+batch is drawn as if the G shard trees hung under one more tree level:
+
+  1. each rank publishes its root priority total (one fp64) — the only collective
+     on the path, an all-gather of G x 8 bytes over NCCL/NVLink;
+  2. every rank scans the G totals in rank order with SumTree's own rule
+     (`q < left ? descend : q -= left`, sum_tree.py:128-139) for each of the B
+     strata and keeps those that land in its shard;
+  3. it descends its local tree with the residual mass, fixes invalid picks with
+     local retries exactly like prioritized_replay_buffer.py:156-170, and gathers
+     its part of the batch.  No frame ever crosses NVLink.
+
+The number of strata a shard serves is data dependent and stays on the device
+(`count`); downstream kernels take it from there.
+"""
+import ctypes
+
+import numpy as np
+
+from dopamine_b200 import _native
+
+
+def all_gather_totals(local_total, group=None):
+  """All-gathers one fp64 per rank into a (world,) tensor on the same device.
+
+  Works with NCCL (CUDA tensors) and gloo (CPU tensors, used by the CPU tests)."""
+  import torch
+  import torch.distributed as dist
+  world = dist.get_world_size(group)
+  out = torch.empty(world, dtype=torch.float64, device=local_total.device)
+  dist.all_gather_into_tensor(out, local_total.reshape(1), group=group)
+  return out
+
+
+def global_index(rank, shard_capacity, local_indices):
+  """Index in the virtual replay of world * shard_capacity transitions."""
+  return rank * shard_capacity + local_indices
+
+
+class ShardedPrioritizedReplay(object):
+  """Global stratified sampling over one local shard per rank."""
+
+  def __init__(self, memory, rank=None, world_size=None, group=None, seed=0):
+    import torch
+    import torch.distributed as dist
+    self.memory = memory
+    self.group = group
+    self.rank = dist.get_rank(group) if rank is None else rank
+    self.world = dist.get_world_size(group) if world_size is None else world_size
+    self.seed = int(seed)
+    self.step_counter = 0
+    self._lib = _native.lib()
+    self._h = memory._h  # pylint: disable=protected-access
+    self._send = torch.zeros(1, dtype=torch.float64, device='cuda')
+    self._count = torch.zeros(1, dtype=torch.int32, device='cuda')
+    self._torch = torch
+
+  def local_total(self):
+    """This shard's root priority as a 1-element CUDA tensor (no host sync)."""
+    _native.check(self._lib.b2r_copy_total_device(
+        self._h, self._send.data_ptr(), _native.current_stream()))
+    return self._send
+
+  def totals(self):
+    return all_gather_totals(self.local_total(), self.group)
+
+  def sample_index_batch(self, global_batch, totals=None, queries01=None,
+                         retry_u01=None):
+    """Returns (slots, indices, count): CUDA int32 tensors of length global_batch
+    whose first `count` (device scalar) entries are this rank's strata."""
+    torch = self._torch
+    if totals is None:
+      totals = self.totals()
+    slots = torch.empty(global_batch, dtype=torch.int32, device='cuda')
+    indices = torch.zeros(global_batch, dtype=torch.int32, device='cuda')
+    self.step_counter += 1
+    n_retry = (len(retry_u01) if retry_u01 is not None else
+               self.memory._max_sample_attempts)  # pylint: disable=protected-access
+    _native.check(self._lib.b2r_sample_indices_sharded_device(
+        self._h, global_batch, self.world, self.rank, totals.data_ptr(),
+        queries01.data_ptr() if queries01 is not None else None, n_retry,
+        retry_u01.data_ptr() if retry_u01 is not None else None, self.seed,
+        self.step_counter, slots.data_ptr(), indices.data_ptr(),
+        self._count.data_ptr(), _native.current_stream()))
+    return slots, indices, self._count
+
+  def sample_transition_batch(self, global_batch, **kwargs):
+    """(slots, count, batch tuple): batch rows [0, count) are valid."""
+    slots, indices, count = self.sample_index_batch(global_batch, **kwargs)
+    mem = self.memory
+    _, arrays, batch = mem._alloc_outputs(global_batch, True)  # pylint: disable=protected-access
+    _native.check(self._lib.b2r_gather_device_counted(
+        self._h, global_batch, count.data_ptr(), indices.data_ptr(),
+        ctypes.byref(batch), _native.current_stream()))
+    return slots, count, tuple(arrays)
+
+  def set_priority(self, indices, priorities, count):
+    """Batched priority write-back for the first `count` (device) entries."""
+    _native.check(self._lib.b2r_set_priority_device_counted(
+        self._h, indices.numel(), count.data_ptr(), indices.data_ptr(),
+        priorities.data_ptr(), _native.current_stream()))
+
+
+class ShardedStep(object):
+  """bench.py's N>1 step: all-gather totals -> sharded sample -> gather -> C51
+  loss/priorities -> write-back, for a global batch spread over the ranks."""
+
+  def __init__(self, workload, global_batch, world, rank, dist):
+    import torch
+    self.wl = workload
+    self.global_batch = global_batch
+    self.dist = dist
+    self.sharded = ShardedPrioritizedReplay(
+        workload.mem, rank=rank, world_size=world, seed=1234)
+    t, b, c = workload.plan(global_batch)
+    self.t, self.b, self.c = t, b, c
+    self.slots = torch.empty(global_batch, dtype=torch.int32, device='cuda')
+    c.batch_count = self.sharded._count.data_ptr()  # pylint: disable=protected-access
+    c.mean_weighted_loss = None
+    self.lib = workload.lib
+    self.h = workload.h
+    self._launches = None
+
+  def step(self):
+    nat, lib, sh = self.wl.native, self.lib, self.sharded
+    stream = nat.current_stream()
+    totals = sh.totals()
+    sh.step_counter += 1
+    count_ptr = sh._count.data_ptr()  # pylint: disable=protected-access
+    nat.check(lib.b2r_sample_indices_sharded_device(
+        self.h, self.global_batch, sh.world, sh.rank, totals.data_ptr(), None,
+        sh.memory._max_sample_attempts, None, sh.seed, sh.step_counter,  # pylint: disable=protected-access
+        self.slots.data_ptr(), self.t['indices'].data_ptr(), count_ptr, stream))
+    nat.check(lib.b2r_gather_device_counted(
+        self.h, self.global_batch, count_ptr, self.t['indices'].data_ptr(),
+        ctypes.byref(self.b), stream))
+    nat.check(lib.b2r_c51_loss(ctypes.byref(self.c), stream))
+    nat.check(lib.b2r_set_priority_device_counted(
+        self.h, self.global_batch, count_ptr, self.t['indices'].data_ptr(),
+        self.t['priorities'].data_ptr(), stream))
+
+  def launches_per_step(self):
+    if self._launches is None:
+      before = self.lib.b2r_launch_count()
+      self.step()
+      self._launches = self.lib.b2r_launch_count() - before
+    return self._launches

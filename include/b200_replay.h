@@ -55,7 +55,7 @@ int64_t b2r_launch_count(void);
 
 /* ------------------------------------------------------------------------- */
 /* Sum tree — replaces sum_tree.SumTree (ST:30-205).                          */
-/* fp64 nodes, one heap array: node (level l, position i) at 2^l - 1 + i.     */
+/* fp64 nodes, one 1-based heap array: node (level l, position i) at 2^l + i.  */
 /* ------------------------------------------------------------------------- */
 
 /* SumTree.__init__ (ST:65-89). capacity <= 0 -> B2R_ERR_INVALID_ARGUMENT. */
@@ -259,14 +259,30 @@ const void *b2r_store_device_ptr(b2r_buffer *buf, int32_t column);
  * totals in rank order, and only the owning rank descends its tree with the
  * residual.  out_slots/out_indices receive this rank's strata (ascending i) and
  * *out_count their number.  Invalid picks are redrawn locally from retry_u01
- * exactly as in PRB:156-170.  DEVICE pointers; asynchronous. */
+ * exactly as in PRB:156-170.  query01 / retry_u01 may be NULL: the uniforms then
+ * come from Philox keyed by (seed, offset) — the strata stream is identical on all
+ * ranks, the retry stream is rank-private (n_retry = attempt budget).
+ * DEVICE pointers; asynchronous. */
 int b2r_sample_indices_sharded_device(b2r_buffer *buf, int32_t global_batch,
                                       int32_t num_shards, int32_t rank,
                                       const double *shard_totals,
                                       const double *query01, int32_t n_retry,
-                                      const double *retry_u01,
-                                      int32_t *out_slots, int32_t *out_indices,
-                                      int32_t *out_count, b2r_stream stream);
+                                      const double *retry_u01, uint64_t seed,
+                                      uint64_t offset, int32_t *out_slots,
+                                      int32_t *out_indices, int32_t *out_count,
+                                      b2r_stream stream);
+/* Variants whose element count lives on the DEVICE (*count <= max_...): what a
+ * shard serves of a global batch is only known there.  Rows past *count are
+ * skipped.  Asynchronous. */
+int b2r_gather_device_counted(b2r_buffer *buf, int32_t max_batch,
+                              const int32_t *count, const int32_t *indices,
+                              const b2r_batch *out, b2r_stream stream);
+int b2r_set_priority_device_counted(b2r_buffer *buf, int64_t max_n,
+                                    const int32_t *count, const int32_t *indices,
+                                    const float *priorities, b2r_stream stream);
+/* Copies the buffer's root total into dst (device), e.g. the send buffer of the
+ * all-gather.  Asynchronous. */
+int b2r_copy_total_device(b2r_buffer *buf, double *dst, b2r_stream stream);
 /* Device address of the buffer's root total (input of the all-gather). */
 const double *b2r_total_device_ptr(b2r_buffer *buf);
 
@@ -297,6 +313,7 @@ typedef struct {
   float *weights;               /* (B,) IS weights / max or NULL       RA:279-280 */
   float *mean_weighted_loss;    /* scalar or NULL                      RA:293, 305 */
   float *grad_logits;           /* (B, A, N) d mean(w*loss)/d online_logits or NULL */
+  const int32_t *batch_count;   /* NULL, or DEVICE count <= batch of rows to process */
 } b2r_c51_args;
 
 /* Bellman target + projection + softmax cross-entropy + new priorities + IS

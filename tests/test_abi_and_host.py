@@ -33,7 +33,7 @@ def test_struct_layouts_match_the_header():
   # sizes the C compiler produces for the by-pointer structs
   assert ctypes.sizeof(_native.Config) == 96
   assert ctypes.sizeof(_native.Batch) == 8 * 8 + 8 * _native.MAX_EXTRAS + 8
-  assert ctypes.sizeof(_native.C51Args) == 16 + 13 * 8
+  assert ctypes.sizeof(_native.C51Args) == 16 + 14 * 8
 
 
 def test_no_cpu_fallback_without_a_device():

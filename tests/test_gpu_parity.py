@@ -440,3 +440,94 @@ def test_c51_loss_matches_numpy_restatement(gpu, batch, actions, atoms):
   assert (uni['weights'].cpu().numpy() == 1.0).all()
   np.testing.assert_allclose(uni['loss'].cpu().numpy(), want['loss'], rtol=2e-6,
                              atol=1e-6)
+
+
+# --------------------------------------------------------------- sharding ----
+@pytest.mark.parametrize('num_shards,global_batch', [(2, 32), (4, 64), (8, 256),
+                                                     (4, 2048)])
+def test_sharded_sampling_matches_oracle(gpu, num_shards, global_batch):
+  """All ranks of a sharded replay emulated on one GPU (one buffer per rank): the
+  strata each rank serves, its local indices incl. retries, the counted gather and
+  the counted write-back must match the CPU statement of the rule."""
+  from dopamine_b200 import _native
+  from dopamine_b200.replay_memory import sharded_replay
+  from oracle import sharded_port
+  import ctypes
+  torch = gpu.torch
+  rng = np.random.RandomState(num_shards * 1000 + global_batch)
+  cap, shape = 400, (8, 8)
+  kw = dict(update_horizon=3, gamma=0.99, max_sample_attempts=64)
+  ours, ports = [], []
+  for g in range(num_shards):
+    o = gpu.prb.OutOfGraphPrioritizedReplayBuffer(shape, 4, cap, 8, output='torch', **kw)
+    p = PortPrioritizedReplay(shape, 4, cap, 8, **kw)
+    _fill_pair(rng, o, p, 300 + 57 * g, shape, True, term_p=0.1)
+    ids = rng.randint(0, min(cap, int(p.add_count)), size=200).astype(np.int32)
+    pr = (np.sqrt(np.abs(rng.randn(200)) + 1e-10) * (1 + g)).astype(np.float32)
+    o.set_priority(ids, pr)
+    p.set_priority(ids, pr)
+    ours.append(o)
+    ports.append(p)
+  totals = np.array([p.sum_tree.total() for p in ports], dtype=np.float64)
+  d_totals = torch.as_tensor(totals, device='cuda')
+  bounds = np.linspace(0., 1., global_batch + 1)
+  queries = bounds[:-1] + (bounds[1:] - bounds[:-1]) * rng.rand(global_batch)
+  d_queries = torch.as_tensor(queries, device='cuda')
+  retries = [rng.rand(max(64, global_batch)) for _ in range(num_shards)]
+  want = sharded_port.sharded_sample(ports, queries, retries)
+  served = []
+  for g in range(num_shards):
+    sh = sharded_replay.ShardedPrioritizedReplay(ours[g], rank=g,
+                                                 world_size=num_shards)
+    # the device total this rank would contribute to the all-gather
+    assert float(sh.local_total().cpu()[0]) == totals[g]
+    d_retry = torch.as_tensor(retries[g], device='cuda')
+    slots, count, batch = sh.sample_transition_batch(
+        global_batch, totals=d_totals, queries01=d_queries, retry_u01=d_retry)
+    n = int(count.cpu()[0])
+    w_slots, w_idx, _ = want[g]
+    assert n == len(w_slots)
+    assert slots[:n].cpu().numpy().tolist() == w_slots
+    idx = batch[7][:n].cpu().numpy()
+    assert idx.tolist() == [int(i) for i in w_idx]
+    served += w_slots
+    if n:
+      ref = ports[g].sample_transition_batch(n, [int(i) for i in w_idx])
+      for w, got in zip(ref, batch):
+        assert w.tobytes() == got[:n].cpu().numpy().tobytes()
+      pr = np.sqrt(np.abs(rng.randn(global_batch)) + 1e-10).astype(np.float32)
+      sh.set_priority(batch[7], torch.as_tensor(pr, device='cuda'), count)
+      ports[g].set_priority(idx, pr[:n])
+      for lo, lp in zip(ours[g].sum_tree.nodes, ports[g].sum_tree.nodes):
+        assert np.array_equal(lo.view(np.uint64), lp.view(np.uint64))
+  assert sorted(served) == list(range(global_batch))
+
+
+def test_sharded_philox_strata_are_shared_by_all_ranks(gpu):
+  """Throughput mode: every rank draws the same strata from Philox(seed, step), so
+  the ranks' slot sets partition the global batch without any exchange of draws."""
+  from dopamine_b200.replay_memory import sharded_replay
+  torch = gpu.torch
+  rng = np.random.RandomState(5)
+  num_shards, global_batch, cap = 4, 128, 500
+  ours = []
+  for g in range(num_shards):
+    o = gpu.prb.OutOfGraphPrioritizedReplayBuffer((8, 8), 4, cap, 8, output='torch',
+                                                  update_horizon=3)
+    for _ in range(450):
+      o.add(rng.randint(0, 256, size=(8, 8)).astype(np.uint8), 1, 0.5,
+            int(rng.rand() < 0.05), float(rng.rand() + 0.1 * g))
+    ours.append(o)
+  totals = torch.cat([
+      sharded_replay.ShardedPrioritizedReplay(o, rank=g, world_size=num_shards)
+      .local_total().clone() for g, o in enumerate(ours)])
+  served = []
+  for g in range(num_shards):
+    sh = sharded_replay.ShardedPrioritizedReplay(ours[g], rank=g,
+                                                 world_size=num_shards, seed=99)
+    slots, idx, count = sh.sample_index_batch(global_batch, totals=totals)
+    n = int(count.cpu()[0])
+    served += slots[:n].cpu().numpy().tolist()
+    valid = [ours[g].is_valid_transition(int(i)) for i in idx[:n].cpu().numpy()]
+    assert all(valid)
+  assert sorted(served) == list(range(global_batch))
