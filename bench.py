@@ -512,7 +512,7 @@ def main():
     sharded = sharded_replay.ShardedStep(wl, args.batch * world, world, rank, dist)
     step_fn = sharded.step
     launches_per_step = sharded.launches_per_step()
-    use_graph = False
+    use_graph = not args.no_graph  # NCCL all-gather is captured with the kernels
   else:
     step_fn = lambda: wl.step(args.batch)
     use_graph = not args.no_graph

@@ -338,6 +338,8 @@ int b2r_create(const b2r_config *cfg, b2r_buffer **out) {
   B2R_CUDA(cudaMemset(b->status, 0, 16));
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->ticket), 4));
   B2R_CUDA(cudaMemset(b->ticket, 0, 4));
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->shard_counter), 8));
+  B2R_CUDA(cudaMemset(b->shard_counter, 0, 8));
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->draw_counter), 8));
   B2R_CUDA(cudaMemset(b->draw_counter, 0, 8));
   *out = b;
@@ -360,6 +362,7 @@ int b2r_destroy(b2r_buffer *b) {
   cudaFree(b->info);
   cudaFree(b->status);
   cudaFree(b->draw_counter);
+  cudaFree(b->shard_counter);
   cudaFree(b->ticket);
   if (b->out_scratch) cudaFree(b->out_scratch);
   b->bounce.release();

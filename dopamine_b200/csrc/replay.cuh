@@ -109,6 +109,8 @@ struct b2r_buffer {
   int32_t *info = nullptr;      // device [4]: status, fail slot, draws used, count
   int64_t *status = nullptr;    // device [2]: latched asynchronous error
   unsigned int *ticket = nullptr;   // device: last-CTA election of the sample kernel
+  uint64_t *shard_counter = nullptr;  // device: like draw_counter, for sharded draws
+                                      // (advances in lockstep on every rank)
   uint64_t *draw_counter = nullptr;  // device: bumps per Philox sample launch, so a
                                      // replayed CUDA graph draws fresh uniforms
   b2r::Bounce bounce;           // HOST-array calls

@@ -549,7 +549,10 @@ int b2r_sample_indices_sharded_device(b2r_buffer *b, int32_t global_batch,
   a.use_philox = (query01 == nullptr) ? 1 : 0;
   a.seed = seed;
   a.offset = offset;
-  a.counter = nullptr;
+  // Philox mode: the draw number also advances on the device, in lockstep on all
+  // ranks (each makes the same sequence of sharded calls), so a captured CUDA
+  // graph draws fresh, rank-consistent strata at every replay.
+  a.counter = a.use_philox ? b->shard_counter : nullptr;
   a.zero = 0;
   a.strat_query01 = query01;
   a.retry_u01 = retry_u01;

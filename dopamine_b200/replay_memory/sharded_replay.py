@@ -52,7 +52,6 @@ class ShardedPrioritizedReplay(object):
     self.rank = dist.get_rank(group) if rank is None else rank
     self.world = dist.get_world_size(group) if world_size is None else world_size
     self.seed = int(seed)
-    self.step_counter = 0
     self._lib = _native.lib()
     self._h = memory._h  # pylint: disable=protected-access
     self._send = torch.zeros(1, dtype=torch.float64, device='cuda')
@@ -77,14 +76,13 @@ class ShardedPrioritizedReplay(object):
       totals = self.totals()
     slots = torch.empty(global_batch, dtype=torch.int32, device='cuda')
     indices = torch.zeros(global_batch, dtype=torch.int32, device='cuda')
-    self.step_counter += 1
     n_retry = (len(retry_u01) if retry_u01 is not None else
                self.memory._max_sample_attempts)  # pylint: disable=protected-access
     _native.check(self._lib.b2r_sample_indices_sharded_device(
         self._h, global_batch, self.world, self.rank, totals.data_ptr(),
         queries01.data_ptr() if queries01 is not None else None, n_retry,
         retry_u01.data_ptr() if retry_u01 is not None else None, self.seed,
-        self.step_counter, slots.data_ptr(), indices.data_ptr(),
+        0, slots.data_ptr(), indices.data_ptr(),
         self._count.data_ptr(), _native.current_stream()))
     return slots, indices, self._count
 
@@ -129,11 +127,10 @@ class ShardedStep(object):
     nat, lib, sh = self.wl.native, self.lib, self.sharded
     stream = nat.current_stream()
     totals = sh.totals()
-    sh.step_counter += 1
     count_ptr = sh._count.data_ptr()  # pylint: disable=protected-access
     nat.check(lib.b2r_sample_indices_sharded_device(
         self.h, self.global_batch, sh.world, sh.rank, totals.data_ptr(), None,
-        sh.memory._max_sample_attempts, None, sh.seed, sh.step_counter,  # pylint: disable=protected-access
+        sh.memory._max_sample_attempts, None, sh.seed, 0,  # pylint: disable=protected-access
         self.slots.data_ptr(), self.t['indices'].data_ptr(), count_ptr, stream))
     nat.check(lib.b2r_gather_device_counted(
         self.h, self.global_batch, count_ptr, self.t['indices'].data_ptr(),

@@ -261,7 +261,9 @@ const void *b2r_store_device_ptr(b2r_buffer *buf, int32_t column);
  * *out_count their number.  Invalid picks are redrawn locally from retry_u01
  * exactly as in PRB:156-170.  query01 / retry_u01 may be NULL: the uniforms then
  * come from Philox keyed by (seed, offset) — the strata stream is identical on all
- * ranks, the retry stream is rank-private (n_retry = attempt budget).
+ * ranks, the retry stream is rank-private (n_retry = attempt budget); the draw
+ * number is offset + a device counter that every such call advances, so all ranks
+ * must make the same sequence of sharded calls.
  * DEVICE pointers; asynchronous. */
 int b2r_sample_indices_sharded_device(b2r_buffer *buf, int32_t global_batch,
                                       int32_t num_shards, int32_t rank,
