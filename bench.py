@@ -26,6 +26,9 @@ import time
 
 import numpy as np
 
+if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+  os.environ['NCCL_DEBUG'] = 'WARN'  # keep stdout to the one JSON line
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
@@ -45,8 +48,8 @@ UNIT = 'transitions/s'
 def parse_args():
   p = argparse.ArgumentParser()
   p.add_argument('--gpus', type=int, default=1)
-  p.add_argument('--steps', type=int, default=2000)
-  p.add_argument('--warmup', type=int, default=50)
+  p.add_argument('--steps', type=int, default=20000)
+  p.add_argument('--warmup', type=int, default=100)
   p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   p.add_argument('--batch', type=int, default=32)
   p.add_argument('--capacity', type=int, default=1000000)
@@ -71,29 +74,73 @@ def workload_name(batch, capacity, n_gpus):
 # clocks sampling (B200_PROFILING.md)
 # --------------------------------------------------------------------------- #
 class ClockSampler(object):
+  """Samples SM clocks and throttle reasons of one GPU during the timed region.
 
-  def __init__(self, index):
+  Uses NVML in-process (no fork: spawning nvidia-smi from several ranks stalls the
+  driver for milliseconds and shows up in a 30 us step); falls back to nvidia-smi."""
+
+  def __init__(self, index, period_s=0.05):
     self.index = index
-    self.rows = []
+    self.period = period_s
+    self.sm, self.sm_max, self.reasons = [], [], set()
     self._stop = threading.Event()
     self._thread = threading.Thread(target=self._run, daemon=True)
+    self._nvml = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self._nvml = pynvml
+      visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+      phys = index
+      if visible:
+        ids = [v for v in visible.split(',') if v.strip()]
+        if index < len(ids) and ids[index].strip().isdigit():
+          phys = int(ids[index])
+      self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+    except Exception:  # pylint: disable=broad-except
+      self._nvml = None
 
-  def _run(self):
+  def _sample_nvml(self):
+    n = self._nvml
+    self.sm.append(int(n.nvmlDeviceGetClockInfo(self._handle, n.NVML_CLOCK_SM)))
+    self.sm_max.append(int(n.nvmlDeviceGetMaxClockInfo(self._handle, n.NVML_CLOCK_SM)))
+    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+               if hasattr(n, 'nvmlDeviceGetCurrentClocksEventReasons') else
+               n.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
+    names = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown',
+             0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
+    for bit, name in names.items():
+      if mask & bit:
+        self.reasons.add(name)
+
+  def _sample_smi(self):
     q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
+    out = subprocess.run(
+        ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+         '--format=csv,noheader,nounits'], capture_output=True, text=True,
+        timeout=5).stdout.strip()
+    r = [x.strip() for x in out.split(',')]
+    if len(r) >= 6 and r[0].isdigit():
+      self.sm.append(int(r[0]))
+      self.sm_max.append(int(r[1]))
+      for k, name in enumerate(['hw_slowdown', 'hw_thermal_slowdown',
+                                'sw_thermal_slowdown', 'sw_power_cap']):
+        if r[2 + k].lower().startswith('active'):
+          self.reasons.add(name)
+
+  def _run(self):
     while not self._stop.is_set():
       try:
-        out = subprocess.run(
-            ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-             '--format=csv,noheader,nounits'], capture_output=True, text=True,
-            timeout=5).stdout.strip()
-        if out:
-          self.rows.append([x.strip() for x in out.split(',')])
+        if self._nvml is not None:
+          self._sample_nvml()
+        else:
+          self._sample_smi()
       except Exception:  # pylint: disable=broad-except
         pass
-      self._stop.wait(0.2)
+      self._stop.wait(self.period if self._nvml is not None else 0.5)
 
   def __enter__(self):
     self._thread.start()
@@ -104,18 +151,11 @@ class ClockSampler(object):
     self._thread.join(timeout=6)
 
   def summary(self):
-    sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-    mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-             'sw_power_cap']
-    reasons = []
-    for k, name in enumerate(names):
-      if any(len(r) > 2 + k and r[2 + k].lower().startswith('active')
-             for r in self.rows):
-        reasons.append(name)
+    sm = sorted(self.sm)
     return {'sm_mhz': sm[len(sm) // 2] if sm else None,
-            'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-            'samples': len(sm)}
+            'sm_max_mhz': max(self.sm_max) if self.sm_max else None,
+            'reasons': sorted(self.reasons), 'samples': len(sm),
+            'source': 'nvml' if self._nvml is not None else 'nvidia-smi'}
 
 
 # --------------------------------------------------------------------------- #
@@ -326,10 +366,78 @@ def measure_gather_roofline(torch, wl, batch, peak_gbs, launches=200):
   }
 
 
-def measure_e2e(torch, wl, batch, steps):
-  """Same step through the reference-facing API with HOST buffers: numpy batch
-  out (D2H), logits in from pinned host memory (H2D), priorities back (D2H),
-  host-array set_priority."""
+def measure_e2e(torch, wl, batch, steps, update_period=4):
+  """The same metric through the public Python API with HOST buffers in the loop.
+
+  Per step, as the agent drives the replay (dqn_agent.py:359-442): `update_period`
+  new transitions are add()-ed from host memory (H2D of the frames), the network
+  outputs are copied in from pinned host memory (H2D), then sample -> gather ->
+  C51 loss -> priority write-back run through WrappedPrioritizedReplayBuffer /
+  rainbow_agent (device tensors, as the reference's wrapper hands TF tensors to the
+  graph), and the per-row losses are read back (D2H, synchronising)."""
+  from dopamine_b200.replay_memory import prioritized_replay_buffer as prb
+  ra = wl.ra
+  wrapped = prb.WrappedPrioritizedReplayBuffer.__new__(
+      prb.WrappedPrioritizedReplayBuffer)
+  wrapped.memory = wl.mem            # the benchmark's filled 1M buffer
+  wrapped.batch_size = batch
+  wrapped.transition = None
+  mem = wl.mem
+  mem._output, mem._reuse_outputs = 'torch', True  # pylint: disable=protected-access
+  mem._batch_size = batch  # pylint: disable=protected-access
+  rng = np.random.RandomState(3)
+  frames = rng.randint(0, 256, size=(64, 84, 84)).astype(np.uint8)
+  online_h = wl.online[:batch].cpu().pin_memory()
+  target_h = wl.target[:batch].cpu().pin_memory()
+  online_d = torch.empty_like(wl.online[:batch])
+  target_d = torch.empty_like(wl.target[:batch])
+  loss_h = torch.empty(batch, dtype=torch.float32).pin_memory()
+  out = None
+  counter = [0]
+
+  def one():
+    nonlocal out
+    for _ in range(update_period):
+      k = counter[0]
+      counter[0] += 1
+      wrapped.add(frames[k & 63], k % NUM_ACTIONS, 0.5, int(k % 1000 == 999),
+                  prb.MAX_RECORDED_PRIORITY)
+    online_d.copy_(online_h, non_blocking=True)
+    target_d.copy_(target_h, non_blocking=True)
+    t = wrapped.sample()
+    out = ra.c51_loss(online_d, target_d, t['action'], t['reward'], t['terminal'],
+                      t['sampling_probabilities'], wl.support, wl.gamma_n,
+                      want_mean=False, out=out)
+    wrapped.tf_set_priority(t['indices'], out['priorities'])
+    loss_h.copy_(out['loss'], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return float(loss_h[0])
+
+  for _ in range(10):
+    one()
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    one()
+  torch.cuda.synchronize()
+  dt = time.perf_counter() - t0
+  row = 7056 + 16  # staged row: frame + action + reward + terminal (padded)
+  h2d = update_period * row + (online_h.numel() + target_h.numel()) * 4
+  d2h = batch * 4
+  e2e = {'value': round(batch * steps / dt, 1), 'unit': UNIT,
+         'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+         'ms_per_step': round(dt * 1e3 / steps, 4), 'steps': steps,
+         'what': ('public Python API per step: %d x add() of host frames, H2D of '
+                  'both logits tensors from pinned memory, sample+gather+C51+'
+                  'set_priority on device tensors, D2H of the per-row losses'
+                  % update_period)}
+  mem._output, mem._reuse_outputs = 'numpy', False  # pylint: disable=protected-access
+  return e2e
+
+
+def measure_e2e_host_batch(torch, wl, batch, steps):
+  """Variant that also ships the whole sampled batch to host numpy arrays, i.e. the
+  reference's OutOfGraph* return convention (1.8 MB of D2H per step at batch 32)."""
   mem, ra = wl.mem, wl.ra
   online_h = wl.online[:batch].cpu().pin_memory()
   target_h = wl.target[:batch].cpu().pin_memory()
@@ -517,9 +625,12 @@ def main():
     step_fn = lambda: wl.step(args.batch)
     use_graph = not args.no_graph
 
-  with ClockSampler(local_rank) as clocks:
-    ms = time_graph_or_eager(torch, step_fn, args.steps, args.warmup, use_graph,
-                             dist)
+  clocks = ClockSampler(local_rank)
+  if rank == 0:
+    clocks.__enter__()
+  ms = time_graph_or_eager(torch, step_fn, args.steps, args.warmup, use_graph, dist)
+  if rank == 0:
+    clocks.__exit__()
   if dist is not None:
     t = torch.tensor([ms], device='cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -559,7 +670,10 @@ def main():
                          'gather_us': roof['us_per_launch']}
       line['sweep'] = sweep
     if not args.no_e2e and world == 1:
-      line['e2e'] = measure_e2e(torch, wl, args.batch, max(50, min(args.steps, 500)))
+      line['e2e_host_batch'] = measure_e2e_host_batch(
+          torch, wl, args.batch, max(50, min(args.steps, 300)))
+      line['e2e'] = measure_e2e(torch, wl, args.batch,
+                                max(50, min(args.steps, 2000)))
     if not args.no_cpu_baseline and world == 1:
       line['cpu_baseline'] = cpu_baseline(args.batch, args.capacity)
     print(json.dumps(line))

@@ -102,7 +102,7 @@ def project_distribution(supports, weights, target_support,
 
 def c51_loss(online_logits, target_logits, actions, rewards, terminals,
              sampling_probabilities, support, cumulative_gamma,
-             want_target=False, want_grad=False):
+             want_target=False, want_grad=False, want_mean=True, out=None):
   """Fused Rainbow update math for one batch, all on the device.
 
   Args:
@@ -116,6 +116,8 @@ def c51_loss(online_logits, target_logits, actions, rewards, terminals,
     dict with 'loss' (B,), 'priorities' (B,) = sqrt(loss + 1e-10), 'weights'
     (B,), 'mean_weighted_loss' (scalar tensor) and optionally 'target' (B, N),
     'grad_logits' (B, A, N) = d mean_weighted_loss / d online_logits.
+    `out` (a dict returned by an earlier call with the same shapes) is reused
+    instead of allocating.
   """
   torch = _torch()
   b, a, n = online_logits.shape
@@ -127,16 +129,21 @@ def c51_loss(online_logits, target_logits, actions, rewards, terminals,
   online_logits = online_logits.contiguous()
   target_logits = target_logits.contiguous()
   dev = online_logits.device
-  out = {
-      'loss': torch.empty(b, dtype=torch.float32, device=dev),
-      'priorities': torch.empty(b, dtype=torch.float32, device=dev),
-      'weights': torch.empty(b, dtype=torch.float32, device=dev),
-      'mean_weighted_loss': torch.empty((), dtype=torch.float32, device=dev),
-  }
-  if want_target:
-    out['target'] = torch.empty(b, n, dtype=torch.float32, device=dev)
-  if want_grad:
-    out['grad_logits'] = torch.empty(b, a, n, dtype=torch.float32, device=dev)
+  if out is None:
+    out = {
+        'loss': torch.empty(b, dtype=torch.float32, device=dev),
+        'priorities': torch.empty(b, dtype=torch.float32, device=dev),
+        'weights': torch.empty(b, dtype=torch.float32, device=dev),
+    }
+    if want_mean:
+      out['mean_weighted_loss'] = torch.empty((), dtype=torch.float32, device=dev)
+    if want_target:
+      out['target'] = torch.empty(b, n, dtype=torch.float32, device=dev)
+    if want_grad:
+      out['grad_logits'] = torch.empty(b, a, n, dtype=torch.float32, device=dev)
+  want_mean = 'mean_weighted_loss' in out
+  want_target = 'target' in out
+  want_grad = 'grad_logits' in out
   args = _native.C51Args()
   args.batch, args.num_actions, args.num_atoms = b, a, n
   args.cumulative_gamma = float(np.float32(cumulative_gamma))
@@ -153,7 +160,8 @@ def c51_loss(online_logits, target_logits, actions, rewards, terminals,
   args.loss = out['loss'].data_ptr()
   args.priorities = out['priorities'].data_ptr()
   args.weights = out['weights'].data_ptr()
-  args.mean_weighted_loss = out['mean_weighted_loss'].data_ptr()
+  args.mean_weighted_loss = (out['mean_weighted_loss'].data_ptr()
+                             if want_mean else None)
   args.grad_logits = out['grad_logits'].data_ptr() if want_grad else None
   _native.check(_native.lib().b2r_c51_loss(ctypes.byref(args),
                                            _native.current_stream()))

@@ -118,7 +118,8 @@ class OutOfGraphReplayBuffer(object):
                reward_dtype=np.float32,
                output='numpy',
                rng='reference',
-               seed=0):
+               seed=0,
+               reuse_outputs=False):
     assert isinstance(observation_shape, tuple)
     if replay_capacity < update_horizon + stack_size:
       raise ValueError('There is not enough capacity to cover '
@@ -157,6 +158,11 @@ class OutOfGraphReplayBuffer(object):
     self._rng = rng
     self._seed = int(seed)
     self._draw_counter = 0
+    # The reference returns fresh arrays on every call (its StagingArea keeps
+    # pointers, CRB:419-421).  reuse_outputs=True hands back the same buffers per
+    # batch size instead: no allocation on the sampling path.
+    self._reuse_outputs = bool(reuse_outputs)
+    self._output_cache = {}
     self._lib = _native.lib()
     self._create_storage()
     # circular_replay_buffer.py:181-183
@@ -234,6 +240,9 @@ class OutOfGraphReplayBuffer(object):
     return self.get_storage_signature()
 
   def get_storage_signature(self):
+    cached = self.__dict__.get('_storage_signature_cache')
+    if cached is not None:
+      return list(cached)
     storage_elements = [
         ReplayElement('observation', self._observation_shape,
                       self._observation_dtype),
@@ -243,6 +252,7 @@ class OutOfGraphReplayBuffer(object):
     ]
     for extra_replay_element in self._extra_storage_types:
       storage_elements.append(extra_replay_element)
+    self._storage_signature_cache = tuple(storage_elements)
     return storage_elements
 
   def get_transition_elements(self, batch_size=None):
@@ -336,16 +346,29 @@ class OutOfGraphReplayBuffer(object):
                      _native.PRIORITY_EXPLICIT)
 
   def _native_add(self, values, priority, priority_mode):
-    rows = []
-    for value, element in zip(values, self.get_storage_signature()):
-      rows.append(np.ascontiguousarray(
-          np.asarray(value).astype(element.type, copy=False)))
-    extras = (ctypes.c_void_p * _native.MAX_EXTRAS)()
-    for k, row in enumerate(rows[4:]):
-      extras[k] = row.ctypes.data
+    # One preallocated, correctly typed row buffer per storage element: numpy
+    # assignment performs the reference's cast (CRB:280-282) without allocating.
+    rows = self.__dict__.get('_row_buffers')
+    if rows is None:
+      rows = [np.zeros(tuple(e.shape), dtype=e.type)
+              for e in self.get_storage_signature()]
+      self._row_buffers = rows
+      self._row_pointers = [r.ctypes.data for r in rows]
+      self._extra_pointers = (ctypes.c_void_p * _native.MAX_EXTRAS)()
+      for k, r in enumerate(rows[4:]):
+        self._extra_pointers[k] = r.ctypes.data
+    ptrs = list(self._row_pointers)
+    obs = values[0]
+    if (isinstance(obs, np.ndarray) and obs.dtype == rows[0].dtype and
+        obs.flags['C_CONTIGUOUS']):
+      ptrs[0] = obs.ctypes.data  # staged by the library before add() returns
+    else:
+      rows[0][...] = obs
+    for k in range(1, len(rows)):
+      rows[k][...] = values[k]
     status = self._lib.b2r_add(
-        self._h, rows[0].ctypes.data, rows[1].ctypes.data, rows[2].ctypes.data,
-        rows[3].ctypes.data, extras, priority, priority_mode, self._stream())
+        self._h, ptrs[0], ptrs[1], ptrs[2], ptrs[3], self._extra_pointers,
+        priority, priority_mode, self._stream())
     if status == _native.ERR_NEGATIVE_PRIORITY:
       raise ValueError(_native.last_error())
     _native.check(status)
@@ -450,6 +473,8 @@ class OutOfGraphReplayBuffer(object):
     return [int(i) for i in out]
 
   def _alloc_outputs(self, batch_size, on_device):
+    if self._reuse_outputs and (batch_size, on_device) in self._output_cache:
+      return self._output_cache[(batch_size, on_device)]
     elements = self.get_transition_elements(batch_size)
     if on_device:
       torch = _torch()
@@ -474,6 +499,8 @@ class OutOfGraphReplayBuffer(object):
       else:
         batch.extras[extra] = p
         extra += 1
+    if self._reuse_outputs:
+      self._output_cache[(batch_size, on_device)] = (elements, arrays, batch)
     return elements, arrays, batch
 
   def _check_explicit_indices(self, indices):

@@ -63,7 +63,8 @@ class OutOfGraphPrioritizedReplayBuffer(
                reward_dtype=np.float32,
                output='numpy',
                rng='reference',
-               seed=0):
+               seed=0,
+               reuse_outputs=False):
     super(OutOfGraphPrioritizedReplayBuffer, self).__init__(
         observation_shape=observation_shape,
         stack_size=stack_size,
@@ -81,7 +82,8 @@ class OutOfGraphPrioritizedReplayBuffer(
         reward_dtype=reward_dtype,
         output=output,
         rng=rng,
-        seed=seed)
+        seed=seed,
+        reuse_outputs=reuse_outputs)
     tree_handle = ctypes.c_void_p(self._lib.b2r_buffer_tree(self._h))
     # Reads of the tree must see every staged add (PRB:139-140 sets the priority
     # inside add), hence the flush hook.
@@ -278,12 +280,14 @@ class WrappedPrioritizedReplayBuffer(
                reward_shape=(),
                reward_dtype=np.float32,
                rng='reference',
-               seed=0):
+               seed=0,
+               reuse_outputs=False):
     memory = OutOfGraphPrioritizedReplayBuffer(
         observation_shape, stack_size, replay_capacity, batch_size,
         update_horizon, gamma, max_sample_attempts,
         extra_storage_types=extra_storage_types,
-        observation_dtype=observation_dtype, output='torch', rng=rng, seed=seed)
+        observation_dtype=observation_dtype, output='torch', rng=rng, seed=seed,
+        reuse_outputs=reuse_outputs)
     super(WrappedPrioritizedReplayBuffer, self).__init__(
         observation_shape,
         stack_size,
