@@ -58,6 +58,12 @@ def parse_args():
   p.add_argument('--no-sweep', action='store_true')
   p.add_argument('--no-cpu-baseline', action='store_true')
   p.add_argument('--no-e2e', action='store_true')
+  p.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'],
+                 help='N>1: shard totals over peer memory inside the sampling '
+                      'kernel (default) or an NCCL all-gather before it')
+  p.add_argument('--unfused', action='store_true',
+                 help='four separate calls (sample+gather, loss, write-back) on one '
+                      'stream instead of b2r_train_step_device')
   return p.parse_args()
 
 
@@ -216,6 +222,7 @@ class GpuWorkload(object):
     self.support = rainbow_agent.make_support(VMAX, NUM_ATOMS)
     self.gamma_n = float(np.float32(math.pow(GAMMA, HORIZON)))
     self.seed = seed + rank
+    self.fused = True
     self._plans = {}
 
   def plan(self, batch):
@@ -269,6 +276,12 @@ class GpuWorkload(object):
     t, b, c = self.plan(batch)
     nat, lib = self.native, self.lib
     stream = nat.current_stream()
+    if self.fused:
+      # one call: the sampler writes the scalar columns, the frame copies run on a
+      # forked stream beside loss + write-back and rejoin before the call returns
+      nat.check(lib.b2r_train_step_device(
+          self.h, batch, self.seed, 0, ctypes.byref(b), ctypes.byref(c), stream))
+      return
     nat.check(lib.b2r_sample_transition_batch_device(
         self.h, batch, self.seed, 0, ctypes.byref(b), stream))
     nat.check(lib.b2r_c51_loss(ctypes.byref(c), stream))
@@ -366,73 +379,61 @@ def measure_gather_roofline(torch, wl, batch, peak_gbs, launches=200):
   }
 
 
-def measure_e2e(torch, wl, batch, steps, update_period=4):
-  """The same metric through the public Python API with HOST buffers in the loop.
+def measure_e2e(torch, wl, batch, steps, update_period=4, pipeline_depth=2):
+  """The same metric end to end through the public host-facing API.
 
   Per step, as the agent drives the replay (dqn_agent.py:359-442): `update_period`
-  new transitions are add()-ed from host memory (H2D of the frames), the network
-  outputs are copied in from pinned host memory (H2D), then sample -> gather ->
-  C51 loss -> priority write-back run through WrappedPrioritizedReplayBuffer /
-  rainbow_agent (device tensors, as the reference's wrapper hands TF tensors to the
-  graph), and the per-row losses are read back (D2H, synchronising)."""
+  new transitions are add()-ed from HOST frames (staged and copied to HBM), then
+  `ReplayTrainer.step` takes both network outputs from pinned HOST memory (H2D),
+  runs sample -> gather -> C51 loss -> priority write-back on the device and
+  hands the per-row losses back in HOST memory (D2H).  With pipeline_depth d the
+  losses returned by a call are those of the step queued d calls earlier, so the
+  host does not wait for the step it has just queued (d = 0: fully synchronous).
+  Every step's copies and kernels are inside the timed region either way."""
   from dopamine_b200.replay_memory import prioritized_replay_buffer as prb
-  ra = wl.ra
-  wrapped = prb.WrappedPrioritizedReplayBuffer.__new__(
-      prb.WrappedPrioritizedReplayBuffer)
-  wrapped.memory = wl.mem            # the benchmark's filled 1M buffer
-  wrapped.batch_size = batch
-  wrapped.transition = None
-  mem = wl.mem
-  mem._output, mem._reuse_outputs = 'torch', True  # pylint: disable=protected-access
-  mem._batch_size = batch  # pylint: disable=protected-access
+  ra, mem = wl.ra, wl.mem
+  trainer = ra.ReplayTrainer(mem, NUM_ACTIONS, NUM_ATOMS, VMAX, batch_size=batch,
+                             pipeline_depth=pipeline_depth, seed=wl.seed)
   rng = np.random.RandomState(3)
   frames = rng.randint(0, 256, size=(64, 84, 84)).astype(np.uint8)
   online_h = wl.online[:batch].cpu().pin_memory()
   target_h = wl.target[:batch].cpu().pin_memory()
-  online_d = torch.empty_like(wl.online[:batch])
-  target_d = torch.empty_like(wl.target[:batch])
-  loss_h = torch.empty(batch, dtype=torch.float32).pin_memory()
-  out = None
+  online_p, target_p = online_h.data_ptr(), target_h.data_ptr()
   counter = [0]
+  sentinel = prb.MAX_RECORDED_PRIORITY
+  stream = wl.native.current_stream()
 
   def one():
-    nonlocal out
     for _ in range(update_period):
       k = counter[0]
       counter[0] += 1
-      wrapped.add(frames[k & 63], k % NUM_ACTIONS, 0.5, int(k % 1000 == 999),
-                  prb.MAX_RECORDED_PRIORITY)
-    online_d.copy_(online_h, non_blocking=True)
-    target_d.copy_(target_h, non_blocking=True)
-    t = wrapped.sample()
-    out = ra.c51_loss(online_d, target_d, t['action'], t['reward'], t['terminal'],
-                      t['sampling_probabilities'], wl.support, wl.gamma_n,
-                      want_mean=False, out=out)
-    wrapped.tf_set_priority(t['indices'], out['priorities'])
-    loss_h.copy_(out['loss'], non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    return float(loss_h[0])
+      mem.add(frames[k & 63], k % NUM_ACTIONS, 0.5, int(k % 1000 == 999), sentinel)
+    return trainer.step_pointers(online_p, target_p, stream)
 
-  for _ in range(10):
+  for _ in range(20):
     one()
+  trainer.drain()
   torch.cuda.synchronize()
   t0 = time.perf_counter()
   for _ in range(steps):
     one()
+  _, last = trainer.drain()
   torch.cuda.synchronize()
   dt = time.perf_counter() - t0
+  assert last == steps + 20 - 1, (last, steps)
+  wl.native.check(wl.lib.b2r_check(wl.h, stream))
   row = 7056 + 16  # staged row: frame + action + reward + terminal (padded)
   h2d = update_period * row + (online_h.numel() + target_h.numel()) * 4
   d2h = batch * 4
-  e2e = {'value': round(batch * steps / dt, 1), 'unit': UNIT,
-         'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-         'ms_per_step': round(dt * 1e3 / steps, 4), 'steps': steps,
-         'what': ('public Python API per step: %d x add() of host frames, H2D of '
-                  'both logits tensors from pinned memory, sample+gather+C51+'
-                  'set_priority on device tensors, D2H of the per-row losses'
-                  % update_period)}
-  mem._output, mem._reuse_outputs = 'numpy', False  # pylint: disable=protected-access
-  return e2e
+  return {'value': round(batch * steps / dt, 1), 'unit': UNIT,
+          'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+          'ms_per_step': round(dt * 1e3 / steps, 4), 'steps': steps,
+          'pipeline_depth': pipeline_depth,
+          'what': ('public host API per step: %d x add() of host frames + '
+                   'ReplayTrainer.step(): H2D of both logits tensors from pinned '
+                   'memory, sample+gather+C51+set_priority on the device, D2H of '
+                   'the per-row losses (returned %d steps later)'
+                   % (update_period, pipeline_depth))}
 
 
 def measure_e2e_host_batch(torch, wl, batch, steps):
@@ -541,39 +542,68 @@ def _replica(args):
   return steps, dt
 
 
+def _usable_replicas(per_replica_bytes, cap=64):
+  """Replica processes the host can carry: one per core, bounded by free memory."""
+  cores = os.cpu_count() or 1
+  try:
+    import psutil
+    free = psutil.virtual_memory().available
+  except Exception:  # pylint: disable=broad-except
+    free = 16 << 30
+  by_mem = int(free * 0.4 // per_replica_bytes)
+  return max(1, min(cores, cap, by_mem))
+
+
 def run_reference(args):
   """--impl reference: the reference's CPU implementation of the path (oracle
-  port; the reference itself is TF-1.x Python and cannot travel) on all host
-  cores, as independent single-threaded replicas (it has no threading)."""
+  port; the reference itself is TF-1.x Python and cannot travel) on the host.
+
+  The reference is single-threaded by construction (one Python process, the GIL,
+  a sequential `random` stream feeding one replay memory), so one core is every
+  host thread it can use for THIS workload (one replay memory of `capacity`
+  transitions): that is `value`.  What the same cores deliver as independent
+  replica processes, each with its own smaller replay memory — a different job,
+  the CPU analogue of running one shard per GPU — is reported beside it in
+  `all_cores_replicas`."""
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
   import multiprocessing as mp
-  cores = os.cpu_count() or 1
-  replicas = max(1, min(cores, 16))
-  per_cap = max(65536, args.capacity // replicas)
-  budget = 10.0
+  budget = 12.0
   t0 = time.perf_counter()
+  port = build_cpu_port(args.capacity, args.batch)
+  cpu_steps(port, args.batch, 0.0, max(3, min(args.warmup, 20)))
+  steps, dt = cpu_steps(port, args.batch, budget, 100000)
+  del port
+  rate = args.batch * steps / dt
+  per_cap = 65536
+  replicas = _usable_replicas(per_cap * (FRAME + 64) * 1.2)
   with mp.get_context('fork').Pool(replicas) as pool:
-    res = pool.map(_replica, [(args.batch, per_cap, budget, 100 + r)
+    res = pool.map(_replica, [(args.batch, per_cap, 8.0, 100 + r)
                               for r in range(replicas)])
   wall = time.perf_counter() - t0
-  rate = sum(args.batch * s / dt for s, dt in res)
-  steps_total = sum(s for s, _ in res)
+  rate_all = sum(args.batch * s / d for s, d in res)
   line = {
       'impl': 'reference', 'metric': METRIC, 'value': round(rate, 1),
       'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-      'warmup': args.warmup,
+      'warmup': args.warmup, 'cpu_steps_timed': steps,
       'ms_per_step': round(1e3 * args.batch / rate, 4),
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
       'dtype': 'u8', 'data': 'synthetic',
       'config': {'workload': workload_name(args.batch, args.capacity, 1)},
       'cpu_baseline': {
-          'value': round(rate, 1), 'unit': UNIT, 'cores': replicas,
-          'kind': 'port',
-          'sample': '{} replica processes x ~{:.0f} s, {} steps of batch {} in '
-                    'total, capacity {} each (wall {:.0f} s)'.format(
-                        replicas, budget, steps_total, args.batch, per_cap, wall),
+          'value': round(rate, 1), 'unit': UNIT, 'cores': 1, 'kind': 'port',
+          'sample': '{} steps of batch {} in {:.1f} s, one process, capacity {} '
+                    '(oracle port of the reference: Python/numpy, single-threaded '
+                    'as the reference is)'.format(steps, args.batch, dt,
+                                                  args.capacity),
+          'all_cores_replicas': {
+              'value': round(rate_all, 1), 'unit': UNIT, 'cores': replicas,
+              'host_cores': os.cpu_count(),
+              'sample': '{} independent replica processes x ~8 s, capacity {} '
+                        'each: not one replay memory, reported for scale'.format(
+                            replicas, per_cap)},
+          'wall_s': round(wall, 1),
       },
       'e2e': {'value': round(rate, 1), 'unit': UNIT, 'h2d_bytes_per_step': 0,
               'd2h_bytes_per_step': 0},
@@ -610,6 +640,7 @@ def main():
   sweep_batches = [] if args.no_sweep else [256, 1024, 4096]
   wl = GpuWorkload(args.capacity,
                    max([args.batch, args.batch * world] + sweep_batches), rank)
+  wl.fused = not args.unfused
   launches_before = _native.lib().b2r_launch_count()
   wl.step(args.batch)
   launches_per_step = _native.lib().b2r_launch_count() - launches_before
@@ -617,7 +648,11 @@ def main():
 
   if world > 1:
     from dopamine_b200.replay_memory import sharded_replay
-    sharded = sharded_replay.ShardedStep(wl, args.batch * world, world, rank, dist)
+    exchange = None
+    if args.exchange == 'p2p':
+      exchange = sharded_replay.PeerExchange(rank=rank, world_size=world)
+    sharded = sharded_replay.ShardedStep(wl, args.batch * world, world, rank, dist,
+                                         exchange=exchange)
     step_fn = sharded.step
     launches_per_step = sharded.launches_per_step()
     use_graph = not args.no_graph  # NCCL all-gather is captured with the kernels
@@ -649,7 +684,14 @@ def main():
           'workload': workload_name(args.batch, args.capacity, world),
           'l2': 'inputs larger than L2: 7.06 GB frame ring per GPU, fresh random '
                 'indices every step (device Philox); no flush needed',
-          'launch': 'CUDA graph replay' if use_graph else 'eager launches',
+          'launch': ('CUDA graph replay' if use_graph else 'eager launches') + (
+              '; one b2r_train_step_device call per step: frame-stack copies on a '
+              'forked stream beside loss + write-back, joined every step'
+              if wl.fused and world == 1 else '') + (
+                  '; shard totals exchanged over peer memory (NVLink) inside the '
+                  'sampling kernel, no NCCL call on the path'
+                  if world > 1 and args.exchange == 'p2p' else
+                  '; NCCL all-gather of shard totals' if world > 1 else ''),
           'rng': 'device Philox4x32-10',
       },
       'gpu_launches': int(launches_per_step * args.steps),
@@ -672,8 +714,11 @@ def main():
     if not args.no_e2e and world == 1:
       line['e2e_host_batch'] = measure_e2e_host_batch(
           torch, wl, args.batch, max(50, min(args.steps, 300)))
+      line['e2e_sync'] = measure_e2e(torch, wl, args.batch,
+                                     max(50, min(args.steps, 2000)),
+                                     pipeline_depth=0)
       line['e2e'] = measure_e2e(torch, wl, args.batch,
-                                max(50, min(args.steps, 2000)))
+                                max(50, min(args.steps, 5000)))
     if not args.no_cpu_baseline and world == 1:
       line['cpu_baseline'] = cpu_baseline(args.batch, args.capacity)
     print(json.dumps(line))

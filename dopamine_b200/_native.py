@@ -22,6 +22,10 @@ ERR_SAMPLE_ATTEMPTS = 5
 ERR_TOO_FEW_TRANSITIONS = 6
 ERR_INDEX_RANGE = 7
 ERR_UNSUPPORTED = 8
+ERR_EXCHANGE = 9
+QUEUE_FULL = 10
+STREAM_NONE = ctypes.c_void_p(-1)
+IPC_HANDLE_BYTES = 64
 
 PRIORITY_EXPLICIT = 0
 PRIORITY_MAX_RECORDED = 1
@@ -91,6 +95,19 @@ class C51Args(ctypes.Structure):
       ('mean_weighted_loss', c_void_p),
       ('grad_logits', c_void_p),
       ('batch_count', c_void_p),
+      ('min_probability', c_void_p),
+  ]
+
+
+class TrainerConfig(ctypes.Structure):
+  _fields_ = [
+      ('batch', c_int32),
+      ('num_actions', c_int32),
+      ('num_atoms', c_int32),
+      ('vmax', c_float),
+      ('cumulative_gamma', c_float),
+      ('seed', c_uint64),
+      ('pipeline_depth', c_int32),
   ]
 
 
@@ -122,6 +139,8 @@ SIGNATURES = {
     'b2r_buffer_tree': (c_void_p, [c_void_p]),
     'b2r_add': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                         P(c_void_p), c_double, c_int, c_void_p]),
+    'b2r_add_atari': (c_int, [c_void_p, c_void_p, c_int32, c_float,
+                              ctypes.c_uint8, c_double, c_int, c_void_p]),
     'b2r_flush': (c_int, [c_void_p, c_void_p]),
     'b2r_add_count': (c_int64, [c_void_p]),
     'b2r_cursor': (c_int64, [c_void_p]),
@@ -168,6 +187,28 @@ SIGNATURES = {
     'b2r_c51_project': (c_int, [c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
     'b2r_c51_loss': (c_int, [P(C51Args), c_void_p]),
+    'b2r_train_step_device': (c_int, [c_void_p, c_int32, c_uint64, c_uint64,
+                                      P(Batch), P(C51Args), c_void_p]),
+    'b2r_train_step_sharded_device': (c_int, [
+        c_void_p, c_void_p, c_int32, c_uint64, c_uint64, P(Batch), P(C51Args),
+        c_void_p, c_void_p, c_void_p]),
+    'b2r_exchange_create': (c_int, [c_int32, c_int32, P(c_void_p)]),
+    'b2r_exchange_destroy': (c_int, [c_void_p]),
+    'b2r_exchange_local_handle': (c_int, [c_void_p, c_void_p]),
+    'b2r_exchange_connect': (c_int, [c_void_p, c_void_p]),
+    'b2r_exchange_connect_pointers': (c_int, [c_void_p, P(c_void_p)]),
+    'b2r_exchange_mailbox': (c_void_p, [c_void_p]),
+    'b2r_exchange_set_timeout': (c_int, [c_void_p, c_double]),
+    'b2r_exchange_publish_device': (c_int, [c_void_p, c_void_p, c_void_p]),
+    'b2r_sample_indices_sharded_p2p_device': (c_int, [
+        c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_uint64,
+        c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'b2r_trainer_create': (c_int, [c_void_p, P(TrainerConfig), P(c_void_p)]),
+    'b2r_trainer_destroy': (c_int, [c_void_p]),
+    'b2r_trainer_step_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
+                                      P(c_int64), c_void_p]),
+    'b2r_trainer_drain': (c_int, [c_void_p, c_void_p, P(c_int64), c_void_p]),
+    'b2r_trainer_views': (c_int, [c_void_p, P(Batch), P(C51Args)]),
 }
 
 _lib = None

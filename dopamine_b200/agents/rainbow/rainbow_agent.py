@@ -229,3 +229,166 @@ class C51Loss(object):
     return cls._function().apply(online_logits, target_logits, actions, rewards,
                                  terminals, sampling_probabilities, support,
                                  gamma_n)
+
+
+# ---------------------------------------------------------------------------
+# The whole hot path in one native call (include/b200_replay.h, "The whole hot
+# path in one call"): what one sess.run of the train op does around the network.
+# ---------------------------------------------------------------------------
+def train_step(memory, online_logits, target_logits, support, cumulative_gamma,
+               batch_size=None, out=None):
+  """Prioritized sample -> C51 loss -> priority write-back in ONE native call.
+
+  Equivalent to `memory.sample_transition_batch()` (device RNG), `c51_loss(...)`
+  and `memory.set_priority(indices, priorities)`, but the sampler writes the
+  scalar columns of the batch itself and the frame-stack copies run on a forked
+  stream beside the loss and the write-back (they rejoin the current stream
+  before this returns).
+
+  Args:
+    memory: OutOfGraphPrioritizedReplayBuffer (uint8 terminals, f32 rewards,
+      scalar int32 actions).
+    online_logits, target_logits: (B, A, N) f32 CUDA tensors.
+    out: dict returned by an earlier call with the same shapes (reused).
+  Returns:
+    (transition tuple in get_transition_elements() order, dict with 'loss',
+    'priorities', 'weights' (B,) CUDA tensors).
+  """
+  torch = _torch()
+  b, a, n = online_logits.shape
+  batch_size = b if batch_size is None else batch_size
+  assert b == batch_size and tuple(target_logits.shape) == (b, a, n)
+  assert online_logits.dtype == torch.float32 and online_logits.is_cuda
+  assert target_logits.dtype == torch.float32 and target_logits.is_cuda
+  _, arrays, batch = memory._alloc_outputs(batch_size, True)  # pylint: disable=protected-access
+  if out is None:
+    out = {k: torch.empty(b, dtype=torch.float32, device='cuda')
+           for k in ('loss', 'priorities', 'weights')}
+  args = _native.C51Args()
+  args.batch, args.num_actions, args.num_atoms = b, a, n
+  args.cumulative_gamma = float(np.float32(cumulative_gamma))
+  args.support = support.data_ptr()
+  args.target_logits = target_logits.contiguous().data_ptr()
+  args.online_logits = online_logits.contiguous().data_ptr()
+  args.loss = out['loss'].data_ptr()
+  args.priorities = out['priorities'].data_ptr()
+  args.weights = out['weights'].data_ptr()
+  status = _native.lib().b2r_train_step_device(
+      memory._h, batch_size, memory._seed, memory._next_offset(),  # pylint: disable=protected-access
+      ctypes.byref(batch), ctypes.byref(args), _native.current_stream())
+  if status == _native.ERR_UNSUPPORTED:
+    raise NotImplementedError(_native.last_error())
+  _native.check(status)
+  return tuple(arrays), out
+
+
+class _DeviceView(object):
+  """A device buffer owned by the native library, for torch.as_tensor."""
+
+  def __init__(self, pointer, shape, typestr):
+    self.__cuda_array_interface__ = {
+        'shape': tuple(shape), 'typestr': typestr, 'data': (int(pointer), False),
+        'version': 2, 'strides': None}
+
+
+class ReplayTrainer(object):
+  """Pipelined host-facing training iteration (b2r_trainer_* in the C ABI).
+
+  `step(online_logits, target_logits)` takes the two network outputs as HOST
+  float32 arrays of shape (B, A, N) (page-locked memory keeps the copies
+  asynchronous: do not overwrite it before the step has run), applies the staged
+  `memory.add()`s, runs sample -> C51 loss -> priority write-back on the device and
+  hands back the per-row losses of the step queued `pipeline_depth` calls earlier,
+  so the host never waits for the step it has just queued.
+  """
+
+  def __init__(self, memory, num_actions, num_atoms=51, vmax=10.,
+               batch_size=None, pipeline_depth=2, seed=0):
+    self._memory = memory
+    self._lib = _native.lib()
+    cfg = _native.TrainerConfig()
+    cfg.batch = memory._batch_size if batch_size is None else batch_size  # pylint: disable=protected-access
+    cfg.num_actions, cfg.num_atoms = num_actions, num_atoms
+    cfg.vmax = float(vmax)
+    cfg.cumulative_gamma = float(np.float32(math.pow(
+        memory._gamma, memory._update_horizon)))  # pylint: disable=protected-access
+    cfg.seed = int(seed)
+    cfg.pipeline_depth = int(pipeline_depth)
+    self.batch_size, self.num_actions, self.num_atoms = (
+        cfg.batch, num_actions, num_atoms)
+    handle = ctypes.c_void_p()
+    status = self._lib.b2r_trainer_create(memory._h, ctypes.byref(cfg),  # pylint: disable=protected-access
+                                          ctypes.byref(handle))
+    if status == _native.ERR_UNSUPPORTED:
+      raise NotImplementedError(_native.last_error())
+    _native.check(status)
+    self._h = handle
+    self._loss = np.empty(cfg.batch, dtype=np.float32)
+    self._loss_ptr = self._loss.ctypes.data
+    self._step = ctypes.c_int64(-1)
+    self._step_ref = ctypes.byref(self._step)
+
+  def __del__(self):
+    if getattr(self, '_h', None):
+      self._lib.b2r_trainer_destroy(self._h)
+      self._h = None
+
+  def step_pointers(self, online_ptr, target_ptr, stream=None):
+    """As `step`, from raw host addresses (no per-call Python work)."""
+    status = self._lib.b2r_trainer_step_host(
+        self._h, online_ptr, target_ptr, self._loss_ptr, self._step_ref,
+        _native.current_stream() if stream is None else stream)
+    if status:
+      _native.check(status)
+    return self._step.value
+
+  def step(self, online_logits, target_logits):
+    """Queues one iteration; returns (losses or None, step number or -1)."""
+    shape = (self.batch_size, self.num_actions, self.num_atoms)
+    pointers = []
+    for x in (online_logits, target_logits):
+      if hasattr(x, 'data_ptr'):  # torch CPU tensor (e.g. pinned)
+        assert not x.is_cuda and tuple(x.shape) == shape and x.is_contiguous()
+        pointers.append(x.data_ptr())
+      else:
+        assert x.dtype == np.float32 and x.shape == shape
+        pointers.append(_native.ptr(x))
+    done = self.step_pointers(pointers[0], pointers[1])
+    return (self._loss.copy() if done >= 0 else None), done
+
+  def drain(self):
+    """Waits for every queued step; returns (losses of the last one, its number)."""
+    _native.check(self._lib.b2r_trainer_drain(
+        self._h, self._loss_ptr, self._step_ref, _native.current_stream()))
+    done = self._step.value
+    return (self._loss.copy() if done >= 0 else None), done
+
+  def views(self):
+    """The trainer's device buffers as torch tensors: (transition dict, loss dict)."""
+    torch = _torch()
+    batch, c51 = _native.Batch(), _native.C51Args()
+    _native.check(self._lib.b2r_trainer_views(self._h, ctypes.byref(batch),
+                                              ctypes.byref(c51)))
+    mem, b = self._memory, self.batch_size
+    obs = tuple(mem._observation_shape) + (mem._stack_size,)  # pylint: disable=protected-access
+
+    def view(pointer, shape, typestr):
+      return torch.as_tensor(_DeviceView(pointer, shape, typestr), device='cuda')
+
+    transition = {
+        'state': view(batch.state, (b,) + obs, '|u1'),
+        'action': view(batch.action, (b,), '<i4'),
+        'reward': view(batch.reward, (b,), '<f4'),
+        'next_state': view(batch.next_state, (b,) + obs, '|u1'),
+        'next_action': view(batch.next_action, (b,), '<i4'),
+        'next_reward': view(batch.next_reward, (b,), '<f4'),
+        'terminal': view(batch.terminal, (b,), '|u1'),
+        'indices': view(batch.indices, (b,), '<i4'),
+        'sampling_probabilities': view(batch.sampling_probabilities, (b,), '<f4'),
+    }
+    losses = {
+        'loss': view(c51.loss, (b,), '<f4'),
+        'priorities': view(c51.priorities, (b,), '<f4'),
+        'weights': view(c51.weights, (b,), '<f4'),
+    }
+    return transition, losses

@@ -8,8 +8,8 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 LIB = os.path.join(PKG, 'libb200replay.so')
 SOURCES = ['common.cu', 'tree.cu', 'replay.cu', 'sample.cu', 'gather.cu',
-           'c51.cu']
-HEADERS = ['common.cuh', 'tree.cuh', 'replay.cuh',
+           'c51.cu', 'step.cu', 'exchange.cu']
+HEADERS = ['common.cuh', 'tree.cuh', 'replay.cuh', 'gather.cuh',
            os.path.join(ROOT, 'include', 'b200_replay.h')]
 
 NVCC_FLAGS = [
@@ -34,10 +34,19 @@ def _stale(target, deps):
   return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra_flags=()):
-  """Compiles every .cu for sm_100a and links the C-ABI shared library."""
+TRACE_LIB = os.path.join(ROOT, 'profiles', 'micro', 'libb200replay_trace.so')
+
+
+def build(force=False, verbose=False, extra_flags=(), trace=False):
+  """Compiles every .cu for sm_100a and links the C-ABI shared library.
+
+  trace=True builds the instrumented copy (-DB2R_TRACE: clock64 phase marks) used
+  by profiles/micro/trace_step.py; it is never the library the package loads."""
   nvcc = _nvcc()
-  obj_dir = os.path.join(HERE, '_obj')
+  obj_dir = os.path.join(HERE, '_obj_trace' if trace else '_obj')
+  lib_path = TRACE_LIB if trace else LIB
+  if trace:
+    extra_flags = tuple(extra_flags) + ('-DB2R_TRACE',)
   os.makedirs(obj_dir, exist_ok=True)
   headers = [h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS]
   objects = []
@@ -50,15 +59,17 @@ def build(force=False, verbose=False, extra_flags=()):
       if verbose:
         print(' '.join(cmd), file=sys.stderr)
       subprocess.check_call(cmd)
-  if force or _stale(LIB, objects):
+  if force or _stale(lib_path, objects):
     cmd = [nvcc, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a',
-           '-o', LIB] + objects + ['-lcudart_static', '-lpthread', '-ldl', '-lrt']
+           '-o', lib_path] + objects + ['-lcudart_static', '-lpthread', '-ldl',
+                                        '-lrt']
     if verbose:
       print(' '.join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
-  return LIB
+  return lib_path
 
 
 if __name__ == '__main__':
   print(build(force='--force' in sys.argv, verbose=True,
-              extra_flags=('-Xptxas', '-v') if '--ptxas' in sys.argv else ()))
+              extra_flags=('-Xptxas', '-v') if '--ptxas' in sys.argv else (),
+              trace='--trace' in sys.argv))

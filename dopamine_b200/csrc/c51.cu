@@ -73,7 +73,6 @@ struct LossArgs {
   float *weighted;        // scratch (B,): w_b * loss_b, reduced by the last CTA
   unsigned int *ticket;   // scratch: CTAs finished (self-resetting)
   int warps;              // warps per CTA = min(num_actions, 32)
-  int parts;              // threads cooperating on one projected atom
 };
 
 // One CTA per batch row, one warp per action (rainbow_agent.py:200-293):
@@ -96,12 +95,13 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x;
   const int N = a.u.num_atoms, A = a.u.num_actions, W = a.warps;
-  float *cur = smem + (size_t)warp * N;          // [W][N] scratch per warp
-  float *bestp = smem + (size_t)(W + warp) * N;  // [W][N] best action's probs
-  float *sup = smem + (size_t)2 * W * N;         // [N] Bellman support
-  float *part = sup + N;                         // [parts][N] projection partials
-  float *tgt = part + (size_t)a.parts * N;       // [N] projected target
+  float *bestp = smem + (size_t)warp * N;        // [W][N] best action's probs
+  float *sup = smem + (size_t)W * N;             // [N] Bellman support
+  int *win_base = reinterpret_cast<int *>(sup + N);  // [N] first atom of j's window
+  float *contrib = sup + 2 * N;                  // [N][4] hat(i, j) * p_j in the window
+  float *tgt = contrib + 4 * N;                  // [N] projected target
   float *onl = tgt + N;                          // [N] chosen online logits
+  float *zs = onl + N;                           // [N] the support, staged
   __shared__ float s_q[32];
   __shared__ int s_a[32];
   __shared__ float s_red[32];
@@ -121,8 +121,12 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   const float r = a.u.rewards[b];
   const float term = (float)a.u.terminals[b];
   const float my_prob = a.u.sampling_probabilities ? a.u.sampling_probabilities[b] : 1.f;
+  // min over the batch of the sampling probabilities (IS-weight normaliser):
+  // handed in by the sampler when it produced the batch, else reduced here.
   float pmin = INFINITY;
-  if (a.u.sampling_probabilities)
+  if (a.u.min_probability)
+    pmin = *a.u.min_probability;
+  else if (a.u.sampling_probabilities)
     for (int k = threadIdx.x; k < rows; k += blockDim.x)
       pmin = fminf(pmin, a.u.sampling_probabilities[k]);
   float zl[PL], xt[PL], xo[PL];
@@ -184,7 +188,6 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
         if (lane + 32 * t < N) bestp[lane + 32 * t] = e[t];
     }
   }
-  (void)cur;
   B2R_MARK(3);
   if (lane == 0) {
     s_q[warp] = best_q;
@@ -199,8 +202,11 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   // Bellman support (rainbow_agent.py:229-235)
   const float live = __fsub_rn(1.0f, term);
   const float gwt = __fmul_rn(a.u.cumulative_gamma, live);
-  for (int j = threadIdx.x; j < N; j += blockDim.x)
-    sup[j] = __fadd_rn(r, __fmul_rn(gwt, z[j]));
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const float zj = z[j];
+    zs[j] = zj;
+    sup[j] = __fadd_rn(r, __fmul_rn(gwt, zj));
+  }
   __syncthreads();
 
   B2R_MARK(4);
@@ -211,25 +217,47 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
     if (s_a[w] < 0) continue;
     if (s_q[w] > s_q[win] || (s_q[w] == s_q[win] && s_a[w] < s_a[win])) win = w;
   }
-  const float *next_p = smem + (size_t)(W + win) * N;
-  const float z0 = z[0], zlast = z[N - 1];
-  const float dz = __fsub_rn(z[1], z[0]);
-  const int per = (N + a.parts - 1) / a.parts;
+  const float *next_p = smem + (size_t)win * N;
+  const float z0 = zs[0], zlast = zs[N - 1];
+  const float dz = __fsub_rn(zs[1], zs[0]);
+  // The dense form sums hat(i, j) * p_j over all j, but hat is exactly 0 unless
+  // |clip(s_j) - z_i| < dz, i.e. for at most the atoms next to s_j: evaluate the
+  // reference's expression only inside a window of `span` atoms around s_j (wide
+  // enough for any rounding of the window position), then add each atom's
+  // contributions in ascending j.  Adding the skipped +0 terms changes nothing.
+  const int span = N < 4 ? N : 4;
 #pragma unroll 1
-  for (int t = threadIdx.x; t < a.parts * N; t += blockDim.x) {
-    const int i = t % N, pt = t / N;
-    const int j0 = pt * per, j1 = min(N, j0 + per);
-    const float zi = z[i];
-    float acc = 0.f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const float clipped = fminf(fmaxf(sup[j], z0), zlast);
+    int l = (int)floorf(__fdividef(clipped - z0, dz)) - 1;
+    l = max(0, min(l, N - span));
+    win_base[j] = l;
+    const float pj = next_p[j];
 #pragma unroll 1
-    for (int j = j0; j < j1; ++j) {
-      const float clipped = fminf(fmaxf(sup[j], z0), zlast);
-      const float gap = fabsf(__fsub_rn(clipped, zi));
-      float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
-      hat = fminf(fmaxf(hat, 0.f), 1.f);
-      acc = __fadd_rn(acc, __fmul_rn(hat, next_p[j]));
+    for (int k = 0; k < span; ++k) {
+      const float gap = fabsf(__fsub_rn(clipped, zs[l + k]));
+      float c = 0.f;
+      if (gap < dz) {
+        float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
+        hat = fminf(fmaxf(hat, 0.f), 1.f);
+        c = __fmul_rn(hat, pj);
+      }
+      contrib[4 * j + k] = c;
     }
-    part[(size_t)pt * N + i] = acc;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < N; ++j) {
+      const int k = i - win_base[j];
+      const bool in = (unsigned)k < (unsigned)span;
+      const float c = contrib[4 * j + (in ? k : 0)];
+      acc = __fadd_rn(acc, in ? c : 0.f);
+    }
+    tgt[i] = acc;
+    if (a.u.target) a.u.target[(size_t)b * N + i] = acc;
   }
   __syncthreads();
 
@@ -249,11 +277,7 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
     float ce_part = 0.f, tsum_part = 0.f;
 #pragma unroll 1
     for (int i = lane; i < N; i += 32) {
-      float t = part[i];
-#pragma unroll 1
-      for (int pt = 1; pt < a.parts; ++pt) t = __fadd_rn(t, part[(size_t)pt * N + i]);
-      tgt[i] = t;
-      if (a.u.target) a.u.target[(size_t)b * N + i] = t;
+      const float t = tgt[i];
       const float logp = __fsub_rn(__fsub_rn(x[i], m), lse);
       ce_part = __fadd_rn(ce_part, __fmul_rn(t, logp));
       tsum_part = __fadd_rn(tsum_part, t);
@@ -371,11 +395,7 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
   a.warps = args->num_actions < 32 ? args->num_actions : 32;
   if (args->batch > 256) a.warps = (a.warps + 2) / 3;
   const int threads = a.warps * 32;
-  a.parts = threads / args->num_atoms;
-  if (a.parts < 1) a.parts = 1;
-  if (a.parts > 4) a.parts = 4;
-  const size_t smem =
-      ((size_t)2 * a.warps + 3 + a.parts) * args->num_atoms * sizeof(float);
+  const size_t smem = ((size_t)a.warps + 9) * args->num_atoms * sizeof(float);
   if (smem > 48 * 1024 || args->num_atoms > 32 * b2r::kMaxAtomsPerLane)
     return fail(B2R_ERR_UNSUPPORTED, "num_atoms above 128 is not supported");
   if (args->batch > b2r::g_weighted_cap) {

@@ -12,6 +12,16 @@ bool pdl_enabled() {
   return on;
 }
 
+int chain_priority() {
+  static const int value = [] {
+    if (std::getenv("B2R_NO_PRIORITY") != nullptr) return 0;
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return 0;
+    return greatest;
+  }();
+  return value;
+}
+
 std::string &last_error_slot() {
   static thread_local std::string slot;
   return slot;
@@ -51,7 +61,7 @@ extern "C" {
 
 const char *b2r_last_error(void) { return b2r::last_error_slot().c_str(); }
 
-int b2r_abi_version(void) { return 1; }
+int b2r_abi_version(void) { return 2; }
 
 int64_t b2r_launch_count(void) {
   return b2r::g_launches.load(std::memory_order_relaxed);

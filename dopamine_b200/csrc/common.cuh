@@ -61,20 +61,43 @@ struct Bounce {
 // own predecessor has completed and flushed (pdl_acquire).
 bool pdl_enabled();
 
+// Launch priority of the latency chain (sample -> loss -> write-back): when the
+// HBM-bound frame copies of the same step run beside it on another stream, the
+// block scheduler must hand freed SM slots to the chain's CTAs first, or the chain
+// queues behind tens of thousands of copy CTAs.
+int chain_priority();  // the device's greatest stream priority (numerically lowest)
+
 template <typename... Params, typename... Args>
-cudaError_t launch(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem,
-                   cudaStream_t stream, Args &&...args) {
+cudaError_t launch_prio(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem,
+                        cudaStream_t stream, int priority, Args &&...args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (priority != 0) {
+    attr[n].id = cudaLaunchAttributePriority;
+    attr[n].val.priority = priority;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
+// Chain kernels (everything but the frame copies) run at chain priority.
+template <typename... Params, typename... Args>
+cudaError_t launch(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem,
+                   cudaStream_t stream, Args &&...args) {
+  return launch_prio(kernel, grid, block, smem, stream, chain_priority(),
+                     static_cast<Args &&>(args)...);
 }
 
 __device__ __forceinline__ void pdl_release() {
@@ -92,10 +115,19 @@ __device__ __forceinline__ void pdl_acquire() {
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)  \
       g_trace[i] = clock64();                                    \
   } while (0)
+// mark from thread 0 of a chosen CTA (blockIdx.x == blk)
+#define B2R_MARK_CTA(i, blk)                                 \
+  do {                                                       \
+    if ((int)blockIdx.x == (blk) && threadIdx.x == 0)        \
+      g_trace[i] = clock64();                                \
+  } while (0)
 #else
 #define B2R_TRACE_DECL
 #define B2R_MARK(i) \
   do {              \
+  } while (0)
+#define B2R_MARK_CTA(i, blk) \
+  do {                       \
   } while (0)
 #endif
 

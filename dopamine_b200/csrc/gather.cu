@@ -17,21 +17,12 @@
 // 16-pixel column of the span — up to 7 x LDG.128, a PRMT byte-transpose into the
 // [pixel][stack] interleave, 8 x STG.128 — with frames shared between state and
 // next_state read once.
-#include "replay.cuh"
+#include "gather.cuh"
 
 namespace b2r {
 namespace {
 
 B2R_TRACE_DECL
-
-constexpr int kMaxRowCopies = 3 + B2R_MAX_EXTRAS;
-
-struct RowCopy {
-  const uint8_t *src;
-  uint8_t *dst;
-  int32_t row_bytes;
-  int32_t at_next;  // 0: row i, 1: row (i + L) mod C
-};
 
 struct GatherArgs {
   int64_t capacity;
@@ -40,125 +31,12 @@ struct GatherArgs {
   int32_t obs_itemsize;
   const uint8_t *obs;
   const uint8_t *term_flag;
-  const void *reward;   // f32 or f64 column
-  int32_t reward_itemsize;
-  const float *discounts;
   const int32_t *indices;
   uint8_t *state, *next_state;
-  void *ret;            // n-step return, reward dtype
-  uint8_t *terminal_out;
-  int32_t terminal_itemsize;
-  int32_t *indices_out;
-  int32_t n_copies;
-  RowCopy copies[kMaxRowCopies];
-  const double *leaves;  // tree leaf level (nullable)
-  float *prio_out;
+  int32_t scalar_rows;   // grid rows of appended scalar CTAs (0: frames only)
+  ScalarArgs sc;
   const int32_t *count;  // nullable: device-side number of rows (<= batch)
 };
-
-// Trajectory length and terminal flag (circular_replay_buffer.py:517-527).  The
-// flags of up to 8 steps are loaded together (one round trip) before any is tested.
-__device__ __forceinline__ int trajectory_length(const uint8_t *__restrict__ term,
-                                                 int64_t i, int horizon,
-                                                 int64_t cap, bool *ends) {
-  for (int base = 0; base < horizon; base += 8) {
-    unsigned flags = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (base + k < horizon) {
-        int64_t s = i + base + k;
-        if (s >= cap) s -= cap;
-        flags |= (term[s] ? 1u : 0u) << k;
-      }
-    }
-    if (flags) {
-      *ends = true;
-      return base + __ffs(flags);
-    }
-  }
-  *ends = false;
-  return horizon;
-}
-
-// np.sum(discount[:L] * reward[i:i+L]) in numpy's evaluation order (probed on
-// numpy 2.3.5; DESIGN.md "n-step return"): L < 8: +0.0f then left to right;
-// 8 <= L <= 128: 8-lane unrolled block, pairwise combine, sequential tail.
-template <typename R>
-__device__ __forceinline__ R mul_rn(float d, R r);
-template <>
-__device__ __forceinline__ float mul_rn<float>(float d, float r) { return __fmul_rn(d, r); }
-template <>
-__device__ __forceinline__ double mul_rn<double>(float d, double r) { return __dmul_rn((double)d, r); }
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-
-template <typename R>
-__device__ __forceinline__ R nstep_return(const R *__restrict__ reward,
-                          const float *__restrict__ disc, int64_t i, int length,
-                          int64_t cap) {
-  auto term = [&](int k) {
-    int64_t s = i + k;
-    if (s >= cap) s -= cap;
-    return mul_rn<R>(disc[k], reward[s]);
-  };
-  if (length < 8) {
-    R acc = (R)0;
-#pragma unroll 1
-    for (int k = 0; k < length; ++k) acc = add_rn(acc, term(k));
-    return acc;
-  }
-  R r[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) r[j] = term(j);
-  int k = 8;
-#pragma unroll 1
-  for (; k < length - (length % 8); k += 8) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = add_rn(r[j], term(k + j));
-  }
-  R acc = add_rn(add_rn(add_rn(r[0], r[1]), add_rn(r[2], r[3])),
-                 add_rn(add_rn(r[4], r[5]), add_rn(r[6], r[7])));
-  for (; k < length; ++k) acc = add_rn(acc, term(k));
-  return acc;
-}
-
-// Scalar outputs: one THREAD per transition, in extra CTAs appended to the grid
-// (rows blockIdx.y >= batch), so they run beside the frame copies and every
-// transition's loads are in flight at once.
-__device__ void write_scalars(const GatherArgs &a, int b) {
-  const int64_t i = a.indices[b];
-  bool ends;
-  const int length = trajectory_length(a.term_flag, i, a.horizon, a.capacity, &ends);
-  int64_t nxt = i + length;
-  if (nxt >= a.capacity) nxt -= a.capacity;
-  if (a.ret) {
-    if (a.reward_itemsize == 4)
-      static_cast<float *>(a.ret)[b] = nstep_return<float>(
-          static_cast<const float *>(a.reward), a.discounts, i, length, a.capacity);
-    else
-      static_cast<double *>(a.ret)[b] = nstep_return<double>(
-          static_cast<const double *>(a.reward), a.discounts, i, length, a.capacity);
-  }
-  if (a.prio_out) a.prio_out[b] = (float)a.leaves[i];  // PRB:231-235
-  if (a.indices_out) a.indices_out[b] = (int32_t)i;
-  if (a.terminal_out) {
-    uint8_t *t = a.terminal_out + (int64_t)b * a.terminal_itemsize;
-    t[0] = ends ? 1 : 0;
-    for (int k = 1; k < a.terminal_itemsize; ++k) t[k] = 0;
-  }
-#pragma unroll 1
-  for (int c = 0; c < a.n_copies; ++c) {
-    const RowCopy rc = a.copies[c];
-    const uint8_t *s = rc.src + (rc.at_next ? nxt : i) * (int64_t)rc.row_bytes;
-    uint8_t *d = rc.dst + (int64_t)b * rc.row_bytes;
-    if ((rc.row_bytes & 3) == 0) {  // word rows (int32 actions, f32 rewards, ...)
-      for (int k = 0; k < rc.row_bytes; k += 4)
-        *reinterpret_cast<uint32_t *>(d + k) = *reinterpret_cast<const uint32_t *>(s + k);
-    } else {
-      for (int k = 0; k < rc.row_bytes; ++k) d[k] = s[k];
-    }
-  }
-}
 
 // [a0 a1 a2 a3] x4 frames -> 4 words [a_p b_p c_p d_p], p = 0..3.
 __device__ __forceinline__ uint4 interleave4(uint32_t a, uint32_t b, uint32_t c,
@@ -195,16 +73,18 @@ __device__ __forceinline__ uint4 load_frame16(const uint8_t *__restrict__ obs,
 
 // Fast path: stack 4, 1-byte pixels, obs_bytes % 16 == 0.
 // grid = (ceil(chunks / blockDim), batch); thread = one 16-pixel column.
-__global__ void __launch_bounds__(128) gather_stack4_u8_kernel(GatherArgs a) {
+// SCALARS: the grid carries appended CTAs that write the scalar columns.
+template <bool SCALARS>
+__global__ void __launch_bounds__(128, 12) gather_stack4_u8_kernel(const __grid_constant__ GatherArgs a) {
   B2R_MARK(0);
   pdl_release();
   pdl_acquire();
   B2R_MARK(1);
   const int rows = a.count ? min(*a.count, a.batch) : a.batch;
-  if (blockIdx.y >= a.batch) {  // appended scalar CTAs: one thread per transition
+  if (SCALARS && blockIdx.y >= a.batch) {  // appended scalar CTAs: one thread per transition
     const int b = ((blockIdx.y - a.batch) * gridDim.x + blockIdx.x) * blockDim.x +
                   threadIdx.x;
-    if (b < rows) write_scalars(a, b);
+    if (b < rows) write_scalars(a.sc, b, a.indices[b]);
     return;
   }
   const int b = blockIdx.y;
@@ -252,14 +132,14 @@ __global__ void __launch_bounds__(128) gather_stack4_u8_kernel(GatherArgs a) {
 }
 
 // General path: any stack size / element size. thread = one observation element.
-__global__ void __launch_bounds__(256) gather_generic_kernel(GatherArgs a) {
+__global__ void __launch_bounds__(256) gather_generic_kernel(const __grid_constant__ GatherArgs a) {
   pdl_release();
   pdl_acquire();
   const int rows = a.count ? min(*a.count, a.batch) : a.batch;
   if (blockIdx.y >= a.batch) {  // appended scalar CTAs: one thread per transition
     const int b = ((blockIdx.y - a.batch) * gridDim.x + blockIdx.x) * blockDim.x +
                   threadIdx.x;
-    if (b < rows) write_scalars(a, b);
+    if (b < rows) write_scalars(a.sc, b, a.indices[b]);
     return;
   }
   const int b = blockIdx.y;
@@ -296,33 +176,21 @@ __global__ void get_priority_kernel(const double *__restrict__ leaves, int64_t n
 
 }  // namespace
 
-int launch_gather(b2r_buffer *b, int32_t batch, const int32_t *indices_dev,
-                  const b2r_batch *out, cudaStream_t stream,
-                  const int32_t *count_dev) {
-  GatherArgs a;
-  a.count = count_dev;
-  a.capacity = b->cfg.capacity;
-  a.stack = b->cfg.stack_size;
-  a.horizon = b->cfg.update_horizon;
-  a.batch = batch;
-  a.obs_bytes = b->cfg.obs_bytes;
-  a.obs_itemsize = b->cfg.obs_itemsize;
-  a.obs = b->col[0].dev;
-  a.term_flag = b->term_flag;
-  a.reward = b->col[2].dev;
-  a.reward_itemsize = b->cfg.reward_itemsize;
-  a.discounts = b->discounts;
-  a.indices = indices_dev;
-  a.state = static_cast<uint8_t *>(out->state);
-  a.next_state = static_cast<uint8_t *>(out->next_state);
-  a.ret = out->reward;
-  a.terminal_out = static_cast<uint8_t *>(out->terminal);
-  a.terminal_itemsize = b->cfg.terminal_itemsize;
-  a.indices_out = out->indices;
-  a.n_copies = 0;
+void fill_scalar_args(const b2r_buffer *b, const b2r_batch *out, ScalarArgs *sc) {
+  sc->capacity = b->cfg.capacity;
+  sc->horizon = b->cfg.update_horizon;
+  sc->term_flag = b->term_flag;
+  sc->reward = b->col[2].dev;
+  sc->reward_itemsize = b->cfg.reward_itemsize;
+  sc->discounts = b->discounts;
+  sc->ret = out->reward;
+  sc->terminal_out = static_cast<uint8_t *>(out->terminal);
+  sc->terminal_itemsize = b->cfg.terminal_itemsize;
+  sc->indices_out = out->indices;
+  sc->n_copies = 0;
   auto add_copy = [&](int column, void *dst, int at_next) {
     if (!dst) return;
-    RowCopy &rc = a.copies[a.n_copies++];
+    RowCopy &rc = sc->copies[sc->n_copies++];
     rc.src = b->col[column].dev;
     rc.dst = static_cast<uint8_t *>(dst);
     rc.row_bytes = (int32_t)b->col[column].row_bytes;
@@ -333,25 +201,59 @@ int launch_gather(b2r_buffer *b, int32_t batch, const int32_t *indices_dev,
   add_copy(B2R_COL_REWARD, out->next_reward, 1);
   for (int e = 0; e < b->cfg.num_extras; ++e)
     add_copy(B2R_COL_EXTRA0 + e, out->extras[e], 0);
-  a.leaves = nullptr;
-  a.prio_out = nullptr;
+  sc->leaves = nullptr;
+  sc->prio_out = nullptr;
   if (b->tree && out->sampling_probabilities) {
-    a.leaves = b->tree->heap + b->tree->leaves;
-    a.prio_out = out->sampling_probabilities;
+    sc->leaves = b->tree->heap + b->tree->leaves;
+    sc->prio_out = out->sampling_probabilities;
   }
+  sc->fast = b->cfg.update_horizon <= kFastHorizon && b->cfg.reward_itemsize == 4 &&
+             b->cfg.terminal_itemsize == 1 && b->cfg.action_bytes == 4 &&
+             b->cfg.num_extras == 0;
+  sc->action_col = reinterpret_cast<const uint32_t *>(b->col[B2R_COL_ACTION].dev);
+  sc->action_out = static_cast<uint32_t *>(out->action);
+  sc->next_action_out = static_cast<uint32_t *>(out->next_action);
+  sc->next_reward_out = static_cast<float *>(out->next_reward);
+}
+
+int launch_gather(b2r_buffer *b, int32_t batch, const int32_t *indices_dev,
+                  const b2r_batch *out, cudaStream_t stream,
+                  const int32_t *count_dev, bool frames_only) {
+  GatherArgs a;
+  a.count = count_dev;
+  a.capacity = b->cfg.capacity;
+  a.stack = b->cfg.stack_size;
+  a.horizon = b->cfg.update_horizon;
+  a.batch = batch;
+  a.obs_bytes = b->cfg.obs_bytes;
+  a.obs_itemsize = b->cfg.obs_itemsize;
+  a.obs = b->col[0].dev;
+  a.term_flag = b->term_flag;
+  a.indices = indices_dev;
+  a.state = static_cast<uint8_t *>(out->state);
+  a.next_state = static_cast<uint8_t *>(out->next_state);
+  fill_scalar_args(b, out, &a.sc);
+  if (frames_only && !a.state && !a.next_state) return B2R_OK;
   const bool fast = a.stack == 4 && a.obs_itemsize == 1 && (a.obs_bytes & 15) == 0;
   if (fast) {
     const int chunks = (int)(a.obs_bytes >> 4);
     const int nx = (chunks + 127) / 128;
     // + rows of scalar CTAs (one thread per transition)
-    dim3 grid(nx, batch + (batch + nx * 128 - 1) / (nx * 128));
-    B2R_CUDA(launch(gather_stack4_u8_kernel, grid, dim3(128), 0, stream, a));
+    a.scalar_rows = frames_only ? 0 : (batch + nx * 128 - 1) / (nx * 128);
+    dim3 grid(nx, batch + a.scalar_rows);
+    if (frames_only)  // beside the chain: lowest priority
+      B2R_CUDA(launch_prio(gather_stack4_u8_kernel<false>, grid, dim3(128), 0, stream,
+                           0, a));
+    else
+      B2R_CUDA(launch(gather_stack4_u8_kernel<true>, grid, dim3(128), 0, stream, a));
   } else {
     const int64_t elems = a.obs_bytes / a.obs_itemsize;
     int gx = (int)((elems + 255) / 256);
     if (gx > 32) gx = 32;
-    dim3 grid(gx, batch + (batch + gx * 256 - 1) / (gx * 256));  // + scalar CTAs
-    B2R_CUDA(launch(gather_generic_kernel, grid, dim3(256), 0, stream, a));
+    a.scalar_rows = frames_only ? 0 : (batch + gx * 256 - 1) / (gx * 256);
+    dim3 grid(gx, batch + a.scalar_rows);
+    B2R_CUDA(launch_prio(gather_generic_kernel, grid, dim3(256), 0, stream,
+                         frames_only ? 0 : chain_priority(), a));
   }
   B2R_LAUNCHED();
   return B2R_OK;

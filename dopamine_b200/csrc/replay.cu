@@ -342,6 +342,11 @@ int b2r_create(const b2r_config *cfg, b2r_buffer **out) {
   B2R_CUDA(cudaMemset(b->shard_counter, 0, 8));
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->draw_counter), 8));
   B2R_CUDA(cudaMemset(b->draw_counter, 0, 8));
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->min_prob), 4));
+  B2R_CUDA(cudaMemset(b->min_prob, 0, 4));
+  B2R_CUDA(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
+  B2R_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+  B2R_CUDA(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
   *out = b;
   return B2R_OK;
 }
@@ -364,6 +369,10 @@ int b2r_destroy(b2r_buffer *b) {
   cudaFree(b->draw_counter);
   cudaFree(b->shard_counter);
   cudaFree(b->ticket);
+  cudaFree(b->min_prob);
+  if (b->side) cudaStreamDestroy(b->side);
+  if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+  if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->out_scratch) cudaFree(b->out_scratch);
   b->bounce.release();
   delete b;
@@ -375,6 +384,11 @@ b2r_tree *b2r_buffer_tree(b2r_buffer *b) { return b ? b->tree : nullptr; }
 int b2r_add(b2r_buffer *b, const void *observation, const void *action,
             const void *reward, const void *terminal, const void *const *extras,
             double priority, int priority_mode, b2r_stream stream) {
+  if (stream == B2R_STREAM_NONE) {
+    // worst case stack_size - 1 zero transitions + the row itself
+    if (b->q_entries + b->cfg.stack_size > b->queue_cap) return B2R_QUEUE_FULL;
+    stream = nullptr;  // no launch can happen below
+  }
   cudaStream_t s = as_stream(stream);
   const void *cols[b2r::kMaxColumns] = {observation, action, reward, terminal};
   for (int e = 0; e < b->cfg.num_extras; ++e) cols[4 + e] = extras[e];
@@ -398,6 +412,16 @@ int b2r_add(b2r_buffer *b, const void *observation, const void *action,
   B2R_TRY(b2r::enqueue(b, true, cols, priority, priority_mode, s));
   b2r::recompute_invalid_range(b);
   return B2R_OK;
+}
+
+int b2r_add_atari(b2r_buffer *b, const void *observation, int32_t action,
+                  float reward, uint8_t terminal, double priority,
+                  int priority_mode, b2r_stream stream) {
+  if (b->cfg.action_bytes != 4 || b->cfg.reward_itemsize != 4 ||
+      b->cfg.terminal_itemsize != 1 || b->cfg.num_extras != 0)
+    return fail(B2R_ERR_UNSUPPORTED, "b2r_add_atari: not the Atari storage layout");
+  return b2r_add(b, observation, &action, &reward, &terminal, nullptr, priority,
+                 priority_mode, stream);
 }
 
 int b2r_flush(b2r_buffer *b, b2r_stream stream) {
@@ -509,6 +533,10 @@ int b2r_check(b2r_buffer *b, b2r_stream stream) {
     B2R_CUDA(cudaMemsetAsync(b->status, 0, 16, s));
     if (st[0] == B2R_ERR_EMPTY_TREE)
       return fail(B2R_ERR_EMPTY_TREE, "Cannot sample from an empty sum tree.");
+    if (st[0] == B2R_ERR_EXCHANGE)
+      return fail(B2R_ERR_EXCHANGE,
+                  "shard %lld did not publish its priority total in time",
+                  (long long)st[1]);
     return fail((int)st[0],
                 "Max sample attempts: Tried %d times but only sampled %lld valid "
                 "indices.",

@@ -65,6 +65,16 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int *warp_counts,
   return before + within;
 }
 
+// Shard totals exchanged through peer memory (see exchange_totals in sample.cu).
+constexpr int kMaxShards = 16;
+struct ExchangeArgs {
+  uint64_t *local;             // this rank's mailbox [2 parities][world][2 words];
+                               // nullptr: no exchange
+  uint64_t *peer[kMaxShards];  // the peers' mailboxes (peer-mapped device pointers)
+  uint64_t *seq;               // device step counter, in lockstep on all ranks
+  int64_t timeout_ns;
+};
+
 struct Column {
   int64_t row_bytes = 0;
   int64_t queue_offset = 0;  // byte offset inside a staged row
@@ -113,20 +123,49 @@ struct b2r_buffer {
                                       // (advances in lockstep on every rank)
   uint64_t *draw_counter = nullptr;  // device: bumps per Philox sample launch, so a
                                      // replayed CUDA graph draws fresh uniforms
+  // fused step: the frame copies run on `side`, forked/joined with these events
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  float *min_prob = nullptr;    // device: min sampling probability of the last batch
   b2r::Bounce bounce;           // HOST-array calls
   uint8_t *out_scratch = nullptr;  // device outputs of b2r_gather (HOST variant)
   size_t out_scratch_cap = 0;
 };
 
+struct b2r_exchange {
+  int world = 0, rank = 0;
+  uint64_t *mailbox = nullptr;  // device, written by the peers
+  uint64_t *seq = nullptr;      // device
+  uint64_t *peer[b2r::kMaxShards] = {nullptr};
+  bool opened[b2r::kMaxShards] = {false};  // peer[g] came from cudaIpcOpenMemHandle
+  bool connected = false;
+  int64_t timeout_ns = 2000000000ll;
+};
+
 namespace b2r {
 int flush_queue(b2r_buffer *buf, cudaStream_t stream);
+void fill_exchange_args(const b2r_exchange *x, ExchangeArgs *out);
+int launch_exchange_publish(const b2r_exchange *x, const b2r_buffer *buf,
+                            cudaStream_t stream);
+// Sharded sampling (one CTA).  Totals come from `shard_totals` (device array) or,
+// when `x` is set, from the peer-memory exchange.  `scalars` / `min_prob_out` as in
+// launch_sample; out_count (nullable, device) receives this rank's row count.
+int launch_sample_sharded(b2r_buffer *buf, int32_t global_batch, int32_t num_shards,
+                          int32_t rank, const double *shard_totals,
+                          const b2r_exchange *x, const double *query01,
+                          int32_t n_retry, const double *retry_u01, uint64_t seed,
+                          uint64_t offset, int32_t *out_slots, int32_t *out_indices,
+                          int32_t *out_count, cudaStream_t stream,
+                          const b2r_batch *scalars = nullptr,
+                          float *min_prob_out = nullptr);
 void fill_valid_ctx(const b2r_buffer *buf, ValidCtx *ctx);
 int ensure_inv_slots(b2r_buffer *buf, int64_t n);
 int launch_gather(b2r_buffer *buf, int32_t batch, const int32_t *indices_dev,
                   const b2r_batch *out, cudaStream_t stream,
-                  const int32_t *count_dev = nullptr);
+                  const int32_t *count_dev = nullptr, bool frames_only = false);
 int launch_sample(b2r_buffer *buf, int32_t batch, bool philox, uint64_t seed,
                   uint64_t offset, const double *strat_dev,
                   const double *retry_dev, int32_t n_retry, int32_t *out_idx_dev,
-                  int32_t *info_dev, cudaStream_t stream);
+                  int32_t *info_dev, cudaStream_t stream,
+                  const b2r_batch *scalars = nullptr, float *min_prob_out = nullptr);
 }  // namespace b2r

@@ -9,7 +9,7 @@
 // retry draw", "stop after max_sample_attempts failures" — become block-wide
 // prefix scans (warp ballots + shuffles) over windows evaluated speculatively in
 // parallel.  Levels 0..10 of the tree are staged in shared memory first.
-#include "replay.cuh"
+#include "gather.cuh"
 
 namespace b2r {
 namespace {
@@ -42,7 +42,98 @@ struct PerSampleArgs {
   int num_shards, rank;
   const double *shard_totals;
   int32_t *out_slots;  // nullable
+  // fused scalar outputs (with_scalars): every row's n-step return, terminal,
+  // actions, ... are written here as soon as its index is final, and the minimum
+  // sampling probability of the batch (the IS-weight normaliser) is reduced.
+  int with_scalars;
+  ScalarArgs sc;
+  float *tile_min;      // scratch [n_tiles]
+  float *min_prob_out;  // nullable
+  int32_t *count_out;   // nullable: number of rows this launch produced
+  // Shard totals over peer memory instead of shard_totals (see exchange_totals).
+  ExchangeArgs xchg;
 };
+
+__device__ __forceinline__ void st_sys_u64(uint64_t *p, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_sys_u64(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// All-gather of one fp64 per rank through peer memory (NVLink / NVSwitch): thread g
+// stores this rank's root total straight into rank g's mailbox and then polls its
+// own mailbox for rank g's.  Each total travels as two 8-byte words that carry half
+// of the payload and the step number in their low 32 bits (the flag is in-band, as
+// in NCCL's LL protocol), so no fence or ordering between the stores is needed.
+// Mailbox slots alternate with the parity of the step: a rank can only be one step
+// ahead of a peer, which has then finished reading the other parity.
+// A peer that does not answer within the timeout latches B2R_ERR_EXCHANGE (and
+// later launches skip the wait), so a lost rank cannot hang the GPU.
+__device__ __forceinline__ void exchange_publish(const ExchangeArgs &x, int world,
+                                                 int rank, double local_total,
+                                                 uint64_t seq) {
+  const int g = threadIdx.x;
+  if (g >= world || g == rank) return;
+  const uint32_t tag = (uint32_t)seq;
+  const uint64_t bits = (uint64_t)__double_as_longlong(local_total);
+  uint64_t *dst = x.peer[g] + ((size_t)(seq & 1) * world + rank) * 2;
+  st_sys_u64(dst, (bits & 0xffffffff00000000ull) | tag);
+  st_sys_u64(dst + 1, (bits << 32) | tag);
+}
+
+__device__ __forceinline__ void exchange_collect(const ExchangeArgs &x, int world,
+                                                 int rank, double local_total,
+                                                 uint64_t seq, double *totals,
+                                                 int64_t *latched) {
+  const int g = threadIdx.x;
+  if (g >= world) return;
+  double got = local_total;
+  if (g != rank) {
+    const uint32_t tag = (uint32_t)seq;
+    const uint64_t *src = x.local + ((size_t)(seq & 1) * world + g) * 2;
+    const bool broken = latched != nullptr && latched[0] == B2R_ERR_EXCHANGE;
+    const uint64_t t0 = global_timer_ns();
+    uint64_t r0 = 0, r1 = 0;
+    bool ok = false;
+    while (!broken) {
+      r0 = ld_sys_u64(src);
+      r1 = ld_sys_u64(src + 1);
+      ok = (uint32_t)r0 == tag && (uint32_t)r1 == tag;
+      if (ok || global_timer_ns() - t0 > (uint64_t)x.timeout_ns) break;
+    }
+    if (ok) {
+      got = __longlong_as_double((long long)((r0 & 0xffffffff00000000ull) | (r1 >> 32)));
+    } else {
+      got = 0.0;
+      if (latched != nullptr) {
+        latched[0] = B2R_ERR_EXCHANGE;
+        latched[1] = g;
+      }
+    }
+  }
+  totals[g] = got;
+}
+
+// Block-wide minimum; every thread of the block must call it.
+__device__ __forceinline__ float block_min(float v, float *scratch) {
+#pragma unroll 1
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float m = INFINITY;
+  const int warps = (blockDim.x + 31) >> 5;
+  for (int w = 0; w < warps; ++w) m = fminf(m, scratch[w]);
+  return m;
+}
 
 // Slot of the ord-th invalid stratum: the per-tile lists are concatenated in tile
 // order (tile_start[] is the exclusive prefix of the per-tile counts).
@@ -60,9 +151,11 @@ __device__ __forceinline__ int invalid_slot(const PerSampleArgs &a, const int *t
 // ordered lists of invalid slots, with block-wide prefix scans over windows of
 // retry draws evaluated speculatively in parallel.
 template <int K, int MAX_THREADS>
-__global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a) {
+__global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_constant__ PerSampleArgs a) {
   __shared__ double top[2 << kTopLevels];
   __shared__ int warp_counts[32];
+  __shared__ float warp_mins[32];
+  __shared__ double s_totals[kMaxShards];
   __shared__ int s_draws_used, s_last_idx, s_last_valid, s_is_last;
   __shared__ int tile_start[kMaxTiles + 1];
 
@@ -72,22 +165,41 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
   B2R_MARK(1);
   const uint64_t draws_before = a.counter ? *a.counter : 0ull;
   const uint64_t draw_offset = a.offset + draws_before;
+  // Peer exchange (one CTA): the totals are on the wire while the top levels are
+  // staged.
+  const bool exchange = a.xchg.local != nullptr && a.num_shards > 1;
+  uint64_t xseq = 0;
+  if (exchange) {
+    xseq = *a.xchg.seq + 1;
+    exchange_publish(a.xchg, a.num_shards, a.rank, a.heap[1], xseq);
+  }
   const int top_depth = stage_top_levels(a.heap, a.depth, top);
   B2R_MARK(2);
   const double local_total = top[1];  // root of the 1-based heap
+  const double *shard_totals = a.shard_totals;
+  if (exchange) {
+    exchange_collect(a.xchg, a.num_shards, a.rank, local_total, xseq, s_totals,
+                     a.latched);
+    __syncthreads();
+    shard_totals = s_totals;
+    if (threadIdx.x == 0) *a.xchg.seq = xseq;
+  }
   // Mass the strata are spread over: the root, or all shards' roots summed in
   // rank order (fp64, left to right).
   double grand_total = local_total;
   if (a.num_shards > 1) {
     grand_total = 0.0;
     for (int g = 0; g < a.num_shards; ++g)
-      grand_total = __dadd_rn(grand_total, a.shard_totals[g]);
+      grand_total = __dadd_rn(grand_total, shard_totals[g]);
   }
   if (grand_total == 0.0 || (a.num_shards == 1 && local_total == 0.0)) {
     // sum_tree.py:159-160 (every CTA takes this branch together)
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       a.info[0] = B2R_ERR_EMPTY_TREE;
       a.info[1] = 0; a.info[2] = 0; a.info[3] = 0;
+      if (a.count_out) *a.count_out = 0;
+      if (a.min_prob_out) *a.min_prob_out = INFINITY;
+      if (a.counter) *a.counter = draws_before + 1;  // ranks stay in lockstep
       if (a.latched && a.latched[0] == 0) a.latched[0] = B2R_ERR_EMPTY_TREE;
     }
     return;
@@ -107,6 +219,8 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
     const int i = tile * tile_size + threadIdx.x;
     bool mine = false, valid = true;
     int64_t idx = 0;
+    ScalarLoads row;
+    const bool fast_scalars = a.with_scalars && a.sc.fast;
     if (i < a.batch) {
       double q01;
       if (a.use_philox) {
@@ -120,7 +234,7 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
       double mass = __dmul_rn(q01, grand_total);
       int owner = 0;
       for (; owner < a.num_shards - 1; ++owner) {
-        const double left = a.shard_totals[owner];
+        const double left = shard_totals[owner];
         if (mass < left) break;
         mass = __dsub_rn(mass, left);
       }
@@ -129,6 +243,8 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
       if (mine) {
         idx = tree_descend_staged<K>(a.heap, top, top_depth, a.depth, mass, a.zero);
         B2R_MARK(4);
+        // the row's scalar inputs travel with the validity flags: one round trip
+        if (fast_scalars) load_scalars(a.sc, idx, &row);
         valid = is_valid_transition(a.valid, idx);
         B2R_MARK(5);
       }
@@ -139,10 +255,17 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
       mine_base += tile_mine;
     }
     const int ipos = block_scan_flag(mine && !valid, warp_counts, &tile_inv);
+    float my_prio = INFINITY;
     if (mine) {
       a.out_idx[pos] = (int32_t)idx;
       if (a.out_slots) a.out_slots[pos] = i;
       if (!valid) a.inv_slots[(size_t)tile * tile_size + ipos] = pos;
+      else if (fast_scalars) my_prio = finish_scalars(a.sc, pos, idx, row);
+      else if (a.with_scalars) my_prio = write_scalars(a.sc, pos, idx);
+    }
+    if (a.with_scalars) {
+      const float m = block_min(my_prio, warp_mins);
+      if (threadIdx.x == 0) a.tile_min[tile] = m;
     }
     if (threadIdx.x == 0) a.tile_counts[tile] = tile_inv;
   }
@@ -176,12 +299,15 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
 
   // ---- in-order replacement of invalid slots (prioritized_replay_buffer.py:156-170)
   int found = 0, drawn = 0;
+  float fix_min = INFINITY;  // sampling probabilities of the rows replaced below
   const int budget = a.max_attempts;
   while (num_invalid > 0 && found < num_invalid && drawn < budget) {
     const int r = drawn + threadIdx.x;
     const bool active = r < budget;
     bool valid = false;
     int64_t idx = 0;
+    ScalarLoads row;
+    const bool fast_scalars = a.with_scalars && a.sc.fast;
     if (active) {
       // Philox retry stream: rank-private (strata streams are shared by all ranks)
       const double u = (a.use_philox || a.retry_u01 == nullptr)
@@ -192,12 +318,18 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
       // sum_tree.py:123-124: query = random.random() * total
       idx = tree_descend_staged<K>(a.heap, top, top_depth, a.depth,
                                    __dmul_rn(u, local_total), a.zero);
+      if (fast_scalars) load_scalars(a.sc, idx, &row);
       valid = is_valid_transition(a.valid, idx);
     }
     int tile_valid;
     const int ord = found + block_scan_flag(active && valid, warp_counts, &tile_valid);
     if (active && valid && ord < num_invalid) {
-      a.out_idx[invalid_slot(a, tile_start, n_tiles, tile_size, ord)] = (int32_t)idx;
+      const int slot = invalid_slot(a, tile_start, n_tiles, tile_size, ord);
+      a.out_idx[slot] = (int32_t)idx;
+      if (fast_scalars)
+        fix_min = fminf(fix_min, finish_scalars(a.sc, slot, idx, row));
+      else if (a.with_scalars)
+        fix_min = fminf(fix_min, write_scalars(a.sc, slot, idx));
       if (ord == num_invalid - 1) s_draws_used = r + 1;
     }
     if (active && r == budget - 1) {
@@ -227,6 +359,8 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
           // the slot burnt the rest of the budget and keeps its last (invalid)
           // draw; only a FURTHER invalid slot raises.
           a.out_idx[next_slot] = s_last_idx;
+          if (a.with_scalars && s_last_idx >= 0 && s_last_idx < a.valid.capacity)
+            fix_min = fminf(fix_min, write_scalars(a.sc, next_slot, s_last_idx));
           if (num_invalid > next + 1) {
             status = B2R_ERR_SAMPLE_ATTEMPTS;
             fail_slot = invalid_slot(a, tile_start, n_tiles, tile_size, next + 1);
@@ -239,9 +373,18 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(PerSampleArgs a
     a.info[1] = a.out_slots ? (status ? a.out_slots[fail_slot] : 0) : fail_slot;
     a.info[2] = used;
     a.info[3] = count;
+    if (a.count_out) *a.count_out = count;
     if (status != B2R_OK && a.latched && a.latched[0] == 0) {
       a.latched[0] = status;
       a.latched[1] = fail_slot;
+    }
+  }
+  if (a.with_scalars && a.min_prob_out) {
+    float m = block_min(fix_min, warp_mins);
+    if (threadIdx.x == 0) {
+      for (int t = 0; t < n_tiles; ++t)
+        m = fminf(m, *(volatile float *)(a.tile_min + t));
+      *a.min_prob_out = m;
     }
   }
   B2R_MARK(8);
@@ -347,17 +490,29 @@ int sample_threads(int n) {
 
 }  // namespace
 
+// Threads per CTA (= strata per tile).  Small batches: one CTA (at least 256
+// threads, so that staging the top levels is two rounds of loads).  Large batches:
+// tiles of 128 strata, so that the descents spread over many SMs.
+static void sample_shape(int batch, int *threads, int *tiles) {
+  if (batch <= 256) {
+    *threads = 256;
+    *tiles = 1;
+  } else {
+    *threads = 128;
+    *tiles = (batch + 127) / 128;
+  }
+}
+
 int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
                   uint64_t offset, const double *strat_dev,
                   const double *retry_dev, int32_t n_retry, int32_t *out_idx_dev,
-                  int32_t *info_dev, cudaStream_t stream) {
-  if (batch > kMaxTiles * 32)
-    return fail(B2R_ERR_UNSUPPORTED, "batch above %d is not supported", kMaxTiles * 32);
-  // At least 256 threads, so that staging the top levels is two rounds of loads.
-  int threads = sample_threads(batch);
-  if (threads < 256) threads = 256;
-  const int tiles = (batch + threads - 1) / threads;
-  B2R_TRY(ensure_inv_slots(b, (int64_t)tiles * threads + kMaxTiles + 8));
+                  int32_t *info_dev, cudaStream_t stream,
+                  const b2r_batch *scalars, float *min_prob_out) {
+  int threads, tiles;
+  sample_shape(batch, &threads, &tiles);
+  if (tiles > kMaxTiles)
+    return fail(B2R_ERR_UNSUPPORTED, "batch above %d is not supported", kMaxTiles * 128);
+  B2R_TRY(ensure_inv_slots(b, (int64_t)tiles * threads + 2 * kMaxTiles + 8));
   PerSampleArgs a;
   a.heap = b->tree->heap;
   a.depth = b->tree->depth;
@@ -374,6 +529,7 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   a.out_idx = out_idx_dev;
   a.inv_slots = b->inv_slots;
   a.tile_counts = b->inv_slots + (int64_t)tiles * threads;
+  a.tile_min = reinterpret_cast<float *>(a.tile_counts + kMaxTiles);
   a.ticket = b->ticket;
   a.info = info_dev;
   a.latched = philox ? b->status : nullptr;
@@ -381,13 +537,102 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   a.rank = 0;
   a.shard_totals = nullptr;
   a.out_slots = nullptr;
-  // Small batches: one CTA; large ones: one CTA per 1024 strata.  3 tree levels
-  // per memory round trip either way (more would bloat the straight-line code,
+  a.with_scalars = scalars != nullptr;
+  a.min_prob_out = min_prob_out;
+  a.count_out = nullptr;
+  a.xchg.local = nullptr;
+  if (scalars) {
+    fill_scalar_args(b, scalars, &a.sc);
+    if (a.sc.indices_out == out_idx_dev) a.sc.indices_out = nullptr;
+  }
+  // 3 tree levels per memory round trip (more would bloat the straight-line code,
   // and a cold instruction cache costs more than the saved round trips).
-  if (batch <= 256)
-    B2R_CUDA(launch(per_sample_kernel<3, 256>, dim3(1), dim3(threads), 0, stream, a));
+  B2R_CUDA(launch(per_sample_kernel<3, 256>, dim3(tiles), dim3(threads), 0, stream, a));
+  B2R_LAUNCHED();
+  return B2R_OK;
+}
+
+void fill_exchange_args(const b2r_exchange *x, ExchangeArgs *out) {
+  out->local = x->mailbox;
+  for (int g = 0; g < kMaxShards; ++g) out->peer[g] = x->peer[g];
+  out->seq = x->seq;
+  out->timeout_ns = x->timeout_ns;
+}
+
+int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shards,
+                          int32_t rank, const double *shard_totals,
+                          const b2r_exchange *x, const double *query01,
+                          int32_t n_retry, const double *retry_u01, uint64_t seed,
+                          uint64_t offset, int32_t *out_slots, int32_t *out_indices,
+                          int32_t *out_count, cudaStream_t s,
+                          const b2r_batch *scalars, float *min_prob_out) {
+  if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
+  if (global_batch <= 0 || num_shards <= 0 || num_shards > kMaxShards || rank < 0 ||
+      rank >= num_shards)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "bad sharding arguments");
+  if (x && !x->connected && x->world > 1)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "the exchange is not connected");
+  // One CTA walks every tile (the compaction of this rank's strata is sequential
+  // over tiles); 256 threads up to a global batch of 256, 1024 above.
+  const int threads = global_batch <= 256 ? 256 : 1024;
+  const int tiles = (global_batch + threads - 1) / threads;
+  if (tiles > kMaxTiles) return fail(B2R_ERR_UNSUPPORTED, "global batch too large");
+  B2R_TRY(ensure_inv_slots(b, (int64_t)tiles * threads + 2 * kMaxTiles + 8));
+  PerSampleArgs a;
+  a.heap = b->tree->heap;
+  a.depth = b->tree->depth;
+  fill_valid_ctx(b, &a.valid);
+  a.batch = global_batch;
+  a.max_attempts = n_retry;
+  a.use_philox = (query01 == nullptr) ? 1 : 0;
+  a.seed = seed;
+  a.offset = offset;
+  // Philox mode: the draw number also advances on the device, in lockstep on all
+  // ranks (each makes the same sequence of sharded calls), so a captured CUDA
+  // graph draws fresh, rank-consistent strata at every replay.
+  a.counter = a.use_philox ? b->shard_counter : nullptr;
+  a.zero = 0;
+  a.strat_query01 = query01;
+  a.retry_u01 = retry_u01;
+  a.out_idx = out_indices;
+  a.inv_slots = b->inv_slots;
+  a.tile_counts = b->inv_slots + (int64_t)tiles * threads;
+  a.tile_min = reinterpret_cast<float *>(a.tile_counts + kMaxTiles);
+  a.ticket = b->ticket;
+  a.info = b->info;
+  a.latched = b->status;
+  a.num_shards = num_shards;
+  a.rank = rank;
+  a.shard_totals = shard_totals;
+  a.out_slots = out_slots;
+  a.with_scalars = scalars != nullptr;
+  a.min_prob_out = min_prob_out;
+  a.count_out = out_count;
+  a.xchg.local = nullptr;
+  if (x && x->world > 1) fill_exchange_args(x, &a.xchg);
+  if (scalars) {
+    fill_scalar_args(b, scalars, &a.sc);
+    if (a.sc.indices_out == out_indices) a.sc.indices_out = nullptr;
+  }
+  if (global_batch <= 256)
+    B2R_CUDA(launch(per_sample_kernel<3, 256>, dim3(1), dim3(threads), 0, s, a));
   else
-    B2R_CUDA(launch(per_sample_kernel<3, 1024>, dim3(tiles), dim3(threads), 0, stream, a));
+    B2R_CUDA(launch(per_sample_kernel<3, 1024>, dim3(1), dim3(threads), 0, s, a));
+  B2R_LAUNCHED();
+  return B2R_OK;
+}
+
+// Publishes a rank's total for the next exchange step without consuming it.
+__global__ void exchange_publish_kernel(ExchangeArgs x, int world, int rank,
+                                        const double *heap) {
+  exchange_publish(x, world, rank, heap[1], *x.seq + 1);
+}
+
+int launch_exchange_publish(const b2r_exchange *x, const b2r_buffer *b,
+                            cudaStream_t s) {
+  ExchangeArgs xa;
+  fill_exchange_args(x, &xa);
+  exchange_publish_kernel<<<1, 32, 0, s>>>(xa, x->world, x->rank, b->tree->heap);
   B2R_LAUNCHED();
   return B2R_OK;
 }
@@ -529,51 +774,27 @@ int b2r_sample_indices_sharded_device(b2r_buffer *b, int32_t global_batch,
                                       uint64_t offset, int32_t *out_slots,
                                       int32_t *out_indices, int32_t *out_count,
                                       b2r_stream stream) {
-  if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
-  if (global_batch <= 0 || num_shards <= 0 || rank < 0 || rank >= num_shards)
-    return fail(B2R_ERR_INVALID_ARGUMENT, "bad sharding arguments");
-  cudaStream_t s = as_stream(stream);
-  B2R_TRY(b2r::flush_queue(b, s));
-  int threads = b2r::sample_threads(global_batch);
-  if (threads < 256) threads = 256;
-  const int tiles = (global_batch + threads - 1) / threads;
-  if (tiles > b2r::kMaxTiles)
-    return fail(B2R_ERR_UNSUPPORTED, "global batch too large");
-  B2R_TRY(b2r::ensure_inv_slots(b, (int64_t)tiles * threads + b2r::kMaxTiles + 8));
-  b2r::PerSampleArgs a;
-  a.heap = b->tree->heap;
-  a.depth = b->tree->depth;
-  b2r::fill_valid_ctx(b, &a.valid);
-  a.batch = global_batch;
-  a.max_attempts = n_retry;
-  a.use_philox = (query01 == nullptr) ? 1 : 0;
-  a.seed = seed;
-  a.offset = offset;
-  // Philox mode: the draw number also advances on the device, in lockstep on all
-  // ranks (each makes the same sequence of sharded calls), so a captured CUDA
-  // graph draws fresh, rank-consistent strata at every replay.
-  a.counter = a.use_philox ? b->shard_counter : nullptr;
-  a.zero = 0;
-  a.strat_query01 = query01;
-  a.retry_u01 = retry_u01;
-  a.out_idx = out_indices;
-  a.inv_slots = b->inv_slots;
-  a.tile_counts = b->inv_slots + (int64_t)tiles * threads;
-  a.ticket = b->ticket;
-  a.info = b->info;
-  a.latched = b->status;
-  a.num_shards = num_shards;
-  a.rank = rank;
-  a.shard_totals = shard_totals;
-  a.out_slots = out_slots;
-  if (global_batch <= 256)
-    B2R_CUDA(b2r::launch(b2r::per_sample_kernel<3, 256>, dim3(1), dim3(threads), 0, s, a));
-  else
-    B2R_CUDA(b2r::launch(b2r::per_sample_kernel<3, 1024>, dim3(1), dim3(threads), 0, s, a));
-  B2R_LAUNCHED();
-  if (out_count)
-    B2R_CUDA(cudaMemcpyAsync(out_count, b->info + 3, 4, cudaMemcpyDeviceToDevice, s));
-  return B2R_OK;
+  if (!shard_totals) return fail(B2R_ERR_INVALID_ARGUMENT, "shard_totals is NULL");
+  B2R_TRY(b2r::flush_queue(b, as_stream(stream)));
+  return b2r::launch_sample_sharded(b, global_batch, num_shards, rank, shard_totals,
+                                    nullptr, query01, n_retry, retry_u01, seed,
+                                    offset, out_slots, out_indices, out_count,
+                                    as_stream(stream));
+}
+
+int b2r_sample_indices_sharded_p2p_device(b2r_buffer *b, b2r_exchange *x,
+                                          int32_t global_batch,
+                                          const double *query01, int32_t n_retry,
+                                          const double *retry_u01, uint64_t seed,
+                                          uint64_t offset, int32_t *out_slots,
+                                          int32_t *out_indices, int32_t *out_count,
+                                          b2r_stream stream) {
+  if (!x) return fail(B2R_ERR_INVALID_ARGUMENT, "exchange is NULL");
+  B2R_TRY(b2r::flush_queue(b, as_stream(stream)));
+  return b2r::launch_sample_sharded(b, global_batch, x->world, x->rank, nullptr, x,
+                                    query01, n_retry, retry_u01, seed, offset,
+                                    out_slots, out_indices, out_count,
+                                    as_stream(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,306 @@
+// The hot path as ONE call: what a sess.run of the Rainbow train op does around the
+// network — prioritized sample (prioritized_replay_buffer.py:142-201)
+// -> C51 target / loss / new priorities (rainbow_agent.py:200-293) -> priority
+// write-back (prioritized_replay_buffer.py:203-214) — plus the host-facing,
+// pipelined trainer built on it.
+//
+// Dependencies inside a step: the loss needs only the SCALAR columns of the batch
+// (action, n-step return, terminal, sampling probability) and the network outputs;
+// the next step's sampler needs this step's write-back.  The frame stacks feed the
+// network, not this chain.  So the sampler emits the scalar columns itself, the
+// chain sample -> loss -> write-back runs on the caller's stream, and the HBM-bound
+// frame copies run beside it on a forked stream, joined before the call returns.
+#include "gather.cuh"
+
+#include <cmath>
+#include <new>
+#include <vector>
+
+namespace b2r {
+
+// One shard of a sharded replay: `batch` is then the GLOBAL batch, this rank's rows
+// are compacted at the front of `out` and counted on the device.
+struct ShardSpec {
+  const b2r_exchange *exchange;
+  int32_t *out_slots;
+  int32_t *out_count;
+};
+
+// wait_before_loss / loss_done (nullable): events of the trainer's copy stream.
+static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offset,
+                      const b2r_batch *out, const b2r_c51_args *c51, cudaStream_t s,
+                      cudaEvent_t wait_before_loss, cudaEvent_t loss_done,
+                      const ShardSpec *shard = nullptr) {
+  if (!b || !out || !c51) return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
+  if (batch <= 0 || batch > 60000)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "batch must be in [1, 60000]");
+  if (b->cfg.terminal_itemsize != 1 || b->cfg.reward_itemsize != 4 ||
+      b->cfg.action_bytes != 4)
+    return fail(B2R_ERR_UNSUPPORTED,
+                "the fused step needs uint8 terminals, float32 rewards and scalar "
+                "int32 actions");
+  if (!out->indices || !out->action || !out->reward || !out->terminal ||
+      !out->sampling_probabilities)
+    return fail(B2R_ERR_INVALID_ARGUMENT,
+                "out->indices, action, reward, terminal and sampling_probabilities "
+                "are required");
+  if (shard && (!shard->exchange || !shard->out_count))
+    return fail(B2R_ERR_INVALID_ARGUMENT, "exchange and out_count are required");
+  const int32_t *count = shard ? shard->out_count : nullptr;
+  B2R_TRY(flush_queue(b, s));
+  if (shard)
+    B2R_TRY(launch_sample_sharded(
+        b, batch, shard->exchange->world, shard->exchange->rank, nullptr,
+        shard->exchange, nullptr, b->cfg.max_sample_attempts, nullptr, seed, offset,
+        shard->out_slots, out->indices, shard->out_count, s, out, b->min_prob));
+  else
+    B2R_TRY(launch_sample(b, batch, true, seed, offset, nullptr, nullptr, 0,
+                          out->indices, b->info, s, out, b->min_prob));
+  const bool frames = out->state != nullptr || out->next_state != nullptr;
+  if (frames) {
+    B2R_CUDA(cudaEventRecord(b->ev_fork, s));
+    B2R_CUDA(cudaStreamWaitEvent(b->side, b->ev_fork, 0));
+    B2R_TRY(launch_gather(b, batch, out->indices, out, b->side, count, true));
+    B2R_CUDA(cudaEventRecord(b->ev_join, b->side));
+  }
+  b2r_c51_args loss = *c51;
+  loss.batch = batch;
+  loss.actions = static_cast<const int32_t *>(out->action);
+  loss.rewards = static_cast<const float *>(out->reward);
+  loss.terminals = static_cast<const uint8_t *>(out->terminal);
+  loss.sampling_probabilities = out->sampling_probabilities;
+  loss.min_probability = b->min_prob;
+  loss.batch_count = count;
+  if (count) loss.mean_weighted_loss = nullptr;
+  if (wait_before_loss) B2R_CUDA(cudaStreamWaitEvent(s, wait_before_loss, 0));
+  B2R_TRY(b2r_c51_loss(&loss, s));
+  if (loss_done) B2R_CUDA(cudaEventRecord(loss_done, s));
+  B2R_TRY((tree_apply<int32_t, float>(b->tree, batch, out->indices, loss.priorities,
+                                      nullptr, s, count)));
+  if (frames) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join, 0));
+  return B2R_OK;
+}
+
+}  // namespace b2r
+
+using b2r::as_stream;
+using b2r::fail;
+
+struct b2r_trainer {
+  b2r_buffer *buf = nullptr;
+  b2r_trainer_config cfg;
+  // device
+  float *logits[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [set][online, target]
+  float *support = nullptr;
+  uint8_t *frames = nullptr;    // state | next_state
+  uint8_t *scalars = nullptr;   // every other batch column and loss output
+  b2r_batch batch;
+  b2r_c51_args c51;
+  // copies run on their own stream, double-buffered against the loss kernel
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr};
+  cudaEvent_t ev_loss[2] = {nullptr, nullptr};
+  // results
+  int ring = 1;
+  float *ring_host = nullptr;  // pinned [ring][batch]
+  std::vector<cudaEvent_t> ev_done;
+  int64_t submitted = 0;
+};
+
+namespace {
+
+int collect(b2r_trainer *t, int64_t step, float *loss_out, int64_t *loss_step) {
+  if (step < 0) {
+    if (loss_step) *loss_step = -1;
+    return B2R_OK;
+  }
+  const int slot = (int)(step % t->ring);
+  B2R_CUDA(cudaEventSynchronize(t->ev_done[slot]));
+  if (loss_out)
+    memcpy(loss_out, t->ring_host + (size_t)slot * t->cfg.batch,
+           (size_t)t->cfg.batch * sizeof(float));
+  if (loss_step) *loss_step = step;
+  return B2R_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2r_train_step_device(b2r_buffer *b, int32_t batch, uint64_t seed,
+                          uint64_t offset, const b2r_batch *out,
+                          const b2r_c51_args *c51, b2r_stream stream) {
+  return b2r::train_step(b, batch, seed, offset, out, c51, as_stream(stream),
+                         nullptr, nullptr);
+}
+
+int b2r_train_step_sharded_device(b2r_buffer *b, b2r_exchange *x,
+                                  int32_t global_batch, uint64_t seed,
+                                  uint64_t offset, const b2r_batch *out,
+                                  const b2r_c51_args *c51, int32_t *out_slots,
+                                  int32_t *out_count, b2r_stream stream) {
+  b2r::ShardSpec shard = {x, out_slots, out_count};
+  return b2r::train_step(b, global_batch, seed, offset, out, c51, as_stream(stream),
+                         nullptr, nullptr, &shard);
+}
+
+int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
+                       b2r_trainer **out) {
+  if (!b || !cfg || !out) return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
+  if (cfg->batch <= 0 || cfg->batch > 60000 || cfg->num_actions <= 0 ||
+      cfg->num_atoms < 2 || cfg->pipeline_depth < 0 || cfg->pipeline_depth > 64)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "bad trainer configuration");
+  b2r_trainer *t = new (std::nothrow) b2r_trainer();
+  if (!t) return fail(B2R_ERR_INVALID_ARGUMENT, "out of host memory");
+  t->buf = b;
+  t->cfg = *cfg;
+  const size_t B = (size_t)cfg->batch, A = (size_t)cfg->num_actions,
+               N = (size_t)cfg->num_atoms;
+  const size_t logit_bytes = B * A * N * sizeof(float);
+  for (int set = 0; set < 2; ++set)
+    for (int k = 0; k < 2; ++k)
+      B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->logits[set][k]), logit_bytes));
+  // tf.linspace(-vmax, vmax, N) as TF-1.x evaluates it: start + i * step in f32
+  // (rainbow_agent.py:124-126).
+  std::vector<float> z(N);
+  const float lo = -cfg->vmax;
+  const float step = (cfg->vmax - lo) / (float)(N - 1);
+  for (size_t i = 0; i < N; ++i) z[i] = lo + (float)i * step;
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->support), N * sizeof(float)));
+  B2R_CUDA(cudaMemcpy(t->support, z.data(), N * sizeof(float), cudaMemcpyHostToDevice));
+
+  const size_t stack_bytes = (size_t)b->cfg.obs_bytes * b->cfg.stack_size;
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->frames), 2 * B * stack_bytes));
+  // scalar columns, 256-byte aligned segments
+  size_t off = 0;
+  auto seg = [&](size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return at;
+  };
+  const size_t o_action = seg(B * 4), o_reward = seg(B * 4), o_naction = seg(B * 4),
+               o_nreward = seg(B * 4), o_term = seg(B), o_idx = seg(B * 4),
+               o_prob = seg(B * 4), o_loss = seg(B * 4), o_prio = seg(B * 4),
+               o_w = seg(B * 4);
+  size_t o_extra[B2R_MAX_EXTRAS];
+  for (int e = 0; e < b->cfg.num_extras; ++e)
+    o_extra[e] = seg(B * (size_t)b->cfg.extra_bytes[e]);
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->scalars), off));
+  B2R_CUDA(cudaMemset(t->scalars, 0, off));
+  memset(&t->batch, 0, sizeof(t->batch));
+  t->batch.state = t->frames;
+  t->batch.next_state = t->frames + B * stack_bytes;
+  t->batch.action = t->scalars + o_action;
+  t->batch.reward = t->scalars + o_reward;
+  t->batch.next_action = t->scalars + o_naction;
+  t->batch.next_reward = t->scalars + o_nreward;
+  t->batch.terminal = t->scalars + o_term;
+  t->batch.indices = reinterpret_cast<int32_t *>(t->scalars + o_idx);
+  t->batch.sampling_probabilities = reinterpret_cast<float *>(t->scalars + o_prob);
+  for (int e = 0; e < b->cfg.num_extras; ++e) t->batch.extras[e] = t->scalars + o_extra[e];
+  memset(&t->c51, 0, sizeof(t->c51));
+  t->c51.batch = cfg->batch;
+  t->c51.num_actions = cfg->num_actions;
+  t->c51.num_atoms = cfg->num_atoms;
+  t->c51.cumulative_gamma = cfg->cumulative_gamma;
+  t->c51.support = t->support;
+  t->c51.loss = reinterpret_cast<float *>(t->scalars + o_loss);
+  t->c51.priorities = reinterpret_cast<float *>(t->scalars + o_prio);
+  t->c51.weights = reinterpret_cast<float *>(t->scalars + o_w);
+
+  B2R_CUDA(cudaStreamCreateWithFlags(&t->copy, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; ++k) {
+    B2R_CUDA(cudaEventCreateWithFlags(&t->ev_in[k], cudaEventDisableTiming));
+    B2R_CUDA(cudaEventCreateWithFlags(&t->ev_loss[k], cudaEventDisableTiming));
+  }
+  t->ring = cfg->pipeline_depth + 1;
+  B2R_CUDA(cudaMallocHost(reinterpret_cast<void **>(&t->ring_host),
+                          (size_t)t->ring * B * sizeof(float)));
+  t->ev_done.resize(t->ring);
+  for (int k = 0; k < t->ring; ++k)
+    B2R_CUDA(cudaEventCreateWithFlags(&t->ev_done[k], cudaEventDisableTiming));
+  *out = t;
+  return B2R_OK;
+}
+
+int b2r_trainer_destroy(b2r_trainer *t) {
+  if (!t) return B2R_OK;
+  cudaDeviceSynchronize();
+  for (int set = 0; set < 2; ++set)
+    for (int k = 0; k < 2; ++k) cudaFree(t->logits[set][k]);
+  cudaFree(t->support);
+  cudaFree(t->frames);
+  cudaFree(t->scalars);
+  if (t->copy) cudaStreamDestroy(t->copy);
+  for (int k = 0; k < 2; ++k) {
+    if (t->ev_in[k]) cudaEventDestroy(t->ev_in[k]);
+    if (t->ev_loss[k]) cudaEventDestroy(t->ev_loss[k]);
+  }
+  if (t->ring_host) cudaFreeHost(t->ring_host);
+  for (cudaEvent_t e : t->ev_done) cudaEventDestroy(e);
+  delete t;
+  return B2R_OK;
+}
+
+int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
+                          const float *target_logits, float *loss_out,
+                          int64_t *loss_step, b2r_stream stream) {
+  if (!t || !online_logits || !target_logits)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
+  cudaStream_t s = as_stream(stream);
+  const int64_t n = t->submitted;
+  const int set = (int)(n & 1);
+  const size_t logit_bytes = (size_t)t->cfg.batch * t->cfg.num_actions *
+                             t->cfg.num_atoms * sizeof(float);
+  // inputs: on the copy stream, beside the sampler; set `set` was last read by the
+  // loss kernel of step n - 2.
+  if (n >= 2) B2R_CUDA(cudaStreamWaitEvent(t->copy, t->ev_loss[set], 0));
+  B2R_CUDA(cudaMemcpyAsync(t->logits[set][0], online_logits, logit_bytes,
+                           cudaMemcpyHostToDevice, t->copy));
+  B2R_CUDA(cudaMemcpyAsync(t->logits[set][1], target_logits, logit_bytes,
+                           cudaMemcpyHostToDevice, t->copy));
+  B2R_CUDA(cudaEventRecord(t->ev_in[set], t->copy));
+  b2r_c51_args c51 = t->c51;
+  c51.online_logits = t->logits[set][0];
+  c51.target_logits = t->logits[set][1];
+  B2R_TRY(b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch, &c51, s,
+                          t->ev_in[set], t->ev_loss[set]));
+  // result: per-row losses into this step's pinned slot (copy stream, after the loss)
+  const int slot = (int)(n % t->ring);
+  B2R_CUDA(cudaStreamWaitEvent(t->copy, t->ev_loss[set], 0));
+  B2R_CUDA(cudaMemcpyAsync(t->ring_host + (size_t)slot * t->cfg.batch, t->c51.loss,
+                           (size_t)t->cfg.batch * sizeof(float),
+                           cudaMemcpyDeviceToHost, t->copy));
+  B2R_CUDA(cudaEventRecord(t->ev_done[slot], t->copy));
+  t->submitted = n + 1;
+  return collect(t, n - t->cfg.pipeline_depth, loss_out, loss_step);
+}
+
+int b2r_trainer_drain(b2r_trainer *t, float *loss_out, int64_t *loss_step,
+                      b2r_stream stream) {
+  if (!t) return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
+  B2R_CUDA(cudaStreamSynchronize(t->copy));
+  B2R_CUDA(cudaStreamSynchronize(as_stream(stream)));
+  return collect(t, t->submitted - 1, loss_out, loss_step);
+}
+
+int b2r_trainer_views(b2r_trainer *t, b2r_batch *batch, b2r_c51_args *c51) {
+  if (!t) return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (batch) *batch = t->batch;
+  if (c51) {
+    *c51 = t->c51;
+    const int set = (int)((t->submitted + 1) & 1);  // set of the last queued step
+    c51->online_logits = t->logits[set][0];
+    c51->target_logits = t->logits[set][1];
+    c51->actions = static_cast<const int32_t *>(t->batch.action);
+    c51->rewards = static_cast<const float *>(t->batch.reward);
+    c51->terminals = static_cast<const uint8_t *>(t->batch.terminal);
+    c51->sampling_probabilities = t->batch.sampling_probabilities;
+  }
+  return B2R_OK;
+}
+
+}  // extern "C"

@@ -7,15 +7,17 @@
 // the deltas of the batch elements below it must be added IN BATCH ORDER.
 //
 // ONE cooperative launch per chunk of <= 4096 sets, one CTA per tree level (see
-// tree_update_kernel): every CTA sorts its (node, k) keys in shared memory, the
-// leaf CTA resolves duplicate leaves as chains and publishes delta[k], a grid
-// barrier, then each internal CTA runs one ordered fp64 add-chain per touched node.
+// tree_update_kernel): every CTA groups the entries by node with a stable radix
+// sort in shared memory, the leaf CTA resolves duplicate leaves as chains and
+// publishes delta[k], a grid barrier, then each internal CTA runs one ordered fp64
+// add-chain per touched node.
 //
 // The critical path is the root's chain of n dependent DADDs; everything else
 // overlaps with it.  Bandwidth is irrelevant here (n * depth * 16 bytes).
 #include "tree.cuh"
 
 #include <cooperative_groups.h>
+#include <cub/block/block_radix_sort.cuh>
 
 #include <new>
 
@@ -27,25 +29,6 @@ namespace {
 B2R_TRACE_DECL
 
 constexpr uint64_t kPadKey = ~0ull;
-
-__device__ __forceinline__ void bitonic_sort(uint64_t *keys, int padded) {
-  for (int k = 2; k <= padded; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < padded; t += blockDim.x) {
-        const int partner = t ^ j;
-        if (partner > t) {
-          const uint64_t a = keys[t], b = keys[partner];
-          const bool ascending = (t & k) == 0;
-          if ((a > b) == ascending) {
-            keys[t] = b;
-            keys[partner] = a;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
 
 template <typename I, typename V>
 struct UpdateArgs {
@@ -64,15 +47,29 @@ struct UpdateArgs {
 };
 
 // ONE cooperative launch, grid = depth + 1 CTAs (CTA l owns level l, CTA `depth`
-// the leaves).  Every CTA sorts its own (node, k) keys concurrently; the leaf CTA
-// then resolves the per-leaf chains and publishes delta[k]; after one grid-wide
-// barrier each internal CTA adds the deltas that fall under each of its nodes in
-// batch order.  Critical path: one sort + the root's chain of n dependent DADDs.
+// the leaves).  Every CTA groups the chunk's elements by their node on its level
+// with a STABLE block radix sort over the node index only (the elements start in
+// batch order, so each group stays in batch order; level l sorts l bits, the root
+// nothing); the leaf CTA then resolves the per-leaf chains and publishes delta[k];
+// after one grid-wide barrier each internal CTA adds the deltas that fall under
+// each of its nodes in batch order.  Critical path: the leaf CTA's sort + the
+// root's chain of n dependent DADDs.
+constexpr int kBigThreads = 1024;
+constexpr int kBigItems = kTreeChunk / kBigThreads;
+using BigSort = cub::BlockRadixSort<uint32_t, kBigThreads, kBigItems, uint32_t>;
+
+struct BigSmem {
+  typename BigSort::TempStorage sort;
+  uint32_t node[kTreeChunk];  // node index on this level, grouped
+  uint32_t elem[kTreeChunk];  // batch position k of the same entry
+  double vals[kTreeChunk];    // value -> leaf delta (leaf CTA) / deltas in group order
+};
+
 template <typename I, typename V>
-__global__ void __launch_bounds__(1024) tree_update_kernel(UpdateArgs<I, V> a) {
+__global__ void __launch_bounds__(kBigThreads) tree_update_kernel(UpdateArgs<I, V> a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint64_t *keys = reinterpret_cast<uint64_t *>(smem_raw);
-  double *vals = reinterpret_cast<double *>(smem_raw) + a.padded;
+  BigSmem &sm = *reinterpret_cast<BigSmem *>(smem_raw);
+  double *vals = sm.vals;
   __shared__ int s_stop;       // first position that must not be applied
   __shared__ int s_stop_code;
   __shared__ double s_max[32];
@@ -80,6 +77,8 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(UpdateArgs<I, V> a) {
   cg::grid_group grid = cg::this_grid();
   const int level = blockIdx.x;
   const bool is_leaf = level == a.depth;
+  B2R_MARK_CTA(0, 0);
+  B2R_MARK_CTA(16, a.depth);
   int n = a.n;
   if (a.n_dev) {
     const int64_t left = (int64_t)*a.n_dev - a.k_base;
@@ -124,17 +123,27 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(UpdateArgs<I, V> a) {
     s_stop_code = (vals[n_eff] < 0.0) ? B2R_ERR_NEGATIVE_PRIORITY
                                       : B2R_ERR_INDEX_RANGE;
 
-  // 2. keys = (node at this level, k): sorting groups the elements under one node
-  //    and keeps batch order inside the group.  The root needs no sort.
+  // 2. group by node: thread t holds entries 4t .. 4t+3 (batch order); pads carry
+  //    all-ones keys and sit behind every real entry, so they stay last.
   const int shift = a.depth - level;
-  int p2 = 32;
-  while (p2 < n_eff) p2 <<= 1;
-  for (int k = threadIdx.x; k < p2; k += blockDim.x)
-    keys[k] = k < n_eff
-                  ? (((uint64_t)((int64_t)a.indices[k] >> shift)) << 32) | (uint32_t)k
-                  : kPadKey;
+  B2R_MARK_CTA(17, a.depth);
+  {
+    uint32_t key[kBigItems], val[kBigItems];
+#pragma unroll
+    for (int j = 0; j < kBigItems; ++j) {
+      const int k = threadIdx.x * kBigItems + j;
+      key[j] = k < n_eff ? (uint32_t)((int64_t)a.indices[k] >> shift) : 0xffffffffu;
+      val[j] = (uint32_t)k;
+    }
+    if (level != 0) BigSort(sm.sort).Sort(key, val, 0, level);
+#pragma unroll
+    for (int j = 0; j < kBigItems; ++j) {
+      sm.node[threadIdx.x * kBigItems + j] = key[j];
+      sm.elem[threadIdx.x * kBigItems + j] = val[j];
+    }
+  }
   __syncthreads();
-  if (level != 0) bitonic_sort(keys, p2);
+  B2R_MARK_CTA(18, a.depth);
 
   if (is_leaf) {
     // max_recorded_priority = max(value, current) over the applied prefix.
@@ -147,11 +156,11 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(UpdateArgs<I, V> a) {
     // one thread per distinct leaf walks its chain in batch order:
     //   delta = value - leaf; leaf += delta   (sum_tree.py:196-202, last level).
     for (int p = threadIdx.x; p < n_eff; p += blockDim.x) {
-      const uint32_t node = (uint32_t)(keys[p] >> 32);
-      if (p > 0 && (uint32_t)(keys[p - 1] >> 32) == node) continue;
+      const uint32_t node = sm.node[p];
+      if (p > 0 && sm.node[p - 1] == node) continue;
       double leaf = a.heap[a.leaves + node];
-      for (int q = p; q < n_eff && (uint32_t)(keys[q] >> 32) == node; ++q) {
-        const uint32_t k = (uint32_t)keys[q];
+      for (int q = p; q < n_eff && sm.node[q] == node; ++q) {
+        const uint32_t k = sm.elem[q];
         const double d = __dsub_rn(vals[k], leaf);
         leaf = __dadd_rn(leaf, d);
         vals[k] = d;
@@ -162,7 +171,10 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(UpdateArgs<I, V> a) {
     for (int k = threadIdx.x; k < n_eff; k += blockDim.x) a.delta[k] = vals[k];
   }
 
+  B2R_MARK_CTA(1, 0);
+  B2R_MARK_CTA(19, a.depth);
   grid.sync();
+  B2R_MARK_CTA(2, 0);
 
   if (is_leaf) {
     if (threadIdx.x == 0) {
@@ -178,26 +190,30 @@ __global__ void __launch_bounds__(1024) tree_update_kernel(UpdateArgs<I, V> a) {
     return;
   }
 
-  // 3. internal level: deltas in sorted order, then one ordered chain per node.
+  // 3. internal level: deltas in group order, then one ordered chain per node.
   double *sorted_delta = vals;
   for (int p = threadIdx.x; p < n_eff; p += blockDim.x)
-    sorted_delta[p] = a.delta[(uint32_t)keys[p]];
+    sorted_delta[p] = a.delta[sm.elem[p]];
   __syncthreads();
+  B2R_MARK_CTA(3, 0);
+  B2R_MARK_CTA(20, 1);
   const int64_t base = ((int64_t)1) << level;
   for (int p = threadIdx.x; p < n_eff; p += blockDim.x) {
-    const uint32_t node = (uint32_t)(keys[p] >> 32);
-    if (p > 0 && (uint32_t)(keys[p - 1] >> 32) == node) continue;
+    const uint32_t node = sm.node[p];
+    if (p > 0 && sm.node[p - 1] == node) continue;
     // end of the segment: first position whose node is larger (binary search).
     int lo = p + 1, hi = n_eff;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if ((uint32_t)(keys[mid] >> 32) > node) hi = mid; else lo = mid + 1;
+      if (sm.node[mid] > node) hi = mid; else lo = mid + 1;
     }
     double acc = a.heap[base + node];
 #pragma unroll 8
     for (int q = p; q < lo; ++q) acc = __dadd_rn(acc, sorted_delta[q]);
     a.heap[base + node] = acc;
   }
+  B2R_MARK_CTA(4, 0);
+  B2R_MARK_CTA(21, 1);
 }
 
 constexpr int kSmallBatch = 256;  // largest batch the single-CTA kernel takes
@@ -394,7 +410,7 @@ int allow_big_smem(K kernel) {
   if (!done) {
     B2R_CUDA(cudaFuncSetAttribute(kernel,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kTreeChunk * 16));
+                                  (int)sizeof(BigSmem)));
     done = true;
   }
   return B2R_OK;
@@ -439,17 +455,12 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
   B2R_TRY(allow_big_smem(tree_update_kernel<I, V>));
   for (int64_t base = 0; base < n; base += kTreeChunk) {
     const int len = (int)((n - base) < kTreeChunk ? (n - base) : kTreeChunk);
-    const int padded = padded_size(len);
-    int threads = padded / 2;
-    if (threads < 32) threads = 32;
-    if (threads > 1024) threads = 1024;
-    const size_t smem = (size_t)padded * 16;
     UpdateArgs<I, V> a;
     a.heap = t->heap;
     a.depth = t->depth;
     a.leaves = t->leaves;
     a.n = len;
-    a.padded = padded;
+    a.padded = kTreeChunk;
     a.indices = indices + base;
     a.values = values + base;
     a.mode = mode ? mode + base : nullptr;
@@ -458,10 +469,19 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     a.max_rec = t->max_rec;
     a.status = t->status;
     a.n_dev = n_dev;
-    void *params[] = {&a};
-    B2R_CUDA(cudaLaunchCooperativeKernel(
-        reinterpret_cast<const void *>(&tree_update_kernel<I, V>),
-        dim3(t->depth + 1), dim3(threads), params, smem, stream));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(t->depth + 1);
+    cfg.blockDim = dim3(kBigThreads);
+    cfg.dynamicSmemBytes = sizeof(BigSmem);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributePriority;
+    attr[1].val.priority = chain_priority();
+    cfg.attrs = attr;
+    cfg.numAttrs = chain_priority() != 0 ? 2 : 1;
+    B2R_CUDA(cudaLaunchKernelEx(&cfg, tree_update_kernel<I, V>, a));
     B2R_LAUNCHED();
   }
   return B2R_OK;

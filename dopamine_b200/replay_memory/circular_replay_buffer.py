@@ -50,6 +50,9 @@ def _torch():
 
 
 _TORCH_DTYPES = None
+# Scalars whose int() / float() conversion equals numpy's assignment cast.
+_PLAIN_SCALARS = frozenset([int, float, bool, np.int32, np.int64, np.uint8,
+                            np.float32, np.float64, np.bool_])
 
 
 def _torch_dtype(np_dtype):
@@ -164,6 +167,12 @@ class OutOfGraphReplayBuffer(object):
     self._reuse_outputs = bool(reuse_outputs)
     self._output_cache = {}
     self._lib = _native.lib()
+    # add() fast path: Atari layout and plain scalars -> one native call.
+    self._fast_add = (
+        tuple(action_shape) == () and np.dtype(action_dtype) == np.int32 and
+        np.dtype(reward_dtype) == np.float32 and
+        np.dtype(terminal_dtype) == np.uint8 and not self._extra_storage_types)
+    self._fast_obs = (tuple(observation_shape), np.dtype(observation_dtype))
     self._create_storage()
     # circular_replay_buffer.py:181-183
     self._cumulative_discount_vector = np.array(
@@ -341,9 +350,46 @@ class OutOfGraphReplayBuffer(object):
     Values are cast to the storage dtypes with numpy assignment semantics
     (CRB:280-282) and staged; one kernel writes them to HBM at the next read.
     """
+    if not args and self._try_fast_add(observation, action, reward, terminal, 0.0,
+                                       _native.PRIORITY_EXPLICIT):
+      return
     self._check_add_types(observation, action, reward, terminal, *args)
     self._native_add((observation, action, reward, terminal) + tuple(args), 0.0,
                      _native.PRIORITY_EXPLICIT)
+
+  def _try_fast_add(self, observation, action, reward, terminal, priority, mode):
+    """One native call when the arguments are what an Atari agent passes: a
+    C-contiguous observation of the storage dtype and plain scalars (whose
+    int()/float() conversion equals numpy's assignment cast, CRB:280-282).
+    Returns False when the general path (and its shape errors) must run."""
+    if not self._fast_add:
+      return False
+    if (type(observation) is not np.ndarray or
+        observation.shape != self._fast_obs[0] or
+        observation.dtype != self._fast_obs[1] or
+        not observation.flags.c_contiguous):
+      return False
+    if (type(action) not in _PLAIN_SCALARS or type(reward) not in _PLAIN_SCALARS
+        or type(terminal) not in _PLAIN_SCALARS):
+      return False
+    terminal = int(terminal)
+    if terminal < 0 or terminal > 255 or not -2147483648 <= action <= 2147483647:
+      return False
+    # No stream look-up per add: the call never launches; when the staging queue
+    # is full it says so, and the flush (which launches) gets the current stream.
+    status = self._lib.b2r_add_atari(
+        self._h, observation.ctypes.data, int(action), reward, terminal, priority,
+        mode, _native.STREAM_NONE)
+    if status == _native.QUEUE_FULL:
+      _native.check(self._lib.b2r_flush(self._h, self._stream()))
+      status = self._lib.b2r_add_atari(
+          self._h, observation.ctypes.data, int(action), reward, terminal,
+          priority, mode, _native.STREAM_NONE)
+    if status == _native.ERR_NEGATIVE_PRIORITY:
+      raise ValueError(_native.last_error())
+    if status:
+      _native.check(status)
+    return True
 
   def _native_add(self, values, priority, priority_mode):
     # One preallocated, correctly typed row buffer per storage element: numpy

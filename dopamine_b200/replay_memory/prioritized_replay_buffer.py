@@ -100,6 +100,16 @@ class OutOfGraphPrioritizedReplayBuffer(
 
   def add(self, observation, action, reward, terminal, *args):
     """add(observation, action, reward, terminal, *extras, priority)."""
+    if len(args) == 1:
+      last = args[0]
+      if last is MAX_RECORDED_PRIORITY:
+        if self._try_fast_add(observation, action, reward, terminal, 0.0,
+                              _native.PRIORITY_MAX_RECORDED):
+          return
+      elif type(last) in circular_replay_buffer._PLAIN_SCALARS:  # pylint: disable=protected-access
+        if self._try_fast_add(observation, action, reward, terminal, last,
+                              _native.PRIORITY_EXPLICIT):
+          return
     if args and args[-1] is MAX_RECORDED_PRIORITY:
       self._check_add_types(observation, action, reward, terminal,
                             *(args[:-1] + (0.0,)))

@@ -36,6 +36,69 @@ def all_gather_totals(local_total, group=None):
   return out
 
 
+class PeerExchange(object):
+  """Shard totals over peer memory (NVLink) instead of an NCCL all-gather.
+
+  Every rank owns a small device mailbox (`b2r_exchange_*` in the C ABI); the
+  sharded sampling kernel stores its root total straight into the peers' mailboxes
+  and polls its own, so the exchange costs one NVLink write latency inside a
+  kernel that runs anyway.  `torch.distributed` is only used once, here, to swap
+  the 64-byte CUDA IPC handles of the mailboxes.
+  """
+
+  def __init__(self, rank=None, world_size=None, group=None, timeout_s=2.0):
+    import torch
+    import torch.distributed as dist
+    self._lib = _native.lib()
+    self.rank = dist.get_rank(group) if rank is None else rank
+    self.world = dist.get_world_size(group) if world_size is None else world_size
+    handle = ctypes.c_void_p()
+    _native.check(self._lib.b2r_exchange_create(self.world, self.rank,
+                                                ctypes.byref(handle)))
+    self._h = handle
+    _native.check(self._lib.b2r_exchange_set_timeout(self._h, float(timeout_s)))
+    if self.world > 1:
+      mine = np.zeros(_native.IPC_HANDLE_BYTES, dtype=np.uint8)
+      _native.check(self._lib.b2r_exchange_local_handle(self._h, _native.ptr(mine)))
+      device = 'cuda' if dist.get_backend(group) == 'nccl' else 'cpu'
+      send = torch.as_tensor(mine, device=device)
+      recv = torch.empty(self.world * _native.IPC_HANDLE_BYTES, dtype=torch.uint8,
+                         device=device)
+      dist.all_gather_into_tensor(recv, send, group=group)
+      handles = np.ascontiguousarray(recv.cpu().numpy())
+      _native.check(self._lib.b2r_exchange_connect(self._h, _native.ptr(handles)))
+      dist.barrier(group)  # every mailbox is mapped before anyone writes
+
+  @classmethod
+  def emulated(cls, world):
+    """`world` exchanges on ONE device wired to each other by raw pointers: ranks
+    emulated by sequential launches (tests)."""
+    lib = _native.lib()
+    out = []
+    for rank in range(world):
+      x = cls.__new__(cls)
+      x._lib, x.rank, x.world = lib, rank, world
+      handle = ctypes.c_void_p()
+      _native.check(lib.b2r_exchange_create(world, rank, ctypes.byref(handle)))
+      x._h = handle
+      out.append(x)
+    boxes = (ctypes.c_void_p * world)(*[lib.b2r_exchange_mailbox(x._h) for x in out])
+    for x in out:
+      _native.check(lib.b2r_exchange_connect_pointers(x._h, boxes))
+    return out
+
+  def publish(self, memory):
+    """Publishes `memory`'s total for the next step ahead of the sampling call
+    (needed only when the ranks are emulated by sequential launches)."""
+    _native.check(self._lib.b2r_exchange_publish_device(
+        self._h, memory._h, _native.current_stream()))  # pylint: disable=protected-access
+
+  def __del__(self):
+    if getattr(self, '_h', None):
+      self._lib.b2r_exchange_destroy(self._h)
+      self._h = None
+
+
 def global_index(rank, shard_capacity, local_indices):
   """Index in the virtual replay of world * shard_capacity transitions."""
   return rank * shard_capacity + local_indices
@@ -44,11 +107,13 @@ def global_index(rank, shard_capacity, local_indices):
 class ShardedPrioritizedReplay(object):
   """Global stratified sampling over one local shard per rank."""
 
-  def __init__(self, memory, rank=None, world_size=None, group=None, seed=0):
+  def __init__(self, memory, rank=None, world_size=None, group=None, seed=0,
+               exchange=None):
     import torch
     import torch.distributed as dist
     self.memory = memory
     self.group = group
+    self.exchange = exchange  # PeerExchange, or None: NCCL / gloo all-gather
     self.rank = dist.get_rank(group) if rank is None else rank
     self.world = dist.get_world_size(group) if world_size is None else world_size
     self.seed = int(seed)
@@ -72,12 +137,20 @@ class ShardedPrioritizedReplay(object):
     """Returns (slots, indices, count): CUDA int32 tensors of length global_batch
     whose first `count` (device scalar) entries are this rank's strata."""
     torch = self._torch
-    if totals is None:
-      totals = self.totals()
     slots = torch.empty(global_batch, dtype=torch.int32, device='cuda')
     indices = torch.zeros(global_batch, dtype=torch.int32, device='cuda')
     n_retry = (len(retry_u01) if retry_u01 is not None else
                self.memory._max_sample_attempts)  # pylint: disable=protected-access
+    if totals is None and self.exchange is not None:
+      _native.check(self._lib.b2r_sample_indices_sharded_p2p_device(
+          self._h, self.exchange._h, global_batch,  # pylint: disable=protected-access
+          queries01.data_ptr() if queries01 is not None else None, n_retry,
+          retry_u01.data_ptr() if retry_u01 is not None else None, self.seed, 0,
+          slots.data_ptr(), indices.data_ptr(), self._count.data_ptr(),
+          _native.current_stream()))
+      return slots, indices, self._count
+    if totals is None:
+      totals = self.totals()
     _native.check(self._lib.b2r_sample_indices_sharded_device(
         self._h, global_batch, self.world, self.rank, totals.data_ptr(),
         queries01.data_ptr() if queries01 is not None else None, n_retry,
@@ -107,13 +180,14 @@ class ShardedStep(object):
   """bench.py's N>1 step: all-gather totals -> sharded sample -> gather -> C51
   loss/priorities -> write-back, for a global batch spread over the ranks."""
 
-  def __init__(self, workload, global_batch, world, rank, dist):
+  def __init__(self, workload, global_batch, world, rank, dist, exchange=None):
     import torch
     self.wl = workload
     self.global_batch = global_batch
     self.dist = dist
+    self.exchange = exchange
     self.sharded = ShardedPrioritizedReplay(
-        workload.mem, rank=rank, world_size=world, seed=1234)
+        workload.mem, rank=rank, world_size=world, seed=1234, exchange=exchange)
     t, b, c = workload.plan(global_batch)
     self.t, self.b, self.c = t, b, c
     self.slots = torch.empty(global_batch, dtype=torch.int32, device='cuda')
@@ -126,8 +200,16 @@ class ShardedStep(object):
   def step(self):
     nat, lib, sh = self.wl.native, self.lib, self.sharded
     stream = nat.current_stream()
-    totals = sh.totals()
     count_ptr = sh._count.data_ptr()  # pylint: disable=protected-access
+    if self.exchange is not None:
+      # one call: totals exchanged over peer memory inside the sampling kernel,
+      # scalar columns from the sampler, frame copies on the forked stream
+      nat.check(lib.b2r_train_step_sharded_device(
+          self.h, self.exchange._h, self.global_batch, sh.seed, 0,  # pylint: disable=protected-access
+          ctypes.byref(self.b), ctypes.byref(self.c), self.slots.data_ptr(),
+          count_ptr, stream))
+      return
+    totals = sh.totals()
     nat.check(lib.b2r_sample_indices_sharded_device(
         self.h, self.global_batch, sh.world, sh.rank, totals.data_ptr(), None,
         sh.memory._max_sample_attempts, None, sh.seed, 0,  # pylint: disable=protected-access

@@ -44,8 +44,16 @@ typedef enum {
   B2R_ERR_SAMPLE_ATTEMPTS = 5,   /* CRB:471-475 / PRB:160-163 RuntimeError    */
   B2R_ERR_TOO_FEW_TRANSITIONS = 6, /* CRB:457-460 RuntimeError                */
   B2R_ERR_INDEX_RANGE = 7,
-  B2R_ERR_UNSUPPORTED = 8
+  B2R_ERR_UNSUPPORTED = 8,
+  B2R_ERR_EXCHANGE = 9,          /* a peer shard did not publish its total in time */
+  B2R_QUEUE_FULL = 10            /* b2r_add with B2R_STREAM_NONE: flush, then retry */
 } b2r_status;
+
+/* Stream argument of b2r_add / b2r_add_atari meaning "never launch from this call":
+ * if the staging queue has no room the call changes nothing and returns
+ * B2R_QUEUE_FULL; the caller then calls b2r_flush(buf, stream) and adds again.
+ * Lets a host loop add rows without looking up its current stream every time. */
+#define B2R_STREAM_NONE ((b2r_stream)(intptr_t)-1)
 
 const char *b2r_last_error(void);
 int b2r_abi_version(void);
@@ -150,6 +158,12 @@ int b2r_add(b2r_buffer *buf, const void *observation, const void *action,
             const void *reward, const void *terminal,
             const void *const *extras, double priority, int priority_mode,
             b2r_stream stream);
+/* b2r_add for the Atari layout (scalar int32 action, float32 reward, uint8 terminal,
+ * no extras) with the scalars passed by value: one call, no host-side row buffers.
+ * Other layouts -> B2R_ERR_UNSUPPORTED. */
+int b2r_add_atari(b2r_buffer *buf, const void *observation, int32_t action,
+                  float reward, uint8_t terminal, double priority,
+                  int priority_mode, b2r_stream stream);
 int b2r_flush(b2r_buffer *buf, b2r_stream stream);
 
 /* add_count (CRB:177), cursor() (CRB:334-336), invalid_range (CRB:53-77, 285-287). */
@@ -273,6 +287,44 @@ int b2r_sample_indices_sharded_device(b2r_buffer *buf, int32_t global_batch,
                                       uint64_t offset, int32_t *out_slots,
                                       int32_t *out_indices, int32_t *out_count,
                                       b2r_stream stream);
+/* Shard totals over peer memory (NVLink / NVSwitch) instead of a collective
+ * library: every rank owns a small device mailbox; inside the sharded sampling
+ * kernel each rank stores its root total straight into every peer's mailbox and
+ * polls its own, so the "all-gather" costs one NVLink write latency and no extra
+ * launch.  Set-up: create on every rank, exchange the 64-byte handles by any
+ * transport (torch.distributed, MPI, a file), connect.  All ranks must then make
+ * the same sequence of exchange-based calls (each call is one step of a device
+ * counter).  A peer that does not answer within the timeout (default 2 s) latches
+ * B2R_ERR_EXCHANGE, reported by b2r_check; later calls then skip the wait. */
+typedef struct b2r_exchange b2r_exchange;
+#define B2R_IPC_HANDLE_BYTES 64
+int b2r_exchange_create(int32_t world, int32_t rank, b2r_exchange **out);
+int b2r_exchange_destroy(b2r_exchange *exchange);
+/* cudaIpcMemHandle_t of this rank's mailbox (B2R_IPC_HANDLE_BYTES bytes, HOST). */
+int b2r_exchange_local_handle(b2r_exchange *exchange, void *handle_out);
+/* handles: world x B2R_IPC_HANDLE_BYTES in rank order (the own entry is ignored);
+ * opens the peers' mailboxes with peer access enabled. */
+int b2r_exchange_connect(b2r_exchange *exchange, const void *handles);
+/* Same-process variant for ranks emulated on one device (tests): mailboxes[g] is
+ * rank g's b2r_exchange_mailbox(). */
+int b2r_exchange_connect_pointers(b2r_exchange *exchange, void *const *mailboxes);
+void *b2r_exchange_mailbox(b2r_exchange *exchange);
+int b2r_exchange_set_timeout(b2r_exchange *exchange, double seconds);
+/* Publishes this rank's total for the NEXT step without consuming the step (the
+ * sampling call publishes again, identically).  Only needed when ranks are
+ * emulated by sequential launches on one device, where a launch cannot wait for a
+ * later one.  Asynchronous. */
+int b2r_exchange_publish_device(b2r_exchange *exchange, b2r_buffer *buf,
+                                b2r_stream stream);
+/* b2r_sample_indices_sharded_device with the totals taken from the exchange. */
+int b2r_sample_indices_sharded_p2p_device(b2r_buffer *buf, b2r_exchange *exchange,
+                                          int32_t global_batch,
+                                          const double *query01, int32_t n_retry,
+                                          const double *retry_u01, uint64_t seed,
+                                          uint64_t offset, int32_t *out_slots,
+                                          int32_t *out_indices, int32_t *out_count,
+                                          b2r_stream stream);
+
 /* Variants whose element count lives on the DEVICE (*count <= max_...): what a
  * shard serves of a global batch is only known there.  Rows past *count are
  * skipped.  Asynchronous. */
@@ -316,11 +368,82 @@ typedef struct {
   float *mean_weighted_loss;    /* scalar or NULL                      RA:293, 305 */
   float *grad_logits;           /* (B, A, N) d mean(w*loss)/d online_logits or NULL */
   const int32_t *batch_count;   /* NULL, or DEVICE count <= batch of rows to process */
+  const float *min_probability; /* NULL, or DEVICE scalar min_b sampling_probabilities[b]
+                                   (what b2r_train_step_device's sampler leaves behind);
+                                   NULL: reduced inside the kernel                  */
 } b2r_c51_args;
 
 /* Bellman target + projection + softmax cross-entropy + new priorities + IS
  * weights in one launch (RA:200-293). */
 int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream);
+
+/* ------------------------------------------------------------------------- */
+/* The whole hot path in one call (what one sess.run(train_op)   */
+/* does around the network): PRB:142-201 -> RA:200-293 -> PRB:203-214.          */
+/* ------------------------------------------------------------------------- */
+
+/* Prioritized sample (device Philox, as b2r_sample_indices_device) -> batch
+ * assembly -> C51 loss / new priorities -> priority write-back.  The sampler
+ * writes the scalar columns of the batch itself (n-step return, terminal, actions,
+ * sampling_probabilities and their minimum), so the loss and the write-back follow
+ * it directly on `stream`, while the frame-stack copies (state / next_state) run
+ * beside them on an internal stream that forks after the sampler and joins
+ * `stream` again before the call returns: later work on `stream` sees the whole
+ * batch.  In `c51`, actions / rewards / terminals / sampling_probabilities /
+ * min_probability and batch are taken from `out` (whatever the caller put there is
+ * ignored).  out->indices, reward, terminal, action and (prioritized buffers)
+ * sampling_probabilities are required.  DEVICE pointers; asynchronous; can be
+ * captured in a CUDA graph. */
+int b2r_train_step_device(b2r_buffer *buf, int32_t batch, uint64_t seed,
+                          uint64_t offset, const b2r_batch *out,
+                          const b2r_c51_args *c51, b2r_stream stream);
+
+/* The same for one shard of a sharded replay: global
+ * stratified batch of `global_batch` strata over `exchange`'s ranks, this rank's
+ * rows compacted at the front of `out` (*out_count of them, device; out_slots[r] =
+ * stratum of row r), loss and write-back over those rows only.  The single
+ * exchange of shard totals happens inside the sampling kernel. */
+int b2r_train_step_sharded_device(b2r_buffer *buf, b2r_exchange *exchange,
+                                  int32_t global_batch, uint64_t seed,
+                                  uint64_t offset, const b2r_batch *out,
+                                  const b2r_c51_args *c51, int32_t *out_slots,
+                                  int32_t *out_count, b2r_stream stream);
+
+/* Host-facing, pipelined form of the same step: what an agent's training loop
+ * calls once per update with the network outputs in HOST memory
+ * (dqn_agent.py:359-442 around rainbow_agent.py:253-305).  The trainer owns the
+ * device copies of the logits, the batch outputs and a ring of pinned result
+ * slots. */
+typedef struct b2r_trainer b2r_trainer;
+
+typedef struct {
+  int32_t batch, num_actions, num_atoms;
+  float vmax;              /* support = linspace(-vmax, vmax, N) in f32 (RA:126)   */
+  float cumulative_gamma;  /* f32(pow(gamma, update_horizon))       (DQ:175)       */
+  uint64_t seed;           /* Philox key of the sampler                            */
+  int32_t pipeline_depth;  /* 0: each call returns its own losses (synchronous);
+                              d > 0: the losses of the step queued d calls earlier */
+} b2r_trainer_config;
+
+int b2r_trainer_create(b2r_buffer *buf, const b2r_trainer_config *config,
+                       b2r_trainer **out);
+int b2r_trainer_destroy(b2r_trainer *trainer);
+
+/* One training iteration.  Applies the staged add()s, copies both logits tensors
+ * ((B, A, N) f32, HOST; page-locked memory keeps the copies asynchronous and must
+ * then stay untouched until the step has run), runs b2r_train_step_device and
+ * copies the per-row losses back.  loss_out (B floats, HOST) receives the losses
+ * of step number *loss_step (0-based; -1 and untouched while the pipeline fills).
+ * The host only ever waits for a step queued pipeline_depth calls ago. */
+int b2r_trainer_step_host(b2r_trainer *trainer, const float *online_logits,
+                          const float *target_logits, float *loss_out,
+                          int64_t *loss_step, b2r_stream stream);
+/* Waits for everything queued; loss_out / *loss_step describe the last step. */
+int b2r_trainer_drain(b2r_trainer *trainer, float *loss_out, int64_t *loss_step,
+                      b2r_stream stream);
+/* Device views of the trainer's batch (valid for the last step that has run) and
+ * of its loss outputs (loss, priorities, weights in a b2r_c51_args). */
+int b2r_trainer_views(b2r_trainer *trainer, b2r_batch *batch, b2r_c51_args *c51);
 
 #ifdef __cplusplus
 }

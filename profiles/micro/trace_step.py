@@ -16,6 +16,7 @@ def main():
   import torch
   from dopamine_b200 import _native
   wl = bench.GpuWorkload(200000, batch, 0)
+  wl.fused = os.environ.get('B2R_UNFUSED') is None
   lib = _native.lib()
   g = torch.cuda.CUDAGraph()
   s = torch.cuda.Stream()
@@ -33,9 +34,11 @@ def main():
     fn = getattr(lib, 'b2r_debug_trace_' + name)
     fn.argtypes = [ctypes.c_void_p]
     fn(out)
-    marks = [v for v in out if v]
-    print(name, 'marks (cycles since mark 0):',
-          [int(v - marks[0]) for v in marks])
+    marks = {i: v for i, v in enumerate(out) if v}
+    if marks:
+      t0 = min(marks.values())
+      print(name, 'marks {index: cycles since the first}:',
+            {i: int(v - t0) for i, v in marks.items()})
 
 
 if __name__ == '__main__':

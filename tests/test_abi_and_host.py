@@ -26,14 +26,31 @@ def test_library_exports_every_declared_symbol():
   for name in names:
     assert hasattr(lib, name), name
   assert sorted(_native.SIGNATURES) == names
-  assert lib.b2r_abi_version() == 1
+  assert lib.b2r_abi_version() == 2
 
 
-def test_struct_layouts_match_the_header():
-  # sizes the C compiler produces for the by-pointer structs
+def test_struct_layouts_match_the_header(tmp_path):
+  """ctypes mirrors vs what a C compiler makes of include/b200_replay.h."""
+  import subprocess
+  src = tmp_path / 'sizes.c'
+  src.write_text(
+      '#include <stdio.h>\n#include <stddef.h>\n#include "b200_replay.h"\n'
+      'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(b2r_config), '
+      'sizeof(b2r_batch), sizeof(b2r_c51_args), sizeof(b2r_trainer_config), '
+      'offsetof(b2r_c51_args, min_probability), '
+      'offsetof(b2r_trainer_config, seed)); return 0; }\n')
+  exe = tmp_path / 'sizes'
+  subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src),
+                         '-o', str(exe)])
+  got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+  assert got == [ctypes.sizeof(_native.Config), ctypes.sizeof(_native.Batch),
+                 ctypes.sizeof(_native.C51Args),
+                 ctypes.sizeof(_native.TrainerConfig),
+                 _native.C51Args.min_probability.offset,
+                 _native.TrainerConfig.seed.offset]
   assert ctypes.sizeof(_native.Config) == 96
   assert ctypes.sizeof(_native.Batch) == 8 * 8 + 8 * _native.MAX_EXTRAS + 8
-  assert ctypes.sizeof(_native.C51Args) == 16 + 14 * 8
+  assert ctypes.sizeof(_native.C51Args) == 16 + 15 * 8
 
 
 def test_no_cpu_fallback_without_a_device():

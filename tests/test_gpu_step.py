@@ -1,0 +1,430 @@
+"""Parity of the fused hot-path step (b2r_train_step_device / b2r_trainer_*) against
+the oracle and against the separately tested sample / gather / loss / write-back
+entry points.  Needs a B200: run with `pytest -m gpu`.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import c51_port
+from oracle import fast
+
+pytestmark = pytest.mark.gpu
+
+FRAME = 84 * 84
+ACTIONS, ATOMS = 18, 51
+
+
+@pytest.fixture(scope='module')
+def gpu():
+  import torch
+  if not torch.cuda.is_available():
+    pytest.fail('-m gpu tests need a CUDA device (no CPU fallback exists)')
+  from dopamine_b200 import _native
+  from dopamine_b200.agents.rainbow import rainbow_agent
+  from dopamine_b200.replay_memory import prioritized_replay_buffer as prb
+
+  class Mods(object):
+    pass
+
+  m = Mods()
+  m.torch, m.prb, m.ra, m.native = torch, prb, rainbow_agent, _native
+  return m
+
+
+def _filled(gpu, cap, batch, seed, horizon=3, term_p=0.01, hot=True):
+  """A full, wrapped prioritized buffer + host mirrors of its columns and tree."""
+  rng = np.random.RandomState(seed)
+  mem = gpu.prb.OutOfGraphPrioritizedReplayBuffer(
+      (84, 84), 4, cap, batch, update_horizon=horizon, gamma=0.99, output='torch',
+      rng='device', seed=seed)
+  pattern = rng.randint(0, 256, size=(1031, FRAME)).astype(np.uint8)
+  obs = np.empty((cap, FRAME), dtype=np.uint8)
+  for start in range(0, cap, 1031):
+    n = min(1031, cap - start)
+    obs[start:start + n] = pattern[:n]
+  obs[:, :8] = np.arange(cap, dtype=np.int64).view(np.uint8).reshape(cap, 8)
+  action = rng.randint(0, ACTIONS, size=cap).astype(np.int32)
+  reward = np.clip(rng.randn(cap), -1, 1).astype(np.float32)
+  terminal = (rng.rand(cap) < term_p).astype(np.uint8)
+  mem._store['observation'] = obs.reshape(cap, 84, 84)
+  mem._store['action'] = action
+  mem._store['reward'] = reward
+  mem._store['terminal'] = terminal
+  add_count = cap + 4242
+  mem.add_count = add_count
+  inv = np.array([(4242 - horizon + i) % cap for i in range(4 + horizon)])
+  mem.invalid_range = inv
+  tree = fast.FastTree(cap)
+  step = 50000
+  for lo in range(0, cap, step):
+    n = min(step, cap - lo)
+    ids = np.arange(lo, lo + n, dtype=np.int32)
+    pr = np.sqrt(np.abs(rng.randn(n)) + 1e-10).astype(np.float32)
+    mem.set_priority(ids, pr)
+    tree.set_seq(ids, pr.astype(np.float64))
+  if hot:  # high-priority slots inside the invalid window: retries must happen
+    ids = np.array(inv[:4], dtype=np.int32)
+    mem.set_priority(ids, np.full(4, 0.02 * cap, dtype=np.float32))
+    tree.set_seq(ids, np.full(4, 0.02 * cap))
+  cols = dict(obs=obs, action=action, reward=reward, terminal=terminal, inv=inv,
+              add_count=add_count)
+  return mem, tree, cols
+
+
+def _check_step(gpu, mem, tree, cols, cap, horizon, got, out, online, target):
+  """One fused step's outputs against the oracles; applies the write-back to `tree`."""
+  idx = got[7].cpu().numpy()
+  assert all(fast.is_valid(int(i), cap, cols['add_count'], 4, horizon, cols['inv'],
+                           cols['terminal']) for i in idx)
+  want = fast.gather_u8(cap, FRAME, 4, horizon, mem._cumulative_discount_vector,
+                        cols['obs'], cols['action'], cols['reward'],
+                        cols['terminal'], idx)
+  names = ['state', 'action', 'reward', 'next_state', 'next_action',
+           'next_reward', 'terminal', 'indices']
+  for nm, w, g in zip(names, want, got[:8]):
+    assert w.tobytes() == g.cpu().numpy().reshape(w.shape).tobytes(), nm
+  leaves = tree.level(tree.depth)
+  probs = leaves[idx].astype(np.float32)
+  assert got[8].cpu().numpy().tobytes() == probs.tobytes()
+  ref = c51_port.rainbow_update(want[2], want[6], want[1], probs, online, target,
+                                update_horizon=horizon)
+  for key in ('loss', 'priorities', 'weights'):
+    np.testing.assert_allclose(out[key].cpu().numpy(), ref[key], rtol=2e-6,
+                               atol=1e-6, err_msg=key)
+  pr = out['priorities'].cpu().numpy()
+  tree.set_seq(idx, pr.astype(np.float64))
+  return idx
+
+
+@pytest.mark.parametrize('cap,batch', [(100000, 32), (100000, 300), (200000, 1024),
+                                       (1000000, 4096)])
+def test_fused_step_matches_oracles(gpu, cap, batch):
+  """sample -> scalars -> C51 -> write-back in one call (frames on the forked
+  stream): every batch column bit-exact against the C restatement at the sampled
+  indices, loss / priorities / weights within 1e-6 of the numpy restatement, every
+  fp64 tree node bit-exact after the write-backs."""
+  torch = gpu.torch
+  mem, tree, cols = _filled(gpu, cap, batch, seed=cap // 1000 + batch)
+  rng = np.random.RandomState(5)
+  support = gpu.ra.make_support(10., ATOMS)
+  out = None
+  seen = set()
+  for step in range(3):
+    online = rng.randn(batch, ACTIONS, ATOMS).astype(np.float32)
+    target = rng.randn(batch, ACTIONS, ATOMS).astype(np.float32)
+    got, out = gpu.ra.train_step(mem, torch.as_tensor(online, device='cuda'),
+                                 torch.as_tensor(target, device='cuda'), support,
+                                 0.99 ** 3, out=out)
+    torch.cuda.synchronize()
+    idx = _check_step(gpu, mem, tree, cols, cap, 3, got, out, online, target)
+    seen.add(tuple(idx[:8].tolist()))
+  assert len(seen) == 3  # fresh strata every step
+  gpu.native.check(gpu.native.lib().b2r_check(mem._h, gpu.native.current_stream()))
+  for l, level in enumerate(mem.sum_tree.nodes):
+    assert np.array_equal(level.view(np.uint64), tree.level(l).view(np.uint64)), l
+
+
+@pytest.mark.parametrize('batch', [32, 1024])
+def test_fused_step_equals_separate_calls(gpu, batch):
+  """Same seed, twin buffers: the fused call and the sequence sample_transition_batch
+  -> c51_loss -> set_priority produce identical bits (indices, batch, losses, tree)."""
+  torch = gpu.torch
+  cap = 100000
+  mem_a, _, _ = _filled(gpu, cap, batch, seed=11)
+  mem_b, _, _ = _filled(gpu, cap, batch, seed=11)
+  rng = np.random.RandomState(2)
+  support = gpu.ra.make_support(10., ATOMS)
+  for step in range(3):
+    online = torch.as_tensor(rng.randn(batch, ACTIONS, ATOMS).astype(np.float32),
+                             device='cuda')
+    target = torch.as_tensor(rng.randn(batch, ACTIONS, ATOMS).astype(np.float32),
+                             device='cuda')
+    got_a, out_a = gpu.ra.train_step(mem_a, online, target, support, 0.99 ** 3)
+    got_b = mem_b.sample_transition_batch(batch)
+    out_b = gpu.ra.c51_loss(online, target, got_b[1], got_b[2], got_b[6], got_b[8],
+                            support, 0.99 ** 3, want_mean=False)
+    mem_b.set_priority(got_b[7], out_b['priorities'])
+    torch.cuda.synchronize()
+    for a, b in zip(got_a, got_b):
+      assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes()
+    for key in ('loss', 'priorities', 'weights'):
+      assert (out_a[key].cpu().numpy().tobytes() ==
+              out_b[key].cpu().numpy().tobytes()), key
+  for la, lb in zip(mem_a.sum_tree.nodes, mem_b.sum_tree.nodes):
+    assert np.array_equal(la.view(np.uint64), lb.view(np.uint64))
+
+
+def test_fused_step_in_cuda_graph(gpu):
+  """The forked frame copies survive stream capture: a replayed graph keeps drawing
+  fresh strata and stays equal to eager execution on a twin buffer."""
+  torch = gpu.torch
+  cap, batch = 100000, 64
+  mem_a, _, _ = _filled(gpu, cap, batch, seed=3)
+  mem_b, _, _ = _filled(gpu, cap, batch, seed=3)
+  rng = np.random.RandomState(9)
+  support = gpu.ra.make_support(10., ATOMS)
+  online = torch.as_tensor(rng.randn(batch, ACTIONS, ATOMS).astype(np.float32),
+                           device='cuda')
+  target = torch.as_tensor(rng.randn(batch, ACTIONS, ATOMS).astype(np.float32),
+                           device='cuda')
+  mem_a._reuse_outputs = mem_b._reuse_outputs = True
+  side = torch.cuda.Stream()
+  side.wait_stream(torch.cuda.current_stream())
+  with torch.cuda.stream(side):
+    got_a, out_a = gpu.ra.train_step(mem_a, online, target, support, 0.99 ** 3)
+    side.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+      gpu.ra.train_step(mem_a, online, target, support, 0.99 ** 3, out=out_a)
+    for _ in range(3):
+      graph.replay()
+    side.synchronize()
+  torch.cuda.current_stream().wait_stream(side)
+  # mem_a ran 1 eager step (host offset 1) + 3 replays of a graph captured with host
+  # offset 2; the device draw counter advanced 0, 1, 2, 3 underneath.
+  out_b = None
+  for host_offset in (1, 2, 2, 2):
+    mem_b._draw_counter = host_offset - 1
+    got_b, out_b = gpu.ra.train_step(mem_b, online, target, support, 0.99 ** 3,
+                                     out=out_b)
+  torch.cuda.synchronize()
+  for a, b in zip(got_a, got_b):
+    assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes()
+  for la, lb in zip(mem_a.sum_tree.nodes, mem_b.sum_tree.nodes):
+    assert np.array_equal(la.view(np.uint64), lb.view(np.uint64))
+
+
+@pytest.mark.parametrize('depth', [0, 2])
+def test_trainer_host_steps_match_oracles(gpu, depth):
+  """The pipelined host-facing trainer: adds between steps, logits from host
+  memory, losses handed back `depth` calls later; batch, losses and tree checked
+  against the oracles step by step."""
+  torch = gpu.torch
+  cap, batch = 50000, 32
+  mem, tree, cols = _filled(gpu, cap, batch, seed=21, hot=False)
+  trainer = gpu.ra.ReplayTrainer(mem, ACTIONS, ATOMS, 10., pipeline_depth=depth,
+                                 seed=21)
+  rng = np.random.RandomState(4)
+  inputs, losses = [], {}
+  for step in range(6):
+    online = rng.randn(batch, ACTIONS, ATOMS).astype(np.float32)
+    target = rng.randn(batch, ACTIONS, ATOMS).astype(np.float32)
+    inputs.append((online, target))
+    loss, done = trainer.step(online, target)
+    assert done == step - depth if step >= depth else done == -1
+    if done >= 0:
+      losses[done] = loss
+    # Every step is checked as it completes (the views are only stable then).
+    torch.cuda.synchronize()
+    transition, out = trainer.views()
+    got = [transition[k] for k in ('state', 'action', 'reward', 'next_state',
+                                   'next_action', 'next_reward', 'terminal',
+                                   'indices', 'sampling_probabilities')]
+    _check_step(gpu, mem, tree, cols, cap, 3, got, out, online, target)
+    losses.setdefault(('device', step), out['loss'].cpu().numpy().copy())
+  loss, done = trainer.drain()
+  assert done == 5
+  losses[done] = loss
+  for step in range(6):
+    if step in losses:
+      assert losses[step].tobytes() == losses[('device', step)].tobytes(), step
+  assert 5 - depth in losses
+  for l, level in enumerate(mem.sum_tree.nodes):
+    assert np.array_equal(level.view(np.uint64), tree.level(l).view(np.uint64)), l
+
+
+def test_trainer_applies_adds_between_steps(gpu):
+  """add() rows staged between trainer steps are in HBM (rows, priorities, validity
+  window) before the next step samples."""
+  from oracle.replay_port import PortPrioritizedReplay
+  torch = gpu.torch
+  cap, batch = 256, 16
+  prb = gpu.prb
+  mem = prb.OutOfGraphPrioritizedReplayBuffer((84, 84), 4, cap, batch,
+                                              update_horizon=3, gamma=0.99,
+                                              output='torch', rng='device', seed=1)
+  port = PortPrioritizedReplay((84, 84), 4, cap, batch, update_horizon=3, gamma=0.99)
+  rng = np.random.RandomState(0)
+  trainer = gpu.ra.ReplayTrainer(mem, ACTIONS, ATOMS, 10., pipeline_depth=1, seed=1)
+  added = 0
+
+  def add_rows(n):
+    nonlocal added
+    for _ in range(n):
+      row = (rng.randint(0, 256, size=(84, 84)).astype(np.uint8), rng.randint(18),
+             np.float32(np.clip(rng.randn(), -1, 1)), int(rng.rand() < 0.05))
+      port.add(*row, port.sum_tree.max_recorded_priority)
+      mem.add(*row, prb.MAX_RECORDED_PRIORITY)
+      added += 1
+
+  add_rows(100)
+  for step in range(40):
+    add_rows(4)
+    online = rng.randn(batch, ACTIONS, ATOMS).astype(np.float32)
+    target = rng.randn(batch, ACTIONS, ATOMS).astype(np.float32)
+    trainer.step(online, target)
+    torch.cuda.synchronize()
+    transition, out = trainer.views()
+    idx = transition['indices'].cpu().numpy()
+    assert all(port.is_valid_transition(int(i)) for i in idx), step
+    want = port.sample_transition_batch(batch, indices=idx.tolist())
+    names = ['state', 'action', 'reward', 'next_state', 'next_action',
+             'next_reward', 'terminal', 'indices', 'sampling_probabilities']
+    for nm, w in zip(names, want):
+      assert w.tobytes() == transition[nm].cpu().numpy().reshape(w.shape).tobytes(), nm
+    port.set_priority(idx, out['priorities'].cpu().numpy())
+  trainer.drain()
+  for a, b in zip(mem.sum_tree.nodes, port.sum_tree.nodes):
+    assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+# ------------------------------------------------- peer-memory exchange ----
+def _shard_pairs(gpu, num_shards, rng, cap=400, shape=(8, 8)):
+  from oracle.replay_port import PortPrioritizedReplay
+  from tests.test_gpu_parity import _fill_pair
+  kw = dict(update_horizon=3, gamma=0.99, max_sample_attempts=64)
+  ours, ports = [], []
+  for g in range(num_shards):
+    o = gpu.prb.OutOfGraphPrioritizedReplayBuffer(shape, 4, cap, 8, output='torch',
+                                                  **kw)
+    p = PortPrioritizedReplay(shape, 4, cap, 8, **kw)
+    _fill_pair(rng, o, p, 300 + 57 * g, shape, True, term_p=0.1)
+    ours.append(o)
+    ports.append(p)
+  return ours, ports
+
+
+@pytest.mark.parametrize('num_shards,global_batch', [(2, 32), (8, 256), (4, 1024)])
+def test_peer_exchange_sampling_matches_oracle(gpu, num_shards, global_batch):
+  """Shard totals through the peer-memory mailboxes (ranks emulated on one device:
+  every rank publishes, then every rank samples): over several steps with the
+  priorities changing in between, each rank must serve exactly the strata and
+  indices of the CPU statement of the rule — i.e. it saw every peer's CURRENT total
+  (both mailbox parities are exercised)."""
+  from dopamine_b200.replay_memory import sharded_replay
+  from oracle import sharded_port
+  torch = gpu.torch
+  rng = np.random.RandomState(num_shards * 100 + global_batch)
+  ours, ports = _shard_pairs(gpu, num_shards, rng)
+  exchanges = sharded_replay.PeerExchange.emulated(num_shards)
+  shards = [sharded_replay.ShardedPrioritizedReplay(
+      ours[g], rank=g, world_size=num_shards, exchange=exchanges[g])
+            for g in range(num_shards)]
+  for step in range(5):
+    for g in range(num_shards):  # priorities move, so the totals differ every step
+      ids = rng.randint(0, 300, size=50).astype(np.int32)
+      pr = (np.sqrt(np.abs(rng.randn(50)) + 1e-10) * (1 + g + step)).astype(np.float32)
+      ours[g].set_priority(ids, pr)
+      ports[g].set_priority(ids, pr)
+    bounds = np.linspace(0., 1., global_batch + 1)
+    queries = bounds[:-1] + (bounds[1:] - bounds[:-1]) * rng.rand(global_batch)
+    d_queries = torch.as_tensor(queries, device='cuda')
+    retries = [rng.rand(max(64, global_batch)) for _ in range(num_shards)]
+    want = sharded_port.sharded_sample(ports, queries, retries)
+    for g in range(num_shards):
+      exchanges[g].publish(ours[g])
+    served = []
+    for g in range(num_shards):
+      slots, idx, count = shards[g].sample_index_batch(
+          global_batch, queries01=d_queries,
+          retry_u01=torch.as_tensor(retries[g], device='cuda'))
+      n = int(count.cpu()[0])
+      w_slots, w_idx, _ = want[g]
+      assert n == len(w_slots), (step, g)
+      assert slots[:n].cpu().numpy().tolist() == w_slots
+      assert idx[:n].cpu().numpy().tolist() == [int(i) for i in w_idx]
+      served += w_slots
+      gpu.native.check(gpu.native.lib().b2r_check(ours[g]._h,
+                                                  gpu.native.current_stream()))
+    assert sorted(served) == list(range(global_batch))
+
+
+def test_peer_exchange_times_out_instead_of_hanging(gpu):
+  """A peer that never publishes must latch B2R_ERR_EXCHANGE after the timeout, and
+  later calls must not wait again."""
+  import time
+  from dopamine_b200.replay_memory import sharded_replay
+  torch = gpu.torch
+  rng = np.random.RandomState(1)
+  ours, _ = _shard_pairs(gpu, 2, rng)
+  exchanges = sharded_replay.PeerExchange.emulated(2)
+  lib = gpu.native.lib()
+  gpu.native.check(lib.b2r_exchange_set_timeout(exchanges[0]._h, 0.05))
+  shard = sharded_replay.ShardedPrioritizedReplay(ours[0], rank=0, world_size=2,
+                                                  exchange=exchanges[0])
+  t0 = time.perf_counter()
+  shard.sample_index_batch(32)   # rank 1 never published
+  torch.cuda.synchronize()
+  first = time.perf_counter() - t0
+  assert 0.04 < first < 2.0
+  t0 = time.perf_counter()
+  for _ in range(20):
+    shard.sample_index_batch(32)
+  torch.cuda.synchronize()
+  assert time.perf_counter() - t0 < 0.5  # latched: no further waits
+  status = lib.b2r_check(ours[0]._h, gpu.native.current_stream())
+  assert status == gpu.native.ERR_EXCHANGE
+  assert 'did not publish' in gpu.native.last_error()
+
+
+def test_sharded_fused_step_matches_oracles(gpu):
+  """b2r_train_step_sharded_device on 4 emulated ranks: each rank's rows (batch
+  columns at its indices, losses, write-back) against the oracles, the rows of all
+  ranks partitioning the global batch."""
+  import ctypes
+  from dopamine_b200.replay_memory import sharded_replay
+  torch, native = gpu.torch, gpu.native
+  lib = native.lib()
+  num_shards, cap, global_batch = 4, 50000, 256
+  shards = [_filled(gpu, cap, 32, seed=40 + g, hot=(g == 1)) for g in range(num_shards)]
+  exchanges = sharded_replay.PeerExchange.emulated(num_shards)
+  rng = np.random.RandomState(8)
+  support = gpu.ra.make_support(10., ATOMS)
+  outs = []
+  for g in range(num_shards):
+    mem = shards[g][0]
+    _, arrays, batch = mem._alloc_outputs(global_batch, True)
+    outs.append(dict(
+        arrays=arrays, batch=batch,
+        loss={k: torch.zeros(global_batch, dtype=torch.float32, device='cuda')
+              for k in ('loss', 'priorities', 'weights')},
+        slots=torch.zeros(global_batch, dtype=torch.int32, device='cuda'),
+        count=torch.zeros(1, dtype=torch.int32, device='cuda')))
+  for step in range(3):
+    online = rng.randn(global_batch, ACTIONS, ATOMS).astype(np.float32)
+    target = rng.randn(global_batch, ACTIONS, ATOMS).astype(np.float32)
+    d_online = torch.as_tensor(online, device='cuda')
+    d_target = torch.as_tensor(target, device='cuda')
+    for g in range(num_shards):
+      exchanges[g].publish(shards[g][0])
+    served = []
+    for g in range(num_shards):
+      mem, tree, cols = shards[g]
+      o = outs[g]
+      args = native.C51Args()
+      args.batch, args.num_actions, args.num_atoms = global_batch, ACTIONS, ATOMS
+      args.cumulative_gamma = float(np.float32(0.99 ** 3))
+      args.support = support.data_ptr()
+      args.online_logits, args.target_logits = d_online.data_ptr(), d_target.data_ptr()
+      args.loss = o['loss']['loss'].data_ptr()
+      args.priorities = o['loss']['priorities'].data_ptr()
+      args.weights = o['loss']['weights'].data_ptr()
+      native.check(lib.b2r_train_step_sharded_device(
+          mem._h, exchanges[g]._h, global_batch, 77, step, ctypes.byref(o['batch']),
+          ctypes.byref(args), o['slots'].data_ptr(), o['count'].data_ptr(),
+          native.current_stream()))
+      torch.cuda.synchronize()
+      n = int(o['count'].cpu()[0])
+      served += o['slots'][:n].cpu().numpy().tolist()
+      if n == 0:
+        continue
+      got = [a[:n] for a in o['arrays']]
+      loss = {k: v[:n] for k, v in o['loss'].items()}
+      _check_step(gpu, mem, tree, cols, cap, 3, got, loss, online[:n], target[:n])
+      native.check(lib.b2r_check(mem._h, native.current_stream()))
+    assert sorted(served) == list(range(global_batch)), step
+  for mem, tree, _ in shards:
+    for l, level in enumerate(mem.sum_tree.nodes):
+      assert np.array_equal(level.view(np.uint64), tree.level(l).view(np.uint64)), l
