@@ -108,6 +108,7 @@ class TrainerConfig(ctypes.Structure):
       ('cumulative_gamma', c_float),
       ('seed', c_uint64),
       ('pipeline_depth', c_int32),
+      ('use_graph', c_int32),
   ]
 
 

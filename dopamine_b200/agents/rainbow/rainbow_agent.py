@@ -303,7 +303,7 @@ class ReplayTrainer(object):
   """
 
   def __init__(self, memory, num_actions, num_atoms=51, vmax=10.,
-               batch_size=None, pipeline_depth=2, seed=0):
+               batch_size=None, pipeline_depth=2, seed=0, use_graph=True):
     self._memory = memory
     self._lib = _native.lib()
     cfg = _native.TrainerConfig()
@@ -314,6 +314,7 @@ class ReplayTrainer(object):
         memory._gamma, memory._update_horizon)))  # pylint: disable=protected-access
     cfg.seed = int(seed)
     cfg.pipeline_depth = int(pipeline_depth)
+    cfg.use_graph = int(bool(use_graph))
     self.batch_size, self.num_actions, self.num_atoms = (
         cfg.batch, num_actions, num_atoms)
     handle = ctypes.c_void_p()

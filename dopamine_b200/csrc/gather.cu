@@ -19,6 +19,9 @@
 // next_state read once.
 #include "gather.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace b2r {
 namespace {
 
@@ -131,6 +134,108 @@ __global__ void __launch_bounds__(128, 12) gather_stack4_u8_kernel(const __grid_
   B2R_MARK(5);
 }
 
+// ---- TMA variant of the fast path ------------------------------------------------
+// One CTA per transition.  An elected thread computes the trajectory length and
+// issues one bulk asynchronous copy (cp.async.bulk, the 1-D form of TMA) per unique
+// frame — 7 x 7 056 B for n = 3 — from the ring into shared memory, completing on
+// an mbarrier; all threads then read the staged frames 4 bytes per frame at a time
+// (conflict-free), interleave them into the [pixel][stack] order and write 16-byte
+// chunks that consecutive threads place consecutively (fully coalesced stores).
+// The ring is read in 7 KB bursts by the copy engine instead of by 16-byte loads
+// held in registers, so few threads keep the whole transition in flight.
+constexpr int kTmaThreads = 256;
+constexpr int kTmaMaxFrames = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                         uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <bool SCALARS>
+__global__ void __launch_bounds__(kTmaThreads)
+gather_stack4_u8_tma_kernel(const __grid_constant__ GatherArgs a) {
+  extern __shared__ __align__(128) uint8_t tma_smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ int s_length;
+  pdl_release();
+  pdl_acquire();
+  const int rows = a.count ? min(*a.count, a.batch) : a.batch;
+  if (SCALARS && (int)blockIdx.x >= a.batch) {  // appended scalar CTAs
+    const int b = ((int)blockIdx.x - a.batch) * blockDim.x + threadIdx.x;
+    if (b < rows) write_scalars(a.sc, b, a.indices[b]);
+    return;
+  }
+  const int b = blockIdx.x;
+  if (b >= rows) return;
+  const uint32_t frame = (uint32_t)a.obs_bytes;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int64_t i = a.indices[b];
+    bool ends;
+    const int length = trajectory_length(a.term_flag, i, a.horizon, a.capacity, &ends);
+    const int shared_frames = length < 4 ? length : 4;  // next-state frames beyond `state`
+    const int unique = 4 + shared_frames;
+    s_length = length;
+    mbar_expect_tx(&bar, (uint32_t)unique * frame);
+    for (int k = 0; k < unique; ++k) {
+      // slots 0..3: frames i-3..i; slots 4..: the frames of next_state not among them
+      int64_t slot = k < 4 ? i - 3 + k : i + length - 3 + (k - shared_frames);
+      if (slot < 0) slot += a.capacity;
+      if (slot >= a.capacity) slot -= a.capacity;
+      bulk_g2s(tma_smem + (size_t)k * frame, a.obs + slot * a.obs_bytes, frame, &bar);
+    }
+  }
+  mbar_wait(&bar, 0);
+  const int length = s_length;
+  const int next_base = length < 4 ? length : 4;  // slot of next_state's first frame
+  const int chunks = (int)(frame >> 2);           // 16-byte output chunks per stack
+  uint8_t *out_state = a.state ? a.state + (int64_t)b * frame * 4 : nullptr;
+  uint8_t *out_next = a.next_state ? a.next_state + (int64_t)b * frame * 4 : nullptr;
+  const uint32_t *f = reinterpret_cast<const uint32_t *>(tma_smem);
+  const uint32_t words = frame >> 2;  // 4-byte words per frame
+#pragma unroll 2
+  for (int o = threadIdx.x; o < chunks; o += kTmaThreads) {
+    if (out_state) {
+      const uint4 v = interleave4(f[o], f[words + o], f[2 * words + o], f[3 * words + o]);
+      reinterpret_cast<uint4 *>(out_state)[o] = v;
+    }
+    if (out_next) {
+      const uint32_t *g = f + (size_t)next_base * words;
+      const uint4 v = interleave4(g[o], g[words + o], g[2 * words + o], g[3 * words + o]);
+      reinterpret_cast<uint4 *>(out_next)[o] = v;
+    }
+  }
+}
+
 // General path: any stack size / element size. thread = one observation element.
 __global__ void __launch_bounds__(256) gather_generic_kernel(const __grid_constant__ GatherArgs a) {
   pdl_release();
@@ -175,6 +280,17 @@ __global__ void get_priority_kernel(const double *__restrict__ leaves, int64_t n
 }
 
 }  // namespace
+
+// 0: register path (LDG.128 -> PRMT -> STG.128), 1: TMA-staged path.  Chosen once
+// from B2R_GATHER (default set from measurements).
+int gather_variant() {
+  static const int v = [] {
+    const char *e = std::getenv("B2R_GATHER");
+    if (e != nullptr) return std::strcmp(e, "tma") == 0 ? 1 : 0;
+    return 0;
+  }();
+  return v;
+}
 
 void fill_scalar_args(const b2r_buffer *b, const b2r_batch *out, ScalarArgs *sc) {
   sc->capacity = b->cfg.capacity;
@@ -235,7 +351,27 @@ int launch_gather(b2r_buffer *b, int32_t batch, const int32_t *indices_dev,
   fill_scalar_args(b, out, &a.sc);
   if (frames_only && !a.state && !a.next_state) return B2R_OK;
   const bool fast = a.stack == 4 && a.obs_itemsize == 1 && (a.obs_bytes & 15) == 0;
-  if (fast) {
+  const size_t tma_bytes = (size_t)kTmaMaxFrames * (size_t)a.obs_bytes;
+  if (fast && gather_variant() == 1 && tma_bytes <= 200 * 1024) {
+    static bool ready = false;
+    if (!ready) {
+      B2R_CUDA(cudaFuncSetAttribute(gather_stack4_u8_tma_kernel<true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    200 * 1024));
+      B2R_CUDA(cudaFuncSetAttribute(gather_stack4_u8_tma_kernel<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    200 * 1024));
+      ready = true;
+    }
+    a.scalar_rows = frames_only ? 0 : (batch + kTmaThreads - 1) / kTmaThreads;
+    dim3 grid(batch + a.scalar_rows);
+    if (frames_only)
+      B2R_CUDA(launch_prio(gather_stack4_u8_tma_kernel<false>, grid, dim3(kTmaThreads),
+                           tma_bytes, stream, 0, a));
+    else
+      B2R_CUDA(launch(gather_stack4_u8_tma_kernel<true>, grid, dim3(kTmaThreads),
+                      tma_bytes, stream, a));
+  } else if (fast) {
     const int chunks = (int)(a.obs_bytes >> 4);
     const int nx = (chunks + 127) / 128;
     // + rows of scalar CTAs (one thread per transition)

@@ -31,6 +31,8 @@ struct AddParams {
   int64_t col_qoff[kMaxColumns];
   uint8_t *term_flag;       // nullptr when it aliases the 1-byte terminal column
   int term_itemsize;
+  const uint64_t *ctx_src;  // ValidCtx image in the staged header
+  uint64_t *ctx_dst;        // the buffer's device ValidCtx
 };
 
 // grid = (x: 16-byte chunks of the observation, y: entries).
@@ -54,6 +56,11 @@ __global__ void __launch_bounds__(256) add_rows_kernel(AddParams p) {
   } else {
     for (int64_t c = tid; c < obs_bytes; c += nthreads) dst[c] = row ? row[c] : 0;
   }
+
+  // the validity context that goes with these rows
+  if (blockIdx.x == 0 && e == 0)
+    for (int w = threadIdx.x; w < (int)(sizeof(ValidCtx) / 8); w += blockDim.x)
+      p.ctx_dst[w] = p.ctx_src[w];
 
   // scalar columns: a handful of bytes, first block of the entry only.
   if (blockIdx.x == 0) {
@@ -171,6 +178,9 @@ int flush_queue(b2r_buffer *b, cudaStream_t stream) {
   if (b->q_entries == 0) return B2R_OK;
   Staging *s = &b->staging[b->active];
   const size_t bytes = (size_t)b->header_bytes + (size_t)b->q_rows * b->row_stride;
+  // the validity context as of these adds travels in the header
+  const size_t ctx_off = (size_t)b->header_bytes - sizeof(ValidCtx);
+  fill_valid_ctx(b, reinterpret_cast<ValidCtx *>(s->host + ctx_off));
   B2R_CUDA(cudaMemcpyAsync(s->dev, s->host, bytes, cudaMemcpyHostToDevice, stream));
   Header hd = header_of(s->dev, b->queue_cap);
   if (b->tree != nullptr) {
@@ -193,6 +203,9 @@ int flush_queue(b2r_buffer *b, cudaStream_t stream) {
   }
   p.term_flag = b->term_flag_owned ? b->term_flag : nullptr;
   p.term_itemsize = b->cfg.terminal_itemsize;
+  p.ctx_src = reinterpret_cast<const uint64_t *>(s->dev + ctx_off);
+  p.ctx_dst = reinterpret_cast<uint64_t *>(b->ctx_dev);
+  b->ctx_dirty = false;
   const int64_t work = (b->cfg.obs_bytes & 15) == 0 ? b->cfg.obs_bytes >> 4
                                                     : b->cfg.obs_bytes;
   int gx = (int)((work + 255) / 256);
@@ -217,6 +230,17 @@ void fill_valid_ctx(const b2r_buffer *b, ValidCtx *ctx) {
   ctx->n_invalid = (int)b->invalid_range.size();
   for (int i = 0; i < ctx->n_invalid; ++i) ctx->invalid[i] = b->invalid_range[i];
   ctx->term_flag = b->term_flag;
+}
+
+int ensure_ctx(b2r_buffer *b, cudaStream_t stream) {
+  if (!b->ctx_dirty) return B2R_OK;
+  ValidCtx image;
+  fill_valid_ctx(b, &image);
+  // pageable source: the runtime stages it before returning, `image` may go away
+  B2R_CUDA(cudaMemcpyAsync(b->ctx_dev, &image, sizeof(image), cudaMemcpyHostToDevice,
+                           stream));
+  b->ctx_dirty = false;
+  return B2R_OK;
 }
 
 int ensure_inv_slots(b2r_buffer *b, int64_t n) {
@@ -292,7 +316,8 @@ int b2r_create(const b2r_config *cfg, b2r_buffer **out) {
   // One flush never holds two rows for the same slot (the row kernel writes
   // entries concurrently), so the queue is no longer than the ring.
   if (b->queue_cap > cfg->capacity) b->queue_cap = (int)cfg->capacity;
-  b->header_bytes = b2r::align_up((int64_t)b->queue_cap * 21 + 64, 256);
+  b->header_bytes = b2r::align_up(
+      (int64_t)b->queue_cap * 21 + 64 + 16 + (int64_t)sizeof(b2r::ValidCtx), 256);
 
   for (int c = 0; c < b->num_columns; ++c) {
     const size_t bytes = (size_t)cfg->capacity * (size_t)b->col[c].row_bytes;
@@ -342,6 +367,8 @@ int b2r_create(const b2r_config *cfg, b2r_buffer **out) {
   B2R_CUDA(cudaMemset(b->shard_counter, 0, 8));
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->draw_counter), 8));
   B2R_CUDA(cudaMemset(b->draw_counter, 0, 8));
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->ctx_dev), sizeof(b2r::ValidCtx)));
+  B2R_CUDA(cudaMemset(b->ctx_dev, 0, sizeof(b2r::ValidCtx)));
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->min_prob), 4));
   B2R_CUDA(cudaMemset(b->min_prob, 0, 4));
   B2R_CUDA(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
@@ -370,6 +397,7 @@ int b2r_destroy(b2r_buffer *b) {
   cudaFree(b->shard_counter);
   cudaFree(b->ticket);
   cudaFree(b->min_prob);
+  cudaFree(b->ctx_dev);
   if (b->side) cudaStreamDestroy(b->side);
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
@@ -444,6 +472,7 @@ int b2r_set_state(b2r_buffer *b, int64_t add_count, const int64_t *invalid_range
     return fail(B2R_ERR_INVALID_ARGUMENT, "bad state");
   b->add_count = add_count;
   b->invalid_range.assign(invalid_range, invalid_range + n);
+  b->ctx_dirty = true;
   return B2R_OK;
 }
 

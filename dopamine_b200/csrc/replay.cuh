@@ -127,6 +127,12 @@ struct b2r_buffer {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float *min_prob = nullptr;    // device: min sampling probability of the last batch
+  // Device copy of the validity context (add_count, cursor, invalid_range): the
+  // prioritized sampler reads it from here, so a captured CUDA graph stays valid
+  // while adds move the cursor.  Refreshed by every flush (the image rides in the
+  // staging header) and lazily after b2r_set_state.
+  b2r::ValidCtx *ctx_dev = nullptr;
+  bool ctx_dirty = true;
   b2r::Bounce bounce;           // HOST-array calls
   uint8_t *out_scratch = nullptr;  // device outputs of b2r_gather (HOST variant)
   size_t out_scratch_cap = 0;
@@ -159,6 +165,7 @@ int launch_sample_sharded(b2r_buffer *buf, int32_t global_batch, int32_t num_sha
                           const b2r_batch *scalars = nullptr,
                           float *min_prob_out = nullptr);
 void fill_valid_ctx(const b2r_buffer *buf, ValidCtx *ctx);
+int ensure_ctx(b2r_buffer *buf, cudaStream_t stream);
 int ensure_inv_slots(b2r_buffer *buf, int64_t n);
 int launch_gather(b2r_buffer *buf, int32_t batch, const int32_t *indices_dev,
                   const b2r_batch *out, cudaStream_t stream,

@@ -21,7 +21,7 @@ constexpr int kMaxTiles = 2048;  // batch / tile size (>= 32 strata per tile)
 struct PerSampleArgs {
   const double *heap;
   int depth;
-  ValidCtx valid;
+  const ValidCtx *valid_dev;  // the buffer's device validity context
   int batch;          // strata (global batch when sharded)
   int max_attempts;
   // uniforms: host-provided (reference RNG stream) or Philox (throughput mode)
@@ -159,10 +159,18 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
   __shared__ int s_draws_used, s_last_idx, s_last_valid, s_is_last;
   __shared__ int tile_start[kMaxTiles + 1];
 
+  __shared__ ValidCtx s_valid;
+  const ValidCtx &valid_ctx = s_valid;
+
   B2R_MARK(0);
   pdl_release();
   pdl_acquire();
   B2R_MARK(1);
+  // validity context: from HBM (it moves with every add), visible after the
+  // barrier inside stage_top_levels
+  for (int w = threadIdx.x; w < (int)(sizeof(ValidCtx) / 8); w += blockDim.x)
+    reinterpret_cast<uint64_t *>(&s_valid)[w] =
+        reinterpret_cast<const uint64_t *>(a.valid_dev)[w];
   const uint64_t draws_before = a.counter ? *a.counter : 0ull;
   const uint64_t draw_offset = a.offset + draws_before;
   // Peer exchange (one CTA): the totals are on the wire while the top levels are
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
         B2R_MARK(4);
         // the row's scalar inputs travel with the validity flags: one round trip
         if (fast_scalars) load_scalars(a.sc, idx, &row);
-        valid = is_valid_transition(a.valid, idx);
+        valid = is_valid_transition(valid_ctx, idx);
         B2R_MARK(5);
       }
     }
@@ -319,7 +327,7 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
       idx = tree_descend_staged<K>(a.heap, top, top_depth, a.depth,
                                    __dmul_rn(u, local_total), a.zero);
       if (fast_scalars) load_scalars(a.sc, idx, &row);
-      valid = is_valid_transition(a.valid, idx);
+      valid = is_valid_transition(valid_ctx, idx);
     }
     int tile_valid;
     const int ord = found + block_scan_flag(active && valid, warp_counts, &tile_valid);
@@ -359,7 +367,7 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
           // the slot burnt the rest of the budget and keeps its last (invalid)
           // draw; only a FURTHER invalid slot raises.
           a.out_idx[next_slot] = s_last_idx;
-          if (a.with_scalars && s_last_idx >= 0 && s_last_idx < a.valid.capacity)
+          if (a.with_scalars && s_last_idx >= 0 && s_last_idx < valid_ctx.capacity)
             fix_min = fminf(fix_min, write_scalars(a.sc, next_slot, s_last_idx));
           if (num_invalid > next + 1) {
             status = B2R_ERR_SAMPLE_ATTEMPTS;
@@ -516,7 +524,8 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   PerSampleArgs a;
   a.heap = b->tree->heap;
   a.depth = b->tree->depth;
-  fill_valid_ctx(b, &a.valid);
+  B2R_TRY(ensure_ctx(b, stream));
+  a.valid_dev = b->ctx_dev;
   a.batch = batch;
   a.max_attempts = philox ? b->cfg.max_sample_attempts : n_retry;
   a.use_philox = philox ? 1 : 0;
@@ -581,7 +590,8 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
   PerSampleArgs a;
   a.heap = b->tree->heap;
   a.depth = b->tree->depth;
-  fill_valid_ctx(b, &a.valid);
+  B2R_TRY(ensure_ctx(b, s));
+  a.valid_dev = b->ctx_dev;
   a.batch = global_batch;
   a.max_attempts = n_retry;
   a.use_philox = (query01 == nullptr) ? 1 : 0;

@@ -101,6 +101,9 @@ struct b2r_trainer {
   cudaStream_t copy = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr};
   cudaEvent_t ev_loss[2] = {nullptr, nullptr};
+  // graph mode: the step's kernels captured once per logits set
+  cudaStream_t cap = nullptr;
+  cudaGraphExec_t exec[2] = {nullptr, nullptr};
   // results
   int ring = 1;
   float *ring_host = nullptr;  // pinned [ring][batch]
@@ -109,6 +112,32 @@ struct b2r_trainer {
 };
 
 namespace {
+
+// Captures one step (sampler, forked frame copies, loss, write-back) on the
+// trainer's private stream; the graph is then launched into the caller's stream.
+int capture_step(b2r_trainer *t, int set) {
+  b2r_c51_args c51 = t->c51;
+  c51.online_logits = t->logits[set][0];
+  c51.target_logits = t->logits[set][1];
+  cudaGraph_t graph = nullptr;
+  B2R_CUDA(cudaStreamBeginCapture(t->cap, cudaStreamCaptureModeThreadLocal));
+  const int status = b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch,
+                                     &c51, t->cap, nullptr, nullptr);
+  const cudaError_t end = cudaStreamEndCapture(t->cap, &graph);
+  if (status != B2R_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return status;
+  }
+  if (end != cudaSuccess)
+    return fail(B2R_ERR_CUDA, "stream capture of the step failed: %s",
+                cudaGetErrorString(end));
+  const cudaError_t inst = cudaGraphInstantiate(&t->exec[set], graph, 0);
+  cudaGraphDestroy(graph);
+  if (inst != cudaSuccess)
+    return fail(B2R_ERR_CUDA, "graph instantiation failed: %s",
+                cudaGetErrorString(inst));
+  return B2R_OK;
+}
 
 int collect(b2r_trainer *t, int64_t step, float *loss_out, int64_t *loss_step) {
   if (step < 0) {
@@ -212,6 +241,7 @@ int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
   t->c51.weights = reinterpret_cast<float *>(t->scalars + o_w);
 
   B2R_CUDA(cudaStreamCreateWithFlags(&t->copy, cudaStreamNonBlocking));
+  B2R_CUDA(cudaStreamCreateWithFlags(&t->cap, cudaStreamNonBlocking));
   for (int k = 0; k < 2; ++k) {
     B2R_CUDA(cudaEventCreateWithFlags(&t->ev_in[k], cudaEventDisableTiming));
     B2R_CUDA(cudaEventCreateWithFlags(&t->ev_loss[k], cudaEventDisableTiming));
@@ -235,6 +265,9 @@ int b2r_trainer_destroy(b2r_trainer *t) {
   cudaFree(t->frames);
   cudaFree(t->scalars);
   if (t->copy) cudaStreamDestroy(t->copy);
+  if (t->cap) cudaStreamDestroy(t->cap);
+  for (int k = 0; k < 2; ++k)
+    if (t->exec[k]) cudaGraphExecDestroy(t->exec[k]);
   for (int k = 0; k < 2; ++k) {
     if (t->ev_in[k]) cudaEventDestroy(t->ev_in[k]);
     if (t->ev_loss[k]) cudaEventDestroy(t->ev_loss[k]);
@@ -263,11 +296,23 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   B2R_CUDA(cudaMemcpyAsync(t->logits[set][1], target_logits, logit_bytes,
                            cudaMemcpyHostToDevice, t->copy));
   B2R_CUDA(cudaEventRecord(t->ev_in[set], t->copy));
-  b2r_c51_args c51 = t->c51;
-  c51.online_logits = t->logits[set][0];
-  c51.target_logits = t->logits[set][1];
-  B2R_TRY(b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch, &c51, s,
-                          t->ev_in[set], t->ev_loss[set]));
+  if (t->cfg.use_graph && n >= 2) {
+    // Everything host-dependent (staged adds, validity context) goes first, eagerly;
+    // the replayed graph reads it from HBM.
+    B2R_TRY(b2r::flush_queue(t->buf, s));
+    B2R_TRY(b2r::ensure_ctx(t->buf, s));
+    if (!t->exec[set]) B2R_TRY(capture_step(t, set));
+    B2R_CUDA(cudaStreamWaitEvent(s, t->ev_in[set], 0));
+    B2R_CUDA(cudaGraphLaunch(t->exec[set], s));
+    b2r::g_launches.fetch_add(4, std::memory_order_relaxed);
+    B2R_CUDA(cudaEventRecord(t->ev_loss[set], s));
+  } else {
+    b2r_c51_args c51 = t->c51;
+    c51.online_logits = t->logits[set][0];
+    c51.target_logits = t->logits[set][1];
+    B2R_TRY(b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch, &c51, s,
+                            t->ev_in[set], t->ev_loss[set]));
+  }
   // result: per-row losses into this step's pinned slot (copy stream, after the loss)
   const int slot = (int)(n % t->ring);
   B2R_CUDA(cudaStreamWaitEvent(t->copy, t->ev_loss[set], 0));

@@ -423,6 +423,8 @@ typedef struct {
   uint64_t seed;           /* Philox key of the sampler                            */
   int32_t pipeline_depth;  /* 0: each call returns its own losses (synchronous);
                               d > 0: the losses of the step queued d calls earlier */
+  int32_t use_graph;       /* != 0: after two eager steps the kernels of a step are
+                              replayed as one captured CUDA graph per call          */
 } b2r_trainer_config;
 
 int b2r_trainer_create(b2r_buffer *buf, const b2r_trainer_config *config,

@@ -428,3 +428,24 @@ def test_sharded_fused_step_matches_oracles(gpu):
   for mem, tree, _ in shards:
     for l, level in enumerate(mem.sum_tree.nodes):
       assert np.array_equal(level.view(np.uint64), tree.level(l).view(np.uint64)), l
+
+
+def test_tma_gather_variant_passes_the_gather_parity_suite():
+  """B2R_GATHER=tma selects the kernel that stages frames through cp.async.bulk into
+  shared memory; the variant is fixed per process, so the gather parity tests are
+  re-run in a child process with it (bit-exact batches at 100k / 1M, wrap-around,
+  terminals inside trajectories, fused step)."""
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  env = dict(os.environ, B2R_GATHER='tma')
+  out = subprocess.run(
+      [sys.executable, '-m', 'pytest', '-q', '-x', '-m', 'gpu',
+       'tests/test_gpu_parity.py', 'tests/test_gpu_step.py', '-k',
+       'gather_full_size or prioritized_full_size or uniform_reference_fixture or '
+       'prioritized_reference_fixture or fused_step_matches_oracles or '
+       'sharded_fused_step'],
+      cwd=root, env=env, capture_output=True, text=True, timeout=900)
+  assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+  assert ' passed' in out.stdout
