@@ -303,7 +303,7 @@ class ReplayTrainer(object):
   """
 
   def __init__(self, memory, num_actions, num_atoms=51, vmax=10.,
-               batch_size=None, pipeline_depth=2, seed=0, use_graph=True):
+               batch_size=None, pipeline_depth=2, seed=0, use_graph=False):
     self._memory = memory
     self._lib = _native.lib()
     cfg = _native.TrainerConfig()

@@ -174,14 +174,26 @@ int enqueue(b2r_buffer *b, bool real, const void *const *cols, double priority,
 
 }  // namespace
 
-int flush_queue(b2r_buffer *b, cudaStream_t stream) {
+int flush_queue(b2r_buffer *b, cudaStream_t stream, bool split) {
   if (b->q_entries == 0) return B2R_OK;
   Staging *s = &b->staging[b->active];
   const size_t bytes = (size_t)b->header_bytes + (size_t)b->q_rows * b->row_stride;
   // the validity context as of these adds travels in the header
   const size_t ctx_off = (size_t)b->header_bytes - sizeof(ValidCtx);
   fill_valid_ctx(b, reinterpret_cast<ValidCtx *>(s->host + ctx_off));
-  B2R_CUDA(cudaMemcpyAsync(s->dev, s->host, bytes, cudaMemcpyHostToDevice, stream));
+  // split: rows (H2D + ring writes) on the side stream, ordered after everything
+  // already queued on `stream` (earlier readers of the ring), beside the tree update.
+  cudaStream_t data = stream;
+  if (split) {
+    data = b->side;
+    B2R_CUDA(cudaEventRecord(b->ev_pre, stream));
+    B2R_CUDA(cudaStreamWaitEvent(data, b->ev_pre, 0));
+  }
+  B2R_CUDA(cudaMemcpyAsync(s->dev, s->host, bytes, cudaMemcpyHostToDevice, data));
+  if (split) {
+    B2R_CUDA(cudaEventRecord(b->ev_h2d, data));
+    B2R_CUDA(cudaStreamWaitEvent(stream, b->ev_h2d, 0));
+  }
   Header hd = header_of(s->dev, b->queue_cap);
   if (b->tree != nullptr) {
     // prioritized_replay_buffer.py:139-140: sum_tree.set(cursor, priority) per row,
@@ -211,8 +223,12 @@ int flush_queue(b2r_buffer *b, cudaStream_t stream) {
   int gx = (int)((work + 255) / 256);
   if (gx < 1) gx = 1;
   if (gx > 64) gx = 64;
-  add_rows_kernel<<<dim3(gx, b->q_entries), 256, 0, stream>>>(p);
+  add_rows_kernel<<<dim3(gx, b->q_entries), 256, 0, data>>>(p);
   B2R_LAUNCHED();
+  if (split) {
+    B2R_CUDA(cudaEventRecord(b->ev_rows, data));
+    B2R_CUDA(cudaStreamWaitEvent(stream, b->ev_rows, 0));
+  }
   B2R_CUDA(cudaEventRecord(s->done, stream));
   s->in_flight = true;
   b->active ^= 1;
@@ -374,6 +390,9 @@ int b2r_create(const b2r_config *cfg, b2r_buffer **out) {
   B2R_CUDA(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
   B2R_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
   B2R_CUDA(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+  B2R_CUDA(cudaEventCreateWithFlags(&b->ev_pre, cudaEventDisableTiming));
+  B2R_CUDA(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming));
+  B2R_CUDA(cudaEventCreateWithFlags(&b->ev_rows, cudaEventDisableTiming));
   *out = b;
   return B2R_OK;
 }
@@ -401,6 +420,9 @@ int b2r_destroy(b2r_buffer *b) {
   if (b->side) cudaStreamDestroy(b->side);
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
+  if (b->ev_pre) cudaEventDestroy(b->ev_pre);
+  if (b->ev_h2d) cudaEventDestroy(b->ev_h2d);
+  if (b->ev_rows) cudaEventDestroy(b->ev_rows);
   if (b->out_scratch) cudaFree(b->out_scratch);
   b->bounce.release();
   delete b;

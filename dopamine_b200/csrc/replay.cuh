@@ -126,6 +126,7 @@ struct b2r_buffer {
   // fused step: the frame copies run on `side`, forked/joined with these events
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_pre = nullptr, ev_h2d = nullptr, ev_rows = nullptr;  // split flush
   float *min_prob = nullptr;    // device: min sampling probability of the last batch
   // Device copy of the validity context (add_count, cursor, invalid_range): the
   // prioritized sampler reads it from here, so a captured CUDA graph stays valid
@@ -149,7 +150,10 @@ struct b2r_exchange {
 };
 
 namespace b2r {
-int flush_queue(b2r_buffer *buf, cudaStream_t stream);
+// Applies the staged adds.  split: the staged rows are copied and written to the
+// ring on the buffer's side stream while the priorities go into the tree on
+// `stream`; `stream` then waits for the rows, so callers see no difference.
+int flush_queue(b2r_buffer *buf, cudaStream_t stream, bool split = false);
 void fill_exchange_args(const b2r_exchange *x, ExchangeArgs *out);
 int launch_exchange_publish(const b2r_exchange *x, const b2r_buffer *buf,
                             cudaStream_t stream);

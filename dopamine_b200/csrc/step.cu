@@ -48,7 +48,10 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   if (shard && (!shard->exchange || !shard->out_count))
     return fail(B2R_ERR_INVALID_ARGUMENT, "exchange and out_count are required");
   const int32_t *count = shard ? shard->out_count : nullptr;
-  B2R_TRY(flush_queue(b, s));
+  // Staged adds: at the agent's batch of 32 a host loop is bound by the number of
+  // driver calls, so everything goes on `s`; at larger batches the device chain is
+  // the bound and the rows are written on the side stream beside the tree update.
+  B2R_TRY(flush_queue(b, s, batch > 64));
   if (shard)
     B2R_TRY(launch_sample_sharded(
         b, batch, shard->exchange->world, shard->exchange->rank, nullptr,
@@ -299,7 +302,7 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   if (t->cfg.use_graph && n >= 2) {
     // Everything host-dependent (staged adds, validity context) goes first, eagerly;
     // the replayed graph reads it from HBM.
-    B2R_TRY(b2r::flush_queue(t->buf, s));
+    B2R_TRY(b2r::flush_queue(t->buf, s, t->cfg.batch > 64));
     B2R_TRY(b2r::ensure_ctx(t->buf, s));
     if (!t->exec[set]) B2R_TRY(capture_step(t, set));
     B2R_CUDA(cudaStreamWaitEvent(s, t->ev_in[set], 0));

@@ -19,6 +19,7 @@
 #include <cooperative_groups.h>
 #include <cub/block/block_radix_sort.cuh>
 
+#include <cstdlib>
 #include <new>
 
 namespace cg = cooperative_groups;
@@ -45,6 +46,51 @@ struct UpdateArgs {
   int64_t *status;
   const int32_t *n_dev;  // nullable: device-side element count of the whole batch
 };
+
+// Add-path batches may ask for "whatever max_recorded_priority is when this entry
+// is applied" (mode[k] != 0, rainbow_agent.py:330-334).  Sequentially that is
+//   v = mode ? running : value;  stop if v < 0 or the index is out of range;
+//   running = max(running, v)
+// Entries that take the running maximum never raise it, so v_k = mode_k ?
+// max(max_rec, explicit values before k) : value_k: an exclusive prefix maximum,
+// evaluated by warp 0 with shuffles, 32 entries per round (one round trip of loads
+// instead of a chain of dependent ones).
+template <typename I, typename V>
+__device__ __forceinline__ void stage_mode_values(const UpdateArgs<I, V> &a, int n,
+                                                  double *vals, int *s_stop,
+                                                  int *s_stop_code) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  double running = *a.max_rec;
+  for (int base = 0; base < n; base += 32) {
+    const int k = base + lane;
+    const bool in = k < n;
+    const bool use_max = in && a.mode[k] != 0;
+    const double v = (in && !use_max) ? (double)a.values[k] : 0.0;
+    const int64_t idx = in ? (int64_t)a.indices[k] : 0;
+    double x = (in && !use_max) ? v : -INFINITY;  // inclusive prefix max of explicit values
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x = fmax(x, y);
+    }
+    double before = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) before = -INFINITY;
+    const double vk = use_max ? fmax(running, before) : v;
+    const bool bad = in && (vk < 0.0 || idx < 0 || idx >= a.leaves);
+    const unsigned bad_mask = __ballot_sync(0xffffffffu, bad);
+    if (in) vals[k] = vk;
+    if (bad_mask) {
+      const int first = __ffs(bad_mask) - 1;
+      if (lane == first) {
+        *s_stop = base + first;
+        *s_stop_code = vk < 0.0 ? B2R_ERR_NEGATIVE_PRIORITY : B2R_ERR_INDEX_RANGE;
+      }
+      break;
+    }
+    running = fmax(running, __shfl_sync(0xffffffffu, x, 31));
+  }
+}
 
 // ONE cooperative launch, grid = depth + 1 CTAs (CTA l owns level l, CTA `depth`
 // the leaves).  Every CTA groups the chunk's elements by their node on its level
@@ -98,17 +144,7 @@ __global__ void __launch_bounds__(kBigThreads) tree_update_kernel(UpdateArgs<I, 
   if (a.mode != nullptr) {
     // add-path batches may ask for "current max_recorded_priority": needs the
     // running maximum in order.  These batches are tiny; one thread walks them.
-    if (threadIdx.x == 0) {
-      double running = *a.max_rec;
-      for (int k = 0; k < n; ++k) {
-        double v = a.mode[k] ? running : (double)a.values[k];
-        const int64_t idx = (int64_t)a.indices[k];
-        if (v < 0.0) { s_stop = k; s_stop_code = B2R_ERR_NEGATIVE_PRIORITY; break; }
-        if (idx < 0 || idx >= a.leaves) { s_stop = k; s_stop_code = B2R_ERR_INDEX_RANGE; break; }
-        if (v > running) running = v;
-        vals[k] = v;
-      }
-    }
+    stage_mode_values(a, n, vals, &s_stop, &s_stop_code);
   } else {
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
       const double v = (double)a.values[k];
@@ -273,17 +309,7 @@ __global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V
   if (latched != 0) return;  // an earlier chunk failed: the sequence stopped there
 
   if (a.mode != nullptr) {
-    if (threadIdx.x == 0) {
-      double running = *a.max_rec;
-      for (int k = 0; k < n; ++k) {
-        double v = a.mode[k] ? running : (double)a.values[k];
-        const int64_t idx = (int64_t)a.indices[k];
-        if (v < 0.0) { s_stop = k; s_stop_code = B2R_ERR_NEGATIVE_PRIORITY; break; }
-        if (idx < 0 || idx >= a.leaves) { s_stop = k; s_stop_code = B2R_ERR_INDEX_RANGE; break; }
-        if (v > running) running = v;
-        vals[k] = v;
-      }
-    }
+    stage_mode_values(a, n, vals, &s_stop, &s_stop_code);
   } else {
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
       const double v = (double)a.values[k];
@@ -421,7 +447,15 @@ int allow_big_smem(K kernel) {
 template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
                const uint8_t *mode, cudaStream_t stream, const int32_t *n_dev) {
-  if (n <= kSmallBatch) {
+  // The one-CTA kernel sorts per warp (cost ~ n log^2 n): it wins for the agent's
+  // batch of 32 and loses to the radix-sorted cooperative kernel beyond ~64 entries
+  // (measured, profiles/r1/README.md).  B2R_TREE_SMALL_MAX overrides the threshold.
+  static const int small_max = [] {
+    const char *e = std::getenv("B2R_TREE_SMALL_MAX");
+    int v = e ? std::atoi(e) : 64;
+    return v < 0 ? 0 : (v > kSmallBatch ? kSmallBatch : v);
+  }();
+  if (n <= small_max) {
     // latency path: one CTA, one warp per level
     static bool small_ready = false;
     const int padded = padded_size((int)n);

@@ -631,7 +631,7 @@ class OutOfGraphReplayBuffer(object):
           if isinstance(value, np.ndarray):
             np.save(outfile, value, allow_pickle=False)
           else:
-            pickle.dump(value, outfile)
+            self._pickle_attribute(attr, value, outfile)
       stale_iteration_number = iteration_number - CHECKPOINT_DURATION
       if stale_iteration_number >= 0:
         stale_filename = self._generate_filename(checkpoint_dir, attr,
@@ -659,7 +659,7 @@ class OutOfGraphReplayBuffer(object):
               current, np.ndarray):
             loaded[attr] = np.load(infile, allow_pickle=False)
           else:
-            loaded[attr] = pickle.load(infile)
+            loaded[attr] = self._unpickle_attribute(attr, infile)
     for attr, value in loaded.items():
       if attr.startswith(STORE_FILENAME_PREFIX):
         self._store[attr[len(STORE_FILENAME_PREFIX):]] = value
@@ -672,6 +672,14 @@ class OutOfGraphReplayBuffer(object):
 
   def _restore_attribute(self, attr, value):
     setattr(self, attr, value)
+
+  def _pickle_attribute(self, attr, value, outfile):
+    del attr
+    pickle.dump(value, outfile)
+
+  def _unpickle_attribute(self, attr, infile):
+    del attr
+    return pickle.load(infile)
 
 
 class WrappedReplayBuffer(object):

@@ -14,6 +14,7 @@ rng='reference' the uniforms are drawn from Python's `random` exactly as the
 reference does, so identical seeds give identical indices.
 """
 import ctypes
+import pickle
 import random
 
 import numpy as np
@@ -34,6 +35,45 @@ class _MaxRecordedPriority(object):
 
 
 MAX_RECORDED_PRIORITY = _MaxRecordedPriority()
+
+
+# -- checkpoint compatibility with the reference --------------------------------
+# The reference pickles `memory.sum_tree`, a dopamine.replay_memory.sum_tree.SumTree
+# instance whose state is {'nodes': [level arrays], 'max_recorded_priority': x}
+# (sum_tree.py:79-89, written by circular_replay_buffer.py:641).  The tree lives in
+# HBM here, so the same pickle is produced / consumed from its level arrays without
+# the reference being importable.
+_REFERENCE_TREE_CLASS = ('dopamine.replay_memory.sum_tree', 'SumTree')
+
+
+class SumTreeState(object):
+  """What a pickled reference SumTree unpickles to when the reference package is
+  absent: a plain holder of `nodes` and `max_recorded_priority`."""
+
+
+class _TreeUnpickler(pickle.Unpickler):
+
+  def find_class(self, module, name):
+    if (module, name) == _REFERENCE_TREE_CLASS or (
+        module.endswith('replay_memory.sum_tree') and name == 'SumTree'):
+      return SumTreeState
+    return super(_TreeUnpickler, self).find_class(module, name)
+
+
+def dump_reference_sum_tree(nodes, max_recorded_priority, outfile):
+  """Writes the pickle the reference's save() writes for its SumTree: protocol-2
+  `SumTree.__new__()` + `__dict__.update(state)`; loads back into the reference
+  class when it is importable, into SumTreeState otherwise."""
+  state = {'nodes': [np.asarray(level, dtype=np.float64) for level in nodes],
+           'max_recorded_priority': max_recorded_priority}
+  body = pickle.dumps(state, protocol=2)
+  assert body[:2] == b'\x80\x02' and body[-1:] == b'.'
+  module, name = _REFERENCE_TREE_CLASS
+  outfile.write(b'\x80\x02' +                       # PROTO 2
+                b'c' + module.encode() + b'\n' + name.encode() + b'\n' +  # GLOBAL
+                b')\x81' +                           # EMPTY_TUPLE, NEWOBJ
+                body[2:-1] +                         # the state dict
+                b'b.')                               # BUILD, STOP
 
 
 def _is_cuda_tensor(x):
@@ -244,17 +284,27 @@ class OutOfGraphPrioritizedReplayBuffer(
     return out
 
   # -- checkpointing: the tree is saved as its level arrays ---------------------------
-  def _checkpoint_value(self, attr):
+  def _pickle_attribute(self, attr, value, outfile):
+    if attr == 'sum_tree':  # byte-compatible with the reference's pickled SumTree
+      dump_reference_sum_tree(value.nodes, value.max_recorded_priority, outfile)
+      return
+    super(OutOfGraphPrioritizedReplayBuffer, self)._pickle_attribute(
+        attr, value, outfile)
+
+  def _unpickle_attribute(self, attr, infile):
     if attr == 'sum_tree':
-      return {'nodes': self.sum_tree.nodes,
-              'max_recorded_priority': self.sum_tree.max_recorded_priority}
-    return super(OutOfGraphPrioritizedReplayBuffer, self)._checkpoint_value(attr)
+      return _TreeUnpickler(infile).load()
+    return super(OutOfGraphPrioritizedReplayBuffer, self)._unpickle_attribute(
+        attr, infile)
 
   def _restore_attribute(self, attr, value):
     if attr == 'sum_tree':
       nodes = value['nodes'] if isinstance(value, dict) else value.nodes
       max_recorded = (value['max_recorded_priority'] if isinstance(value, dict)
                       else value.max_recorded_priority)
+      if len(nodes) != len(self.sum_tree.nodes):
+        raise ValueError('checkpointed sum tree has {} levels, this buffer {}'.
+                         format(len(nodes), len(self.sum_tree.nodes)))
       for level, array in enumerate(nodes):
         array = np.ascontiguousarray(array, dtype=np.float64)
         _native.check(self._lib.b2r_tree_write_level(

@@ -158,12 +158,60 @@ def golden_prioritized(prb):
   np.savez_compressed(os.path.join(OUT, 'prioritized_replay.npz'), **out)
 
 
+def golden_checkpoint(prb):
+  """A checkpoint WRITTEN BY THE REFERENCE's save() (circular_replay_buffer.py:
+  612-653): the gzip files go to tests/golden/ckpt_ref/ verbatim; what the
+  reference does after load()-ing them again goes to checkpoint.npz."""
+  ckpt_dir = os.path.join(OUT, 'ckpt_ref')
+  os.makedirs(ckpt_dir, exist_ok=True)
+  for f in os.listdir(ckpt_dir):
+    os.remove(os.path.join(ckpt_dir, f))
+  rng = np.random.RandomState(77)
+  shape, stack, cap, batch, n = (6, 6), 4, 50, 8, 3
+  kw = dict(update_horizon=n, gamma=0.99, max_sample_attempts=100)
+  mem = prb.OutOfGraphPrioritizedReplayBuffer(shape, stack, cap, batch, **kw)
+  obs, act, rew, term = synth_history(rng, 83, shape, 0.08)
+  for k in range(83):
+    mem.add(obs[k], act[k], rew[k], term[k], mem.sum_tree.max_recorded_priority)
+    if k % 9 == 4:
+      ids = rng.randint(0, min(cap, int(mem.add_count)), size=5).astype(np.int32)
+      mem.set_priority(ids, np.sqrt(np.abs(rng.randn(5)) + 1e-10).astype(np.float32))
+  mem.save(ckpt_dir, 7)
+  fresh = prb.OutOfGraphPrioritizedReplayBuffer(shape, stack, cap, batch, **kw)
+  fresh.load(ckpt_dir, '7')
+  out = {'cfg': np.array([stack, cap, batch, n], dtype=np.int64),
+         'shape': np.array(shape, dtype=np.int64),
+         'add_count': np.int64(fresh.add_count),
+         'invalid_range': np.asarray(fresh.invalid_range, dtype=np.int64),
+         'max_recorded': np.float64(fresh.sum_tree.max_recorded_priority)}
+  for name, array in fresh._store.items():  # pylint: disable=protected-access
+    out['store_' + name] = array.copy()
+  for l, level in enumerate(fresh.sum_tree.nodes):
+    out['level%d' % l] = level.copy()
+  random.seed(3)
+  sampled = fresh.sample_transition_batch()
+  out['next_u'] = np.float64(random.random())
+  for e, arr in zip(fresh.get_transition_elements(), sampled):
+    out['out_' + e.name] = arr
+  # and it keeps working: two more adds, one more priority batch
+  more_obs, more_act, more_rew, more_term = synth_history(rng, 2, shape, 0.0)
+  for k in range(2):
+    fresh.add(more_obs[k], more_act[k], more_rew[k], more_term[k], 2.5)
+  out['more_obs'], out['more_act'] = more_obs, more_act
+  out['more_rew'], out['more_term'] = more_rew, more_term
+  out['after_add_count'] = np.int64(fresh.add_count)
+  for l, level in enumerate(fresh.sum_tree.nodes):
+    out['after_level%d' % l] = level.copy()
+  np.savez_compressed(os.path.join(OUT, 'checkpoint.npz'), **out)
+
+
 def main():
   st, crb, prb = refshim.load_reference()
   os.makedirs(OUT, exist_ok=True)
   golden_sum_tree(st)
   golden_uniform(crb)
   golden_prioritized(prb)
+  golden_checkpoint(prb)
   for f in sorted(os.listdir(OUT)):
     print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -196,8 +196,8 @@ def test_fused_step_in_cuda_graph(gpu):
     assert np.array_equal(la.view(np.uint64), lb.view(np.uint64))
 
 
-@pytest.mark.parametrize('depth', [0, 2])
-def test_trainer_host_steps_match_oracles(gpu, depth):
+@pytest.mark.parametrize('depth,graph', [(0, False), (2, False), (2, True)])
+def test_trainer_host_steps_match_oracles(gpu, depth, graph):
   """The pipelined host-facing trainer: adds between steps, logits from host
   memory, losses handed back `depth` calls later; batch, losses and tree checked
   against the oracles step by step."""
@@ -205,7 +205,7 @@ def test_trainer_host_steps_match_oracles(gpu, depth):
   cap, batch = 50000, 32
   mem, tree, cols = _filled(gpu, cap, batch, seed=21, hot=False)
   trainer = gpu.ra.ReplayTrainer(mem, ACTIONS, ATOMS, 10., pipeline_depth=depth,
-                                 seed=21)
+                                 seed=21, use_graph=graph)
   rng = np.random.RandomState(4)
   inputs, losses = [], {}
   for step in range(6):
@@ -235,7 +235,8 @@ def test_trainer_host_steps_match_oracles(gpu, depth):
     assert np.array_equal(level.view(np.uint64), tree.level(l).view(np.uint64)), l
 
 
-def test_trainer_applies_adds_between_steps(gpu):
+@pytest.mark.parametrize('graph', [False, True])
+def test_trainer_applies_adds_between_steps(gpu, graph):
   """add() rows staged between trainer steps are in HBM (rows, priorities, validity
   window) before the next step samples."""
   from oracle.replay_port import PortPrioritizedReplay
@@ -247,7 +248,8 @@ def test_trainer_applies_adds_between_steps(gpu):
                                               output='torch', rng='device', seed=1)
   port = PortPrioritizedReplay((84, 84), 4, cap, batch, update_horizon=3, gamma=0.99)
   rng = np.random.RandomState(0)
-  trainer = gpu.ra.ReplayTrainer(mem, ACTIONS, ATOMS, 10., pipeline_depth=1, seed=1)
+  trainer = gpu.ra.ReplayTrainer(mem, ACTIONS, ATOMS, 10., pipeline_depth=1, seed=1,
+                                 use_graph=graph)
   added = 0
 
   def add_rows(n):
