@@ -436,6 +436,40 @@ def measure_e2e(torch, wl, batch, steps, update_period=4, pipeline_depth=2):
                    % (update_period, pipeline_depth))}
 
 
+def measure_full_train_step(torch, wl, batch, steps, ddp=False):
+  """BASELINE config 5: the whole Rainbow update on the synthetic Atari shape —
+  fused sample + gather feeding the cuDNN Nature-DQN distribution network (online on
+  state, target on next_state), fused C51 loss, backward, Adam, priority write-back
+  (dopamine_b200/agents/rainbow/agent.py).  Eager PyTorch around the kernels."""
+  from dopamine_b200.agents.rainbow import agent
+  mem = wl.mem
+  saved = (mem._output, mem._reuse_outputs, mem._batch_size)  # pylint: disable=protected-access
+  mem._output, mem._reuse_outputs, mem._batch_size = 'torch', True, batch  # pylint: disable=protected-access
+  learner = agent.RainbowLearner(NUM_ACTIONS, batch_size=batch, memory=mem, ddp=ddp,
+                                 update_horizon=HORIZON, gamma=GAMMA, vmax=VMAX)
+  for _ in range(10):
+    learner.train_step()
+  torch.cuda.synchronize()
+  start = torch.cuda.Event(enable_timing=True)
+  end = torch.cuda.Event(enable_timing=True)
+  t0 = time.perf_counter()
+  start.record()
+  for _ in range(steps):
+    loss = learner.train_step()
+  end.record()
+  end.synchronize()
+  wall = time.perf_counter() - t0
+  ms = start.elapsed_time(end)
+  mem._output, mem._reuse_outputs, mem._batch_size = saved  # pylint: disable=protected-access
+  return {'updates_per_s': round(steps / (ms * 1e-3), 1),
+          'transitions_per_s': round(batch * steps / (ms * 1e-3), 1),
+          'ms_per_update': round(ms / steps, 4), 'wall_ms_per_update':
+          round(wall * 1e3 / steps, 4), 'batch': batch, 'steps': steps,
+          'last_loss': round(float(loss), 5),
+          'what': 'sample+gather -> conv nets (cuDNN, fp32/TF32) -> fused C51 loss '
+                  '-> backward -> Adam -> set_priority; eager PyTorch host loop'}
+
+
 def measure_e2e_host_batch(torch, wl, batch, steps):
   """Variant that also ships the whole sampled batch to host numpy arrays, i.e. the
   reference's OutOfGraph* return convention (1.8 MB of D2H per step at batch 32)."""
@@ -503,15 +537,23 @@ def build_cpu_port(capacity, batch, seed=1234):
   return port
 
 
-def cpu_steps(port, batch, budget_s, max_steps, seed=7):
+def cpu_steps(port, batch, budget_s, max_steps, seed=7, update_period=4):
+  """The e2e workload on the CPU: `update_period` add()s, then one pass of the path
+  (sample_transition_batch -> C51 loss / priorities -> set_priority)."""
   from oracle import c51_port
   rng = np.random.RandomState(seed)
   online = rng.randn(batch, NUM_ACTIONS, NUM_ATOMS).astype(np.float32)
   target = rng.randn(batch, NUM_ACTIONS, NUM_ATOMS).astype(np.float32)
+  frames = rng.randint(0, 256, size=(64, 84, 84)).astype(np.uint8)
   random.seed(0)
   done = 0
+  k = 0
   t0 = time.perf_counter()
   while done < max_steps and (time.perf_counter() - t0 < budget_s or done < 3):
+    for _ in range(update_period):
+      port.add(frames[k & 63], k % NUM_ACTIONS, 0.5, int(k % 1000 == 999),
+               port.sum_tree.max_recorded_priority)
+      k += 1
     b = port.sample_transition_batch(batch)
     out = c51_port.rainbow_update(b[2], b[6], b[1], b[8], online, target,
                                   vmax=VMAX, num_atoms=NUM_ATOMS, gamma=GAMMA,
@@ -528,9 +570,9 @@ def cpu_baseline(batch, capacity, budget_s=12.0):
   return {
       'value': round(batch * steps / dt, 1), 'unit': UNIT, 'cores': 1,
       'kind': 'port',
-      'sample': '{} steps of batch {} in {:.1f} s, capacity {} (oracle port of the '
-                'reference: Python/numpy, single thread as the reference is)'
-                .format(steps, batch, dt, capacity),
+      'sample': '{} steps (4 x add() + sample + C51 + set_priority each) of batch {} '
+                'in {:.1f} s, capacity {} (oracle port of the reference: Python/numpy, '
+                'single thread as the reference is)'.format(steps, batch, dt, capacity),
   }
 
 
@@ -593,10 +635,10 @@ def run_reference(args):
       'config': {'workload': workload_name(args.batch, args.capacity, 1)},
       'cpu_baseline': {
           'value': round(rate, 1), 'unit': UNIT, 'cores': 1, 'kind': 'port',
-          'sample': '{} steps of batch {} in {:.1f} s, one process, capacity {} '
-                    '(oracle port of the reference: Python/numpy, single-threaded '
-                    'as the reference is)'.format(steps, args.batch, dt,
-                                                  args.capacity),
+          'sample': '{} steps (4 x add() + sample + C51 + set_priority each) of '
+                    'batch {} in {:.1f} s, one process, capacity {} (oracle port of '
+                    'the reference: Python/numpy, single-threaded as the reference '
+                    'is)'.format(steps, args.batch, dt, args.capacity),
           'all_cores_replicas': {
               'value': round(rate_all, 1), 'unit': UNIT, 'cores': replicas,
               'host_cores': os.cpu_count(),
@@ -719,6 +761,10 @@ def main():
                                      pipeline_depth=0)
       line['e2e'] = measure_e2e(torch, wl, args.batch,
                                 max(50, min(args.steps, 5000)))
+    if not args.no_e2e and world == 1:
+      line['full_train_step'] = {
+          str(b): measure_full_train_step(torch, wl, b, 200 if b <= 256 else 50)
+          for b in ([args.batch] + ([256] if sweep_batches else []))}
     if not args.no_cpu_baseline and world == 1:
       line['cpu_baseline'] = cpu_baseline(args.batch, args.capacity)
     print(json.dumps(line))

@@ -1,0 +1,173 @@
+"""The learner half of the Rainbow agent on top of the B200 replay path.
+
+Mirrors what `RainbowAgent` builds around the replay memory
+(dopamine/agents/rainbow/rainbow_agent.py:93-337 on dqn_agent.py:341-442): the
+convolutional distribution network (atari_lib.py:108-144, cuDNN through PyTorch —
+the only dense contraction on the path, so the only part that is NOT a hand-written
+kernel here), the C51 train op, Adam with the reference's hyper-parameters
+(rainbow.gin:21-25), priority write-back and the target-network sync.  Acting in an
+environment (epsilon-greedy, frame stacking) stays with the caller, which feeds
+`store_transition` exactly as the reference's `_store_transition` feeds `add`.
+
+One `train_step()`:
+  sample + gather (one fused call, batch stays in HBM) -> online net on `state`,
+  target net on `next_state` -> fused C51 loss kernel (also yields d loss / d logits)
+  -> backward + Adam -> batched priority write-back.
+With `ddp=True` every rank owns its own replay shard and the gradients are averaged
+by torch DistributedDataParallel over NCCL.
+"""
+import math
+
+import numpy as np
+
+from dopamine_b200.agents.rainbow import rainbow_agent
+from dopamine_b200.replay_memory import prioritized_replay_buffer
+
+
+def _torch():
+  import torch  # pylint: disable=g-import-not-at-top
+  return torch
+
+
+def _same_pad(size, kernel, stride):
+  """TensorFlow 'SAME' padding (before, after) for one spatial dimension."""
+  out = -(-size // stride)
+  total = max((out - 1) * stride + kernel - size, 0)
+  return total // 2, total - total // 2
+
+
+def make_rainbow_network(num_actions, num_atoms, observation_shape=(84, 84),
+                         stack_size=4):
+  """atari_lib.rainbow_network (atari_lib.py:108-144): uint8 (B, H, W, stack) in,
+  (B, num_actions, num_atoms) logits out; conv 32x8x8/4, 64x4x4/2, 64x3x3/1 with
+  SAME padding, FC 512, FC A*N; uniform variance-scaling init, factor 1/sqrt(3),
+  fan-in (atari_lib.py:122-123)."""
+  torch = _torch()
+  nn = torch.nn
+
+  class RainbowNetwork(nn.Module):
+
+    def __init__(self):
+      super().__init__()
+      h, w = observation_shape
+      specs = [(stack_size, 32, 8, 4), (32, 64, 4, 2), (64, 64, 3, 1)]
+      self.convs = nn.ModuleList()
+      self.pads = []
+      for cin, cout, k, s in specs:
+        ph, pw = _same_pad(h, k, s), _same_pad(w, k, s)
+        self.pads.append((pw[0], pw[1], ph[0], ph[1]))
+        self.convs.append(nn.Conv2d(cin, cout, k, stride=s))
+        h, w = -(-h // s), -(-w // s)
+      self.fc1 = nn.Linear(h * w * 64, 512)
+      self.fc2 = nn.Linear(512, num_actions * num_atoms)
+      for m in list(self.convs) + [self.fc1, self.fc2]:
+        fan_in = m.weight[0].numel()
+        # variance_scaling_initializer(factor, 'FAN_IN', uniform=True):
+        # limit = sqrt(3 * factor / fan_in)
+        limit = math.sqrt(3.0 * (1.0 / math.sqrt(3.0)) / fan_in)
+        nn.init.uniform_(m.weight, -limit, limit)
+        nn.init.zeros_(m.bias)
+
+    def forward(self, state):
+      x = state.permute(0, 3, 1, 2).to(torch.float32).div_(255.)  # atari_lib.py:124-125
+      for pad, conv in zip(self.pads, self.convs):
+        x = torch.relu(conv(torch.nn.functional.pad(x, pad)))
+      # slim.flatten works on NHWC; keep that ordering of the 7 744 features
+      x = x.permute(0, 2, 3, 1).flatten(1)
+      x = torch.relu(self.fc1(x))
+      return self.fc2(x).view(-1, num_actions, num_atoms)
+
+  return RainbowNetwork()
+
+
+class RainbowLearner(object):
+  """Replay + train op of RainbowAgent (rainbow_agent.py:93-337)."""
+
+  def __init__(self, num_actions, observation_shape=(84, 84), stack_size=4,
+               num_atoms=51, vmax=10., gamma=0.99, update_horizon=3,
+               replay_capacity=1000000, batch_size=32, target_update_period=8000,
+               update_period=4, replay_scheme='prioritized', learning_rate=6.25e-5,
+               adam_epsilon=1.5e-4, seed=0, ddp=False, memory=None):
+    torch = _torch()
+    if replay_scheme not in ('prioritized', 'uniform'):
+      raise ValueError('Invalid replay scheme: {}'.format(replay_scheme))
+    self.num_actions, self.num_atoms = num_actions, num_atoms
+    self.batch_size = batch_size
+    self.replay_scheme = replay_scheme
+    self.update_period = update_period
+    self.target_update_period = target_update_period
+    # rainbow_agent.py:188-198: the prioritized buffer is used for both schemes.
+    self.memory = memory or prioritized_replay_buffer.OutOfGraphPrioritizedReplayBuffer(
+        observation_shape, stack_size, replay_capacity, batch_size,
+        update_horizon=update_horizon, gamma=gamma, output='torch', rng='device',
+        seed=seed, reuse_outputs=True)
+    self.support = rainbow_agent.make_support(vmax, num_atoms)
+    self.cumulative_gamma = math.pow(gamma, update_horizon)  # dqn_agent.py:175
+    torch.manual_seed(seed)
+    self.online = make_rainbow_network(num_actions, num_atoms, observation_shape,
+                                       stack_size).cuda()
+    self.target = make_rainbow_network(num_actions, num_atoms, observation_shape,
+                                       stack_size).cuda()
+    self.target.load_state_dict(self.online.state_dict())
+    for p in self.target.parameters():
+      p.requires_grad_(False)
+    self._net = self.online
+    if ddp:
+      from torch.nn.parallel import DistributedDataParallel  # pylint: disable=g-import-not-at-top
+      self._net = DistributedDataParallel(
+          self.online, device_ids=[torch.cuda.current_device()])
+    self.optimizer = torch.optim.Adam(self.online.parameters(), lr=learning_rate,
+                                      eps=adam_epsilon)  # rainbow.gin:21-25
+    self.training_steps = 0
+    self.updates = 0
+
+  # -- the add side (rainbow_agent.py:307-337) -------------------------------------
+  def store_transition(self, last_observation, action, reward, is_terminal,
+                       priority=None):
+    if priority is None:
+      priority = (1. if self.replay_scheme == 'uniform' else
+                  prioritized_replay_buffer.MAX_RECORDED_PRIORITY)
+    self.memory.add(last_observation, action, reward, is_terminal, priority)
+
+  def q_values(self, state):
+    """(B, A) expected values of the online network (atari_lib.py:141-143)."""
+    torch = _torch()
+    with torch.no_grad():
+      probs = torch.softmax(self.online(state), dim=2)
+      return (probs * self.support).sum(dim=2)
+
+  # -- the train op (rainbow_agent.py:253-305) ---------------------------------------
+  def train_step(self):
+    """One update; returns the scalar training loss (a CUDA tensor, no sync)."""
+    torch = _torch()
+    batch = self.memory.sample_transition_batch(self.batch_size)
+    (state, action, reward, next_state, _, _, terminal, indices, probs) = batch[:9]
+    with torch.no_grad():
+      target_logits = self.target(next_state)
+    online_logits = self._net(state)
+    scheme_probs = probs if self.replay_scheme == 'prioritized' else None
+    loss, priorities, _, _ = rainbow_agent.C51Loss.apply(
+        online_logits, target_logits, action, reward, terminal, scheme_probs,
+        self.support, self.cumulative_gamma)
+    self.optimizer.zero_grad(set_to_none=True)
+    loss.backward()
+    self.optimizer.step()
+    if self.replay_scheme == 'prioritized':  # rainbow_agent.py:289-295
+      self.memory.set_priority(indices, priorities)
+    self.updates += 1
+    return loss
+
+  def sync_target(self):
+    self.target.load_state_dict(self.online.state_dict())
+
+  def step_cadence(self):
+    """dqn_agent.py:418-442: called once per environment step by the acting loop;
+    trains every `update_period` steps and syncs the target network every
+    `target_update_period` steps."""
+    loss = None
+    if self.training_steps % self.update_period == 0:
+      loss = self.train_step()
+    if self.training_steps % self.target_update_period == 0:
+      self.sync_target()
+    self.training_steps += 1
+    return loss

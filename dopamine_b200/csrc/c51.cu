@@ -13,6 +13,8 @@
 // read, <= 204 B target + 12 B scalars written (+3 672 B if grad_logits is asked).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace b2r {
 namespace {
 
@@ -20,14 +22,29 @@ B2R_TRACE_DECL
 
 constexpr int kWarpsPerBlock = 4;
 
+// UNROLLED = false keeps the reductions as 5-trip loops (compact code for the
+// latency-bound small-batch instance); true unrolls them: the large-batch instance
+// is bound by instruction issue and the loop control is 2/3 of a rolled reduction.
+template <bool UNROLLED = false>
 __device__ __forceinline__ float warp_max(float v) {
+  if (UNROLLED) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  } else {
 #pragma unroll 1
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  }
   return v;
 }
+template <bool UNROLLED = false>
 __device__ __forceinline__ float warp_sum(float v) {
+  if (UNROLLED) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  } else {
 #pragma unroll 1
-  for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  }
   return v;
 }
 
@@ -89,7 +106,7 @@ constexpr int kMaxAtomsPerLane = 4;  // num_atoms <= 128
 
 // PL = atoms per lane (2 covers C51's 51 atoms; fewer unrolled copies = less
 // straight-line code to fetch on a cold instruction cache).
-template <int PL>
+template <int PL, bool FAST>
 __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,13 +148,15 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
       pmin = fminf(pmin, a.u.sampling_probabilities[k]);
   float zl[PL], xt[PL], xo[PL];
   const int act0 = warp;  // first (usually only) action of this warp
+  const float *__restrict__ trow = a.u.target_logits + (size_t)b * A * N;
+  const float *__restrict__ orow = a.u.online_logits + (size_t)b * A * N;
 #pragma unroll
   for (int t = 0; t < PL; ++t) {
     const int i = lane + 32 * t;
     const bool ok = i < N && act0 < A;
     zl[t] = i < N ? z[i] : 0.f;
-    xt[t] = ok ? a.u.target_logits[((size_t)b * A + act0) * N + i] : -INFINITY;
-    xo[t] = ok ? a.u.online_logits[((size_t)b * A + act0) * N + i] : 0.f;
+    xt[t] = ok ? trow[act0 * N + i] : -INFINITY;
+    xo[t] = ok ? orow[act0 * N + i] : 0.f;
   }
 
   B2R_MARK(2);
@@ -149,8 +168,9 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
 #pragma unroll
       for (int t = 0; t < PL; ++t) {
         const int i = lane + 32 * t;
-        xt[t] = i < N ? a.u.target_logits[((size_t)b * A + act) * N + i] : -INFINITY;
-        xo[t] = i < N ? a.u.online_logits[((size_t)b * A + act) * N + i] : 0.f;
+        xt[t] = i < N ? trow[act * N + i] : -INFINITY;
+        // only the chosen action's online logits are ever used
+        xo[t] = (i < N && act == chosen) ? orow[act * N + i] : 0.f;
       }
     }
     if (act == chosen) {
@@ -161,7 +181,7 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
     float m = -INFINITY;
 #pragma unroll
     for (int t = 0; t < PL; ++t) m = fmaxf(m, xt[t]);
-    m = warp_max(m);
+    m = warp_max<FAST>(m);
     float e[PL];
     float psum = 0.f;
 #pragma unroll
@@ -170,7 +190,7 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
       e[t] = ok ? expf(__fsub_rn(xt[t], m)) : 0.f;
       if (ok) psum = __fadd_rn(psum, e[t]);
     }
-    const float denom = warp_sum(psum);
+    const float denom = warp_sum<FAST>(psum);
     float qpart = 0.f;
 #pragma unroll
     for (int t = 0; t < PL; ++t) {
@@ -179,7 +199,7 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
         qpart = __fadd_rn(qpart, __fmul_rn(zl[t], e[t]));
       }
     }
-    const float q = warp_sum(qpart);
+    const float q = warp_sum<FAST>(qpart);
     if (best_a < 0 || q > best_q) {  // strict > keeps the first maximum
       best_q = q;
       best_a = act;
@@ -412,12 +432,22 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
   }
   a.weighted = b2r::g_weighted;
   a.ticket = b2r::g_ticket;
-  if (args->num_atoms <= 64)
-    B2R_CUDA(b2r::launch(b2r::c51_loss_kernel<2>, dim3(args->batch), dim3(threads),
-                         smem, s, a));
-  else
-    B2R_CUDA(b2r::launch(b2r::c51_loss_kernel<4>, dim3(args->batch), dim3(threads),
-                         smem, s, a));
+  static const int force_fast = [] {
+    const char *e = std::getenv("B2R_C51_FAST");
+    return e ? std::atoi(e) : -1;
+  }();
+  const bool fast = force_fast >= 0 ? force_fast != 0 : args->batch > 256;
+  if (args->num_atoms <= 64) {
+    if (fast)
+      B2R_CUDA(b2r::launch(b2r::c51_loss_kernel<2, true>, dim3(args->batch),
+                           dim3(threads), smem, s, a));
+    else
+      B2R_CUDA(b2r::launch(b2r::c51_loss_kernel<2, false>, dim3(args->batch),
+                           dim3(threads), smem, s, a));
+  } else {
+    B2R_CUDA(b2r::launch(b2r::c51_loss_kernel<4, false>, dim3(args->batch),
+                         dim3(threads), smem, s, a));
+  }
   B2R_LAUNCHED();
   return B2R_OK;
 }

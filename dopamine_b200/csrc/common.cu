@@ -22,6 +22,40 @@ int chain_priority() {
   return value;
 }
 
+TreeWindow &tree_window() {
+  static thread_local TreeWindow w;
+  return w;
+}
+
+void set_tree_window(void *base, size_t bytes) {
+  static const bool enabled = std::getenv("B2R_NO_L2_PERSIST") == nullptr;
+  static size_t reserved = 0;
+  TreeWindow &w = tree_window();
+  if (!enabled || base == nullptr) {
+    w.base = nullptr;
+    w.bytes = 0;
+    return;
+  }
+  int device = 0, max_persist = 0, max_window = 0;
+  if (cudaGetDevice(&device) != cudaSuccess) return;
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+  if (max_persist <= 0 || max_window <= 0) {
+    w.base = nullptr;
+    return;
+  }
+  if (bytes > (size_t)max_window) bytes = (size_t)max_window;
+  const size_t want = bytes < (size_t)max_persist ? bytes : (size_t)max_persist;
+  if (want > reserved) {  // grow the set-aside (a device-wide limit) when needed
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+      reserved = want;
+    else
+      cudaGetLastError();
+  }
+  w.base = base;
+  w.bytes = bytes;
+}
+
 std::string &last_error_slot() {
   static thread_local std::string slot;
   return slot;

@@ -67,6 +67,20 @@ bool pdl_enabled();
 // queues behind tens of thousands of copy CTAs.
 int chain_priority();  // the device's greatest stream priority (numerically lowest)
 
+// L2 residency of the sum tree.  The frame copies stream hundreds of MB through the
+// 126 MB L2 beside the chain; without protection they evict the 16 MB tree that the
+// sampler's descents and the write-back's read-modify-writes live on.  Chain kernels
+// are launched with an access-policy window over the tree heap (persisting hits);
+// the copy kernels use streaming loads / stores.  set_tree_window() is called by
+// the launch sites that touch a tree; the window applies to the next launches made
+// through launch() on this thread.
+struct TreeWindow {
+  void *base = nullptr;
+  size_t bytes = 0;
+};
+TreeWindow &tree_window();
+void set_tree_window(void *base, size_t bytes);  // also reserves the L2 set-aside once
+
 template <typename... Params, typename... Args>
 cudaError_t launch_prio(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem,
                         cudaStream_t stream, int priority, Args &&...args) {
@@ -75,8 +89,18 @@ cudaError_t launch_prio(void (*kernel)(Params...), dim3 grid, dim3 block, size_t
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int n = 0;
+  const TreeWindow &w = tree_window();
+  if (w.base != nullptr && priority != 0) {
+    attr[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[n].val.accessPolicyWindow.base_ptr = w.base;
+    attr[n].val.accessPolicyWindow.num_bytes = w.bytes;
+    attr[n].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[n].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    ++n;
+  }
   if (pdl_enabled()) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;

@@ -60,10 +60,10 @@ __device__ __forceinline__ void store_stack16(uint8_t *dst, const uint4 f0,
                                               const uint4 f1, const uint4 f2,
                                               const uint4 f3) {
   uint4 *d = reinterpret_cast<uint4 *>(dst);
-  d[0] = interleave4(f0.x, f1.x, f2.x, f3.x);
-  d[1] = interleave4(f0.y, f1.y, f2.y, f3.y);
-  d[2] = interleave4(f0.z, f1.z, f2.z, f3.z);
-  d[3] = interleave4(f0.w, f1.w, f2.w, f3.w);
+  __stcs(d + 0, interleave4(f0.x, f1.x, f2.x, f3.x));
+  __stcs(d + 1, interleave4(f0.y, f1.y, f2.y, f3.y));
+  __stcs(d + 2, interleave4(f0.z, f1.z, f2.z, f3.z));
+  __stcs(d + 3, interleave4(f0.w, f1.w, f2.w, f3.w));
 }
 
 __device__ __forceinline__ uint4 load_frame16(const uint8_t *__restrict__ obs,
@@ -71,7 +71,8 @@ __device__ __forceinline__ uint4 load_frame16(const uint8_t *__restrict__ obs,
                                               int64_t obs_bytes, int chunk) {
   if (slot < 0) slot += cap;
   if (slot >= cap) slot -= cap;
-  return __ldg(reinterpret_cast<const uint4 *>(obs + slot * obs_bytes) + chunk);
+  // streamed: every frame byte is read once per batch; keep L2 for the sum tree
+  return __ldcs(reinterpret_cast<const uint4 *>(obs + slot * obs_bytes) + chunk);
 }
 
 // Fast path: stack 4, 1-byte pixels, obs_bytes % 16 == 0.

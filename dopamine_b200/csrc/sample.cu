@@ -554,6 +554,7 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
     fill_scalar_args(b, scalars, &a.sc);
     if (a.sc.indices_out == out_idx_dev) a.sc.indices_out = nullptr;
   }
+  set_tree_window(b->tree->heap, (size_t)b->tree->leaves * 16);
   // 3 tree levels per memory round trip (more would bloat the straight-line code,
   // and a cold instruction cache costs more than the saved round trips).
   B2R_CUDA(launch(per_sample_kernel<3, 256>, dim3(tiles), dim3(threads), 0, stream, a));
@@ -624,6 +625,7 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
     fill_scalar_args(b, scalars, &a.sc);
     if (a.sc.indices_out == out_indices) a.sc.indices_out = nullptr;
   }
+  set_tree_window(b->tree->heap, (size_t)b->tree->leaves * 16);
   if (global_batch <= 256)
     B2R_CUDA(launch(per_sample_kernel<3, 256>, dim3(1), dim3(threads), 0, s, a));
   else

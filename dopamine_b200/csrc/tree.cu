@@ -104,12 +104,116 @@ constexpr int kBigThreads = 1024;
 constexpr int kBigItems = kTreeChunk / kBigThreads;
 using BigSort = cub::BlockRadixSort<uint32_t, kBigThreads, kBigItems, uint32_t>;
 
-struct BigSmem {
+constexpr int kHashSlots = 2 * kTreeChunk;  // load factor <= 0.5
+constexpr int kHashBits = 13;
+static_assert((1 << kHashBits) == kHashSlots, "hash size");
+constexpr int kMaxDup = 512;  // duplicate-leaf entries the hashed leaf pass handles
+
+struct GroupSmem {
   typename BigSort::TempStorage sort;
   uint32_t node[kTreeChunk];  // node index on this level, grouped
   uint32_t elem[kTreeChunk];  // batch position k of the same entry
+};
+struct HashSmem {
+  uint32_t key[kHashSlots];   // leaf index owning the slot
+  uint32_t count[kHashSlots]; // entries of the chunk that hit it
+};
+struct BigSmem {
+  union {
+    GroupSmem g;
+    HashSmem h;               // leaf CTA only, before (instead of) the sort
+  };
   double vals[kTreeChunk];    // value -> leaf delta (leaf CTA) / deltas in group order
 };
+
+// Leaf pass without sorting.  The leaf deltas gate every other level (the root's
+// chain of n dependent adds starts when they are published), so the leaf CTA avoids
+// the 20-bit sort whenever it can: a shared-memory hash set finds the entries whose
+// leaf occurs more than once in the chunk; all others are independent
+// (delta = value - leaf, leaf += delta, sum_tree.py:196-202), and the few duplicates
+// are ordered by (leaf, batch position) with a counting rank and walked as chains.
+// Returns false (nothing written) when more than kMaxDup entries share leaves; the
+// caller then takes the sorted path.
+template <typename I, typename V>
+__device__ __forceinline__ bool leaf_deltas_hashed(const UpdateArgs<I, V> &a, int n_eff,
+                                                   HashSmem &h, double *vals) {
+  __shared__ uint32_t d_idx[kMaxDup], d_k[kMaxDup], ds_idx[kMaxDup], ds_k[kMaxDup];
+  __shared__ int s_ndup;
+  constexpr uint32_t kEmpty = 0xffffffffu;
+  for (int i = threadIdx.x; i < kHashSlots; i += blockDim.x) {
+    h.key[i] = kEmpty;
+    h.count[i] = 0;
+  }
+  if (threadIdx.x == 0) s_ndup = 0;
+  __syncthreads();
+  uint32_t my_idx[kBigItems], my_slot[kBigItems];
+  double my_leaf[kBigItems];
+#pragma unroll
+  for (int j = 0; j < kBigItems; ++j) {
+    const int k = threadIdx.x + j * kBigThreads;
+    my_idx[j] = kEmpty;
+    if (k < n_eff) {
+      const uint32_t idx = (uint32_t)a.indices[k];
+      my_idx[j] = idx;
+      my_leaf[j] = a.heap[a.leaves + idx];  // in flight while the hash set fills
+      uint32_t slot = (idx * 2654435761u) >> (32 - kHashBits);
+      while (true) {
+        const uint32_t old = atomicCAS(&h.key[slot], kEmpty, idx);
+        if (old == kEmpty || old == idx) break;
+        slot = (slot + 1) & (kHashSlots - 1);
+      }
+      atomicAdd(&h.count[slot], 1u);
+      my_slot[j] = slot;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kBigItems; ++j) {
+    if (my_idx[j] != kEmpty && h.count[my_slot[j]] > 1) {
+      const int pos = atomicAdd(&s_ndup, 1);
+      if (pos < kMaxDup) {
+        d_idx[pos] = my_idx[j];
+        d_k[pos] = (uint32_t)(threadIdx.x + j * kBigThreads);
+      }
+    }
+  }
+  __syncthreads();
+  const int ndup = s_ndup;
+  if (ndup > kMaxDup) return false;
+  // entries whose leaf is theirs alone
+#pragma unroll
+  for (int j = 0; j < kBigItems; ++j) {
+    if (my_idx[j] != kEmpty && h.count[my_slot[j]] == 1) {
+      const int k = threadIdx.x + j * kBigThreads;
+      const double d = __dsub_rn(vals[k], my_leaf[j]);
+      a.heap[a.leaves + my_idx[j]] = __dadd_rn(my_leaf[j], d);
+      vals[k] = d;
+    }
+  }
+  // duplicates: order by (leaf, batch position), one chain per leaf
+  if ((int)threadIdx.x < ndup) {
+    const uint64_t me = ((uint64_t)d_idx[threadIdx.x] << 32) | d_k[threadIdx.x];
+    int rank = 0;
+    for (int j = 0; j < ndup; ++j)
+      rank += ((((uint64_t)d_idx[j] << 32) | d_k[j]) < me) ? 1 : 0;
+    ds_idx[rank] = d_idx[threadIdx.x];
+    ds_k[rank] = d_k[threadIdx.x];
+  }
+  __syncthreads();
+  const int p = threadIdx.x;
+  if (p < ndup && (p == 0 || ds_idx[p - 1] != ds_idx[p])) {
+    const uint32_t idx = ds_idx[p];
+    double leaf = a.heap[a.leaves + idx];
+    for (int q = p; q < ndup && ds_idx[q] == idx; ++q) {
+      const uint32_t k = ds_k[q];
+      const double d = __dsub_rn(vals[k], leaf);
+      leaf = __dadd_rn(leaf, d);
+      vals[k] = d;
+    }
+    a.heap[a.leaves + idx] = leaf;
+  }
+  return true;
+}
 
 template <typename I, typename V>
 __global__ void __launch_bounds__(kBigThreads) tree_update_kernel(UpdateArgs<I, V> a) {
@@ -159,11 +263,26 @@ __global__ void __launch_bounds__(kBigThreads) tree_update_kernel(UpdateArgs<I, 
     s_stop_code = (vals[n_eff] < 0.0) ? B2R_ERR_NEGATIVE_PRIORITY
                                       : B2R_ERR_INDEX_RANGE;
 
-  // 2. group by node: thread t holds entries 4t .. 4t+3 (batch order); pads carry
+  // 2. leaf CTA: the sort-free pass when duplicates are few (the usual case)
+  B2R_MARK_CTA(17, a.depth);
+  bool leaf_done = false;
+  if (is_leaf) {
+    // max_recorded_priority = max(value, current) over the applied prefix
+    // (before vals[] turns into deltas).
+    double local_max = 0.0;
+    for (int k = threadIdx.x; k < n_eff; k += blockDim.x)
+      local_max = fmax(local_max, vals[k]);
+    for (int off = 16; off > 0; off >>= 1)
+      local_max = fmax(local_max, __shfl_xor_sync(0xffffffffu, local_max, off));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = local_max;
+    leaf_done = leaf_deltas_hashed(a, n_eff, sm.h, vals);
+    __syncthreads();
+  }
+
+  // 3. group by node: thread t holds entries 4t .. 4t+3 (batch order); pads carry
   //    all-ones keys and sit behind every real entry, so they stay last.
   const int shift = a.depth - level;
-  B2R_MARK_CTA(17, a.depth);
-  {
+  if (!leaf_done) {
     uint32_t key[kBigItems], val[kBigItems];
 #pragma unroll
     for (int j = 0; j < kBigItems; ++j) {
@@ -171,39 +290,34 @@ __global__ void __launch_bounds__(kBigThreads) tree_update_kernel(UpdateArgs<I, 
       key[j] = k < n_eff ? (uint32_t)((int64_t)a.indices[k] >> shift) : 0xffffffffu;
       val[j] = (uint32_t)k;
     }
-    if (level != 0) BigSort(sm.sort).Sort(key, val, 0, level);
+    if (level != 0) BigSort(sm.g.sort).Sort(key, val, 0, level);
 #pragma unroll
     for (int j = 0; j < kBigItems; ++j) {
-      sm.node[threadIdx.x * kBigItems + j] = key[j];
-      sm.elem[threadIdx.x * kBigItems + j] = val[j];
+      sm.g.node[threadIdx.x * kBigItems + j] = key[j];
+      sm.g.elem[threadIdx.x * kBigItems + j] = val[j];
     }
   }
   __syncthreads();
   B2R_MARK_CTA(18, a.depth);
 
   if (is_leaf) {
-    // max_recorded_priority = max(value, current) over the applied prefix.
-    double local_max = 0.0;
-    for (int k = threadIdx.x; k < n_eff; k += blockDim.x)
-      local_max = fmax(local_max, vals[k]);
-    for (int off = 16; off > 0; off >>= 1)
-      local_max = fmax(local_max, __shfl_xor_sync(0xffffffffu, local_max, off));
-    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = local_max;
-    // one thread per distinct leaf walks its chain in batch order:
-    //   delta = value - leaf; leaf += delta   (sum_tree.py:196-202, last level).
-    for (int p = threadIdx.x; p < n_eff; p += blockDim.x) {
-      const uint32_t node = sm.node[p];
-      if (p > 0 && sm.node[p - 1] == node) continue;
-      double leaf = a.heap[a.leaves + node];
-      for (int q = p; q < n_eff && sm.node[q] == node; ++q) {
-        const uint32_t k = sm.elem[q];
-        const double d = __dsub_rn(vals[k], leaf);
-        leaf = __dadd_rn(leaf, d);
-        vals[k] = d;
+    if (!leaf_done) {
+      // many duplicates: one thread per distinct leaf walks its chain in batch order
+      //   delta = value - leaf; leaf += delta   (sum_tree.py:196-202, last level).
+      for (int p = threadIdx.x; p < n_eff; p += blockDim.x) {
+        const uint32_t node = sm.g.node[p];
+        if (p > 0 && sm.g.node[p - 1] == node) continue;
+        double leaf = a.heap[a.leaves + node];
+        for (int q = p; q < n_eff && sm.g.node[q] == node; ++q) {
+          const uint32_t k = sm.g.elem[q];
+          const double d = __dsub_rn(vals[k], leaf);
+          leaf = __dadd_rn(leaf, d);
+          vals[k] = d;
+        }
+        a.heap[a.leaves + node] = leaf;
       }
-      a.heap[a.leaves + node] = leaf;
+      __syncthreads();
     }
-    __syncthreads();
     for (int k = threadIdx.x; k < n_eff; k += blockDim.x) a.delta[k] = vals[k];
   }
 
@@ -229,19 +343,19 @@ __global__ void __launch_bounds__(kBigThreads) tree_update_kernel(UpdateArgs<I, 
   // 3. internal level: deltas in group order, then one ordered chain per node.
   double *sorted_delta = vals;
   for (int p = threadIdx.x; p < n_eff; p += blockDim.x)
-    sorted_delta[p] = a.delta[sm.elem[p]];
+    sorted_delta[p] = a.delta[sm.g.elem[p]];
   __syncthreads();
   B2R_MARK_CTA(3, 0);
   B2R_MARK_CTA(20, 1);
   const int64_t base = ((int64_t)1) << level;
   for (int p = threadIdx.x; p < n_eff; p += blockDim.x) {
-    const uint32_t node = sm.node[p];
-    if (p > 0 && sm.node[p - 1] == node) continue;
+    const uint32_t node = sm.g.node[p];
+    if (p > 0 && sm.g.node[p - 1] == node) continue;
     // end of the segment: first position whose node is larger (binary search).
     int lo = p + 1, hi = n_eff;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if (sm.node[mid] > node) hi = mid; else lo = mid + 1;
+      if (sm.g.node[mid] > node) hi = mid; else lo = mid + 1;
     }
     double acc = a.heap[base + node];
 #pragma unroll 8
@@ -447,6 +561,7 @@ int allow_big_smem(K kernel) {
 template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
                const uint8_t *mode, cudaStream_t stream, const int32_t *n_dev) {
+  set_tree_window(t->heap, (size_t)t->leaves * 16);
   // The one-CTA kernel sorts per warp (cost ~ n log^2 n): it wins for the agent's
   // batch of 32 and loses to the radix-sorted cooperative kernel beyond ~64 entries
   // (measured, profiles/r1/README.md).  B2R_TREE_SMALL_MAX overrides the threshold.
@@ -508,13 +623,24 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     cfg.blockDim = dim3(kBigThreads);
     cfg.dynamicSmemBytes = sizeof(BigSmem);
     cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    attr[1].id = cudaLaunchAttributePriority;
-    attr[1].val.priority = chain_priority();
+    cudaLaunchAttribute attr[3];
+    int n_attr = 0;
+    attr[n_attr].id = cudaLaunchAttributeCooperative;
+    attr[n_attr++].val.cooperative = 1;
+    if (chain_priority() != 0) {
+      attr[n_attr].id = cudaLaunchAttributePriority;
+      attr[n_attr++].val.priority = chain_priority();
+    }
+    if (tree_window().base != nullptr) {
+      attr[n_attr].id = cudaLaunchAttributeAccessPolicyWindow;
+      attr[n_attr].val.accessPolicyWindow.base_ptr = tree_window().base;
+      attr[n_attr].val.accessPolicyWindow.num_bytes = tree_window().bytes;
+      attr[n_attr].val.accessPolicyWindow.hitRatio = 1.0f;
+      attr[n_attr].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr[n_attr++].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = chain_priority() != 0 ? 2 : 1;
+    cfg.numAttrs = n_attr;
     B2R_CUDA(cudaLaunchKernelEx(&cfg, tree_update_kernel<I, V>, a));
     B2R_LAUNCHED();
   }
