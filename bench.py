@@ -369,10 +369,19 @@ def measure_gather_roofline(torch, wl, batch, peak_gbs, launches=200):
   ms = time_graph_or_eager(torch, body, reps, 3, True)
   sec_per_launch = ms * 1e-3 / (reps * nbuf)
   achieved = bytes_per_launch / sec_per_launch / 1e9
+  traffic, traffic_note = None, None
+  try:  # per-launch DRAM bytes of this kernel from the committed ncu capture
+    t = json.load(open(os.path.join(ROOT, 'profiles', 'r1', 'traffic.json')))
+    t = t['gather_stack4_u8_kernel'].get(str(batch))
+    if t:
+      traffic, traffic_note = t['traffic_bytes'], t['note']
+  except Exception:  # pylint: disable=broad-except
+    pass
   return {
       'bound': 'hbm', 'kernel': 'gather_stack4_u8_kernel',
       'achieved': round(achieved, 1), 'peak': peak_gbs, 'unit': 'GB/s',
-      'frac': round(achieved / peak_gbs, 4), 'traffic': None,
+      'frac': round(achieved / peak_gbs, 4), 'traffic': traffic,
+      'traffic_note': traffic_note,
       'us_per_launch': round(sec_per_launch * 1e6, 3),
       'algorithmic_bytes_per_launch': int(bytes_per_launch),
       'peak_source': 'MEASURED_PEAKS.json hbm_gbs (burst, kernel timed alone)',
