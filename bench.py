@@ -388,7 +388,8 @@ def measure_gather_roofline(torch, wl, batch, peak_gbs, launches=200):
   }
 
 
-def measure_e2e(torch, wl, batch, steps, update_period=4, pipeline_depth=2):
+def measure_e2e(torch, wl, batch, steps, update_period=4, pipeline_depth=2,
+                dist=None, world=1, rank=0):
   """The same metric end to end through the public host-facing API.
 
   Per step, as the agent drives the replay (dqn_agent.py:359-442): `update_period`
@@ -401,8 +402,15 @@ def measure_e2e(torch, wl, batch, steps, update_period=4, pipeline_depth=2):
   Every step's copies and kernels are inside the timed region either way."""
   from dopamine_b200.replay_memory import prioritized_replay_buffer as prb
   ra, mem = wl.ra, wl.mem
+  # N > 1: one trainer per rank over its own shard; `batch` is the GLOBAL batch, the
+  # shard totals travel through a peer-memory exchange of the trainer's own, every
+  # rank adds its own rows and gets the losses of the rows it served.
   trainer = ra.ReplayTrainer(mem, NUM_ACTIONS, NUM_ATOMS, VMAX, batch_size=batch,
-                             pipeline_depth=pipeline_depth, seed=wl.seed)
+                             pipeline_depth=pipeline_depth,
+                             seed=wl.seed if world == 1 else 4321)
+  if world > 1:
+    from dopamine_b200.replay_memory import sharded_replay
+    trainer.set_exchange(sharded_replay.PeerExchange(rank=rank, world_size=world))
   rng = np.random.RandomState(3)
   frames = rng.randint(0, 256, size=(64, 84, 84)).astype(np.uint8)
   online_h = wl.online[:batch].cpu().pin_memory()
@@ -423,17 +431,23 @@ def measure_e2e(torch, wl, batch, steps, update_period=4, pipeline_depth=2):
     one()
   trainer.drain()
   torch.cuda.synchronize()
+  if dist is not None:
+    dist.barrier()
   t0 = time.perf_counter()
   for _ in range(steps):
     one()
   _, last = trainer.drain()
   torch.cuda.synchronize()
   dt = time.perf_counter() - t0
+  if dist is not None:  # the slowest rank's clock
+    slowest = torch.tensor([dt], device='cuda', dtype=torch.float64)
+    dist.all_reduce(slowest, op=dist.ReduceOp.MAX)
+    dt = float(slowest.item())
   assert last == steps + 20 - 1, (last, steps)
   wl.native.check(wl.lib.b2r_check(wl.h, stream))
   row = 7056 + 16  # staged row: frame + action + reward + terminal (padded)
-  h2d = update_period * row + (online_h.numel() + target_h.numel()) * 4
-  d2h = batch * 4
+  h2d = world * (update_period * row + (online_h.numel() + target_h.numel()) * 4)
+  d2h = world * (batch + 1) * 4
   return {'value': round(batch * steps / dt, 1), 'unit': UNIT,
           'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
           'ms_per_step': round(dt * 1e3 / steps, 4), 'steps': steps,
@@ -474,7 +488,7 @@ def measure_full_train_step(torch, wl, batch, steps, ddp=False):
           'transitions_per_s': round(batch * steps / (ms * 1e-3), 1),
           'ms_per_update': round(ms / steps, 4), 'wall_ms_per_update':
           round(wall * 1e3 / steps, 4), 'batch': batch, 'steps': steps,
-          'last_loss': round(float(loss), 5),
+          'last_loss': round(float(loss.detach()), 5),
           'what': 'sample+gather -> conv nets (cuDNN, fp32/TF32) -> fused C51 loss '
                   '-> backward -> Adam -> set_priority; eager PyTorch host loop'}
 
@@ -748,8 +762,23 @@ def main():
       'gpu_launches': int(launches_per_step * args.steps),
       'clocks': clocks.summary(),
   }
+  # N > 1: the end-to-end loop and the full train step run on every rank together
+  e2e_multi, full_multi = None, None
+  if world > 1 and not args.no_e2e:
+    e2e_multi = measure_e2e(torch, wl, args.batch * world,
+                            max(50, min(args.steps, 3000)), dist=dist, world=world,
+                            rank=rank)
+    e2e_multi['what'] += ('; %d ranks, each over its own shard, global batch %d, shard '
+                          'totals over peer memory' % (world, args.batch * world))
+    full = measure_full_train_step(torch, wl, args.batch, 100, ddp=True)
+    full['transitions_per_s'] = round(full['transitions_per_s'] * world, 1)
+    full['what'] += '; DistributedDataParallel over %d ranks (NCCL), one shard each' % world
+    full_multi = {str(args.batch): full}
   if rank == 0:
     line['roofline'] = measure_gather_roofline(torch, wl, args.batch, peak_gbs)
+    if e2e_multi is not None:
+      line['e2e'] = e2e_multi
+      line['full_train_step'] = full_multi
     if sweep_batches and world == 1:
       sweep = {}
       for b in sweep_batches:

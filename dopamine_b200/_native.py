@@ -99,6 +99,24 @@ class C51Args(ctypes.Structure):
   ]
 
 
+class DqnArgs(ctypes.Structure):
+  _fields_ = [
+      ('batch', c_int32),
+      ('num_actions', c_int32),
+      ('cumulative_gamma', c_float),
+      ('target_q', c_void_p),
+      ('online_q', c_void_p),
+      ('actions', c_void_p),
+      ('rewards', c_void_p),
+      ('terminals', c_void_p),
+      ('loss', c_void_p),
+      ('target', c_void_p),
+      ('mean_loss', c_void_p),
+      ('grad_q', c_void_p),
+      ('batch_count', c_void_p),
+  ]
+
+
 class TrainerConfig(ctypes.Structure):
   _fields_ = [
       ('batch', c_int32),
@@ -188,6 +206,7 @@ SIGNATURES = {
     'b2r_c51_project': (c_int, [c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
     'b2r_c51_loss': (c_int, [P(C51Args), c_void_p]),
+    'b2r_dqn_loss': (c_int, [P(DqnArgs), c_void_p]),
     'b2r_train_step_device': (c_int, [c_void_p, c_int32, c_uint64, c_uint64,
                                       P(Batch), P(C51Args), c_void_p]),
     'b2r_train_step_sharded_device': (c_int, [
@@ -208,6 +227,8 @@ SIGNATURES = {
     'b2r_trainer_destroy': (c_int, [c_void_p]),
     'b2r_trainer_step_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
                                       P(c_int64), c_void_p]),
+    'b2r_trainer_set_exchange': (c_int, [c_void_p, c_void_p]),
+    'b2r_trainer_last_rows': (c_int32, [c_void_p]),
     'b2r_trainer_drain': (c_int, [c_void_p, c_void_p, P(c_int64), c_void_p]),
     'b2r_trainer_views': (c_int, [c_void_p, P(Batch), P(C51Args)]),
 }

@@ -334,6 +334,18 @@ class ReplayTrainer(object):
       self._lib.b2r_trainer_destroy(self._h)
       self._h = None
 
+  def set_exchange(self, exchange):
+    """Makes this the trainer of one shard of a sharded replay
+    (`sharded_replay.PeerExchange`): `batch_size` becomes the GLOBAL batch, this
+    rank's rows come first and `last_rows` counts them."""
+    _native.check(self._lib.b2r_trainer_set_exchange(self._h, exchange._h))  # pylint: disable=protected-access
+    self._exchange = exchange  # keep it alive
+
+  @property
+  def last_rows(self):
+    """Rows of the step reported by the last step() / drain()."""
+    return int(self._lib.b2r_trainer_last_rows(self._h))
+
   def step_pointers(self, online_ptr, target_ptr, stream=None):
     """As `step`, from raw host addresses (no per-call Python work)."""
     status = self._lib.b2r_trainer_step_host(

@@ -104,6 +104,11 @@ struct b2r_trainer {
   cudaStream_t copy = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr};
   cudaEvent_t ev_loss[2] = {nullptr, nullptr};
+  // sharded mode
+  b2r_exchange *exchange = nullptr;
+  int32_t *slots = nullptr;   // device [batch]: stratum of every local row
+  int32_t *count = nullptr;   // device: local rows of the step (lives behind `loss`)
+  int32_t last_rows = 0;
   // graph mode: the step's kernels captured once per logits set
   cudaStream_t cap = nullptr;
   cudaGraphExec_t exec[2] = {nullptr, nullptr};
@@ -149,9 +154,10 @@ int collect(b2r_trainer *t, int64_t step, float *loss_out, int64_t *loss_step) {
   }
   const int slot = (int)(step % t->ring);
   B2R_CUDA(cudaEventSynchronize(t->ev_done[slot]));
-  if (loss_out)
-    memcpy(loss_out, t->ring_host + (size_t)slot * t->cfg.batch,
-           (size_t)t->cfg.batch * sizeof(float));
+  const float *row = t->ring_host + (size_t)slot * (t->cfg.batch + 1);
+  if (loss_out) memcpy(loss_out, row, (size_t)t->cfg.batch * sizeof(float));
+  t->last_rows = t->cfg.batch;
+  if (t->exchange) memcpy(&t->last_rows, row + t->cfg.batch, sizeof(int32_t));
   if (loss_step) *loss_step = step;
   return B2R_OK;
 }
@@ -215,8 +221,8 @@ int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
   };
   const size_t o_action = seg(B * 4), o_reward = seg(B * 4), o_naction = seg(B * 4),
                o_nreward = seg(B * 4), o_term = seg(B), o_idx = seg(B * 4),
-               o_prob = seg(B * 4), o_loss = seg(B * 4), o_prio = seg(B * 4),
-               o_w = seg(B * 4);
+               o_prob = seg(B * 4), o_loss = seg((B + 1) * 4), o_prio = seg(B * 4),
+               o_w = seg(B * 4), o_slots = seg(B * 4);
   size_t o_extra[B2R_MAX_EXTRAS];
   for (int e = 0; e < b->cfg.num_extras; ++e)
     o_extra[e] = seg(B * (size_t)b->cfg.extra_bytes[e]);
@@ -242,6 +248,8 @@ int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
   t->c51.loss = reinterpret_cast<float *>(t->scalars + o_loss);
   t->c51.priorities = reinterpret_cast<float *>(t->scalars + o_prio);
   t->c51.weights = reinterpret_cast<float *>(t->scalars + o_w);
+  t->slots = reinterpret_cast<int32_t *>(t->scalars + o_slots);
+  t->count = reinterpret_cast<int32_t *>(t->c51.loss + B);  // copied back with the losses
 
   B2R_CUDA(cudaStreamCreateWithFlags(&t->copy, cudaStreamNonBlocking));
   B2R_CUDA(cudaStreamCreateWithFlags(&t->cap, cudaStreamNonBlocking));
@@ -251,7 +259,7 @@ int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
   }
   t->ring = cfg->pipeline_depth + 1;
   B2R_CUDA(cudaMallocHost(reinterpret_cast<void **>(&t->ring_host),
-                          (size_t)t->ring * B * sizeof(float)));
+                          (size_t)t->ring * (B + 1) * sizeof(float)));
   t->ev_done.resize(t->ring);
   for (int k = 0; k < t->ring; ++k)
     B2R_CUDA(cudaEventCreateWithFlags(&t->ev_done[k], cudaEventDisableTiming));
@@ -299,7 +307,14 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   B2R_CUDA(cudaMemcpyAsync(t->logits[set][1], target_logits, logit_bytes,
                            cudaMemcpyHostToDevice, t->copy));
   B2R_CUDA(cudaEventRecord(t->ev_in[set], t->copy));
-  if (t->cfg.use_graph && n >= 2) {
+  if (t->exchange) {
+    b2r_c51_args c51 = t->c51;
+    c51.online_logits = t->logits[set][0];
+    c51.target_logits = t->logits[set][1];
+    b2r::ShardSpec shard = {t->exchange, t->slots, t->count};
+    B2R_TRY(b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch, &c51, s,
+                            t->ev_in[set], t->ev_loss[set], &shard));
+  } else if (t->cfg.use_graph && n >= 2) {
     // Everything host-dependent (staged adds, validity context) goes first, eagerly;
     // the replayed graph reads it from HBM.
     B2R_TRY(b2r::flush_queue(t->buf, s, t->cfg.batch > 64));
@@ -319,13 +334,23 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   // result: per-row losses into this step's pinned slot (copy stream, after the loss)
   const int slot = (int)(n % t->ring);
   B2R_CUDA(cudaStreamWaitEvent(t->copy, t->ev_loss[set], 0));
-  B2R_CUDA(cudaMemcpyAsync(t->ring_host + (size_t)slot * t->cfg.batch, t->c51.loss,
-                           (size_t)t->cfg.batch * sizeof(float),
+  B2R_CUDA(cudaMemcpyAsync(t->ring_host + (size_t)slot * (t->cfg.batch + 1),
+                           t->c51.loss, (size_t)(t->cfg.batch + 1) * sizeof(float),
                            cudaMemcpyDeviceToHost, t->copy));
   B2R_CUDA(cudaEventRecord(t->ev_done[slot], t->copy));
   t->submitted = n + 1;
   return collect(t, n - t->cfg.pipeline_depth, loss_out, loss_step);
 }
+
+int b2r_trainer_set_exchange(b2r_trainer *t, b2r_exchange *x) {
+  if (!t || !x) return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (t->submitted != 0)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "set the exchange before the first step");
+  t->exchange = x;
+  return B2R_OK;
+}
+
+int32_t b2r_trainer_last_rows(const b2r_trainer *t) { return t ? t->last_rows : 0; }
 
 int b2r_trainer_drain(b2r_trainer *t, float *loss_out, int64_t *loss_step,
                       b2r_stream stream) {

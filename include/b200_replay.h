@@ -377,6 +377,25 @@ typedef struct {
  * weights in one launch (RA:200-293). */
 int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream);
 
+/* DQN (dqn_agent.py:283-322): Bellman target r + gamma^n max_a Q_target(s') (1 - t),
+ * Huber loss (delta 1) against Q_online(s, a), optional mean and gradient.  f32,
+ * DEVICE pointers, asynchronous. */
+typedef struct {
+  int32_t batch, num_actions;
+  float cumulative_gamma;       /* f32(pow(gamma, n))               DQ:175 */
+  const float *target_q;        /* (B, A) target net on next_state  DQ:291-292 */
+  const float *online_q;        /* (B, A) online net on state       DQ:308-312 */
+  const int32_t *actions;       /* (B,)                                         */
+  const float *rewards;         /* (B,) n-step returns                          */
+  const uint8_t *terminals;     /* (B,)                                         */
+  float *loss;                  /* (B,) Huber loss per row or NULL  DQ:315-316  */
+  float *target;                /* (B,) Bellman target or NULL      DQ:299-300  */
+  float *mean_loss;             /* scalar or NULL                   DQ:321      */
+  float *grad_q;                /* (B, A) d mean(loss)/d online_q or NULL       */
+  const int32_t *batch_count;   /* NULL, or DEVICE count <= batch of rows       */
+} b2r_dqn_args;
+int b2r_dqn_loss(const b2r_dqn_args *args, b2r_stream stream);
+
 /* ------------------------------------------------------------------------- */
 /* The whole hot path in one call (what one sess.run(train_op)   */
 /* does around the network): PRB:142-201 -> RA:200-293 -> PRB:203-214.          */
@@ -440,6 +459,13 @@ int b2r_trainer_destroy(b2r_trainer *trainer);
 int b2r_trainer_step_host(b2r_trainer *trainer, const float *online_logits,
                           const float *target_logits, float *loss_out,
                           int64_t *loss_step, b2r_stream stream);
+/* Sharded trainer (one per rank): the configured batch becomes the GLOBAL batch of
+ * b2r_train_step_sharded_device, this rank's rows are compacted at the front of the
+ * batch and of loss_out, and b2r_trainer_last_rows() tells how many of them the step
+ * reported by the last step_host / drain call had.  Call before the first step; the
+ * sharded trainer always launches eagerly (use_graph is ignored). */
+int b2r_trainer_set_exchange(b2r_trainer *trainer, b2r_exchange *exchange);
+int32_t b2r_trainer_last_rows(const b2r_trainer *trainer);
 /* Waits for everything queued; loss_out / *loss_step describe the last step. */
 int b2r_trainer_drain(b2r_trainer *trainer, float *loss_out, int64_t *loss_step,
                       b2r_stream stream);

@@ -451,3 +451,47 @@ def test_tma_gather_variant_passes_the_gather_parity_suite():
       cwd=root, env=env, capture_output=True, text=True, timeout=900)
   assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
   assert ' passed' in out.stdout
+
+
+def test_sharded_trainer_matches_oracles(gpu):
+  """The host-facing trainer on two emulated shards: every update's local rows (batch
+  columns, losses handed back through pinned memory, write-back) against the
+  oracles; the two ranks' rows partition the global batch."""
+  from dopamine_b200.replay_memory import sharded_replay
+  torch = gpu.torch
+  cap, global_batch, world = 50000, 64, 2
+  shards = [_filled(gpu, cap, 32, seed=60 + g, hot=False) for g in range(world)]
+  exchanges = sharded_replay.PeerExchange.emulated(world)
+  trainers = []
+  for g in range(world):
+    t = gpu.ra.ReplayTrainer(shards[g][0], ACTIONS, ATOMS, 10., batch_size=global_batch,
+                             pipeline_depth=0, seed=5)
+    t.set_exchange(exchanges[g])
+    trainers.append(t)
+  rng = np.random.RandomState(6)
+  for step in range(4):
+    online = rng.randn(global_batch, ACTIONS, ATOMS).astype(np.float32)
+    target = rng.randn(global_batch, ACTIONS, ATOMS).astype(np.float32)
+    for g in range(world):
+      exchanges[g].publish(shards[g][0])
+    total_rows = 0
+    for g in range(world):
+      mem, tree, cols = shards[g]
+      loss, done = trainers[g].step(online, target)
+      assert done == step
+      n = trainers[g].last_rows
+      total_rows += n
+      torch.cuda.synchronize()
+      transition, out = trainers[g].views()
+      got = [transition[k][:n] for k in (
+          'state', 'action', 'reward', 'next_state', 'next_action', 'next_reward',
+          'terminal', 'indices', 'sampling_probabilities')]
+      dev = {k: v[:n] for k, v in out.items()}
+      if n:
+        _check_step(gpu, mem, tree, cols, cap, 3, got, dev, online[:n], target[:n])
+        assert loss[:n].tobytes() == dev['loss'].cpu().numpy().tobytes()
+      gpu.native.check(gpu.native.lib().b2r_check(mem._h, gpu.native.current_stream()))
+    assert total_rows == global_batch, step
+  for mem, tree, _ in shards:
+    for l, level in enumerate(mem.sum_tree.nodes):
+      assert np.array_equal(level.view(np.uint64), tree.level(l).view(np.uint64)), l
