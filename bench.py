@@ -459,7 +459,7 @@ def measure_e2e(torch, wl, batch, steps, update_period=4, pipeline_depth=2,
                    % (update_period, pipeline_depth))}
 
 
-def measure_full_train_step(torch, wl, batch, steps, ddp=False):
+def measure_full_train_step(torch, wl, batch, steps, ddp=False, cuda_graph=False):
   """BASELINE config 5: the whole Rainbow update on the synthetic Atari shape —
   fused sample + gather feeding the cuDNN Nature-DQN distribution network (online on
   state, target on next_state), fused C51 loss, backward, Adam, priority write-back
@@ -469,7 +469,8 @@ def measure_full_train_step(torch, wl, batch, steps, ddp=False):
   saved = (mem._output, mem._reuse_outputs, mem._batch_size)  # pylint: disable=protected-access
   mem._output, mem._reuse_outputs, mem._batch_size = 'torch', True, batch  # pylint: disable=protected-access
   learner = agent.RainbowLearner(NUM_ACTIONS, batch_size=batch, memory=mem, ddp=ddp,
-                                 update_horizon=HORIZON, gamma=GAMMA, vmax=VMAX)
+                                 update_horizon=HORIZON, gamma=GAMMA, vmax=VMAX,
+                                 cuda_graph=cuda_graph)
   for _ in range(10):
     learner.train_step()
   torch.cuda.synchronize()
@@ -490,7 +491,9 @@ def measure_full_train_step(torch, wl, batch, steps, ddp=False):
           round(wall * 1e3 / steps, 4), 'batch': batch, 'steps': steps,
           'last_loss': round(float(loss.detach()), 5),
           'what': 'sample+gather -> conv nets (cuDNN, fp32/TF32) -> fused C51 loss '
-                  '-> backward -> Adam -> set_priority; eager PyTorch host loop'}
+                  '-> backward -> Adam -> set_priority; ' + (
+                      'whole update replayed as one CUDA graph' if cuda_graph else
+                      'eager PyTorch host loop')}
 
 
 def measure_e2e_host_batch(torch, wl, batch, steps):
@@ -802,6 +805,10 @@ def main():
     if not args.no_e2e and world == 1:
       line['full_train_step'] = {
           str(b): measure_full_train_step(torch, wl, b, 200 if b <= 256 else 50)
+          for b in ([args.batch] + ([256] if sweep_batches else []))}
+      line['full_train_step_graph'] = {
+          str(b): measure_full_train_step(torch, wl, b, 200 if b <= 256 else 50,
+                                          cuda_graph=True)
           for b in ([args.batch] + ([256] if sweep_batches else []))}
     if not args.no_cpu_baseline and world == 1:
       line['cpu_baseline'] = cpu_baseline(args.batch, args.capacity)

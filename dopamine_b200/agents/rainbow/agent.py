@@ -87,7 +87,8 @@ class RainbowLearner(object):
                num_atoms=51, vmax=10., gamma=0.99, update_horizon=3,
                replay_capacity=1000000, batch_size=32, target_update_period=8000,
                update_period=4, replay_scheme='prioritized', learning_rate=6.25e-5,
-               adam_epsilon=1.5e-4, seed=0, ddp=False, memory=None):
+               adam_epsilon=1.5e-4, seed=0, ddp=False, memory=None,
+               cuda_graph=False):
     torch = _torch()
     if replay_scheme not in ('prioritized', 'uniform'):
       raise ValueError('Invalid replay scheme: {}'.format(replay_scheme))
@@ -116,8 +117,19 @@ class RainbowLearner(object):
       from torch.nn.parallel import DistributedDataParallel  # pylint: disable=g-import-not-at-top
       self._net = DistributedDataParallel(
           self.online, device_ids=[torch.cuda.current_device()])
+    # cuda_graph: the whole update (replay kernels, both networks, backward, Adam,
+    # write-back) is captured once and replayed: one launch per update instead of
+    # ~150 eager ones.  Staged adds are flushed before every replay; the sampler's
+    # validity context and draw counter live on the device, so the replayed graph
+    # sees new transitions and draws fresh strata.
+    if cuda_graph and ddp:
+      raise NotImplementedError('cuda_graph is not combined with ddp')
+    self._cuda_graph = bool(cuda_graph)
+    self._graph = None
+    self._static_loss = None
     self.optimizer = torch.optim.Adam(self.online.parameters(), lr=learning_rate,
-                                      eps=adam_epsilon)  # rainbow.gin:21-25
+                                      eps=adam_epsilon,  # rainbow.gin:21-25
+                                      capturable=self._cuda_graph)
     self.training_steps = 0
     self.updates = 0
 
@@ -139,6 +151,30 @@ class RainbowLearner(object):
   # -- the train op (rainbow_agent.py:253-305) ---------------------------------------
   def train_step(self):
     """One update; returns the scalar training loss (a CUDA tensor, no sync)."""
+    if not self._cuda_graph:
+      return self._update()
+    if self._graph is None:
+      self._capture()
+    self.memory._flush()  # pylint: disable=protected-access
+    self._graph.replay()
+    self.updates += 1
+    return self._static_loss
+
+  def _capture(self):
+    torch = _torch()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      for _ in range(3):  # lazy allocations, cuDNN algorithm selection, Adam state
+        self._update()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    self.memory._flush()  # pylint: disable=protected-access
+    self._graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(self._graph):
+      self._static_loss = self._update()
+
+  def _update(self):
     torch = _torch()
     batch = self.memory.sample_transition_batch(self.batch_size)
     (state, action, reward, next_state, _, _, terminal, indices, probs) = batch[:9]
@@ -154,7 +190,8 @@ class RainbowLearner(object):
     self.optimizer.step()
     if self.replay_scheme == 'prioritized':  # rainbow_agent.py:289-295
       self.memory.set_priority(indices, priorities)
-    self.updates += 1
+    if not self._cuda_graph or self._graph is None:
+      self.updates += 1
     return loss
 
   def sync_target(self):

@@ -114,9 +114,7 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   const int N = a.u.num_atoms, A = a.u.num_actions, W = a.warps;
   float *bestp = smem + (size_t)warp * N;        // [W][N] best action's probs
   float *sup = smem + (size_t)W * N;             // [N] Bellman support
-  int *win_base = reinterpret_cast<int *>(sup + N);  // [N] first atom of j's window
-  float *contrib = sup + 2 * N;                  // [N][4] hat(i, j) * p_j in the window
-  float *tgt = contrib + 4 * N;                  // [N] projected target
+  float *tgt = sup + N;                          // [N] projected target
   float *onl = tgt + N;                          // [N] chosen online logits
   float *zs = onl + N;                           // [N] the support, staged
   __shared__ float s_q[32];
@@ -241,40 +239,36 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   const float z0 = zs[0], zlast = zs[N - 1];
   const float dz = __fsub_rn(zs[1], zs[0]);
   // The dense form sums hat(i, j) * p_j over all j, but hat is exactly 0 unless
-  // |clip(s_j) - z_i| < dz, i.e. for at most the atoms next to s_j: evaluate the
-  // reference's expression only inside a window of `span` atoms around s_j (wide
-  // enough for any rounding of the window position), then add each atom's
-  // contributions in ascending j.  Adding the skipped +0 terms changes nothing.
-  const int span = N < 4 ? N : 4;
+  // |clip(s_j) - z_i| < dz.  The Bellman atoms s_j = r + g * z_j are non-decreasing
+  // in j (g = gamma^n (1 - terminal) >= 0), so the j that can reach atom i form one
+  // interval: those with s_j inside (z_i - dz, z_i + dz), open-ended below for the
+  // first atom and above for the last one (clipping).  Each thread evaluates the
+  // reference's expression over a conservative superset of its interval (two extra
+  // positions either side cover any rounding of the bounds; terminal rows, where all
+  // s_j coincide, take the whole range) in ascending j.  Skipped terms are exact
+  // zeros, so the sum is the dense form's.
 #pragma unroll 1
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    const float clipped = fminf(fmaxf(sup[j], z0), zlast);
-    int l = (int)floorf(__fdividef(clipped - z0, dz)) - 1;
-    l = max(0, min(l, N - span));
-    win_base[j] = l;
-    const float pj = next_p[j];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float zi = zs[i];
+    int jl = 0, jh = N - 1;
+    if (gwt > 0.f) {
+      // s_j > zi - dz  <=>  j > ((zi - dz - r) / g - z0) / dz
+      const float inv = __fdividef(1.0f, gwt * dz);
+      const float lo = (zi - dz - r - gwt * z0) * inv;
+      const float hi = (zi + dz - r - gwt * z0) * inv;
+      if (i > 0 && lo > 2.f) jl = min(N - 1, (int)fminf(lo, 1e6f) - 2);
+      if (i < N - 1 && hi < (float)(N - 3)) jh = max(0, (int)fmaxf(hi, -1e6f) + 3);
+    }
+    float acc = 0.f;
 #pragma unroll 1
-    for (int k = 0; k < span; ++k) {
-      const float gap = fabsf(__fsub_rn(clipped, zs[l + k]));
-      float c = 0.f;
+    for (int j = jl; j <= jh; ++j) {
+      const float clipped = fminf(fmaxf(sup[j], z0), zlast);
+      const float gap = fabsf(__fsub_rn(clipped, zi));
       if (gap < dz) {
         float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
         hat = fminf(fmaxf(hat, 0.f), 1.f);
-        c = __fmul_rn(hat, pj);
+        acc = __fadd_rn(acc, __fmul_rn(hat, next_p[j]));
       }
-      contrib[4 * j + k] = c;
-    }
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    float acc = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < N; ++j) {
-      const int k = i - win_base[j];
-      const bool in = (unsigned)k < (unsigned)span;
-      const float c = contrib[4 * j + (in ? k : 0)];
-      acc = __fadd_rn(acc, in ? c : 0.f);
     }
     tgt[i] = acc;
     if (a.u.target) a.u.target[(size_t)b * N + i] = acc;
@@ -415,7 +409,7 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
   a.warps = args->num_actions < 32 ? args->num_actions : 32;
   if (args->batch > 256) a.warps = (a.warps + 2) / 3;
   const int threads = a.warps * 32;
-  const size_t smem = ((size_t)a.warps + 9) * args->num_atoms * sizeof(float);
+  const size_t smem = ((size_t)a.warps + 4) * args->num_atoms * sizeof(float);
   if (smem > 48 * 1024 || args->num_atoms > 32 * b2r::kMaxAtomsPerLane)
     return fail(B2R_ERR_UNSUPPORTED, "num_atoms above 128 is not supported");
   if (args->batch > b2r::g_weighted_cap) {

@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V
 #pragma unroll 1
   for (int p = lane; p < n_eff; p += 32) sorted_delta[p] = vals[(uint32_t)keys[p]];
   __syncwarp();
+  B2R_MARK(8);
 #pragma unroll 1
   for (int p = lane; p < n_eff; p += 32) {
     const uint32_t node = (uint32_t)(keys[p] >> 32);
@@ -505,8 +506,10 @@ __global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V
       const int mid = (lo + hi) >> 1;
       if ((uint32_t)(keys[mid] >> 32) > node) hi = mid; else lo = mid + 1;
     }
+    B2R_MARK(9);
 #pragma unroll 4
     for (int q = p; q < lo; ++q) acc = __dadd_rn(acc, sorted_delta[q]);
+    B2R_MARK(10);
     a.heap[base + node] = acc;
   }
   B2R_MARK(7);
