@@ -12,8 +12,11 @@ Drop-in for the hot-path pieces of `dopamine/agents/rainbow/rainbow_agent.py`:
   * `C51Loss` — the same as a differentiable torch op, so the conv Q-network
     (cuDNN through PyTorch, the only dense contraction on the path) trains on it.
 
-The agent class `RainbowAgent` (host glue: epsilon-greedy acting, update cadence,
-target sync) lives in `dopamine_b200/agents/rainbow/agent.py`.
+  * `train_step` / `ReplayTrainer` — the whole replay-and-update step as one native
+    call on device tensors, and as one pipelined host-facing call per update.
+
+The learner that puts the conv network, Adam and the target sync around these
+(`RainbowLearner`) lives in `dopamine_b200/agents/rainbow/agent.py`.
 """
 import ctypes
 import math

@@ -3,12 +3,14 @@
 // (prioritized_replay_buffer.py:142-171), incl. SumTree.stratified_sample
 // (sum_tree.py:143-166).
 //
-// Both kernels are one CTA: the batch is at most a few thousand independent
-// root-to-leaf descents (20 dependent fp64 loads each at capacity 1M), and the
-// sequential parts of the reference — "the j-th invalid slot takes the j-th valid
-// retry draw", "stop after max_sample_attempts failures" — become block-wide
-// prefix scans (warp ballots + shuffles) over windows evaluated speculatively in
-// parallel.  Levels 0..10 of the tree are staged in shared memory first.
+// A batch is at most a few thousand independent root-to-leaf descents (20 dependent
+// fp64 loads each at capacity 1M): one CTA up to 256 strata, tiles of 128 strata over
+// many CTAs above.  The sequential parts of the reference — "the j-th invalid slot
+// takes the j-th valid retry draw", "stop after max_sample_attempts failures" — become
+// block-wide prefix scans (warp ballots + shuffles) over windows evaluated
+// speculatively in parallel, by the last CTA to finish.  Levels 0..10 of the tree are
+// staged in shared memory first.  The prioritized kernel can also write the scalar
+// columns of the batch (gather.cuh) and exchange shard totals over peer memory.
 #include "gather.cuh"
 
 namespace b2r {
