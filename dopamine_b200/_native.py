@@ -264,6 +264,28 @@ def lib():
   return _lib
 
 
+_fast = None
+
+
+def fast():
+  """The CPython fast-call shims (dopamine_b200/csrc/fastcall.c), bound to the same
+  library; built on first use like the library itself."""
+  global _fast
+  if _fast is None:
+    lib()
+    from dopamine_b200.csrc import build as _build  # pylint: disable=g-import-not-at-top
+    path = _build.fast_module_path()
+    if not os.path.exists(path):
+      _build.build_fast()
+    import importlib.util  # pylint: disable=g-import-not-at-top
+    spec = importlib.util.spec_from_file_location('_b2rfast', path)
+    module = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(module)
+    module.bind(LIB_PATH)
+    _fast = module
+  return _fast
+
+
 def last_error():
   return lib().b2r_last_error().decode('utf-8', 'replace')
 

@@ -331,6 +331,9 @@ class ReplayTrainer(object):
     self._loss_ptr = self._loss.ctypes.data
     self._step = ctypes.c_int64(-1)
     self._step_ref = ctypes.byref(self._step)
+    self._step_addr = ctypes.addressof(self._step)
+    self._fast_step = _native.fast().trainer_step
+    self._h_int = self._h.value
 
   def __del__(self):
     if getattr(self, '_h', None):
@@ -351,8 +354,8 @@ class ReplayTrainer(object):
 
   def step_pointers(self, online_ptr, target_ptr, stream=None):
     """As `step`, from raw host addresses (no per-call Python work)."""
-    status = self._lib.b2r_trainer_step_host(
-        self._h, online_ptr, target_ptr, self._loss_ptr, self._step_ref,
+    status = self._fast_step(
+        self._h_int, online_ptr, target_ptr, self._loss_ptr, self._step_addr,
         _native.current_stream() if stream is None else stream)
     if status:
       _native.check(status)

@@ -35,6 +35,26 @@ def _stale(target, deps):
 
 
 TRACE_LIB = os.path.join(ROOT, 'profiles', 'micro', 'libb200replay_trace.so')
+FAST_SRC = os.path.join(HERE, 'fastcall.c')
+
+
+def fast_module_path():
+  import sysconfig
+  return os.path.join(PKG, '_b2rfast' + (sysconfig.get_config_var('EXT_SUFFIX') or '.so'))
+
+
+def build_fast(force=False, verbose=False):
+  """Compiles the CPython fast-call shims (gcc; no CUDA, no link to the library)."""
+  import sysconfig
+  target = fast_module_path()
+  if not force and not _stale(target, [FAST_SRC, __file__]):
+    return target
+  cmd = ['gcc', '-O2', '-shared', '-fPIC', '-I', sysconfig.get_paths()['include'],
+         FAST_SRC, '-o', target, '-ldl']
+  if verbose:
+    print(' '.join(cmd), file=sys.stderr)
+  subprocess.check_call(cmd)
+  return target
 
 
 def build(force=False, verbose=False, extra_flags=(), trace=False):
@@ -66,6 +86,8 @@ def build(force=False, verbose=False, extra_flags=(), trace=False):
     if verbose:
       print(' '.join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
+  if not trace:
+    build_fast(force=force, verbose=verbose)
   return lib_path
 
 

@@ -377,14 +377,22 @@ class OutOfGraphReplayBuffer(object):
       return False
     # No stream look-up per add: the call never launches; when the staging queue
     # is full it says so, and the flush (which launches) gets the current stream.
-    status = self._lib.b2r_add_atari(
-        self._h, observation.ctypes.data, int(action), reward, terminal, priority,
-        mode, _native.STREAM_NONE)
+    # The call goes through the CPython shim (csrc/fastcall.c): b2r_add_atari with
+    # the observation taken through the buffer protocol.
+    add_atari = self.__dict__.get('_fast_add_fn')
+    if add_atari is None:
+      add_atari = self._fast_add_fn = _native.fast().add_atari
+      self._h_int = self._h.value
+      self._obs_bytes = int(np.prod(self._fast_obs[0], dtype=np.int64))
+    action = int(action)
+    status = add_atari(self._h_int, self._obs_bytes, observation, action, reward,
+                       terminal, priority, mode, -1)
     if status == _native.QUEUE_FULL:
       _native.check(self._lib.b2r_flush(self._h, self._stream()))
-      status = self._lib.b2r_add_atari(
-          self._h, observation.ctypes.data, int(action), reward, terminal,
-          priority, mode, _native.STREAM_NONE)
+      status = add_atari(self._h_int, self._obs_bytes, observation, action, reward,
+                         terminal, priority, mode, -1)
+    if status == -1:
+      return False
     if status == _native.ERR_NEGATIVE_PRIORITY:
       raise ValueError(_native.last_error())
     if status:

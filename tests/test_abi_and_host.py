@@ -89,3 +89,17 @@ def test_product_never_imports_the_oracle():
         text = open(os.path.join(base, f)).read()
         assert 'import oracle' not in text and 'from oracle' not in text, f
         assert 'fast_oracle' not in text, f
+
+
+def test_fastcall_shim_builds_and_binds():
+  """csrc/fastcall.c: the CPython shim loads, binds the library's entry points and
+  rejects an observation of the wrong size without touching the library."""
+  fast = _native.fast()
+  assert callable(fast.add_atari) and callable(fast.trainer_step)
+  obs = np.zeros((84, 84), dtype=np.uint8)
+  # wrong byte count -> -1 (caller falls back to the general path); handle unused
+  assert fast.add_atari(0, 10, obs, 1, 0.5, 0, 1.0, 0, -1) == -1
+  # not a buffer at all -> -1 as well
+  assert fast.add_atari(0, 7056, object(), 1, 0.5, 0, 1.0, 0, -1) == -1
+  with pytest.raises(TypeError):
+    fast.add_atari(0, 7056, obs)
