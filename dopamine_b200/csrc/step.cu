@@ -13,10 +13,21 @@
 #include "gather.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
 namespace b2r {
+
+// Batch size above which the staged adds are flushed "split" (rows on the side
+// stream beside the tree update).  B2R_SPLIT_MIN overrides (experiments).
+static int split_min() {
+  static const int v = [] {
+    const char *e = std::getenv("B2R_SPLIT_MIN");
+    return e ? std::atoi(e) : 64;
+  }();
+  return v;
+}
 
 // One shard of a sharded replay: `batch` is then the GLOBAL batch, this rank's rows
 // are compacted at the front of `out` and counted on the device.
@@ -51,7 +62,7 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   // Staged adds: at the agent's batch of 32 a host loop is bound by the number of
   // driver calls, so everything goes on `s`; at larger batches the device chain is
   // the bound and the rows are written on the side stream beside the tree update.
-  B2R_TRY(flush_queue(b, s, batch > 64));
+  B2R_TRY(flush_queue(b, s, batch > split_min()));
   if (shard)
     B2R_TRY(launch_sample_sharded(
         b, batch, shard->exchange->world, shard->exchange->rank, nullptr,
@@ -195,6 +206,7 @@ int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
   if (!t) return fail(B2R_ERR_INVALID_ARGUMENT, "out of host memory");
   t->buf = b;
   t->cfg = *cfg;
+  if (const char *e = std::getenv("B2R_TRAINER_GRAPH")) t->cfg.use_graph = std::atoi(e);
   const size_t B = (size_t)cfg->batch, A = (size_t)cfg->num_actions,
                N = (size_t)cfg->num_atoms;
   const size_t logit_bytes = B * A * N * sizeof(float);
@@ -317,7 +329,7 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   } else if (t->cfg.use_graph && n >= 2) {
     // Everything host-dependent (staged adds, validity context) goes first, eagerly;
     // the replayed graph reads it from HBM.
-    B2R_TRY(b2r::flush_queue(t->buf, s, t->cfg.batch > 64));
+    B2R_TRY(b2r::flush_queue(t->buf, s, t->cfg.batch > b2r::split_min()));
     B2R_TRY(b2r::ensure_ctx(t->buf, s));
     if (!t->exec[set]) B2R_TRY(capture_step(t, set));
     B2R_CUDA(cudaStreamWaitEvent(s, t->ev_in[set], 0));
