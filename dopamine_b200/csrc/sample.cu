@@ -52,6 +52,11 @@ struct PerSampleArgs {
   float *tile_min;      // scratch [n_tiles]
   float *min_prob_out;  // nullable
   int32_t *count_out;   // nullable: number of rows this launch produced
+  // Sharded + Philox + large batch: stratified queries grow with the stratum index
+  // and the rank-order scan is monotone, so a rank's strata are ONE index range
+  // [lo, hi).  Every CTA finds the range with a parallel k-ary search and then works
+  // on a tile of it: the sharded sampler scales over CTAs like the plain one.
+  int shard_ranges;
   // Shard totals over peer memory instead of shard_totals (see exchange_totals).
   ExchangeArgs xchg;
 };
@@ -158,6 +163,7 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
   __shared__ int warp_counts[32];
   __shared__ float warp_mins[32];
   __shared__ double s_totals[kMaxShards];
+  __shared__ int s_first[2];
   __shared__ int s_draws_used, s_last_idx, s_last_valid, s_is_last;
   __shared__ int tile_start[kMaxTiles + 1];
 
@@ -186,13 +192,17 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
   const int top_depth = stage_top_levels(a.heap, a.depth, top);
   B2R_MARK(2);
   const double local_total = top[1];  // root of the 1-based heap
+  // The first tile's uniforms need no totals: drawn while the peers' totals travel.
+  const int first_i = blockIdx.x * blockDim.x + threadIdx.x;
+  double first_u = 0.0;
+  if (a.use_philox && first_i < a.batch)
+    first_u = philox_uniform53(a.seed, draw_offset, (uint64_t)first_i);
   const double *shard_totals = a.shard_totals;
   if (exchange) {
     exchange_collect(a.xchg, a.num_shards, a.rank, local_total, xseq, s_totals,
                      a.latched);
     __syncthreads();
     shard_totals = s_totals;
-    if (threadIdx.x == 0) *a.xchg.seq = xseq;
   }
   // Mass the strata are spread over: the root, or all shards' roots summed in
   // rank order (fp64, left to right).
@@ -203,13 +213,17 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
       grand_total = __dadd_rn(grand_total, shard_totals[g]);
   }
   if (grand_total == 0.0 || (a.num_shards == 1 && local_total == 0.0)) {
-    // sum_tree.py:159-160 (every CTA takes this branch together)
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // sum_tree.py:159-160 (every CTA takes this branch together; the last one to
+    // arrive advances the step counters, which every CTA read on entry)
+    if (threadIdx.x == 0 &&
+        (gridDim.x == 1 || atomicAdd(a.ticket, 1u) == gridDim.x - 1)) {
+      if (gridDim.x > 1) *a.ticket = 0u;
       a.info[0] = B2R_ERR_EMPTY_TREE;
       a.info[1] = 0; a.info[2] = 0; a.info[3] = 0;
       if (a.count_out) *a.count_out = 0;
       if (a.min_prob_out) *a.min_prob_out = INFINITY;
       if (a.counter) *a.counter = draws_before + 1;  // ranks stay in lockstep
+      if (exchange) *a.xchg.seq = xseq;
       if (a.latched && a.latched[0] == 0) a.latched[0] = B2R_ERR_EMPTY_TREE;
     }
     return;
@@ -222,32 +236,87 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
 
   // ---- stratified pass (sum_tree.py:162-166 + prioritized_replay_buffer.py:155)
   const int tile_size = blockDim.x;
-  const int n_tiles = (a.batch + tile_size - 1) / tile_size;
   const double step = 1.0 / (double)a.batch;  // np.linspace(0, 1, batch + 1)
-  int mine_base = 0;  // running output position (single-CTA / sharded mode)
+  // Owner of stratum i under the rank-order scan (ST:128-139 applied to the shard
+  // totals) and the mass left inside the owning shard.
+  auto stratum_owner = [&](int i, double u, double *residual) {
+    double q01;
+    if (a.use_philox) {
+      const double lo = __dmul_rn((double)i, step);
+      const double hi = (i + 1 == a.batch) ? 1.0 : __dmul_rn((double)(i + 1), step);
+      q01 = __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), u));  // random.uniform
+    } else {
+      q01 = a.strat_query01[i];
+    }
+    double mass = __dmul_rn(q01, grand_total);
+    int owner = 0;
+    for (; owner < a.num_shards - 1; ++owner) {
+      const double left = shard_totals[owner];
+      if (mass < left) break;
+      mass = __dsub_rn(mass, left);
+    }
+    *residual = mass;
+    return owner;
+  };
+  // This rank's strata: everything, or (shard_ranges) the range [lo, hi) found by two
+  // simultaneous k-ary searches for the first stratum owned by a rank >= ours and the
+  // first owned by a rank > ours; blockDim candidates per round.
+  int range_lo = 0, range_hi = a.batch;
+  if (a.shard_ranges) {
+    int base[2] = {0, 0}, limit[2] = {a.batch, a.batch};
+    while (base[0] < limit[0] || base[1] < limit[1]) {
+      if (threadIdx.x < 2) s_first[threadIdx.x] = tile_size;
+      __syncthreads();
+      int cand[2], stride[2];
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int width = limit[w] - base[w];
+        stride[w] = (width + tile_size - 1) / tile_size;
+        cand[w] = base[w] + (int)threadIdx.x * stride[w];
+        if (width > 0) {
+          bool hit = cand[w] >= limit[w];  // at or past the known upper bound
+          if (!hit) {
+            double unused;
+            const int owner = stratum_owner(
+                cand[w], philox_uniform53(a.seed, draw_offset, (uint64_t)cand[w]),
+                &unused);
+            hit = w == 0 ? owner >= a.rank : owner > a.rank;
+          }
+          if (hit) atomicMin(&s_first[w], (int)threadIdx.x);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        if (base[w] >= limit[w]) continue;
+        const int t = s_first[w];  // first candidate that satisfies the predicate
+        const int hit = base[w] + t * stride[w];
+        const int new_limit = hit < limit[w] ? hit : limit[w];
+        // the answer lies in (previous candidate, new_limit]
+        base[w] = t == 0 ? new_limit : base[w] + (t - 1) * stride[w] + 1;
+        if (base[w] > new_limit) base[w] = new_limit;
+        limit[w] = new_limit;
+      }
+      __syncthreads();
+    }
+    range_lo = base[0];
+    range_hi = base[1];
+  }
+  const int n_mine = range_hi - range_lo;  // strata walked by this launch's tiles
+  const int n_tiles = (n_mine + tile_size - 1) / tile_size;
+  int mine_base = 0;  // running output position (single-CTA sharded mode)
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int i = tile * tile_size + threadIdx.x;
+    const int i = range_lo + tile * tile_size + threadIdx.x;
     bool mine = false, valid = true;
     int64_t idx = 0;
     ScalarLoads row;
     const bool fast_scalars = a.with_scalars && a.sc.fast;
-    if (i < a.batch) {
-      double q01;
-      if (a.use_philox) {
-        const double lo = __dmul_rn((double)i, step);
-        const double hi = (i + 1 == a.batch) ? 1.0 : __dmul_rn((double)(i + 1), step);
-        const double u = philox_uniform53(a.seed, draw_offset, (uint64_t)i);
-        q01 = __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), u));  // random.uniform
-      } else {
-        q01 = a.strat_query01[i];
-      }
-      double mass = __dmul_rn(q01, grand_total);
-      int owner = 0;
-      for (; owner < a.num_shards - 1; ++owner) {
-        const double left = shard_totals[owner];
-        if (mass < left) break;
-        mass = __dsub_rn(mass, left);
-      }
+    if (i < range_hi) {
+      double u = 0.0;
+      if (a.use_philox)
+        u = i == first_i ? first_u : philox_uniform53(a.seed, draw_offset, (uint64_t)i);
+      double mass;
+      const int owner = stratum_owner(i, u, &mass);
       mine = (owner == a.rank);
       B2R_MARK(3);
       if (mine) {
@@ -259,8 +328,8 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
         B2R_MARK(5);
       }
     }
-    int pos = i, tile_mine = 0, tile_inv;
-    if (a.num_shards > 1) {  // compact this rank's strata (grid is 1 CTA here)
+    int pos = i - range_lo, tile_mine = 0, tile_inv;
+    if (a.num_shards > 1 && !a.shard_ranges) {  // compact (grid is 1 CTA here)
       pos = mine_base + block_scan_flag(mine, warp_counts, &tile_mine);
       mine_base += tile_mine;
     }
@@ -280,7 +349,7 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
     if (threadIdx.x == 0) a.tile_counts[tile] = tile_inv;
   }
   B2R_MARK(6);
-  const int count = a.num_shards > 1 ? mine_base : a.batch;
+  const int count = a.shard_ranges ? n_mine : (a.num_shards > 1 ? mine_base : a.batch);
 
   // ---- only the last CTA to finish goes on
   if (gridDim.x > 1) {
@@ -379,6 +448,7 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
       }
     }
     if (a.counter) *a.counter = draws_before + 1;
+    if (exchange) *a.xchg.seq = xseq;
     a.info[0] = status;
     a.info[1] = a.out_slots ? (status ? a.out_slots[fail_slot] : 0) : fail_slot;
     a.info[2] = used;
@@ -551,6 +621,7 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   a.with_scalars = scalars != nullptr;
   a.min_prob_out = min_prob_out;
   a.count_out = nullptr;
+  a.shard_ranges = 0;
   a.xchg.local = nullptr;
   if (scalars) {
     fill_scalar_args(b, scalars, &a.sc);
@@ -584,9 +655,11 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
     return fail(B2R_ERR_INVALID_ARGUMENT, "bad sharding arguments");
   if (x && !x->connected && x->world > 1)
     return fail(B2R_ERR_INVALID_ARGUMENT, "the exchange is not connected");
-  // One CTA walks every tile (the compaction of this rank's strata is sequential
-  // over tiles); 256 threads up to a global batch of 256, 1024 above.
-  const int threads = global_batch <= 256 ? 256 : 1024;
+  // Small global batches and caller-supplied queries (any order): one CTA walks
+  // every tile and compacts this rank's strata with block scans.  Philox strata of a
+  // large global batch: tiles of 128 over many CTAs (see shard_ranges).
+  const bool ranges = query01 == nullptr && global_batch > 256 && num_shards > 1;
+  const int threads = global_batch <= 256 ? 256 : (ranges ? 128 : 1024);
   const int tiles = (global_batch + threads - 1) / threads;
   if (tiles > kMaxTiles) return fail(B2R_ERR_UNSUPPORTED, "global batch too large");
   B2R_TRY(ensure_inv_slots(b, (int64_t)tiles * threads + 2 * kMaxTiles + 8));
@@ -621,6 +694,7 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
   a.with_scalars = scalars != nullptr;
   a.min_prob_out = min_prob_out;
   a.count_out = out_count;
+  a.shard_ranges = ranges ? 1 : 0;
   a.xchg.local = nullptr;
   if (x && x->world > 1) fill_exchange_args(x, &a.xchg);
   if (scalars) {
@@ -630,6 +704,8 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
   set_tree_window(b->tree->heap, (size_t)b->tree->leaves * 16);
   if (global_batch <= 256)
     B2R_CUDA(launch(per_sample_kernel<3, 256>, dim3(1), dim3(threads), 0, s, a));
+  else if (ranges)
+    B2R_CUDA(launch(per_sample_kernel<3, 256>, dim3(tiles), dim3(threads), 0, s, a));
   else
     B2R_CUDA(launch(per_sample_kernel<3, 1024>, dim3(1), dim3(threads), 0, s, a));
   B2R_LAUNCHED();

@@ -495,3 +495,53 @@ def test_sharded_trainer_matches_oracles(gpu):
   for mem, tree, _ in shards:
     for l, level in enumerate(mem.sum_tree.nodes):
       assert np.array_equal(level.view(np.uint64), tree.level(l).view(np.uint64)), l
+
+
+@pytest.mark.parametrize('num_shards,global_batch', [(4, 128), (4, 2048), (8, 4096),
+                                                     (2, 300)])
+def test_sharded_device_rng_matches_oracle(gpu, num_shards, global_batch):
+  """Throughput mode (Philox strata and retries drawn on the device), single-CTA
+  compaction (<= 256 strata) and the multi-CTA range search above: with the same
+  uniforms from the numpy Philox port, every emulated rank must serve exactly the
+  strata and indices of the CPU statement of the rule, step after step."""
+  from dopamine_b200.replay_memory import sharded_replay
+  from oracle import philox_port
+  from oracle import sharded_port
+  torch = gpu.torch
+  rng = np.random.RandomState(num_shards + global_batch)
+  ours, ports = _shard_pairs(gpu, num_shards, rng, cap=3000)
+  for g in range(num_shards):  # uneven shards
+    ids = rng.randint(0, 300, size=200).astype(np.int32)
+    pr = (np.sqrt(np.abs(rng.randn(200)) + 1e-10) * (1 + 2 * g)).astype(np.float32)
+    ours[g].set_priority(ids, pr)
+    ports[g].set_priority(ids, pr)
+  exchanges = sharded_replay.PeerExchange.emulated(num_shards)
+  seed = 31
+  shards = [sharded_replay.ShardedPrioritizedReplay(
+      ours[g], rank=g, world_size=num_shards, exchange=exchanges[g], seed=seed)
+            for g in range(num_shards)]
+  budget = ours[0]._max_sample_attempts
+  for step in range(3):
+    queries = philox_port.stratified_queries(seed, step, global_batch)
+    retries = [philox_port.retry_uniforms(seed, g, step, global_batch, budget)
+               for g in range(num_shards)]
+    want = sharded_port.sharded_sample(ports, queries, retries)
+    for g in range(num_shards):
+      exchanges[g].publish(ours[g])
+    served = []
+    for g in range(num_shards):
+      slots, idx, count = shards[g].sample_index_batch(global_batch)
+      n = int(count.cpu()[0])
+      w_slots, w_idx, _ = want[g]
+      assert n == len(w_slots), (step, g, n, len(w_slots))
+      assert slots[:n].cpu().numpy().tolist() == w_slots
+      assert idx[:n].cpu().numpy().tolist() == [int(i) for i in w_idx]
+      served += w_slots
+      gpu.native.check(gpu.native.lib().b2r_check(ours[g]._h,
+                                                  gpu.native.current_stream()))
+    assert sorted(served) == list(range(global_batch))
+    for g in range(num_shards):  # the totals move between steps
+      ids = rng.randint(0, 300, size=20).astype(np.int32)
+      pr = np.sqrt(np.abs(rng.randn(20)) + 1e-10).astype(np.float32)
+      ours[g].set_priority(ids, pr)
+      ports[g].set_priority(ids, pr)

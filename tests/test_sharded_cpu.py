@@ -76,3 +76,20 @@ def test_apportion_matches_one_big_tree():
   owners = sharded_port.apportion([t.total() for t in shards], queries)
   for q, (o, mass) in zip(queries, owners):
     assert o * cap + shards[o].descend(mass) == big.descend(q * big.total())
+
+
+def test_philox_port_known_answers():
+  """oracle/philox_port.py against the Random123 known-answer vectors of
+  philox4x32_10 (kat_vectors: zero and all-ones counter/key, and the pi digits)."""
+  from oracle import philox_port as p
+  assert p.philox4x32_10((0, 0, 0, 0), (0, 0)) == (
+      0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+  assert p.philox4x32_10((0xffffffff,) * 4, (0xffffffff,) * 2) == (
+      0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+  assert p.philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344),
+                         (0xa4093822, 0x299f31d0)) == (
+      0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+  u = p.uniform53(1, 2, 3)
+  assert 0.0 <= u < 1.0
+  q = p.stratified_queries(7, 0, 16)
+  assert all(i / 16 <= q[i] < (i + 1) / 16 for i in range(16))
