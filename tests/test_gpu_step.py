@@ -283,16 +283,17 @@ def test_trainer_applies_adds_between_steps(gpu, graph):
 
 
 # ------------------------------------------------- peer-memory exchange ----
-def _shard_pairs(gpu, num_shards, rng, cap=400, shape=(8, 8)):
+def _shard_pairs(gpu, num_shards, rng, cap=400, shape=(8, 8), attempts=64,
+                 term_p=0.1):
   from oracle.replay_port import PortPrioritizedReplay
   from tests.test_gpu_parity import _fill_pair
-  kw = dict(update_horizon=3, gamma=0.99, max_sample_attempts=64)
+  kw = dict(update_horizon=3, gamma=0.99, max_sample_attempts=attempts)
   ours, ports = [], []
   for g in range(num_shards):
     o = gpu.prb.OutOfGraphPrioritizedReplayBuffer(shape, 4, cap, 8, output='torch',
                                                   **kw)
     p = PortPrioritizedReplay(shape, 4, cap, 8, **kw)
-    _fill_pair(rng, o, p, 300 + 57 * g, shape, True, term_p=0.1)
+    _fill_pair(rng, o, p, 300 + 57 * g, shape, True, term_p=term_p)
     ours.append(o)
     ports.append(p)
   return ours, ports
@@ -509,7 +510,8 @@ def test_sharded_device_rng_matches_oracle(gpu, num_shards, global_batch):
   from oracle import sharded_port
   torch = gpu.torch
   rng = np.random.RandomState(num_shards + global_batch)
-  ours, ports = _shard_pairs(gpu, num_shards, rng, cap=3000)
+  ours, ports = _shard_pairs(gpu, num_shards, rng, cap=3000, attempts=1500,
+                             term_p=0.03)
   for g in range(num_shards):  # uneven shards
     ids = rng.randint(0, 300, size=200).astype(np.int32)
     pr = (np.sqrt(np.abs(rng.randn(200)) + 1e-10) * (1 + 2 * g)).astype(np.float32)
