@@ -547,3 +547,32 @@ def test_sharded_device_rng_matches_oracle(gpu, num_shards, global_batch):
       pr = np.sqrt(np.abs(rng.randn(20)) + 1e-10).astype(np.float32)
       ours[g].set_priority(ids, pr)
       ports[g].set_priority(ids, pr)
+
+
+@pytest.mark.parametrize('batch', [32, 256, 1000, 4096])
+def test_device_rng_sampling_matches_oracle(gpu, batch):
+  """rng='device' on one buffer (one CTA up to 256 strata, tiles of 128 above): with
+  the Philox port's uniforms the CPU statement of PRB:142-171 picks the same indices,
+  retries included."""
+  from oracle import philox_port
+  from oracle import sharded_port
+  rng = np.random.RandomState(batch)
+  ours, ports = _shard_pairs(gpu, 1, rng, cap=3000, attempts=1500, term_p=0.03)
+  mem, port = ours[0], ports[0]
+  ids = rng.randint(0, 300, size=200).astype(np.int32)
+  pr = np.sqrt(np.abs(rng.randn(200)) + 1e-10).astype(np.float32)
+  mem.set_priority(ids, pr)
+  port.set_priority(ids, pr)
+  mem._rng, mem._seed = 'device', 77
+  retried = 0
+  for call in range(3):
+    got = mem.sample_index_batch(batch).cpu().numpy()
+    draw_offset = (call + 1) + call  # host offset (1, 2, 3) + device counter (0, 1, 2)
+    queries = philox_port.stratified_queries(77, draw_offset, batch)
+    retries = philox_port.retry_uniforms(77, 0, draw_offset, batch, 1500)
+    (slots, want, used), = sharded_port.sharded_sample([port], queries, [retries])
+    assert slots == list(range(batch))
+    assert got.tolist() == [int(i) for i in want], call
+    retried += used
+    gpu.native.check(gpu.native.lib().b2r_check(mem._h, gpu.native.current_stream()))
+  assert retried > 0 or batch < 100  # the retry stream was exercised
