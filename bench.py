@@ -707,7 +707,8 @@ def main():
 
   sweep_batches = [] if args.no_sweep else [256, 1024, 4096]
   wl = GpuWorkload(args.capacity,
-                   max([args.batch, args.batch * world] + sweep_batches), rank)
+                   max([args.batch * world] + [b * world for b in sweep_batches]),
+                   rank)
   wl.fused = not args.unfused
   launches_before = _native.lib().b2r_launch_count()
   wl.step(args.batch)
@@ -765,6 +766,21 @@ def main():
       'gpu_launches': int(launches_per_step * args.steps),
       'clocks': clocks.summary(),
   }
+  # N > 1: the larger batches of config 3 / 4 (per-GPU batch b, global b * N)
+  sweep_multi = None
+  if world > 1 and sweep_batches:
+    sweep_multi = {}
+    for b in sweep_batches:
+      st = sharded_replay.ShardedStep(wl, b * world, world, rank, dist,
+                                      exchange=exchange)
+      k = max(20, min(args.steps, 300))
+      ms_b = time_graph_or_eager(torch, st.step, k, 5, use_graph, dist)
+      t = torch.tensor([ms_b], device='cuda')
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms_b = float(t.item())
+      sweep_multi[str(b)] = {'global_batch': b * world,
+                             'value': round(b * world * k / (ms_b * 1e-3), 1),
+                             'ms_per_step': round(ms_b / k, 5)}
   # N > 1: the end-to-end loop and the full train step run on every rank together
   e2e_multi, full_multi = None, None
   if world > 1 and not args.no_e2e:
@@ -779,6 +795,8 @@ def main():
     full_multi = {str(args.batch): full}
   if rank == 0:
     line['roofline'] = measure_gather_roofline(torch, wl, args.batch, peak_gbs)
+    if sweep_multi is not None:
+      line['sweep'] = sweep_multi
     if e2e_multi is not None:
       line['e2e'] = e2e_multi
       line['full_train_step'] = full_multi

@@ -642,8 +642,10 @@ int b2r_set_priority_device_counted(b2r_buffer *b, int64_t max_n,
   if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
   if (max_n <= 0) return B2R_OK;
   B2R_TRY(b2r::flush_queue(b, as_stream(stream)));
+  // the count is a fraction of max_n (a shard's part of a global batch)
   return b2r::tree_apply<int32_t, float>(b->tree, max_n, indices, priorities,
-                                         nullptr, as_stream(stream), count);
+                                         nullptr, as_stream(stream), count,
+                                         max_n <= 256 ? 0 : -1);
 }
 
 int b2r_copy_total_device(b2r_buffer *b, double *dst, b2r_stream stream) {

@@ -90,8 +90,9 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   if (wait_before_loss) B2R_CUDA(cudaStreamWaitEvent(s, wait_before_loss, 0));
   B2R_TRY(b2r_c51_loss(&loss, s));
   if (loss_done) B2R_CUDA(cudaEventRecord(loss_done, s));
-  B2R_TRY((tree_apply<int32_t, float>(b->tree, batch, out->indices, loss.priorities,
-                                      nullptr, s, count)));
+  B2R_TRY((tree_apply<int32_t, float>(
+      b->tree, batch, out->indices, loss.priorities, nullptr, s, count,
+      shard ? (batch + shard->exchange->world - 1) / shard->exchange->world : -1)));
   if (frames) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join, 0));
   return B2R_OK;
 }

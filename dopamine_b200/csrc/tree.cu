@@ -563,7 +563,8 @@ int allow_big_smem(K kernel) {
 
 template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
-               const uint8_t *mode, cudaStream_t stream, const int32_t *n_dev) {
+               const uint8_t *mode, cudaStream_t stream, const int32_t *n_dev,
+               int64_t expected_n) {
   set_tree_window(t->heap, (size_t)t->leaves * 16);
   // The one-CTA kernel sorts per warp (cost ~ n log^2 n): it wins for the agent's
   // batch of 32 and loses to the radix-sorted cooperative kernel beyond ~64 entries
@@ -573,7 +574,10 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     int v = e ? std::atoi(e) : 64;
     return v < 0 ? 0 : (v > kSmallBatch ? kSmallBatch : v);
   }();
-  if (n <= small_max) {
+  // A device-side count (sharded replay) is only bounded by n on the host: the
+  // caller's expectation decides, the one-CTA kernel copes with up to kSmallBatch.
+  const int64_t likely = expected_n >= 0 ? expected_n : n;
+  if (n <= kSmallBatch && likely <= small_max) {
     // latency path: one CTA, one warp per level
     static bool small_ready = false;
     const int padded = padded_size((int)n);
@@ -652,13 +656,13 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
 
 template int tree_apply<int64_t, double>(b2r_tree *, int64_t, const int64_t *,
                                          const double *, const uint8_t *,
-                                         cudaStream_t, const int32_t *);
+                                         cudaStream_t, const int32_t *, int64_t);
 template int tree_apply<int32_t, float>(b2r_tree *, int64_t, const int32_t *,
                                         const float *, const uint8_t *,
-                                        cudaStream_t, const int32_t *);
+                                        cudaStream_t, const int32_t *, int64_t);
 template int tree_apply<int32_t, double>(b2r_tree *, int64_t, const int32_t *,
                                          const double *, const uint8_t *,
-                                         cudaStream_t, const int32_t *);
+                                         cudaStream_t, const int32_t *, int64_t);
 
 }  // namespace b2r
 

@@ -182,9 +182,11 @@ __device__ __forceinline__ int stage_top_levels(const double *__restrict__ heap,
 // Applies n sets in array order (device arrays).  mode (nullable): 1 = use the
 // running max_recorded_priority instead of values[k].
 // n_dev (nullable): device count, the effective n is min(n, *n_dev).
+// expected_n (>= 0): how many entries the caller expects when only the device knows
+// (n_dev); picks between the one-CTA and the cooperative kernel.
 template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
                const uint8_t *mode, cudaStream_t stream,
-               const int32_t *n_dev = nullptr);
+               const int32_t *n_dev = nullptr, int64_t expected_n = -1);
 
 }  // namespace b2r
