@@ -784,9 +784,11 @@ def main():
   # N > 1: the end-to-end loop and the full train step run on every rank together
   e2e_multi, full_multi = None, None
   if world > 1 and not args.no_e2e:
+    # deeper pipeline than at N = 1: every step waits for the slowest rank, so the
+    # queue has to absorb the host jitter of all ranks
     e2e_multi = measure_e2e(torch, wl, args.batch * world,
-                            max(50, min(args.steps, 3000)), dist=dist, world=world,
-                            rank=rank)
+                            max(50, min(args.steps, 3000)), pipeline_depth=8,
+                            dist=dist, world=world, rank=rank)
     e2e_multi['what'] += ('; %d ranks, each over its own shard, global batch %d, shard '
                           'totals over peer memory' % (world, args.batch * world))
     full = measure_full_train_step(torch, wl, args.batch, 100, ddp=True)

@@ -237,6 +237,9 @@ __global__ void __launch_bounds__(kBigThreads) tree_update_kernel(UpdateArgs<I, 
   // An earlier chunk failed: the reference's loop stopped there.  The latch is
   // only written after the grid barrier, so every CTA takes the same branch.
   if (a.status[0] != 0) return;
+  // A chunk beyond the device-side count (sharded replay: the host launches for the
+  // largest possible count) has nothing to do; every CTA sees the same n.
+  if (n <= 0) return;
   if (threadIdx.x == 0) {
     s_stop = n;
     s_stop_code = 0;
