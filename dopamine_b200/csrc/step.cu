@@ -17,10 +17,32 @@
 #include <new>
 #include <vector>
 
+#include <chrono>
+
 namespace b2r {
 
+// Host-side cost of the trainer's driver calls, by segment (B2R_HOST_TRACE=1 prints
+// the averages when a trainer is destroyed).  Off: one predictable branch per call.
+struct HostTrace {
+  bool on = std::getenv("B2R_HOST_TRACE") != nullptr;
+  double acc[8] = {0};
+  long calls = 0;
+  std::chrono::steady_clock::time_point last;
+  void start() { if (on) last = std::chrono::steady_clock::now(); }
+  void lap(int k) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    acc[k] += std::chrono::duration<double, std::micro>(now - last).count();
+    last = now;
+  }
+};
+static HostTrace g_host_trace;
+
 // Batch size above which the staged adds are flushed "split" (rows on the side
-// stream beside the tree update).  B2R_SPLIT_MIN overrides (experiments).
+// stream beside the tree update).  Measured at batch 32 (e2e_breakdown.py): 49.7 us
+// per update unsplit, 54.7 us split — the side stream also carries the forked frame
+// copies, and the extra event hops cost more than the 3 us row kernel they hide.
+// B2R_SPLIT_MIN overrides.
 static int split_min() {
   static const int v = [] {
     const char *e = std::getenv("B2R_SPLIT_MIN");
@@ -59,10 +81,10 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   if (shard && (!shard->exchange || !shard->out_count))
     return fail(B2R_ERR_INVALID_ARGUMENT, "exchange and out_count are required");
   const int32_t *count = shard ? shard->out_count : nullptr;
-  // Staged adds: at the agent's batch of 32 a host loop is bound by the number of
-  // driver calls, so everything goes on `s`; at larger batches the device chain is
-  // the bound and the rows are written on the side stream beside the tree update.
+  g_host_trace.lap(1);
+  // Staged adds (rows on the side stream beside the tree update at larger batches).
   B2R_TRY(flush_queue(b, s, batch > split_min()));
+  g_host_trace.lap(2);
   if (shard)
     B2R_TRY(launch_sample_sharded(
         b, batch, shard->exchange->world, shard->exchange->rank, nullptr,
@@ -71,6 +93,7 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   else
     B2R_TRY(launch_sample(b, batch, true, seed, offset, nullptr, nullptr, 0,
                           out->indices, b->info, s, out, b->min_prob));
+  g_host_trace.lap(3);
   const bool frames = out->state != nullptr || out->next_state != nullptr;
   if (frames) {
     B2R_CUDA(cudaEventRecord(b->ev_fork, s));
@@ -78,6 +101,7 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
     B2R_TRY(launch_gather(b, batch, out->indices, out, b->side, count, true));
     B2R_CUDA(cudaEventRecord(b->ev_join, b->side));
   }
+  g_host_trace.lap(4);
   b2r_c51_args loss = *c51;
   loss.batch = batch;
   loss.actions = static_cast<const int32_t *>(out->action);
@@ -87,13 +111,18 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   loss.min_probability = b->min_prob;
   loss.batch_count = count;
   if (count) loss.mean_weighted_loss = nullptr;
+  // (Measured: waiting for the logits before the sampler, or recording "loss done"
+  // after the write-back, serialises the input copy of the next step behind this
+  // step's tail and costs 13 us per update.)
   if (wait_before_loss) B2R_CUDA(cudaStreamWaitEvent(s, wait_before_loss, 0));
   B2R_TRY(b2r_c51_loss(&loss, s));
   if (loss_done) B2R_CUDA(cudaEventRecord(loss_done, s));
+  g_host_trace.lap(5);
   B2R_TRY((tree_apply<int32_t, float>(
       b->tree, batch, out->indices, loss.priorities, nullptr, s, count,
       shard ? (batch + shard->exchange->world - 1) / shard->exchange->world : -1)));
   if (frames) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join, 0));
+  g_host_trace.lap(6);
   return B2R_OK;
 }
 
@@ -283,6 +312,18 @@ int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
 int b2r_trainer_destroy(b2r_trainer *t) {
   if (!t) return B2R_OK;
   cudaDeviceSynchronize();
+  if (b2r::g_host_trace.on && b2r::g_host_trace.calls > 0) {
+    static const char *names[8] = {"collect (wait + copy out)", "logits H2D + events",
+                                   "flush staged adds", "sampler launch",
+                                   "gather fork", "loss launch", "write-back + join",
+                                   "loss D2H + events"};
+    fprintf(stderr, "b2r host trace over %ld trainer steps (us per step):\n",
+            b2r::g_host_trace.calls);
+    for (int k = 1; k <= 8; ++k)
+      fprintf(stderr, "  %-28s %6.2f\n", names[k % 8],
+              b2r::g_host_trace.acc[k % 8] / b2r::g_host_trace.calls);
+    b2r::g_host_trace = b2r::HostTrace();
+  }
   for (int set = 0; set < 2; ++set)
     for (int k = 0; k < 2; ++k) cudaFree(t->logits[set][k]);
   cudaFree(t->support);
@@ -308,6 +349,7 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   if (!t || !online_logits || !target_logits)
     return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
   cudaStream_t s = as_stream(stream);
+  b2r::g_host_trace.start();
   const int64_t n = t->submitted;
   const int set = (int)(n & 1);
   const size_t logit_bytes = (size_t)t->cfg.batch * t->cfg.num_actions *
@@ -352,7 +394,11 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
                            cudaMemcpyDeviceToHost, t->copy));
   B2R_CUDA(cudaEventRecord(t->ev_done[slot], t->copy));
   t->submitted = n + 1;
-  return collect(t, n - t->cfg.pipeline_depth, loss_out, loss_step);
+  b2r::g_host_trace.lap(7);
+  const int status = collect(t, n - t->cfg.pipeline_depth, loss_out, loss_step);
+  b2r::g_host_trace.lap(0);
+  b2r::g_host_trace.calls += 1;
+  return status;
 }
 
 int b2r_trainer_set_exchange(b2r_trainer *t, b2r_exchange *x) {
