@@ -14,69 +14,15 @@
 #include "replay.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 namespace b2r {
 namespace {
 
-struct AddParams {
-  int n_entries;
-  int num_columns;
-  int64_t row_stride;
-  const int64_t *slots;     // device, per entry
-  const int32_t *src_rows;  // device, per entry; -1 = all-zero padding transition
-  const uint8_t *rows;      // device staged rows
-  uint8_t *col_dev[kMaxColumns];
-  int64_t col_bytes[kMaxColumns];
-  int64_t col_qoff[kMaxColumns];
-  uint8_t *term_flag;       // nullptr when it aliases the 1-byte terminal column
-  int term_itemsize;
-  const uint64_t *ctx_src;  // ValidCtx image in the staged header
-  uint64_t *ctx_dst;        // the buffer's device ValidCtx
-};
-
 // grid = (x: 16-byte chunks of the observation, y: entries).
 __global__ void __launch_bounds__(256) add_rows_kernel(AddParams p) {
-  const int e = blockIdx.y;
-  const int64_t slot = p.slots[e];
-  const int src = p.src_rows[e];
-  const uint8_t *row = src >= 0 ? p.rows + (int64_t)src * p.row_stride : nullptr;
-
-  // observation: coalesced 16-byte stores when the frame size allows it.
-  const int64_t obs_bytes = p.col_bytes[0];
-  uint8_t *dst = p.col_dev[0] + slot * obs_bytes;
-  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t nthreads = gridDim.x * (int64_t)blockDim.x;
-  if ((obs_bytes & 15) == 0) {
-    const int64_t chunks = obs_bytes >> 4;
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(row);
-    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
-    for (int64_t c = tid; c < chunks; c += nthreads)
-      d4[c] = row ? s4[c] : make_uint4(0, 0, 0, 0);
-  } else {
-    for (int64_t c = tid; c < obs_bytes; c += nthreads) dst[c] = row ? row[c] : 0;
-  }
-
-  // the validity context that goes with these rows
-  if (blockIdx.x == 0 && e == 0)
-    for (int w = threadIdx.x; w < (int)(sizeof(ValidCtx) / 8); w += blockDim.x)
-      p.ctx_dst[w] = p.ctx_src[w];
-
-  // scalar columns: a handful of bytes, first block of the entry only.
-  if (blockIdx.x == 0) {
-    for (int c = 1; c < p.num_columns; ++c) {
-      const int64_t nb = p.col_bytes[c];
-      uint8_t *d = p.col_dev[c] + slot * nb;
-      const uint8_t *s = row ? row + p.col_qoff[c] : nullptr;
-      for (int64_t b = threadIdx.x; b < nb; b += blockDim.x) d[b] = s ? s[b] : 0;
-    }
-    if (p.term_flag != nullptr && threadIdx.x == 0) {
-      uint8_t any = 0;
-      if (row)
-        for (int b = 0; b < p.term_itemsize; ++b) any |= row[p.col_qoff[3] + b];
-      p.term_flag[slot] = any ? 1 : 0;
-    }
-  }
+  add_rows_body(p, blockIdx.y, blockIdx.x, gridDim.x);
 }
 
 __global__ void valid_mask_kernel(ValidCtx ctx, int64_t n,
@@ -183,6 +129,44 @@ int flush_queue(b2r_buffer *b, cudaStream_t stream, bool split) {
   fill_valid_ctx(b, reinterpret_cast<ValidCtx *>(s->host + ctx_off));
   // split: rows (H2D + ring writes) on the side stream, ordered after everything
   // already queued on `stream` (earlier readers of the ring), beside the tree update.
+  // Small flushes of a prioritized buffer (the agent's add loop: a handful of rows
+  // per update): ONE launch that reads the staging buffer straight from pinned host
+  // memory — tree update in CTA 0, row writes in the others (tree.cu).
+  if (b->tree != nullptr && !split && s->host_dev != nullptr &&
+      b->q_entries <= tree_small_max() && std::getenv("B2R_NO_FUSED_FLUSH") == nullptr) {
+    Header hh = header_of(s->host_dev, b->queue_cap);
+    AddParams p;
+    p.n_entries = b->q_entries;
+    p.num_columns = b->num_columns;
+    p.row_stride = b->row_stride;
+    p.slots = hh.slots;
+    p.src_rows = hh.src_rows;
+    p.rows = s->host_dev + b->header_bytes;
+    for (int c = 0; c < b->num_columns; ++c) {
+      p.col_dev[c] = b->col[c].dev;
+      p.col_bytes[c] = b->col[c].row_bytes;
+      p.col_qoff[c] = b->col[c].queue_offset;
+    }
+    p.term_flag = b->term_flag_owned ? b->term_flag : nullptr;
+    p.term_itemsize = b->cfg.terminal_itemsize;
+    p.ctx_src = reinterpret_cast<const uint64_t *>(s->host_dev + ctx_off);
+    p.ctx_dst = reinterpret_cast<uint64_t *>(b->ctx_dev);
+    const int64_t chunks = (b->cfg.obs_bytes & 15) == 0 ? b->cfg.obs_bytes >> 4
+                                                         : b->cfg.obs_bytes;
+    const int threads = 32 * (b->tree->depth + 1);
+    int per_entry = (int)((chunks + threads - 1) / threads);
+    if (per_entry < 1) per_entry = 1;
+    if (per_entry > 8) per_entry = 8;
+    B2R_TRY(flush_fused(b->tree, b->q_entries, hh.slots, hh.prio, hh.mode, p, per_entry,
+                        stream));
+    b->ctx_dirty = false;
+    B2R_CUDA(cudaEventRecord(s->done, stream));
+    s->in_flight = true;
+    b->active ^= 1;
+    b->q_entries = 0;
+    b->q_rows = 0;
+    return B2R_OK;
+  }
   cudaStream_t data = stream;
   if (split) {
     data = b->side;
@@ -369,6 +353,11 @@ int b2r_create(const b2r_config *cfg, b2r_buffer **out) {
   for (int k = 0; k < 2; ++k) {
     B2R_CUDA(cudaMallocHost(reinterpret_cast<void **>(&b->staging[k].host),
                             staging_bytes));
+    void *as_device = nullptr;
+    if (cudaHostGetDevicePointer(&as_device, b->staging[k].host, 0) == cudaSuccess)
+      b->staging[k].host_dev = static_cast<uint8_t *>(as_device);
+    else
+      cudaGetLastError();
     B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->staging[k].dev),
                         staging_bytes));
     B2R_CUDA(cudaEventCreateWithFlags(&b->staging[k].done,

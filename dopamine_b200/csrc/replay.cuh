@@ -75,6 +75,70 @@ struct ExchangeArgs {
   int64_t timeout_ns;
 };
 
+// Staged rows -> ring (replay.cu: flush_queue).  In a header because the fused flush
+// kernel of tree.cu runs it beside the priority update.
+struct AddParams {
+  int n_entries;
+  int num_columns;
+  int64_t row_stride;
+  const int64_t *slots;     // device, per entry
+  const int32_t *src_rows;  // device, per entry; -1 = all-zero padding transition
+  const uint8_t *rows;      // device staged rows
+  uint8_t *col_dev[kMaxColumns];
+  int64_t col_bytes[kMaxColumns];
+  int64_t col_qoff[kMaxColumns];
+  uint8_t *term_flag;       // nullptr when it aliases the 1-byte terminal column
+  int term_itemsize;
+  const uint64_t *ctx_src;  // ValidCtx image in the staged header
+  uint64_t *ctx_dst;        // the buffer's device ValidCtx
+};
+
+// One CTA of the row writer: entry e, chunk-block bx of nbx.
+#ifdef __CUDACC__
+__device__ __forceinline__ void add_rows_body(const AddParams &p, int e, int bx, int nbx) {
+  const int64_t slot = p.slots[e];
+  const int src = p.src_rows[e];
+  const uint8_t *row = src >= 0 ? p.rows + (int64_t)src * p.row_stride : nullptr;
+
+  // observation: coalesced 16-byte stores when the frame size allows it.
+  const int64_t obs_bytes = p.col_bytes[0];
+  uint8_t *dst = p.col_dev[0] + slot * obs_bytes;
+  const int64_t tid = bx * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nthreads = nbx * (int64_t)blockDim.x;
+  if ((obs_bytes & 15) == 0) {
+    const int64_t chunks = obs_bytes >> 4;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(row);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (int64_t c = tid; c < chunks; c += nthreads)
+      d4[c] = row ? s4[c] : make_uint4(0, 0, 0, 0);
+  } else {
+    for (int64_t c = tid; c < obs_bytes; c += nthreads) dst[c] = row ? row[c] : 0;
+  }
+
+  // the validity context that goes with these rows
+  if (bx == 0 && e == 0)
+    for (int w = threadIdx.x; w < (int)(sizeof(ValidCtx) / 8); w += blockDim.x)
+      p.ctx_dst[w] = p.ctx_src[w];
+
+  // scalar columns: a handful of bytes, first block of the entry only.
+  if (bx == 0) {
+    for (int c = 1; c < p.num_columns; ++c) {
+      const int64_t nb = p.col_bytes[c];
+      uint8_t *d = p.col_dev[c] + slot * nb;
+      const uint8_t *s = row ? row + p.col_qoff[c] : nullptr;
+      for (int64_t b = threadIdx.x; b < nb; b += blockDim.x) d[b] = s ? s[b] : 0;
+    }
+    if (p.term_flag != nullptr && threadIdx.x == 0) {
+      uint8_t any = 0;
+      if (row)
+        for (int b = 0; b < p.term_itemsize; ++b) any |= row[p.col_qoff[3] + b];
+      p.term_flag[slot] = any ? 1 : 0;
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
 struct Column {
   int64_t row_bytes = 0;
   int64_t queue_offset = 0;  // byte offset inside a staged row
@@ -83,6 +147,7 @@ struct Column {
 
 struct Staging {
   uint8_t *host = nullptr;  // pinned
+  uint8_t *host_dev = nullptr;  // the same memory as the device sees it (zero-copy)
   uint8_t *dev = nullptr;
   cudaEvent_t done = nullptr;
   bool in_flight = false;
@@ -170,6 +235,12 @@ int launch_sample_sharded(b2r_buffer *buf, int32_t global_batch, int32_t num_sha
                           float *min_prob_out = nullptr);
 void fill_valid_ctx(const b2r_buffer *buf, ValidCtx *ctx);
 int ensure_ctx(b2r_buffer *buf, cudaStream_t stream);
+// tree.cu: largest batch the one-CTA tree kernel takes, and the fused flush launch
+// (priorities of n new rows + their row writes, staging read zero-copy).
+int tree_small_max();
+int flush_fused(b2r_tree *tree, int n, const int64_t *slots, const double *prio,
+                const uint8_t *mode, const AddParams &rows, int row_blocks_per_entry,
+                cudaStream_t stream);
 int ensure_inv_slots(b2r_buffer *buf, int64_t n);
 int launch_gather(b2r_buffer *buf, int32_t batch, const int32_t *indices_dev,
                   const b2r_batch *out, cudaStream_t stream,

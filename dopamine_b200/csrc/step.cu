@@ -142,7 +142,10 @@ struct b2r_trainer {
   b2r_batch batch;
   b2r_c51_args c51;
   // copies run on their own stream, double-buffered against the loss kernel
-  cudaStream_t copy = nullptr;
+  cudaStream_t copy = nullptr;      // inputs (H2D of the logits)
+  cudaStream_t copy_out = nullptr;  // results (D2H of the losses): a result copy waits
+                                    // for its step, and must not hold up the inputs
+                                    // of the next one
   cudaEvent_t ev_in[2] = {nullptr, nullptr};
   cudaEvent_t ev_loss[2] = {nullptr, nullptr};
   // sharded mode
@@ -294,6 +297,7 @@ int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
   t->count = reinterpret_cast<int32_t *>(t->c51.loss + B);  // copied back with the losses
 
   B2R_CUDA(cudaStreamCreateWithFlags(&t->copy, cudaStreamNonBlocking));
+  B2R_CUDA(cudaStreamCreateWithFlags(&t->copy_out, cudaStreamNonBlocking));
   B2R_CUDA(cudaStreamCreateWithFlags(&t->cap, cudaStreamNonBlocking));
   for (int k = 0; k < 2; ++k) {
     B2R_CUDA(cudaEventCreateWithFlags(&t->ev_in[k], cudaEventDisableTiming));
@@ -330,6 +334,7 @@ int b2r_trainer_destroy(b2r_trainer *t) {
   cudaFree(t->frames);
   cudaFree(t->scalars);
   if (t->copy) cudaStreamDestroy(t->copy);
+  if (t->copy_out) cudaStreamDestroy(t->copy_out);
   if (t->cap) cudaStreamDestroy(t->cap);
   for (int k = 0; k < 2; ++k)
     if (t->exec[k]) cudaGraphExecDestroy(t->exec[k]);
@@ -388,11 +393,11 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   }
   // result: per-row losses into this step's pinned slot (copy stream, after the loss)
   const int slot = (int)(n % t->ring);
-  B2R_CUDA(cudaStreamWaitEvent(t->copy, t->ev_loss[set], 0));
+  B2R_CUDA(cudaStreamWaitEvent(t->copy_out, t->ev_loss[set], 0));
   B2R_CUDA(cudaMemcpyAsync(t->ring_host + (size_t)slot * (t->cfg.batch + 1),
                            t->c51.loss, (size_t)(t->cfg.batch + 1) * sizeof(float),
-                           cudaMemcpyDeviceToHost, t->copy));
-  B2R_CUDA(cudaEventRecord(t->ev_done[slot], t->copy));
+                           cudaMemcpyDeviceToHost, t->copy_out));
+  B2R_CUDA(cudaEventRecord(t->ev_done[slot], t->copy_out));
   t->submitted = n + 1;
   b2r::g_host_trace.lap(7);
   const int status = collect(t, n - t->cfg.pipeline_depth, loss_out, loss_step);
@@ -415,6 +420,7 @@ int b2r_trainer_drain(b2r_trainer *t, float *loss_out, int64_t *loss_step,
                       b2r_stream stream) {
   if (!t) return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
   B2R_CUDA(cudaStreamSynchronize(t->copy));
+  B2R_CUDA(cudaStreamSynchronize(t->copy_out));
   B2R_CUDA(cudaStreamSynchronize(as_stream(stream)));
   return collect(t, t->submitted - 1, loss_out, loss_step);
 }

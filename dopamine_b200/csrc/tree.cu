@@ -14,7 +14,7 @@
 //
 // The critical path is the root's chain of n dependent DADDs; everything else
 // overlaps with it.  Bandwidth is irrelevant here (n * depth * 16 bytes).
-#include "tree.cuh"
+#include "replay.cuh"
 
 #include <cooperative_groups.h>
 #include <cub/block/block_radix_sort.cuh>
@@ -400,7 +400,7 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t *keys, int padded, in
 // with shuffled-free warp-synchronous bitonic steps while the leaf warp resolves
 // the leaf chains; internal warps prefetch their node values before the barrier.
 template <typename I, typename V>
-__global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V> a) {
+__device__ __forceinline__ void tree_update_small_body(const UpdateArgs<I, V> &a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int levels = a.depth + 1;
@@ -518,6 +518,29 @@ __global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V
   B2R_MARK(7);
 }
 
+template <typename I, typename V>
+__global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V> a) {
+  tree_update_small_body(a);
+}
+
+// The flush of staged adds as ONE launch: CTA 0 applies the priorities of the new
+// rows to the tree (the body above), the other CTAs write the rows into the ring
+// (replay.cuh: add_rows_body).  Both read the staging buffer straight from pinned
+// host memory (zero-copy), so an add flush puts one kernel on the stream instead of
+// a copy and two kernels.
+__global__ void __launch_bounds__(1024)
+flush_fused_kernel(UpdateArgs<int64_t, double> a, AddParams p, int row_blocks_per_entry) {
+  if (blockIdx.x == 0) {
+    tree_update_small_body(a);
+    return;
+  }
+  pdl_release();
+  pdl_acquire();
+  const int r = blockIdx.x - 1;
+  add_rows_body(p, r / row_blocks_per_entry, r % row_blocks_per_entry,
+                row_blocks_per_entry);
+}
+
 __global__ void tree_get_kernel(const double *__restrict__ heap, int64_t leaves,
                                 int64_t n, const int64_t *__restrict__ indices,
                                 double *__restrict__ out) {
@@ -564,34 +587,77 @@ int allow_big_smem(K kernel) {
 
 }  // namespace
 
-template <typename I, typename V>
-int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
-               const uint8_t *mode, cudaStream_t stream, const int32_t *n_dev,
-               int64_t expected_n) {
-  set_tree_window(t->heap, (size_t)t->leaves * 16);
-  // The one-CTA kernel sorts per warp (cost ~ n log^2 n): it wins for the agent's
-  // batch of 32 and loses to the radix-sorted cooperative kernel beyond ~64 entries
-  // (measured, profiles/r1/README.md).  B2R_TREE_SMALL_MAX overrides the threshold.
+// The one-CTA kernel sorts per warp (cost ~ n log^2 n): it wins for the agent's batch
+// of 32 and loses to the radix-sorted cooperative kernel beyond ~64 entries (measured,
+// profiles/r1/README.md).  B2R_TREE_SMALL_MAX overrides the threshold.
+int tree_small_max() {
   static const int small_max = [] {
     const char *e = std::getenv("B2R_TREE_SMALL_MAX");
     int v = e ? std::atoi(e) : 64;
     return v < 0 ? 0 : (v > kSmallBatch ? kSmallBatch : v);
   }();
+  return small_max;
+}
+
+static int allow_small_smem() {
+  static bool ready = false;
+  if (!ready) {
+    const int bytes = kSmallBatch * 8 * (1 + 2 * 32);
+    B2R_CUDA(cudaFuncSetAttribute(tree_update_small_kernel<int64_t, double>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B2R_CUDA(cudaFuncSetAttribute(tree_update_small_kernel<int32_t, float>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B2R_CUDA(cudaFuncSetAttribute(tree_update_small_kernel<int32_t, double>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    B2R_CUDA(cudaFuncSetAttribute(flush_fused_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    ready = true;
+  }
+  return B2R_OK;
+}
+
+int flush_fused(b2r_tree *t, int n, const int64_t *slots, const double *prio,
+                const uint8_t *mode, const AddParams &rows, int row_blocks_per_entry,
+                cudaStream_t stream) {
+  set_tree_window(t->heap, (size_t)t->leaves * 16);
+  B2R_TRY(allow_small_smem());
+  const int padded = padded_size(n);
+  const size_t smem = (size_t)padded * 8 * (1 + 2 * (size_t)(t->depth + 1));
+  UpdateArgs<int64_t, double> a;
+  a.heap = t->heap;
+  a.depth = t->depth;
+  a.leaves = t->leaves;
+  a.n = n;
+  a.padded = padded;
+  a.indices = slots;
+  a.values = prio;
+  a.mode = mode;
+  a.k_base = 0;
+  a.delta = t->delta;
+  a.max_rec = t->max_rec;
+  a.status = t->status;
+  a.n_dev = nullptr;
+  B2R_CUDA(launch(flush_fused_kernel, dim3(1 + n * row_blocks_per_entry),
+                  dim3(32 * (t->depth + 1)), smem, stream, a, rows,
+                  row_blocks_per_entry));
+  B2R_LAUNCHED();
+  return B2R_OK;
+}
+
+template <typename I, typename V>
+int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
+               const uint8_t *mode, cudaStream_t stream, const int32_t *n_dev,
+               int64_t expected_n) {
+  set_tree_window(t->heap, (size_t)t->leaves * 16);
+  const int small_max = tree_small_max();
   // A device-side count (sharded replay) is only bounded by n on the host: the
   // caller's expectation decides, the one-CTA kernel copes with up to kSmallBatch.
   const int64_t likely = expected_n >= 0 ? expected_n : n;
   if (n <= kSmallBatch && likely <= small_max) {
     // latency path: one CTA, one warp per level
-    static bool small_ready = false;
     const int padded = padded_size((int)n);
     const size_t smem = (size_t)padded * 8 * (1 + 2 * (size_t)(t->depth + 1));
-    if (!small_ready) {
-      B2R_CUDA(cudaFuncSetAttribute(
-          tree_update_small_kernel<I, V>,
-          cudaFuncAttributeMaxDynamicSharedMemorySize,
-          kSmallBatch * 8 * (1 + 2 * 32)));
-      small_ready = true;
-    }
+    B2R_TRY(allow_small_smem());
     UpdateArgs<I, V> a;
     a.heap = t->heap;
     a.depth = t->depth;

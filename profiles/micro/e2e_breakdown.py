@@ -48,13 +48,19 @@ def main():
 
   timed('4 x add() + flush', lambda: (adds(), mem._flush()))
   timed('4 x add() only (flush every 32 iters)', adds)
-  for depth in (2, 0, 8):
+  import gc
+  for depth in (2, 0):
+    # one trainer per loop: with B2R_HOST_TRACE=1 each prints its own host segments
     tr = ra.ReplayTrainer(mem, 18, 51, 10., batch_size=32, pipeline_depth=depth, seed=1)
     timed('trainer.step only, depth %d' % depth,
           lambda: tr.step_pointers(op, tp, stream), after=tr.drain)
+    del tr
+    gc.collect()
+    tr = ra.ReplayTrainer(mem, 18, 51, 10., batch_size=32, pipeline_depth=depth, seed=1)
     timed('4 x add() + trainer.step, depth %d' % depth,
           lambda: (adds(), tr.step_pointers(op, tp, stream)), after=tr.drain)
     del tr
+    gc.collect()
 
 
 if __name__ == '__main__':
