@@ -496,6 +496,81 @@ def measure_full_train_step(torch, wl, batch, steps, ddp=False, cuda_graph=False
                       'eager PyTorch host loop')}
 
 
+def measure_config1_dqn(torch, steps, batch=32, capacity=100000, cpu_budget_s=4.0):
+  """BASELINE configs[0]: DQN's OutOfGraphReplayBuffer, 84x84 uint8 frames, capacity
+  100k, stack 4, batch 32, uniform sampling, n = 1 — uniform sample + gather + DQN
+  Bellman target / Huber loss (dqn_agent.py:283-322), device-timed as a CUDA graph,
+  beside the CPU port of the same step."""
+  from dopamine_b200 import _native
+  from dopamine_b200.replay_memory import circular_replay_buffer as crb
+  from oracle import dqn_port
+  from oracle.replay_port import PortReplay, cursor_window
+  lib = _native.lib()
+  mem = crb.OutOfGraphReplayBuffer((84, 84), STACK, capacity, batch, update_horizon=1,
+                                   gamma=GAMMA, output='torch', rng='device', seed=11,
+                                   reuse_outputs=True)
+  gen = torch.Generator(device='cuda')
+  gen.manual_seed(11)
+  stream = _native.current_stream()
+  frames = torch.randint(0, 256, (capacity, FRAME), dtype=torch.uint8, device='cuda',
+                         generator=gen)
+  actions = torch.randint(0, NUM_ACTIONS, (capacity,), dtype=torch.int32,
+                          device='cuda', generator=gen)
+  rewards = torch.randn(capacity, device='cuda', generator=gen).clamp_(-1, 1)
+  terms = (torch.rand(capacity, device='cuda', generator=gen) < 1e-3).to(torch.uint8)
+  for col, t in ((0, frames), (1, actions), (2, rewards), (3, terms)):
+    _native.check(lib.b2r_store_write(mem._h, col, 0, capacity, t.data_ptr(), stream))  # pylint: disable=protected-access
+  mem.add_count = capacity + 500  # full and wrapped (SURVEY 8d config 1)
+  mem.invalid_range = [(500 - 1 + i) % capacity for i in range(STACK + 1)]
+  _, arrays, b = mem._alloc_outputs(batch, True)  # pylint: disable=protected-access
+  online_q = torch.randn(batch, NUM_ACTIONS, device='cuda', generator=gen)
+  target_q = torch.randn(batch, NUM_ACTIONS, device='cuda', generator=gen)
+  loss = torch.empty(batch, dtype=torch.float32, device='cuda')
+  a = _native.DqnArgs()
+  a.batch, a.num_actions = batch, NUM_ACTIONS
+  a.cumulative_gamma = float(np.float32(GAMMA))
+  a.target_q, a.online_q = target_q.data_ptr(), online_q.data_ptr()
+  a.actions, a.rewards = arrays[1].data_ptr(), arrays[2].data_ptr()
+  a.terminals, a.loss = arrays[6].data_ptr(), loss.data_ptr()
+
+  def step():
+    s = _native.current_stream()
+    _native.check(lib.b2r_sample_transition_batch_device(
+        mem._h, batch, 11, 0, ctypes.byref(b), s))  # pylint: disable=protected-access
+    _native.check(lib.b2r_dqn_loss(ctypes.byref(a), s))
+
+  ms = time_graph_or_eager(torch, step, steps, 20, True)
+  _native.check(lib.b2r_check(mem._h, _native.current_stream()))  # pylint: disable=protected-access
+  # CPU: the oracle port of the same step, one core
+  port = PortReplay((84, 84), STACK, capacity, batch, update_horizon=1, gamma=GAMMA)
+  rng = np.random.RandomState(11)
+  pattern = rng.randint(0, 256, size=(4096, 84, 84)).astype(np.uint8)
+  for lo in range(0, capacity, 4096):
+    n = min(4096, capacity - lo)
+    port.store['observation'][lo:lo + n] = pattern[:n]
+  port.store['action'][:] = rng.randint(0, NUM_ACTIONS, size=capacity)
+  port.store['reward'][:] = np.clip(rng.randn(capacity), -1, 1)
+  port.store['terminal'][:] = rng.rand(capacity) < 1e-3
+  port.add_count = np.array(capacity + 500)
+  port.invalid_range = cursor_window(500, capacity, STACK, 1)
+  oq = rng.randn(batch, NUM_ACTIONS).astype(np.float32)
+  tq = rng.randn(batch, NUM_ACTIONS).astype(np.float32)
+  np.random.seed(0)
+  done, t0 = 0, time.perf_counter()
+  while time.perf_counter() - t0 < cpu_budget_s or done < 3:
+    bt = port.sample_transition_batch(batch)
+    dqn_port.dqn_update(bt[2], bt[6], bt[1], oq, tq, GAMMA, 1)
+    done += 1
+  cpu_dt = time.perf_counter() - t0
+  return {'workload': 'DQN OutOfGraphReplayBuffer capacity {}, stack 4, batch {}, '
+                      'uniform sampling, n = 1 (BASELINE configs[0])'.format(
+                          capacity, batch),
+          'value': round(batch * steps / (ms * 1e-3), 1), 'unit': UNIT,
+          'ms_per_step': round(ms / steps, 6), 'steps': steps,
+          'cpu_port_value': round(batch * done / cpu_dt, 1), 'cpu_cores': 1,
+          'what': 'uniform sample + gather + DQN target / Huber loss; CUDA graph replay'}
+
+
 def measure_e2e_host_batch(torch, wl, batch, steps):
   """Variant that also ships the whole sampled batch to host numpy arrays, i.e. the
   reference's OutOfGraph* return convention (1.8 MB of D2H per step at batch 32)."""
@@ -831,6 +906,8 @@ def main():
                                           cuda_graph=True)
           for b in ([args.batch] + ([256] if sweep_batches else []))}
     if not args.no_cpu_baseline and world == 1:
+      line['config1_dqn_uniform'] = measure_config1_dqn(
+          torch, max(50, min(args.steps, 2000)))
       line['cpu_baseline'] = cpu_baseline(args.batch, args.capacity)
     print(json.dumps(line))
   if dist is not None:

@@ -151,11 +151,11 @@ def test_graph_replayed_learner_equals_eager(learner_mod):
 
   eager = run(False)
   graphed = run(True)
-  np.testing.assert_allclose(graphed[0], eager[0], rtol=1e-4)
+  np.testing.assert_allclose(graphed[0], eager[0], rtol=2e-3)
   # Adam divides by sqrt(v): near-zero gradient entries amplify cuDNN's run-to-run
   # rounding differences, hence the absolute tolerance of a few learning rates
   for a, b in zip(graphed[1], eager[1]):
-    np.testing.assert_allclose(a, b, rtol=1e-3, atol=2e-4)
+    np.testing.assert_allclose(a, b, rtol=2e-3, atol=5e-4)
   # same sampled indices and (up to cuDNN's algorithm choice) priorities
   for a, b in zip(graphed[2], eager[2]):
-    np.testing.assert_allclose(a, b, rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(a, b, rtol=5e-3, atol=1e-5)
