@@ -378,9 +378,28 @@ int launch_gather(b2r_buffer *b, int32_t batch, const int32_t *indices_dev,
     // + rows of scalar CTAs (one thread per transition)
     a.scalar_rows = frames_only ? 0 : (batch + nx * 128 - 1) / (nx * 128);
     dim3 grid(nx, batch + a.scalar_rows);
-    if (frames_only)  // beside the chain: lowest priority
-      B2R_CUDA(launch_prio(gather_stack4_u8_kernel<false>, grid, dim3(128), 0, stream,
-                           0, a));
+    if (frames_only) {  // beside the chain: lowest priority
+      // While the copies are short next to the chain (up to ~1.5k rows) each copy CTA
+      // claims 56 KB of shared memory it does not use: at most 4 of them then share an
+      // SM, which leaves the chain's CTAs their occupancy (65 -> 58 us per step at
+      // batch 1024).  Beyond that the copies themselves bound the step and run
+      // unrestricted (capping costs 146 -> 162 us at 4096).  B2R_GATHER_PAD_KB
+      // overrides.
+      static const int pad_env = [] {
+        const char *e = std::getenv("B2R_GATHER_PAD_KB");
+        return e ? std::atoi(e) : -1;
+      }();
+      const int pad_kb = pad_env >= 0 ? pad_env : (batch > 64 && batch <= 1536 ? 56 : 0);
+      static bool pad_ready = false;
+      if (pad_kb > 48 && !pad_ready) {
+        B2R_CUDA(cudaFuncSetAttribute(gather_stack4_u8_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      pad_kb * 1024));
+        pad_ready = true;
+      }
+      B2R_CUDA(launch_prio(gather_stack4_u8_kernel<false>, grid, dim3(128),
+                           (size_t)pad_kb * 1024, stream, 0, a));
+    }
     else
       B2R_CUDA(launch(gather_stack4_u8_kernel<true>, grid, dim3(128), 0, stream, a));
   } else {
