@@ -100,31 +100,41 @@ __device__ __forceinline__ void stage_mode_values(const UpdateArgs<I, V> &a, int
 // after one grid-wide barrier each internal CTA adds the deltas that fall under
 // each of its nodes in batch order.  Critical path: the leaf CTA's sort + the
 // root's chain of n dependent DADDs.
-constexpr int kBigThreads = 1024;
-constexpr int kBigItems = kTreeChunk / kBigThreads;
-using BigSort = cub::BlockRadixSort<uint32_t, kBigThreads, kBigItems, uint32_t>;
-
-constexpr int kHashSlots = 2 * kTreeChunk;  // load factor <= 0.5
-constexpr int kHashBits = 13;
-static_assert((1 << kHashBits) == kHashSlots, "hash size");
-constexpr int kMaxDup = 512;  // duplicate-leaf entries the hashed leaf pass handles
-
-struct GroupSmem {
-  typename BigSort::TempStorage sort;
-  uint32_t node[kTreeChunk];  // node index on this level, grouped
-  uint32_t elem[kTreeChunk];  // batch position k of the same entry
-};
-struct HashSmem {
-  uint32_t key[kHashSlots];   // leaf index owning the slot
-  uint32_t count[kHashSlots]; // entries of the chunk that hit it
-};
-struct BigSmem {
-  union {
-    GroupSmem g;
-    HashSmem h;               // leaf CTA only, before (instead of) the sort
+// Geometry of the cooperative kernel: THREADS x ITEMS entries per chunk.  Two
+// instances: 1024 x 4 for chunks of up to 4096 entries, 256 x 4 for batches of up to
+// 1024 (a radix pass over 1024 slots costs a fraction of one over 4096, and every
+// level pays its passes before it can apply the deltas).
+template <int THREADS, int ITEMS>
+struct BigCfg {
+  static constexpr int kThreads = THREADS;
+  static constexpr int kItems = ITEMS;
+  static constexpr int kChunk = THREADS * ITEMS;
+  static constexpr int kHashSlots = 2 * kChunk;  // load factor <= 0.5
+  static constexpr int kHashBits = kChunk == 4096 ? 13 : (kChunk == 1024 ? 11 : -1);
+  static_assert(kHashBits > 0 && (1 << kHashBits) == kHashSlots, "hash size");
+  // duplicate-leaf entries the hashed leaf pass handles (one thread ranks each)
+  static constexpr int kMaxDup = THREADS < 512 ? THREADS : 512;
+  using Sort = cub::BlockRadixSort<uint32_t, THREADS, ITEMS, uint32_t>;
+  struct GroupSmem {
+    typename Sort::TempStorage sort;
+    uint32_t node[kChunk];  // node index on this level, grouped
+    uint32_t elem[kChunk];  // batch position k of the same entry
   };
-  double vals[kTreeChunk];    // value -> leaf delta (leaf CTA) / deltas in group order
+  struct HashSmem {
+    uint32_t key[kHashSlots];    // leaf index owning the slot
+    uint32_t count[kHashSlots];  // entries of the chunk that hit it
+  };
+  struct Smem {
+    union {
+      GroupSmem g;
+      HashSmem h;           // leaf CTA only, before (instead of) the sort
+    };
+    double vals[kChunk];    // value -> leaf delta (leaf CTA) / deltas in group order
+  };
 };
+using BigCfg4096 = BigCfg<1024, 4>;
+using BigCfg1024 = BigCfg<256, 4>;
+static_assert(BigCfg4096::kChunk == kTreeChunk, "chunk size");
 
 // Leaf pass without sorting.  The leaf deltas gate every other level (the root's
 // chain of n dependent adds starts when they are published), so the leaf CTA avoids
@@ -132,11 +142,15 @@ struct BigSmem {
 // leaf occurs more than once in the chunk; all others are independent
 // (delta = value - leaf, leaf += delta, sum_tree.py:196-202), and the few duplicates
 // are ordered by (leaf, batch position) with a counting rank and walked as chains.
-// Returns false (nothing written) when more than kMaxDup entries share leaves; the
+// Returns false (nothing written) when more than C::kMaxDup entries share leaves; the
 // caller then takes the sorted path.
-template <typename I, typename V>
+template <typename C, typename I, typename V>
 __device__ __forceinline__ bool leaf_deltas_hashed(const UpdateArgs<I, V> &a, int n_eff,
-                                                   HashSmem &h, double *vals) {
+                                                   typename C::HashSmem &h,
+                                                   double *vals) {
+  constexpr int kBigItems = C::kItems, kBigThreads = C::kThreads;
+  constexpr int kHashSlots = C::kHashSlots, kHashBits = C::kHashBits;
+  constexpr int kMaxDup = C::kMaxDup;
   __shared__ uint32_t d_idx[kMaxDup], d_k[kMaxDup], ds_idx[kMaxDup], ds_k[kMaxDup];
   __shared__ int s_ndup;
   constexpr uint32_t kEmpty = 0xffffffffu;
@@ -215,10 +229,12 @@ __device__ __forceinline__ bool leaf_deltas_hashed(const UpdateArgs<I, V> &a, in
   return true;
 }
 
-template <typename I, typename V>
-__global__ void __launch_bounds__(kBigThreads) tree_update_kernel(UpdateArgs<I, V> a) {
+template <typename I, typename V, typename C>
+__global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, V> a) {
+  constexpr int kBigItems = C::kItems;
+  using BigSort = typename C::Sort;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  BigSmem &sm = *reinterpret_cast<BigSmem *>(smem_raw);
+  typename C::Smem &sm = *reinterpret_cast<typename C::Smem *>(smem_raw);
   double *vals = sm.vals;
   __shared__ int s_stop;       // first position that must not be applied
   __shared__ int s_stop_code;
@@ -278,7 +294,7 @@ __global__ void __launch_bounds__(kBigThreads) tree_update_kernel(UpdateArgs<I, 
     for (int off = 16; off > 0; off >>= 1)
       local_max = fmax(local_max, __shfl_xor_sync(0xffffffffu, local_max, off));
     if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = local_max;
-    leaf_done = leaf_deltas_hashed(a, n_eff, sm.h, vals);
+    leaf_done = leaf_deltas_hashed<C>(a, n_eff, sm.h, vals);
     __syncthreads();
   }
 
@@ -573,15 +589,47 @@ int padded_size(int n) {
   return p;
 }
 
-template <typename K>
+template <typename C, typename K>
 int allow_big_smem(K kernel) {
   static bool done = false;  // per instantiation
   if (!done) {
     B2R_CUDA(cudaFuncSetAttribute(kernel,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sizeof(BigSmem)));
+                                  (int)sizeof(typename C::Smem)));
     done = true;
   }
+  return B2R_OK;
+}
+
+// One chunk of the cooperative kernel with geometry C.
+template <typename C, typename I, typename V>
+int launch_big_chunk(const UpdateArgs<I, V> &a, int depth, cudaStream_t stream) {
+  B2R_TRY((allow_big_smem<C>(tree_update_kernel<I, V, C>)));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(depth + 1);
+  cfg.blockDim = dim3(C::kThreads);
+  cfg.dynamicSmemBytes = sizeof(typename C::Smem);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[3];
+  int n_attr = 0;
+  attr[n_attr].id = cudaLaunchAttributeCooperative;
+  attr[n_attr++].val.cooperative = 1;
+  if (chain_priority() != 0) {
+    attr[n_attr].id = cudaLaunchAttributePriority;
+    attr[n_attr++].val.priority = chain_priority();
+  }
+  if (tree_window().base != nullptr) {
+    attr[n_attr].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[n_attr].val.accessPolicyWindow.base_ptr = tree_window().base;
+    attr[n_attr].val.accessPolicyWindow.num_bytes = tree_window().bytes;
+    attr[n_attr].val.accessPolicyWindow.hitRatio = 1.0f;
+    attr[n_attr].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[n_attr++].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
+  B2R_CUDA(cudaLaunchKernelEx(&cfg, tree_update_kernel<I, V, C>, a));
+  B2R_LAUNCHED();
   return B2R_OK;
 }
 
@@ -677,15 +725,18 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     B2R_LAUNCHED();
     return B2R_OK;
   }
-  B2R_TRY(allow_big_smem(tree_update_kernel<I, V>));
-  for (int64_t base = 0; base < n; base += kTreeChunk) {
-    const int len = (int)((n - base) < kTreeChunk ? (n - base) : kTreeChunk);
+  // Up to 1024 entries (known on the host): the 256 x 4 geometry; above, chunks of
+  // 4096 through the 1024 x 4 one.
+  const bool compact = n <= BigCfg1024::kChunk;
+  const int64_t chunk = compact ? BigCfg1024::kChunk : BigCfg4096::kChunk;
+  for (int64_t base = 0; base < n; base += chunk) {
+    const int len = (int)((n - base) < chunk ? (n - base) : chunk);
     UpdateArgs<I, V> a;
     a.heap = t->heap;
     a.depth = t->depth;
     a.leaves = t->leaves;
     a.n = len;
-    a.padded = kTreeChunk;
+    a.padded = (int)chunk;
     a.indices = indices + base;
     a.values = values + base;
     a.mode = mode ? mode + base : nullptr;
@@ -694,31 +745,10 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     a.max_rec = t->max_rec;
     a.status = t->status;
     a.n_dev = n_dev;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(t->depth + 1);
-    cfg.blockDim = dim3(kBigThreads);
-    cfg.dynamicSmemBytes = sizeof(BigSmem);
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[3];
-    int n_attr = 0;
-    attr[n_attr].id = cudaLaunchAttributeCooperative;
-    attr[n_attr++].val.cooperative = 1;
-    if (chain_priority() != 0) {
-      attr[n_attr].id = cudaLaunchAttributePriority;
-      attr[n_attr++].val.priority = chain_priority();
-    }
-    if (tree_window().base != nullptr) {
-      attr[n_attr].id = cudaLaunchAttributeAccessPolicyWindow;
-      attr[n_attr].val.accessPolicyWindow.base_ptr = tree_window().base;
-      attr[n_attr].val.accessPolicyWindow.num_bytes = tree_window().bytes;
-      attr[n_attr].val.accessPolicyWindow.hitRatio = 1.0f;
-      attr[n_attr].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      attr[n_attr++].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = n_attr;
-    B2R_CUDA(cudaLaunchKernelEx(&cfg, tree_update_kernel<I, V>, a));
-    B2R_LAUNCHED();
+    if (compact)
+      B2R_TRY((launch_big_chunk<BigCfg1024>(a, t->depth, stream)));
+    else
+      B2R_TRY((launch_big_chunk<BigCfg4096>(a, t->depth, stream)));
   }
   return B2R_OK;
 }
