@@ -405,18 +405,23 @@ def measure_e2e(torch, wl, batch, steps, update_period=4, pipeline_depth=2,
   # N > 1: one trainer per rank over its own shard; `batch` is the GLOBAL batch, the
   # shard totals travel through a peer-memory exchange of the trainer's own, every
   # rank adds its own rows and gets the losses of the rows it served.
+  # a rank's network produces logits for the rows the rank serves (its share of the
+  # global batch, here capped at twice the mean share: +6 sigma at 8 ranks)
+  logit_rows = batch if world == 1 else min(batch, 2 * (batch // world))
   trainer = ra.ReplayTrainer(mem, NUM_ACTIONS, NUM_ATOMS, VMAX, batch_size=batch,
                              pipeline_depth=pipeline_depth,
-                             seed=wl.seed if world == 1 else 4321)
+                             seed=wl.seed if world == 1 else 4321,
+                             logit_rows=logit_rows)
   if world > 1:
     from dopamine_b200.replay_memory import sharded_replay
     trainer.set_exchange(sharded_replay.PeerExchange(rank=rank, world_size=world))
   rng = np.random.RandomState(3)
   frames = rng.randint(0, 256, size=(64, 84, 84)).astype(np.uint8)
-  online_h = wl.online[:batch].cpu().pin_memory()
-  target_h = wl.target[:batch].cpu().pin_memory()
+  online_h = wl.online[:logit_rows].cpu().pin_memory()
+  target_h = wl.target[:logit_rows].cpu().pin_memory()
   online_p, target_p = online_h.data_ptr(), target_h.data_ptr()
   counter = [0]
+  most_rows = [0]
   sentinel = prb.MAX_RECORDED_PRIORITY
   stream = wl.native.current_stream()
 
@@ -425,7 +430,10 @@ def measure_e2e(torch, wl, batch, steps, update_period=4, pipeline_depth=2,
       k = counter[0]
       counter[0] += 1
       mem.add(frames[k & 63], k % NUM_ACTIONS, 0.5, int(k % 1000 == 999), sentinel)
-    return trainer.step_pointers(online_p, target_p, stream)
+    done = trainer.step_pointers(online_p, target_p, stream)
+    if world > 1:
+      most_rows[0] = max(most_rows[0], trainer.last_rows)
+    return done
 
   for _ in range(20):
     one()
@@ -444,6 +452,7 @@ def measure_e2e(torch, wl, batch, steps, update_period=4, pipeline_depth=2,
     dist.all_reduce(slowest, op=dist.ReduceOp.MAX)
     dt = float(slowest.item())
   assert last == steps + 20 - 1, (last, steps)
+  assert most_rows[0] <= logit_rows, (most_rows[0], logit_rows)
   wl.native.check(wl.lib.b2r_check(wl.h, stream))
   row = 7056 + 16  # staged row: frame + action + reward + terminal (padded)
   h2d = world * (update_period * row + (online_h.numel() + target_h.numel()) * 4)
@@ -754,6 +763,34 @@ def run_reference(args):
   print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(local_rank):
+  """One process per GPU: run (and first-touch pinned memory) on the CPU cores the
+  GPU is attached to, as NCCL does for its own threads.  The host loop of a rank
+  reads and writes pinned buffers that its GPU accesses over PCIe; from the far
+  socket every such access crosses the inter-socket link as well."""
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+    phys = local_rank
+    if visible:
+      ids = [v for v in visible.split(',') if v.strip()]
+      if local_rank < len(ids) and ids[local_rank].strip().isdigit():
+        phys = int(ids[local_rank])
+    handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+    words = (os.cpu_count() + 63) // 64
+    mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+    cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64)
+            if (int(word) >> b) & 1]
+    cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+    if cpus:
+      os.sched_setaffinity(0, cpus)
+      return len(cpus)
+  except Exception:  # pylint: disable=broad-except
+    pass
+  return None
+
+
 # --------------------------------------------------------------------------- #
 def main():
   args = parse_args()
@@ -766,6 +803,7 @@ def main():
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
   torch.cuda.set_device(local_rank)
   dist = None
   if world > 1:
@@ -837,6 +875,8 @@ def main():
                   if world > 1 and args.exchange == 'p2p' else
                   '; NCCL all-gather of shard totals' if world > 1 else ''),
           'rng': 'device Philox4x32-10',
+          'cpu_affinity': ('GPU-local NUMA node (%d cores per rank)' % numa_cpus
+                           if numa_cpus else 'unbound'),
       },
       'gpu_launches': int(launches_per_step * args.steps),
       'clocks': clocks.summary(),

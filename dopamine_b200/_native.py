@@ -127,6 +127,7 @@ class TrainerConfig(ctypes.Structure):
       ('seed', c_uint64),
       ('pipeline_depth', c_int32),
       ('use_graph', c_int32),
+      ('logit_rows', c_int32),
   ]
 
 

@@ -306,7 +306,8 @@ class ReplayTrainer(object):
   """
 
   def __init__(self, memory, num_actions, num_atoms=51, vmax=10.,
-               batch_size=None, pipeline_depth=2, seed=0, use_graph=False):
+               batch_size=None, pipeline_depth=2, seed=0, use_graph=False,
+               logit_rows=None):
     self._memory = memory
     self._lib = _native.lib()
     cfg = _native.TrainerConfig()
@@ -318,6 +319,8 @@ class ReplayTrainer(object):
     cfg.seed = int(seed)
     cfg.pipeline_depth = int(pipeline_depth)
     cfg.use_graph = int(bool(use_graph))
+    cfg.logit_rows = int(logit_rows or 0)
+    self.logit_rows = int(logit_rows or cfg.batch)
     self.batch_size, self.num_actions, self.num_atoms = (
         cfg.batch, num_actions, num_atoms)
     handle = ctypes.c_void_p()
@@ -363,7 +366,7 @@ class ReplayTrainer(object):
 
   def step(self, online_logits, target_logits):
     """Queues one iteration; returns (losses or None, step number or -1)."""
-    shape = (self.batch_size, self.num_actions, self.num_atoms)
+    shape = (self.logit_rows, self.num_actions, self.num_atoms)
     pointers = []
     for x in (online_logits, target_logits):
       if hasattr(x, 'data_ptr'):  # torch CPU tensor (e.g. pinned)

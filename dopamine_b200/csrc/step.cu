@@ -233,19 +233,23 @@ int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
   *out = nullptr;
   if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
   if (cfg->batch <= 0 || cfg->batch > 60000 || cfg->num_actions <= 0 ||
-      cfg->num_atoms < 2 || cfg->pipeline_depth < 0 || cfg->pipeline_depth > 64)
+      cfg->num_atoms < 2 || cfg->pipeline_depth < 0 || cfg->pipeline_depth > 64 ||
+      cfg->logit_rows < 0 || cfg->logit_rows > cfg->batch)
     return fail(B2R_ERR_INVALID_ARGUMENT, "bad trainer configuration");
   b2r_trainer *t = new (std::nothrow) b2r_trainer();
   if (!t) return fail(B2R_ERR_INVALID_ARGUMENT, "out of host memory");
   t->buf = b;
   t->cfg = *cfg;
+  if (t->cfg.logit_rows == 0) t->cfg.logit_rows = cfg->batch;
   if (const char *e = std::getenv("B2R_TRAINER_GRAPH")) t->cfg.use_graph = std::atoi(e);
   const size_t B = (size_t)cfg->batch, A = (size_t)cfg->num_actions,
                N = (size_t)cfg->num_atoms;
   const size_t logit_bytes = B * A * N * sizeof(float);
   for (int set = 0; set < 2; ++set)
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < 2; ++k) {
       B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->logits[set][k]), logit_bytes));
+      B2R_CUDA(cudaMemset(t->logits[set][k], 0, logit_bytes));
+    }
   // tf.linspace(-vmax, vmax, N) as TF-1.x evaluates it: start + i * step in f32
   // (rainbow_agent.py:124-126).
   std::vector<float> z(N);
@@ -357,7 +361,7 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   b2r::g_host_trace.start();
   const int64_t n = t->submitted;
   const int set = (int)(n & 1);
-  const size_t logit_bytes = (size_t)t->cfg.batch * t->cfg.num_actions *
+  const size_t logit_bytes = (size_t)t->cfg.logit_rows * t->cfg.num_actions *
                              t->cfg.num_atoms * sizeof(float);
   // inputs: on the copy stream, beside the sampler; set `set` was last read by the
   // loss kernel of step n - 2.

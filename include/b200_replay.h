@@ -444,6 +444,11 @@ typedef struct {
                               d > 0: the losses of the step queued d calls earlier */
   int32_t use_graph;       /* != 0: after two eager steps the kernels of a step are
                               replayed as one captured CUDA graph per call          */
+  int32_t logit_rows;      /* rows of each logits tensor copied per step; 0 = batch.
+                              A sharded trainer's batch is the GLOBAL batch, but a
+                              rank's network only produces logits for the rows it
+                              serves: the caller passes (logit_rows, A, N) tensors and
+                              guarantees that a step never serves more rows          */
 } b2r_trainer_config;
 
 int b2r_trainer_create(b2r_buffer *buf, const b2r_trainer_config *config,
