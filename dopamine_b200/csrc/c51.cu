@@ -117,10 +117,12 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   float *tgt = sup + N;                          // [N] projected target
   float *onl = tgt + N;                          // [N] chosen online logits
   float *zs = onl + N;                           // [N] the support, staged
+  float *lgp = zs + N;                           // [N] log_softmax of the chosen logits
   __shared__ float s_q[32];
   __shared__ int s_a[32];
   __shared__ float s_red[32];
   __shared__ float s_scalar[4];  // tsum, w_b, m, denom
+  __shared__ float s_ce;
   __shared__ bool s_last;
   const float *z = a.u.support;
   B2R_MARK(0);
@@ -172,9 +174,30 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
       }
     }
     if (act == chosen) {
+      // log_softmax of the chosen action's online logits (rainbow_agent.py:262-271),
+      // by the warp that holds them, while the other warps do their softmaxes
+      float mo = -INFINITY;
 #pragma unroll
       for (int t = 0; t < PL; ++t)
-        if (lane + 32 * t < N) onl[lane + 32 * t] = xo[t];
+        if (lane + 32 * t < N) mo = fmaxf(mo, xo[t]);
+      mo = warp_max<FAST>(mo);
+      float ps = 0.f;
+#pragma unroll
+      for (int t = 0; t < PL; ++t)
+        if (lane + 32 * t < N) ps = __fadd_rn(ps, expf(__fsub_rn(xo[t], mo)));
+      const float den_o = warp_sum<FAST>(ps);
+      const float lse = logf(den_o);
+#pragma unroll
+      for (int t = 0; t < PL; ++t) {
+        if (lane + 32 * t < N) {
+          onl[lane + 32 * t] = xo[t];
+          lgp[lane + 32 * t] = __fsub_rn(__fsub_rn(xo[t], mo), lse);
+        }
+      }
+      if (lane == 0) {
+        s_scalar[2] = mo;
+        s_scalar[3] = den_o;
+      }
     }
     float m = -INFINITY;
 #pragma unroll
@@ -229,11 +252,23 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
 
   B2R_MARK(4);
   // ---- B. argmax action (first maximum, RA:238-248), projection (RA:381-494)
-  int win = 0;
-#pragma unroll 1
-  for (int w = 1; w < W; ++w) {
-    if (s_a[w] < 0) continue;
-    if (s_q[w] > s_q[win] || (s_q[w] == s_q[win] && s_a[w] < s_a[win])) win = w;
+  // every warp reduces the per-warp bests itself (5 shuffle steps instead of a
+  // serial scan of shared memory): highest q, ties to the smaller action index
+  int win = lane;
+  {
+    float q = lane < W ? s_q[lane] : 0.f;
+    int act = lane < W ? s_a[lane] : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float q2 = __shfl_xor_sync(0xffffffffu, q, o);
+      const int act2 = __shfl_xor_sync(0xffffffffu, act, o);
+      const int win2 = __shfl_xor_sync(0xffffffffu, win, o);
+      if (act2 >= 0 && (act < 0 || q2 > q || (q2 == q && act2 < act))) {
+        q = q2;
+        act = act2;
+        win = win2;
+      }
+    }
   }
   const float *next_p = smem + (size_t)win * N;
   const float z0 = zs[0], zlast = zs[N - 1];
@@ -279,46 +314,42 @@ __global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
   // ---- C. cross entropy (RA:262-271), priority (RA:290), weight (RA:279-280)
   const float *x = onl;
   if (warp == 0) {
-    float m = -INFINITY;
-#pragma unroll 1
-    for (int i = lane; i < N; i += 32) m = fmaxf(m, x[i]);
-    m = warp_max(m);
-    float psum = 0.f;
-#pragma unroll 1
-    for (int i = lane; i < N; i += 32) psum = __fadd_rn(psum, expf(__fsub_rn(x[i], m)));
-    const float denom = warp_sum(psum);
-    const float lse = logf(denom);
     float ce_part = 0.f, tsum_part = 0.f;
 #pragma unroll 1
     for (int i = lane; i < N; i += 32) {
       const float t = tgt[i];
-      const float logp = __fsub_rn(__fsub_rn(x[i], m), lse);
+      const float logp = lgp[i];
       ce_part = __fadd_rn(ce_part, __fmul_rn(t, logp));
       tsum_part = __fadd_rn(tsum_part, t);
     }
     const float ce = -warp_sum(ce_part);
     const float tsum = warp_sum(tsum_part);
     if (lane == 0) {
-      float w = 1.f;
-      if (a.u.sampling_probabilities) {
-        float mn = s_red[0];
-#pragma unroll 1
-        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) mn = fminf(mn, s_red[k]);
-        const float wmax = __fdiv_rn(1.0f, sqrtf(__fadd_rn(mn, 1e-10f)));
-        const float raw = __fdiv_rn(1.0f, sqrtf(__fadd_rn(my_prob, 1e-10f)));
-        w = __fdiv_rn(raw, wmax);
-      }
       a.u.loss[b] = ce;
       a.u.priorities[b] = sqrtf(__fadd_rn(ce, 1e-10f));
-      if (a.u.weights) a.u.weights[b] = w;
-      a.weighted[b] = __fmul_rn(w, ce);
       s_scalar[0] = tsum;
-      s_scalar[1] = w;
-      s_scalar[2] = m;
-      s_scalar[3] = denom;
+      s_ce = ce;
     }
   }
+  // importance weight (RA:279-280), by another warp beside the cross entropy
+  if (warp == (W > 1 ? 1 : 0) && lane == 0) {
+    float w = 1.f;
+    if (a.u.sampling_probabilities) {
+      float mn = pmin;  // handed over by the sampler, or reduced per warp above
+      if (!a.u.min_probability) {
+        mn = s_red[0];
+#pragma unroll 1
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) mn = fminf(mn, s_red[k]);
+      }
+      const float wmax = __fdiv_rn(1.0f, sqrtf(__fadd_rn(mn, 1e-10f)));
+      const float raw = __fdiv_rn(1.0f, sqrtf(__fadd_rn(my_prob, 1e-10f)));
+      w = __fdiv_rn(raw, wmax);
+    }
+    if (a.u.weights) a.u.weights[b] = w;
+    s_scalar[1] = w;
+  }
   __syncthreads();
+  if (threadIdx.x == 0) a.weighted[b] = __fmul_rn(s_scalar[1], s_ce);
 
   B2R_MARK(6);
   // ---- D. gradient of mean(w * ce) w.r.t. the online logits
@@ -409,7 +440,7 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
   a.warps = args->num_actions < 32 ? args->num_actions : 32;
   if (args->batch > 256) a.warps = (a.warps + 2) / 3;
   const int threads = a.warps * 32;
-  const size_t smem = ((size_t)a.warps + 4) * args->num_atoms * sizeof(float);
+  const size_t smem = ((size_t)a.warps + 5) * args->num_atoms * sizeof(float);
   if (smem > 48 * 1024 || args->num_atoms > 32 * b2r::kMaxAtomsPerLane)
     return fail(B2R_ERR_UNSUPPORTED, "num_atoms above 128 is not supported");
   if (args->batch > b2r::g_weighted_cap) {
