@@ -333,6 +333,34 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
       pos = mine_base + block_scan_flag(mine, warp_counts, &tile_mine);
       mine_base += tile_mine;
     }
+    // The usual case of the agent's batch — one CTA, one tile, every pick valid —
+    // needs none of the machinery below (slot lists, ticket, retries): one barrier
+    // says so, the rows are written and thread 0 closes the launch.
+    if (gridDim.x == 1 && n_tiles == 1 && __syncthreads_or(mine && !valid) == 0) {
+      float row_prio = INFINITY;
+      if (mine) {
+        a.out_idx[pos] = (int32_t)idx;
+        if (a.out_slots) a.out_slots[pos] = i;
+        if (fast_scalars) row_prio = finish_scalars(a.sc, pos, idx, row);
+        else if (a.with_scalars) row_prio = write_scalars(a.sc, pos, idx);
+      }
+      const bool want_min = a.with_scalars && a.min_prob_out != nullptr;
+      const float m = want_min ? block_min(row_prio, warp_mins) : INFINITY;
+      if (threadIdx.x == 0) {
+        const int rows = a.shard_ranges ? n_mine
+                                        : (a.num_shards > 1 ? mine_base : a.batch);
+        if (a.counter) *a.counter = draws_before + 1;
+        if (exchange) *a.xchg.seq = xseq;
+        a.info[0] = B2R_OK;
+        a.info[1] = 0;
+        a.info[2] = 0;
+        a.info[3] = rows;
+        if (a.count_out) *a.count_out = rows;
+        if (want_min) *a.min_prob_out = m;
+      }
+      B2R_MARK(8);
+      return;
+    }
     const int ipos = block_scan_flag(mine && !valid, warp_counts, &tile_inv);
     float my_prio = INFINITY;
     if (mine) {

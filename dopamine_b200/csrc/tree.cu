@@ -461,44 +461,71 @@ __device__ __forceinline__ void tree_update_small_body(const UpdateArgs<I, V> &a
   const int level = warp;
   const bool is_leaf = level == a.depth;
   const int shift = a.depth - level;
+  // The leaf warp gates every other level (they wait for its deltas at the barrier
+  // below).  With at most one entry per lane it needs no sort: __match_any_sync finds
+  // the lanes that share a leaf, the lowest of them walks its group in lane (= batch)
+  // order; the leaf values are already in flight when the groups are formed.
+  const bool leaf_by_match = is_leaf && n_eff <= 32;
+  const int64_t base = ((int64_t)1) << level;
   int p2 = 32;
   while (p2 < n_eff) p2 <<= 1;
-  for (int k = lane; k < p2; k += 32)
-    keys[k] = k < n_eff
-                  ? (((uint64_t)((int64_t)a.indices[k] >> shift)) << 32) | (uint32_t)k
-                  : kPadKey;
-  __syncwarp();
+  if (!leaf_by_match) {
+    for (int k = lane; k < p2; k += 32)
+      keys[k] = k < n_eff
+                    ? (((uint64_t)((int64_t)a.indices[k] >> shift)) << 32) | (uint32_t)k
+                    : kPadKey;
+    __syncwarp();
+  }
   B2R_MARK(3);
-  if (level != 0) warp_bitonic_sort(keys, p2, lane);
+  if (level != 0 && !leaf_by_match) warp_bitonic_sort(keys, p2, lane);
   B2R_MARK(4);
 
-  // (Loops below stay rolled: this code runs once per launch on a cold
-  // instruction cache, so compact code beats unrolling.)
-  const int64_t base = ((int64_t)1) << level;
+  // (Loops below stay rolled: compact code beats unrolling in these one-shot phases.)
   if (is_leaf) {
+    // (loaded here, not where it is compared: one memory round trip less at the end)
+    const double recorded_max = lane == 0 ? *a.max_rec : 0.0;
     double local_max = 0.0;
 #pragma unroll 1
     for (int k = lane; k < n_eff; k += 32) local_max = fmax(local_max, vals[k]);
 #pragma unroll 1
     for (int off = 16; off > 0; off >>= 1)
       local_max = fmax(local_max, __shfl_xor_sync(0xffffffffu, local_max, off));
+    if (leaf_by_match) {
+      const bool in = lane < n_eff;
+      // lanes without an entry get distinct keys that no leaf index can take
+      const long long idx = in ? (long long)a.indices[lane] : -1ll - lane;
+      double leaf = in ? a.heap[base + idx] : 0.0;
+      const unsigned same = __match_any_sync(0xffffffffu, idx);
+      if (in && lane == __ffs(same) - 1) {
+        unsigned rest = same;
 #pragma unroll 1
-    for (int p = lane; p < n_eff; p += 32) {
-      const uint32_t node = (uint32_t)(keys[p] >> 32);
-      if (p > 0 && (uint32_t)(keys[p - 1] >> 32) == node) continue;
-      double leaf = a.heap[base + node];
-#pragma unroll 1
-      for (int q = p; q < n_eff && (uint32_t)(keys[q] >> 32) == node; ++q) {
-        const uint32_t k = (uint32_t)keys[q];
-        const double d = __dsub_rn(vals[k], leaf);
-        leaf = __dadd_rn(leaf, d);
-        vals[k] = d;
+        while (rest) {
+          const int k = __ffs(rest) - 1;
+          rest &= rest - 1;
+          const double d = __dsub_rn(vals[k], leaf);
+          leaf = __dadd_rn(leaf, d);
+          vals[k] = d;
+        }
+        a.heap[base + idx] = leaf;
       }
-      a.heap[base + node] = leaf;
+    } else {
+#pragma unroll 1
+      for (int p = lane; p < n_eff; p += 32) {
+        const uint32_t node = (uint32_t)(keys[p] >> 32);
+        if (p > 0 && (uint32_t)(keys[p - 1] >> 32) == node) continue;
+        double leaf = a.heap[base + node];
+#pragma unroll 1
+        for (int q = p; q < n_eff && (uint32_t)(keys[q] >> 32) == node; ++q) {
+          const uint32_t k = (uint32_t)keys[q];
+          const double d = __dsub_rn(vals[k], leaf);
+          leaf = __dadd_rn(leaf, d);
+          vals[k] = d;
+        }
+        a.heap[base + node] = leaf;
+      }
     }
     if (lane == 0) {
-      const double m = *a.max_rec;
-      if (n_eff > 0 && local_max > m) *a.max_rec = local_max;
+      if (n_eff > 0 && local_max > recorded_max) *a.max_rec = local_max;
       if (n_eff < n) {
         a.status[0] = s_stop_code;
         a.status[1] = a.k_base + n_eff;

@@ -159,18 +159,18 @@ __device__ __forceinline__ int stage_top_levels(const double *__restrict__ heap,
                                                 int depth, double *top) {
   const int top_depth = depth < kTopLevels ? depth : kTopLevels;
   const int count = 2 << top_depth;
-  // 4 independent loads in flight per thread and iteration; the loop stays rolled
-  // (compact code matters more than the last bit of memory-level parallelism).
+  // 8 independent loads in flight per thread and iteration: 256 threads stage the
+  // 2048 nodes of levels 0..10 in ONE round trip (two with 4 loads per iteration).
 #pragma unroll 1
-  for (int i0 = threadIdx.x; i0 < count; i0 += 4 * blockDim.x) {
-    double r[4];
+  for (int i0 = threadIdx.x; i0 < count; i0 += 8 * blockDim.x) {
+    double r[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const int i = i0 + j * blockDim.x;
       r[j] = i < count ? heap[i] : 0.0;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const int i = i0 + j * blockDim.x;
       if (i < count) top[i] = r[j];
     }
