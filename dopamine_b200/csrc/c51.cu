@@ -106,8 +106,12 @@ constexpr int kMaxAtomsPerLane = 4;  // num_atoms <= 128
 
 // PL = atoms per lane (2 covers C51's 51 atoms; fewer unrolled copies = less
 // straight-line code to fetch on a cold instruction cache).
+// The large-batch instance runs a third of the warps per row (<= 11 warps) and wants
+// many rows resident per SM: bounds that keep it at 32 registers (10 CTAs of 192
+// threads per SM); the small-batch instance runs one warp per action.
 template <int PL, bool FAST>
-__global__ void __launch_bounds__(1024) c51_loss_kernel(LossArgs a) {
+__global__ void __launch_bounds__(FAST ? 384 : 1024, FAST ? 5 : 1)
+c51_loss_kernel(LossArgs a) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x;
@@ -461,7 +465,9 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
     const char *e = std::getenv("B2R_C51_FAST");
     return e ? std::atoi(e) : -1;
   }();
-  const bool fast = force_fast >= 0 ? force_fast != 0 : args->batch > 256;
+  // (the unrolled instance is compiled for at most 384 threads per CTA)
+  const bool fast = (force_fast >= 0 ? force_fast != 0 : args->batch > 256) &&
+                    threads <= 384;
   if (args->num_atoms <= 64) {
     if (fast)
       B2R_CUDA(b2r::launch(b2r::c51_loss_kernel<2, true>, dim3(args->batch),
