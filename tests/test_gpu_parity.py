@@ -395,7 +395,9 @@ def test_projection_shape_errors(gpu):
 
 @pytest.mark.parametrize('batch,actions,atoms', [(32, 18, 51), (256, 4, 51),
                                                  (1024, 18, 51), (7, 3, 5),
-                                                 (4096, 18, 51), (33, 6, 101)])
+                                                 (4096, 18, 51), (33, 6, 101),
+                                                 (1000, 6, 51), (600, 32, 51),
+                                                 (300, 40, 21)])
 def test_c51_loss_matches_numpy_restatement(gpu, batch, actions, atoms):
   """Projection, loss, new priorities and IS weights within 1e-6 relative of the
   f32 numpy restatement (north_star tolerance; TF's own assertAllClose default)."""

@@ -372,15 +372,17 @@ def test_peer_exchange_times_out_instead_of_hanging(gpu):
   assert 'did not publish' in gpu.native.last_error()
 
 
-def test_sharded_fused_step_matches_oracles(gpu):
-  """b2r_train_step_sharded_device on 4 emulated ranks: each rank's rows (batch
-  columns at its indices, losses, write-back) against the oracles, the rows of all
-  ranks partitioning the global batch."""
+@pytest.mark.parametrize('global_batch', [256, 2048])
+def test_sharded_fused_step_matches_oracles(gpu, global_batch):
+  """b2r_train_step_sharded_device on 4 emulated ranks (one sampling CTA up to a
+  global batch of 256, tiles over each rank's stratum range above): each rank's rows
+  (batch columns at its indices, losses, write-back) against the oracles, the rows of
+  all ranks partitioning the global batch."""
   import ctypes
   from dopamine_b200.replay_memory import sharded_replay
   torch, native = gpu.torch, gpu.native
   lib = native.lib()
-  num_shards, cap, global_batch = 4, 50000, 256
+  num_shards, cap = 4, 50000
   shards = [_filled(gpu, cap, 32, seed=40 + g, hot=(g == 1)) for g in range(num_shards)]
   exchanges = sharded_replay.PeerExchange.emulated(num_shards)
   rng = np.random.RandomState(8)
