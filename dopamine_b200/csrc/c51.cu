@@ -397,6 +397,296 @@ c51_loss_kernel(LossArgs a) {
   }
 }
 
+// ---- throughput instance (batches above 256 rows, num_atoms <= 64) ----------
+// One WARP per batch row, kRowWarps rows per CTA.  The CTA-per-row kernel above
+// spends most of its issue slots on 5-step shuffle reductions whose lanes are 80 %
+// idle on the second atom pass (51 atoms over 32 lanes) and on block barriers: 6 300
+// warp instructions per row at A = 18, N = 51.  Here G lanes share an action and hold
+// 64 / G atoms each, so one warp instruction serves 32 / G actions, a reduction is
+// log2(G) shuffle steps, and nothing but __syncwarp separates the phases.  The
+// arithmetic is the same f32 sequence per element (exp of the max-shifted logit,
+// probabilities, q = sum z p, first maximum), except that a probability is
+// e * (1 / denom) instead of e / denom (<= 1 ulp apart; parity bound 1e-6 relative).
+constexpr int kRowWarps = 4;
+constexpr int kRowAtoms = 64;
+
+template <int G>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Pad value of the lanes beyond num_atoms (and of the groups beyond num_actions):
+// finite, so max-shifting never forms inf - inf, and exp(pad - max) is exactly 0.
+constexpr float kLogitPad = -1e30f;
+
+// NC = num_atoms at compile time (51: the lanes' bounds tests fold away), 0 = runtime.
+template <int G, int NC>
+__global__ void __launch_bounds__(kRowWarps * 32)
+c51_loss_rows_kernel(LossArgs a) {
+  constexpr int PL = NC ? (NC + G - 1) / G : kRowAtoms / G;  // atoms per lane
+  constexpr int GROUPS = 32 / G;     // actions per warp instruction
+  __shared__ float s_bestp[kRowWarps][kRowAtoms];  // greedy action's probabilities
+  __shared__ float s_sup[kRowWarps][kRowAtoms];    // Bellman support
+  __shared__ float s_red[kRowWarps];
+  __shared__ bool s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / G, l = lane % G;
+  const int N = NC ? NC : a.u.num_atoms, A = a.u.num_actions;
+  const float *__restrict__ z = a.u.support;
+  pdl_release();
+  pdl_acquire();
+  const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
+  if ((int)blockIdx.x * kRowWarps >= rows) return;  // (no mean loss with batch_count)
+  const int b = blockIdx.x * kRowWarps + warp;
+  const bool row_ok = b < rows;
+
+  // min over the batch of the sampling probabilities (IS-weight normaliser): handed
+  // in by the sampler when it produced the batch, else reduced by the CTA.
+  float pmin = INFINITY;
+  if (a.u.sampling_probabilities) {
+    if (a.u.min_probability) {
+      pmin = *a.u.min_probability;
+    } else {
+      for (int k = threadIdx.x; k < rows; k += blockDim.x)
+        pmin = fminf(pmin, a.u.sampling_probabilities[k]);
+      pmin = -group_max<32>(-pmin);
+      if (lane == 0) s_red[warp] = pmin;
+      __syncthreads();
+      pmin = s_red[0];
+#pragma unroll
+      for (int k = 1; k < kRowWarps; ++k) pmin = fminf(pmin, s_red[k]);
+      __syncthreads();  // s_red is reused by the mean-loss reduction
+    }
+  }
+
+  if (row_ok) {
+    const int chosen = a.u.actions[b];
+    const float r = a.u.rewards[b];
+    const float term = (float)a.u.terminals[b];
+    const float my_prob = a.u.sampling_probabilities ? a.u.sampling_probabilities[b] : 1.f;
+    const float *__restrict__ trow = a.u.target_logits + (size_t)b * A * N;
+    const float *__restrict__ orow = a.u.online_logits + (size_t)b * A * N;
+    float zl[PL], xn[PL];
+#pragma unroll
+    for (int t = 0; t < PL; ++t) {
+      const int i = l + G * t;
+      zl[t] = i < N ? z[i] : 0.f;
+      xn[t] = (i < N && grp < A) ? trow[grp * N + i] : kLogitPad;
+    }
+    float xo[2];  // the chosen action's online logits, atoms lane and lane + 32
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      xo[t] = lane + 32 * t < N ? orow[chosen * N + lane + 32 * t] : kLogitPad;
+
+    // ---- A. per-action softmax + q-value (atari_lib.py:141-143), GROUPS actions per
+    // round; the next round's logits are in flight while this one is reduced
+    float best_q = 0.f;
+    int best_a = -1;
+    float bp[PL];
+#pragma unroll
+    for (int t = 0; t < PL; ++t) bp[t] = 0.f;
+    const int rounds = (A + GROUPS - 1) / GROUPS;
+#pragma unroll 1
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int act = rd * GROUPS + grp;
+      const bool valid = act < A;
+      float xt[PL];
+#pragma unroll
+      for (int t = 0; t < PL; ++t) xt[t] = xn[t];
+      const int nact = act + GROUPS;
+#pragma unroll
+      for (int t = 0; t < PL; ++t) {
+        const int i = l + G * t;
+        xn[t] = (i < N && nact < A) ? trow[nact * N + i] : kLogitPad;
+      }
+      float m = xt[0];
+#pragma unroll
+      for (int t = 1; t < PL; ++t) m = fmaxf(m, xt[t]);
+      m = group_max<G>(m);
+      float e[PL];
+      float psum = 0.f;
+#pragma unroll
+      for (int t = 0; t < PL; ++t) {
+        e[t] = expf(__fsub_rn(xt[t], m));  // pads: exactly 0
+        psum = __fadd_rn(psum, e[t]);
+      }
+      const float denom = group_sum<G>(psum);  // >= 1: the maximum contributes 1
+      const float inv = __frcp_rn(denom);
+      float qpart = 0.f;
+#pragma unroll
+      for (int t = 0; t < PL; ++t) {
+        e[t] = __fmul_rn(e[t], inv);
+        qpart = __fadd_rn(qpart, __fmul_rn(zl[t], e[t]));
+      }
+      const float q = group_sum<G>(qpart);
+      if (valid && (best_a < 0 || q > best_q)) {  // strict > keeps the first maximum
+        best_q = q;
+        best_a = act;
+#pragma unroll
+        for (int t = 0; t < PL; ++t) bp[t] = e[t];
+      }
+    }
+    // first maximum over the groups (RA:238-248): highest q, ties to the smaller action
+    const int own_a = best_a;
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) {
+      const float q2 = __shfl_xor_sync(0xffffffffu, best_q, o);
+      const int a2 = __shfl_xor_sync(0xffffffffu, best_a, o);
+      if (a2 >= 0 && (best_a < 0 || q2 > best_q || (q2 == best_q && a2 < best_a))) {
+        best_q = q2;
+        best_a = a2;
+      }
+    }
+    if (own_a == best_a && own_a >= 0) {
+#pragma unroll
+      for (int t = 0; t < PL; ++t)
+        if (l + G * t < N) s_bestp[warp][l + G * t] = bp[t];
+    }
+
+    // log_softmax of the chosen action's online logits (rainbow_agent.py:262-271):
+    // atoms lane, lane + 32 — the layout of the projection below
+    float mo = fmaxf(xo[0], xo[1]);
+    mo = group_max<32>(mo);
+    const float eo0 = expf(__fsub_rn(xo[0], mo)), eo1 = expf(__fsub_rn(xo[1], mo));
+    const float den_o = group_sum<32>(__fadd_rn(eo0, eo1));  // pads add exactly 0
+    const float lse = logf(den_o);
+    const float lgp[2] = {__fsub_rn(__fsub_rn(xo[0], mo), lse),
+                          __fsub_rn(__fsub_rn(xo[1], mo), lse)};
+    // Bellman support (rainbow_agent.py:229-235)
+    const float live = __fsub_rn(1.0f, term);
+    const float gwt = __fmul_rn(a.u.cumulative_gamma, live);
+    for (int j = lane; j < N; j += 32) s_sup[warp][j] = __fadd_rn(r, __fmul_rn(gwt, z[j]));
+    __syncwarp();
+
+    // ---- B. projection (RA:381-494).  hat(i, j) is exactly 0 unless
+    // |clip(s_j) - z_i| < dz, and the Bellman atoms s_j = r + g z_j are non-decreasing
+    // in j (g >= 0), so the j that reach atom i form one interval: s_j inside
+    // (z_i - dz, z_i + dz), i.e. lo < j < hi in units of atoms, open-ended below for
+    // the first atom and above for the last (clipping).  Each lane sums the
+    // reference's expression in ascending j over [floor(lo), floor(hi) + 1]: one
+    // spare position either side, against a rounding error of lo / hi below 1e-4.
+    // Skipped terms are exact zeros, so the sum is the dense form's.
+    const float *sup = s_sup[warp], *next_p = s_bestp[warp];
+    const float z0 = z[0], zlast = z[N - 1];
+    const float dz = __fsub_rn(z[1], z0);
+    float tg[2] = {0.f, 0.f};
+    float ce_part = 0.f, tsum_part = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int i = lane + 32 * t;
+      if (i < N) {
+        const float zi = z[i];
+        float acc = 0.f;
+        if (gwt == 0.f) {
+          // terminal row: every s_j is r, so hat(i, .) is one number, and it is 0 for
+          // all but the (at most two) atoms next to clip(r)
+          const float clipped = fminf(fmaxf(sup[0], z0), zlast);
+          const float gap = fabsf(__fsub_rn(clipped, zi));
+          if (gap < dz) {
+            float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
+            hat = fminf(fmaxf(hat, 0.f), 1.f);
+#pragma unroll 1
+            for (int j = 0; j < N; ++j) acc = __fadd_rn(acc, __fmul_rn(hat, next_p[j]));
+          }
+        } else {
+          int jl = 0, jh = N - 1;
+          if (gwt > 0.f) {
+            const float inv = __fdividef(1.0f, gwt * dz);
+            const float lo = (zi - dz - r - gwt * z0) * inv;
+            const float hi = (zi + dz - r - gwt * z0) * inv;
+            if (i > 0 && lo > 0.f) jl = min(N - 1, (int)fminf(lo, 1e6f));
+            if (i < N - 1 && hi < (float)(N - 2)) jh = max(0, (int)fmaxf(hi, -1e6f) + 1);
+          }
+#pragma unroll 1
+          for (int j = jl; j <= jh; ++j) {
+            const float clipped = fminf(fmaxf(sup[j], z0), zlast);
+            const float gap = fabsf(__fsub_rn(clipped, zi));
+            if (gap < dz) {
+              float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
+              hat = fminf(fmaxf(hat, 0.f), 1.f);
+              acc = __fadd_rn(acc, __fmul_rn(hat, next_p[j]));
+            }
+          }
+        }
+        tg[t] = acc;
+        if (a.u.target) a.u.target[(size_t)b * N + i] = acc;
+        ce_part = __fadd_rn(ce_part, __fmul_rn(acc, lgp[t]));
+        tsum_part = __fadd_rn(tsum_part, acc);
+      }
+    }
+
+    // ---- C. cross entropy (RA:262-271), priority (RA:290), weight (RA:279-280)
+    const float ce = -group_sum<32>(ce_part);
+    const float tsum = group_sum<32>(tsum_part);
+    float w = 1.f;
+    if (a.u.sampling_probabilities) {
+      const float wmax = __fdiv_rn(1.0f, sqrtf(__fadd_rn(pmin, 1e-10f)));
+      const float raw = __fdiv_rn(1.0f, sqrtf(__fadd_rn(my_prob, 1e-10f)));
+      w = __fdiv_rn(raw, wmax);
+    }
+    if (lane == 0) {
+      a.u.loss[b] = ce;
+      a.u.priorities[b] = sqrtf(__fadd_rn(ce, 1e-10f));
+      if (a.u.weights) a.u.weights[b] = w;
+      a.weighted[b] = __fmul_rn(w, ce);
+    }
+
+    // ---- D. gradient of mean(w * ce) w.r.t. the online logits
+    if (a.u.grad_logits) {
+      const float scale = __fmul_rn(w, __fdiv_rn(1.0f, (float)rows));
+      float *g = a.u.grad_logits + (size_t)b * A * N;
+      float v[2] = {0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int i = lane + 32 * t;
+        if (i < N) {
+          const float p = __fdiv_rn(t == 0 ? eo0 : eo1, den_o);
+          v[t] = __fmul_rn(__fsub_rn(__fmul_rn(p, tsum), tg[t]), scale);
+        }
+      }
+      for (int act = 0; act < A; ++act) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int i = lane + 32 * t;
+          if (i < N) g[act * N + i] = act == chosen ? v[t] : 0.f;
+        }
+      }
+    }
+  }
+
+  // ---- mean weighted loss: the last CTA to finish reduces in a fixed order.
+  if (a.u.mean_weighted_loss == nullptr) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(a.ticket, 1u);
+    s_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < a.u.batch; k += blockDim.x)
+    acc = __fadd_rn(acc, __ldcg(a.weighted + k));
+  acc = group_sum<32>(acc);
+  if (lane == 0) s_red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float total = 0.f;
+    for (int k = 0; k < kRowWarps; ++k) total = __fadd_rn(total, s_red[k]);
+    *a.u.mean_weighted_loss = __fdiv_rn(total, (float)a.u.batch);
+    *a.ticket = 0u;  // ready for the next launch
+  }
+}
+
 float *g_weighted = nullptr;
 unsigned int *g_ticket = nullptr;
 int g_weighted_cap = 0;
@@ -461,6 +751,30 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
   }
   a.weighted = b2r::g_weighted;
   a.ticket = b2r::g_ticket;
+  // Above kRowsMinBatch rows: one warp per row (B2R_C51_ROWS_MIN overrides the
+  // threshold, B2R_C51_GROUP = 16 picks the half-warp-per-action instance).
+  static const int rows_min = [] {
+    const char *e = std::getenv("B2R_C51_ROWS_MIN");
+    return e ? std::atoi(e) : 257;
+  }();
+  static const int rows_group = [] {
+    const char *e = std::getenv("B2R_C51_GROUP");
+    return e ? std::atoi(e) : 8;
+  }();
+  if (args->batch >= rows_min && args->num_atoms <= b2r::kRowAtoms) {
+    const int blocks = (args->batch + b2r::kRowWarps - 1) / b2r::kRowWarps;
+    const dim3 grid(blocks), block(b2r::kRowWarps * 32);
+    if (rows_group == 16)
+      B2R_CUDA(b2r::launch(b2r::c51_loss_rows_kernel<16, 0>, grid, block, 0, s, a));
+    else if (rows_group == 4 && args->num_atoms == 51)
+      B2R_CUDA(b2r::launch(b2r::c51_loss_rows_kernel<4, 51>, grid, block, 0, s, a));
+    else if (args->num_atoms == 51)
+      B2R_CUDA(b2r::launch(b2r::c51_loss_rows_kernel<8, 51>, grid, block, 0, s, a));
+    else
+      B2R_CUDA(b2r::launch(b2r::c51_loss_rows_kernel<8, 0>, grid, block, 0, s, a));
+    B2R_LAUNCHED();
+    return B2R_OK;
+  }
   static const int force_fast = [] {
     const char *e = std::getenv("B2R_C51_FAST");
     return e ? std::atoi(e) : -1;

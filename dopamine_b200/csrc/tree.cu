@@ -45,6 +45,9 @@ struct UpdateArgs {
   double *max_rec;
   int64_t *status;
   const int32_t *n_dev;  // nullable: device-side element count of the whole batch
+  // internal levels whose average chain (n >> level) is at least this long run their
+  // ordered add-chains as a verified scan (chains_by_verified_scan); 0 = never
+  int scan_min_chain = 0;
 };
 
 // Add-path batches may ask for "whatever max_recorded_priority is when this entry
@@ -154,22 +157,31 @@ __device__ __forceinline__ bool leaf_deltas_hashed(const UpdateArgs<I, V> &a, in
   __shared__ uint32_t d_idx[kMaxDup], d_k[kMaxDup], ds_idx[kMaxDup], ds_k[kMaxDup];
   __shared__ int s_ndup;
   constexpr uint32_t kEmpty = 0xffffffffu;
+  // every global load of the pass is issued before the hash set is touched: the
+  // indices first, then the leaves they point at (in flight while the set fills)
+  uint32_t my_idx[kBigItems], my_slot[kBigItems];
+  double my_leaf[kBigItems];
+#pragma unroll
+  for (int j = 0; j < kBigItems; ++j) {
+    const int k = threadIdx.x + j * kBigThreads;
+    my_idx[j] = k < n_eff ? (uint32_t)a.indices[k] : kEmpty;
+  }
+#pragma unroll
+  for (int j = 0; j < kBigItems; ++j) {
+    my_leaf[j] = 0.0;
+    my_slot[j] = 0;
+    if (my_idx[j] != kEmpty) my_leaf[j] = a.heap[a.leaves + my_idx[j]];
+  }
   for (int i = threadIdx.x; i < kHashSlots; i += blockDim.x) {
     h.key[i] = kEmpty;
     h.count[i] = 0;
   }
   if (threadIdx.x == 0) s_ndup = 0;
   __syncthreads();
-  uint32_t my_idx[kBigItems], my_slot[kBigItems];
-  double my_leaf[kBigItems];
 #pragma unroll
   for (int j = 0; j < kBigItems; ++j) {
-    const int k = threadIdx.x + j * kBigThreads;
-    my_idx[j] = kEmpty;
-    if (k < n_eff) {
-      const uint32_t idx = (uint32_t)a.indices[k];
-      my_idx[j] = idx;
-      my_leaf[j] = a.heap[a.leaves + idx];  // in flight while the hash set fills
+    if (my_idx[j] != kEmpty) {
+      const uint32_t idx = my_idx[j];
       uint32_t slot = (idx * 2654435761u) >> (32 - kHashBits);
       while (true) {
         const uint32_t old = atomicCAS(&h.key[slot], kEmpty, idx);
@@ -229,6 +241,152 @@ __device__ __forceinline__ bool leaf_deltas_hashed(const UpdateArgs<I, V> &a, in
   return true;
 }
 
+// Ordered fp64 add-chains without the serial dependence, when the data allow it.
+//
+// For every node the reference adds the deltas below it in batch order, rounding
+// after each add (sum_tree.py:198-205); at the root that is a chain of n dependent
+// DADDs (25 us at n = 4096), and fp64 addition is not associative, so a parallel
+// prefix sum has no right to the same bits.  But it usually HAS them: priorities are
+// f32 numbers cast to f64, so the deltas are multiples of 2^-32 or coarser while a
+// node worth 2^20 has an ulp of 2^-33 — no add in the chain rounds at all, and any
+// summation order gives the sequential result.  So: run a segmented prefix scan
+// (segment = node, base = the node's stored value), then CHECK the sequential
+// recurrence  P[p] == fl(P[p-1] + d[p])  at every position, bit for bit.  Positions
+// inside a thread satisfy it by construction (the thread re-walks its ITEMS entries
+// from its carry-in); what is checked is each thread's carry-in against the value its
+// left neighbour actually ended on.  If all hold, induction from the segment heads
+// makes P the sequential chain.  A carry that fails is replaced by a fresh segment
+// head  fl(P[p-1] + d[p])  taken from the neighbour's verified value and the scan is
+// repeated (every round fixes at least the first failure of each segment); after
+// kScanRounds rounds the caller falls back to the serial chains, which have read and
+// written nothing yet.  Returns true when the nodes were written.
+constexpr int kScanRounds = 3;
+
+template <typename C>
+__device__ __forceinline__ bool chains_by_verified_scan(double *__restrict__ level_nodes,
+                                                        const double *node_val,
+                                                        const uint32_t *node,
+                                                        const double *sorted_delta,
+                                                        int n_eff) {
+  constexpr int T = C::kThreads, ITEMS = C::kItems, WARPS = T / 32;
+  static_assert(WARPS <= 32, "one warp scans the warp totals");
+  __shared__ double s_last[T];
+  __shared__ double s_wv[32];
+  __shared__ int s_wf[32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  double d[ITEMS], hv[ITEMS], P[ITEMS];
+  uint32_t nd[ITEMS];
+  bool head[ITEMS];
+  const int p0 = t * ITEMS;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int p = p0 + j;
+    const bool in = p < n_eff;
+    nd[j] = in ? node[p] : 0xffffffffu;
+    d[j] = in ? sorted_delta[p] : 0.0;
+    const uint32_t before = j > 0 ? nd[j - 1] : (p > 0 && in ? node[p - 1] : 0xfffffffeu);
+    head[j] = !in || before != nd[j];   // (pads are heads worth 0: they carry nothing)
+    hv[j] = 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j)  // node_val[j]: the stored value of a head's node
+    if (head[j] && p0 + j < n_eff) hv[j] = __dadd_rn(node_val[j], d[j]);
+  const bool checked = t > 0 && p0 < n_eff && !head[0];  // takes a carry from the left
+  bool promoted = false;
+  bool ok = false;
+#pragma unroll 1
+  for (int round = 0; round < kScanRounds; ++round) {
+    // the thread's entries as one scan element: (value, "contains a head")
+    double v = head[0] ? hv[0] : d[0];
+    int f = head[0] ? 1 : 0;
+#pragma unroll
+    for (int j = 1; j < ITEMS; ++j) {
+      if (head[j]) {
+        v = hv[j];
+        f = 1;
+      } else {
+        v = __dadd_rn(v, d[j]);
+      }
+    }
+    // inclusive segmented scan over the warp, then over the warp totals
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double v2 = __shfl_up_sync(0xffffffffu, v, o);
+      const int f2 = __shfl_up_sync(0xffffffffu, f, o);
+      if (lane >= o) {
+        if (!f) v = __dadd_rn(v2, v);
+        f |= f2;
+      }
+    }
+    if (lane == 31) {
+      s_wv[warp] = v;
+      s_wf[warp] = f;
+    }
+    const double ev = __shfl_up_sync(0xffffffffu, v, 1);  // lanes before this one
+    const int ef = __shfl_up_sync(0xffffffffu, f, 1);
+    __syncthreads();
+    if (warp == 0) {
+      double wv = lane < WARPS ? s_wv[lane] : 0.0;
+      int wf = lane < WARPS ? s_wf[lane] : 1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double v2 = __shfl_up_sync(0xffffffffu, wv, o);
+        const int f2 = __shfl_up_sync(0xffffffffu, wf, o);
+        if (lane >= o) {
+          if (!wf) wv = __dadd_rn(v2, wv);
+          wf |= f2;
+        }
+      }
+      s_wv[lane] = wv;
+    }
+    __syncthreads();
+    double carry = 0.0;  // (thread 0 starts on a head and never uses it)
+    if (lane > 0)
+      carry = (ef || warp == 0) ? ev : __dadd_rn(s_wv[warp - 1], ev);
+    else if (warp > 0)
+      carry = s_wv[warp - 1];
+    double acc = carry;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      acc = head[j] ? hv[j] : __dadd_rn(acc, d[j]);
+      P[j] = acc;
+    }
+    s_last[t] = acc;
+    __syncthreads();
+    bool bad = false;
+    if (checked) {
+      const double left = s_last[t - 1];
+      if (promoted) {
+        const double need = __dadd_rn(left, d[0]);
+        if (__double_as_longlong(need) != __double_as_longlong(hv[0])) {
+          hv[0] = need;
+          bad = true;
+        }
+      } else if (__double_as_longlong(carry) != __double_as_longlong(left)) {
+        promoted = true;
+        head[0] = true;
+        hv[0] = __dadd_rn(left, d[0]);
+        bad = true;
+      }
+    }
+    if (!__syncthreads_or(bad)) {
+      ok = true;
+      break;
+    }
+  }
+  if (!ok) return false;
+#pragma unroll
+  for (int j = 0; j < ITEMS; ++j) {
+    const int p = p0 + j;
+    if (p < n_eff) {
+      const uint32_t after = p + 1 < n_eff ? (j + 1 < ITEMS ? nd[j + 1] : node[p + 1])
+                                           : 0xffffffffu;
+      if (after != nd[j]) level_nodes[nd[j]] = P[j];
+    }
+  }
+  return true;
+}
+
 template <typename I, typename V, typename C>
 __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, V> a) {
   constexpr int kBigItems = C::kItems;
@@ -245,6 +403,7 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
   const bool is_leaf = level == a.depth;
   B2R_MARK_CTA(0, 0);
   B2R_MARK_CTA(16, a.depth);
+  B2R_MARK_CTA(22, a.depth - 1);
   int n = a.n;
   if (a.n_dev) {
     const int64_t left = (int64_t)*a.n_dev - a.k_base;
@@ -284,6 +443,8 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
 
   // 2. leaf CTA: the sort-free pass when duplicates are few (the usual case)
   B2R_MARK_CTA(17, a.depth);
+  B2R_MARK_CTA(23, a.depth - 1);
+  B2R_MARK_CTA(29, 0);
   bool leaf_done = false;
   if (is_leaf) {
     // max_recorded_priority = max(value, current) over the applied prefix
@@ -340,10 +501,28 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
     for (int k = threadIdx.x; k < n_eff; k += blockDim.x) a.delta[k] = vals[k];
   }
 
+  // Internal levels: thread t owns the grouped positions 4t .. 4t+3; the stored value
+  // of every node whose group starts there is fetched now, so that its DRAM round
+  // trip hides behind the wait for the leaf deltas (only this CTA writes this level).
+  const int64_t base = ((int64_t)1) << level;
+  double node_val[kBigItems];
+#pragma unroll
+  for (int j = 0; j < kBigItems; ++j) {
+    const int p = threadIdx.x * kBigItems + j;
+    node_val[j] = 0.0;
+    if (!is_leaf && p < n_eff) {
+      const uint32_t node = sm.g.node[p];
+      if (p == 0 || sm.g.node[p - 1] != node) node_val[j] = a.heap[base + node];
+    }
+  }
+
   B2R_MARK_CTA(1, 0);
   B2R_MARK_CTA(19, a.depth);
+  B2R_MARK_CTA(24, a.depth - 1);
   grid.sync();
   B2R_MARK_CTA(2, 0);
+  B2R_MARK_CTA(25, a.depth - 1);
+  B2R_MARK_CTA(28, a.depth);
 
   if (is_leaf) {
     if (threadIdx.x == 0) {
@@ -366,23 +545,49 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
   __syncthreads();
   B2R_MARK_CTA(3, 0);
   B2R_MARK_CTA(20, 1);
-  const int64_t base = ((int64_t)1) << level;
-  for (int p = threadIdx.x; p < n_eff; p += blockDim.x) {
-    const uint32_t node = sm.g.node[p];
-    if (p > 0 && sm.g.node[p - 1] == node) continue;
-    // end of the segment: first position whose node is larger (binary search).
-    int lo = p + 1, hi = n_eff;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (sm.g.node[mid] > node) hi = mid; else lo = mid + 1;
+  B2R_MARK_CTA(26, a.depth - 1);
+  // long chains (the upper levels): verified scan; it declines when adds round
+  if (a.scan_min_chain > 0 && (n_eff >> level) >= a.scan_min_chain &&
+      chains_by_verified_scan<C>(a.heap + base, node_val, sm.g.node, sorted_delta,
+                                 n_eff)) {
+    B2R_MARK_CTA(4, 0);
+    B2R_MARK_CTA(21, 1);
+    B2R_MARK_CTA(27, a.depth - 1);
+    return;
+  }
+  // serial chains: the thread that owns a group's first position walks the group
+  int seg_end[kBigItems];
+#pragma unroll
+  for (int j = 0; j < kBigItems; ++j) {
+    const int p = threadIdx.x * kBigItems + j;
+    seg_end[j] = p;  // (empty: not a group start)
+    if (p < n_eff) {
+      const uint32_t node = sm.g.node[p];
+      if (p == 0 || sm.g.node[p - 1] != node) {
+        // first position whose node is larger: the neighbour, else a binary search
+        int lo = p + 1, hi = n_eff;
+        if (lo < hi && sm.g.node[lo] > node) hi = lo;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (sm.g.node[mid] > node) hi = mid; else lo = mid + 1;
+        }
+        seg_end[j] = lo;
+      }
     }
-    double acc = a.heap[base + node];
+  }
+#pragma unroll
+  for (int j = 0; j < kBigItems; ++j) {
+    const int p = threadIdx.x * kBigItems + j;
+    if (seg_end[j] > p) {
+      double acc = node_val[j];
 #pragma unroll 8
-    for (int q = p; q < lo; ++q) acc = __dadd_rn(acc, sorted_delta[q]);
-    a.heap[base + node] = acc;
+      for (int q = p; q < seg_end[j]; ++q) acc = __dadd_rn(acc, sorted_delta[q]);
+      a.heap[base + sm.g.node[p]] = acc;
+    }
   }
   B2R_MARK_CTA(4, 0);
   B2R_MARK_CTA(21, 1);
+  B2R_MARK_CTA(27, a.depth - 1);
 }
 
 constexpr int kSmallBatch = 256;  // largest batch the single-CTA kernel takes
@@ -674,6 +879,18 @@ int tree_small_max() {
   return small_max;
 }
 
+// Shortest average chain (entries per touched node of a level) that is worth the
+// verified scan: a round costs about as much as 60-80 dependent DADDs.
+// B2R_TREE_SCAN_MIN overrides it (0 = serial chains everywhere).
+int tree_scan_min_chain() {
+  static const int v = [] {
+    const char *e = std::getenv("B2R_TREE_SCAN_MIN");
+    const int x = e ? std::atoi(e) : 32;
+    return x < 0 ? 0 : x;
+  }();
+  return v;
+}
+
 static int allow_small_smem() {
   static bool ready = false;
   if (!ready) {
@@ -772,6 +989,7 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     a.max_rec = t->max_rec;
     a.status = t->status;
     a.n_dev = n_dev;
+    a.scan_min_chain = tree_scan_min_chain();
     if (compact)
       B2R_TRY((launch_big_chunk<BigCfg1024>(a, t->depth, stream)));
     else

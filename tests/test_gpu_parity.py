@@ -77,6 +77,37 @@ def test_tree_batched_sets_bit_exact(gpu, cap, batch):
   assert got.tolist() == want.descend(q * want.heap[0]).tolist()
 
 
+@pytest.mark.parametrize('batch', [300, 1024, 4096, 6000])
+@pytest.mark.parametrize('odd', [0, 1, 2, 3, 9, 500])
+def test_tree_long_chains_verified_scan_bit_exact(gpu, batch, odd):
+  """The upper levels add their deltas as a prefix scan that is only kept when it
+  satisfies the sequential recurrence bit for bit (tree.cu: chains_by_verified_scan).
+  f32 priorities on a tree worth ~1e6 never round (scan accepted at once); `odd`
+  entries with full 53-bit mantissas make adds round: 1-2 are repaired by re-rooting
+  the scan, more exhaust the rounds and the serial chains run.  Every case must leave
+  the oracle's bits on every level."""
+  cap = 1 << 20
+  rng = np.random.RandomState(batch + odd)
+  tree = gpu.st.SumTree(cap)
+  want = fast.FastTree(cap)
+  fill_idx = np.arange(cap, dtype=np.int64)
+  fill = (0.5 + rng.rand(cap)).astype(np.float32).astype(np.float64)
+  tree.set_batch(fill_idx, fill)
+  assert want.set_seq(fill_idx, fill) == 0
+  for rep in range(3):
+    idx = rng.randint(0, cap, size=batch).astype(np.int64)
+    val = np.sqrt(np.abs(rng.randn(batch)) + 1e-10).astype(np.float32).astype(np.float64)
+    if odd:
+      val[rng.choice(batch, size=min(odd, batch), replace=False)] = rng.rand(
+          min(odd, batch)) * np.pi
+    tree.set_batch(idx, val)
+    assert want.set_seq(idx, val) == 0
+    for l, level in enumerate(tree.nodes):
+      assert np.array_equal(level.view(np.uint64), want.level(l).view(np.uint64)), (
+          'level %d differs after batch %d' % (l, rep))
+  assert tree.max_recorded_priority == float(want.max_recorded[0])
+
+
 def test_tree_negative_value_stops_the_batch(gpu):
   tree = gpu.st.SumTree(64)
   with pytest.raises(ValueError, match='nonnegative. Got -2.0'):
