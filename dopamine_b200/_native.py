@@ -134,6 +134,21 @@ class TrainerConfig(ctypes.Structure):
 P = ctypes.POINTER
 
 # name -> (restype, argtypes); must list every symbol of include/b200_replay.h.
+class IqnArgs(ctypes.Structure):
+  """b2r_iqn_args."""
+  _fields_ = [
+      ('batch', c_int32), ('num_actions', c_int32), ('num_tau_samples', c_int32),
+      ('num_tau_prime_samples', c_int32), ('num_quantile_samples', c_int32),
+      ('cumulative_gamma', ctypes.c_float), ('kappa', ctypes.c_float),
+      ('reserved', c_int32),
+      ('action_quantile_values', c_void_p), ('target_quantile_values', c_void_p),
+      ('online_quantile_values', c_void_p), ('quantiles', c_void_p),
+      ('actions', c_void_p), ('rewards', c_void_p), ('terminals', c_void_p),
+      ('loss', c_void_p), ('mean_loss', c_void_p),
+      ('grad_quantile_values', c_void_p), ('next_action', c_void_p),
+  ]
+
+
 SIGNATURES = {
     'b2r_last_error': (ctypes.c_char_p, []),
     'b2r_abi_version': (c_int, []),
@@ -232,6 +247,11 @@ SIGNATURES = {
     'b2r_trainer_last_rows': (c_int32, [c_void_p]),
     'b2r_trainer_drain': (c_int, [c_void_p, c_void_p, P(c_int64), c_void_p]),
     'b2r_trainer_views': (c_int, [c_void_p, P(Batch), P(C51Args)]),
+    'b2r_iqn_loss': (c_int, [P(IqnArgs), c_void_p]),
+    'b2r_actor_create': (c_int, [c_int64, c_int32, c_int32, c_int32, P(c_void_p)]),
+    'b2r_actor_destroy': (c_int, [c_void_p]),
+    'b2r_actor_reset': (c_int, [c_void_p, c_void_p, c_void_p]),
+    'b2r_actor_record': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

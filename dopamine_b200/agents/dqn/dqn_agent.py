@@ -6,9 +6,18 @@ Drop-in for the hot-path pieces of `dopamine/agents/dqn/dqn_agent.py`:
 fixed-order mean).  The replay side is `OutOfGraphReplayBuffer` /
 `WrappedReplayBuffer` of `dopamine_b200.replay_memory.circular_replay_buffer`
 (uniform sampling, BASELINE config 1).
+
+Also the actor side of the agent: the epsilon
+schedules (dqn_agent.py:45-88), `ActorState` — `DQNAgent.state` kept in HBM, rolled
+and refilled by one kernel per environment step (`_record_observation`,
+dqn_agent.py:444-458) — and `ActingLoop`, the episode interface the reference's
+runner drives (`begin_episode` / `step` / `end_episode` / `_select_action` /
+`_train_step` / `bundle_and_checkpoint` / `unbundle`, dqn_agent.py:341-442, 480-560).
 """
 import ctypes
 import math
+import os
+import random
 
 import numpy as np
 
@@ -98,3 +107,209 @@ class DQNLoss(object):
 
       cls._fn = _Fn
     return cls._fn.apply(online_q, target_q, actions, rewards, terminals, gamma_n)
+
+
+# ------------------------------------------------------------- actor side ----
+def linearly_decaying_epsilon(decay_period, step, warmup_steps, epsilon):
+  """dqn_agent.py:45-67: 1.0 for `warmup_steps`, then linearly down to `epsilon`
+  over `decay_period` steps, then `epsilon`."""
+  steps_left = decay_period + warmup_steps - step
+  bonus = (1.0 - epsilon) * steps_left / decay_period
+  bonus = np.clip(bonus, 0., 1. - epsilon)
+  return epsilon + bonus
+
+
+def identity_epsilon(unused_decay_period, unused_step, unused_warmup_steps, epsilon):
+  """dqn_agent.py:70-88."""
+  return epsilon
+
+
+class ActorState(object):
+  """`DQNAgent.state` (dqn_agent.py:181-184): the (1,) + observation_shape +
+  (stack_size,) frame stack the online network acts on, as a CUDA tensor.
+
+  `record(observation)` is `_record_observation` (dqn_agent.py:444-458) and
+  `reset()` is `_reset_state` (dqn_agent.py:474-476); both are one launch of
+  `b2r_actor_record` / `b2r_actor_reset` (csrc/actor.cu), the observation going
+  through a pinned slot that the kernel reads in place."""
+
+  def __init__(self, observation_shape, stack_size, observation_dtype=np.uint8,
+               slots=4):
+    from dopamine_b200.replay_memory import circular_replay_buffer  # pylint: disable=g-import-not-at-top
+    torch = _torch()
+    self.observation_shape = tuple(observation_shape)
+    self.stack_size = int(stack_size)
+    self.observation_dtype = np.dtype(observation_dtype)
+    self.tensor = torch.zeros(
+        (1,) + self.observation_shape + (self.stack_size,),
+        dtype=circular_replay_buffer._torch_dtype(self.observation_dtype),  # pylint: disable=protected-access
+        device='cuda')
+    self._lib = _native.lib()
+    self._h = ctypes.c_void_p()
+    pixels = int(np.prod(self.observation_shape, dtype=np.int64))
+    _native.check(self._lib.b2r_actor_create(
+        pixels, self.observation_dtype.itemsize, self.stack_size, slots,
+        ctypes.byref(self._h)))
+
+  def reset(self):
+    _native.check(self._lib.b2r_actor_reset(self._h, self.tensor.data_ptr(),
+                                            _native.current_stream()))
+
+  def record(self, observation):
+    """Rolls the stack and appends `observation`; returns the frame as stored
+    (`DQNAgent._observation`: reshaped to observation_shape, cast by assignment)."""
+    frame = np.ascontiguousarray(
+        np.reshape(observation, self.observation_shape).astype(
+            self.observation_dtype, copy=False))
+    _native.check(self._lib.b2r_actor_record(
+        self._h, self.tensor.data_ptr(), frame.ctypes.data,
+        _native.current_stream()))
+    return frame
+
+  def numpy(self):
+    return self.tensor.cpu().numpy()
+
+  def close(self):
+    if getattr(self, '_h', None) is not None and self._h:
+      self._lib.b2r_actor_destroy(self._h)
+      self._h = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+
+class ActingLoop(object):
+  """The episode interface of `DQNAgent` (dqn_agent.py:341-442, 480-560) for a
+  learner that provides `num_actions`, `memory` (the replay buffer), `q_values(state)`,
+  `train_step()`, `sync_target()` and `_store_transition(...)`.
+
+  Same attribute names and the same order of effects as the reference: `state`
+  (here a CUDA tensor), `_observation`, `_last_observation`, `action`, `eval_mode`,
+  `training_steps`.  Random numbers come from Python's `random` module exactly as in
+  `_select_action` (dqn_agent.py:397-416), so a seeded run picks the same exploratory
+  actions."""
+
+  def _init_acting(self, observation_shape, stack_size, observation_dtype=np.uint8,
+                   min_replay_history=20000, update_period=4,
+                   target_update_period=8000,
+                   epsilon_fn=linearly_decaying_epsilon, epsilon_train=0.01,
+                   epsilon_eval=0.001, epsilon_decay_period=250000,
+                   allow_partial_reload=False):
+    self.observation_shape = tuple(observation_shape)
+    self.stack_size = stack_size
+    self.min_replay_history = min_replay_history
+    self.update_period = update_period
+    self.target_update_period = target_update_period
+    self.epsilon_fn = epsilon_fn
+    self.epsilon_train = epsilon_train
+    self.epsilon_eval = epsilon_eval
+    self.epsilon_decay_period = epsilon_decay_period
+    self.allow_partial_reload = allow_partial_reload
+    self.eval_mode = False
+    self.training_steps = 0
+    self.action = None
+    self._observation = None
+    self._last_observation = None
+    self._actor_state = ActorState(observation_shape, stack_size, observation_dtype)
+
+  @property
+  def state(self):
+    return self._actor_state.tensor
+
+  def begin_episode(self, observation):
+    """dqn_agent.py:341-358."""
+    self._reset_state()
+    self._record_observation(observation)
+    if not self.eval_mode:
+      self._train_step()
+    self.action = self._select_action()
+    return self.action
+
+  def step(self, reward, observation):
+    """dqn_agent.py:360-381."""
+    self._last_observation = self._observation
+    self._record_observation(observation)
+    if not self.eval_mode:
+      self._store_transition(self._last_observation, self.action, reward, False)
+      self._train_step()
+    self.action = self._select_action()
+    return self.action
+
+  def end_episode(self, reward):
+    """dqn_agent.py:383-393."""
+    if not self.eval_mode:
+      self._store_transition(self._observation, self.action, reward, True)
+
+  def _select_action(self):
+    """dqn_agent.py:395-416."""
+    if self.eval_mode:
+      epsilon = self.epsilon_eval
+    else:
+      epsilon = self.epsilon_fn(self.epsilon_decay_period, self.training_steps,
+                                self.min_replay_history, self.epsilon_train)
+    if random.random() <= epsilon:
+      return random.randint(0, self.num_actions - 1)
+    return int(self.q_values(self.state).argmax(dim=1)[0])
+
+  def _train_step(self):
+    """dqn_agent.py:418-442."""
+    if self.memory.add_count > self.min_replay_history:
+      if self.training_steps % self.update_period == 0:
+        self.train_step()
+      if self.training_steps % self.target_update_period == 0:
+        self.sync_target()
+    self.training_steps += 1
+
+  def _record_observation(self, observation):
+    """dqn_agent.py:444-458."""
+    self._observation = self._actor_state.record(observation)
+
+  def _reset_state(self):
+    """dqn_agent.py:474-476."""
+    self._actor_state.reset()
+
+  def _store_transition(self, last_observation, action, reward, is_terminal):
+    """dqn_agent.py:460-472."""
+    self.memory.add(last_observation, action, reward, is_terminal)
+
+  # -- checkpointing (dqn_agent.py:480-560) ------------------------------------------
+  def _network_state(self):
+    """What the reference's tf.train.Saver holds: every variable of the graph."""
+    return {'online': self.online.state_dict(), 'target': self.target.state_dict(),
+            'optimizer': self.optimizer.state_dict()}
+
+  def _load_network_state(self, blob):
+    self.online.load_state_dict(blob['online'])
+    self.target.load_state_dict(blob['target'])
+    self.optimizer.load_state_dict(blob['optimizer'])
+
+  def bundle_and_checkpoint(self, checkpoint_dir, iteration_number):
+    if not os.path.exists(checkpoint_dir):
+      return None
+    torch = _torch()
+    torch.save(self._network_state(),
+               os.path.join(checkpoint_dir, 'torch_ckpt-{}'.format(iteration_number)))
+    self.memory.save(checkpoint_dir, iteration_number)
+    return {'state': self._actor_state.numpy(), 'training_steps': self.training_steps}
+
+  def unbundle(self, checkpoint_dir, iteration_number, bundle_dictionary):
+    torch = _torch()
+    try:
+      self.memory.load(checkpoint_dir, iteration_number)
+    except (IOError, OSError):  # the reference catches tf.errors.NotFoundError
+      if not self.allow_partial_reload:
+        return False
+    if bundle_dictionary is not None:
+      if 'state' in bundle_dictionary:
+        self.state.copy_(torch.as_tensor(np.asarray(bundle_dictionary['state'])))
+      for key in self.__dict__:
+        if key in bundle_dictionary and key != 'state':
+          self.__dict__[key] = bundle_dictionary[key]
+    elif not self.allow_partial_reload:
+      return False
+    self._load_network_state(torch.load(
+        os.path.join(checkpoint_dir, 'torch_ckpt-{}'.format(iteration_number))))
+    return True

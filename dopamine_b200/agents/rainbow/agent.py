@@ -5,9 +5,11 @@ Mirrors what `RainbowAgent` builds around the replay memory
 convolutional distribution network (atari_lib.py:108-144, cuDNN through PyTorch —
 the only dense contraction on the path, so the only part that is NOT a hand-written
 kernel here), the C51 train op, Adam with the reference's hyper-parameters
-(rainbow.gin:21-25), priority write-back and the target-network sync.  Acting in an
-environment (epsilon-greedy, frame stacking) stays with the caller, which feeds
-`store_transition` exactly as the reference's `_store_transition` feeds `add`.
+(rainbow.gin:21-25), priority write-back and the target-network sync.
+`RainbowLearner` is that half alone (the caller feeds `store_transition` exactly as
+the reference's `_store_transition` feeds `add`); `RainbowAgent` adds the episode
+interface the reference's runner drives (`dqn_agent.ActingLoop`: epsilon-greedy
+acting on a frame stack kept in HBM, the `_train_step` cadence, checkpoint bundles).
 
 One `train_step()`:
   sample + gather (one fused call, batch stays in HBM) -> online net on `state`,
@@ -20,6 +22,7 @@ import math
 
 import numpy as np
 
+from dopamine_b200.agents.dqn import dqn_agent
 from dopamine_b200.agents.rainbow import rainbow_agent
 from dopamine_b200.replay_memory import prioritized_replay_buffer
 
@@ -208,3 +211,49 @@ class RainbowLearner(object):
       self.sync_target()
     self.training_steps += 1
     return loss
+
+
+class RainbowAgent(RainbowLearner, dqn_agent.ActingLoop):
+  """`RainbowAgent` (rainbow_agent.py:50-337) as the reference's runner sees it:
+  `begin_episode(observation)`, `step(reward, observation)`, `end_episode(reward)`,
+  `eval_mode`, `bundle_and_checkpoint`, `unbundle`.  Constructor arguments keep the
+  reference's names and defaults (rainbow_agent.py:53-87); `sess`, `tf_device`,
+  `use_staging`, `optimizer` and the summary arguments have no meaning here."""
+
+  def __init__(self, sess=None, num_actions=None, observation_shape=(84, 84),
+               observation_dtype=np.uint8, stack_size=4, num_atoms=51, vmax=10.,
+               gamma=0.99, update_horizon=1, min_replay_history=20000,
+               update_period=4, target_update_period=8000,
+               epsilon_fn=dqn_agent.linearly_decaying_epsilon, epsilon_train=0.01,
+               epsilon_eval=0.001, epsilon_decay_period=250000,
+               replay_scheme='prioritized', replay_capacity=1000000, batch_size=32,
+               learning_rate=6.25e-5, adam_epsilon=1.5e-4, seed=0,
+               allow_partial_reload=False, memory=None, cuda_graph=False):
+    del sess
+    if num_actions is None:
+      raise ValueError('num_actions is required')
+    if np.dtype(observation_dtype) != np.uint8:
+      raise NotImplementedError('the convolutional network takes uint8 frames')
+    RainbowLearner.__init__(
+        self, num_actions, observation_shape=observation_shape,
+        stack_size=stack_size, num_atoms=num_atoms, vmax=vmax, gamma=gamma,
+        update_horizon=update_horizon, replay_capacity=replay_capacity,
+        batch_size=batch_size, target_update_period=target_update_period,
+        update_period=update_period, replay_scheme=replay_scheme,
+        learning_rate=learning_rate, adam_epsilon=adam_epsilon, seed=seed,
+        memory=memory, cuda_graph=cuda_graph)
+    self._init_acting(observation_shape, stack_size, observation_dtype,
+                      min_replay_history=min_replay_history,
+                      update_period=update_period,
+                      target_update_period=target_update_period,
+                      epsilon_fn=epsilon_fn, epsilon_train=epsilon_train,
+                      epsilon_eval=epsilon_eval,
+                      epsilon_decay_period=epsilon_decay_period,
+                      allow_partial_reload=allow_partial_reload)
+
+  def _store_transition(self, last_observation, action, reward, is_terminal,
+                        priority=None):
+    """rainbow_agent.py:307-337 (the default priority of the prioritized scheme,
+    "the maximum ever seen", is resolved on the device when the row is applied)."""
+    if not self.eval_mode:
+      self.store_transition(last_observation, action, reward, is_terminal, priority)

@@ -478,6 +478,54 @@ int b2r_trainer_drain(b2r_trainer *trainer, float *loss_out, int64_t *loss_step,
  * of its loss outputs (loss, priorities, weights in a b2r_c51_args). */
 int b2r_trainer_views(b2r_trainer *trainer, b2r_batch *batch, b2r_c51_args *c51);
 
+/* Actor side of the path (the step before add): DQNAgent.state, a (1, H, W, S)
+ * frame stack with the stack index innermost, and the two methods that change it
+ * (dqn_agent.py:444-458 _record_observation: np.roll(state, -1, axis=-1) then
+ * state[0, ..., -1] = observation; dqn_agent.py:474-476 _reset_state: fill(0)).
+ * `state` is the caller's DEVICE tensor (pixels * stack_size elements of elem_size
+ * bytes); the handle owns a ring of `slots` pinned host frames (0 = default) that
+ * b2r_actor_record copies the HOST observation into and that ONE kernel reads
+ * zero-copy while it rolls the stack.  A slot is reused only after the launch that
+ * read it has completed, so the call never waits unless `slots` records are in
+ * flight. */
+typedef struct b2r_actor b2r_actor;
+int b2r_actor_create(int64_t pixels, int32_t elem_size, int32_t stack_size,
+                     int32_t slots, b2r_actor **out);
+int b2r_actor_destroy(b2r_actor *actor);
+int b2r_actor_reset(b2r_actor *actor, void *state, b2r_stream stream);
+int b2r_actor_record(b2r_actor *actor, void *state, const void *observation,
+                     b2r_stream stream);
+
+/* IQN (implicit_quantile_agent.py:166-315): greedy next action from the action
+ * network's K quantile samples (:176-188), target quantile values
+ * r + gamma^n (1 - t) Z_target[., a*] (:190-231), the quantile-Huber loss of every
+ * (target sample t', online sample t) pair, summed over t and averaged over t'
+ * (:278-311), its mean over the batch (:315) and d mean / d Z_online.  All network
+ * outputs are DEVICE (samples * batch, num_actions) f32 matrices with the
+ * reference's sample-major row order (row = sample * batch + b).  One launch. */
+typedef struct {
+  int32_t batch, num_actions;
+  int32_t num_tau_samples;        /* N : online samples  (:233-262)              */
+  int32_t num_tau_prime_samples;  /* N': target samples  (:196-231)              */
+  int32_t num_quantile_samples;   /* K : samples behind the greedy action (:166) */
+  float cumulative_gamma;         /* f32(pow(gamma, update_horizon))  (DQ:175)   */
+  float kappa;                    /* Huber threshold, > 0             (:283-289) */
+  int32_t reserved;
+  const float *action_quantile_values; /* (K * B, A): target net, or online net with
+                                          double_dqn (:166-175)                   */
+  const float *target_quantile_values; /* (N' * B, A)                             */
+  const float *online_quantile_values; /* (N * B, A)                              */
+  const float *quantiles;              /* (N * B): tau of each online row         */
+  const int32_t *actions;              /* (B)                                     */
+  const float *rewards;                /* (B)                                     */
+  const uint8_t *terminals;            /* (B)                                     */
+  float *loss;                         /* (B) out                                 */
+  float *mean_loss;                    /* scalar out, nullable                    */
+  float *grad_quantile_values;         /* (N * B, A) out, nullable                */
+  int32_t *next_action;                /* (B) out, nullable: a*                   */
+} b2r_iqn_args;
+int b2r_iqn_loss(const b2r_iqn_args *args, b2r_stream stream);
+
 #ifdef __cplusplus
 }
 #endif
