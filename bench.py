@@ -580,6 +580,78 @@ def measure_config1_dqn(torch, steps, batch=32, capacity=100000, cpu_budget_s=4.
           'what': 'uniform sample + gather + DQN target / Huber loss; CUDA graph replay'}
 
 
+def measure_next_rows(torch, batch=32):
+  """SURVEY 8f rows 3-4, one number each: IQN's quantile-Huber loss (64 x 64 tau
+  samples, 32 action samples, 18 actions) as one device-timed launch beside its numpy
+  port, and the actor's per-environment-step record_observation (host call + kernel)
+  beside the reference's np.roll + assignment."""
+  from dopamine_b200.agents.dqn import dqn_agent
+  from dopamine_b200.agents.implicit_quantile import implicit_quantile_agent as iqa
+  from oracle import iqn_port
+  out = {}
+  n, n_prime, k = 64, 64, 32
+  rng = np.random.RandomState(5)
+  case = dict(
+      rewards=np.clip(rng.randn(batch), -1, 1).astype(np.float32),
+      terminals=(rng.rand(batch) < 0.05).astype(np.uint8),
+      actions=rng.randint(0, NUM_ACTIONS, size=batch).astype(np.int32),
+      online_quantile_values=rng.randn(n * batch, NUM_ACTIONS).astype(np.float32),
+      quantiles=rng.rand(n * batch, 1).astype(np.float32),
+      target_quantile_values=rng.randn(n_prime * batch, NUM_ACTIONS).astype(np.float32),
+      action_quantile_values=rng.randn(k * batch, NUM_ACTIONS).astype(np.float32))
+  dev = {key: torch.as_tensor(v, device='cuda') for key, v in case.items()}
+  res = iqa.quantile_huber_loss(
+      dev['online_quantile_values'], dev['quantiles'], dev['target_quantile_values'],
+      dev['action_quantile_values'], dev['actions'], dev['rewards'], dev['terminals'],
+      GAMMA ** 3, 1.0, want_grad=True)
+
+  def iqn():
+    iqa.quantile_huber_loss(
+        dev['online_quantile_values'], dev['quantiles'], dev['target_quantile_values'],
+        dev['action_quantile_values'], dev['actions'], dev['rewards'],
+        dev['terminals'], GAMMA ** 3, 1.0, want_grad=True, out=res)
+
+  reps = 500
+  ms = time_graph_or_eager(torch, iqn, reps, 10, True)
+  t0, done = time.perf_counter(), 0
+  while time.perf_counter() - t0 < 1.0 or done < 3:
+    iqn_port.iqn_update(num_tau_samples=n, num_tau_prime_samples=n_prime,
+                        num_quantile_samples=k, gamma=GAMMA, update_horizon=3, **case)
+    done += 1
+  out['iqn_loss'] = {
+      'batch': batch, 'tau_samples': [n, n_prime, k],
+      'us_per_launch': round(ms * 1e3 / reps, 2),
+      'cpu_port_us': round((time.perf_counter() - t0) / done * 1e6, 1),
+      'what': 'greedy next action + target quantiles + quantile-Huber loss + '
+              'gradient, one launch (b2r_iqn_loss)'}
+  # actor: wall clock per call (host memcpy into a pinned slot + one launch)
+  actor = dqn_agent.ActorState((84, 84), STACK, np.uint8, slots=8)
+  frames = rng.randint(0, 256, size=(64, 84, 84)).astype(np.uint8)
+  for i in range(50):
+    actor.record(frames[i % 64])
+  torch.cuda.synchronize()
+  calls = 5000
+  t0 = time.perf_counter()
+  for i in range(calls):
+    actor.record(frames[i % 64])
+  torch.cuda.synchronize()
+  record_us = (time.perf_counter() - t0) / calls * 1e6
+  state = np.zeros((1, 84, 84, STACK), np.uint8)
+  t0 = time.perf_counter()
+  for i in range(calls):
+    state = np.roll(state, -1, axis=-1)
+    state[0, ..., -1] = frames[i % 64]
+  out['record_observation'] = {
+      'us_per_call': round(record_us, 2),
+      'numpy_roll_us': round((time.perf_counter() - t0) / calls * 1e6, 2),
+      'what': 'ActorState.record: frame through a pinned slot, roll + insert of the '
+              '(1, 84, 84, 4) state in HBM in one launch; beside the reference\'s '
+              'np.roll + assignment on the host (which still has to ship the state to '
+              'the device)'}
+  actor.close()
+  return out
+
+
 def measure_e2e_host_batch(torch, wl, batch, steps):
   """Variant that also ships the whole sampled batch to host numpy arrays, i.e. the
   reference's OutOfGraph* return convention (1.8 MB of D2H per step at batch 32)."""
@@ -948,6 +1020,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
       line['config1_dqn_uniform'] = measure_config1_dqn(
           torch, max(50, min(args.steps, 2000)))
+      line['next_rows'] = measure_next_rows(torch)
       line['cpu_baseline'] = cpu_baseline(args.batch, args.capacity)
     print(json.dumps(line))
   if dist is not None:
