@@ -55,6 +55,10 @@ def parse_args():
   p.add_argument('--capacity', type=int, default=1000000)
   p.add_argument('--no-graph', action='store_true',
                  help='launch eagerly instead of replaying a CUDA graph')
+  p.add_argument('--steps-per-graph', type=int, default=10,
+                 help='consecutive steps captured in one CUDA graph (the largest '
+                      'divisor of --steps up to this is used); 1 = one graph launch '
+                      'per step')
   p.add_argument('--no-sweep', action='store_true')
   p.add_argument('--no-cpu-baseline', action='store_true')
   p.add_argument('--no-e2e', action='store_true')
@@ -311,8 +315,22 @@ class GpuWorkload(object):
     return total
 
 
-def time_graph_or_eager(torch, fn, steps, warmup, use_graph, dist=None):
-  """Times `steps` calls of fn with CUDA events on the launching stream."""
+def steps_per_graph(steps, limit):
+  """Largest divisor of `steps` that is <= limit (so that exactly `steps` run)."""
+  g = max(1, min(int(limit), int(steps)))
+  while steps % g:
+    g -= 1
+  return g
+
+
+def time_graph_or_eager(torch, fn, steps, warmup, use_graph, dist=None, per_graph=1):
+  """Times `steps` calls of fn with CUDA events on the launching stream.
+
+  per_graph > 1 captures that many consecutive calls in one CUDA graph (it must
+  divide `steps`): consecutive graph launches are paced by the front end in units of
+  about 2 us on B200 (a one-kernel graph replayed back to back reports 6.16, 8.21,
+  10.26 ... us whatever the kernel does), and programmatic dependent launch cannot
+  overlap a step's first kernel with the previous graph's last one."""
   side = torch.cuda.Stream()
   side.wait_stream(torch.cuda.current_stream())
   with torch.cuda.stream(side):
@@ -322,19 +340,23 @@ def time_graph_or_eager(torch, fn, steps, warmup, use_graph, dist=None):
     runner = fn
     if use_graph:
       graph = torch.cuda.CUDAGraph()
+      assert steps % per_graph == 0, (steps, per_graph)
       with torch.cuda.graph(graph, stream=side):
-        fn()
+        for _ in range(per_graph):
+          fn()
       runner = graph.replay
       for _ in range(3):
         runner()
       side.synchronize()
+    else:
+      per_graph = 1
     if dist is not None:
       dist.barrier()
     torch.cuda.synchronize()
     start = torch.cuda.Event(enable_timing=True)
     end = torch.cuda.Event(enable_timing=True)
     start.record(side)
-    for _ in range(steps):
+    for _ in range(steps // per_graph):
       runner()
     end.record(side)
     end.synchronize()
@@ -917,7 +939,9 @@ def main():
   clocks = ClockSampler(local_rank)
   if rank == 0:
     clocks.__enter__()
-  ms = time_graph_or_eager(torch, step_fn, args.steps, args.warmup, use_graph, dist)
+  per_graph = steps_per_graph(args.steps, args.steps_per_graph) if use_graph else 1
+  ms = time_graph_or_eager(torch, step_fn, args.steps, args.warmup, use_graph, dist,
+                           per_graph=per_graph)
   if rank == 0:
     clocks.__exit__()
   if dist is not None:
@@ -938,7 +962,8 @@ def main():
           'workload': workload_name(args.batch, args.capacity, world),
           'l2': 'inputs larger than L2: 7.06 GB frame ring per GPU, fresh random '
                 'indices every step (device Philox); no flush needed',
-          'launch': ('CUDA graph replay' if use_graph else 'eager launches') + (
+          'launch': ('CUDA graph replay, %d consecutive steps per graph launch' % per_graph
+                     if use_graph else 'eager launches') + (
               '; one b2r_train_step_device call per step: frame-stack copies on a '
               'forked stream beside loss + write-back, joined every step'
               if wl.fused and world == 1 else '') + (
@@ -961,7 +986,8 @@ def main():
       st = sharded_replay.ShardedStep(wl, b * world, world, rank, dist,
                                       exchange=exchange)
       k = max(20, min(args.steps, 300))
-      ms_b = time_graph_or_eager(torch, st.step, k, 5, use_graph, dist)
+      ms_b = time_graph_or_eager(torch, st.step, k, 5, use_graph, dist,
+                                 per_graph=steps_per_graph(k, args.steps_per_graph))
       t = torch.tensor([ms_b], device='cuda')
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
       ms_b = float(t.item())
@@ -993,7 +1019,8 @@ def main():
       sweep = {}
       for b in sweep_batches:
         k = max(20, min(args.steps, 400))
-        ms_b = time_graph_or_eager(torch, lambda: wl.step(b), k, 5, use_graph)
+        ms_b = time_graph_or_eager(torch, lambda: wl.step(b), k, 5, use_graph,
+                                   per_graph=steps_per_graph(k, args.steps_per_graph))
         roof = measure_gather_roofline(torch, wl, b, peak_gbs, launches=60)
         sweep[str(b)] = {'value': round(b * k / (ms_b * 1e-3), 1),
                          'ms_per_step': round(ms_b / k, 5),

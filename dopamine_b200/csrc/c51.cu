@@ -751,11 +751,14 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
   }
   a.weighted = b2r::g_weighted;
   a.ticket = b2r::g_ticket;
-  // Above kRowsMinBatch rows: one warp per row (B2R_C51_ROWS_MIN overrides the
-  // threshold, B2R_C51_GROUP = 16 picks the half-warp-per-action instance).
+  // From 128 rows up: one warp per row (B2R_C51_ROWS_MIN overrides the threshold,
+  // B2R_C51_GROUP = 4 | 16 picks another lanes-per-action instance).  Measured with
+  // 10 launches per graph (profiles/r1/README.md): at batch 32 the CTA-per-row kernel
+  // and the G = 4 instance tie (5.95 us), at 256 the rows kernel wins once the logits
+  // no longer sit in L2 (10.2 -> 7.0 us).
   static const int rows_min = [] {
     const char *e = std::getenv("B2R_C51_ROWS_MIN");
-    return e ? std::atoi(e) : 257;
+    return e ? std::atoi(e) : 128;
   }();
   static const int rows_group = [] {
     const char *e = std::getenv("B2R_C51_GROUP");

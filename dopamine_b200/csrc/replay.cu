@@ -120,6 +120,10 @@ int enqueue(b2r_buffer *b, bool real, const void *const *cols, double priority,
 
 }  // namespace
 
+// Largest flush that goes out as the one fused launch (its tree half is the one-CTA
+// kernel body, which copes with up to 256 entries but is only quick for a few dozen).
+constexpr int kFusedFlushMax = 64;
+
 int flush_queue(b2r_buffer *b, cudaStream_t stream, bool split) {
   if (b->q_entries == 0) return B2R_OK;
   Staging *s = &b->staging[b->active];
@@ -133,7 +137,7 @@ int flush_queue(b2r_buffer *b, cudaStream_t stream, bool split) {
   // per update): ONE launch that reads the staging buffer straight from pinned host
   // memory — tree update in CTA 0, row writes in the others (tree.cu).
   if (b->tree != nullptr && !split && s->host_dev != nullptr &&
-      b->q_entries <= tree_small_max() && std::getenv("B2R_NO_FUSED_FLUSH") == nullptr) {
+      b->q_entries <= kFusedFlushMax && std::getenv("B2R_NO_FUSED_FLUSH") == nullptr) {
     Header hh = header_of(s->host_dev, b->queue_cap);
     AddParams p;
     p.n_entries = b->q_entries;

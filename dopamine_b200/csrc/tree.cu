@@ -868,12 +868,13 @@ int launch_big_chunk(const UpdateArgs<I, V> &a, int depth, cudaStream_t stream) 
 }  // namespace
 
 // The one-CTA kernel sorts per warp (cost ~ n log^2 n): it wins for the agent's batch
-// of 32 and loses to the radix-sorted cooperative kernel beyond ~64 entries (measured,
+// of 32 (4.9 us) and already loses to the 256 x 4 cooperative kernel at 64 entries
+// (10.5 vs 9.2 us; at 256: 43 vs 9.8 us — measured with 10 launches per graph,
 // profiles/r1/README.md).  B2R_TREE_SMALL_MAX overrides the threshold.
 int tree_small_max() {
   static const int small_max = [] {
     const char *e = std::getenv("B2R_TREE_SMALL_MAX");
-    int v = e ? std::atoi(e) : 64;
+    int v = e ? std::atoi(e) : 32;
     return v < 0 ? 0 : (v > kSmallBatch ? kSmallBatch : v);
   }();
   return small_max;

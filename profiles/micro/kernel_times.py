@@ -22,6 +22,9 @@ def main():
   p.add_argument('--batches', default='32,256,1024,4096')
   p.add_argument('--capacity', type=int, default=1000000)
   p.add_argument('--reps', type=int, default=200)
+  p.add_argument('--per-graph', type=int, default=1,
+                 help='calls captured per CUDA graph (1: each replay is one launch and '
+                      'the time is quantised by the ~2 us graph-launch pacing)')
   a = p.parse_args()
   batches = [int(b) for b in a.batches.split(',')]
   import torch
@@ -62,7 +65,8 @@ def main():
     for name, fn in (('sample_us', sample), ('gather_us', gather),
                      ('c51_loss_us', loss), ('write_back_us', write_back),
                      ('step_unfused_us', unfused), ('step_fused_us', fused)):
-      ms = bench.time_graph_or_eager(torch, fn, reps, 5, True)
+      ms = bench.time_graph_or_eager(torch, fn, reps, 5, True,
+                                     per_graph=bench.steps_per_graph(reps, a.per_graph))
       row[name] = round(ms * 1e3 / reps, 2)
     row['parts_sum_us'] = round(row['sample_us'] + row['gather_us'] +
                                 row['c51_loss_us'] + row['write_back_us'], 2)
