@@ -570,7 +570,8 @@ def measure_config1_dqn(torch, steps, batch=32, capacity=100000, cpu_budget_s=4.
         mem._h, batch, 11, 0, ctypes.byref(b), s))  # pylint: disable=protected-access
     _native.check(lib.b2r_dqn_loss(ctypes.byref(a), s))
 
-  ms = time_graph_or_eager(torch, step, steps, 20, True)
+  ms = time_graph_or_eager(torch, step, steps, 20, True,
+                           per_graph=steps_per_graph(steps, 10))
   _native.check(lib.b2r_check(mem._h, _native.current_stream()))  # pylint: disable=protected-access
   # CPU: the oracle port of the same step, one core
   port = PortReplay((84, 84), STACK, capacity, batch, update_horizon=1, gamma=GAMMA)
@@ -599,7 +600,8 @@ def measure_config1_dqn(torch, steps, batch=32, capacity=100000, cpu_budget_s=4.
           'value': round(batch * steps / (ms * 1e-3), 1), 'unit': UNIT,
           'ms_per_step': round(ms / steps, 6), 'steps': steps,
           'cpu_port_value': round(batch * done / cpu_dt, 1), 'cpu_cores': 1,
-          'what': 'uniform sample + gather + DQN target / Huber loss; CUDA graph replay'}
+          'what': 'uniform sample + gather + DQN target / Huber loss; CUDA graph replay, '
+                  '10 steps per graph launch'}
 
 
 def measure_next_rows(torch, batch=32):
@@ -634,7 +636,7 @@ def measure_next_rows(torch, batch=32):
         dev['terminals'], GAMMA ** 3, 1.0, want_grad=True, out=res)
 
   reps = 500
-  ms = time_graph_or_eager(torch, iqn, reps, 10, True)
+  ms = time_graph_or_eager(torch, iqn, reps, 10, True, per_graph=10)
   t0, done = time.perf_counter(), 0
   while time.perf_counter() - t0 < 1.0 or done < 3:
     iqn_port.iqn_update(num_tau_samples=n, num_tau_prime_samples=n_prime,

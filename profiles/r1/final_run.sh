@@ -10,7 +10,8 @@ tail -2 $O/final_${T}_tests.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/final_${T}_smoke.log 2>&1; tail -1 $O/final_${T}_smoke.log
 timeout 400 python bench.py > $O/final_${T}_n1.json 2> $O/final_${T}_n1.err; echo "bench rc=$?"
 timeout 200 python bench.py --impl reference --steps 5 --warmup 3 > $O/final_${T}_ref.json 2> $O/final_${T}_ref.err; echo "ref rc=$?"
-timeout 100 python profiles/micro/kernel_times.py > $O/kernel_times_${T}.log 2>&1; cat $O/kernel_times_${T}.log
+timeout 100 python profiles/micro/kernel_times.py --per-graph 10 > $O/kernel_times_${T}.log 2>&1; cat $O/kernel_times_${T}.log
+[ "${2:-}" = "no-ncu" ] && exit 0
 for B in 32 4096; do
   timeout 100 python profiles/profile_step.py --batch $B --steps 3 > $O/plain_${T}_$B.log 2>&1 || continue
   timeout 200 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none \
