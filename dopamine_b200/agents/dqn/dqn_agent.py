@@ -111,12 +111,12 @@ class DQNLoss(object):
 
 # ------------------------------------------------------------- actor side ----
 def linearly_decaying_epsilon(decay_period, step, warmup_steps, epsilon):
-  """dqn_agent.py:45-67: 1.0 for `warmup_steps`, then linearly down to `epsilon`
-  over `decay_period` steps, then `epsilon`."""
-  steps_left = decay_period + warmup_steps - step
-  bonus = (1.0 - epsilon) * steps_left / decay_period
-  bonus = np.clip(bonus, 0., 1. - epsilon)
-  return epsilon + bonus
+  """The Nature-DQN schedule of dqn_agent.py:45-67: 1.0 until `warmup_steps`, a straight
+  line down to `epsilon` over the next `decay_period` steps, `epsilon` from then on
+  (same operation order as the reference, so the same doubles)."""
+  remaining = decay_period + warmup_steps - step
+  extra = (1.0 - epsilon) * remaining / decay_period
+  return epsilon + min(max(extra, 0.), 1. - epsilon)
 
 
 def identity_epsilon(unused_decay_period, unused_step, unused_warmup_steps, epsilon):
@@ -213,33 +213,42 @@ class ActingLoop(object):
     self.action = None
     self._observation = None
     self._last_observation = None
-    self._actor_state = ActorState(observation_shape, stack_size, observation_dtype)
+    self._actor_state = self._make_actor_state(observation_shape, stack_size,
+                                               observation_dtype)
+
+  def _make_actor_state(self, observation_shape, stack_size, observation_dtype):
+    return ActorState(observation_shape, stack_size, observation_dtype)
 
   @property
   def state(self):
     return self._actor_state.tensor
 
   def begin_episode(self, observation):
-    """dqn_agent.py:341-358."""
+    """dqn_agent.py:341-358: clear the stack, then the common tail without a
+    transition to store."""
     self._reset_state()
-    self._record_observation(observation)
-    if not self.eval_mode:
-      self._train_step()
-    self.action = self._select_action()
-    return self.action
+    return self._observe_and_act(observation, finished=None)
 
   def step(self, reward, observation):
-    """dqn_agent.py:360-381."""
+    """dqn_agent.py:360-381: the observation before this one is stored together with
+    the reward it earned."""
     self._last_observation = self._observation
+    return self._observe_and_act(observation, finished=(self._last_observation, reward))
+
+  def _observe_and_act(self, observation, finished):
+    """What begin_episode and step share, in the reference's order: record the frame;
+    in training mode store the finished (observation, action, reward) and run the
+    train-step cadence; pick the next action."""
     self._record_observation(observation)
     if not self.eval_mode:
-      self._store_transition(self._last_observation, self.action, reward, False)
+      if finished is not None:
+        self._store_transition(finished[0], self.action, finished[1], False)
       self._train_step()
     self.action = self._select_action()
     return self.action
 
   def end_episode(self, reward):
-    """dqn_agent.py:383-393."""
+    """dqn_agent.py:383-393: the episode's last observation closes it."""
     if not self.eval_mode:
       self._store_transition(self._observation, self.action, reward, True)
 

@@ -108,6 +108,116 @@ class _MockMemory(object):
     self.calls.append(args)
 
 
+class _HostActorState(object):
+  """Test double for ActorState (CPU tests): the reference's two numpy lines."""
+
+  def __init__(self, observation_shape, stack_size, observation_dtype):
+    self.observation_shape = tuple(observation_shape)
+    self.tensor = np.zeros((1,) + self.observation_shape + (stack_size,),
+                           dtype=observation_dtype)
+
+  def reset(self):
+    self.tensor.fill(0)
+
+  def record(self, observation):
+    frame = np.reshape(observation, self.observation_shape).astype(self.tensor.dtype)
+    self.tensor = np.roll(self.tensor, -1, axis=-1)
+    self.tensor[0, ..., -1] = frame
+    return frame
+
+  def numpy(self):
+    return self.tensor
+
+
+def _host_agent(**kw):
+  """ActingLoop over stubs: the episode logic needs no device."""
+  from dopamine_b200.agents.dqn import dqn_agent
+
+  class HostAgent(dqn_agent.ActingLoop):
+
+    def __init__(self, num_actions, **acting):
+      self.num_actions = num_actions
+      self.memory = _MockMemory()
+      self.train_ops, self.syncs = [], []
+      self._init_acting((5, 3), 4, np.uint8, **acting)
+
+    def _make_actor_state(self, shape, stack, dtype):
+      return _HostActorState(shape, stack, dtype)
+
+    def q_values(self, state):
+      class _Q(object):  # stands in for a (1, A) tensor whose argmax is action 2
+
+        def argmax(self, dim):
+          del dim
+          return [2]
+      return _Q()
+
+    def train_step(self):
+      self.train_ops.append(self.training_steps)
+
+    def sync_target(self):
+      self.syncs.append(self.training_steps)
+
+  return HostAgent(**kw)
+
+
+def test_acting_loop_cadence_on_the_host():
+  """dqn_agent.py:341-442 without a device: what is stored when, when the train op and
+  the target sync fire (add_count > min_replay_history, multiples of update_period /
+  target_update_period), what eval mode suppresses."""
+  agent = _host_agent(num_actions=4, min_replay_history=3, update_period=2,
+                      target_update_period=4, epsilon_fn=lambda w, x, y, z: 0.0,
+                      epsilon_eval=0.0)
+  obs = lambda v: np.full((5, 3, 1), v)
+  assert agent.begin_episode(obs(1)) == 2
+  assert agent.training_steps == 1 and not agent.memory.calls
+  for step in range(2, 9):
+    agent.memory.add_count = len(agent.memory.calls)  # what add() would have counted
+    assert agent.step(0.5, obs(step)) == 2
+    stored = agent.memory.calls[-1]
+    assert np.array_equal(stored[0], np.full((5, 3), step - 1))
+    assert stored[1:] == (2, 0.5, False)
+  assert agent.training_steps == 8
+  # the cadence saw add_count = 0..6 before steps 1..7 (counters 1..7): add_count > 3
+  # from counter 5 on; train op on even counters, sync on multiples of 4
+  assert agent.train_ops == [6] and agent.syncs == []
+  agent.memory.add_count = 7
+  agent.step(0.5, obs(9))  # counter 8: both fire
+  assert agent.train_ops == [6, 8] and agent.syncs == [8]
+  agent.end_episode(1.0)
+  assert agent.memory.calls[-1][1:] == (2, 1.0, True)
+  assert np.array_equal(agent.memory.calls[-1][0], np.full((5, 3), 9))
+  want = np.zeros((1, 5, 3, 4), np.uint8)
+  for k, v in enumerate((6, 7, 8, 9)):
+    want[..., k] = v
+  assert np.array_equal(agent.state, want)
+  # eval mode: nothing stored, nothing trained, the state still rolls
+  agent.eval_mode = True
+  calls, steps = len(agent.memory.calls), agent.training_steps
+  agent.begin_episode(obs(3))
+  agent.step(1.0, obs(4))
+  agent.end_episode(1.0)
+  assert len(agent.memory.calls) == calls and agent.training_steps == steps
+  assert agent.state[0, 0, 0].tolist() == [0, 0, 3, 4]
+
+
+def test_select_action_uses_the_reference_random_stream():
+  """dqn_agent.py:411-413: one random.random() per decision, then random.randint."""
+  from dopamine_b200.agents.dqn import dqn_agent
+  agent = _host_agent(num_actions=6, epsilon_fn=dqn_agent.identity_epsilon,
+                      epsilon_train=0.5, epsilon_eval=0.0)
+  agent.begin_episode(np.zeros((5, 3)))
+  random.seed(3)
+  got = [agent._select_action() for _ in range(50)]
+  random.seed(3)
+  want = []
+  for _ in range(50):
+    want.append(random.randint(0, 5) if random.random() <= 0.5 else 2)
+  assert got == want and len(set(got)) > 2
+  agent.eval_mode = True
+  assert [agent._select_action() for _ in range(5)] == [2] * 5
+
+
 @pytest.mark.gpu
 def test_begin_episode(mods):
   """dqn_agent_test.py:103-137 / rainbow_agent_test.py:384-418."""
