@@ -2,12 +2,15 @@
 // weights: replaces the TensorFlow graph built by RainbowAgent
 // (rainbow_agent.py:200-305) and project_distribution (rainbow_agent.py:340-494).
 //
-// One CTA per batch row, one warp per action; atoms are strided over lanes,
-// reductions are warp shuffles, the (Bellman support, probability) pairs of a row
-// sit in shared memory so that each output atom is accumulated over all j exactly
-// as the dense [B, N, N] form does — without ever materialising it.  All
-// arithmetic is f32 with explicit round-to-nearest intrinsics where TF evaluates
-// separate ops (no FMA contraction), true division and IEEE sqrt.
+// Two kernels share the arithmetic.  Batches below 128 rows (latency-bound): one CTA per
+// row, one warp per action (c51_loss_kernel).  From 128 rows (bound by instruction
+// issue): one WARP per row, 8 lanes per action (c51_loss_rows_kernel) — a third of the
+// instructions per row.  In both, atoms are strided over lanes, reductions are warp
+// shuffles, the (Bellman support, probability) pairs of a row sit in shared memory so
+// that each output atom is accumulated over all j exactly as the dense [B, N, N] form
+// does — without ever materialising it.  All arithmetic is f32 with explicit
+// round-to-nearest intrinsics where TF evaluates separate ops (no FMA contraction),
+// true division and IEEE sqrt.
 //
 // Traffic per row (A=18, N=51): 3 672 B of target logits + 204 B of online logits
 // read, <= 204 B target + 12 B scalars written (+3 672 B if grad_logits is asked).

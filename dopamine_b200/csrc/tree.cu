@@ -9,11 +9,14 @@
 // ONE cooperative launch per chunk of <= 4096 sets, one CTA per tree level (see
 // tree_update_kernel): every CTA groups the entries by node with a stable radix
 // sort in shared memory, the leaf CTA resolves duplicate leaves as chains and
-// publishes delta[k], a grid barrier, then each internal CTA runs one ordered fp64
-// add-chain per touched node.
+// publishes delta[k], a grid barrier, then each internal CTA adds the deltas of every
+// touched node in batch order: as a prefix scan that is kept only if it reproduces the
+// sequential recurrence bit for bit on the upper levels (chains_by_verified_scan),
+// as serial fp64 add-chains elsewhere and whenever the scan does not verify.
 //
-// The critical path is the root's chain of n dependent DADDs; everything else
-// overlaps with it.  Bandwidth is irrelevant here (n * depth * 16 bytes).
+// The root's chain of n dependent DADDs used to be the critical path (25 us at
+// n = 4096); with the verified scan it is the deepest levels' radix sort before the
+// barrier.  Bandwidth is irrelevant here (n * depth * 16 bytes).
 #include "replay.cuh"
 
 #include <cooperative_groups.h>
