@@ -205,6 +205,80 @@ def golden_checkpoint(prb):
   np.savez_compressed(os.path.join(OUT, 'checkpoint.npz'), **out)
 
 
+from tests.golden_cases import (ACTOR_CASES, ACTOR_PARAMS, actor_script,  # pylint: disable=g-import-not-at-top
+                                greedy_rule)
+
+
+def golden_actor(dqn_agent, crb):
+  """Drives the reference's own DQNAgent methods (dqn_agent.py:341-476), bound to a
+  hand-made object whose `_sess.run` answers the three ops they evaluate: the greedy
+  action (greedy_rule of the fed state), the train op and the target sync (recorded).
+  The replay memory is the reference's OutOfGraphReplayBuffer.  The last episode runs
+  in eval mode."""
+  import types
+  import zlib
+  out = {}
+  for name, (shape, stack, num_actions) in ACTOR_CASES.items():
+    memory = crb.OutOfGraphReplayBuffer(shape, stack, 200, 8, update_horizon=1)
+    log = dict(train=[], sync=[], stored=[])
+
+    class Self(object):
+      pass
+
+    me = Self()
+    me.observation_shape, me.stack_size, me.num_actions = shape, stack, num_actions
+    me.state = np.zeros((1,) + shape + (stack,), dtype=np.uint8)
+    me.eval_mode, me.training_steps = False, 0
+    me.epsilon_fn = dqn_agent.linearly_decaying_epsilon
+    for key, value in ACTOR_PARAMS.items():
+      setattr(me, key, value)
+    me.summary_writer = None
+    me._q_argmax, me._train_op, me._sync_qt_ops, me.state_ph = 'q', 'train', 'sync', 'ph'
+
+    def run(op, feed=None, me=me, log=log, num_actions=num_actions):
+      if op == 'q':
+        return greedy_rule(feed['ph'], num_actions)
+      log[op].append(me.training_steps)
+      return None
+
+    def add(obs, action, reward, terminal, memory=memory, log=log):
+      log['stored'].append((zlib.crc32(np.ascontiguousarray(obs).tobytes()),
+                            int(action), float(reward), int(terminal)))
+      memory.add(obs, action, reward, terminal)
+
+    me._sess = types.SimpleNamespace(run=run)
+    me._replay = types.SimpleNamespace(memory=memory, add=add)
+    for method in ('begin_episode', 'step', 'end_episode', '_select_action',
+                   '_train_step', '_record_observation', '_reset_state',
+                   '_store_transition'):
+      setattr(me, method, types.MethodType(getattr(dqn_agent.DQNAgent, method), me))
+    random.seed(2024)
+    actions, state_crcs = [], []
+    episodes = actor_script(name)
+    for e, episode in enumerate(episodes):
+      me.eval_mode = e == len(episodes) - 1
+      actions.append(me.begin_episode(episode[0][1]))
+      state_crcs.append(zlib.crc32(me.state.tobytes()))
+      for reward, observation in episode[1:]:
+        actions.append(me.step(reward, observation))
+        state_crcs.append(zlib.crc32(me.state.tobytes()))
+      me.end_episode(episode[-1][0])
+    p = name + '_'
+    out[p + 'actions'] = np.array(actions, np.int64)
+    out[p + 'state_crcs'] = np.array(state_crcs, np.uint32)
+    out[p + 'final_state'] = me.state.copy()
+    out[p + 'stored_crc'] = np.array([x[0] for x in log['stored']], np.uint32)
+    out[p + 'stored_action'] = np.array([x[1] for x in log['stored']], np.int64)
+    out[p + 'stored_reward'] = np.array([x[2] for x in log['stored']], np.float64)
+    out[p + 'stored_terminal'] = np.array([x[3] for x in log['stored']], np.int64)
+    out[p + 'train_steps'] = np.array(log['train'], np.int64)
+    out[p + 'sync_steps'] = np.array(log['sync'], np.int64)
+    out[p + 'training_steps'] = np.int64(me.training_steps)
+    out[p + 'add_count'] = np.int64(memory.add_count)
+    out[p + 'random_after'] = np.float64(random.random())
+  np.savez_compressed(os.path.join(OUT, 'actor_episodes.npz'), **out)
+
+
 def main():
   st, crb, prb = refshim.load_reference()
   os.makedirs(OUT, exist_ok=True)
@@ -212,6 +286,8 @@ def main():
   golden_uniform(crb)
   golden_prioritized(prb)
   golden_checkpoint(prb)
+  dqn_agent, _ = refshim.load_reference_agents()
+  golden_actor(dqn_agent, crb)
   for f in sorted(os.listdir(OUT)):
     print(f, os.path.getsize(os.path.join(OUT, f)))
 

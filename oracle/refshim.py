@@ -13,6 +13,16 @@ be imported without TensorFlow / gin installed, by registering stub modules:
 * `gin` / `gin.tf`: `@gin.configurable(...)` is used as a decorator on the
   Wrapped* classes (circular_replay_buffer.py:690, prioritized_replay_buffer.py:255).
 
+`load_reference_agents()` additionally imports `dopamine/agents/dqn/dqn_agent.py` and
+`dopamine/agents/rainbow/rainbow_agent.py`.  Their module bodies touch `tf.contrib.slim`,
+`tf.train.RMSPropOptimizer(...)` (a default argument) and import gym / atari_py / cv2
+through `atari_lib`; a permissive stand-in object answers those.  The agents' GRAPH
+code cannot run this way — only their plain-Python methods can (`begin_episode`, `step`,
+`end_episode`, `_select_action`, `_train_step`, `_record_observation`, `_reset_state`,
+`_store_transition`, `linearly_decaying_epsilon`), which is what
+`oracle/make_golden.py:golden_actor` and `tests/test_oracle_golden.py` execute, bound to
+a hand-made object in place of a constructed agent.
+
 No reference source is copied or modified.
 """
 import os
@@ -74,3 +84,37 @@ def load_reference():
   from dopamine.replay_memory import circular_replay_buffer
   from dopamine.replay_memory import prioritized_replay_buffer
   return sum_tree, circular_replay_buffer, prioritized_replay_buffer
+
+
+class _Anything(object):
+  """Answers any attribute access or call with itself (import-time stand-in)."""
+
+  def __getattr__(self, name):
+    if name.startswith('__') and name.endswith('__'):
+      raise AttributeError(name)
+    return self
+
+  def __call__(self, *args, **kwargs):
+    return self
+
+
+def load_reference_agents():
+  """Returns the reference's (dqn_agent, rainbow_agent) modules; see the header."""
+  load_reference()
+  anything = _Anything()
+  tf = sys.modules['tensorflow']
+  if not isinstance(tf, types.ModuleType) or getattr(tf, '__file__', None):
+    raise RuntimeError('a real TensorFlow is installed: import the agents directly')
+  if '__getattr__' not in tf.__dict__:
+    tf.__getattr__ = lambda name: anything  # PEP 562: tf.contrib, tf.train, ...
+  for name in ('atari_py', 'gym', 'gym.spaces', 'gym.spaces.box', 'cv2'):
+    if name not in sys.modules:
+      mod = types.ModuleType(name)
+      mod.__getattr__ = lambda attr: anything
+      sys.modules[name] = mod
+  gin = sys.modules['gin']
+  if '__getattr__' not in gin.__dict__:
+    gin.__getattr__ = lambda name: anything  # gin.constant, gin.REQUIRED, ...
+  from dopamine.agents.dqn import dqn_agent  # pylint: disable=g-import-not-at-top
+  from dopamine.agents.rainbow import rainbow_agent
+  return dqn_agent, rainbow_agent

@@ -137,3 +137,73 @@ def check_prioritized(make_buffer, name, nodes_of):
     got = to_np(got)
     assert got.dtype == want.dtype, (nm, got.dtype, want.dtype)
     assert got.tobytes() == want.tobytes(), 'output %r differs' % nm
+
+
+# ----------------------------------------------------------------- actor side ----
+# tests/golden/actor_episodes.npz: oracle/make_golden.py:golden_actor ran the
+# reference's own DQNAgent methods (dqn_agent.py:341-476) over these scripts.
+ACTOR_CASES = {
+    # name: (observation_shape, stack_size, num_actions)
+    'atari': ((84, 84), 4, 6),
+    'small': ((6, 5), 4, 4),
+    'stack1': ((3, 4), 1, 3),
+}
+
+ACTOR_PARAMS = dict(min_replay_history=10, update_period=2, target_update_period=8,
+                    epsilon_train=0.1, epsilon_eval=0.05, epsilon_decay_period=40)
+
+
+def actor_script(name):
+  """The episode script both sides replay (regenerated from the seed, not stored):
+  per episode a list of (reward, observation); the last entry closes the episode."""
+  shape, _, _ = ACTOR_CASES[name]
+  rng = np.random.RandomState(sum(map(ord, name)))
+  episodes = []
+  for length in (9, 17, 12, 8):
+    episodes.append([(float(np.float32(np.clip(rng.randn(), -1, 1))),
+                      rng.randint(0, 256, size=shape + (1,)).astype(np.uint8))
+                     for _ in range(length)])
+  return episodes
+
+
+def greedy_rule(state, num_actions):
+  """What the stand-in network prefers: a function of the WHOLE frame stack, so a
+  wrong roll or insert changes the actions."""
+  return int(to_np(state).astype(np.int64).sum() % num_actions)
+
+
+def check_actor(make_agent, name):
+  """make_agent(shape, stack, num_actions, params, log) -> an agent with the
+  reference's episode interface whose greedy action is greedy_rule(state), whose
+  train op / target sync append `training_steps` to log['train'] / log['sync'] and
+  whose replay adds append (crc32(obs), action, reward, terminal) to log['stored']
+  before reaching a real replay memory (`agent.memory`)."""
+  import zlib
+  g = load('actor_episodes')
+  p = name + '_'
+  shape, stack, num_actions = ACTOR_CASES[name]
+  log = dict(train=[], sync=[], stored=[])
+  agent = make_agent(shape, stack, num_actions, dict(ACTOR_PARAMS), log)
+  random.seed(2024)
+  actions, state_crcs = [], []
+  episodes = actor_script(name)
+  for e, episode in enumerate(episodes):
+    agent.eval_mode = e == len(episodes) - 1
+    actions.append(agent.begin_episode(episode[0][1]))
+    state_crcs.append(zlib.crc32(to_np(agent.state).tobytes()))
+    for reward, observation in episode[1:]:
+      actions.append(agent.step(reward, observation))
+      state_crcs.append(zlib.crc32(to_np(agent.state).tobytes()))
+    agent.end_episode(episode[-1][0])
+  assert actions == g[p + 'actions'].tolist()
+  assert state_crcs == g[p + 'state_crcs'].tolist()
+  assert to_np(agent.state).tobytes() == g[p + 'final_state'].tobytes()
+  assert [x[0] for x in log['stored']] == g[p + 'stored_crc'].tolist()
+  assert [x[1] for x in log['stored']] == g[p + 'stored_action'].tolist()
+  assert [x[2] for x in log['stored']] == g[p + 'stored_reward'].tolist()
+  assert [x[3] for x in log['stored']] == g[p + 'stored_terminal'].tolist()
+  assert log['train'] == g[p + 'train_steps'].tolist()
+  assert log['sync'] == g[p + 'sync_steps'].tolist()
+  assert agent.training_steps == int(g[p + 'training_steps'])
+  assert int(agent.memory.add_count) == int(g[p + 'add_count'])
+  assert random.random() == float(g[p + 'random_after'])  # same draws consumed

@@ -7,9 +7,12 @@ The agent tests restate tests/dopamine/agents/dqn/dqn_agent_test.py (testBeginEp
 testLinearlyDecayingEpsilon :297, testBundling :346) and rainbow_agent_test.py
 (testStoreTransitionWith*Sampling :493-520) against our classes."""
 import random
+import zlib
 
 import numpy as np
 import pytest
+
+from tests import golden_cases
 
 
 def test_linearly_decaying_epsilon_reference_schedule():
@@ -218,6 +221,66 @@ def test_select_action_uses_the_reference_random_stream():
   assert [agent._select_action() for _ in range(5)] == [2] * 5
 
 
+class _LoggedMemory(object):
+  """Forwards add() to a real replay memory after logging what the agent stored."""
+
+  def __init__(self, memory, log):
+    self._memory, self._log = memory, log
+
+  def add(self, obs, action, reward, terminal, *rest):
+    self._log['stored'].append((zlib.crc32(np.ascontiguousarray(obs).tobytes()),
+                                int(action), float(reward), int(terminal)))
+    self._memory.add(obs, action, reward, terminal, *rest)
+
+  def __getattr__(self, name):
+    return getattr(self._memory, name)
+
+
+@pytest.mark.parametrize('name', sorted(golden_cases.ACTOR_CASES))
+def test_acting_loop_matches_reference_fixture_on_the_host(name):
+  """tests/golden/actor_episodes.npz was written by the reference's own DQNAgent
+  methods (oracle/make_golden.py:golden_actor).  ActingLoop over the numpy stand-in
+  for the device state and the CPU port of the replay memory must reproduce it:
+  actions (greedy and exploratory), every intermediate state, every stored
+  transition, the steps on which the train op and the target sync ran, add_count
+  and the position of Python's random stream afterwards."""
+  from dopamine_b200.agents.dqn import dqn_agent
+  from oracle.replay_port import PortReplay
+
+  def make_agent(shape, stack, num_actions, params, log):
+
+    class HostAgent(dqn_agent.ActingLoop):
+
+      def __init__(self):
+        self.num_actions = num_actions
+        self.memory = _LoggedMemory(PortReplay(shape, stack, 200, 8, update_horizon=1),
+                                    log)
+        self._init_acting(shape, stack, np.uint8, **params)
+
+      def _make_actor_state(self, s, k, d):
+        return _HostActorState(s, k, d)
+
+      def q_values(self, state):
+        best = golden_cases.greedy_rule(state, num_actions)
+
+        class _Q(object):
+
+          def argmax(self, dim):
+            del dim
+            return [best]
+        return _Q()
+
+      def train_step(self):
+        log['train'].append(self.training_steps)
+
+      def sync_target(self):
+        log['sync'].append(self.training_steps)
+
+    return HostAgent()
+
+  golden_cases.check_actor(make_agent, name)
+
+
 @pytest.mark.gpu
 def test_begin_episode(mods):
   """dqn_agent_test.py:103-137 / rainbow_agent_test.py:384-418."""
@@ -350,3 +413,35 @@ def test_train_cadence_exploration_and_bundle(mods, tmp_path):
     assert torch.equal(a, b)
   x = agent.state
   assert torch.equal(agent.q_values(x), clone.q_values(x))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(golden_cases.ACTOR_CASES))
+def test_agent_matches_reference_fixture(mods, name):
+  """The same fixture through the real thing: RainbowAgent with its frame stack in
+  HBM (b2r_actor_record / b2r_actor_reset), the CUDA replay memory behind it
+  (uniform scheme: priority 1.0) and the reference's episode interface."""
+  torch = mods.torch
+
+  def make_agent(shape, stack, num_actions, params, log):
+
+    class Agent(mods.agent.RainbowAgent):
+
+      def q_values(self, state):
+        q = torch.zeros(1, num_actions, device='cuda')
+        q[0, golden_cases.greedy_rule(state, num_actions)] = 1.0
+        return q
+
+      def train_step(self):
+        log['train'].append(self.training_steps)
+
+      def sync_target(self):
+        log['sync'].append(self.training_steps)
+
+    agent = Agent(num_actions=num_actions, observation_shape=shape, stack_size=stack,
+                  update_horizon=1, replay_scheme='uniform', replay_capacity=200,
+                  batch_size=8, **params)
+    agent.memory = _LoggedMemory(agent.memory, log)
+    return agent
+
+  golden_cases.check_actor(make_agent, name)
