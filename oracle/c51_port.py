@@ -15,9 +15,14 @@ installed and cannot be, so this is a restatement, function by function:
 
 Parity: `project_distribution` is PINNED by the six known-answer vectors of
 tests/dopamine/agents/rainbow/rainbow_agent_test.py:178-285 (see
-tests/test_oracle_golden.py).  Loss / priority / IS-weight values are NOT pinned
-by any reference test: for those, "parity unpinned" — they
-are defined by this restatement, compared at 1e-6 relative.
+tests/test_oracle_golden.py).  Loss / priority / IS-weight values are not pinned
+by any reference TEST; they are pinned to the reference's CODE:
+tests/golden/losses.npz holds what RainbowAgent._build_target_distribution and
+_build_train_op (rainbow_agent.py:200-305) compute when executed unmodified over numpy
+stand-ins for the TensorFlow ops they call (oracle/tfshim.py, generator
+oracle/make_golden.py:golden_losses), and tests/test_loss_goldens.py holds this port to
+it at 1e-6 relative.  That fixes every structural decision of the reference (gathers,
+masks, axes, operation order), not the rounding of TensorFlow's own kernels.
 """
 import math
 

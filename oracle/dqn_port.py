@@ -5,9 +5,12 @@ max_a Q_target(s') * (1 - terminal)) and :302-322 (_build_train_op: chosen q thr
 one-hot, tf.losses.huber_loss with delta 1.0 and Reduction.NONE, then reduce_mean),
 with tf.losses.huber_loss as TF 1.x defines it: error = predictions - labels,
 quadratic = min(|error|, delta), linear = |error| - quadratic,
-loss = 0.5 quadratic^2 + delta * linear.  TensorFlow is absent here, so parity for
-these values is unpinned by the reference (no known-answer test exists for them in
-tests/dopamine/agents/dqn/dqn_agent_test.py); tolerance 1e-6 relative.
+loss = 0.5 quadratic^2 + delta * linear.  No known-answer test exists for these values
+in tests/dopamine/agents/dqn/dqn_agent_test.py and TensorFlow is absent; the port is
+pinned to the reference's CODE instead: DQNAgent._build_networks / _build_target_q_op /
+_build_train_op executed unmodified over numpy stand-ins for the TensorFlow ops
+(oracle/tfshim.py) wrote tests/golden/losses.npz, which tests/test_loss_goldens.py
+compares with at 1e-6 relative (structure pinned; TensorFlow's kernel rounding not).
 """
 import math
 

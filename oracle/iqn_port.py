@@ -9,12 +9,18 @@ the reference's tiling conventions ((samples x batch) rows, sample-major):
             |tau - 1[error < 0]| weighting, / kappa, reduce_sum over t, reduce_mean
             over t', and the scalar loss reduce_mean over the batch.
 
-PARITY UNPINNED: the reference holds no numeric test of this loss
+Parity: the reference holds no numeric test of this loss
 (tests/dopamine/agents/implicit_quantile/implicit_quantile_agent_test.py checks shapes
-and q-values only) and TensorFlow is not importable here, so no fixture could be
-generated.  `closed_form_f64` below is an independent float64 statement of the same
-mathematics that the port is cross-checked against (tests/test_iqn.py); tolerance of
-the CUDA path against this port: 2e-6 relative (f32 summation order differs).
+and q-values only) and TensorFlow is not importable here.  The port is pinned to the
+reference's CODE: ImplicitQuantileAgent._build_networks, _build_target_quantile_values_op
+and _build_train_op executed unmodified over numpy stand-ins for the TensorFlow ops they
+call (oracle/tfshim.py; generator oracle/make_golden.py:golden_losses) wrote
+tests/golden/losses.npz, and tests/test_loss_goldens.py holds this port to it at 1e-6
+relative (greedy actions exact).  That fixes the tiling / gather / transpose / mask /
+reduction structure, not the rounding of TensorFlow's kernels.  `closed_form_f64` below
+is an independent float64 statement of the same mathematics, a second check
+(tests/test_iqn.py); tolerance of the CUDA path against this port: 2e-6 relative (f32
+summation order differs).
 """
 import math
 

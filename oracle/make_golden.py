@@ -9,6 +9,7 @@ CPU test-suite never need the reference tree.
 Every fixture stores the inputs (so a test can replay the same history through the
 port / the CUDA library) and the reference's outputs.
 """
+import math
 import os
 import random
 import sys
@@ -279,6 +280,197 @@ def golden_actor(dqn_agent, crb):
   np.savez_compressed(os.path.join(OUT, 'actor_episodes.npz'), **out)
 
 
+def _bind(obj, cls, names):
+  import types
+  for name in names:
+    setattr(obj, name, types.MethodType(getattr(cls, name), obj))
+
+
+def golden_losses(dqn_agent, rainbow_agent, iq_agent):
+  """tests/golden/losses.npz: the reference's own loss-building methods, executed
+  eagerly on numpy arrays through oracle/tfshim.py (see its header for what that does
+  and does not pin).  The "networks" are seeded arrays handed out by a stand-in for
+  tf.make_template; everything downstream of them is the reference's code."""
+  import collections
+  import functools
+  import types
+  from oracle import tfshim
+  tf = sys.modules['tensorflow']
+  tfshim.install(tf)
+  tf.make_template = lambda name, fn, **unused: functools.partial(fn, name)
+  T = tfshim.tensor
+  out = {}
+
+  def replay(rng, batch, num_actions, with_probs):
+    r = types.SimpleNamespace()
+    r.batch_size = batch
+    r.states, r.next_states = 'states', 'next_states'
+    r.rewards = T(np.clip(rng.randn(batch), -1, 1).astype(np.float32))
+    r.terminals = T((rng.rand(batch) < 0.25).astype(np.uint8))
+    r.actions = T(rng.randint(0, num_actions, size=batch).astype(np.int32))
+    r.indices = T(np.arange(batch, dtype=np.int32))
+    r.transition = {}
+    if with_probs:
+      r.transition['sampling_probabilities'] = T(
+          np.sqrt(np.abs(rng.randn(batch)) + 1e-10).astype(np.float32))
+    r.set_priority_calls = []
+    r.tf_set_priority = lambda idx, pr: r.set_priority_calls.append(
+        (np.asarray(idx).copy(), np.asarray(pr).copy())) or 'update_priorities'
+    return r
+
+  # ---- Rainbow / C51 (RA:200-305 on DQ:237-263, AL:141-143) ----------------------
+  for case, (batch, num_actions, num_atoms, scheme, horizon) in {
+      'c51_per': (16, 6, 51, 'prioritized', 3),
+      'c51_uniform': (9, 4, 51, 'uniform', 1),
+      'c51_atoms11': (12, 3, 11, 'prioritized', 3)}.items():
+    rng = np.random.RandomState(sum(map(ord, case)))
+    me = types.SimpleNamespace()
+    me._replay = replay(rng, batch, num_actions, scheme == 'prioritized')
+    me._num_atoms, me.num_actions = num_atoms, num_actions
+    vmax = 10.
+    me._support = tf.linspace(-vmax, vmax, num_atoms)  # rainbow_agent.py:126
+    me.cumulative_gamma = math.pow(0.99, horizon)  # dqn_agent.py:175 (a Python float)
+    me._replay_scheme = scheme
+    me.summary_writer = None
+    me.state_ph = 'state_ph'
+    me.optimizer = types.SimpleNamespace(minimize=lambda loss: loss)
+    logits = {('Online', 'states'): rng.randn(batch, num_actions, num_atoms),
+              ('Target', 'next_states'): rng.randn(batch, num_actions, num_atoms),
+              ('Online', 'state_ph'): rng.randn(1, num_actions, num_atoms)}
+    net_type = collections.namedtuple('c51_network',
+                                      ['q_values', 'logits', 'probabilities'])
+
+    def template(name, state, me=me, logits=logits, net_type=net_type):
+      lg = T(logits[(name, state)].astype(np.float32))
+      probabilities = tf.softmax(lg)                      # atari_lib.py:142
+      q_values = tf.reduce_sum(me._support * probabilities, axis=2)  # :143
+      return net_type(q_values, lg, probabilities)
+
+    me._network_template = template
+    _bind(me, dqn_agent.DQNAgent, ['_build_networks'])
+    _bind(me, rainbow_agent.RainbowAgent, ['_build_target_distribution',
+                                           '_build_train_op'])
+    me._build_networks()
+    target = me._build_target_distribution()
+    mean_loss, loss = me._build_train_op()
+    p = case + '_'
+    out[p + 'cfg'] = np.array([batch, num_actions, num_atoms, horizon,
+                               int(scheme == 'prioritized')], np.int64)
+    out[p + 'online_logits'] = logits[('Online', 'states')].astype(np.float32)
+    out[p + 'target_logits'] = logits[('Target', 'next_states')].astype(np.float32)
+    out[p + 'rewards'] = np.asarray(me._replay.rewards)
+    out[p + 'terminals'] = np.asarray(me._replay.terminals)
+    out[p + 'actions'] = np.asarray(me._replay.actions)
+    if scheme == 'prioritized':
+      out[p + 'probs'] = np.asarray(me._replay.transition['sampling_probabilities'])
+      (_, priorities), = me._replay.set_priority_calls
+      out[p + 'priorities'] = priorities
+    out[p + 'support'] = np.asarray(me._support)
+    out[p + 'target'] = np.asarray(target)
+    out[p + 'weighted_loss'] = np.asarray(loss)
+    out[p + 'mean_loss'] = np.float32(mean_loss)
+    out[p + 'q_argmax'] = np.int64(me._q_argmax)
+
+  # ---- DQN (DQ:237-322) -----------------------------------------------------------
+  for case, (batch, num_actions, horizon) in {'dqn_a': (16, 6, 1),
+                                              'dqn_b': (7, 3, 3)}.items():
+    rng = np.random.RandomState(sum(map(ord, case)))
+    me = types.SimpleNamespace()
+    me._replay = replay(rng, batch, num_actions, False)
+    me.num_actions = num_actions
+    me.cumulative_gamma = math.pow(0.99, horizon)  # dqn_agent.py:175 (a Python float)
+    me.summary_writer = None
+    me.state_ph = 'state_ph'
+    me.optimizer = types.SimpleNamespace(minimize=lambda loss: loss)
+    q = {('Online', 'states'): rng.randn(batch, num_actions) * 2,
+         ('Target', 'next_states'): rng.randn(batch, num_actions) * 2,
+         ('Online', 'state_ph'): rng.randn(1, num_actions)}
+    net_type = collections.namedtuple('DQN_network', ['q_values'])
+    me._network_template = lambda name, state, q=q, net_type=net_type: net_type(
+        T(q[(name, state)].astype(np.float32)))
+    _bind(me, dqn_agent.DQNAgent, ['_build_networks', '_build_target_q_op',
+                                   '_build_train_op'])
+    me._build_networks()
+    losses = []
+    tf.losses.huber_loss = (lambda real: lambda *a, **k: losses.append(real(*a, **k))
+                            or losses[-1])(tfshim._huber_loss)  # pylint: disable=protected-access
+    mean_loss = me._build_train_op()
+    tf.losses.huber_loss = tfshim._huber_loss  # pylint: disable=protected-access
+    p = case + '_'
+    out[p + 'cfg'] = np.array([batch, num_actions, horizon], np.int64)
+    out[p + 'online_q'] = q[('Online', 'states')].astype(np.float32)
+    out[p + 'target_q'] = q[('Target', 'next_states')].astype(np.float32)
+    out[p + 'rewards'] = np.asarray(me._replay.rewards)
+    out[p + 'terminals'] = np.asarray(me._replay.terminals)
+    out[p + 'actions'] = np.asarray(me._replay.actions)
+    out[p + 'target'] = np.asarray(me._build_target_q_op())
+    out[p + 'loss'] = np.asarray(losses[0])
+    out[p + 'mean_loss'] = np.float32(mean_loss)
+
+  # ---- IQN (IQ:120-321) -----------------------------------------------------------
+  for case, (batch, num_actions, n, n_prime, k, kappa, horizon, double_dqn) in {
+      'iqn_a': (8, 5, 16, 12, 8, 1.0, 3, False),
+      'iqn_kappa': (6, 3, 8, 8, 4, 0.5, 1, True),
+      'iqn_paper': (4, 18, 64, 64, 32, 1.0, 3, False)}.items():
+    rng = np.random.RandomState(sum(map(ord, case)))
+    me = types.SimpleNamespace()
+    me._replay = replay(rng, batch, num_actions, False)
+    me.num_actions = num_actions
+    me.num_tau_samples, me.num_tau_prime_samples = n, n_prime
+    me.num_quantile_samples, me.kappa, me.double_dqn = k, kappa, double_dqn
+    me.cumulative_gamma = math.pow(0.99, horizon)  # dqn_agent.py:175 (a Python float)
+    me.summary_writer = None
+    me.state_ph = 'state_ph'
+    me.optimizer = types.SimpleNamespace(minimize=lambda loss: loss)
+    nets = {}
+    net_type = collections.namedtuple('iqn_network', ['quantile_values', 'quantiles'])
+
+    def template(name, state, num_quantiles, nets=nets, rng=rng, batch=batch,
+                 num_actions=num_actions, net_type=net_type):
+      rows = num_quantiles * (1 if state == 'state_ph' else batch)
+      key = (name, state, num_quantiles)
+      nets[key] = net_type(T((rng.randn(rows, num_actions) * 1.5).astype(np.float32)),
+                           T(rng.rand(rows, 1).astype(np.float32)))
+      return nets[key]
+
+    me._network_template = template
+    _bind(me, iq_agent.ImplicitQuantileAgent, ['_build_networks',
+                                               '_build_target_quantile_values_op',
+                                               '_build_train_op'])
+    me._build_networks()
+    # the per-row loss is what the final tf.reduce_mean (no axis, IQ:315-321) is fed
+    row_losses = []
+    real_mean = tf.reduce_mean
+
+    def spy_mean(x, *a, **k):
+      if not a and not k:
+        row_losses.append(np.asarray(x).copy())
+      return real_mean(x, *a, **k)
+
+    tf.reduce_mean = spy_mean
+    _, mean_loss = me._build_train_op()
+    tf.reduce_mean = real_mean
+    action_net = 'Online' if double_dqn else 'Target'
+    p = case + '_'
+    out[p + 'cfg'] = np.array([batch, num_actions, n, n_prime, k, horizon], np.int64)
+    out[p + 'kappa'] = np.float64(kappa)
+    out[p + 'online_quantile_values'] = np.asarray(
+        nets[('Online', 'states', n)].quantile_values)
+    out[p + 'quantiles'] = np.asarray(nets[('Online', 'states', n)].quantiles)
+    out[p + 'target_quantile_values'] = np.asarray(
+        nets[('Target', 'next_states', n_prime)].quantile_values)
+    out[p + 'action_quantile_values'] = np.asarray(
+        nets[(action_net, 'next_states', k)].quantile_values)
+    out[p + 'rewards'] = np.asarray(me._replay.rewards)
+    out[p + 'terminals'] = np.asarray(me._replay.terminals)
+    out[p + 'actions'] = np.asarray(me._replay.actions)
+    out[p + 'next_action'] = np.asarray(me._replay_next_qt_argmax)
+    out[p + 'target'] = np.asarray(me._build_target_quantile_values_op())
+    out[p + 'mean_loss'] = np.float32(mean_loss)
+    out[p + 'loss'] = row_losses[-1].reshape(batch)
+  np.savez_compressed(os.path.join(OUT, 'losses.npz'), **out)
+
+
 def main():
   st, crb, prb = refshim.load_reference()
   os.makedirs(OUT, exist_ok=True)
@@ -288,6 +480,8 @@ def main():
   golden_checkpoint(prb)
   dqn_agent, _ = refshim.load_reference_agents()
   golden_actor(dqn_agent, crb)
+  from dopamine.agents.implicit_quantile import implicit_quantile_agent  # pylint: disable=g-import-not-at-top
+  golden_losses(dqn_agent, refshim.load_reference_agents()[1], implicit_quantile_agent)
   for f in sorted(os.listdir(OUT)):
     print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -98,6 +98,14 @@ class _Anything(object):
     return self
 
 
+def _module_fallback(anything):
+  def fallback(name):
+    if name.startswith('__') and name.endswith('__'):
+      raise AttributeError(name)
+    return anything
+  return fallback
+
+
 def load_reference_agents():
   """Returns the reference's (dqn_agent, rainbow_agent) modules; see the header."""
   load_reference()
@@ -106,15 +114,15 @@ def load_reference_agents():
   if not isinstance(tf, types.ModuleType) or getattr(tf, '__file__', None):
     raise RuntimeError('a real TensorFlow is installed: import the agents directly')
   if '__getattr__' not in tf.__dict__:
-    tf.__getattr__ = lambda name: anything  # PEP 562: tf.contrib, tf.train, ...
+    tf.__getattr__ = _module_fallback(anything)  # PEP 562: tf.contrib, tf.train, ...
   for name in ('atari_py', 'gym', 'gym.spaces', 'gym.spaces.box', 'cv2'):
     if name not in sys.modules:
       mod = types.ModuleType(name)
-      mod.__getattr__ = lambda attr: anything
+      mod.__getattr__ = _module_fallback(anything)
       sys.modules[name] = mod
   gin = sys.modules['gin']
   if '__getattr__' not in gin.__dict__:
-    gin.__getattr__ = lambda name: anything  # gin.constant, gin.REQUIRED, ...
+    gin.__getattr__ = _module_fallback(anything)  # gin.constant, gin.REQUIRED, ...
   from dopamine.agents.dqn import dqn_agent  # pylint: disable=g-import-not-at-top
   from dopamine.agents.rainbow import rainbow_agent
   return dqn_agent, rainbow_agent
