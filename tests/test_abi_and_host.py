@@ -35,10 +35,13 @@ def test_struct_layouts_match_the_header(tmp_path):
   src = tmp_path / 'sizes.c'
   src.write_text(
       '#include <stdio.h>\n#include <stddef.h>\n#include "b200_replay.h"\n'
-      'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(b2r_config), '
+      'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", '
+      'sizeof(b2r_config), '
       'sizeof(b2r_batch), sizeof(b2r_c51_args), sizeof(b2r_trainer_config), '
       'offsetof(b2r_c51_args, min_probability), '
-      'offsetof(b2r_trainer_config, seed)); return 0; }\n')
+      'offsetof(b2r_trainer_config, seed), sizeof(b2r_iqn_args), '
+      'offsetof(b2r_iqn_args, action_quantile_values), '
+      'offsetof(b2r_iqn_args, next_action), sizeof(b2r_dqn_args)); return 0; }\n')
   exe = tmp_path / 'sizes'
   subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), str(src),
                          '-o', str(exe)])
@@ -47,7 +50,9 @@ def test_struct_layouts_match_the_header(tmp_path):
                  ctypes.sizeof(_native.C51Args),
                  ctypes.sizeof(_native.TrainerConfig),
                  _native.C51Args.min_probability.offset,
-                 _native.TrainerConfig.seed.offset]
+                 _native.TrainerConfig.seed.offset, ctypes.sizeof(_native.IqnArgs),
+                 _native.IqnArgs.action_quantile_values.offset,
+                 _native.IqnArgs.next_action.offset, ctypes.sizeof(_native.DqnArgs)]
   assert ctypes.sizeof(_native.Config) == 96
   assert ctypes.sizeof(_native.Batch) == 8 * 8 + 8 * _native.MAX_EXTRAS + 8
   assert ctypes.sizeof(_native.C51Args) == 16 + 15 * 8
