@@ -155,3 +155,39 @@ def test_port_side_by_side_with_imported_reference():
   b = port.sample_transition_batch()
   for x, y in zip(a, b):
     assert x.tobytes() == y.tobytes()
+
+
+@needs_reference
+def test_port_matches_reference_on_the_gairl_usage():
+  """GAIRL drives the uniform buffer directly (gairl_agent.py:300-316, 419, 453-455,
+  604): the configured batch of 256 from `sample_transition_batch()` and single
+  transitions from `sample_transition_batch(batch_size=1)` until a non-terminal one
+  turns up.  Same numpy global stream on both sides."""
+  _, crb, _ = refshim.load_reference()
+  shape, stack, cap = (6, 4), 4, 600
+  ref = crb.OutOfGraphReplayBuffer(shape, stack, cap, 256, update_horizon=1)
+  port = PortReplay(shape, stack, cap, 256, update_horizon=1)
+  rng = np.random.RandomState(21)
+  for _ in range(900):  # wraps once
+    row = (rng.randint(0, 256, size=shape).astype(np.uint8), rng.randint(4),
+           np.float32(rng.randn()), int(rng.rand() < 0.15))
+    ref.add(*row)
+    port.add(*row)
+  for seed in range(3):
+    np.random.seed(seed)
+    a = ref.sample_transition_batch()
+    np.random.seed(seed)
+    b = port.sample_transition_batch()
+    assert len(a[7]) == 256
+    for x, y in zip(a, b):
+      assert x.tobytes() == y.tobytes()
+  np.random.seed(8)
+  picks_ref = [ref.sample_transition_batch(batch_size=1) for _ in range(40)]
+  state_after_ref = np.random.get_state()[1].copy()
+  np.random.seed(8)
+  picks_port = [port.sample_transition_batch(batch_size=1) for _ in range(40)]
+  assert np.array_equal(state_after_ref, np.random.get_state()[1])
+  for a, b in zip(picks_ref, picks_port):
+    for x, y in zip(a, b):
+      assert x.tobytes() == y.tobytes()
+  assert any(int(t[6][0]) for t in picks_ref) and not all(int(t[6][0]) for t in picks_ref)
