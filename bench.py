@@ -1014,10 +1014,13 @@ def main():
     line['roofline'] = measure_gather_roofline(torch, wl, args.batch, peak_gbs)
     # the whole step (sampler + copies + loss + write-back) against the same peak:
     # algorithmic bytes of one step / device time of one step (N = 1: this rank's)
-    step_gbs = (line['roofline']['algorithmic_bytes_per_launch'] /
-                (ms / args.steps * 1e-3) / 1e9)
-    line['roofline']['whole_step_GBps'] = round(step_gbs, 1)
-    line['roofline']['whole_step_frac'] = round(step_gbs / peak_gbs, 4)
+    try:
+      step_gbs = (line['roofline']['algorithmic_bytes_per_launch'] /
+                  (ms / args.steps * 1e-3) / 1e9)
+      line['roofline']['whole_step_GBps'] = round(step_gbs, 1)
+      line['roofline']['whole_step_frac'] = round(step_gbs / peak_gbs, 4)
+    except (KeyError, ZeroDivisionError, TypeError):  # reporting only
+      pass
     if sweep_multi is not None:
       line['sweep'] = sweep_multi
     if e2e_multi is not None:
@@ -1030,14 +1033,17 @@ def main():
         ms_b = time_graph_or_eager(torch, lambda: wl.step(b), k, 5, use_graph,
                                    per_graph=steps_per_graph(k, args.steps_per_graph))
         roof = measure_gather_roofline(torch, wl, b, peak_gbs, launches=60)
-        step_gbs = roof['algorithmic_bytes_per_launch'] / (ms_b / k * 1e-3) / 1e9
         sweep[str(b)] = {'value': round(b * k / (ms_b * 1e-3), 1),
                          'ms_per_step': round(ms_b / k, 5),
                          'gather_GBps': roof['achieved'],
                          'gather_frac': roof['frac'],
-                         'gather_us': roof['us_per_launch'],
-                         'whole_step_GBps': round(step_gbs, 1),
-                         'whole_step_frac': round(step_gbs / peak_gbs, 4)}
+                         'gather_us': roof['us_per_launch']}
+        try:
+          step_gbs = roof['algorithmic_bytes_per_launch'] / (ms_b / k * 1e-3) / 1e9
+          sweep[str(b)]['whole_step_GBps'] = round(step_gbs, 1)
+          sweep[str(b)]['whole_step_frac'] = round(step_gbs / peak_gbs, 4)
+        except (KeyError, ZeroDivisionError, TypeError):  # reporting only
+          pass
       line['sweep'] = sweep
     if not args.no_e2e and world == 1:
       line['e2e_host_batch'] = measure_e2e_host_batch(
