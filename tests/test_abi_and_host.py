@@ -108,3 +108,15 @@ def test_fastcall_shim_builds_and_binds():
   assert fast.add_atari(0, 7056, object(), 1, 0.5, 0, 1.0, 0, -1) == -1
   with pytest.raises(TypeError):
     fast.add_atari(0, 7056, obs)
+
+
+def test_bench_steps_per_graph_times_exactly_the_requested_steps():
+  """bench.py captures several steps per CUDA graph launch; the group size must
+  divide --steps so that exactly K steps are timed, whatever K the driver passes."""
+  import bench
+  for steps in list(range(1, 60)) + [97, 100, 2000, 20000]:
+    for limit in (1, 10, 20):
+      g = bench.steps_per_graph(steps, limit)
+      assert 1 <= g <= limit and steps % g == 0
+      assert all(steps % d for d in range(g + 1, min(limit, steps) + 1))
+  assert bench.steps_per_graph(20000, 10) == 10 and bench.steps_per_graph(7, 10) == 7
