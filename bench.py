@@ -714,33 +714,69 @@ def measure_e2e_host_batch(torch, wl, batch, steps):
 # --------------------------------------------------------------------------- #
 # CPU arm: the oracle port (the reference's algorithm, Python/numpy)
 # --------------------------------------------------------------------------- #
-def build_cpu_port(capacity, batch, seed=1234):
-  from oracle.replay_port import PortPrioritizedReplay
+def cpu_arm_kind():
+  """'reference': the reference's own replay classes are importable (from
+  /root/reference, or from the copy `make -C oracle _ref` made for the GPU box);
+  'port': only the oracle restatement is."""
+  from oracle import refshim
+  return 'reference' if refshim.reference_available() else 'port'
+
+
+def build_cpu_port(capacity, batch, seed=1234, kind=None):
+  """A full, wrapped prioritized replay memory on the host with the bench's synthetic
+  contents: the reference's OutOfGraphPrioritizedReplayBuffer itself (kind
+  'reference'; prioritized_replay_buffer.py, imported unmodified behind
+  oracle/refshim.py's tensorflow / gin stubs) or the oracle port of it."""
+  kind = kind or cpu_arm_kind()
   rng = np.random.RandomState(seed)
-  port = PortPrioritizedReplay((84, 84), STACK, capacity, batch,
-                               update_horizon=HORIZON, gamma=GAMMA)
+  if kind == 'reference':
+    from oracle import refshim
+    _, crb, prb = refshim.load_reference()
+    port = prb.OutOfGraphPrioritizedReplayBuffer(
+        (84, 84), STACK, capacity, batch, update_horizon=HORIZON, gamma=GAMMA)
+    store = port._store  # pylint: disable=protected-access
+    levels = port.sum_tree.nodes
+    window = lambda cursor: crb.invalid_range(cursor, capacity, STACK, HORIZON)
+  else:
+    from oracle.replay_port import PortPrioritizedReplay, cursor_window
+    port = PortPrioritizedReplay((84, 84), STACK, capacity, batch,
+                                 update_horizon=HORIZON, gamma=GAMMA)
+    store = port.store
+    levels = [port.sum_tree.level(l) for l in range(port.sum_tree.depth + 1)]
+    window = lambda cursor: cursor_window(cursor, capacity, STACK, HORIZON)
   pattern = rng.randint(0, 256, size=(4096, 84, 84)).astype(np.uint8)
-  obs = port.store['observation']
+  obs = store['observation']
   for lo in range(0, capacity, 4096):
     n = min(4096, capacity - lo)
     obs[lo:lo + n] = pattern[:n]
-  port.store['action'][:] = rng.randint(0, NUM_ACTIONS, size=capacity)
-  port.store['reward'][:] = np.clip(rng.randn(capacity), -1, 1)
-  port.store['terminal'][:] = rng.rand(capacity) < 1e-3
+  store['action'][:] = rng.randint(0, NUM_ACTIONS, size=capacity)
+  store['reward'][:] = np.clip(rng.randn(capacity), -1, 1)
+  store['terminal'][:] = rng.rand(capacity) < 1e-3
   port.add_count = np.array(capacity + 500)
-  from oracle.replay_port import cursor_window
-  port.invalid_range = cursor_window(500, capacity, STACK, HORIZON)
+  port.invalid_range = window(500 % capacity)
   # tree: leaves = priorities, parents = child sums (timing only needs the shape)
-  tree = port.sum_tree
-  leaves = np.zeros(1 << tree.depth)
+  depth = len(levels) - 1
+  leaves = np.zeros(1 << depth)
   leaves[:capacity] = np.sqrt(np.abs(rng.randn(capacity)) + 1e-10).astype(
       np.float32)
   level = leaves
-  for l in range(tree.depth, -1, -1):
-    tree.level(l)[:] = level
+  for l in range(depth, -1, -1):
+    levels[l][:] = level
     level = level.reshape(-1, 2).sum(axis=1) if l else level
-  tree.max_recorded_priority = float(leaves.max())
+  port.sum_tree.max_recorded_priority = float(leaves.max())
   return port
+
+
+CPU_ARM_WHAT = {
+    'reference': 'the reference itself: dopamine.replay_memory (sum_tree, circular_'
+                 'replay_buffer, prioritized_replay_buffer) imported unmodified behind '
+                 'tensorflow/gin stubs for add / sample_transition_batch / set_priority; '
+                 'its C51 loss is TensorFlow-1.x graph code (absent), so that part is '
+                 'the numpy restatement oracle/c51_port.py; single thread as the '
+                 'reference is',
+    'port': 'oracle port of the reference: Python/numpy, single thread as the '
+            'reference is',
+}
 
 
 def cpu_steps(port, batch, budget_s, max_steps, seed=7, update_period=4):
@@ -770,15 +806,16 @@ def cpu_steps(port, batch, budget_s, max_steps, seed=7, update_period=4):
 
 
 def cpu_baseline(batch, capacity, budget_s=12.0):
-  port = build_cpu_port(capacity, batch)
+  kind = cpu_arm_kind()
+  port = build_cpu_port(capacity, batch, kind=kind)
   cpu_steps(port, batch, 0.0, 3)  # warm-up
   steps, dt = cpu_steps(port, batch, budget_s, 100000)
   return {
       'value': round(batch * steps / dt, 1), 'unit': UNIT, 'cores': 1,
-      'kind': 'port',
+      'kind': kind,
       'sample': '{} steps (4 x add() + sample + C51 + set_priority each) of batch {} '
-                'in {:.1f} s, capacity {} (oracle port of the reference: Python/numpy, '
-                'single thread as the reference is)'.format(steps, batch, dt, capacity),
+                'in {:.1f} s, capacity {} ({})'.format(steps, batch, dt, capacity,
+                                                       CPU_ARM_WHAT[kind]),
   }
 
 
@@ -818,8 +855,9 @@ def run_reference(args):
     return
   import multiprocessing as mp
   budget = 12.0
+  kind = cpu_arm_kind()
   t0 = time.perf_counter()
-  port = build_cpu_port(args.capacity, args.batch)
+  port = build_cpu_port(args.capacity, args.batch, kind=kind)
   cpu_steps(port, args.batch, 0.0, max(3, min(args.warmup, 20)))
   steps, dt = cpu_steps(port, args.batch, budget, 100000)
   del port
@@ -840,11 +878,10 @@ def run_reference(args):
       'dtype': 'u8', 'data': 'synthetic',
       'config': {'workload': workload_name(args.batch, args.capacity, 1)},
       'cpu_baseline': {
-          'value': round(rate, 1), 'unit': UNIT, 'cores': 1, 'kind': 'port',
+          'value': round(rate, 1), 'unit': UNIT, 'cores': 1, 'kind': kind,
           'sample': '{} steps (4 x add() + sample + C51 + set_priority each) of '
-                    'batch {} in {:.1f} s, one process, capacity {} (oracle port of '
-                    'the reference: Python/numpy, single-threaded as the reference '
-                    'is)'.format(steps, args.batch, dt, args.capacity),
+                    'batch {} in {:.1f} s, one process, capacity {} ({})'.format(
+                        steps, args.batch, dt, args.capacity, CPU_ARM_WHAT[kind]),
           'all_cores_replicas': {
               'value': round(rate_all, 1), 'unit': UNIT, 'cores': replicas,
               'host_cores': os.cpu_count(),

@@ -222,9 +222,11 @@ int flush_queue(b2r_buffer *buf, cudaStream_t stream, bool split = false);
 void fill_exchange_args(const b2r_exchange *x, ExchangeArgs *out);
 int launch_exchange_publish(const b2r_exchange *x, const b2r_buffer *buf,
                             cudaStream_t stream);
-// Sharded sampling (one CTA).  Totals come from `shard_totals` (device array) or,
-// when `x` is set, from the peer-memory exchange.  `scalars` / `min_prob_out` as in
-// launch_sample; out_count (nullable, device) receives this rank's row count.
+// Sharded sampling.  Totals come from `shard_totals` (device array) or, when `x` is
+// set, from the peer-memory exchange.  `scalars` / `min_prob_out` as in launch_sample;
+// out_count (nullable, device) receives this rank's row count.  max_rows (> 0): rows
+// the caller's outputs hold — a rank whose share of a Philox batch is larger serves the
+// first max_rows and latches B2R_ERR_UNSUPPORTED (0: global_batch rows).
 int launch_sample_sharded(b2r_buffer *buf, int32_t global_batch, int32_t num_shards,
                           int32_t rank, const double *shard_totals,
                           const b2r_exchange *x, const double *query01,
@@ -232,7 +234,7 @@ int launch_sample_sharded(b2r_buffer *buf, int32_t global_batch, int32_t num_sha
                           uint64_t offset, int32_t *out_slots, int32_t *out_indices,
                           int32_t *out_count, cudaStream_t stream,
                           const b2r_batch *scalars = nullptr,
-                          float *min_prob_out = nullptr);
+                          float *min_prob_out = nullptr, int32_t max_rows = 0);
 void fill_valid_ctx(const b2r_buffer *buf, ValidCtx *ctx);
 int ensure_ctx(b2r_buffer *buf, cudaStream_t stream);
 // tree.cu: largest batch the one-CTA tree kernel takes, and the fused flush launch

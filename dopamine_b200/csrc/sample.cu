@@ -13,6 +13,10 @@
 // columns of the batch (gather.cuh) and exchange shard totals over peer memory.
 #include "gather.cuh"
 
+#include <cstddef>
+#include <cstdlib>
+#include <cstring>
+
 namespace b2r {
 namespace {
 
@@ -498,6 +502,431 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
   B2R_MARK(8);
 }
 
+// ---- warp-per-stratum sampler -------------------------------------------------------
+// The kernel above gives a stratum to a THREAD and stages tree levels 0..10 in shared
+// memory first (one DRAM/L2 round trip, 3.2 k cycles, before any descent starts), then
+// walks three levels per round trip.  Here a stratum belongs to a WARP
+// (tree_descend_warp: five levels per round trip, nothing staged), every per-row load
+// that follows the descent is issued together, and the only block-wide work left is the
+// in-order replacement of invalid picks by the last CTA to finish.  A batch of B strata
+// is B warps spread over B / warps-per-CTA CTAs, so the sampler's latency is that of ONE
+// descent whatever the batch: ~4 L2 round trips for a 1M-leaf tree.
+//
+// The validity context (ValidCtx, 70 words) is read by the warp as 3 coalesced words
+// per lane and stays in registers: scalars come out by shuffle, `index in
+// invalid_range` is one compare per lane and a vote.
+constexpr int kCtxWords = (int)(sizeof(ValidCtx) / 8);
+static_assert(sizeof(ValidCtx) == 560 && offsetof(ValidCtx, invalid) == 40 &&
+              offsetof(ValidCtx, term_flag) == 552 && offsetof(ValidCtx, stack) == 24 &&
+              offsetof(ValidCtx, n_invalid) == 32,
+              "WarpCtx picks ValidCtx fields by word");
+
+struct WarpCtx {
+  uint64_t w[3];  // words lane, lane + 32, lane + 64 of the ValidCtx image
+  int64_t capacity, add_count, cursor;
+  int stack, horizon, n_invalid;
+  const uint8_t *term_flag;
+};
+
+__device__ __forceinline__ void warp_ctx_issue(const ValidCtx *src, int lane, WarpCtx *c) {
+  const uint64_t *p = reinterpret_cast<const uint64_t *>(src);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    c->w[r] = lane + 32 * r < kCtxWords ? p[lane + 32 * r] : 0ull;
+}
+
+__device__ __forceinline__ void warp_ctx_finish(WarpCtx *c) {
+  const unsigned full = 0xffffffffu;
+  c->capacity = (int64_t)__shfl_sync(full, c->w[0], 0);
+  c->add_count = (int64_t)__shfl_sync(full, c->w[0], 1);
+  c->cursor = (int64_t)__shfl_sync(full, c->w[0], 2);
+  const uint64_t sh = __shfl_sync(full, c->w[0], 3);
+  c->stack = (int)(uint32_t)sh;
+  c->horizon = (int)(uint32_t)(sh >> 32);
+  c->n_invalid = (int)(uint32_t)__shfl_sync(full, c->w[0], 4);
+  c->term_flag = reinterpret_cast<const uint8_t *>(__shfl_sync(full, c->w[2], 5));
+}
+
+// is_valid_transition (circular_replay_buffer.py:381-414) by a warp; the same answer in
+// every lane.
+__device__ __forceinline__ bool warp_is_valid(const WarpCtx &c, int64_t index, int lane) {
+  if (index < 0 || index >= c.capacity) return false;
+  bool ok = true;
+  if (c.add_count < c.capacity)  // not full
+    ok = index < c.cursor - c.horizon && index >= c.stack - 1;
+  bool bad = false;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int k = lane + 32 * r - 5;  // invalid[k] is word 5 + k
+    bad = bad || (k >= 0 && k < c.n_invalid && (int64_t)c.w[r] == index);
+  }
+  // get_terminal_stack(index)[:-1].any()
+  for (int k = lane + 1; k < c.stack; k += 32) {
+    int64_t s = index - k;
+    if (s < 0) s += c.capacity;
+    bad = bad || c.term_flag[s] != 0;
+  }
+  return ok && !__any_sync(0xffffffffu, bad);
+}
+
+// Thread-per-draw descent from the root with nothing staged (the rare later rounds of
+// the retry loop); out of line so that its registers do not burden the warp path.
+static __device__ __noinline__ int64_t descend_from_root(const double *heap, int depth,
+                                                         double q, uint32_t zero) {
+  return tree_descend_staged<3>(heap, nullptr, 0, depth, q, zero);
+}
+
+// grid = ceil(strata / warps per CTA) CTAs (sharded: an estimate of this rank's share;
+// the warps stride over whatever the share turns out to be).  Scratch, all int32 words
+// of a.inv_slots: [0, cap) invalid flag of every output position, [cap, 2 cap) the
+// ordered list of invalid positions (built by the last CTA); a.tile_min: one minimum
+// per CTA.  a.tile_counts is unused.
+__global__ void __launch_bounds__(256)
+per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a, int scratch_cap) {
+  __shared__ double s_totals[kMaxShards];
+  __shared__ int s_first[2];
+  __shared__ float s_wmin[8];
+  __shared__ int warp_counts[32];
+  __shared__ float warp_mins[32];
+  __shared__ int s_wvalid[8];
+  __shared__ int s_draws_used, s_last_idx, s_last_valid, s_is_last;
+  __shared__ ValidCtx s_valid;  // thread-per-draw retry rounds only
+
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+  pdl_release();
+  pdl_acquire();
+  // every load of the prologue is issued before the first one is used
+  WarpCtx ctx;
+  warp_ctx_issue(a.valid_dev, lane, &ctx);
+  const uint64_t draws_before = a.counter ? *a.counter : 0ull;
+  const bool exchange = a.xchg.local != nullptr && a.num_shards > 1;
+  uint64_t xseq = 0;
+  if (exchange) xseq = *a.xchg.seq + 1;
+  const double local_total = a.heap[1];  // root of the 1-based heap
+  const uint64_t draw_offset = a.offset + draws_before;
+  if (exchange && blockIdx.x == 0)
+    exchange_publish(a.xchg, a.num_shards, a.rank, local_total, xseq);
+  const double *shard_totals = a.shard_totals;
+  if (exchange) {
+    exchange_collect(a.xchg, a.num_shards, a.rank, local_total, xseq, s_totals,
+                     a.latched);
+    __syncthreads();
+    shard_totals = s_totals;
+  }
+  warp_ctx_finish(&ctx);
+  double grand_total = local_total;
+  if (a.num_shards > 1) {
+    grand_total = 0.0;
+    for (int g = 0; g < a.num_shards; ++g)
+      grand_total = __dadd_rn(grand_total, shard_totals[g]);
+  }
+  if (grand_total == 0.0 || (a.num_shards == 1 && local_total == 0.0)) {
+    // sum_tree.py:159-160; every CTA takes this branch, the last to arrive closes
+    if (threadIdx.x == 0 &&
+        (gridDim.x == 1 || atomicAdd(a.ticket, 1u) == gridDim.x - 1)) {
+      if (gridDim.x > 1) *a.ticket = 0u;
+      a.info[0] = B2R_ERR_EMPTY_TREE;
+      a.info[1] = 0; a.info[2] = 0; a.info[3] = 0;
+      if (a.count_out) *a.count_out = 0;
+      if (a.min_prob_out) *a.min_prob_out = INFINITY;
+      if (a.counter) *a.counter = draws_before + 1;
+      if (exchange) *a.xchg.seq = xseq;
+      if (a.latched && a.latched[0] == 0) a.latched[0] = B2R_ERR_EMPTY_TREE;
+    }
+    return;
+  }
+
+  const double step = 1.0 / (double)a.batch;  // np.linspace(0, 1, batch + 1)
+  auto stratum_owner = [&](int i, double u, double *residual) {
+    double q01;
+    if (a.use_philox) {
+      const double lo = __dmul_rn((double)i, step);
+      const double hi = (i + 1 == a.batch) ? 1.0 : __dmul_rn((double)(i + 1), step);
+      q01 = __dadd_rn(lo, __dmul_rn(__dsub_rn(hi, lo), u));  // random.uniform
+    } else {
+      q01 = a.strat_query01[i];
+    }
+    double mass = __dmul_rn(q01, grand_total);
+    int owner = 0;
+    for (; owner < a.num_shards - 1; ++owner) {
+      const double left = shard_totals[owner];
+      if (mass < left) break;
+      mass = __dsub_rn(mass, left);
+    }
+    *residual = mass;
+    return owner;
+  };
+  // This rank's strata: all of them, or (shard_ranges: Philox strata grow with the
+  // stratum index and the rank-order scan is monotone) the range [lo, hi) found by two
+  // simultaneous k-ary searches, blockDim candidates per round.
+  int range_lo = 0, range_hi = a.batch;
+  if (a.shard_ranges) {
+    const int fan = blockDim.x;
+    int base[2] = {0, 0}, limit[2] = {a.batch, a.batch};
+    while (base[0] < limit[0] || base[1] < limit[1]) {
+      if (threadIdx.x < 2) s_first[threadIdx.x] = fan;
+      __syncthreads();
+      int stride[2];
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int width = limit[w] - base[w];
+        stride[w] = (width + fan - 1) / fan;
+        const int cand = base[w] + (int)threadIdx.x * stride[w];
+        if (width > 0) {
+          bool hit = cand >= limit[w];
+          if (!hit) {
+            double unused;
+            const int owner = stratum_owner(
+                cand, philox_uniform53(a.seed, draw_offset, (uint64_t)cand), &unused);
+            hit = w == 0 ? owner >= a.rank : owner > a.rank;
+          }
+          if (hit) atomicMin(&s_first[w], (int)threadIdx.x);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        if (base[w] >= limit[w]) continue;
+        const int t = s_first[w];
+        const int hit = base[w] + t * stride[w];
+        const int new_limit = hit < limit[w] ? hit : limit[w];
+        base[w] = t == 0 ? new_limit : base[w] + (t - 1) * stride[w] + 1;
+        if (base[w] > new_limit) base[w] = new_limit;
+        limit[w] = new_limit;
+      }
+      __syncthreads();
+    }
+    range_lo = base[0];
+    range_hi = base[1];
+  }
+  const int n_all = range_hi - range_lo;
+  // rows beyond the scratch / output capacity of a sharded step are dropped and latched
+  const int n_mine = n_all < scratch_cap ? n_all : scratch_cap;
+  int32_t *inv_flag = a.inv_slots;
+  int32_t *inv_list = a.inv_slots + scratch_cap;
+  const bool fast_scalars = a.with_scalars && a.sc.fast;
+  const bool want_min = a.with_scalars && a.min_prob_out != nullptr;
+
+  // ---- stratified pass (sum_tree.py:162-166 + prioritized_replay_buffer.py:155)
+  float my_min = INFINITY;
+#pragma unroll 1
+  for (int pos = blockIdx.x * warps + warp; pos < n_mine; pos += gridDim.x * warps) {
+    const int i = range_lo + pos;
+    const double u = a.use_philox ? philox_uniform53(a.seed, draw_offset, (uint64_t)i) : 0.0;
+    double mass;
+    stratum_owner(i, u, &mass);  // (inside the range the owner is this rank)
+    const int64_t idx = tree_descend_warp(a.heap, a.depth, mass, lane);
+    ScalarLoads row;
+    if (fast_scalars && lane == 0) load_scalars(a.sc, idx, &row);
+    const bool valid = warp_is_valid(ctx, idx, lane);
+    if (lane == 0) {
+      a.out_idx[pos] = (int32_t)idx;
+      if (a.out_slots) a.out_slots[pos] = i;
+      inv_flag[pos] = valid ? 0 : 1;
+      if (valid) {
+        float p = INFINITY;
+        if (fast_scalars) p = finish_scalars(a.sc, pos, idx, row);
+        else if (a.with_scalars) p = write_scalars(a.sc, pos, idx);
+        my_min = fminf(my_min, p);
+      }
+    }
+  }
+  if (want_min) {
+    if (lane == 0) s_wmin[warp] = my_min;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = s_wmin[0];
+      for (int w = 1; w < warps; ++w) m = fminf(m, s_wmin[w]);
+      a.tile_min[blockIdx.x] = m;
+    }
+  }
+
+  // ---- only the last CTA to finish goes on
+  if (gridDim.x > 1) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+  } else {
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    s_draws_used = 0;
+    s_last_idx = -1;
+    s_last_valid = 0;
+    if (gridDim.x > 1) *a.ticket = 0u;  // ready for the next launch
+  }
+  // ordered list of the invalid positions: thread t owns a contiguous run of flags
+  const int per = (n_mine + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int f0 = min(n_mine, (int)threadIdx.x * per), f1 = min(n_mine, f0 + per);
+  int mine_inv = 0;
+  for (int p = f0; p < f1; ++p) mine_inv += __ldcg(inv_flag + p);
+  int inc = mine_inv;  // inclusive scan over the block
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(full, inc, o);
+    if (lane >= o) inc += v;
+  }
+  if (lane == 31) warp_counts[warp] = inc;
+  __syncthreads();
+  int before = inc - mine_inv, num_invalid = 0;
+  for (int w = 0; w < warps; ++w) {
+    const int cnt = warp_counts[w];
+    if (w < warp) before += cnt;
+    num_invalid += cnt;
+  }
+  if (mine_inv > 0)
+    for (int p = f0; p < f1; ++p)
+      if (__ldcg(inv_flag + p)) inv_list[before++] = p;
+  __syncthreads();  // inv_list (global) and the shared scalars are visible to the block
+
+  // ---- in-order replacement of invalid slots (prioritized_replay_buffer.py:156-170):
+  // the j-th invalid slot takes the j-th valid draw out of a shared budget.  Windows of
+  // retry draws are evaluated speculatively in parallel — the first one warp per draw
+  // (a handful of invalid picks is the usual case), later ones a thread per draw.
+  int found = 0, drawn = 0;
+  float fix_min = INFINITY;
+  const int budget = a.max_attempts;
+  const uint64_t retry_seed = a.seed + 0x9E3779B97F4A7C15ull * (uint64_t)(a.rank + 1);
+  auto retry_uniform = [&](int r) {
+    // Philox retry stream: rank-private (strata streams are shared by all ranks)
+    return (a.use_philox || a.retry_u01 == nullptr)
+               ? philox_uniform53(retry_seed, draw_offset, (uint64_t)a.batch + (uint64_t)r)
+               : a.retry_u01[r];
+  };
+  bool first_round = true;
+  while (num_invalid > 0 && found < num_invalid && drawn < budget) {
+    int round_valid;
+    if (first_round) {
+      const int r = drawn + warp;
+      const bool active = r < budget;
+      bool valid = false;
+      int64_t idx = 0;
+      ScalarLoads row;
+      if (active) {
+        // sum_tree.py:123-124: query = random.random() * total
+        idx = tree_descend_warp(a.heap, a.depth, __dmul_rn(retry_uniform(r), local_total),
+                                lane);
+        if (fast_scalars && lane == 0) load_scalars(a.sc, idx, &row);
+        valid = warp_is_valid(ctx, idx, lane);
+      }
+      if (lane == 0) s_wvalid[warp] = active && valid ? 1 : 0;
+      __syncthreads();
+      int ord = found;
+      round_valid = 0;
+      for (int w = 0; w < warps; ++w) {
+        if (w < warp) ord += s_wvalid[w];
+        round_valid += s_wvalid[w];
+      }
+      if (lane == 0 && active) {
+        if (valid && ord < num_invalid) {
+          const int slot = inv_list[ord];
+          a.out_idx[slot] = (int32_t)idx;
+          if (fast_scalars)
+            fix_min = fminf(fix_min, finish_scalars(a.sc, slot, idx, row));
+          else if (a.with_scalars)
+            fix_min = fminf(fix_min, write_scalars(a.sc, slot, idx));
+          if (ord == num_invalid - 1) s_draws_used = r + 1;
+        }
+        if (r == budget - 1) {
+          s_last_idx = (int)idx;
+          s_last_valid = valid ? 1 : 0;
+        }
+      }
+      drawn += warps;
+      first_round = false;
+      // the thread-per-draw rounds test validity against a shared-memory context
+      for (int w = threadIdx.x; w < kCtxWords; w += blockDim.x)
+        reinterpret_cast<uint64_t *>(&s_valid)[w] =
+            reinterpret_cast<const uint64_t *>(a.valid_dev)[w];
+    } else {
+      const int r = drawn + threadIdx.x;
+      const bool active = r < budget;
+      bool valid = false;
+      int64_t idx = 0;
+      ScalarLoads row;
+      if (active) {
+        idx = descend_from_root(a.heap, a.depth,
+                                __dmul_rn(retry_uniform(r), local_total), a.zero);
+        if (fast_scalars) load_scalars(a.sc, idx, &row);
+        valid = is_valid_transition(s_valid, idx);
+      }
+      const int ord = found + block_scan_flag(active && valid, warp_counts, &round_valid);
+      if (active && valid && ord < num_invalid) {
+        const int slot = inv_list[ord];
+        a.out_idx[slot] = (int32_t)idx;
+        if (fast_scalars)
+          fix_min = fminf(fix_min, finish_scalars(a.sc, slot, idx, row));
+        else if (a.with_scalars)
+          fix_min = fminf(fix_min, write_scalars(a.sc, slot, idx));
+        if (ord == num_invalid - 1) s_draws_used = r + 1;
+      }
+      if (active && r == budget - 1) {
+        s_last_idx = (int)idx;
+        s_last_valid = valid ? 1 : 0;
+      }
+      drawn += blockDim.x;
+    }
+    found += round_valid;
+    __syncthreads();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int status = B2R_OK, fail_slot = 0, used = 0;
+    if (num_invalid > 0) {
+      if (found >= num_invalid) {
+        used = s_draws_used;
+      } else {
+        // Every one of the `budget` draws was consumed; `found` slots were fixed.
+        used = budget;
+        const int next_slot = inv_list[found];  // first invalid slot still unresolved
+        if (budget == 0 || s_last_valid) {
+          // budget already 0 when this slot is reached -> PRB:159-163
+          status = B2R_ERR_SAMPLE_ATTEMPTS;
+          fail_slot = next_slot;
+        } else {
+          // the slot burnt the rest of the budget and keeps its last (invalid) draw;
+          // only a FURTHER invalid slot raises.
+          a.out_idx[next_slot] = s_last_idx;
+          if (a.with_scalars && s_last_idx >= 0 && s_last_idx < ctx.capacity)
+            fix_min = fminf(fix_min, write_scalars(a.sc, next_slot, s_last_idx));
+          if (num_invalid > found + 1) {
+            status = B2R_ERR_SAMPLE_ATTEMPTS;
+            fail_slot = inv_list[found + 1];
+          }
+        }
+      }
+    }
+    if (n_all > n_mine && status == B2R_OK) {  // a sharded step outgrew its buffers
+      status = B2R_ERR_UNSUPPORTED;
+      fail_slot = n_all;
+    }
+    if (a.counter) *a.counter = draws_before + 1;
+    if (exchange) *a.xchg.seq = xseq;
+    a.info[0] = status;
+    a.info[1] = a.out_slots ? (status ? a.out_slots[fail_slot < n_mine ? fail_slot : 0] : 0)
+                            : fail_slot;
+    a.info[2] = used;
+    a.info[3] = n_mine;
+    if (a.count_out) *a.count_out = n_mine;
+    if (status != B2R_OK && a.latched && a.latched[0] == 0) {
+      a.latched[0] = status;
+      a.latched[1] = fail_slot;
+    }
+  }
+  if (want_min) {
+    float m = fix_min;
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x)
+      m = fminf(m, __ldcg(a.tile_min + c));
+    m = block_min(m, warp_mins);
+    if (threadIdx.x == 0) *a.min_prob_out = m;
+  }
+}
+
 struct UniformSampleArgs {
   ValidCtx valid;
   int batch;
@@ -611,6 +1040,34 @@ static void sample_shape(int batch, int *threads, int *tiles) {
   }
 }
 
+// 1 (default): a warp per stratum (per_sample_warp_kernel); 0: a thread per stratum
+// over shared-memory-staged top levels (per_sample_kernel; B2R_SAMPLER=thread).
+// Caller-supplied queries of a SHARDED batch always take the thread kernel: their
+// owners need not be monotone in the stratum index, so the rank's rows are compacted
+// by one CTA.
+static int sampler_variant() {
+  static const int v = [] {
+    const char *e = std::getenv("B2R_SAMPLER");
+    return e != nullptr && std::strcmp(e, "thread") == 0 ? 0 : 1;
+  }();
+  return v;
+}
+
+// Grid of the warp sampler for `strata` expected strata; scratch for `cap` rows.
+static int warp_sampler_setup(b2r_buffer *b, int strata, int cap, PerSampleArgs *a,
+                              int *threads, int *ctas) {
+  const int warps = strata <= 64 ? 4 : 8;
+  *threads = warps * 32;
+  *ctas = (strata + warps - 1) / warps;
+  if (*ctas < 1) *ctas = 1;
+  if (*ctas > 8192) *ctas = 8192;  // the warps stride
+  B2R_TRY(ensure_inv_slots(b, 2 * (int64_t)cap + *ctas + 8));
+  a->inv_slots = b->inv_slots;
+  a->tile_counts = nullptr;
+  a->tile_min = reinterpret_cast<float *>(b->inv_slots + 2 * (int64_t)cap);
+  return B2R_OK;
+}
+
 int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
                   uint64_t offset, const double *strat_dev,
                   const double *retry_dev, int32_t n_retry, int32_t *out_idx_dev,
@@ -620,8 +1077,12 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   sample_shape(batch, &threads, &tiles);
   if (tiles > kMaxTiles)
     return fail(B2R_ERR_UNSUPPORTED, "batch above %d is not supported", kMaxTiles * 128);
-  B2R_TRY(ensure_inv_slots(b, (int64_t)tiles * threads + 2 * kMaxTiles + 8));
+  const bool by_warp = sampler_variant() == 1;
   PerSampleArgs a;
+  if (by_warp)
+    B2R_TRY(warp_sampler_setup(b, batch, batch, &a, &threads, &tiles));
+  else
+    B2R_TRY(ensure_inv_slots(b, (int64_t)tiles * threads + 2 * kMaxTiles + 8));
   a.heap = b->tree->heap;
   a.depth = b->tree->depth;
   B2R_TRY(ensure_ctx(b, stream));
@@ -636,9 +1097,11 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   a.strat_query01 = strat_dev;
   a.retry_u01 = retry_dev;
   a.out_idx = out_idx_dev;
-  a.inv_slots = b->inv_slots;
-  a.tile_counts = b->inv_slots + (int64_t)tiles * threads;
-  a.tile_min = reinterpret_cast<float *>(a.tile_counts + kMaxTiles);
+  if (!by_warp) {
+    a.inv_slots = b->inv_slots;
+    a.tile_counts = b->inv_slots + (int64_t)tiles * threads;
+    a.tile_min = reinterpret_cast<float *>(a.tile_counts + kMaxTiles);
+  }
   a.ticket = b->ticket;
   a.info = info_dev;
   a.latched = philox ? b->status : nullptr;
@@ -656,6 +1119,12 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
     if (a.sc.indices_out == out_idx_dev) a.sc.indices_out = nullptr;
   }
   set_tree_window(b->tree->heap, (size_t)b->tree->leaves * 16);
+  if (by_warp) {
+    B2R_CUDA(launch(per_sample_warp_kernel, dim3(tiles), dim3(threads), 0, stream, a,
+                    (int)batch));
+    B2R_LAUNCHED();
+    return B2R_OK;
+  }
   // 3 tree levels per memory round trip (more would bloat the straight-line code,
   // and a cold instruction cache costs more than the saved round trips).
   B2R_CUDA(launch(per_sample_kernel<3, 256>, dim3(tiles), dim3(threads), 0, stream, a));
@@ -676,22 +1145,38 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
                           int32_t n_retry, const double *retry_u01, uint64_t seed,
                           uint64_t offset, int32_t *out_slots, int32_t *out_indices,
                           int32_t *out_count, cudaStream_t s,
-                          const b2r_batch *scalars, float *min_prob_out) {
+                          const b2r_batch *scalars, float *min_prob_out,
+                          int32_t max_rows) {
   if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
   if (global_batch <= 0 || num_shards <= 0 || num_shards > kMaxShards || rank < 0 ||
       rank >= num_shards)
     return fail(B2R_ERR_INVALID_ARGUMENT, "bad sharding arguments");
   if (x && !x->connected && x->world > 1)
     return fail(B2R_ERR_INVALID_ARGUMENT, "the exchange is not connected");
-  // Small global batches and caller-supplied queries (any order): one CTA walks
-  // every tile and compacts this rank's strata with block scans.  Philox strata of a
-  // large global batch: tiles of 128 over many CTAs (see shard_ranges).
-  const bool ranges = query01 == nullptr && global_batch > 256 && num_shards > 1;
-  const int threads = global_batch <= 256 ? 256 : (ranges ? 128 : 1024);
-  const int tiles = (global_batch + threads - 1) / threads;
+  // Philox strata: the warp sampler over this rank's stratum range (see shard_ranges).
+  // Caller-supplied queries (any order): one CTA of the thread kernel walks every tile
+  // and compacts this rank's strata with block scans (tiles of 128 over many CTAs with
+  // the range search for Philox strata when B2R_SAMPLER=thread).
+  const bool by_warp = sampler_variant() == 1 && query01 == nullptr;
+  const bool ranges = query01 == nullptr && num_shards > 1 &&
+                      (by_warp || global_batch > 256);
+  int threads = global_batch <= 256 ? 256 : (ranges ? 128 : 1024);
+  int tiles = (global_batch + threads - 1) / threads;
   if (tiles > kMaxTiles) return fail(B2R_ERR_UNSUPPORTED, "global batch too large");
-  B2R_TRY(ensure_inv_slots(b, (int64_t)tiles * threads + 2 * kMaxTiles + 8));
   PerSampleArgs a;
+  const int cap = max_rows > 0 && max_rows < global_batch ? max_rows : global_batch;
+  if (by_warp) {
+    // grid for the expected share plus a margin; the warps stride over the rest
+    int expect = num_shards > 1 ? global_batch / num_shards + global_batch / (4 * num_shards) + 8
+                                : global_batch;
+    if (expect > cap) expect = cap;
+    B2R_TRY(warp_sampler_setup(b, expect, cap, &a, &threads, &tiles));
+  } else {
+    B2R_TRY(ensure_inv_slots(b, (int64_t)tiles * threads + 2 * kMaxTiles + 8));
+    a.inv_slots = b->inv_slots;
+    a.tile_counts = b->inv_slots + (int64_t)tiles * threads;
+    a.tile_min = reinterpret_cast<float *>(a.tile_counts + kMaxTiles);
+  }
   a.heap = b->tree->heap;
   a.depth = b->tree->depth;
   B2R_TRY(ensure_ctx(b, s));
@@ -709,9 +1194,6 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
   a.strat_query01 = query01;
   a.retry_u01 = retry_u01;
   a.out_idx = out_indices;
-  a.inv_slots = b->inv_slots;
-  a.tile_counts = b->inv_slots + (int64_t)tiles * threads;
-  a.tile_min = reinterpret_cast<float *>(a.tile_counts + kMaxTiles);
   a.ticket = b->ticket;
   a.info = b->info;
   a.latched = b->status;
@@ -730,7 +1212,9 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
     if (a.sc.indices_out == out_indices) a.sc.indices_out = nullptr;
   }
   set_tree_window(b->tree->heap, (size_t)b->tree->leaves * 16);
-  if (global_batch <= 256)
+  if (by_warp)
+    B2R_CUDA(launch(per_sample_warp_kernel, dim3(tiles), dim3(threads), 0, s, a, cap));
+  else if (global_batch <= 256)
     B2R_CUDA(launch(per_sample_kernel<3, 256>, dim3(1), dim3(threads), 0, s, a));
   else if (ranges)
     B2R_CUDA(launch(per_sample_kernel<3, 256>, dim3(tiles), dim3(threads), 0, s, a));

@@ -152,6 +152,52 @@ __device__ __forceinline__ int64_t tree_descend_staged(
   return h - (((int64_t)1) << depth);
 }
 
+// Root-to-leaf descent by a whole WARP (sum_tree.py:126-141), up to 5 levels per
+// memory round trip and nothing staged.  A round below node h0 needs the left children
+// of 1 + 2 + 4 + 8 + 16 = 31 nodes: lane L fetches the one numbered L in breadth-first
+// order (ONE load instruction for the warp).  Then lane p takes the K-bit path p as a
+// hypothesis and replays the reference's K decisions along it — `q < left` goes left,
+// else `q -= left` (rounded, __dsub_rn) goes right — checking at every level that the
+// comparison agrees with its bit.  The decisions are deterministic, so exactly one lane
+// is consistent on all K levels: its path is the reference's, its residual the
+// reference's q.  The K subtractions of a lane depend on each other, the shuffles that
+// feed them do not: a round costs one L2 round trip plus ~K dependent fp64 operations,
+// against K dependent round trips for the textbook walk.  All lanes return the leaf.
+__device__ __forceinline__ int64_t tree_descend_warp(const double *__restrict__ heap,
+                                                     int depth, double q, int lane) {
+  const unsigned full = 0xffffffffu;
+  const int d_me = 32 - __clz(lane + 1);             // level below h0 of my candidate
+  const int prefix_me = lane + 1 - (1 << (d_me - 1));  // its position on that level
+  int64_t h = 1;
+  int level = 0;
+#pragma unroll 1
+  while (level < depth) {
+    const int K = depth - level < 5 ? depth - level : 5;
+    double c = 0.0;
+    if (d_me <= K) c = heap[(h << d_me) + 2 * prefix_me];
+    double r = q;
+    bool ok = lane < (1 << K);
+#pragma unroll
+    for (int d = 1; d <= 5; ++d) {
+      if (d <= K) {
+        const int pre = lane >> (K - d + 1);  // the first d - 1 decisions of path `lane`
+        const double left = __shfl_sync(full, c, ((1 << (d - 1)) - 1 + pre) & 31);
+        if ((lane >> (K - d)) & 1) {
+          ok = ok && !(r < left);
+          r = __dsub_rn(r, left);
+        } else {
+          ok = ok && (r < left);
+        }
+      }
+    }
+    const int w = __ffs(__ballot_sync(full, ok)) - 1;
+    h = (h << K) + w;
+    q = __shfl_sync(full, r, w);
+    level += K;
+  }
+  return h - (((int64_t)1) << depth);
+}
+
 // Cooperative copy of heap[0 .. 2^(min(depth, kTopLevels)+1)) into shared memory:
 // every thread issues all of its loads before the first store, so staging costs one
 // memory round trip (needs blockDim.x >= 128).

@@ -1,8 +1,10 @@
 """Import shim for the UNMODIFIED reference replay code (authoring container only).
 
-TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only `oracle/make_golden.py` and the
-`-m "not gpu"` tests may use this, and only when `/root/reference` exists (it
-does not exist on the GPU box).  It lets the reference's
+TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only `oracle/make_golden.py`, the
+`-m "not gpu"` tests and the CPU legs of `bench.py` (`--impl reference`,
+`cpu_baseline`) may use this.  `/root/reference` does not exist on the GPU box; there
+bench.py finds the copy of the three replay files that `make -C oracle _ref` made
+(oracle/Makefile), the tests skip.  It lets the reference's
 `dopamine/replay_memory/{sum_tree,circular_replay_buffer,prioritized_replay_buffer}.py`
 be imported without TensorFlow / gin installed, by registering stub modules:
 
@@ -29,7 +31,21 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get('DOPAMINE_REFERENCE_ROOT', '/root/reference')
+_TRAVELLING_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
+
+
+def _default_root():
+  """/root/reference in the authoring container; on the GPU box the byte-for-byte
+  copy of the three replay files that `make -C oracle _ref` made (git-ignored, shipped
+  by gpurun) — enough for load_reference(), not for load_reference_agents()."""
+  if os.path.isdir('/root/reference/dopamine/replay_memory'):
+    return '/root/reference'
+  if os.path.isdir(os.path.join(_TRAVELLING_COPY, 'dopamine', 'replay_memory')):
+    return _TRAVELLING_COPY
+  return '/root/reference'
+
+
+REFERENCE_ROOT = os.environ.get('DOPAMINE_REFERENCE_ROOT') or _default_root()
 
 
 def reference_available():
