@@ -82,14 +82,15 @@ TreeWindow &tree_window();
 void set_tree_window(void *base, size_t bytes);  // also reserves the L2 set-aside once
 
 template <typename... Params, typename... Args>
-cudaError_t launch_prio(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem,
-                        cudaStream_t stream, int priority, Args &&...args) {
+cudaError_t launch_prio_cluster(void (*kernel)(Params...), dim3 grid, dim3 block,
+                                size_t smem, cudaStream_t stream, int priority,
+                                int cluster_x, Args &&...args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[3];
+  cudaLaunchAttribute attr[4];
   int n = 0;
   const TreeWindow &w = tree_window();
   if (w.base != nullptr && priority != 0) {
@@ -111,9 +112,23 @@ cudaError_t launch_prio(void (*kernel)(Params...), dim3 grid, dim3 block, size_t
     attr[n].val.priority = priority;
     ++n;
   }
+  if (cluster_x > 1) {  // the whole grid as thread-block clusters of cluster_x CTAs
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
   cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
+template <typename... Params, typename... Args>
+cudaError_t launch_prio(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem,
+                        cudaStream_t stream, int priority, Args &&...args) {
+  return launch_prio_cluster(kernel, grid, block, smem, stream, priority, 1,
+                             static_cast<Args &&>(args)...);
 }
 
 // Chain kernels (everything but the frame copies) run at chain priority.
@@ -145,10 +160,18 @@ __device__ __forceinline__ void pdl_acquire() {
     if ((int)blockIdx.x == (blk) && threadIdx.x == 0)        \
       g_trace[i] = clock64();                                \
   } while (0)
+// mark from thread 0 of whichever CTA gets there (e.g. the last one to finish)
+#define B2R_MARK_ANY(i)                        \
+  do {                                         \
+    if (threadIdx.x == 0) g_trace[i] = clock64(); \
+  } while (0)
 #else
 #define B2R_TRACE_DECL
 #define B2R_MARK(i) \
   do {              \
+  } while (0)
+#define B2R_MARK_ANY(i) \
+  do {                  \
   } while (0)
 #define B2R_MARK_CTA(i, blk) \
   do {                       \
@@ -189,6 +212,29 @@ __device__ __forceinline__ double philox_uniform53(uint64_t seed, uint64_t offse
                 o);
   uint64_t a = o[0] >> 5, b = o[1] >> 6;  // 27 + 26 bits
   return (double)((a << 26) | b) * (1.0 / 9007199254740992.0);
+}
+
+// The same draw with the ten rounds unrolled and each 32 x 32 product taken once as a
+// 64-bit multiply: a dependent chain of ~20 instructions instead of ~140.  For kernels
+// where a lone warp waits on the draw (the warp sampler).
+__device__ __forceinline__ double philox_uniform53_fast(uint64_t seed, uint64_t offset,
+                                                        uint64_t n) {
+  uint32_t c0 = (uint32_t)n, c1 = (uint32_t)(n >> 32), c2 = (uint32_t)offset,
+           c3 = (uint32_t)(offset >> 32);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const uint64_t hi = c0 >> 5, lo = c1 >> 6;  // 27 + 26 bits
+  return (double)((hi << 26) | lo) * (1.0 / 9007199254740992.0);
 }
 
 }  // namespace b2r

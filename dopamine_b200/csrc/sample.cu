@@ -13,9 +13,13 @@
 // columns of the batch (gather.cuh) and exchange shard totals over peer memory.
 #include "gather.cuh"
 
+#include <cooperative_groups.h>
+
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
+
+namespace cg = cooperative_groups;
 
 namespace b2r {
 namespace {
@@ -63,6 +67,9 @@ struct PerSampleArgs {
   int shard_ranges;
   // Shard totals over peer memory instead of shard_totals (see exchange_totals).
   ExchangeArgs xchg;
+  // 1.0 / batch as IEEE double division gives it (np.linspace's step), computed on the
+  // host: an fp64 division is a ~500-cycle subroutine on the device.
+  double step;
 };
 
 __device__ __forceinline__ void st_sys_u64(uint64_t *p, uint64_t v) {
@@ -506,11 +513,12 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
 // The kernel above gives a stratum to a THREAD and stages tree levels 0..10 in shared
 // memory first (one DRAM/L2 round trip, 3.2 k cycles, before any descent starts), then
 // walks three levels per round trip.  Here a stratum belongs to a WARP
-// (tree_descend_warp: five levels per round trip, nothing staged), every per-row load
-// that follows the descent is issued together, and the only block-wide work left is the
-// in-order replacement of invalid picks by the last CTA to finish.  A batch of B strata
-// is B warps spread over B / warps-per-CTA CTAs, so the sampler's latency is that of ONE
-// descent whatever the batch: ~4 L2 round trips for a 1M-leaf tree.
+// (tree_descend_warp: five levels per round trip, nothing staged, the first round's
+// nodes fetched with the prologue), and the replacement draws for invalid picks are
+// evaluated SPECULATIVELY by extra warps of the same grid, so that the last CTA to
+// finish only has to match the j-th invalid slot with the j-th valid draw.  A batch of B
+// strata is B warps spread over B / warps-per-CTA CTAs: the sampler's latency is that of
+// ONE descent whatever the batch — three dependent L2 round trips for a 1M-leaf tree.
 //
 // The validity context (ValidCtx, 70 words) is read by the warp as 3 coalesced words
 // per lane and stays in registers: scalars come out by shuffle, `index in
@@ -576,28 +584,71 @@ static __device__ __noinline__ int64_t descend_from_root(const double *heap, int
   return tree_descend_staged<3>(heap, nullptr, 0, depth, q, zero);
 }
 
-// grid = ceil(strata / warps per CTA) CTAs (sharded: an estimate of this rank's share;
-// the warps stride over whatever the share turns out to be).  Scratch, all int32 words
-// of a.inv_slots: [0, cap) invalid flag of every output position, [cap, 2 cap) the
-// ordered list of invalid positions (built by the last CTA); a.tile_min: one minimum
-// per CTA.  a.tile_counts is unused.
-__global__ void __launch_bounds__(256)
-per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a, int scratch_cap) {
+constexpr int kSpecMax = 64;  // speculative replacement draws per launch
+
+// Scratch of the warp sampler (carved out of b2r_buffer::inv_slots by the host).
+struct WarpScratch {
+  uint8_t *inv_flag;    // [cap, padded to 16]: 1 = the stratified pick of this position
+                        // is invalid
+  int32_t *inv_list;    // [cap]: positions of the invalid picks in order (last CTA)
+  int32_t *spec_idx;    // [kSpecMax]: leaf of replacement draw r
+  int32_t *spec_valid;  // [kSpecMax]: 1 = that leaf is a valid transition
+  float *cta_min;       // [grid]: smallest sampling probability a CTA wrote
+  int cap;              // rows the caller's outputs hold
+  int spec;             // replacement draws evaluated up front (0: none)
+  int cluster;          // the grid is one thread-block cluster (host-side switch)
+};
+
+// grid = ceil((strata + spec) / warps per CTA) CTAs (sharded: an estimate of this rank's
+// share; the warps stride over whatever the share turns out to be).
+//
+// CLUSTER (batches of a few dozen strata, the agent's batch of 32): the whole grid is
+// ONE thread-block cluster.  Flags, speculative draws and minima go straight into the
+// shared memory of CTA 0 (distributed shared memory) and a cluster barrier replaces the
+// fence + atomic ticket + L2 round trip by which the last CTA of a plain grid finds out
+// that it is the last: ~0.6 k instead of ~3 k cycles on the critical path.
+constexpr int kClusterCap = 1024;  // output rows a clustered launch can flag in smem
+
+template <bool CLUSTER, typename T>
+__device__ __forceinline__ T ld_scratch(const T *p) {
+  if (CLUSTER) return *p;  // shared memory of this CTA
+  return __ldcg(p);
+}
+
+template <int MIN_CTAS, bool CLUSTER>
+__global__ void __launch_bounds__(256, MIN_CTAS)
+per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
+                       const __grid_constant__ WarpScratch ws_in) {
+  __shared__ __align__(16) uint8_t s_flag[CLUSTER ? kClusterCap : 16];
+  __shared__ int s_cl_spec_idx[kSpecMax], s_cl_spec_valid[kSpecMax];
+  __shared__ float s_cl_min[16];
+  WarpScratch ws = ws_in;
+  if (CLUSTER) {
+    // where everybody writes: CTA 0's arrays (generic addresses into its shared memory)
+    cg::cluster_group cluster = cg::this_cluster();
+    ws.inv_flag = cluster.map_shared_rank(s_flag, 0);
+    ws.spec_idx = cluster.map_shared_rank(s_cl_spec_idx, 0);
+    ws.spec_valid = cluster.map_shared_rank(s_cl_spec_valid, 0);
+    ws.cta_min = cluster.map_shared_rank(s_cl_min, 0);
+  }
   __shared__ double s_totals[kMaxShards];
   __shared__ int s_first[2];
   __shared__ float s_wmin[8];
   __shared__ int warp_counts[32];
   __shared__ float warp_mins[32];
-  __shared__ int s_wvalid[8];
+  __shared__ int s_draw_of[kSpecMax], s_spec_idx[kSpecMax];
   __shared__ int s_draws_used, s_last_idx, s_last_valid, s_is_last;
   __shared__ ValidCtx s_valid;  // thread-per-draw retry rounds only
 
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps = blockDim.x >> 5;
+  B2R_MARK(10);
   pdl_release();
   pdl_acquire();
-  // every load of the prologue is issued before the first one is used
+  B2R_MARK(11);
+  // every load of the prologue is issued before the first one is used; the nodes of
+  // the first descent round (levels 1..5 under the root) ride along
   WarpCtx ctx;
   warp_ctx_issue(a.valid_dev, lane, &ctx);
   const uint64_t draws_before = a.counter ? *a.counter : 0ull;
@@ -605,6 +656,7 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a, int scratch_cap)
   uint64_t xseq = 0;
   if (exchange) xseq = *a.xchg.seq + 1;
   const double local_total = a.heap[1];  // root of the 1-based heap
+  double c_top = warp_candidate(a.heap, 1, a.depth < 5 ? a.depth : 5, lane);
   const uint64_t draw_offset = a.offset + draws_before;
   if (exchange && blockIdx.x == 0)
     exchange_publish(a.xchg, a.num_shards, a.rank, local_total, xseq);
@@ -616,6 +668,7 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a, int scratch_cap)
     shard_totals = s_totals;
   }
   warp_ctx_finish(&ctx);
+  B2R_MARK(12);
   double grand_total = local_total;
   if (a.num_shards > 1) {
     grand_total = 0.0;
@@ -625,8 +678,9 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a, int scratch_cap)
   if (grand_total == 0.0 || (a.num_shards == 1 && local_total == 0.0)) {
     // sum_tree.py:159-160; every CTA takes this branch, the last to arrive closes
     if (threadIdx.x == 0 &&
-        (gridDim.x == 1 || atomicAdd(a.ticket, 1u) == gridDim.x - 1)) {
-      if (gridDim.x > 1) *a.ticket = 0u;
+        (CLUSTER ? blockIdx.x == 0
+                 : (gridDim.x == 1 || atomicAdd(a.ticket, 1u) == gridDim.x - 1))) {
+      if (!CLUSTER && gridDim.x > 1) *a.ticket = 0u;
       a.info[0] = B2R_ERR_EMPTY_TREE;
       a.info[1] = 0; a.info[2] = 0; a.info[3] = 0;
       if (a.count_out) *a.count_out = 0;
@@ -638,7 +692,7 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a, int scratch_cap)
     return;
   }
 
-  const double step = 1.0 / (double)a.batch;  // np.linspace(0, 1, batch + 1)
+  const double step = a.step;  // np.linspace(0, 1, batch + 1)
   auto stratum_owner = [&](int i, double u, double *residual) {
     double q01;
     if (a.use_philox) {
@@ -702,49 +756,85 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a, int scratch_cap)
     range_hi = base[1];
   }
   const int n_all = range_hi - range_lo;
-  // rows beyond the scratch / output capacity of a sharded step are dropped and latched
-  const int n_mine = n_all < scratch_cap ? n_all : scratch_cap;
-  int32_t *inv_flag = a.inv_slots;
-  int32_t *inv_list = a.inv_slots + scratch_cap;
+  // rows beyond the output capacity of a sharded step are dropped and latched
+  const int n_mine = n_all < ws.cap ? n_all : ws.cap;
   const bool fast_scalars = a.with_scalars && a.sc.fast;
   const bool want_min = a.with_scalars && a.min_prob_out != nullptr;
+  const int budget = a.max_attempts;
+  const int n_spec = ws.spec < budget ? ws.spec : budget;  // draws evaluated up front
+  const uint64_t retry_seed = a.seed + 0x9E3779B97F4A7C15ull * (uint64_t)(a.rank + 1);
+  auto retry_uniform = [&](int r) {
+    // Philox retry stream: rank-private (strata streams are shared by all ranks)
+    return (a.use_philox || a.retry_u01 == nullptr)
+               ? philox_uniform53_fast(retry_seed, draw_offset,
+                                       (uint64_t)a.batch + (uint64_t)r)
+               : a.retry_u01[r];
+  };
 
-  // ---- stratified pass (sum_tree.py:162-166 + prioritized_replay_buffer.py:155)
+  // ---- stratified pass (sum_tree.py:162-166 + prioritized_replay_buffer.py:155) and,
+  // by the warps behind it, the first n_spec replacement draws (sum_tree.py:123-124:
+  // query = random.random() * total), whether or not they will be needed
   float my_min = INFINITY;
+  bool first_item = true;
 #pragma unroll 1
-  for (int pos = blockIdx.x * warps + warp; pos < n_mine; pos += gridDim.x * warps) {
-    const int i = range_lo + pos;
-    const double u = a.use_philox ? philox_uniform53(a.seed, draw_offset, (uint64_t)i) : 0.0;
+  for (int pos = blockIdx.x * warps + warp; pos < n_mine + n_spec;
+       pos += gridDim.x * warps) {
+    const bool stratum = pos < n_mine;
     double mass;
-    stratum_owner(i, u, &mass);  // (inside the range the owner is this rank)
-    const int64_t idx = tree_descend_warp(a.heap, a.depth, mass, lane);
+    if (stratum) {
+      const int i = range_lo + pos;
+      const double u =
+          a.use_philox ? philox_uniform53_fast(a.seed, draw_offset, (uint64_t)i) : 0.0;
+      stratum_owner(i, u, &mass);  // (inside the range the owner is this rank)
+    } else {
+      mass = __dmul_rn(retry_uniform(pos - n_mine), local_total);
+    }
+    B2R_MARK(13);
+    if (!first_item) c_top = warp_candidate(a.heap, 1, a.depth < 5 ? a.depth : 5, lane);
+    first_item = false;
+    const int64_t idx = tree_descend_warp(a.heap, a.depth, mass, lane, c_top);
+    B2R_MARK(14);
     ScalarLoads row;
-    if (fast_scalars && lane == 0) load_scalars(a.sc, idx, &row);
+    if (stratum && fast_scalars && lane == 0) load_scalars(a.sc, idx, &row);
     const bool valid = warp_is_valid(ctx, idx, lane);
+    B2R_MARK(15);
     if (lane == 0) {
-      a.out_idx[pos] = (int32_t)idx;
-      if (a.out_slots) a.out_slots[pos] = i;
-      inv_flag[pos] = valid ? 0 : 1;
-      if (valid) {
-        float p = INFINITY;
-        if (fast_scalars) p = finish_scalars(a.sc, pos, idx, row);
-        else if (a.with_scalars) p = write_scalars(a.sc, pos, idx);
-        my_min = fminf(my_min, p);
+      if (stratum) {
+        a.out_idx[pos] = (int32_t)idx;
+        if (a.out_slots) a.out_slots[pos] = range_lo + pos;
+        ws.inv_flag[pos] = valid ? 0 : 1;
+        if (valid) {
+          float p = INFINITY;
+          if (fast_scalars) p = finish_scalars(a.sc, pos, idx, row);
+          else if (a.with_scalars) p = write_scalars(a.sc, pos, idx);
+          my_min = fminf(my_min, p);
+        }
+      } else {
+        ws.spec_idx[pos - n_mine] = (int32_t)idx;
+        ws.spec_valid[pos - n_mine] = valid ? 1 : 0;
       }
     }
   }
+  B2R_MARK(16);
   if (want_min) {
     if (lane == 0) s_wmin[warp] = my_min;
     __syncthreads();
     if (threadIdx.x == 0) {
       float m = s_wmin[0];
       for (int w = 1; w < warps; ++w) m = fminf(m, s_wmin[w]);
-      a.tile_min[blockIdx.x] = m;
+      ws.cta_min[blockIdx.x] = m;
     }
   }
 
-  // ---- only the last CTA to finish goes on
-  if (gridDim.x > 1) {
+  // ---- only the last CTA to finish goes on (CLUSTER: CTA 0, after the barrier)
+  if (CLUSTER) {
+    cg::this_cluster().sync();
+    if (blockIdx.x != 0) return;
+    ws.inv_flag = s_flag;
+    ws.spec_idx = s_cl_spec_idx;
+    ws.spec_valid = s_cl_spec_valid;
+    ws.cta_min = s_cl_min;
+  } else if (gridDim.x > 1) {
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_is_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
@@ -754,127 +844,153 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a, int scratch_cap)
   } else {
     __syncthreads();
   }
+  B2R_MARK_ANY(17);
   if (threadIdx.x == 0) {
     s_draws_used = 0;
     s_last_idx = -1;
     s_last_valid = 0;
-    if (gridDim.x > 1) *a.ticket = 0u;  // ready for the next launch
+    if (!CLUSTER && gridDim.x > 1) *a.ticket = 0u;  // ready for the next launch
   }
-  // ordered list of the invalid positions: thread t owns a contiguous run of flags
-  const int per = (n_mine + (int)blockDim.x - 1) / (int)blockDim.x;
-  const int f0 = min(n_mine, (int)threadIdx.x * per), f1 = min(n_mine, f0 + per);
-  int mine_inv = 0;
-  for (int p = f0; p < f1; ++p) mine_inv += __ldcg(inv_flag + p);
-  int inc = mine_inv;  // inclusive scan over the block
+  // Ordered list of the invalid positions (16 flag bytes per thread and round) and, in
+  // the same block scan, the order of the valid speculative draws: every load of this
+  // phase is issued before the first one is used.
+  float min_seen = INFINITY;
+  if (want_min)
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x)
+      min_seen = fminf(min_seen, ld_scratch<CLUSTER>(ws.cta_min + c));
+  const bool spec_mine = (int)threadIdx.x < n_spec;
+  const int spec_v = spec_mine ? ld_scratch<CLUSTER>(ws.spec_valid + threadIdx.x) : 0;
+  if (spec_mine) s_spec_idx[threadIdx.x] = ld_scratch<CLUSTER>(ws.spec_idx + threadIdx.x);
+  int num_invalid = 0, spec_good = 0;
+  for (int base = 0; base < n_mine || base == 0; base += 16 * (int)blockDim.x) {
+    const int p0 = base + 16 * (int)threadIdx.x;
+    uint32_t f[4] = {0, 0, 0, 0};
+    if (p0 < n_mine) {
+      const uint4 v = ld_scratch<CLUSTER>(reinterpret_cast<const uint4 *>(ws.inv_flag + p0));
+      f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(full, inc, o);
-    if (lane >= o) inc += v;
+      for (int k = 0; k < 4; ++k) {  // bytes at or beyond n_mine are stale
+        const int left = n_mine - (p0 + 4 * k);
+        f[k] &= left >= 4 ? 0x01010101u : (left <= 0 ? 0u : (0x01010101u >> (8 * (4 - left))));
+      }
+    }
+    const int mine_inv = __popc(f[0]) + __popc(f[1]) + __popc(f[2]) + __popc(f[3]);
+    const int mine_spec = base == 0 && spec_v == 1 ? 1 : 0;
+    const int mine_packed = mine_inv | (mine_spec << 20);  // two counts, one scan
+    int inc = mine_packed;  // inclusive scan over the block
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(full, inc, o);
+      if (lane >= o) inc += v;
+    }
+    __syncthreads();  // (warp_counts of the previous round has been read)
+    if (lane == 31) warp_counts[warp] = inc;
+    __syncthreads();
+    int before = inc - mine_packed, total = 0;
+    for (int w = 0; w < warps; ++w) {
+      const int cnt = warp_counts[w];
+      if (w < warp) before += cnt;
+      total += cnt;
+    }
+    int slot_at = num_invalid + (before & 0xfffff);
+    if (mine_inv > 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if ((f[k] >> (8 * b)) & 1u) ws.inv_list[slot_at++] = p0 + 4 * k + b;
+    }
+    if (mine_spec) s_draw_of[before >> 20] = threadIdx.x;
+    num_invalid += total & 0xfffff;
+    if (base == 0) spec_good = total >> 20;
   }
-  if (lane == 31) warp_counts[warp] = inc;
-  __syncthreads();
-  int before = inc - mine_inv, num_invalid = 0;
-  for (int w = 0; w < warps; ++w) {
-    const int cnt = warp_counts[w];
-    if (w < warp) before += cnt;
-    num_invalid += cnt;
-  }
-  if (mine_inv > 0)
-    for (int p = f0; p < f1; ++p)
-      if (__ldcg(inv_flag + p)) inv_list[before++] = p;
-  __syncthreads();  // inv_list (global) and the shared scalars are visible to the block
+  __syncthreads();  // inv_list (global), s_draw_of and the shared scalars are visible
+  B2R_MARK_ANY(18);
 
   // ---- in-order replacement of invalid slots (prioritized_replay_buffer.py:156-170):
-  // the j-th invalid slot takes the j-th valid draw out of a shared budget.  Windows of
-  // retry draws are evaluated speculatively in parallel — the first one warp per draw
-  // (a handful of invalid picks is the usual case), later ones a thread per draw.
+  // the j-th invalid slot takes the j-th valid draw out of a shared budget.
   int found = 0, drawn = 0;
   float fix_min = INFINITY;
-  const int budget = a.max_attempts;
-  const uint64_t retry_seed = a.seed + 0x9E3779B97F4A7C15ull * (uint64_t)(a.rank + 1);
-  auto retry_uniform = [&](int r) {
-    // Philox retry stream: rank-private (strata streams are shared by all ranks)
-    return (a.use_philox || a.retry_u01 == nullptr)
-               ? philox_uniform53(retry_seed, draw_offset, (uint64_t)a.batch + (uint64_t)r)
-               : a.retry_u01[r];
-  };
-  bool first_round = true;
-  while (num_invalid > 0 && found < num_invalid && drawn < budget) {
-    int round_valid;
-    if (first_round) {
-      const int r = drawn + warp;
-      const bool active = r < budget;
-      bool valid = false;
-      int64_t idx = 0;
-      ScalarLoads row;
-      if (active) {
-        // sum_tree.py:123-124: query = random.random() * total
-        idx = tree_descend_warp(a.heap, a.depth, __dmul_rn(retry_uniform(r), local_total),
-                                lane);
-        if (fast_scalars && lane == 0) load_scalars(a.sc, idx, &row);
-        valid = warp_is_valid(ctx, idx, lane);
+  if (num_invalid > 0 && budget > 0) {
+    int spec_done = n_spec;
+    if (spec_done == 0) {
+      // nothing was evaluated up front (single-CTA launches): one warp per draw, now
+      spec_done = warps < budget ? warps : budget;
+      if (warp < spec_done) {
+        const double c0 = warp_candidate(a.heap, 1, a.depth < 5 ? a.depth : 5, lane);
+        const int64_t idx = tree_descend_warp(
+            a.heap, a.depth, __dmul_rn(retry_uniform(warp), local_total), lane, c0);
+        const bool valid = warp_is_valid(ctx, idx, lane);
+        if (lane == 0) {
+          ws.spec_idx[warp] = (int32_t)idx;
+          ws.spec_valid[warp] = valid ? 1 : 0;
+        }
       }
-      if (lane == 0) s_wvalid[warp] = active && valid ? 1 : 0;
       __syncthreads();
-      int ord = found;
-      round_valid = 0;
-      for (int w = 0; w < warps; ++w) {
-        if (w < warp) ord += s_wvalid[w];
-        round_valid += s_wvalid[w];
+      const bool v = (int)threadIdx.x < spec_done && ws.spec_valid[threadIdx.x] == 1;
+      const int ord = block_scan_flag(v, warp_counts, &spec_good);
+      if (v) s_draw_of[ord] = threadIdx.x;
+      __syncthreads();
+    }
+    // draw r fills invalid slot number (valid draws before r)
+    const int fixed = num_invalid < spec_good ? num_invalid : spec_good;
+    for (int j = threadIdx.x; j < fixed; j += blockDim.x) {
+      const int r = s_draw_of[j];
+      const int idx = n_spec > 0 ? s_spec_idx[r] : ld_scratch<CLUSTER>(ws.spec_idx + r);
+      const int slot = ws.inv_list[j];
+      a.out_idx[slot] = idx;
+      if (fast_scalars) {  // one round trip for every input of the row
+        ScalarLoads row;
+        load_scalars(a.sc, idx, &row);
+        fix_min = fminf(fix_min, finish_scalars(a.sc, slot, idx, row));
+      } else if (a.with_scalars) {
+        fix_min = fminf(fix_min, write_scalars(a.sc, slot, idx));
       }
-      if (lane == 0 && active) {
-        if (valid && ord < num_invalid) {
-          const int slot = inv_list[ord];
-          a.out_idx[slot] = (int32_t)idx;
-          if (fast_scalars)
-            fix_min = fminf(fix_min, finish_scalars(a.sc, slot, idx, row));
-          else if (a.with_scalars)
-            fix_min = fminf(fix_min, write_scalars(a.sc, slot, idx));
-          if (ord == num_invalid - 1) s_draws_used = r + 1;
-        }
-        if (r == budget - 1) {
-          s_last_idx = (int)idx;
-          s_last_valid = valid ? 1 : 0;
-        }
-      }
-      drawn += warps;
-      first_round = false;
-      // the thread-per-draw rounds test validity against a shared-memory context
+      if (j == num_invalid - 1) s_draws_used = r + 1;
+    }
+    if (threadIdx.x == 0 && spec_done == budget) {
+      s_last_idx = ld_scratch<CLUSTER>(ws.spec_idx + budget - 1);
+      s_last_valid = ld_scratch<CLUSTER>(ws.spec_valid + budget - 1) == 1 ? 1 : 0;
+    }
+    found = fixed;
+    drawn = spec_done;
+    if (found < num_invalid && drawn < budget) {
+      // (rare) the speculative draws did not suffice: windows of blockDim draws, a
+      // thread per draw, validity against a shared-memory copy of the context
       for (int w = threadIdx.x; w < kCtxWords; w += blockDim.x)
         reinterpret_cast<uint64_t *>(&s_valid)[w] =
             reinterpret_cast<const uint64_t *>(a.valid_dev)[w];
-    } else {
+      __syncthreads();
+    }
+    while (found < num_invalid && drawn < budget) {
       const int r = drawn + threadIdx.x;
       const bool active = r < budget;
       bool valid = false;
       int64_t idx = 0;
-      ScalarLoads row;
       if (active) {
         idx = descend_from_root(a.heap, a.depth,
                                 __dmul_rn(retry_uniform(r), local_total), a.zero);
-        if (fast_scalars) load_scalars(a.sc, idx, &row);
         valid = is_valid_transition(s_valid, idx);
       }
-      const int ord = found + block_scan_flag(active && valid, warp_counts, &round_valid);
+      int tile_valid;
+      const int ord = found + block_scan_flag(active && valid, warp_counts, &tile_valid);
       if (active && valid && ord < num_invalid) {
-        const int slot = inv_list[ord];
+        const int slot = ws.inv_list[ord];
         a.out_idx[slot] = (int32_t)idx;
-        if (fast_scalars)
-          fix_min = fminf(fix_min, finish_scalars(a.sc, slot, idx, row));
-        else if (a.with_scalars)
-          fix_min = fminf(fix_min, write_scalars(a.sc, slot, idx));
+        if (a.with_scalars) fix_min = fminf(fix_min, write_scalars(a.sc, slot, idx));
         if (ord == num_invalid - 1) s_draws_used = r + 1;
       }
       if (active && r == budget - 1) {
         s_last_idx = (int)idx;
         s_last_valid = valid ? 1 : 0;
       }
+      found += tile_valid;
       drawn += blockDim.x;
+      __syncthreads();
     }
-    found += round_valid;
-    __syncthreads();
   }
   __syncthreads();
+  B2R_MARK_ANY(19);
   if (threadIdx.x == 0) {
     int status = B2R_OK, fail_slot = 0, used = 0;
     if (num_invalid > 0) {
@@ -883,7 +999,7 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a, int scratch_cap)
       } else {
         // Every one of the `budget` draws was consumed; `found` slots were fixed.
         used = budget;
-        const int next_slot = inv_list[found];  // first invalid slot still unresolved
+        const int next_slot = ws.inv_list[found];  // first invalid slot still unresolved
         if (budget == 0 || s_last_valid) {
           // budget already 0 when this slot is reached -> PRB:159-163
           status = B2R_ERR_SAMPLE_ATTEMPTS;
@@ -896,7 +1012,7 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a, int scratch_cap)
             fix_min = fminf(fix_min, write_scalars(a.sc, next_slot, s_last_idx));
           if (num_invalid > found + 1) {
             status = B2R_ERR_SAMPLE_ATTEMPTS;
-            fail_slot = inv_list[found + 1];
+            fail_slot = ws.inv_list[found + 1];
           }
         }
       }
@@ -919,12 +1035,10 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a, int scratch_cap)
     }
   }
   if (want_min) {
-    float m = fix_min;
-    for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x)
-      m = fminf(m, __ldcg(a.tile_min + c));
-    m = block_min(m, warp_mins);
+    const float m = block_min(fminf(min_seen, fix_min), warp_mins);
     if (threadIdx.x == 0) *a.min_prob_out = m;
   }
+  B2R_MARK_ANY(20);
 }
 
 struct UniformSampleArgs {
@@ -1053,19 +1167,62 @@ static int sampler_variant() {
   return v;
 }
 
-// Grid of the warp sampler for `strata` expected strata; scratch for `cap` rows.
-static int warp_sampler_setup(b2r_buffer *b, int strata, int cap, PerSampleArgs *a,
+// Grid and scratch of the warp sampler for `strata` expected strata and outputs of
+// `cap` rows.
+static int warp_sampler_setup(b2r_buffer *b, int strata, int cap, WarpScratch *ws,
                               int *threads, int *ctas) {
-  const int warps = strata <= 64 ? 4 : 8;
+  static const bool use_cluster = [] {
+    const char *e = std::getenv("B2R_SAMPLER_CLUSTER");
+    return e == nullptr || std::atoi(e) != 0;
+  }();
+  int warps = strata <= 64 ? 4 : 8;
+  // replacement draws evaluated up front: a pick is invalid with probability ~0.3 % in
+  // an Atari-like memory (a terminal among the three frames before it)
+  int spec = strata / 64;
+  if (spec < 4) spec = 4;
+  if (spec > kSpecMax) spec = kSpecMax;
+  ws->cluster = 0;
+  if (use_cluster && strata + 4 <= 64 && cap <= kClusterCap) {
+    // one cluster of 8 CTAs; the warps left over after the strata draw replacements
+    ws->cluster = 1;
+    *ctas = 8;
+    warps = (strata + 4 + 7) / 8;
+    spec = 8 * warps - strata;
+  } else {
+    *ctas = (strata + spec + warps - 1) / warps;
+    if (*ctas > 8192) *ctas = 8192;  // the warps stride
+  }
   *threads = warps * 32;
-  *ctas = (strata + warps - 1) / warps;
-  if (*ctas < 1) *ctas = 1;
-  if (*ctas > 8192) *ctas = 8192;  // the warps stride
-  B2R_TRY(ensure_inv_slots(b, 2 * (int64_t)cap + *ctas + 8));
-  a->inv_slots = b->inv_slots;
-  a->tile_counts = nullptr;
-  a->tile_min = reinterpret_cast<float *>(b->inv_slots + 2 * (int64_t)cap);
+  const int64_t flag_words = ((int64_t)cap + 15) / 16 * 4;
+  B2R_TRY(ensure_inv_slots(b, flag_words + cap + 2 * kSpecMax + *ctas + 16));
+  ws->inv_flag = reinterpret_cast<uint8_t *>(b->inv_slots);
+  ws->inv_list = b->inv_slots + flag_words;
+  ws->spec_idx = ws->inv_list + cap;
+  ws->spec_valid = ws->spec_idx + kSpecMax;
+  ws->cta_min = reinterpret_cast<float *>(ws->spec_valid + kSpecMax);
+  ws->cap = cap;
+  ws->spec = spec;
   return B2R_OK;
+}
+
+// Two register budgets: 126 registers (no spills, 16 warps per SM) while every warp of
+// the launch is resident anyway; 64 registers (a few spills outside the descent, 32 warps
+// per SM) for the batches that would otherwise need a second wave.
+// B2R_SAMPLER_WAVE_CTAS overrides the switch point.
+static cudaError_t launch_warp_sampler(int ctas, int threads, cudaStream_t stream,
+                                       const PerSampleArgs &a, const WarpScratch &ws) {
+  static const int wave_ctas = [] {
+    const char *e = std::getenv("B2R_SAMPLER_WAVE_CTAS");
+    return e ? std::atoi(e) : 296;
+  }();
+  if (ws.cluster)
+    return launch_prio_cluster(per_sample_warp_kernel<2, true>, dim3(ctas), dim3(threads),
+                               0, stream, chain_priority(), ctas, a, ws);
+  if (ctas > wave_ctas)
+    return launch(per_sample_warp_kernel<4, false>, dim3(ctas), dim3(threads), 0, stream,
+                  a, ws);
+  return launch(per_sample_warp_kernel<2, false>, dim3(ctas), dim3(threads), 0, stream, a,
+                ws);
 }
 
 int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
@@ -1079,8 +1236,9 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
     return fail(B2R_ERR_UNSUPPORTED, "batch above %d is not supported", kMaxTiles * 128);
   const bool by_warp = sampler_variant() == 1;
   PerSampleArgs a;
+  WarpScratch ws;
   if (by_warp)
-    B2R_TRY(warp_sampler_setup(b, batch, batch, &a, &threads, &tiles));
+    B2R_TRY(warp_sampler_setup(b, batch, batch, &ws, &threads, &tiles));
   else
     B2R_TRY(ensure_inv_slots(b, (int64_t)tiles * threads + 2 * kMaxTiles + 8));
   a.heap = b->tree->heap;
@@ -1088,6 +1246,7 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   B2R_TRY(ensure_ctx(b, stream));
   a.valid_dev = b->ctx_dev;
   a.batch = batch;
+  a.step = 1.0 / (double)batch;
   a.max_attempts = philox ? b->cfg.max_sample_attempts : n_retry;
   a.use_philox = philox ? 1 : 0;
   a.seed = seed;
@@ -1120,8 +1279,10 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   }
   set_tree_window(b->tree->heap, (size_t)b->tree->leaves * 16);
   if (by_warp) {
-    B2R_CUDA(launch(per_sample_warp_kernel, dim3(tiles), dim3(threads), 0, stream, a,
-                    (int)batch));
+    a.inv_slots = nullptr;
+    a.tile_counts = nullptr;
+    a.tile_min = nullptr;
+    B2R_CUDA(launch_warp_sampler(tiles, threads, stream, a, ws));
     B2R_LAUNCHED();
     return B2R_OK;
   }
@@ -1164,13 +1325,17 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
   int tiles = (global_batch + threads - 1) / threads;
   if (tiles > kMaxTiles) return fail(B2R_ERR_UNSUPPORTED, "global batch too large");
   PerSampleArgs a;
+  WarpScratch ws;
   const int cap = max_rows > 0 && max_rows < global_batch ? max_rows : global_batch;
   if (by_warp) {
     // grid for the expected share plus a margin; the warps stride over the rest
     int expect = num_shards > 1 ? global_batch / num_shards + global_batch / (4 * num_shards) + 8
                                 : global_batch;
     if (expect > cap) expect = cap;
-    B2R_TRY(warp_sampler_setup(b, expect, cap, &a, &threads, &tiles));
+    B2R_TRY(warp_sampler_setup(b, expect, cap, &ws, &threads, &tiles));
+    a.inv_slots = nullptr;
+    a.tile_counts = nullptr;
+    a.tile_min = nullptr;
   } else {
     B2R_TRY(ensure_inv_slots(b, (int64_t)tiles * threads + 2 * kMaxTiles + 8));
     a.inv_slots = b->inv_slots;
@@ -1182,6 +1347,7 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
   B2R_TRY(ensure_ctx(b, s));
   a.valid_dev = b->ctx_dev;
   a.batch = global_batch;
+  a.step = 1.0 / (double)global_batch;
   a.max_attempts = n_retry;
   a.use_philox = (query01 == nullptr) ? 1 : 0;
   a.seed = seed;
@@ -1213,7 +1379,7 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
   }
   set_tree_window(b->tree->heap, (size_t)b->tree->leaves * 16);
   if (by_warp)
-    B2R_CUDA(launch(per_sample_warp_kernel, dim3(tiles), dim3(threads), 0, s, a, cap));
+    B2R_CUDA(launch_warp_sampler(tiles, threads, s, a, ws));
   else if (global_batch <= 256)
     B2R_CUDA(launch(per_sample_kernel<3, 256>, dim3(1), dim3(threads), 0, s, a));
   else if (ranges)

@@ -163,22 +163,42 @@ __device__ __forceinline__ int64_t tree_descend_staged(
 // reference's q.  The K subtractions of a lane depend on each other, the shuffles that
 // feed them do not: a round costs one L2 round trip plus ~K dependent fp64 operations,
 // against K dependent round trips for the textbook walk.  All lanes return the leaf.
-__device__ __forceinline__ int64_t tree_descend_warp(const double *__restrict__ heap,
-                                                     int depth, double q, int lane) {
-  const unsigned full = 0xffffffffu;
-  const int d_me = 32 - __clz(lane + 1);             // level below h0 of my candidate
+// warp_candidate: the node lane `lane` fetches for a round of K levels below h.
+__device__ __forceinline__ double warp_candidate(const double *__restrict__ heap,
+                                                 int64_t h, int K, int lane) {
+  const int d_me = 32 - __clz(lane + 1);               // level below h of my candidate
   const int prefix_me = lane + 1 - (1 << (d_me - 1));  // its position on that level
-  int64_t h = 1;
-  int level = 0;
-#pragma unroll 1
-  while (level < depth) {
-    const int K = depth - level < 5 ? depth - level : 5;
-    double c = 0.0;
-    if (d_me <= K) c = heap[(h << d_me) + 2 * prefix_me];
-    double r = q;
-    bool ok = lane < (1 << K);
+  return d_me <= K ? heap[(h << d_me) + 2 * prefix_me] : 0.0;
+}
+
+// One round: K levels walked from (h, q) over the candidates `c` of warp_candidate.
+__device__ __forceinline__ void warp_walk(double c, int K, int lane, int64_t &h,
+                                          double &q) {
+  const unsigned full = 0xffffffffu;
+  double r = q;
+  bool ok;
+  if (K == 5) {  // the usual round: sources and bits are per-lane constants
+    ok = true;
+    const double l1 = __shfl_sync(full, c, 0);
+    const double l2 = __shfl_sync(full, c, 1 + (lane >> 4));
+    const double l3 = __shfl_sync(full, c, 3 + (lane >> 3));
+    const double l4 = __shfl_sync(full, c, 7 + (lane >> 2));
+    const double l5 = __shfl_sync(full, c, 15 + (lane >> 1));
+    const double left[5] = {l1, l2, l3, l4, l5};
 #pragma unroll
-    for (int d = 1; d <= 5; ++d) {
+    for (int d = 0; d < 5; ++d) {
+      const bool lt = r < left[d];
+      if ((lane >> (4 - d)) & 1) {
+        ok = ok && !lt;
+        r = __dsub_rn(r, left[d]);
+      } else {
+        ok = ok && lt;
+      }
+    }
+  } else {
+    ok = lane < (1 << K);
+#pragma unroll
+    for (int d = 1; d <= 4; ++d) {
       if (d <= K) {
         const int pre = lane >> (K - d + 1);  // the first d - 1 decisions of path `lane`
         const double left = __shfl_sync(full, c, ((1 << (d - 1)) - 1 + pre) & 31);
@@ -190,10 +210,27 @@ __device__ __forceinline__ int64_t tree_descend_warp(const double *__restrict__ 
         }
       }
     }
-    const int w = __ffs(__ballot_sync(full, ok)) - 1;
-    h = (h << K) + w;
-    q = __shfl_sync(full, r, w);
+  }
+  const int w = __ffs(__ballot_sync(full, ok)) - 1;
+  h = (h << K) + w;
+  q = __shfl_sync(full, r, w);
+}
+
+// c_first: warp_candidate(heap, 1, min(depth, 5), lane), fetched by the caller ahead of
+// time (it does not depend on q).
+__device__ __forceinline__ int64_t tree_descend_warp(const double *__restrict__ heap,
+                                                     int depth, double q, int lane,
+                                                     double c_first) {
+  int64_t h = 1;
+  int level = 0;
+  double c = c_first;
+#pragma unroll 1
+  while (true) {
+    const int K = depth - level < 5 ? depth - level : 5;
+    warp_walk(c, K, lane, h, q);
     level += K;
+    if (level >= depth) break;
+    c = warp_candidate(heap, h, depth - level < 5 ? depth - level : 5, lane);
   }
   return h - (((int64_t)1) << depth);
 }
