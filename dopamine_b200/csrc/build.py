@@ -66,7 +66,11 @@ def build(force=False, verbose=False, extra_flags=(), trace=False):
   obj_dir = os.path.join(HERE, '_obj_trace' if trace else '_obj')
   lib_path = TRACE_LIB if trace else LIB
   if trace:
+    # clock64 phase marks; B2R_TRACE_GT=1 in the environment: %globaltimer marks
+    # (one timeline for all kernels of the step)
     extra_flags = tuple(extra_flags) + ('-DB2R_TRACE',)
+    if os.environ.get('B2R_TRACE_GT'):
+      extra_flags += ('-DB2R_TRACE_GT',)
   os.makedirs(obj_dir, exist_ok=True)
   headers = [h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS]
   objects = []

@@ -376,6 +376,7 @@ c51_loss_kernel(LossArgs a) {
   }
 
   B2R_MARK(7);
+  B2R_MARK_END(8);
   // ---- mean weighted loss: the last CTA to finish reduces in a fixed order.
   if (a.u.mean_weighted_loss == nullptr) return;
   __threadfence();
@@ -444,8 +445,10 @@ c51_loss_rows_kernel(LossArgs a) {
   const int grp = lane / G, l = lane % G;
   const int N = NC ? NC : a.u.num_atoms, A = a.u.num_actions;
   const float *__restrict__ z = a.u.support;
+  B2R_MARK(10);
   pdl_release();
   pdl_acquire();
+  B2R_MARK(11);
   const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
   if ((int)blockIdx.x * kRowWarps >= rows) return;  // (no mean loss with batch_count)
   const int b = blockIdx.x * kRowWarps + warp;
@@ -665,6 +668,7 @@ c51_loss_rows_kernel(LossArgs a) {
     }
   }
 
+  B2R_MARK_END(12);
   // ---- mean weighted loss: the last CTA to finish reduces in a fixed order.
   if (a.u.mean_weighted_loss == nullptr) return;
   __threadfence();

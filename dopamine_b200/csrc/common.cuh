@@ -148,22 +148,40 @@ __device__ __forceinline__ void pdl_acquire() {
 
 // ---- optional phase tracing (build with -DB2R_TRACE; never in the shipped .so) ---
 #ifdef B2R_TRACE
+// -DB2R_TRACE_GT: marks are %globaltimer nanoseconds (one clock for all kernels and
+// SMs: a timeline of the whole step); otherwise clock64 cycles of the marking SM.
+#ifdef B2R_TRACE_GT
+__device__ __forceinline__ long long b2r_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return (long long)t;
+}
+#else
+__device__ __forceinline__ long long b2r_now() { return clock64(); }
+#endif
 #define B2R_TRACE_DECL static __device__ long long g_trace[32];
 #define B2R_MARK(i)                                              \
   do {                                                           \
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)  \
-      g_trace[i] = clock64();                                    \
+      g_trace[i] = b2r_now();                                    \
   } while (0)
 // mark from thread 0 of a chosen CTA (blockIdx.x == blk)
 #define B2R_MARK_CTA(i, blk)                                 \
   do {                                                       \
     if ((int)blockIdx.x == (blk) && threadIdx.x == 0)        \
-      g_trace[i] = clock64();                                \
+      g_trace[i] = b2r_now();                                \
   } while (0)
 // mark from thread 0 of whichever CTA gets there (e.g. the last one to finish)
 #define B2R_MARK_ANY(i)                        \
   do {                                         \
-    if (threadIdx.x == 0) g_trace[i] = clock64(); \
+    if (threadIdx.x == 0) g_trace[i] = b2r_now(); \
+  } while (0)
+// the latest time any CTA passed here
+#define B2R_MARK_END(i)                                                         \
+  do {                                                                          \
+    if (threadIdx.x == 0)                                                       \
+      atomicMax(reinterpret_cast<unsigned long long *>(&g_trace[i]),            \
+                (unsigned long long)b2r_now());                                 \
   } while (0)
 #else
 #define B2R_TRACE_DECL
@@ -171,6 +189,9 @@ __device__ __forceinline__ void pdl_acquire() {
   do {              \
   } while (0)
 #define B2R_MARK_ANY(i) \
+  do {                  \
+  } while (0)
+#define B2R_MARK_END(i) \
   do {                  \
   } while (0)
 #define B2R_MARK_CTA(i, blk) \

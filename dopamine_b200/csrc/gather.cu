@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(128, 12) gather_stack4_u8_kernel(const __grid_
   if (a.state) store_stack16(a.state + out_off, s0, s1, s2, s3);
   if (a.next_state) store_stack16(a.next_state + out_off, n0, n1, n2, n3);
   B2R_MARK(5);
+  B2R_MARK_END(6);
 }
 
 // ---- TMA variant of the fast path ------------------------------------------------

@@ -383,6 +383,12 @@ int b2r_create(const b2r_config *cfg, b2r_buffer **out) {
   B2R_CUDA(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
   B2R_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
   B2R_CUDA(cudaEventCreateWithFlags(&b->ev_join, cudaEventDisableTiming));
+  {
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    B2R_CUDA(cudaStreamCreateWithPriority(&b->side2, cudaStreamNonBlocking, greatest));
+  }
+  B2R_CUDA(cudaEventCreateWithFlags(&b->ev_join2, cudaEventDisableTiming));
   B2R_CUDA(cudaEventCreateWithFlags(&b->ev_pre, cudaEventDisableTiming));
   B2R_CUDA(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming));
   B2R_CUDA(cudaEventCreateWithFlags(&b->ev_rows, cudaEventDisableTiming));
@@ -413,6 +419,8 @@ int b2r_destroy(b2r_buffer *b) {
   if (b->side) cudaStreamDestroy(b->side);
   if (b->ev_fork) cudaEventDestroy(b->ev_fork);
   if (b->ev_join) cudaEventDestroy(b->ev_join);
+  if (b->side2) cudaStreamDestroy(b->side2);
+  if (b->ev_join2) cudaEventDestroy(b->ev_join2);
   if (b->ev_pre) cudaEventDestroy(b->ev_pre);
   if (b->ev_h2d) cudaEventDestroy(b->ev_h2d);
   if (b->ev_rows) cudaEventDestroy(b->ev_rows);

@@ -191,6 +191,10 @@ struct b2r_buffer {
   // fused step: the frame copies run on `side`, forked/joined with these events
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // ... and the write-back's grouping pass (needs the indices only) on `side2`, beside
+  // the loss kernel
+  cudaStream_t side2 = nullptr;
+  cudaEvent_t ev_join2 = nullptr;
   cudaEvent_t ev_pre = nullptr, ev_h2d = nullptr, ev_rows = nullptr;  // split flush
   float *min_prob = nullptr;    // device: min sampling probability of the last batch
   // Device copy of the validity context (add_count, cursor, invalid_range): the

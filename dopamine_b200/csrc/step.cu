@@ -95,8 +95,20 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
                           out->indices, b->info, s, out, b->min_prob));
   g_host_trace.lap(3);
   const bool frames = out->state != nullptr || out->next_state != nullptr;
+  // The write-back groups the batch by tree node on every level — which needs the
+  // sampled indices, not the new priorities: that half runs on a second forked stream
+  // while the loss kernel works, and the write-back proper only applies the values.
+  const int64_t expected_rows =
+      shard ? (batch + shard->exchange->world - 1) / shard->exchange->world : -1;
+  const bool presort = tree_can_presort(batch, expected_rows);
+  if (frames || presort) B2R_CUDA(cudaEventRecord(b->ev_fork, s));
+  if (presort) {
+    B2R_CUDA(cudaStreamWaitEvent(b->side2, b->ev_fork, 0));
+    B2R_TRY((tree_apply<int32_t, float>(b->tree, batch, out->indices, nullptr, nullptr,
+                                        b->side2, count, expected_rows, 1)));
+    B2R_CUDA(cudaEventRecord(b->ev_join2, b->side2));
+  }
   if (frames) {
-    B2R_CUDA(cudaEventRecord(b->ev_fork, s));
     B2R_CUDA(cudaStreamWaitEvent(b->side, b->ev_fork, 0));
     B2R_TRY(launch_gather(b, batch, out->indices, out, b->side, count, true));
     B2R_CUDA(cudaEventRecord(b->ev_join, b->side));
@@ -118,9 +130,9 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   B2R_TRY(b2r_c51_loss(&loss, s));
   if (loss_done) B2R_CUDA(cudaEventRecord(loss_done, s));
   g_host_trace.lap(5);
-  B2R_TRY((tree_apply<int32_t, float>(
-      b->tree, batch, out->indices, loss.priorities, nullptr, s, count,
-      shard ? (batch + shard->exchange->world - 1) / shard->exchange->world : -1)));
+  if (presort) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join2, 0));
+  B2R_TRY((tree_apply<int32_t, float>(b->tree, batch, out->indices, loss.priorities,
+                                      nullptr, s, count, expected_rows, presort ? 2 : 0)));
   if (frames) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join, 0));
   g_host_trace.lap(6);
   return B2R_OK;

@@ -51,7 +51,19 @@ struct UpdateArgs {
   // internal levels whose average chain (n >> level) is at least this long run their
   // ordered add-chains as a verified scan (chains_by_verified_scan); 0 = never
   int scan_min_chain = 0;
+  // Two-launch form of the cooperative kernel (the fused step): grouping the entries by
+  // node needs the INDICES only, so it can run while the loss kernel is still producing
+  // the values.  kPresort: every level CTA sorts and leaves (node, entry) in `sorted`
+  // ([level][node | entry][chunk] words), nothing else.  kApply: the level CTAs read
+  // those lists instead of sorting — unless an entry must not be applied (negative value,
+  // index out of range), in which case the lists are ignored and the kernel sorts the
+  // applied prefix itself, as kFull always does.
+  int phase = 0;
+  uint32_t *sorted = nullptr;
+  // role ticket, barrier flag, barrier arrivals (see tree_update_kernel)
+  unsigned int *sync_words = nullptr;
 };
+constexpr int kFull = 0, kPresort = 1, kApply = 2;
 
 // Add-path batches may ask for "whatever max_recorded_priority is when this entry
 // is applied" (mode[k] != 0, rainbow_agent.py:330-334).  Sequentially that is
@@ -401,8 +413,18 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
   __shared__ int s_stop_code;
   __shared__ double s_max[32];
 
-  cg::grid_group grid = cg::this_grid();
-  const int level = blockIdx.x;
+  // Levels are handed out in order of arrival, the leaf level first: the other CTAs
+  // wait for its deltas at a flag (below), so the CTA they wait for is always one that
+  // is already running — no cooperative launch, which would keep this kernel from
+  // sharing the GPU with the frame copies of the same step (a cooperative grid starts
+  // only once every CTA of it can be resident).
+  __shared__ int s_role;
+  B2R_MARK(a.phase == kPresort ? 12 : 13);
+  pdl_release();
+  pdl_acquire();
+  if (threadIdx.x == 0) s_role = (int)atomicInc(a.sync_words, (unsigned)a.depth);
+  __syncthreads();
+  const int level = s_role == 0 ? a.depth : s_role - 1;
   const bool is_leaf = level == a.depth;
   B2R_MARK_CTA(0, 0);
   B2R_MARK_CTA(16, a.depth);
@@ -418,6 +440,26 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
   // A chunk beyond the device-side count (sharded replay: the host launches for the
   // largest possible count) has nothing to do; every CTA sees the same n.
   if (n <= 0) return;
+  if (a.phase == kPresort) {
+    // group the n entries by their node on this level and leave the lists in HBM
+    uint32_t key[kBigItems], val[kBigItems];
+    const int shift0 = a.depth - level;
+#pragma unroll
+    for (int j = 0; j < kBigItems; ++j) {
+      const int k = threadIdx.x * kBigItems + j;
+      key[j] = k < n ? (uint32_t)((int64_t)a.indices[k] >> shift0) : 0xffffffffu;
+      val[j] = (uint32_t)k;
+    }
+    if (level != 0) BigSort(sm.g.sort).Sort(key, val, 0, level);
+    uint32_t *dst = a.sorted + (size_t)level * 2 * C::kChunk;
+#pragma unroll
+    for (int j = 0; j < kBigItems; ++j) {  // thread-contiguous: 16-byte stores
+      dst[threadIdx.x * kBigItems + j] = key[j];
+      dst[C::kChunk + threadIdx.x * kBigItems + j] = val[j];
+    }
+    B2R_MARK_END(14);
+    return;
+  }
   if (threadIdx.x == 0) {
     s_stop = n;
     s_stop_code = 0;
@@ -431,11 +473,22 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
     // running maximum in order.  These batches are tiny; one thread walks them.
     stage_mode_values(a, n, vals, &s_stop, &s_stop_code);
   } else {
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-      const double v = (double)a.values[k];
-      const int64_t idx = (int64_t)a.indices[k];
-      vals[k] = v;
-      if (v < 0.0 || idx < 0 || idx >= a.leaves) atomicMin(&s_stop, k);
+    // (every load of a thread is in flight before the first is used: one round trip)
+    double v[kBigItems];
+    int64_t ix[kBigItems];
+#pragma unroll
+    for (int j = 0; j < kBigItems; ++j) {
+      const int k = threadIdx.x + j * C::kThreads;
+      v[j] = k < n ? (double)a.values[k] : 0.0;
+      ix[j] = k < n ? (int64_t)a.indices[k] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < kBigItems; ++j) {
+      const int k = threadIdx.x + j * C::kThreads;
+      if (k < n) {
+        vals[k] = v[j];
+        if (v[j] < 0.0 || ix[j] < 0 || ix[j] >= a.leaves) atomicMin(&s_stop, k);
+      }
     }
   }
   __syncthreads();
@@ -449,6 +502,8 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
   B2R_MARK_CTA(23, a.depth - 1);
   B2R_MARK_CTA(29, 0);
   bool leaf_done = false;
+  // kApply: the presorted lists hold all n entries; they serve iff all n are applied
+  const bool presorted = a.phase == kApply && n_eff == n;
   if (is_leaf) {
     // max_recorded_priority = max(value, current) over the applied prefix
     // (before vals[] turns into deltas).
@@ -458,14 +513,22 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
     for (int off = 16; off > 0; off >>= 1)
       local_max = fmax(local_max, __shfl_xor_sync(0xffffffffu, local_max, off));
     if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = local_max;
-    leaf_done = leaf_deltas_hashed<C>(a, n_eff, sm.h, vals);
+    if (!presorted) leaf_done = leaf_deltas_hashed<C>(a, n_eff, sm.h, vals);
     __syncthreads();
   }
 
   // 3. group by node: thread t holds entries 4t .. 4t+3 (batch order); pads carry
   //    all-ones keys and sit behind every real entry, so they stay last.
   const int shift = a.depth - level;
-  if (!leaf_done) {
+  if (presorted) {
+    const uint32_t *src = a.sorted + (size_t)level * 2 * C::kChunk;
+#pragma unroll
+    for (int j = 0; j < kBigItems; ++j) {
+      sm.g.node[threadIdx.x * kBigItems + j] = __ldcg(src + threadIdx.x * kBigItems + j);
+      sm.g.elem[threadIdx.x * kBigItems + j] =
+          __ldcg(src + C::kChunk + threadIdx.x * kBigItems + j);
+    }
+  } else if (!leaf_done) {
     uint32_t key[kBigItems], val[kBigItems];
 #pragma unroll
     for (int j = 0; j < kBigItems; ++j) {
@@ -487,10 +550,21 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
     if (!leaf_done) {
       // many duplicates: one thread per distinct leaf walks its chain in batch order
       //   delta = value - leaf; leaf += delta   (sum_tree.py:196-202, last level).
-      for (int p = threadIdx.x; p < n_eff; p += blockDim.x) {
+      // (the leaves of a thread's group heads are fetched together)
+      double leaf0[kBigItems];
+      bool head[kBigItems];
+#pragma unroll
+      for (int j = 0; j < kBigItems; ++j) {
+        const int p = threadIdx.x + j * C::kThreads;
+        head[j] = p < n_eff && (p == 0 || sm.g.node[p - 1] != sm.g.node[p]);
+        leaf0[j] = head[j] ? a.heap[a.leaves + sm.g.node[p]] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < kBigItems; ++j) {
+        if (!head[j]) continue;
+        const int p = threadIdx.x + j * C::kThreads;
         const uint32_t node = sm.g.node[p];
-        if (p > 0 && sm.g.node[p - 1] == node) continue;
-        double leaf = a.heap[a.leaves + node];
+        double leaf = leaf0[j];
         for (int q = p; q < n_eff && sm.g.node[q] == node; ++q) {
           const uint32_t k = sm.g.elem[q];
           const double d = __dsub_rn(vals[k], leaf);
@@ -522,7 +596,46 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
   B2R_MARK_CTA(1, 0);
   B2R_MARK_CTA(19, a.depth);
   B2R_MARK_CTA(24, a.depth - 1);
-  grid.sync();
+  // ---- one-way barrier: the leaf CTA's deltas (and leaf writes) are published
+  // A failure is latched by the LAST level to pass (every CTA has read the latch by
+  // then: CTAs start whenever an SM has room, and one that started after the latch was
+  // set would skip the launch — and the barrier).
+  long long *pending = reinterpret_cast<long long *>(a.sync_words + 4);
+  if (is_leaf) {
+    if (threadIdx.x == 0) {
+      pending[0] = n_eff < n ? s_stop_code : 0;
+      pending[1] = a.k_base + n_eff;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.sync_words + 1), "r"(1u)
+                   : "memory");
+    }
+    B2R_MARK_ANY(10);
+  } else {
+    if (threadIdx.x == 0) {
+      unsigned seen = 0;
+      const long long t0 = clock64();
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
+                     : "=r"(seen)
+                     : "l"(a.sync_words + 1)
+                     : "memory");
+      } while (seen == 0 && clock64() - t0 < 4000000000ll);  // (2 s: never hang the GPU)
+      if (seen == 0 && a.status[0] == 0) a.status[0] = B2R_ERR_CUDA;
+      // the last level to leave re-arms the flag for the next launch
+      if (atomicInc(a.sync_words + 2, (unsigned)a.depth - 1) == (unsigned)a.depth - 1) {
+        a.sync_words[1] = 0u;
+        if (pending[0] != 0 && a.status[0] == 0) {
+          a.status[0] = pending[0];
+          a.status[1] = pending[1];
+        }
+      }
+    }
+    __syncthreads();
+    B2R_MARK_END(11);
+  }
   B2R_MARK_CTA(2, 0);
   B2R_MARK_CTA(25, a.depth - 1);
   B2R_MARK_CTA(28, a.depth);
@@ -533,18 +646,30 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
       for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w)
         if (s_max[w] > m) m = s_max[w];
       if (n_eff > 0) *a.max_rec = m;
-      if (n_eff < n) {
+      if (n_eff < n && a.depth == 0) {  // (a one-node tree has no other level to latch)
         a.status[0] = s_stop_code;
         a.status[1] = a.k_base + n_eff;
       }
     }
+    B2R_MARK_END(15);
     return;
   }
 
   // 3. internal level: deltas in group order, then one ordered chain per node.
   double *sorted_delta = vals;
-  for (int p = threadIdx.x; p < n_eff; p += blockDim.x)
-    sorted_delta[p] = a.delta[sm.g.elem[p]];
+  {
+    double d[kBigItems];
+#pragma unroll
+    for (int j = 0; j < kBigItems; ++j) {
+      const int p = threadIdx.x + j * C::kThreads;
+      d[j] = p < n_eff ? __ldcg(a.delta + sm.g.elem[p]) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < kBigItems; ++j) {
+      const int p = threadIdx.x + j * C::kThreads;
+      if (p < n_eff) sorted_delta[p] = d[j];
+    }
+  }
   __syncthreads();
   B2R_MARK_CTA(3, 0);
   B2R_MARK_CTA(20, 1);
@@ -556,6 +681,7 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
     B2R_MARK_CTA(4, 0);
     B2R_MARK_CTA(21, 1);
     B2R_MARK_CTA(27, a.depth - 1);
+    B2R_MARK_END(15);
     return;
   }
   // serial chains: the thread that owns a group's first position walks the group
@@ -591,6 +717,7 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
   B2R_MARK_CTA(4, 0);
   B2R_MARK_CTA(21, 1);
   B2R_MARK_CTA(27, a.depth - 1);
+  B2R_MARK_END(15);
 }
 
 constexpr int kSmallBatch = 256;  // largest batch the single-CTA kernel takes
@@ -790,8 +917,10 @@ __device__ __forceinline__ void tree_update_tiny_body(const UpdateArgs<I, V> &a)
   __shared__ int s_stop;
   const unsigned full = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  B2R_MARK(5);
   pdl_release();
   pdl_acquire();
+  B2R_MARK(6);
   int n = a.n;
   if (a.n_dev) n = min(n, max(*a.n_dev, 0));
   const int64_t latched = a.status[0];
@@ -883,6 +1012,7 @@ __device__ __forceinline__ void tree_update_tiny_body(const UpdateArgs<I, V> &a)
     }
   }
   if (live && lane == __ffs(same) - 1) a.heap[base + node] = acc;
+  B2R_MARK_END(7);
 }
 
 template <typename I, typename V>
@@ -967,8 +1097,10 @@ int launch_big_chunk(const UpdateArgs<I, V> &a, int depth, cudaStream_t stream) 
   cfg.stream = stream;
   cudaLaunchAttribute attr[3];
   int n_attr = 0;
-  attr[n_attr].id = cudaLaunchAttributeCooperative;
-  attr[n_attr++].val.cooperative = 1;
+  if (pdl_enabled()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr++].val.programmaticStreamSerializationAllowed = 1;
+  }
   if (chain_priority() != 0) {
     attr[n_attr].id = cudaLaunchAttributePriority;
     attr[n_attr++].val.priority = chain_priority();
@@ -1070,11 +1202,35 @@ int flush_fused(b2r_tree *t, int n, const int64_t *slots, const double *prio,
   return B2R_OK;
 }
 
+// Does a batch of n sets (expected_n as in tree_apply) go through the cooperative
+// kernel in ONE chunk, i.e. can its grouping be done ahead of the values?
+bool tree_can_presort(int64_t n, int64_t expected_n) {
+  static const bool on = [] {
+    const char *e = std::getenv("B2R_TREE_PRESORT");
+    return e == nullptr || std::atoi(e) != 0;
+  }();
+  const int64_t likely = expected_n >= 0 ? expected_n : n;
+  if (n <= kSmallBatch && likely <= tree_small_max()) return false;
+  return on && n <= BigCfg4096::kChunk;
+}
+
+static int ensure_sorted(b2r_tree *t) {
+  if (t->sorted) return B2R_OK;
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->sorted),
+                      (size_t)(t->depth + 1) * 2 * BigCfg4096::kChunk * sizeof(uint32_t)));
+  return B2R_OK;
+}
+
 template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
                const uint8_t *mode, cudaStream_t stream, const int32_t *n_dev,
-               int64_t expected_n) {
+               int64_t expected_n, int phase) {
   set_tree_window(t->heap, (size_t)t->leaves * 16);
+  if (phase != kFull) {
+    if (!tree_can_presort(n, expected_n) || mode != nullptr)
+      return fail(B2R_ERR_INVALID_ARGUMENT, "this batch cannot be presorted");
+    B2R_TRY(ensure_sorted(t));
+  }
   const int small_max = tree_small_max();
   // A device-side count (sharded replay) is only bounded by n on the host: the
   // caller's expectation decides, the one-CTA kernel copes with up to kSmallBatch.
@@ -1128,6 +1284,9 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     a.status = t->status;
     a.n_dev = n_dev;
     a.scan_min_chain = tree_scan_min_chain();
+    a.phase = phase;
+    a.sorted = t->sorted;
+    a.sync_words = t->sync_words;
     if (compact)
       B2R_TRY((launch_big_chunk<BigCfg1024>(a, t->depth, stream)));
     else
@@ -1138,13 +1297,13 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
 
 template int tree_apply<int64_t, double>(b2r_tree *, int64_t, const int64_t *,
                                          const double *, const uint8_t *,
-                                         cudaStream_t, const int32_t *, int64_t);
+                                         cudaStream_t, const int32_t *, int64_t, int);
 template int tree_apply<int32_t, float>(b2r_tree *, int64_t, const int32_t *,
                                         const float *, const uint8_t *,
-                                        cudaStream_t, const int32_t *, int64_t);
+                                        cudaStream_t, const int32_t *, int64_t, int);
 template int tree_apply<int32_t, double>(b2r_tree *, int64_t, const int32_t *,
                                          const double *, const uint8_t *,
-                                         cudaStream_t, const int32_t *, int64_t);
+                                         cudaStream_t, const int32_t *, int64_t, int);
 
 }  // namespace b2r
 
@@ -1180,6 +1339,8 @@ int b2r_tree_create(int64_t capacity, b2r_tree **out) {
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->status), 16));
   B2R_CUDA(cudaMemset(t->status, 0, 16));
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->delta), b2r::kTreeChunk * 8));
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->sync_words), 64));
+  B2R_CUDA(cudaMemset(t->sync_words, 0, 64));
   const double one = 1.0;  // ST:89
   B2R_CUDA(cudaMemcpy(t->max_rec, &one, 8, cudaMemcpyHostToDevice));
   *out = t;
@@ -1192,6 +1353,8 @@ int b2r_tree_destroy(b2r_tree *t) {
   cudaFree(t->max_rec);
   cudaFree(t->status);
   cudaFree(t->delta);
+  if (t->sorted) cudaFree(t->sorted);
+  cudaFree(t->sync_words);
   t->bounce.release();
   delete t;
   return B2R_OK;

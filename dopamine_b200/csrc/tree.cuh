@@ -17,6 +17,10 @@ struct b2r_tree {
   double *max_rec = nullptr;   // device scalar: max_recorded_priority
   int64_t *status = nullptr;   // device [2]: latched error code, offending position
   double *delta = nullptr;     // device scratch: per-element leaf deltas of a chunk
+  uint32_t *sorted = nullptr;  // device scratch: per-level (node, entry) lists of a
+                               // presorted chunk (tree.cu: kPresort / kApply)
+  unsigned int *sync_words = nullptr;  // device: level ticket, barrier flag, arrivals,
+                                       // pending failure (tree_update_kernel)
   b2r::Bounce bounce;
 };
 
@@ -267,9 +271,13 @@ __device__ __forceinline__ int stage_top_levels(const double *__restrict__ heap,
 // n_dev (nullable): device count, the effective n is min(n, *n_dev).
 // expected_n (>= 0): how many entries the caller expects when only the device knows
 // (n_dev); picks between the one-CTA and the cooperative kernel.
+// phase: 0 = the whole update; 1 = only group the entries by node (needs the indices,
+// not the values: tree_can_presort says whether this batch can); 2 = apply the values
+// over the lists of a phase-1 launch with the same n / indices / n_dev / expected_n.
 template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
                const uint8_t *mode, cudaStream_t stream,
-               const int32_t *n_dev = nullptr, int64_t expected_n = -1);
+               const int32_t *n_dev = nullptr, int64_t expected_n = -1, int phase = 0);
+bool tree_can_presort(int64_t n, int64_t expected_n);
 
 }  // namespace b2r

@@ -57,6 +57,21 @@ def main():
       wl.fused = False
       wl.step(batch)
 
+    # the latency chain alone (fused call without the frame outputs) and the sampler
+    # followed by the frame copies alone
+    b_noframes = type(b).from_buffer_copy(b)
+    b_noframes.state = None
+    b_noframes.next_state = None
+
+    def chain_only():
+      nat.check(lib.b2r_train_step_device(wl.h, batch, wl.seed, 0,
+                                          ctypes.byref(b_noframes), ctypes.byref(c),
+                                          stream()))
+
+    def sample_gather():
+      nat.check(lib.b2r_sample_transition_batch_device(wl.h, batch, wl.seed, 0,
+                                                       ctypes.byref(b), stream()))
+
     wl.fused = False
     wl.step(batch)  # valid indices / priorities in the plan's buffers
     torch.cuda.synchronize()
@@ -64,7 +79,8 @@ def main():
     reps = max(20, a.reps // max(1, batch // 256))
     for name, fn in (('sample_us', sample), ('gather_us', gather),
                      ('c51_loss_us', loss), ('write_back_us', write_back),
-                     ('step_unfused_us', unfused), ('step_fused_us', fused)):
+                     ('step_unfused_us', unfused), ('step_fused_us', fused),
+                     ('chain_only_us', chain_only), ('sample_gather_us', sample_gather)):
       ms = bench.time_graph_or_eager(torch, fn, reps, 5, True,
                                      per_graph=bench.steps_per_graph(reps, a.per_graph))
       row[name] = round(ms * 1e3 / reps, 2)
