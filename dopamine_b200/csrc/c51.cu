@@ -14,7 +14,7 @@
 //
 // Traffic per row (A=18, N=51): 3 672 B of target logits + 204 B of online logits
 // read, <= 204 B target + 12 B scalars written (+3 672 B if grad_logits is asked).
-#include "common.cuh"
+#include "tree.cuh"
 
 #include <cstdlib>
 
@@ -93,6 +93,12 @@ struct LossArgs {
   float *weighted;        // scratch (B,): w_b * loss_b, reduced by the last CTA
   unsigned int *ticket;   // scratch: CTAs finished (self-resetting)
   int warps;              // warps per CTA = min(num_actions, 32)
+  // Priority write-back at the tail of the loss kernel (batches of at most 32 rows:
+  // the fused step at the agent's batch size).  The last CTA to finish its row runs the
+  // match-based tree update over the priorities the grid has just produced — one kernel
+  // boundary less on a chain of three short kernels.
+  int fuse_tree;
+  UpdateArgs<int32_t, float> tree;
 };
 
 // One CTA per batch row, one warp per action (rainbow_agent.py:200-293):
@@ -377,16 +383,24 @@ c51_loss_kernel(LossArgs a) {
 
   B2R_MARK(7);
   B2R_MARK_END(8);
-  // ---- mean weighted loss: the last CTA to finish reduces in a fixed order.
-  if (a.u.mean_weighted_loss == nullptr) return;
+  // ---- the last CTA to finish: mean weighted loss, reduced in a fixed order, and
+  // (fuse_tree) the priority write-back.
+  if (a.u.mean_weighted_loss == nullptr && !a.fuse_tree) return;
   __threadfence();
+  __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int done = atomicAdd(a.ticket, 1u);
     s_last = (done == gridDim.x - 1);
+    if (s_last) *a.ticket = 0u;  // ready for the next launch
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  if (a.fuse_tree) {
+    tree_update_tiny_body<false>(a.tree);
+    B2R_MARK_END(9);
+  }
+  if (a.u.mean_weighted_loss == nullptr) return;
   float acc = 0.f;
   for (int k = threadIdx.x; k < a.u.batch; k += blockDim.x)
     acc = __fadd_rn(acc, __ldcg(a.weighted + k));
@@ -397,7 +411,6 @@ c51_loss_kernel(LossArgs a) {
     float total = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) total = __fadd_rn(total, s_red[w]);
     *a.u.mean_weighted_loss = __fdiv_rn(total, (float)a.u.batch);
-    *a.ticket = 0u;  // ready for the next launch
   }
 }
 
@@ -723,7 +736,42 @@ int b2r_c51_project(int32_t batch, int32_t num_atoms, const float *supports,
   return B2R_OK;
 }
 
+}  // extern "C"
+
+namespace b2r {
+
+// Can the write-back of this batch ride at the tail of its loss kernel?
+bool c51_can_fuse_writeback(const b2r_c51_args *args, const b2r_tree *tree) {
+  // Off unless B2R_FUSE_WRITEBACK=1: measured on one B200 in one process
+  // (profiles/r2/README.md), the fence + ticket by which the last CTA finds out that it
+  // is the last costs what the kernel boundary it replaces costs (17.4 vs 17.2 us per
+  // step at batch 32).
+  static const bool on = [] {
+    const char *e = std::getenv("B2R_FUSE_WRITEBACK");
+    return e != nullptr && std::atoi(e) != 0;
+  }();
+  return on && tree != nullptr && args->batch <= kTinyBatch && args->batch_count == nullptr &&
+         tree_tiny_enabled() && tree->depth + 1 <= 32 && args->num_atoms <= 64;
+}
+
+int c51_loss_launch(const b2r_c51_args *args, cudaStream_t s, b2r_tree *tree,
+                    const int32_t *indices);
+
+}  // namespace b2r
+
+extern "C" {
+
 int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
+  return b2r::c51_loss_launch(args, as_stream(stream), nullptr, nullptr);
+}
+
+}  // extern "C"
+
+namespace b2r {
+
+// tree != nullptr (c51_can_fuse_writeback): also set_priority(indices, priorities).
+int c51_loss_launch(const b2r_c51_args *args, cudaStream_t s, b2r_tree *tree,
+                    const int32_t *indices) {
   if (!args || args->batch <= 0 || args->num_atoms < 2 || args->num_actions <= 0)
     return fail(B2R_ERR_INVALID_ARGUMENT, "bad C51 shape");
   if (args->batch_count && args->mean_weighted_loss)
@@ -733,14 +781,34 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
       !args->actions || !args->rewards || !args->terminals || !args->loss ||
       !args->priorities)
     return fail(B2R_ERR_INVALID_ARGUMENT, "a required C51 pointer is NULL");
-  cudaStream_t s = as_stream(stream);
   b2r::LossArgs a;
   a.u = *args;
+  a.fuse_tree = 0;
+  if (tree != nullptr) {
+    if (!c51_can_fuse_writeback(args, tree))
+      return fail(B2R_ERR_INVALID_ARGUMENT, "this batch cannot fuse its write-back");
+    set_tree_window(tree->heap, (size_t)tree->leaves * 16);
+    a.fuse_tree = 1;
+    a.tree.heap = tree->heap;
+    a.tree.depth = tree->depth;
+    a.tree.leaves = tree->leaves;
+    a.tree.n = args->batch;
+    a.tree.padded = 32;
+    a.tree.indices = indices;
+    a.tree.values = args->priorities;
+    a.tree.mode = nullptr;
+    a.tree.k_base = 0;
+    a.tree.delta = tree->delta;
+    a.tree.max_rec = tree->max_rec;
+    a.tree.status = tree->status;
+    a.tree.n_dev = nullptr;
+  }
   // Small batches are latency-bound: one warp per action.  Large batches are
   // throughput-bound: a third of that, so more rows are resident per SM.
   a.warps = args->num_actions < 32 ? args->num_actions : 32;
   if (args->batch > 256) a.warps = (a.warps + 2) / 3;
-  const int threads = a.warps * 32;
+  int threads = a.warps * 32;
+  if (a.fuse_tree && threads < 32 * (tree->depth + 1)) threads = 32 * (tree->depth + 1);
   const size_t smem = ((size_t)a.warps + 5) * args->num_atoms * sizeof(float);
   if (smem > 48 * 1024 || args->num_atoms > 32 * b2r::kMaxAtomsPerLane)
     return fail(B2R_ERR_UNSUPPORTED, "num_atoms above 128 is not supported");
@@ -807,7 +875,7 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
   return B2R_OK;
 }
 
-}  // extern "C"
+}  // namespace b2r
 
 #ifdef B2R_TRACE
 extern "C" int b2r_debug_trace_c51(long long *out) {

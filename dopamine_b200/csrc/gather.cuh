@@ -75,7 +75,8 @@ __device__ __forceinline__ void load_scalars(const ScalarArgs &a, int64_t i,
 
 // Writes row b from the loaded values; returns f32(leaf) (+inf without a tree).
 __device__ __forceinline__ float finish_scalars(const ScalarArgs &a, int b, int64_t i,
-                                                const ScalarLoads &r) {
+                                                const ScalarLoads &r,
+                                                int *length_out = nullptr) {
   int length = a.horizon;
   bool ends = false;
 #pragma unroll
@@ -94,6 +95,7 @@ __device__ __forceinline__ float finish_scalars(const ScalarArgs &a, int b, int6
     }
   }
   const float prio = a.leaves ? (float)r.leaf : INFINITY;
+  if (length_out) *length_out = length;
   if (a.ret) static_cast<float *>(a.ret)[b] = acc;
   if (a.prio_out) a.prio_out[b] = prio;
   if (a.indices_out) a.indices_out[b] = (int32_t)i;

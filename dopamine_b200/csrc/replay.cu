@@ -256,6 +256,33 @@ int ensure_inv_slots(b2r_buffer *b, int64_t n) {
   return B2R_OK;
 }
 
+int row_flags_for(b2r_buffer *b, int64_t rows, RowFlags *out) {
+  // Off unless B2R_ROW_FLAGS=1: measured (profiles/r2/README.md), starting the copies
+  // row by row gains 0.4-1 us of a 33 us sampler + copies pair at batch 1024 and costs
+  // 2 us at batch 32, where the sampler's first CTA has to hold back its dependents.
+  static const bool on = [] {
+    const char *e = std::getenv("B2R_ROW_FLAGS");
+    return e != nullptr && std::atoi(e) != 0;
+  }();
+  out->desc = nullptr;
+  out->tag_word = out->final_word = nullptr;
+  if (!on) return B2R_OK;
+  if (rows > b->row_flags_cap) {
+    if (b->row_flags) cudaFree(b->row_flags);
+    b->row_flags = nullptr;
+    b->row_flags_cap = 0;
+    int64_t cap = 4096;
+    while (cap < rows) cap *= 2;
+    B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->row_flags), (size_t)(cap + 4) * 8));
+    B2R_CUDA(cudaMemset(b->row_flags, 0, (size_t)(cap + 4) * 8));
+    b->row_flags_cap = cap;
+  }
+  out->tag_word = b->row_flags;
+  out->final_word = b->row_flags + 1;
+  out->desc = reinterpret_cast<uint64_t *>(b->row_flags + 8);
+  return B2R_OK;
+}
+
 }  // namespace b2r
 
 using b2r::as_stream;
@@ -408,6 +435,7 @@ int b2r_destroy(b2r_buffer *b) {
     if (b->staging[k].dev) cudaFree(b->staging[k].dev);
     if (b->staging[k].done) cudaEventDestroy(b->staging[k].done);
   }
+  if (b->row_flags) cudaFree(b->row_flags);
   if (b->inv_slots) cudaFree(b->inv_slots);
   cudaFree(b->info);
   cudaFree(b->status);

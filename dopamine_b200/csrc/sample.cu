@@ -70,6 +70,8 @@ struct PerSampleArgs {
   // 1.0 / batch as IEEE double division gives it (np.linspace's step), computed on the
   // host: an fp64 division is a ~500-cycle subroutine on the device.
   double step;
+  // Row-by-row hand-over to the step's consumers (warp sampler, Philox draws only).
+  RowFlags flags;
 };
 
 __device__ __forceinline__ void st_sys_u64(uint64_t *p, uint64_t v) {
@@ -644,14 +646,28 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps = blockDim.x >> 5;
   B2R_MARK(10);
-  pdl_release();
-  pdl_acquire();
+  const bool hand_over = a.flags.desc != nullptr && a.counter != nullptr && a.with_scalars &&
+                         a.sc.fast;
+  if (hand_over && blockIdx.x == 0) {
+    // CTA 0 names the step before it lets the dependents start (RowFlags)
+    pdl_acquire();
+    if (threadIdx.x == 0) {
+      st_release_u32(a.flags.tag_word, (uint32_t)(*a.counter + 1));
+      __threadfence();
+    }
+    __syncthreads();
+    pdl_release();
+  } else {
+    pdl_release();
+    pdl_acquire();
+  }
   B2R_MARK(11);
   // every load of the prologue is issued before the first one is used; the nodes of
   // the first descent round (levels 1..5 under the root) ride along
   WarpCtx ctx;
   warp_ctx_issue(a.valid_dev, lane, &ctx);
   const uint64_t draws_before = a.counter ? *a.counter : 0ull;
+  const uint32_t row_tag = (uint32_t)(draws_before + 1);
   const bool exchange = a.xchg.local != nullptr && a.num_shards > 1;
   uint64_t xseq = 0;
   if (exchange) xseq = *a.xchg.seq + 1;
@@ -688,6 +704,7 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
       if (a.counter) *a.counter = draws_before + 1;
       if (exchange) *a.xchg.seq = xseq;
       if (a.latched && a.latched[0] == 0) a.latched[0] = B2R_ERR_EMPTY_TREE;
+      if (hand_over) st_release_u32(a.flags.final_word, row_tag);
     }
     return;
   }
@@ -805,9 +822,12 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
         ws.inv_flag[pos] = valid ? 0 : 1;
         if (valid) {
           float p = INFINITY;
-          if (fast_scalars) p = finish_scalars(a.sc, pos, idx, row);
+          int length = 0;
+          if (fast_scalars) p = finish_scalars(a.sc, pos, idx, row, &length);
           else if (a.with_scalars) p = write_scalars(a.sc, pos, idx);
           my_min = fminf(my_min, p);
+          if (hand_over)
+            st_release_u64(a.flags.desc + pos, row_descriptor(row_tag, length, idx));
         }
       } else {
         ws.spec_idx[pos - n_mine] = (int32_t)idx;
@@ -939,13 +959,16 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
       const int idx = n_spec > 0 ? s_spec_idx[r] : ld_scratch<CLUSTER>(ws.spec_idx + r);
       const int slot = ws.inv_list[j];
       a.out_idx[slot] = idx;
+      int length = 0;
       if (fast_scalars) {  // one round trip for every input of the row
         ScalarLoads row;
         load_scalars(a.sc, idx, &row);
-        fix_min = fminf(fix_min, finish_scalars(a.sc, slot, idx, row));
+        fix_min = fminf(fix_min, finish_scalars(a.sc, slot, idx, row, &length));
       } else if (a.with_scalars) {
         fix_min = fminf(fix_min, write_scalars(a.sc, slot, idx));
       }
+      if (hand_over)
+        st_release_u64(a.flags.desc + slot, row_descriptor(row_tag, length, idx));
       if (j == num_invalid - 1) s_draws_used = r + 1;
     }
     if (threadIdx.x == 0 && spec_done == budget) {
@@ -977,7 +1000,16 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
       if (active && valid && ord < num_invalid) {
         const int slot = ws.inv_list[ord];
         a.out_idx[slot] = (int32_t)idx;
-        if (a.with_scalars) fix_min = fminf(fix_min, write_scalars(a.sc, slot, idx));
+        int length = 0;
+        if (fast_scalars) {
+          ScalarLoads row;
+          load_scalars(a.sc, idx, &row);
+          fix_min = fminf(fix_min, finish_scalars(a.sc, slot, idx, row, &length));
+        } else if (a.with_scalars) {
+          fix_min = fminf(fix_min, write_scalars(a.sc, slot, idx));
+        }
+        if (hand_over)
+          st_release_u64(a.flags.desc + slot, row_descriptor(row_tag, length, idx));
         if (ord == num_invalid - 1) s_draws_used = r + 1;
       }
       if (active && r == budget - 1) {
@@ -1008,8 +1040,21 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
           // the slot burnt the rest of the budget and keeps its last (invalid) draw;
           // only a FURTHER invalid slot raises.
           a.out_idx[next_slot] = s_last_idx;
-          if (a.with_scalars && s_last_idx >= 0 && s_last_idx < ctx.capacity)
-            fix_min = fminf(fix_min, write_scalars(a.sc, next_slot, s_last_idx));
+          if (a.with_scalars && s_last_idx >= 0 && s_last_idx < ctx.capacity) {
+            // (the reference hands this invalid index on: so do the consumers' rows)
+            int length = 0;
+            if (fast_scalars) {
+              ScalarLoads row;
+              load_scalars(a.sc, s_last_idx, &row);
+              fix_min = fminf(fix_min,
+                              finish_scalars(a.sc, next_slot, s_last_idx, row, &length));
+            } else {
+              fix_min = fminf(fix_min, write_scalars(a.sc, next_slot, s_last_idx));
+            }
+            if (hand_over)
+              st_release_u64(a.flags.desc + next_slot,
+                             row_descriptor(row_tag, length, s_last_idx));
+          }
           if (num_invalid > found + 1) {
             status = B2R_ERR_SAMPLE_ATTEMPTS;
             fail_slot = ws.inv_list[found + 1];
@@ -1038,6 +1083,7 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
     const float m = block_min(fminf(min_seen, fix_min), warp_mins);
     if (threadIdx.x == 0) *a.min_prob_out = m;
   }
+  if (hand_over && threadIdx.x == 0) st_release_u32(a.flags.final_word, row_tag);
   B2R_MARK_ANY(20);
 }
 
@@ -1167,6 +1213,24 @@ static int sampler_variant() {
   return v;
 }
 
+// Largest number of strata the warp sampler takes.  Every instruction of it serves ONE
+// stratum, so from a few thousand strata on it is bound by instruction issue (4096
+// warps x ~2 k instructions = 14 k cycles on 592 schedulers) and the thread-per-stratum
+// kernel, 32 strata per instruction, is the faster one again: measured in the fused
+// step at 4096, 116 us against 109 us (profiles/r2/README.md).  B2R_SAMPLER_WARP_MAX
+// overrides.
+static int sampler_warp_max() {
+  static const int v = [] {
+    const char *e = std::getenv("B2R_SAMPLER_WARP_MAX");
+    return e ? std::atoi(e) : 2048;
+  }();
+  return v;
+}
+
+bool sampler_hands_over_rows(int strata) {
+  return sampler_variant() == 1 && strata <= sampler_warp_max();
+}
+
 // Grid and scratch of the warp sampler for `strata` expected strata and outputs of
 // `cap` rows.
 static int warp_sampler_setup(b2r_buffer *b, int strata, int cap, WarpScratch *ws,
@@ -1229,12 +1293,12 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
                   uint64_t offset, const double *strat_dev,
                   const double *retry_dev, int32_t n_retry, int32_t *out_idx_dev,
                   int32_t *info_dev, cudaStream_t stream,
-                  const b2r_batch *scalars, float *min_prob_out) {
+                  const b2r_batch *scalars, float *min_prob_out, const RowFlags *flags) {
   int threads, tiles;
   sample_shape(batch, &threads, &tiles);
   if (tiles > kMaxTiles)
     return fail(B2R_ERR_UNSUPPORTED, "batch above %d is not supported", kMaxTiles * 128);
-  const bool by_warp = sampler_variant() == 1;
+  const bool by_warp = sampler_variant() == 1 && batch <= sampler_warp_max();
   PerSampleArgs a;
   WarpScratch ws;
   if (by_warp)
@@ -1273,6 +1337,9 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   a.count_out = nullptr;
   a.shard_ranges = 0;
   a.xchg.local = nullptr;
+  a.flags.desc = nullptr;
+  a.flags.tag_word = a.flags.final_word = nullptr;
+  if (flags != nullptr && by_warp && philox) a.flags = *flags;
   if (scalars) {
     fill_scalar_args(b, scalars, &a.sc);
     if (a.sc.indices_out == out_idx_dev) a.sc.indices_out = nullptr;
@@ -1318,7 +1385,9 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
   // Caller-supplied queries (any order): one CTA of the thread kernel walks every tile
   // and compacts this rank's strata with block scans (tiles of 128 over many CTAs with
   // the range search for Philox strata when B2R_SAMPLER=thread).
-  const bool by_warp = sampler_variant() == 1 && query01 == nullptr;
+  // (a rank's expected share decides, not the global batch)
+  const bool by_warp = sampler_variant() == 1 && query01 == nullptr &&
+                       global_batch / num_shards <= sampler_warp_max();
   const bool ranges = query01 == nullptr && num_shards > 1 &&
                       (by_warp || global_batch > 256);
   int threads = global_batch <= 256 ? 256 : (ranges ? 128 : 1024);
@@ -1372,6 +1441,8 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
   a.count_out = out_count;
   a.shard_ranges = ranges ? 1 : 0;
   a.xchg.local = nullptr;
+  a.flags.desc = nullptr;
+  a.flags.tag_word = a.flags.final_word = nullptr;
   if (x && x->world > 1) fill_exchange_args(x, &a.xchg);
   if (scalars) {
     fill_scalar_args(b, scalars, &a.sc);

@@ -51,6 +51,17 @@ static int split_min() {
   return v;
 }
 
+// Profiling switch (never set in production): B2R_DEBUG_SKIP is a bit mask of step
+// kernels to leave out — 1 loss, 2 write-back, 4 its grouping pass, 8 frame copies — to
+// see what each costs the others when they share the GPU.
+static int debug_skip() {
+  static const int v = [] {
+    const char *e = std::getenv("B2R_DEBUG_SKIP");
+    return e ? std::atoi(e) : 0;
+  }();
+  return v;
+}
+
 // One shard of a sharded replay: `batch` is then the GLOBAL batch, this rank's rows
 // are compacted at the front of `out` and counted on the device.
 struct ShardSpec {
@@ -85,6 +96,13 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   // Staged adds (rows on the side stream beside the tree update at larger batches).
   B2R_TRY(flush_queue(b, s, batch > split_min()));
   g_host_trace.lap(2);
+  // Frame copies start row by row as the sampler finalises rows (RowFlags) when the
+  // fast gather path will run: stack 4, 1-byte pixels, 16-byte frames, register variant.
+  RowFlags flags = {nullptr, nullptr, nullptr};
+  const bool frames_wanted =
+      (out->state != nullptr || out->next_state != nullptr) && !(debug_skip() & 8);
+  if (!shard && frames_wanted && sampler_hands_over_rows(batch) && gather_takes_row_flags(b))
+    B2R_TRY(row_flags_for(b, batch, &flags));
   if (shard)
     B2R_TRY(launch_sample_sharded(
         b, batch, shard->exchange->world, shard->exchange->rank, nullptr,
@@ -92,15 +110,16 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
         shard->out_slots, out->indices, shard->out_count, s, out, b->min_prob));
   else
     B2R_TRY(launch_sample(b, batch, true, seed, offset, nullptr, nullptr, 0,
-                          out->indices, b->info, s, out, b->min_prob));
+                          out->indices, b->info, s, out, b->min_prob,
+                          flags.desc ? &flags : nullptr));
   g_host_trace.lap(3);
-  const bool frames = out->state != nullptr || out->next_state != nullptr;
+  const bool frames = frames_wanted;
   // The write-back groups the batch by tree node on every level — which needs the
   // sampled indices, not the new priorities: that half runs on a second forked stream
   // while the loss kernel works, and the write-back proper only applies the values.
   const int64_t expected_rows =
       shard ? (batch + shard->exchange->world - 1) / shard->exchange->world : -1;
-  const bool presort = tree_can_presort(batch, expected_rows);
+  const bool presort = tree_can_presort(batch, expected_rows) && !(debug_skip() & 6);
   if (frames || presort) B2R_CUDA(cudaEventRecord(b->ev_fork, s));
   if (presort) {
     B2R_CUDA(cudaStreamWaitEvent(b->side2, b->ev_fork, 0));
@@ -110,7 +129,8 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   }
   if (frames) {
     B2R_CUDA(cudaStreamWaitEvent(b->side, b->ev_fork, 0));
-    B2R_TRY(launch_gather(b, batch, out->indices, out, b->side, count, true));
+    B2R_TRY(launch_gather(b, batch, out->indices, out, b->side, count, true,
+                          flags.desc ? &flags : nullptr));
     B2R_CUDA(cudaEventRecord(b->ev_join, b->side));
   }
   g_host_trace.lap(4);
@@ -127,12 +147,19 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   // after the write-back, serialises the input copy of the next step behind this
   // step's tail and costs 13 us per update.)
   if (wait_before_loss) B2R_CUDA(cudaStreamWaitEvent(s, wait_before_loss, 0));
-  B2R_TRY(b2r_c51_loss(&loss, s));
+  // At the agent's batch size the write-back rides at the tail of the loss kernel.
+  const bool tail_writeback = !shard && !debug_skip() && c51_can_fuse_writeback(&loss, b->tree);
+  if (tail_writeback)
+    B2R_TRY(c51_loss_launch(&loss, s, b->tree, out->indices));
+  else if (!(debug_skip() & 1))
+    B2R_TRY(b2r_c51_loss(&loss, s));
   if (loss_done) B2R_CUDA(cudaEventRecord(loss_done, s));
   g_host_trace.lap(5);
   if (presort) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join2, 0));
-  B2R_TRY((tree_apply<int32_t, float>(b->tree, batch, out->indices, loss.priorities,
-                                      nullptr, s, count, expected_rows, presort ? 2 : 0)));
+  if (!(debug_skip() & 2) && !tail_writeback)
+    B2R_TRY((tree_apply<int32_t, float>(b->tree, batch, out->indices, loss.priorities,
+                                        nullptr, s, count, expected_rows,
+                                        presort ? 2 : 0)));
   if (frames) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join, 0));
   g_host_trace.lap(6);
   return B2R_OK;

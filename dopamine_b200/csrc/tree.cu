@@ -34,36 +34,7 @@ B2R_TRACE_DECL
 
 constexpr uint64_t kPadKey = ~0ull;
 
-template <typename I, typename V>
-struct UpdateArgs {
-  double *heap;
-  int depth;
-  int64_t leaves;
-  int n, padded;
-  const I *indices;
-  const V *values;
-  const uint8_t *mode;
-  int64_t k_base;
-  double *delta;      // global scratch [n]: leaf deltas, produced by the leaf CTA
-  double *max_rec;
-  int64_t *status;
-  const int32_t *n_dev;  // nullable: device-side element count of the whole batch
-  // internal levels whose average chain (n >> level) is at least this long run their
-  // ordered add-chains as a verified scan (chains_by_verified_scan); 0 = never
-  int scan_min_chain = 0;
-  // Two-launch form of the cooperative kernel (the fused step): grouping the entries by
-  // node needs the INDICES only, so it can run while the loss kernel is still producing
-  // the values.  kPresort: every level CTA sorts and leaves (node, entry) in `sorted`
-  // ([level][node | entry][chunk] words), nothing else.  kApply: the level CTAs read
-  // those lists instead of sorting — unless an entry must not be applied (negative value,
-  // index out of range), in which case the lists are ignored and the kernel sorts the
-  // applied prefix itself, as kFull always does.
-  int phase = 0;
-  uint32_t *sorted = nullptr;
-  // role ticket, barrier flag, barrier arrivals (see tree_update_kernel)
-  unsigned int *sync_words = nullptr;
-};
-constexpr int kFull = 0, kPresort = 1, kApply = 2;
+
 
 // Add-path batches may ask for "whatever max_recorded_priority is when this entry
 // is applied" (mode[k] != 0, rainbow_agent.py:330-334).  Sequentially that is
@@ -901,123 +872,9 @@ __global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V
   tree_update_small_body(a);
 }
 
-// At most 32 sets (the agent's batch, an add flush): entry k lives in lane k of every
-// warp, warp l owns tree level l, and nothing is sorted.  __match_any_sync groups the
-// lanes whose entries share a node; the lowest lane of a group adds the group's deltas
-// in lane (= batch) order, fed by shuffles that do not depend on the running sum, so a
-// level costs its longest chain of DADDs and no more.  The leaf warp resolves duplicate
-// leaves the same way (delta = value - leaf; leaf += delta, sum_tree.py:196-202) and
-// publishes the deltas through shared memory; every other warp has its node values in
-// flight before that barrier.
-constexpr int kTinyBatch = 32;
-
-template <typename I, typename V>
-__device__ __forceinline__ void tree_update_tiny_body(const UpdateArgs<I, V> &a) {
-  __shared__ double s_delta[kTinyBatch];
-  __shared__ int s_stop;
-  const unsigned full = 0xffffffffu;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  B2R_MARK(5);
-  pdl_release();
-  pdl_acquire();
-  B2R_MARK(6);
-  int n = a.n;
-  if (a.n_dev) n = min(n, max(*a.n_dev, 0));
-  const int64_t latched = a.status[0];
-  const int level = warp;
-  const bool is_leaf = level == a.depth;
-  if (level > a.depth) return;  // (no block barrier is reached by a partial set of warps:
-                                //  the launch has exactly depth + 1 warps)
-  const int shift = a.depth - level;
-  const int64_t base = ((int64_t)1) << level;
-  const bool in = lane < n;
-  const int64_t idx = in ? (int64_t)a.indices[lane] : 0;
-  const bool use_max = in && a.mode != nullptr && a.mode[lane] != 0;
-  const double explicit_v = (in && !use_max) ? (double)a.values[lane] : 0.0;
-  const bool idx_ok = in && idx >= 0 && idx < a.leaves;
-  // every lane fetches the node its entry sits under (group mates fetch the same word)
-  const int64_t node = idx_ok ? (idx >> shift) : 0;
-  double node_val = idx_ok ? a.heap[base + node] : 0.0;
-  if (latched != 0) return;  // an earlier chunk failed: the sequence stopped there
-
-  if (is_leaf) {
-    // v_k = mode ? max(max_recorded, explicit values before k) : value_k
-    // (stage_mode_values), the first entry the reference would raise on, and
-    // max_recorded_priority over the applied prefix.
-    const double recorded = *a.max_rec;
-    double x = (in && !use_max) ? explicit_v : -INFINITY;  // inclusive prefix max
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double y = __shfl_up_sync(full, x, o);
-      if (lane >= o) x = fmax(x, y);
-    }
-    double before = __shfl_up_sync(full, x, 1);
-    if (lane == 0) before = -INFINITY;
-    const double v = use_max ? fmax(recorded, before) : explicit_v;
-    const bool bad = in && (v < 0.0 || !idx_ok);
-    const unsigned bad_mask = __ballot_sync(full, bad);
-    const int n_eff = bad_mask ? __ffs(bad_mask) - 1 : n;
-    const bool live = lane < n_eff;
-    double vmax = live ? v : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(full, vmax, o));
-    // lanes that share a leaf: the lowest walks the group in batch order
-    const long long key = live ? (long long)idx : -1ll - lane;
-    const unsigned same = __match_any_sync(full, key);
-    double delta = __dsub_rn(v, node_val);
-    double leaf = __dadd_rn(node_val, delta);
-    if (__any_sync(full, live && (same & (same - 1)) != 0)) {
-      // duplicate leaves: every lane replays its group's chain from the stored leaf
-      double run = node_val;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const double vj = __shfl_sync(full, v, j);
-        if ((same >> j) & 1u) {
-          const double dj = __dsub_rn(vj, run);
-          run = __dadd_rn(run, dj);
-          if (j == lane) delta = dj;
-        }
-      }
-      leaf = run;  // the group's final leaf, in every lane of the group
-    }
-    if (live) {
-      s_delta[lane] = delta;
-      if (lane == __ffs(same) - 1) a.heap[base + idx] = leaf;
-    }
-    // the code of the failure: value first (sum_tree.py:191-193), else the index
-    const double bad_v = __shfl_sync(full, v, bad_mask ? __ffs(bad_mask) - 1 : 0);
-    if (lane == 0) {
-      s_stop = n_eff;
-      if (n_eff > 0 && vmax > recorded) *a.max_rec = vmax;
-      if (n_eff < n) {
-        a.status[0] = bad_v < 0.0 ? B2R_ERR_NEGATIVE_PRIORITY : B2R_ERR_INDEX_RANGE;
-        a.status[1] = a.k_base + n_eff;
-      }
-    }
-  }
-  __syncthreads();  // deltas and n_eff are in shared memory
-  if (is_leaf) return;
-  const int n_eff = s_stop;
-  const bool live = lane < n_eff;
-  const double d = live ? s_delta[lane] : 0.0;
-  const long long key = live ? (long long)node : -1ll - lane;
-  const unsigned same = __match_any_sync(full, key);
-  double acc = __dadd_rn(node_val, d);
-  if (__any_sync(full, live && (same & (same - 1)) != 0)) {
-    acc = node_val;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const double dj = __shfl_sync(full, d, j);
-      if ((same >> j) & 1u) acc = __dadd_rn(acc, dj);
-    }
-  }
-  if (live && lane == __ffs(same) - 1) a.heap[base + node] = acc;
-  B2R_MARK_END(7);
-}
-
 template <typename I, typename V>
 __global__ void __launch_bounds__(1024) tree_update_tiny_kernel(UpdateArgs<I, V> a) {
-  tree_update_tiny_body(a);
+  tree_update_tiny_body<true>(a);
 }
 
 // The flush of staged adds as ONE launch: CTA 0 applies the priorities of the new
@@ -1030,7 +887,7 @@ flush_fused_kernel(UpdateArgs<int64_t, double> a, AddParams p, int row_blocks_pe
                    int tiny) {
   if (blockIdx.x == 0) {
     if (tiny)
-      tree_update_tiny_body(a);
+      tree_update_tiny_body<true>(a);
     else
       tree_update_small_body(a);
     return;
@@ -1097,7 +954,9 @@ int launch_big_chunk(const UpdateArgs<I, V> &a, int depth, cudaStream_t stream) 
   cfg.stream = stream;
   cudaLaunchAttribute attr[3];
   int n_attr = 0;
-  if (pdl_enabled()) {
+  // Launched early (programmatic dependent launch) only in the 256 x 4 geometry: 21
+  // early CTAs of 1024 threads would sit on 21 SMs for the whole loss kernel.
+  if (pdl_enabled() && C::kThreads <= 256) {
     attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n_attr++].val.programmaticStreamSerializationAllowed = 1;
   }
@@ -1211,7 +1070,13 @@ bool tree_can_presort(int64_t n, int64_t expected_n) {
   }();
   const int64_t likely = expected_n >= 0 ? expected_n : n;
   if (n <= kSmallBatch && likely <= tree_small_max()) return false;
-  return on && n <= BigCfg4096::kChunk;
+  // Beyond the 256 x 4 geometry the frame copies bound the step and the write-back
+  // hides behind them anyway: a second pass would only take SM slots from the copies.
+  static const int64_t presort_max = [] {
+    const char *e = std::getenv("B2R_TREE_PRESORT_MAX");
+    return e ? (int64_t)std::atoi(e) : (int64_t)BigCfg1024::kChunk;
+  }();
+  return on && n <= BigCfg4096::kChunk && n <= presort_max;
 }
 
 static int ensure_sorted(b2r_tree *t) {
