@@ -43,6 +43,10 @@ STACK = 4
 METRIC = ('sampled transitions/sec (PER sample+gather+C51 target+priority '
           'update)')
 UNIT = 'transitions/s'
+# largest batch whose frame copies are deferred (see main)
+DEFER_MAX_BATCH = 2048
+# shortest timed work the headline number may rest on (see time_graph_or_eager)
+MIN_TIMED_MS = 50.0
 
 
 def parse_args():
@@ -60,6 +64,8 @@ def parse_args():
                       'divisor of --steps up to this is used); 1 = one graph launch '
                       'per step')
   p.add_argument('--no-sweep', action='store_true')
+  p.add_argument('--no-defer', action='store_true',
+                 help='join the frame copies into the stream after every step')
   p.add_argument('--no-cpu-baseline', action='store_true')
   p.add_argument('--no-e2e', action='store_true')
   p.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'],
@@ -228,6 +234,7 @@ class GpuWorkload(object):
     self.seed = seed + rank
     self.fused = True
     self._plans = {}
+    self.deferred = False
 
   def plan(self, batch):
     """Preallocated outputs + argument structs for a batch size (reused across
@@ -274,6 +281,17 @@ class GpuWorkload(object):
     c.grad_logits = None
     self._plans[batch] = (t, b, c)
     return self._plans[batch]
+
+  def set_deferred(self, on):
+    """Deferred frame copies (b2r_set_deferred_frames): the copies of step n run beside
+    the sampler -> loss -> write-back chain of step n + 1; `join` is then part of every
+    timed group of steps."""
+    self.native.check(self.lib.b2r_join_frames(self.h, self.native.current_stream()))
+    self.native.check(self.lib.b2r_set_deferred_frames(self.h, 1 if on else 0))
+    self.deferred = bool(on)
+
+  def join(self):
+    self.native.check(self.lib.b2r_join_frames(self.h, self.native.current_stream()))
 
   def step(self, batch):
     """sample -> gather -> C51 loss/priorities -> write-back, all in HBM."""
@@ -323,47 +341,91 @@ def steps_per_graph(steps, limit):
   return g
 
 
-def time_graph_or_eager(torch, fn, steps, warmup, use_graph, dist=None, per_graph=1):
+def time_graph_or_eager(torch, fn, steps, warmup, use_graph, dist=None, per_graph=1,
+                        min_ms=0.0, info=None, finish=None):
   """Times `steps` calls of fn with CUDA events on the launching stream.
 
   per_graph > 1 captures that many consecutive calls in one CUDA graph (it must
   divide `steps`): consecutive graph launches are paced by the front end in units of
   about 2 us on B200 (a one-kernel graph replayed back to back reports 6.16, 8.21,
   10.26 ... us whatever the kernel does), and programmatic dependent launch cannot
-  overlap a step's first kernel with the previous graph's last one."""
+  overlap a step's first kernel with the previous graph's last one.
+
+  min_ms > 0: a timed region of `steps` steps that is shorter than min_ms is REPEATED
+  (each repetition is again exactly `steps` steps between two events, barrier and
+  synchronize on both sides) until min_ms of timed work has run, and the MEDIAN region
+  is returned — so that `--steps 20` does not rest on one 0.4 ms sample.  With `dist`
+  every rank runs the same number of regions and each region counts with its maximum
+  over the ranks.  info (dict, optional) receives what was done.
+
+  finish (optional): called after every group of per_graph calls (inside the captured
+  graph; after each call when eager) — the join of work that fn leaves running on other
+  streams (deferred frame copies), so that every timed region contains ALL the work of
+  its steps."""
   side = torch.cuda.Stream()
   side.wait_stream(torch.cuda.current_stream())
   with torch.cuda.stream(side):
     for _ in range(max(3, warmup)):
       fn()
+    if finish is not None:
+      finish()
     side.synchronize()
     runner = fn
+    if finish is not None:
+      def runner():  # eager: one call, then the join
+        fn()
+        finish()
     if use_graph:
       graph = torch.cuda.CUDAGraph()
       assert steps % per_graph == 0, (steps, per_graph)
       with torch.cuda.graph(graph, stream=side):
         for _ in range(per_graph):
           fn()
+        if finish is not None:
+          finish()
       runner = graph.replay
       for _ in range(3):
         runner()
       side.synchronize()
     else:
       per_graph = 1
-    if dist is not None:
-      dist.barrier()
-    torch.cuda.synchronize()
-    start = torch.cuda.Event(enable_timing=True)
-    end = torch.cuda.Event(enable_timing=True)
-    start.record(side)
-    for _ in range(steps // per_graph):
-      runner()
-    end.record(side)
-    end.synchronize()
-    torch.cuda.synchronize()
-    if dist is not None:
-      dist.barrier()
-    ms = start.elapsed_time(end)
+
+    def region():
+      if dist is not None:
+        dist.barrier()
+      torch.cuda.synchronize()
+      start = torch.cuda.Event(enable_timing=True)
+      end = torch.cuda.Event(enable_timing=True)
+      start.record(side)
+      for _ in range(steps // per_graph):
+        runner()
+      end.record(side)
+      end.synchronize()
+      torch.cuda.synchronize()
+      if dist is not None:
+        dist.barrier()
+      return start.elapsed_time(end)
+
+    regions = [region()]
+    if min_ms > 0.0:
+      first = torch.tensor([regions[0]], dtype=torch.float64, device='cuda')
+      if dist is not None:
+        dist.all_reduce(first, op=dist.ReduceOp.MAX)  # every rank repeats equally often
+      more = 0
+      if float(first.item()) < min_ms:
+        more = min(2000, int(np.ceil(min_ms / max(float(first.item()), 1e-3))) - 1)
+        more += (more + 1) % 2 == 0  # odd number of regions: the median is one of them
+      regions += [region() for _ in range(more)]
+    ms_all = torch.tensor(regions, dtype=torch.float64, device='cuda')
+    if dist is not None and len(regions) > 1:
+      dist.all_reduce(ms_all, op=dist.ReduceOp.MAX)
+    ms = float(ms_all.median().item()) if len(regions) > 1 else regions[0]
+    if info is not None:
+      info.update({'timed_regions': len(regions), 'steps_per_region': steps,
+                   'timed_total_ms': round(float(ms_all.sum().item()), 3),
+                   'region_ms_min': round(float(ms_all.min().item()), 5),
+                   'region_ms_median': round(ms, 5),
+                   'region_ms_max': round(float(ms_all.max().item()), 5)})
   torch.cuda.current_stream().wait_stream(side)
   return ms
 
@@ -478,7 +540,7 @@ def measure_e2e(torch, wl, batch, steps, update_period=4, pipeline_depth=2,
   wl.native.check(wl.lib.b2r_check(wl.h, stream))
   row = 7056 + 16  # staged row: frame + action + reward + terminal (padded)
   h2d = world * (update_period * row + (online_h.numel() + target_h.numel()) * 4)
-  d2h = world * (batch + 1) * 4
+  d2h = world * (logit_rows + 1) * 4
   return {'value': round(batch * steps / dt, 1), 'unit': UNIT,
           'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
           'ms_per_step': round(dt * 1e3 / steps, 4), 'steps': steps,
@@ -896,6 +958,38 @@ def run_reference(args):
   print(json.dumps(line))
 
 
+def ordered_line(line):
+  """Key order of the JSON line: the contract's keys first, then a compact copy of the
+  sweep (whole-step fraction of the HBM peak and microseconds per step, per batch), the
+  roofline / e2e / baseline objects, and the long descriptive objects last; the compact
+  sweep is repeated as the very last key, so that a record which keeps only one end of
+  the line still has it."""
+  compact = None
+  if isinstance(line.get('sweep'), dict):
+    compact = {}
+    for b, r in line['sweep'].items():
+      compact[b] = {k: r[k] for k in ('whole_step_frac', 'gather_frac', 'value')
+                    if k in r}
+      if 'ms_per_step' in r:
+        compact[b]['us_per_step'] = round(r['ms_per_step'] * 1e3, 2)
+  front = ['metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step',
+           'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data']
+  middle = ['roofline', 'e2e', 'cpu_baseline', 'gpu_launches', 'clocks', 'shard_check',
+            'timing', 'e2e_sync', 'e2e_host_batch']
+  out = {k: line[k] for k in front if k in line}
+  if compact is not None:
+    out['sweep_summary'] = compact
+  for k in middle:
+    if k in line:
+      out[k] = line[k]
+  for k, v in line.items():
+    if k not in out:
+      out[k] = v
+  if compact is not None:
+    out['sweep_summary_again'] = compact
+  return out
+
+
 def bind_to_gpu_numa_node(local_rank):
   """One process per GPU: run (and first-touch pinned memory) on the CPU cores the
   GPU is attached to, as NCCL does for its own threads.  The host loop of a rank
@@ -974,13 +1068,22 @@ def main():
   else:
     step_fn = lambda: wl.step(args.batch)
     use_graph = not args.no_graph
+  # N = 1, fused step: the frame copies of step n run beside the chain of step n + 1 and
+  # are joined once per timed group of steps (b2r_set_deferred_frames), up to the batch
+  # where the copies saturate HBM and anything beside them only slows both down.
+  defer = lambda b: world == 1 and wl.fused and not args.no_defer and b <= DEFER_MAX_BATCH
+  finish_of = lambda b: wl.join if defer(b) else None
+  wl.set_deferred(defer(args.batch))
 
   clocks = ClockSampler(local_rank)
   if rank == 0:
     clocks.__enter__()
   per_graph = steps_per_graph(args.steps, args.steps_per_graph) if use_graph else 1
+  timing = {}
   ms = time_graph_or_eager(torch, step_fn, args.steps, args.warmup, use_graph, dist,
-                           per_graph=per_graph)
+                           per_graph=per_graph, min_ms=MIN_TIMED_MS, info=timing,
+                           finish=finish_of(args.batch))
+  wl.set_deferred(False)
   if rank == 0:
     clocks.__exit__()
   if dist is not None:
@@ -988,6 +1091,16 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
   _native.check(_native.lib().b2r_check(wl.h, _native.current_stream()))
+  shard_check = None
+  if world > 1:
+    # every rank has run the same steps: the last one's rows must partition the global
+    # batch across the ranks (asserts; see ShardedStep.check_partition)
+    counts = sharded.check_partition()
+    shard_check = {'partition_of_global_batch': True, 'rows_per_rank': counts,
+                   'what': 'after the timed region: all ranks\' strata of the last step '
+                           'all-gathered, asserted to be a partition of range(%d), rows '
+                           'asserted valid transitions of their shard' % (
+                               args.batch * world)}
   transitions = args.batch * world * args.steps
   value = transitions / (ms * 1e-3)
 
@@ -1004,7 +1117,10 @@ def main():
           'launch': ('CUDA graph replay, %d consecutive steps per graph launch' % per_graph
                      if use_graph else 'eager launches') + (
               '; one b2r_train_step_device call per step: frame-stack copies on a '
-              'forked stream beside loss + write-back, joined every step'
+              'forked stream beside loss + write-back' + (
+                  ', joined once per graph launch (deferred: they also run beside the '
+                  'NEXT step\'s sampler -> loss -> write-back)' if defer(args.batch)
+                  else ', joined every step')
               if wl.fused and world == 1 else '') + (
                   '; shard totals exchanged over peer memory (NVLink) inside the '
                   'sampling kernel, no NCCL call on the path'
@@ -1016,6 +1132,11 @@ def main():
       },
       'gpu_launches': int(launches_per_step * args.steps),
       'clocks': clocks.summary(),
+      'timing': dict(timing, what=(
+          'exactly --steps steps per timed region (CUDA events, barrier + synchronize on '
+          'both sides); regions shorter than %d ms are repeated until that much timed work '
+          'has run and the median region is reported (max over ranks per region)'
+          % MIN_TIMED_MS)),
   }
   # N > 1: the larger batches of config 3 / 4 (per-GPU batch b, global b * N)
   sweep_multi = None
@@ -1026,7 +1147,8 @@ def main():
                                       exchange=exchange)
       k = max(20, min(args.steps, 300))
       ms_b = time_graph_or_eager(torch, st.step, k, 5, use_graph, dist,
-                                 per_graph=steps_per_graph(k, args.steps_per_graph))
+                                 per_graph=steps_per_graph(k, args.steps_per_graph),
+                                 min_ms=MIN_TIMED_MS)
       t = torch.tensor([ms_b], device='cuda')
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
       ms_b = float(t.item())
@@ -1058,6 +1180,8 @@ def main():
       line['roofline']['whole_step_frac'] = round(step_gbs / peak_gbs, 4)
     except (KeyError, ZeroDivisionError, TypeError):  # reporting only
       pass
+    if shard_check is not None:
+      line['shard_check'] = shard_check
     if sweep_multi is not None:
       line['sweep'] = sweep_multi
     if e2e_multi is not None:
@@ -1067,11 +1191,15 @@ def main():
       sweep = {}
       for b in sweep_batches:
         k = max(20, min(args.steps, 400))
+        wl.set_deferred(defer(b))
         ms_b = time_graph_or_eager(torch, lambda: wl.step(b), k, 5, use_graph,
-                                   per_graph=steps_per_graph(k, args.steps_per_graph))
+                                   per_graph=steps_per_graph(k, args.steps_per_graph),
+                                   min_ms=MIN_TIMED_MS, finish=finish_of(b))
+        wl.set_deferred(False)
         roof = measure_gather_roofline(torch, wl, b, peak_gbs, launches=60)
         sweep[str(b)] = {'value': round(b * k / (ms_b * 1e-3), 1),
                          'ms_per_step': round(ms_b / k, 5),
+                         'frame_copies': 'deferred' if defer(b) else 'joined every step',
                          'gather_GBps': roof['achieved'],
                          'gather_frac': roof['frac'],
                          'gather_us': roof['us_per_launch']}
@@ -1103,7 +1231,7 @@ def main():
           torch, max(50, min(args.steps, 2000)))
       line['next_rows'] = measure_next_rows(torch)
       line['cpu_baseline'] = cpu_baseline(args.batch, args.capacity)
-    print(json.dumps(line))
+    print(json.dumps(ordered_line(line)))
   if dist is not None:
     dist.barrier()
     dist.destroy_process_group()

@@ -330,7 +330,7 @@ class ReplayTrainer(object):
       raise NotImplementedError(_native.last_error())
     _native.check(status)
     self._h = handle
-    self._loss = np.empty(cfg.batch, dtype=np.float32)
+    self._loss = np.empty(self.logit_rows, dtype=np.float32)
     self._loss_ptr = self._loss.ctypes.data
     self._step = ctypes.c_int64(-1)
     self._step_ref = ctypes.byref(self._step)
@@ -391,7 +391,7 @@ class ReplayTrainer(object):
     batch, c51 = _native.Batch(), _native.C51Args()
     _native.check(self._lib.b2r_trainer_views(self._h, ctypes.byref(batch),
                                               ctypes.byref(c51)))
-    mem, b = self._memory, self.batch_size
+    mem, b = self._memory, self.logit_rows
     obs = tuple(mem._observation_shape) + (mem._stack_size,)  # pylint: disable=protected-access
 
     def view(pointer, shape, typestr):

@@ -14,7 +14,7 @@
 //
 // Traffic per row (A=18, N=51): 3 672 B of target logits + 204 B of online logits
 // read, <= 204 B target + 12 B scalars written (+3 672 B if grad_logits is asked).
-#include "tree.cuh"
+#include "replay.cuh"
 
 #include <cstdlib>
 
@@ -99,6 +99,7 @@ struct LossArgs {
   // boundary less on a chain of three short kernels.
   int fuse_tree;
   UpdateArgs<int32_t, float> tree;
+  int64_t *err;  // nullable: asynchronous error latch (an action outside [0, A))
 };
 
 // One CTA per batch row, one warp per action (rainbow_agent.py:200-293):
@@ -147,7 +148,11 @@ c51_loss_kernel(LossArgs a) {
 
   // ---- every global load the row needs is issued here, before the first use:
   // the kernel is latency-bound at batch 32 and this keeps it to one round trip.
-  const int chosen = a.u.actions[b];
+  // an action outside [0, A) (tf.gather_nd raises): the row is evaluated for action 0,
+  // reports a zero loss and latches B2R_ERR_INDEX_RANGE where the caller gave a latch
+  const int chosen_raw = a.u.actions[b];
+  const bool bad_action = chosen_raw < 0 || chosen_raw >= A;
+  const int chosen = bad_action ? 0 : chosen_raw;
   const float r = a.u.rewards[b];
   const float term = (float)a.u.terminals[b];
   const float my_prob = a.u.sampling_probabilities ? a.u.sampling_probabilities[b] : 1.f;
@@ -335,8 +340,15 @@ c51_loss_kernel(LossArgs a) {
       ce_part = __fadd_rn(ce_part, __fmul_rn(t, logp));
       tsum_part = __fadd_rn(tsum_part, t);
     }
-    const float ce = -warp_sum(ce_part);
+    float ce = -warp_sum(ce_part);
     const float tsum = warp_sum(tsum_part);
+    if (bad_action) {
+      ce = 0.f;
+      if (lane == 0 && a.err != nullptr && a.err[0] == 0) {
+        a.err[0] = B2R_ERR_INDEX_RANGE;
+        a.err[1] = b;
+      }
+    }
     if (lane == 0) {
       a.u.loss[b] = ce;
       a.u.priorities[b] = sqrtf(__fadd_rn(ce, 1e-10f));
@@ -422,8 +434,8 @@ c51_loss_kernel(LossArgs a) {
 // 64 / G atoms each, so one warp instruction serves 32 / G actions, a reduction is
 // log2(G) shuffle steps, and nothing but __syncwarp separates the phases.  The
 // arithmetic is the same f32 sequence per element (exp of the max-shifted logit,
-// probabilities, q = sum z p, first maximum), except that a probability is
-// e * (1 / denom) instead of e / denom (<= 1 ulp apart; parity bound 1e-6 relative).
+// probabilities by true division, q = sum z p, first maximum); only the order in which
+// a row's 51 terms are summed differs between the instances.
 constexpr int kRowWarps = 4;
 constexpr int kRowAtoms = 64;
 
@@ -487,7 +499,9 @@ c51_loss_rows_kernel(LossArgs a) {
   }
 
   if (row_ok) {
-    const int chosen = a.u.actions[b];
+    const int chosen_raw = a.u.actions[b];
+    const bool bad_action = chosen_raw < 0 || chosen_raw >= A;  // (see c51_loss_kernel)
+    const int chosen = bad_action ? 0 : chosen_raw;
     const float r = a.u.rewards[b];
     const float term = (float)a.u.terminals[b];
     const float my_prob = a.u.sampling_probabilities ? a.u.sampling_probabilities[b] : 1.f;
@@ -538,11 +552,10 @@ c51_loss_rows_kernel(LossArgs a) {
         psum = __fadd_rn(psum, e[t]);
       }
       const float denom = group_sum<G>(psum);  // >= 1: the maximum contributes 1
-      const float inv = __frcp_rn(denom);
       float qpart = 0.f;
 #pragma unroll
       for (int t = 0; t < PL; ++t) {
-        e[t] = __fmul_rn(e[t], inv);
+        e[t] = __fdiv_rn(e[t], denom);
         qpart = __fadd_rn(qpart, __fmul_rn(zl[t], e[t]));
       }
       const float q = group_sum<G>(qpart);
@@ -643,8 +656,15 @@ c51_loss_rows_kernel(LossArgs a) {
     }
 
     // ---- C. cross entropy (RA:262-271), priority (RA:290), weight (RA:279-280)
-    const float ce = -group_sum<32>(ce_part);
+    float ce = -group_sum<32>(ce_part);
     const float tsum = group_sum<32>(tsum_part);
+    if (bad_action) {
+      ce = 0.f;
+      if (lane == 0 && a.err != nullptr && a.err[0] == 0) {
+        a.err[0] = B2R_ERR_INDEX_RANGE;
+        a.err[1] = b;
+      }
+    }
     float w = 1.f;
     if (a.u.sampling_probabilities) {
       const float wmax = __fdiv_rn(1.0f, sqrtf(__fadd_rn(pmin, 1e-10f)));
@@ -682,6 +702,501 @@ c51_loss_rows_kernel(LossArgs a) {
   }
 
   B2R_MARK_END(12);
+  // ---- mean weighted loss: the last CTA to finish reduces in a fixed order.
+  if (a.u.mean_weighted_loss == nullptr) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(a.ticket, 1u);
+    s_last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < a.u.batch; k += blockDim.x)
+    acc = __fadd_rn(acc, __ldcg(a.weighted + k));
+  acc = group_sum<32>(acc);
+  if (lane == 0) s_red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float total = 0.f;
+    for (int k = 0; k < kRowWarps; ++k) total = __fadd_rn(total, s_red[k]);
+    *a.u.mean_weighted_loss = __fdiv_rn(total, (float)a.u.batch);
+    *a.ticket = 0u;  // ready for the next launch
+  }
+}
+
+// ---- the loss in two halves (the fused step) --------------------------------------
+// What a row's loss needs from the NETWORK OUTPUTS alone — softmax and q-value of every
+// action's target logits, the greedy next action and its probabilities, the log-sum-exp
+// of every action's online logits — does not depend on which transitions were sampled;
+// what depends on the sample (action, n-step return, terminal, sampling probability) is
+// a short tail: Bellman support, projection of ONE distribution, cross entropy against
+// ONE row of online logits.  The fused step runs the first half (c51_pre_*) beside the
+// sampler and the tail (c51_post_kernel) behind it (PreSync, replay.cuh, says how the two
+// meet).  The arithmetic is that of c51_loss_kernel, element by element.
+//
+// Scratch per row (kPreRow floats): [0, 64) probabilities of the greedy next action,
+// [64, 128) online softmax statistics, (max, log of the denominator) per action for the
+// first 32 actions (c51_pre_kernel only; stats == 0 in PostArgs: the tail computes them).
+constexpr int kPreRow = 2 * kRowAtoms;
+
+struct PreArgs {
+  const float *target_logits;
+  const float *online_logits;
+  const float *support;
+  float *scratch;  // [rows][kPreRow]
+  int rows, num_actions, num_atoms, warps;
+  PreSync sync;
+};
+
+// CTA per row, warp per action (rows below 128: latency-bound).
+template <int PL>
+__global__ void __launch_bounds__(1024) c51_pre_kernel(PreArgs a) {
+  __shared__ float s_q[32];
+  __shared__ int s_a[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const int N = a.num_atoms, A = a.num_actions, W = a.warps;
+  B2R_MARK(0);
+  pdl_release();
+  pdl_acquire();
+  B2R_MARK(1);
+  const float *__restrict__ trow = a.target_logits + (size_t)b * A * N;
+  const float *__restrict__ orow = a.online_logits + (size_t)b * A * N;
+  float zl[PL], xt[PL], xo[PL], bp[PL];
+#pragma unroll
+  for (int t = 0; t < PL; ++t) {
+    const int i = lane + 32 * t;
+    zl[t] = i < N ? a.support[i] : 0.f;
+    xt[t] = (i < N && warp < A) ? trow[warp * N + i] : -INFINITY;
+    xo[t] = (i < N && warp < A) ? orow[warp * N + i] : -INFINITY;
+    bp[t] = 0.f;
+  }
+  float best_q = 0.f;
+  int best_a = -1;
+  for (int act = warp; act < A; act += W) {
+    if (act != warp) {
+#pragma unroll
+      for (int t = 0; t < PL; ++t) {
+        const int i = lane + 32 * t;
+        xt[t] = i < N ? trow[act * N + i] : -INFINITY;
+        xo[t] = i < N ? orow[act * N + i] : -INFINITY;
+      }
+    }
+    // the two softmaxes interleave: their reductions do not depend on each other
+    float m = -INFINITY, mo = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < PL; ++t) {
+      m = fmaxf(m, xt[t]);
+      mo = fmaxf(mo, xo[t]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      mo = fmaxf(mo, __shfl_xor_sync(0xffffffffu, mo, o));
+    }
+    float e[PL];
+    float psum = 0.f, osum = 0.f;
+#pragma unroll
+    for (int t = 0; t < PL; ++t) {
+      const bool ok = lane + 32 * t < N;
+      e[t] = ok ? expf(__fsub_rn(xt[t], m)) : 0.f;
+      if (ok) psum = __fadd_rn(psum, e[t]);
+      if (ok) osum = __fadd_rn(osum, expf(__fsub_rn(xo[t], mo)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      psum = __fadd_rn(psum, __shfl_xor_sync(0xffffffffu, psum, o));
+      osum = __fadd_rn(osum, __shfl_xor_sync(0xffffffffu, osum, o));
+    }
+    const float denom = psum;
+    // log_softmax(x) = (x - max) - log(sum exp(x - max))   (rainbow_agent.py:262-271)
+    if (lane == 0 && act < 32) {
+      float2 st;
+      st.x = mo;
+      st.y = logf(osum);
+      *reinterpret_cast<float2 *>(a.scratch + (size_t)b * kPreRow + kRowAtoms + 2 * act) = st;
+    }
+    float qpart = 0.f;
+#pragma unroll
+    for (int t = 0; t < PL; ++t) {
+      if (lane + 32 * t < N) {
+        e[t] = __fdiv_rn(e[t], denom);
+        qpart = __fadd_rn(qpart, __fmul_rn(zl[t], e[t]));
+      }
+    }
+    const float q = warp_sum<true>(qpart);
+    if (best_a < 0 || q > best_q) {  // strict > keeps the first maximum
+      best_q = q;
+      best_a = act;
+#pragma unroll
+      for (int t = 0; t < PL; ++t) bp[t] = e[t];
+    }
+  }
+  if (lane == 0) {
+    s_q[warp] = best_q;
+    s_a[warp] = best_a;
+  }
+  __syncthreads();
+  // first maximum over the actions (RA:238-248): highest q, ties to the smaller action
+  int win = lane;
+  {
+    float q = lane < W ? s_q[lane] : 0.f;
+    int act = lane < W ? s_a[lane] : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float q2 = __shfl_xor_sync(0xffffffffu, q, o);
+      const int act2 = __shfl_xor_sync(0xffffffffu, act, o);
+      const int win2 = __shfl_xor_sync(0xffffffffu, win, o);
+      if (act2 >= 0 && (act < 0 || q2 > q || (q2 == q && act2 < act))) {
+        q = q2;
+        act = act2;
+        win = win2;
+      }
+    }
+  }
+  if (warp == win) {
+#pragma unroll
+    for (int t = 0; t < PL; ++t)
+      if (lane + 32 * t < N) a.scratch[(size_t)b * kPreRow + lane + 32 * t] = bp[t];
+  }
+  B2R_MARK_END(8);
+  pre_sync_signal(a.sync);
+}
+
+// Warp per row, G lanes per action (rows from 128 up: bound by instruction issue).
+template <int G, int NC>
+__global__ void __launch_bounds__(kRowWarps * 32) c51_pre_rows_kernel(PreArgs a) {
+  constexpr int PL = NC ? (NC + G - 1) / G : kRowAtoms / G;
+  constexpr int GROUPS = 32 / G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / G, l = lane % G;
+  const int N = NC ? NC : a.num_atoms, A = a.num_actions;
+  B2R_MARK(0);
+  pdl_release();
+  pdl_acquire();
+  B2R_MARK(1);
+  const int b = blockIdx.x * kRowWarps + warp;
+  if (b < a.rows) {
+    const float *__restrict__ trow = a.target_logits + (size_t)b * A * N;
+    float zl[PL], xn[PL];
+#pragma unroll
+    for (int t = 0; t < PL; ++t) {
+      const int i = l + G * t;
+      zl[t] = i < N ? a.support[i] : 0.f;
+      xn[t] = (i < N && grp < A) ? trow[grp * N + i] : kLogitPad;
+    }
+    float best_q = 0.f;
+    int best_a = -1;
+    float bp[PL];
+#pragma unroll
+    for (int t = 0; t < PL; ++t) bp[t] = 0.f;
+    const int rounds = (A + GROUPS - 1) / GROUPS;
+#pragma unroll 1
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int act = rd * GROUPS + grp;
+      const bool valid = act < A;
+      float xt[PL];
+#pragma unroll
+      for (int t = 0; t < PL; ++t) xt[t] = xn[t];
+      const int nact = act + GROUPS;
+#pragma unroll
+      for (int t = 0; t < PL; ++t) {
+        const int i = l + G * t;
+        xn[t] = (i < N && nact < A) ? trow[nact * N + i] : kLogitPad;
+      }
+      float m = xt[0];
+#pragma unroll
+      for (int t = 1; t < PL; ++t) m = fmaxf(m, xt[t]);
+      m = group_max<G>(m);
+      float e[PL];
+      float psum = 0.f;
+#pragma unroll
+      for (int t = 0; t < PL; ++t) {
+        e[t] = expf(__fsub_rn(xt[t], m));  // pads: exactly 0
+        psum = __fadd_rn(psum, e[t]);
+      }
+      const float denom = group_sum<G>(psum);  // >= 1: the maximum contributes 1
+      float qpart = 0.f;
+#pragma unroll
+      for (int t = 0; t < PL; ++t) {
+        e[t] = __fdiv_rn(e[t], denom);
+        qpart = __fadd_rn(qpart, __fmul_rn(zl[t], e[t]));
+      }
+      const float q = group_sum<G>(qpart);
+      if (valid && (best_a < 0 || q > best_q)) {
+        best_q = q;
+        best_a = act;
+#pragma unroll
+        for (int t = 0; t < PL; ++t) bp[t] = e[t];
+      }
+    }
+    const int own_a = best_a;
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) {
+      const float q2 = __shfl_xor_sync(0xffffffffu, best_q, o);
+      const int a2 = __shfl_xor_sync(0xffffffffu, best_a, o);
+      if (a2 >= 0 && (best_a < 0 || q2 > best_q || (q2 == best_q && a2 < best_a))) {
+        best_q = q2;
+        best_a = a2;
+      }
+    }
+    if (own_a == best_a && own_a >= 0) {
+#pragma unroll
+      for (int t = 0; t < PL; ++t)
+        if (l + G * t < N) a.scratch[(size_t)b * kPreRow + l + G * t] = bp[t];
+    }
+  }
+  B2R_MARK_END(8);
+  pre_sync_signal(a.sync);
+}
+
+// The tail: one warp per row, kRowWarps rows per CTA, lanes own atoms lane and lane + 32.
+// Everything a row needs arrives in two memory round trips (the row's scalars, the
+// greedy action's probabilities and the statistics of all actions; then the chosen
+// action's online logits); the candidate terms of a projected atom are evaluated side by
+// side and added in ascending j, as the dense form adds them.
+constexpr int kProjTerms = 6;  // Bellman atoms within dz of an output atom, with slack
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+c51_post_kernel(LossArgs a, const float *__restrict__ scratch, int have_stats) {
+  __shared__ float s_bestp[kRowWarps][kRowAtoms];
+  __shared__ float s_sup[kRowWarps][kRowAtoms];
+  __shared__ float s_red[kRowWarps];
+  __shared__ bool s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = a.u.num_atoms, A = a.u.num_actions;
+  const float *__restrict__ z = a.u.support;
+  B2R_MARK(10);
+  pdl_release();
+  pdl_acquire();
+  B2R_MARK(11);
+  const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
+  if ((int)blockIdx.x * kRowWarps >= rows) return;  // (no mean loss with batch_count)
+  const int b = blockIdx.x * kRowWarps + warp;
+  const bool row_ok = b < rows;
+
+  float pmin = INFINITY;
+  if (a.u.sampling_probabilities) {
+    if (a.u.min_probability) {
+      pmin = *a.u.min_probability;
+    } else {
+      for (int k = threadIdx.x; k < rows; k += blockDim.x)
+        pmin = fminf(pmin, a.u.sampling_probabilities[k]);
+      pmin = -group_max<32>(-pmin);
+      if (lane == 0) s_red[warp] = pmin;
+      __syncthreads();
+      pmin = s_red[0];
+#pragma unroll
+      for (int k = 1; k < kRowWarps; ++k) pmin = fminf(pmin, s_red[k]);
+      __syncthreads();  // s_red is reused by the mean-loss reduction
+    }
+  }
+
+  if (row_ok) {
+    // ---- round trip 1
+    int chosen = a.u.actions[b];
+    const float r = a.u.rewards[b];
+    const float term = (float)a.u.terminals[b];
+    const float my_prob = a.u.sampling_probabilities ? a.u.sampling_probabilities[b] : 1.f;
+    float zl[2], bp[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int i = lane + 32 * t;
+      zl[t] = i < N ? z[i] : 0.f;
+      bp[t] = i < N ? scratch[(size_t)b * kPreRow + i] : 0.f;
+    }
+    float2 st = make_float2(0.f, 0.f);  // lane = action: (max, log denominator)
+    if (have_stats && lane < A)
+      st = *reinterpret_cast<const float2 *>(scratch + (size_t)b * kPreRow + kRowAtoms + 2 * lane);
+    B2R_MARK(13);
+    // an action outside [0, A) (tf.gather_nd raises): evaluated for action 0, zero loss,
+    // B2R_ERR_INDEX_RANGE latched
+    const bool bad_action = chosen < 0 || chosen >= A;
+    if (bad_action) chosen = 0;
+    // ---- round trip 2
+    const float *__restrict__ orow = a.u.online_logits + ((size_t)b * A + chosen) * N;
+    float xo[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) xo[t] = lane + 32 * t < N ? orow[lane + 32 * t] : kLogitPad;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      if (lane + 32 * t < N) s_bestp[warp][lane + 32 * t] = bp[t];
+    // Bellman support (rainbow_agent.py:229-235)
+    const float live = __fsub_rn(1.0f, term);
+    const float gwt = __fmul_rn(a.u.cumulative_gamma, live);
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      if (lane + 32 * t < N) s_sup[warp][lane + 32 * t] = __fadd_rn(r, __fmul_rn(gwt, zl[t]));
+    __syncwarp();
+    // log_softmax of the chosen action's online logits (rainbow_agent.py:262-271)
+    float mo, lse, eo0 = 0.f, eo1 = 0.f, den_o = 1.f;
+    if (have_stats && chosen < 32) {
+      mo = __shfl_sync(0xffffffffu, st.x, chosen);
+      lse = __shfl_sync(0xffffffffu, st.y, chosen);
+      if (a.u.grad_logits) {
+        eo0 = expf(__fsub_rn(xo[0], mo));
+        eo1 = expf(__fsub_rn(xo[1], mo));
+        den_o = group_sum<32>(__fadd_rn(eo0, eo1));
+      }
+    } else {
+      mo = group_max<32>(fmaxf(xo[0], xo[1]));
+      eo0 = expf(__fsub_rn(xo[0], mo));
+      eo1 = expf(__fsub_rn(xo[1], mo));
+      den_o = group_sum<32>(__fadd_rn(eo0, eo1));  // pads add exactly 0
+      lse = logf(den_o);
+    }
+    const float lgp[2] = {__fsub_rn(__fsub_rn(xo[0], mo), lse),
+                          __fsub_rn(__fsub_rn(xo[1], mo), lse)};
+    B2R_MARK(14);
+
+    // projection (RA:381-494): see c51_loss_rows_kernel for the interval argument
+    const float *sup = s_sup[warp], *next_p = s_bestp[warp];
+    const float z0 = __shfl_sync(0xffffffffu, zl[0], 0);
+    const float z1 = __shfl_sync(0xffffffffu, zl[0], 1);
+    const float zlast = __shfl_sync(0xffffffffu, N > 32 ? zl[1] : zl[0], (N - 1) & 31);
+    const float dz = __fsub_rn(z1, z0);
+    float tg[2] = {0.f, 0.f};
+    if (gwt == 0.f) {
+      // terminal row: every s_j is r, so hat(i, .) is one number, and it is 0 for all but
+      // the (at most two) atoms next to clip(r)
+      const float clipped = fminf(fmaxf(sup[0], z0), zlast);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int i = lane + 32 * t;
+        const float gap = fabsf(__fsub_rn(clipped, zl[t]));
+        if (i < N && gap < dz) {
+          float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
+          hat = fminf(fmaxf(hat, 0.f), 1.f);
+          float acc = 0.f;
+#pragma unroll 1
+          for (int j = 0; j < N; ++j) acc = __fadd_rn(acc, __fmul_rn(hat, next_p[j]));
+          tg[t] = acc;
+        }
+      }
+    } else {
+      int jl[2], jh[2];
+      const float inv = __fdividef(1.0f, gwt * dz);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int i = lane + 32 * t;
+        jl[t] = 0;
+        jh[t] = i < N ? N - 1 : -1;
+        if (gwt > 0.f && i < N) {
+          const float lo = (zl[t] - dz - r - gwt * z0) * inv;
+          const float hi = (zl[t] + dz - r - gwt * z0) * inv;
+          if (i > 0 && lo > 0.f) jl[t] = min(N - 1, (int)fminf(lo, 1e6f));
+          if (i < N - 1 && hi < (float)(N - 2)) jh[t] = max(0, (int)fmaxf(hi, -1e6f) + 1);
+        }
+      }
+      const bool narrow = jh[0] - jl[0] < kProjTerms && jh[1] - jl[1] < kProjTerms;
+      if (__all_sync(0xffffffffu, narrow)) {
+        float term_v[2][kProjTerms];
+        bool term_on[2][kProjTerms];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+#pragma unroll
+          for (int k = 0; k < kProjTerms; ++k) {
+            const int j = jl[t] + k;
+            const bool in = j <= jh[t];
+            const int jj = in ? j : 0;
+            const float clipped = fminf(fmaxf(sup[jj], z0), zlast);
+            const float gap = fabsf(__fsub_rn(clipped, zl[t]));
+            float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
+            hat = fminf(fmaxf(hat, 0.f), 1.f);
+            term_v[t][k] = __fmul_rn(hat, next_p[jj]);
+            term_on[t][k] = in && gap < dz;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          float acc = 0.f;
+#pragma unroll
+          for (int k = 0; k < kProjTerms; ++k)
+            if (term_on[t][k]) acc = __fadd_rn(acc, term_v[t][k]);
+          tg[t] = acc;
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          float acc = 0.f;
+#pragma unroll 1
+          for (int j = jl[t]; j <= jh[t]; ++j) {
+            const float clipped = fminf(fmaxf(sup[j], z0), zlast);
+            const float gap = fabsf(__fsub_rn(clipped, zl[t]));
+            if (gap < dz) {
+              float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
+              hat = fminf(fmaxf(hat, 0.f), 1.f);
+              acc = __fadd_rn(acc, __fmul_rn(hat, next_p[j]));
+            }
+          }
+          tg[t] = acc;
+        }
+      }
+    }
+    float ce_part = 0.f, tsum_part = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int i = lane + 32 * t;
+      if (i < N) {
+        if (a.u.target) a.u.target[(size_t)b * N + i] = tg[t];
+        ce_part = __fadd_rn(ce_part, __fmul_rn(tg[t], lgp[t]));
+        tsum_part = __fadd_rn(tsum_part, tg[t]);
+      }
+    }
+
+    // cross entropy (RA:262-271), priority (RA:290), weight (RA:279-280)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ce_part = __fadd_rn(ce_part, __shfl_xor_sync(0xffffffffu, ce_part, o));
+      tsum_part = __fadd_rn(tsum_part, __shfl_xor_sync(0xffffffffu, tsum_part, o));
+    }
+    float ce = -ce_part;
+    const float tsum = tsum_part;
+    if (bad_action) {
+      ce = 0.f;
+      if (lane == 0 && a.err != nullptr && a.err[0] == 0) {
+        a.err[0] = B2R_ERR_INDEX_RANGE;
+        a.err[1] = b;
+      }
+    }
+    float w = 1.f;
+    if (a.u.sampling_probabilities) {
+      const float wmax = __fdiv_rn(1.0f, sqrtf(__fadd_rn(pmin, 1e-10f)));
+      const float raw = __fdiv_rn(1.0f, sqrtf(__fadd_rn(my_prob, 1e-10f)));
+      w = __fdiv_rn(raw, wmax);
+    }
+    if (lane == 0) {
+      a.u.loss[b] = ce;
+      a.u.priorities[b] = sqrtf(__fadd_rn(ce, 1e-10f));
+      if (a.u.weights) a.u.weights[b] = w;
+      a.weighted[b] = __fmul_rn(w, ce);
+    }
+    if (a.u.grad_logits) {
+      const float scale = __fmul_rn(w, __fdiv_rn(1.0f, (float)rows));
+      float *g = a.u.grad_logits + (size_t)b * A * N;
+      float v[2] = {0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int i = lane + 32 * t;
+        if (i < N) {
+          const float p = __fdiv_rn(t == 0 ? eo0 : eo1, den_o);
+          v[t] = __fmul_rn(__fsub_rn(__fmul_rn(p, tsum), tg[t]), scale);
+        }
+      }
+      for (int act = 0; act < A; ++act) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int i = lane + 32 * t;
+          if (i < N) g[act * N + i] = act == chosen ? v[t] : 0.f;
+        }
+      }
+    }
+  }
+  B2R_MARK_END(12);
+
   // ---- mean weighted loss: the last CTA to finish reduces in a fixed order.
   if (a.u.mean_weighted_loss == nullptr) return;
   __threadfence();
@@ -769,6 +1284,100 @@ int b2r_c51_loss(const b2r_c51_args *args, b2r_stream stream) {
 
 namespace b2r {
 
+static int ensure_loss_scratch(int batch) {
+  if (batch > g_weighted_cap) {
+    if (g_weighted) cudaFree(g_weighted);
+    g_weighted = nullptr;
+    int cap = 4096;
+    while (cap < batch) cap *= 2;
+    B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&g_weighted), (size_t)cap * 4));
+    g_weighted_cap = cap;
+  }
+  if (!g_ticket) {
+    B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&g_ticket), 4));
+    B2R_CUDA(cudaMemset(g_ticket, 0, 4));
+  }
+  return B2R_OK;
+}
+
+// ---- the loss in two halves (see c51_pre_kernel) ----
+bool c51_can_split(const b2r_c51_args *args) {
+  // B2R_C51_SPLIT=0 keeps the one-kernel loss in the fused step (comparison runs);
+  // B2R_C51_SPLIT_MAX: largest batch that splits.  Measured per step, one kernel against
+  // two halves (profiles/r2/README.md): 16.8 / 16.0 us at batch 32, 27.9 / 25.7 at 256,
+  // 39.5 / 37.1 at 1024 (deferred copies), but 111 / 119 at 4096, where the first half's
+  // 1024 CTAs take issue slots from the sampler that everything else waits for.
+  static const bool on = [] {
+    const char *e = std::getenv("B2R_C51_SPLIT");
+    return e == nullptr || std::atoi(e) != 0;
+  }();
+  static const int split_max = [] {
+    const char *e = std::getenv("B2R_C51_SPLIT_MAX");
+    return e ? std::atoi(e) : 2048;
+  }();
+  return on && args->batch <= split_max && args->num_atoms >= 2 &&
+         args->num_atoms <= kRowAtoms && args->num_actions > 0;
+}
+
+int c51_scratch_floats_per_row() { return kPreRow; }
+
+// First half over `rows` rows of logits; scratch: device [rows][kPreRow] floats.  Sets
+// *have_stats when the launch leaves the online softmax statistics in the scratch.
+int c51_pre_launch(const b2r_c51_args *args, int rows, float *scratch, const PreSync &sync,
+                   cudaStream_t s, int *have_stats) {
+  if (!args || rows <= 0 || !scratch || !args->target_logits || !args->online_logits ||
+      !args->support)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "bad C51 arguments");
+  PreArgs a;
+  a.target_logits = args->target_logits;
+  a.online_logits = args->online_logits;
+  a.support = args->support;
+  a.scratch = scratch;
+  a.rows = rows;
+  a.num_actions = args->num_actions;
+  a.num_atoms = args->num_atoms;
+  a.warps = args->num_actions < 32 ? args->num_actions : 32;
+  a.sync = sync;
+  if (rows >= 128) {
+    const dim3 grid((rows + kRowWarps - 1) / kRowWarps), block(kRowWarps * 32);
+    if (args->num_atoms == 51)
+      B2R_CUDA(launch(c51_pre_rows_kernel<8, 51>, grid, block, 0, s, a));
+    else
+      B2R_CUDA(launch(c51_pre_rows_kernel<8, 0>, grid, block, 0, s, a));
+    *have_stats = 0;
+  } else {
+    B2R_CUDA(launch(c51_pre_kernel<2>, dim3(rows), dim3(a.warps * 32), 0, s, a));
+    *have_stats = 1;
+  }
+  B2R_LAUNCHED();
+  return B2R_OK;
+}
+
+// The tail over the sampled rows.
+int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_stats,
+                    cudaStream_t s, int64_t *err) {
+  if (!args || args->batch <= 0 || !scratch)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "bad C51 shape");
+  if (args->batch_count && args->mean_weighted_loss)
+    return fail(B2R_ERR_UNSUPPORTED,
+                "mean_weighted_loss cannot be combined with batch_count");
+  if (!args->support || !args->online_logits || !args->actions || !args->rewards ||
+      !args->terminals || !args->loss || !args->priorities)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "a required C51 pointer is NULL");
+  LossArgs a;
+  a.u = *args;
+  a.fuse_tree = 0;
+  a.err = err;
+  a.warps = 0;
+  B2R_TRY(ensure_loss_scratch(args->batch));
+  a.weighted = g_weighted;
+  a.ticket = g_ticket;
+  const dim3 grid((args->batch + kRowWarps - 1) / kRowWarps), block(kRowWarps * 32);
+  B2R_CUDA(launch(c51_post_kernel, grid, block, 0, s, a, scratch, have_stats));
+  B2R_LAUNCHED();
+  return B2R_OK;
+}
+
 // tree != nullptr (c51_can_fuse_writeback): also set_priority(indices, priorities).
 int c51_loss_launch(const b2r_c51_args *args, cudaStream_t s, b2r_tree *tree,
                     const int32_t *indices) {
@@ -784,6 +1393,7 @@ int c51_loss_launch(const b2r_c51_args *args, cudaStream_t s, b2r_tree *tree,
   b2r::LossArgs a;
   a.u = *args;
   a.fuse_tree = 0;
+  a.err = nullptr;
   if (tree != nullptr) {
     if (!c51_can_fuse_writeback(args, tree))
       return fail(B2R_ERR_INVALID_ARGUMENT, "this batch cannot fuse its write-back");
@@ -812,18 +1422,7 @@ int c51_loss_launch(const b2r_c51_args *args, cudaStream_t s, b2r_tree *tree,
   const size_t smem = ((size_t)a.warps + 5) * args->num_atoms * sizeof(float);
   if (smem > 48 * 1024 || args->num_atoms > 32 * b2r::kMaxAtomsPerLane)
     return fail(B2R_ERR_UNSUPPORTED, "num_atoms above 128 is not supported");
-  if (args->batch > b2r::g_weighted_cap) {
-    if (b2r::g_weighted) cudaFree(b2r::g_weighted);
-    b2r::g_weighted = nullptr;
-    int cap = 4096;
-    while (cap < args->batch) cap *= 2;
-    B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b2r::g_weighted), (size_t)cap * 4));
-    b2r::g_weighted_cap = cap;
-  }
-  if (!b2r::g_ticket) {
-    B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b2r::g_ticket), 4));
-    B2R_CUDA(cudaMemset(b2r::g_ticket, 0, 4));
-  }
+  B2R_TRY(ensure_loss_scratch(args->batch));
   a.weighted = b2r::g_weighted;
   a.ticket = b2r::g_ticket;
   // From 128 rows up: one warp per row (B2R_C51_ROWS_MIN overrides the threshold,

@@ -124,8 +124,19 @@ int enqueue(b2r_buffer *b, bool real, const void *const *cols, double priority,
 // kernel body, which copes with up to 256 entries but is only quick for a few dozen).
 constexpr int kFusedFlushMax = 64;
 
+int join_frames(b2r_buffer *b, cudaStream_t stream) {
+  if (!b->frames_pending) return B2R_OK;
+  B2R_CUDA(cudaStreamWaitEvent(stream, b->ev_join, 0));
+  b->frames_pending = false;
+  b->slot_busy[0] = b->slot_busy[1] = false;  // (the copies run in order)
+  return B2R_OK;
+}
+
 int flush_queue(b2r_buffer *b, cudaStream_t stream, bool split) {
   if (b->q_entries == 0) return B2R_OK;
+  // the new rows overwrite ring slots that deferred frame copies may still be reading
+  B2R_TRY(join_frames(b, stream));
+  if (b->deferred_frames) split = false;  // (`side` is the copies' stream)
   Staging *s = &b->staging[b->active];
   const size_t bytes = (size_t)b->header_bytes + (size_t)b->q_rows * b->row_stride;
   // the validity context as of these adds travels in the header
@@ -414,7 +425,14 @@ int b2r_create(const b2r_config *cfg, b2r_buffer **out) {
     int least = 0, greatest = 0;
     cudaDeviceGetStreamPriorityRange(&least, &greatest);
     B2R_CUDA(cudaStreamCreateWithPriority(&b->side2, cudaStreamNonBlocking, greatest));
+    B2R_CUDA(cudaStreamCreateWithPriority(&b->side3, cudaStreamNonBlocking, greatest));
   }
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->pre_sync), 16));
+  B2R_CUDA(cudaMemset(b->pre_sync, 0, 16));
+  for (int k = 0; k < 2; ++k)
+    B2R_CUDA(cudaEventCreateWithFlags(&b->ev_slot_free[k], cudaEventDisableTiming));
+  B2R_CUDA(cudaEventCreateWithFlags(&b->ev_c51_fork, cudaEventDisableTiming));
+  B2R_CUDA(cudaEventCreateWithFlags(&b->ev_c51_pre, cudaEventDisableTiming));
   B2R_CUDA(cudaEventCreateWithFlags(&b->ev_join2, cudaEventDisableTiming));
   B2R_CUDA(cudaEventCreateWithFlags(&b->ev_pre, cudaEventDisableTiming));
   B2R_CUDA(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming));
@@ -449,6 +467,14 @@ int b2r_destroy(b2r_buffer *b) {
   if (b->ev_join) cudaEventDestroy(b->ev_join);
   if (b->side2) cudaStreamDestroy(b->side2);
   if (b->ev_join2) cudaEventDestroy(b->ev_join2);
+  if (b->side3) cudaStreamDestroy(b->side3);
+  if (b->ev_c51_fork) cudaEventDestroy(b->ev_c51_fork);
+  if (b->ev_c51_pre) cudaEventDestroy(b->ev_c51_pre);
+  if (b->c51_bestp) cudaFree(b->c51_bestp);
+  if (b->pre_sync) cudaFree(b->pre_sync);
+  if (b->idx_ring) cudaFree(b->idx_ring);
+  for (int k = 0; k < 2; ++k)
+    if (b->ev_slot_free[k]) cudaEventDestroy(b->ev_slot_free[k]);
   if (b->ev_pre) cudaEventDestroy(b->ev_pre);
   if (b->ev_h2d) cudaEventDestroy(b->ev_h2d);
   if (b->ev_rows) cudaEventDestroy(b->ev_rows);
@@ -616,6 +642,14 @@ int b2r_check(b2r_buffer *b, b2r_stream stream) {
     if (st[0] == B2R_ERR_EXCHANGE)
       return fail(B2R_ERR_EXCHANGE,
                   "shard %lld did not publish its priority total in time",
+                  (long long)st[1]);
+    if (st[0] == B2R_ERR_UNSUPPORTED)
+      return fail(B2R_ERR_UNSUPPORTED,
+                  "a sharded step's share of the global batch (%lld strata) outgrew the "
+                  "rows its outputs hold (max_rows)", (long long)st[1]);
+    if (st[0] == B2R_ERR_INDEX_RANGE)
+      return fail(B2R_ERR_INDEX_RANGE,
+                  "row %lld of the batch holds an action outside [0, num_actions)",
                   (long long)st[1]);
     return fail((int)st[0],
                 "Max sample attempts: Tried %d times but only sampled %lld valid "

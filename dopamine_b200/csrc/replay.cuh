@@ -75,6 +75,22 @@ struct ExchangeArgs {
   int64_t timeout_ns;
 };
 
+// Completion hand-shake between the first half of the C51 loss (c51.cu: c51_pre_*,
+// launched on a forked stream beside the sampler because it needs the network outputs
+// only) and the sampler of the same step.  The loss tail must follow BOTH; a kernel node
+// with two parents loses its programmatic early launch (measured: 2.4 us from the end of
+// the sampler to the first instruction of the tail, against 0.5 us with one parent), so
+// the dependency on the first half goes through memory instead of through the graph:
+// its last CTA bumps `done` (release), the sampler's closing thread waits for that bump
+// (acquire) before the kernel ends, and the tail has the sampler as its only parent.
+// The first half is a few microseconds of work that starts together with the sampler,
+// so the wait normally finds the bump already there.
+struct PreSync {
+  unsigned int *done;    // first-half launches completed (monotone); nullptr: no hand-shake
+  unsigned int *seen;    // ... consumed by a sampler (touched by its closing thread only)
+  unsigned int *ticket;  // CTAs finished in the running first-half launch
+};
+
 // Row-by-row hand-over from the sampling kernel to the kernels that consume its rows in
 // the same step (the frame copies; see per_sample_warp_kernel and
 // gather_stack4_u8_kernel).  Those kernels are programmatic dependents of the sampler:
@@ -111,6 +127,32 @@ __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p) {
   uint64_t v;
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const unsigned int *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Last statement of a first-half CTA (every thread calls it).
+__device__ __forceinline__ void pre_sync_signal(const PreSync &p) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(p.ticket, 1u) == gridDim.x - 1) {
+    *p.ticket = 0u;  // ready for the next launch
+    __threadfence();
+    st_release_u32(p.done, *p.done + 1u);
+  }
+}
+// Called by the sampler's closing thread (ONE thread) before the kernel ends.  Gives up
+// after 2 s: a first half that never ran must not hang the GPU (the tail then reads stale
+// rows; the launch error that caused it has been reported to the caller).
+__device__ __forceinline__ void pre_sync_consume(const PreSync &p) {
+  if (p.done == nullptr) return;
+  const unsigned int seen = *p.seen;
+  const long long t0 = clock64();
+  while (ld_acquire_u32(p.done) == seen)
+    if (clock64() - t0 > 4000000000ll) break;
+  *p.seen = seen + 1u;
 }
 // 24-bit form of the step tag, never 0 (a descriptor that was never written is 0)
 __device__ __forceinline__ uint32_t row_tag24(uint32_t tag) { return tag % 0xffffffu + 1u; }
@@ -263,6 +305,28 @@ struct b2r_buffer {
   cudaStream_t side2 = nullptr;
   cudaEvent_t ev_join2 = nullptr;
   cudaEvent_t ev_pre = nullptr, ev_h2d = nullptr, ev_rows = nullptr;  // split flush
+  // ... and the half of the C51 loss that needs the network outputs only on `side3`,
+  // beside the sampler (c51.cu: c51_pre_kernel)
+  cudaStream_t side3 = nullptr;
+  cudaEvent_t ev_c51_fork = nullptr, ev_c51_pre = nullptr;
+  float *c51_bestp = nullptr;  // device [c51_bestp_rows][64 probabilities | 64 stats]
+  int64_t c51_bestp_rows = 0;
+  unsigned int *pre_sync = nullptr;  // device [4]: PreSync done, seen, ticket
+  // Deferred frame copies (b2r_set_deferred_frames): the copies of a fused step are not
+  // joined into the caller's stream when the call returns but when b2r_join_frames is
+  // called (or staged adds are flushed: they overwrite ring slots the copies may still
+  // read), so the next step's sampler -> loss -> write-back chain runs BESIDE them.  The
+  // copies read their indices from a private two-slot ring: the next sampler overwrites
+  // the caller's `indices` while they are still running.
+  bool deferred_frames = false;
+  bool frames_pending = false;   // a copy was queued on `side` since the last join
+  int frame_parity = 0;
+  int32_t *idx_ring = nullptr;   // device [2][idx_ring_cap]
+  int64_t idx_ring_cap = 0;
+  // copies that read ring slot p have finished (a sampler may then overwrite it: the
+  // chain runs at most one step ahead of the copies)
+  cudaEvent_t ev_slot_free[2] = {nullptr, nullptr};
+  bool slot_busy[2] = {false, false};
   float *min_prob = nullptr;    // device: min sampling probability of the last batch
   uint32_t *row_flags = nullptr;  // device: tag word, final word, desc[row] (RowFlags)
   int64_t row_flags_cap = 0;
@@ -292,6 +356,8 @@ namespace b2r {
 // ring on the buffer's side stream while the priorities go into the tree on
 // `stream`; `stream` then waits for the rows, so callers see no difference.
 int flush_queue(b2r_buffer *buf, cudaStream_t stream, bool split = false);
+// Makes `stream` wait for every deferred frame copy queued so far (no-op otherwise).
+int join_frames(b2r_buffer *buf, cudaStream_t stream);
 void fill_exchange_args(const b2r_exchange *x, ExchangeArgs *out);
 int launch_exchange_publish(const b2r_exchange *x, const b2r_buffer *buf,
                             cudaStream_t stream);
@@ -307,7 +373,8 @@ int launch_sample_sharded(b2r_buffer *buf, int32_t global_batch, int32_t num_sha
                           uint64_t offset, int32_t *out_slots, int32_t *out_indices,
                           int32_t *out_count, cudaStream_t stream,
                           const b2r_batch *scalars = nullptr,
-                          float *min_prob_out = nullptr, int32_t max_rows = 0);
+                          float *min_prob_out = nullptr, int32_t max_rows = 0,
+                          const PreSync *pre = nullptr);
 void fill_valid_ctx(const b2r_buffer *buf, ValidCtx *ctx);
 int ensure_ctx(b2r_buffer *buf, cudaStream_t stream);
 // tree.cu: largest batch the one-CTA tree kernel takes, and the fused flush launch
@@ -331,5 +398,5 @@ int launch_sample(b2r_buffer *buf, int32_t batch, bool philox, uint64_t seed,
                   const double *retry_dev, int32_t n_retry, int32_t *out_idx_dev,
                   int32_t *info_dev, cudaStream_t stream,
                   const b2r_batch *scalars = nullptr, float *min_prob_out = nullptr,
-                  const RowFlags *flags = nullptr);
+                  const RowFlags *flags = nullptr, const PreSync *pre = nullptr);
 }  // namespace b2r

@@ -72,6 +72,13 @@ struct PerSampleArgs {
   double step;
   // Row-by-row hand-over to the step's consumers (warp sampler, Philox draws only).
   RowFlags flags;
+  // Fused step: the first half of the C51 loss runs beside this kernel; the closing
+  // thread waits for it before the kernel ends (PreSync; done == nullptr: nothing to wait
+  // for).
+  PreSync pre;
+  // Rows the caller's outputs hold (a sharded step sizes them by a bound on its share of
+  // the global batch): rows beyond it are dropped and B2R_ERR_UNSUPPORTED is latched.
+  int out_cap;
 };
 
 __device__ __forceinline__ void st_sys_u64(uint64_t *p, uint64_t v) {
@@ -236,6 +243,7 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
       if (a.count_out) *a.count_out = 0;
       if (a.min_prob_out) *a.min_prob_out = INFINITY;
       if (a.counter) *a.counter = draws_before + 1;  // ranks stay in lockstep
+      pre_sync_consume(a.pre);
       if (exchange) *a.xchg.seq = xseq;
       if (a.latched && a.latched[0] == 0) a.latched[0] = B2R_ERR_EMPTY_TREE;
     }
@@ -315,8 +323,11 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
     range_lo = base[0];
     range_hi = base[1];
   }
-  const int n_mine = range_hi - range_lo;  // strata walked by this launch's tiles
+  const int n_all = range_hi - range_lo;
+  // strata walked by this launch's tiles (shard_ranges: at most the output capacity)
+  const int n_mine = a.shard_ranges && n_all > a.out_cap ? a.out_cap : n_all;
   const int n_tiles = (n_mine + tile_size - 1) / tile_size;
+  range_hi = range_lo + n_mine;
   int mine_base = 0;  // running output position (single-CTA sharded mode)
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int i = range_lo + tile * tile_size + threadIdx.x;
@@ -345,6 +356,7 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
     if (a.num_shards > 1 && !a.shard_ranges) {  // compact (grid is 1 CTA here)
       pos = mine_base + block_scan_flag(mine, warp_counts, &tile_mine);
       mine_base += tile_mine;
+      if (pos >= a.out_cap) mine = false;  // beyond the outputs: dropped, latched below
     }
     // The usual case of the agent's batch — one CTA, one tile, every pick valid —
     // needs none of the machinery below (slot lists, ticket, retries): one barrier
@@ -360,16 +372,21 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
       const bool want_min = a.with_scalars && a.min_prob_out != nullptr;
       const float m = want_min ? block_min(row_prio, warp_mins) : INFINITY;
       if (threadIdx.x == 0) {
-        const int rows = a.shard_ranges ? n_mine
-                                        : (a.num_shards > 1 ? mine_base : a.batch);
+        const int all = a.shard_ranges ? n_all : (a.num_shards > 1 ? mine_base : a.batch);
+        const int rows = all < a.out_cap ? all : a.out_cap;
         if (a.counter) *a.counter = draws_before + 1;
         if (exchange) *a.xchg.seq = xseq;
-        a.info[0] = B2R_OK;
+        a.info[0] = all > rows ? B2R_ERR_UNSUPPORTED : B2R_OK;
         a.info[1] = 0;
         a.info[2] = 0;
         a.info[3] = rows;
         if (a.count_out) *a.count_out = rows;
         if (want_min) *a.min_prob_out = m;
+        if (all > rows && a.latched && a.latched[0] == 0) {  // the share outgrew the buffers
+          a.latched[0] = B2R_ERR_UNSUPPORTED;
+          a.latched[1] = all;
+        }
+        pre_sync_consume(a.pre);
       }
       B2R_MARK(8);
       return;
@@ -390,7 +407,8 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
     if (threadIdx.x == 0) a.tile_counts[tile] = tile_inv;
   }
   B2R_MARK(6);
-  const int count = a.shard_ranges ? n_mine : (a.num_shards > 1 ? mine_base : a.batch);
+  const int count_all = a.shard_ranges ? n_all : (a.num_shards > 1 ? mine_base : a.batch);
+  const int count = count_all < a.out_cap ? count_all : a.out_cap;
 
   // ---- only the last CTA to finish goes on
   if (gridDim.x > 1) {
@@ -488,10 +506,14 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
         }
       }
     }
+    const bool outgrew = count_all > count && status == B2R_OK;
+    if (outgrew) status = B2R_ERR_UNSUPPORTED;  // a sharded step outgrew its buffers
     if (a.counter) *a.counter = draws_before + 1;
     if (exchange) *a.xchg.seq = xseq;
     a.info[0] = status;
-    a.info[1] = a.out_slots ? (status ? a.out_slots[fail_slot] : 0) : fail_slot;
+    a.info[1] = outgrew ? count_all
+                        : (a.out_slots ? (status ? a.out_slots[fail_slot] : 0) : fail_slot);
+    if (outgrew) fail_slot = count_all;
     a.info[2] = used;
     a.info[3] = count;
     if (a.count_out) *a.count_out = count;
@@ -508,6 +530,7 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
       *a.min_prob_out = m;
     }
   }
+  if (threadIdx.x == 0) pre_sync_consume(a.pre);
   B2R_MARK(8);
 }
 
@@ -705,6 +728,7 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
       if (exchange) *a.xchg.seq = xseq;
       if (a.latched && a.latched[0] == 0) a.latched[0] = B2R_ERR_EMPTY_TREE;
       if (hand_over) st_release_u32(a.flags.final_word, row_tag);
+      pre_sync_consume(a.pre);
     }
     return;
   }
@@ -1064,7 +1088,7 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
     }
     if (n_all > n_mine && status == B2R_OK) {  // a sharded step outgrew its buffers
       status = B2R_ERR_UNSUPPORTED;
-      fail_slot = n_all;
+      fail_slot = n_all;  // (reported: the size of the share)
     }
     if (a.counter) *a.counter = draws_before + 1;
     if (exchange) *a.xchg.seq = xseq;
@@ -1084,6 +1108,7 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
     if (threadIdx.x == 0) *a.min_prob_out = m;
   }
   if (hand_over && threadIdx.x == 0) st_release_u32(a.flags.final_word, row_tag);
+  if (threadIdx.x == 0) pre_sync_consume(a.pre);
   B2R_MARK_ANY(20);
 }
 
@@ -1293,7 +1318,8 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
                   uint64_t offset, const double *strat_dev,
                   const double *retry_dev, int32_t n_retry, int32_t *out_idx_dev,
                   int32_t *info_dev, cudaStream_t stream,
-                  const b2r_batch *scalars, float *min_prob_out, const RowFlags *flags) {
+                  const b2r_batch *scalars, float *min_prob_out, const RowFlags *flags,
+                  const PreSync *pre) {
   int threads, tiles;
   sample_shape(batch, &threads, &tiles);
   if (tiles > kMaxTiles)
@@ -1336,6 +1362,9 @@ int launch_sample(b2r_buffer *b, int32_t batch, bool philox, uint64_t seed,
   a.min_prob_out = min_prob_out;
   a.count_out = nullptr;
   a.shard_ranges = 0;
+  a.out_cap = batch;
+  a.pre.done = a.pre.seen = a.pre.ticket = nullptr;
+  if (pre != nullptr) a.pre = *pre;
   a.xchg.local = nullptr;
   a.flags.desc = nullptr;
   a.flags.tag_word = a.flags.final_word = nullptr;
@@ -1374,7 +1403,7 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
                           uint64_t offset, int32_t *out_slots, int32_t *out_indices,
                           int32_t *out_count, cudaStream_t s,
                           const b2r_batch *scalars, float *min_prob_out,
-                          int32_t max_rows) {
+                          int32_t max_rows, const PreSync *pre) {
   if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
   if (global_batch <= 0 || num_shards <= 0 || num_shards > kMaxShards || rank < 0 ||
       rank >= num_shards)
@@ -1390,12 +1419,14 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
                        global_batch / num_shards <= sampler_warp_max();
   const bool ranges = query01 == nullptr && num_shards > 1 &&
                       (by_warp || global_batch > 256);
+  const int cap = max_rows > 0 && max_rows < global_batch ? max_rows : global_batch;
   int threads = global_batch <= 256 ? 256 : (ranges ? 128 : 1024);
-  int tiles = (global_batch + threads - 1) / threads;
+  // (with ranges a CTA works on tiles of this rank's range: the grid follows the
+  // capacity of the outputs, not the global batch)
+  int tiles = ((ranges ? cap : global_batch) + threads - 1) / threads;
   if (tiles > kMaxTiles) return fail(B2R_ERR_UNSUPPORTED, "global batch too large");
   PerSampleArgs a;
   WarpScratch ws;
-  const int cap = max_rows > 0 && max_rows < global_batch ? max_rows : global_batch;
   if (by_warp) {
     // grid for the expected share plus a margin; the warps stride over the rest
     int expect = num_shards > 1 ? global_batch / num_shards + global_batch / (4 * num_shards) + 8
@@ -1440,6 +1471,9 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
   a.min_prob_out = min_prob_out;
   a.count_out = out_count;
   a.shard_ranges = ranges ? 1 : 0;
+  a.out_cap = cap;
+  a.pre.done = a.pre.seen = a.pre.ticket = nullptr;
+  if (pre != nullptr) a.pre = *pre;
   a.xchg.local = nullptr;
   a.flags.desc = nullptr;
   a.flags.tag_word = a.flags.final_word = nullptr;

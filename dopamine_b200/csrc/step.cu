@@ -68,6 +68,10 @@ struct ShardSpec {
   const b2r_exchange *exchange;
   int32_t *out_slots;
   int32_t *out_count;
+  // Rows the caller's outputs (and logits) hold: a bound on this rank's share of the
+  // global batch.  Every launch behind the sampler is sized by it, not by the global
+  // batch; 0 = global batch rows.
+  int32_t max_rows;
 };
 
 // wait_before_loss / loss_done (nullable): events of the trainer's copy stream.
@@ -92,50 +96,12 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   if (shard && (!shard->exchange || !shard->out_count))
     return fail(B2R_ERR_INVALID_ARGUMENT, "exchange and out_count are required");
   const int32_t *count = shard ? shard->out_count : nullptr;
+  // rows behind the sampler: the batch, or the capacity of a shard's outputs
+  const int32_t rows_cap =
+      shard && shard->max_rows > 0 && shard->max_rows < batch ? shard->max_rows : batch;
   g_host_trace.lap(1);
-  // Staged adds (rows on the side stream beside the tree update at larger batches).
-  B2R_TRY(flush_queue(b, s, batch > split_min()));
-  g_host_trace.lap(2);
-  // Frame copies start row by row as the sampler finalises rows (RowFlags) when the
-  // fast gather path will run: stack 4, 1-byte pixels, 16-byte frames, register variant.
-  RowFlags flags = {nullptr, nullptr, nullptr};
-  const bool frames_wanted =
-      (out->state != nullptr || out->next_state != nullptr) && !(debug_skip() & 8);
-  if (!shard && frames_wanted && sampler_hands_over_rows(batch) && gather_takes_row_flags(b))
-    B2R_TRY(row_flags_for(b, batch, &flags));
-  if (shard)
-    B2R_TRY(launch_sample_sharded(
-        b, batch, shard->exchange->world, shard->exchange->rank, nullptr,
-        shard->exchange, nullptr, b->cfg.max_sample_attempts, nullptr, seed, offset,
-        shard->out_slots, out->indices, shard->out_count, s, out, b->min_prob));
-  else
-    B2R_TRY(launch_sample(b, batch, true, seed, offset, nullptr, nullptr, 0,
-                          out->indices, b->info, s, out, b->min_prob,
-                          flags.desc ? &flags : nullptr));
-  g_host_trace.lap(3);
-  const bool frames = frames_wanted;
-  // The write-back groups the batch by tree node on every level — which needs the
-  // sampled indices, not the new priorities: that half runs on a second forked stream
-  // while the loss kernel works, and the write-back proper only applies the values.
-  const int64_t expected_rows =
-      shard ? (batch + shard->exchange->world - 1) / shard->exchange->world : -1;
-  const bool presort = tree_can_presort(batch, expected_rows) && !(debug_skip() & 6);
-  if (frames || presort) B2R_CUDA(cudaEventRecord(b->ev_fork, s));
-  if (presort) {
-    B2R_CUDA(cudaStreamWaitEvent(b->side2, b->ev_fork, 0));
-    B2R_TRY((tree_apply<int32_t, float>(b->tree, batch, out->indices, nullptr, nullptr,
-                                        b->side2, count, expected_rows, 1)));
-    B2R_CUDA(cudaEventRecord(b->ev_join2, b->side2));
-  }
-  if (frames) {
-    B2R_CUDA(cudaStreamWaitEvent(b->side, b->ev_fork, 0));
-    B2R_TRY(launch_gather(b, batch, out->indices, out, b->side, count, true,
-                          flags.desc ? &flags : nullptr));
-    B2R_CUDA(cudaEventRecord(b->ev_join, b->side));
-  }
-  g_host_trace.lap(4);
   b2r_c51_args loss = *c51;
-  loss.batch = batch;
+  loss.batch = rows_cap;
   loss.actions = static_cast<const int32_t *>(out->action);
   loss.rewards = static_cast<const float *>(out->reward);
   loss.terminals = static_cast<const uint8_t *>(out->terminal);
@@ -143,13 +109,123 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   loss.min_probability = b->min_prob;
   loss.batch_count = count;
   if (count) loss.mean_weighted_loss = nullptr;
+  // The half of the loss that needs the network outputs only (every action's softmax
+  // and q-value, the greedy next action) starts now, on a forked stream beside the
+  // sampler; the tail that needs the sampled rows follows the sampler (c51.cu).
+  // (A shard does not know its row count before it has sampled: the first half covers
+  // every row its logits hold.)
+  const bool split_loss = !debug_skip() && c51_can_split(&loss);
+  PreSync pre_sync = {nullptr, nullptr, nullptr};
+  int have_stats = 0;
+  if (split_loss) {
+    if (b->c51_bestp_rows < rows_cap) {
+      if (b->c51_bestp) cudaFree(b->c51_bestp);
+      b->c51_bestp = nullptr;
+      b->c51_bestp_rows = 0;
+      int64_t cap = 256;
+      while (cap < rows_cap) cap *= 2;
+      B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->c51_bestp),
+                          (size_t)cap * c51_scratch_floats_per_row() * sizeof(float)));
+      b->c51_bestp_rows = cap;
+    }
+    pre_sync.done = b->pre_sync;
+    pre_sync.seen = b->pre_sync + 1;
+    pre_sync.ticket = b->pre_sync + 2;
+    B2R_CUDA(cudaEventRecord(b->ev_c51_fork, s));
+    B2R_CUDA(cudaStreamWaitEvent(b->side3, b->ev_c51_fork, 0));
+    if (wait_before_loss) B2R_CUDA(cudaStreamWaitEvent(b->side3, wait_before_loss, 0));
+    B2R_TRY(c51_pre_launch(&loss, rows_cap, b->c51_bestp, pre_sync, b->side3, &have_stats));
+    B2R_CUDA(cudaEventRecord(b->ev_c51_pre, b->side3));
+  }
+  // Staged adds (rows on the side stream beside the tree update at larger batches).
+  B2R_TRY(flush_queue(b, s, batch > split_min()));
+  g_host_trace.lap(2);
+  // Deferred frame copies: the copies read their indices from a private ring slot (the
+  // next step's sampler overwrites out->indices while they may still be running).
+  const bool deferred = b->deferred_frames && !shard;
+  int32_t *sample_idx = out->indices;
+  int ring_slot = 0;
+  if (deferred) {
+    if (b->idx_ring_cap < batch) {
+      B2R_TRY(join_frames(b, s));
+      B2R_CUDA(cudaStreamSynchronize(b->side));
+      if (b->idx_ring) cudaFree(b->idx_ring);
+      b->idx_ring = nullptr;
+      b->idx_ring_cap = 0;
+      int64_t cap = 256;
+      while (cap < batch) cap *= 2;
+      B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->idx_ring), (size_t)cap * 2 * 4));
+      b->idx_ring_cap = cap;
+    }
+    ring_slot = b->frame_parity & 1;
+    sample_idx = b->idx_ring + (size_t)ring_slot * b->idx_ring_cap;
+    b->frame_parity ^= 1;
+    // the copies of two steps ago read this slot
+    if (b->slot_busy[ring_slot])
+      B2R_CUDA(cudaStreamWaitEvent(s, b->ev_slot_free[ring_slot], 0));
+  }
+  // Frame copies start row by row as the sampler finalises rows (RowFlags) when the
+  // fast gather path will run: stack 4, 1-byte pixels, 16-byte frames, register variant.
+  RowFlags flags = {nullptr, nullptr, nullptr};
+  const bool frames_wanted =
+      (out->state != nullptr || out->next_state != nullptr) && !(debug_skip() & 8);
+  if (!shard && !deferred && frames_wanted && sampler_hands_over_rows(batch) &&
+      gather_takes_row_flags(b))
+    B2R_TRY(row_flags_for(b, batch, &flags));
+  if (shard)
+    B2R_TRY(launch_sample_sharded(
+        b, batch, shard->exchange->world, shard->exchange->rank, nullptr,
+        shard->exchange, nullptr, b->cfg.max_sample_attempts, nullptr, seed, offset,
+        shard->out_slots, out->indices, shard->out_count, s, out, b->min_prob, rows_cap,
+        split_loss ? &pre_sync : nullptr));
+  else
+    B2R_TRY(launch_sample(b, batch, true, seed, offset, nullptr, nullptr, 0,
+                          sample_idx, b->info, s, out, b->min_prob,
+                          flags.desc ? &flags : nullptr, split_loss ? &pre_sync : nullptr));
+  g_host_trace.lap(3);
+  const bool frames = frames_wanted;
+  // The write-back groups the batch by tree node on every level — which needs the
+  // sampled indices, not the new priorities: that half runs on a second forked stream
+  // while the loss kernel works, and the write-back proper only applies the values.
+  int64_t expected_rows =
+      shard ? (batch + shard->exchange->world - 1) / shard->exchange->world : -1;
+  if (expected_rows > rows_cap) expected_rows = rows_cap;
+  const bool presort = tree_can_presort(rows_cap, expected_rows) && !(debug_skip() & 6);
+  if (frames || presort) B2R_CUDA(cudaEventRecord(b->ev_fork, s));
+  if (presort) {
+    B2R_CUDA(cudaStreamWaitEvent(b->side2, b->ev_fork, 0));
+    B2R_TRY((tree_apply<int32_t, float>(b->tree, rows_cap, out->indices, nullptr, nullptr,
+                                        b->side2, count, expected_rows, 1)));
+    B2R_CUDA(cudaEventRecord(b->ev_join2, b->side2));
+  }
+  if (frames) {
+    B2R_CUDA(cudaStreamWaitEvent(b->side, b->ev_fork, 0));
+    // (deferred: the first half of the loss rejoins through the copies' stream, so that
+    // the next sampler's only parent in a captured graph is this step's write-back)
+    if (deferred && split_loss) B2R_CUDA(cudaStreamWaitEvent(b->side, b->ev_c51_pre, 0));
+    B2R_TRY(launch_gather(b, rows_cap, sample_idx, out, b->side, count, true,
+                          flags.desc ? &flags : nullptr));
+    B2R_CUDA(cudaEventRecord(b->ev_join, b->side));
+    if (deferred) {
+      b->frames_pending = true;
+      B2R_CUDA(cudaEventRecord(b->ev_slot_free[ring_slot], b->side));
+      b->slot_busy[ring_slot] = true;
+    }
+  }
+  g_host_trace.lap(4);
   // (Measured: waiting for the logits before the sampler, or recording "loss done"
   // after the write-back, serialises the input copy of the next step behind this
   // step's tail and costs 13 us per update.)
-  if (wait_before_loss) B2R_CUDA(cudaStreamWaitEvent(s, wait_before_loss, 0));
-  // At the agent's batch size the write-back rides at the tail of the loss kernel.
-  const bool tail_writeback = !shard && !debug_skip() && c51_can_fuse_writeback(&loss, b->tree);
-  if (tail_writeback)
+  // (The first half has signalled the sampler's closing thread by now — PreSync — so the
+  // tail's only parent in a captured graph is the sampler: it keeps its programmatic
+  // early launch.  Its stream rejoins below, with the frame copies.)
+  if (!split_loss && wait_before_loss) B2R_CUDA(cudaStreamWaitEvent(s, wait_before_loss, 0));
+  // (B2R_FUSE_WRITEBACK=1, unsplit loss only: write-back at the tail of the loss kernel)
+  const bool tail_writeback =
+      !split_loss && !shard && !debug_skip() && c51_can_fuse_writeback(&loss, b->tree);
+  if (split_loss)
+    B2R_TRY(c51_post_launch(&loss, b->c51_bestp, have_stats, s, b->status));
+  else if (tail_writeback)
     B2R_TRY(c51_loss_launch(&loss, s, b->tree, out->indices));
   else if (!(debug_skip() & 1))
     B2R_TRY(b2r_c51_loss(&loss, s));
@@ -157,10 +233,11 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   g_host_trace.lap(5);
   if (presort) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join2, 0));
   if (!(debug_skip() & 2) && !tail_writeback)
-    B2R_TRY((tree_apply<int32_t, float>(b->tree, batch, out->indices, loss.priorities,
+    B2R_TRY((tree_apply<int32_t, float>(b->tree, rows_cap, out->indices, loss.priorities,
                                         nullptr, s, count, expected_rows,
                                         presort ? 2 : 0)));
-  if (frames) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join, 0));
+  if (frames && !deferred) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join, 0));
+  if (split_loss && !(deferred && frames)) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_c51_pre, 0));
   g_host_trace.lap(6);
   return B2R_OK;
 }
@@ -237,10 +314,11 @@ int collect(b2r_trainer *t, int64_t step, float *loss_out, int64_t *loss_step) {
   }
   const int slot = (int)(step % t->ring);
   B2R_CUDA(cudaEventSynchronize(t->ev_done[slot]));
-  const float *row = t->ring_host + (size_t)slot * (t->cfg.batch + 1);
-  if (loss_out) memcpy(loss_out, row, (size_t)t->cfg.batch * sizeof(float));
-  t->last_rows = t->cfg.batch;
-  if (t->exchange) memcpy(&t->last_rows, row + t->cfg.batch, sizeof(int32_t));
+  const int rows = t->cfg.logit_rows;
+  const float *row = t->ring_host + (size_t)slot * (rows + 1);
+  if (loss_out) memcpy(loss_out, row, (size_t)rows * sizeof(float));
+  t->last_rows = rows;
+  if (t->exchange) memcpy(&t->last_rows, row + rows, sizeof(int32_t));
   if (loss_step) *loss_step = step;
   return B2R_OK;
 }
@@ -256,12 +334,25 @@ int b2r_train_step_device(b2r_buffer *b, int32_t batch, uint64_t seed,
                          nullptr, nullptr);
 }
 
+int b2r_set_deferred_frames(b2r_buffer *b, int32_t on) {
+  if (!b) return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
+  b->deferred_frames = on != 0;
+  return B2R_OK;
+}
+
+int b2r_join_frames(b2r_buffer *b, b2r_stream stream) {
+  if (!b) return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
+  return b2r::join_frames(b, as_stream(stream));
+}
+
 int b2r_train_step_sharded_device(b2r_buffer *b, b2r_exchange *x,
                                   int32_t global_batch, uint64_t seed,
                                   uint64_t offset, const b2r_batch *out,
                                   const b2r_c51_args *c51, int32_t *out_slots,
-                                  int32_t *out_count, b2r_stream stream) {
-  b2r::ShardSpec shard = {x, out_slots, out_count};
+                                  int32_t *out_count, int32_t max_rows,
+                                  b2r_stream stream) {
+  if (max_rows < 0) return fail(B2R_ERR_INVALID_ARGUMENT, "max_rows must be >= 0");
+  b2r::ShardSpec shard = {x, out_slots, out_count, max_rows};
   return b2r::train_step(b, global_batch, seed, offset, out, c51, as_stream(stream),
                          nullptr, nullptr, &shard);
 }
@@ -281,7 +372,9 @@ int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
   t->cfg = *cfg;
   if (t->cfg.logit_rows == 0) t->cfg.logit_rows = cfg->batch;
   if (const char *e = std::getenv("B2R_TRAINER_GRAPH")) t->cfg.use_graph = std::atoi(e);
-  const size_t B = (size_t)cfg->batch, A = (size_t)cfg->num_actions,
+  // Every buffer holds logit_rows rows: the batch, or (a shard's trainer) the bound on
+  // this rank's share of the global batch — nothing here grows with the world size.
+  const size_t B = (size_t)t->cfg.logit_rows, A = (size_t)cfg->num_actions,
                N = (size_t)cfg->num_atoms;
   const size_t logit_bytes = B * A * N * sizeof(float);
   for (int set = 0; set < 2; ++set)
@@ -328,7 +421,7 @@ int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
   t->batch.sampling_probabilities = reinterpret_cast<float *>(t->scalars + o_prob);
   for (int e = 0; e < b->cfg.num_extras; ++e) t->batch.extras[e] = t->scalars + o_extra[e];
   memset(&t->c51, 0, sizeof(t->c51));
-  t->c51.batch = cfg->batch;
+  t->c51.batch = t->cfg.logit_rows;
   t->c51.num_actions = cfg->num_actions;
   t->c51.num_atoms = cfg->num_atoms;
   t->c51.cumulative_gamma = cfg->cumulative_gamma;
@@ -396,6 +489,9 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
                           int64_t *loss_step, b2r_stream stream) {
   if (!t || !online_logits || !target_logits)
     return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (!t->exchange && t->cfg.logit_rows != t->cfg.batch)
+    return fail(B2R_ERR_INVALID_ARGUMENT,
+                "logit_rows below the batch is for a shard's trainer (set the exchange)");
   cudaStream_t s = as_stream(stream);
   b2r::g_host_trace.start();
   const int64_t n = t->submitted;
@@ -414,7 +510,7 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
     b2r_c51_args c51 = t->c51;
     c51.online_logits = t->logits[set][0];
     c51.target_logits = t->logits[set][1];
-    b2r::ShardSpec shard = {t->exchange, t->slots, t->count};
+    b2r::ShardSpec shard = {t->exchange, t->slots, t->count, t->cfg.logit_rows};
     B2R_TRY(b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch, &c51, s,
                             t->ev_in[set], t->ev_loss[set], &shard));
   } else if (t->cfg.use_graph && n >= 2) {
@@ -437,8 +533,8 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   // result: per-row losses into this step's pinned slot (copy stream, after the loss)
   const int slot = (int)(n % t->ring);
   B2R_CUDA(cudaStreamWaitEvent(t->copy_out, t->ev_loss[set], 0));
-  B2R_CUDA(cudaMemcpyAsync(t->ring_host + (size_t)slot * (t->cfg.batch + 1),
-                           t->c51.loss, (size_t)(t->cfg.batch + 1) * sizeof(float),
+  B2R_CUDA(cudaMemcpyAsync(t->ring_host + (size_t)slot * (t->cfg.logit_rows + 1),
+                           t->c51.loss, (size_t)(t->cfg.logit_rows + 1) * sizeof(float),
                            cudaMemcpyDeviceToHost, t->copy_out));
   B2R_CUDA(cudaEventRecord(t->ev_done[slot], t->copy_out));
   t->submitted = n + 1;

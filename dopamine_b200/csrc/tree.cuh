@@ -310,38 +310,52 @@ constexpr int kFull = 0, kPresort = 1, kApply = 2;
 // flight before that barrier.
 constexpr int kTinyBatch = 32;
 
-// PDL: the body opens a kernel of its own (programmatic dependent launch hand-shake);
-// false when it runs at the tail of another kernel (c51.cu: the loss kernel's last CTA).
-template <bool PDL, typename I, typename V>
-__device__ __forceinline__ void tree_update_tiny_body(const UpdateArgs<I, V> &a) {
+// The update in two halves, so that a kernel which PRODUCES the values (c51.cu: the
+// loss tail of the fused step) can have every tree load in flight before it starts on
+// them: tiny_issue needs the indices only; tiny_finish takes the entry's value.
+struct TinyLoads {
+  int n;
+  int64_t latched, idx, node;
+  bool in, use_max, idx_ok;
+  double node_val;
+};
+
+template <typename I, typename V>
+__device__ __forceinline__ void tree_update_tiny_issue(const UpdateArgs<I, V> &a, int level,
+                                                       int lane, TinyLoads *t) {
+  t->n = a.n;
+  if (a.n_dev) t->n = min(t->n, max(*a.n_dev, 0));
+  t->latched = a.status[0];
+  const int shift = a.depth - level;
+  const int64_t base = ((int64_t)1) << level;
+  t->in = lane < t->n && level <= a.depth;
+  t->idx = t->in ? (int64_t)a.indices[lane] : 0;
+  t->use_max = t->in && a.mode != nullptr && a.mode[lane] != 0;
+  t->idx_ok = t->in && t->idx >= 0 && t->idx < a.leaves;
+  // every lane fetches the node its entry sits under (group mates fetch the same word)
+  t->node = t->idx_ok ? (t->idx >> shift) : 0;
+  t->node_val = t->idx_ok ? a.heap[base + t->node] : 0.0;
+}
+
+// Every warp of the block must call this (one block barrier inside); warps whose level
+// lies beyond the tree's depth only take part in the barrier.
+template <typename I, typename V>
+__device__ __forceinline__ void tree_update_tiny_finish(const UpdateArgs<I, V> &a, int level,
+                                                        int lane, const TinyLoads &t,
+                                                        double explicit_v) {
   __shared__ double s_delta[kTinyBatch];
   __shared__ int s_stop;
   const unsigned full = 0xffffffffu;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (PDL) {
-    pdl_release();
-    pdl_acquire();
-  }
-  int n = a.n;
-  if (a.n_dev) n = min(n, max(*a.n_dev, 0));
-  const int64_t latched = a.status[0];
-  const int level = warp;
+  const int n = t.n;
   const bool is_leaf = level == a.depth;
-  if (level > a.depth) return;  // (no block barrier is reached by a partial set of warps:
-                                //  the launch has exactly depth + 1 warps)
-  const int shift = a.depth - level;
-  const int64_t base = ((int64_t)1) << level;
-  const bool in = lane < n;
-  const int64_t idx = in ? (int64_t)a.indices[lane] : 0;
-  const bool use_max = in && a.mode != nullptr && a.mode[lane] != 0;
-  const double explicit_v = (in && !use_max) ? (double)a.values[lane] : 0.0;
-  const bool idx_ok = in && idx >= 0 && idx < a.leaves;
-  // every lane fetches the node its entry sits under (group mates fetch the same word)
-  const int64_t node = idx_ok ? (idx >> shift) : 0;
-  double node_val = idx_ok ? a.heap[base + node] : 0.0;
-  if (latched != 0) return;  // an earlier chunk failed: the sequence stopped there
+  const bool skip = level > a.depth || t.latched != 0;  // an earlier chunk failed: the
+                                                        // sequence stopped there
+  const int64_t base = ((int64_t)1) << (level <= a.depth ? level : 0);
+  const bool in = t.in, use_max = t.use_max, idx_ok = t.idx_ok;
+  const int64_t idx = t.idx, node = t.node;
+  const double node_val = t.node_val;
 
-  if (is_leaf) {
+  if (is_leaf && !skip) {
     // v_k = mode ? max(max_recorded, explicit values before k) : value_k
     // (stage_mode_values), the first entry the reference would raise on, and
     // max_recorded_priority over the applied prefix.
@@ -397,7 +411,7 @@ __device__ __forceinline__ void tree_update_tiny_body(const UpdateArgs<I, V> &a)
     }
   }
   __syncthreads();  // deltas and n_eff are in shared memory
-  if (is_leaf) return;
+  if (is_leaf || skip) return;
   const int n_eff = s_stop;
   const bool live = lane < n_eff;
   const double d = live ? s_delta[lane] : 0.0;
@@ -413,6 +427,21 @@ __device__ __forceinline__ void tree_update_tiny_body(const UpdateArgs<I, V> &a)
     }
   }
   if (live && lane == __ffs(same) - 1) a.heap[base + node] = acc;
+}
+
+// PDL: the body opens a kernel of its own (programmatic dependent launch hand-shake);
+// false when it runs at the tail of another kernel.
+template <bool PDL, typename I, typename V>
+__device__ __forceinline__ void tree_update_tiny_body(const UpdateArgs<I, V> &a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (PDL) {
+    pdl_release();
+    pdl_acquire();
+  }
+  TinyLoads t;
+  tree_update_tiny_issue(a, warp, lane, &t);
+  const double explicit_v = (t.in && !t.use_max) ? (double)a.values[lane] : 0.0;
+  tree_update_tiny_finish(a, warp, lane, t, explicit_v);
 }
 
 #endif  // __CUDACC__
@@ -435,5 +464,16 @@ bool tree_tiny_enabled();
 bool c51_can_fuse_writeback(const b2r_c51_args *args, const b2r_tree *tree);
 int c51_loss_launch(const b2r_c51_args *args, cudaStream_t stream, b2r_tree *tree,
                     const int32_t *indices);
+// c51.cu: the loss in two halves (the fused step): what depends on the network outputs
+// alone, over `rows` rows, into scratch ([rows][c51_scratch_floats_per_row()] floats),
+// signalling `sync` when done ...
+struct PreSync;
+bool c51_can_split(const b2r_c51_args *args);
+int c51_scratch_floats_per_row();
+int c51_pre_launch(const b2r_c51_args *args, int rows, float *scratch, const PreSync &sync,
+                   cudaStream_t stream, int *have_stats);
+// ... and the tail over the sampled rows.  err (nullable): asynchronous error latch.
+int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_stats,
+                    cudaStream_t stream, int64_t *err);
 
 }  // namespace b2r

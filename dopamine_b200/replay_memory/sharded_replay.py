@@ -176,11 +176,21 @@ class ShardedPrioritizedReplay(object):
         priorities.data_ptr(), _native.current_stream()))
 
 
+def share_bound(global_batch, world, slack=1.5, extra=32):
+  """Rows a rank provides for its share of a global batch: `slack` times the even share
+  plus `extra`, never more than the global batch.  A shard serves
+  global_batch * total_g / sum(totals) strata, so shards fed alike stay within a few rows
+  of the even share; a step that outgrows the bound latches B2R_ERR_UNSUPPORTED."""
+  even = -(-int(global_batch) // int(world))
+  return min(int(global_batch), int(np.ceil(slack * even)) + int(extra))
+
+
 class ShardedStep(object):
   """bench.py's N>1 step: all-gather totals -> sharded sample -> gather -> C51
   loss/priorities -> write-back, for a global batch spread over the ranks."""
 
-  def __init__(self, workload, global_batch, world, rank, dist, exchange=None):
+  def __init__(self, workload, global_batch, world, rank, dist, exchange=None,
+               max_rows=None):
     import torch
     self.wl = workload
     self.global_batch = global_batch
@@ -188,9 +198,15 @@ class ShardedStep(object):
     self.exchange = exchange
     self.sharded = ShardedPrioritizedReplay(
         workload.mem, rank=rank, world_size=world, seed=1234, exchange=exchange)
-    t, b, c = workload.plan(global_batch)
+    # Outputs, logits and launches are sized by a bound on the LOCAL share (peer
+    # exchange path), so that a rank's memory and grids do not grow with the world size.
+    self.max_rows = global_batch
+    if exchange is not None:
+      self.max_rows = (share_bound(global_batch, world) if max_rows is None
+                       else min(int(max_rows), global_batch))
+    t, b, c = workload.plan(self.max_rows)
     self.t, self.b, self.c = t, b, c
-    self.slots = torch.empty(global_batch, dtype=torch.int32, device='cuda')
+    self.slots = torch.empty(self.max_rows, dtype=torch.int32, device='cuda')
     c.batch_count = self.sharded._count.data_ptr()  # pylint: disable=protected-access
     c.mean_weighted_loss = None
     self.lib = workload.lib
@@ -207,7 +223,7 @@ class ShardedStep(object):
       nat.check(lib.b2r_train_step_sharded_device(
           self.h, self.exchange._h, self.global_batch, sh.seed, 0,  # pylint: disable=protected-access
           ctypes.byref(self.b), ctypes.byref(self.c), self.slots.data_ptr(),
-          count_ptr, stream))
+          count_ptr, self.max_rows, stream))
       return
     totals = sh.totals()
     nat.check(lib.b2r_sample_indices_sharded_device(
@@ -221,6 +237,40 @@ class ShardedStep(object):
     nat.check(lib.b2r_set_priority_device_counted(
         self.h, self.global_batch, count_ptr, self.t['indices'].data_ptr(),
         self.t['priorities'].data_ptr(), stream))
+
+  def check_partition(self, max_valid_checks=512):
+    """After a step has run on EVERY rank: all-gathers each rank's (count, strata) and
+    asserts that the ranks' strata partition range(global_batch) exactly — no stratum
+    served twice or by nobody — and that this rank's rows are valid transitions of its
+    own shard (circular_replay_buffer.py:381-414).  This is the check of the real
+    multi-process exchange (CUDA-IPC mailboxes over NVLink): the ranks agree on the
+    apportioning only if every one of them read the same G totals.  Returns the row
+    counts of all ranks."""
+    import torch
+    dist, world = self.dist, self.sharded.world
+    torch.cuda.synchronize()
+    count = int(self.sharded._count.item())  # pylint: disable=protected-access
+    cap = int(self.slots.numel())
+    assert 0 <= count <= cap, (count, cap)
+    send = torch.full((cap + 1,), -1, dtype=torch.int32, device='cuda')
+    send[0] = count
+    send[1:1 + count] = self.slots[:count]
+    recv = torch.empty(world * (cap + 1), dtype=torch.int32, device='cuda')
+    dist.all_gather_into_tensor(recv, send)
+    recv = recv.cpu().numpy().reshape(world, cap + 1)
+    counts = [int(c) for c in recv[:, 0]]
+    strata = np.concatenate([recv[g, 1:1 + counts[g]] for g in range(world)])
+    assert sum(counts) == self.global_batch, (counts, self.global_batch)
+    assert np.array_equal(np.sort(strata), np.arange(self.global_batch)), (
+        'the ranks\' strata do not partition the global batch')
+    for g in range(world):  # rank-order scan: a rank's strata are ascending
+      mine = recv[g, 1:1 + counts[g]]
+      assert np.all(np.diff(mine) > 0), g
+    indices = self.t['indices'][:count].cpu().numpy()
+    mem = self.sharded.memory
+    for index in indices[:max_valid_checks]:
+      assert mem.is_valid_transition(int(index)), int(index)
+    return counts
 
   def launches_per_step(self):
     if self._launches is None:

@@ -417,16 +417,38 @@ int b2r_train_step_device(b2r_buffer *buf, int32_t batch, uint64_t seed,
                           uint64_t offset, const b2r_batch *out,
                           const b2r_c51_args *c51, b2r_stream stream);
 
+/* Deferred frame copies.  By default the frame-stack copies of b2r_train_step_device are
+ * joined into `stream` before the call returns.  With on != 0 they are joined only by
+ * b2r_join_frames (or by the next flush of staged add()s, which overwrite ring slots the
+ * copies may still read): the NEXT step's sampler -> loss -> write-back chain, which
+ * needs this step's priorities but not its frames, then runs beside the HBM-bound copies
+ * of this step — the analogue of the reference's staged prefetch (use_staging,
+ * CRB:728-779), except that the tree sees exactly the sequential order sample(n),
+ * set_priority(n), sample(n+1).  The copies of consecutive steps stay in order among
+ * themselves (they share the output buffers in `out`).  The caller joins before it
+ * reads state / next_state, before it ends a stream capture, and before destroying
+ * `out`'s buffers.  out->indices is valid as soon as the step's sampler has run; the
+ * copies read a private copy of it. */
+int b2r_set_deferred_frames(b2r_buffer *buf, int32_t on);
+int b2r_join_frames(b2r_buffer *buf, b2r_stream stream);
+
 /* The same for one shard of a sharded replay: global
  * stratified batch of `global_batch` strata over `exchange`'s ranks, this rank's
  * rows compacted at the front of `out` (*out_count of them, device; out_slots[r] =
  * stratum of row r), loss and write-back over those rows only.  The single
- * exchange of shard totals happens inside the sampling kernel. */
+ * exchange of shard totals happens inside the sampling kernel.
+ * max_rows: rows that `out`, `out_slots`, the logits and the outputs of `c51` hold — a
+ * bound on this rank's share of the global batch chosen by the caller (its expected
+ * share is global_batch / world when the shards' totals are alike); every launch
+ * behind the sampler and every buffer is sized by it, so a rank's memory and grids do
+ * not grow with the number of ranks.  A step whose share exceeds it serves its first
+ * max_rows strata and latches B2R_ERR_UNSUPPORTED (b2r_check).  0 = global_batch. */
 int b2r_train_step_sharded_device(b2r_buffer *buf, b2r_exchange *exchange,
                                   int32_t global_batch, uint64_t seed,
                                   uint64_t offset, const b2r_batch *out,
                                   const b2r_c51_args *c51, int32_t *out_slots,
-                                  int32_t *out_count, b2r_stream stream);
+                                  int32_t *out_count, int32_t max_rows,
+                                  b2r_stream stream);
 
 /* Host-facing, pipelined form of the same step: what an agent's training loop
  * calls once per update with the network outputs in HOST memory
@@ -447,8 +469,11 @@ typedef struct {
   int32_t logit_rows;      /* rows of each logits tensor copied per step; 0 = batch.
                               A sharded trainer's batch is the GLOBAL batch, but a
                               rank's network only produces logits for the rows it
-                              serves: the caller passes (logit_rows, A, N) tensors and
-                              guarantees that a step never serves more rows          */
+                              serves: the caller passes (logit_rows, A, N) tensors.
+                              It is the max_rows of b2r_train_step_sharded_device:
+                              every device buffer, the loss_out of a step and the
+                              launches behind the sampler are sized by it, and a step
+                              whose share exceeds it latches B2R_ERR_UNSUPPORTED     */
 } b2r_trainer_config;
 
 int b2r_trainer_create(b2r_buffer *buf, const b2r_trainer_config *config,

@@ -57,6 +57,10 @@ def main():
       wl.fused = False
       wl.step(batch)
 
+    def fused_deferred():
+      wl.fused = True
+      wl.step(batch)
+
     # the latency chain alone (fused call without the frame outputs) and the sampler
     # followed by the frame copies alone
     b_noframes = type(b).from_buffer_copy(b)
@@ -80,9 +84,16 @@ def main():
     for name, fn in (('sample_us', sample), ('gather_us', gather),
                      ('c51_loss_us', loss), ('write_back_us', write_back),
                      ('step_unfused_us', unfused), ('step_fused_us', fused),
-                     ('chain_only_us', chain_only), ('sample_gather_us', sample_gather)):
+                     ('chain_only_us', chain_only), ('sample_gather_us', sample_gather),
+                     ('step_fused_deferred_us', fused_deferred)):
+      deferred = fn is fused_deferred
+      if deferred:
+        wl.set_deferred(True)
       ms = bench.time_graph_or_eager(torch, fn, reps, 5, True,
-                                     per_graph=bench.steps_per_graph(reps, a.per_graph))
+                                     per_graph=bench.steps_per_graph(reps, a.per_graph),
+                                     finish=wl.join if deferred else None)
+      if deferred:
+        wl.set_deferred(False)
       row[name] = round(ms * 1e3 / reps, 2)
     row['parts_sum_us'] = round(row['sample_us'] + row['gather_us'] +
                                 row['c51_loss_us'] + row['write_back_us'], 2)

@@ -18,8 +18,9 @@ NAMES = {
                16: 'S rows written (CTA 0)', 17: 'S last CTA: alone', 18: 'S invalid list',
                19: 'S fix-ups done', 20: 'S END'},
     'gather': {0: 'G start (CTA 0)', 1: 'G acquired', 5: 'G CTA 0 stored', 6: 'G END'},
-    'c51': {0: 'L start (CTA per row)', 1: 'L acquired', 3: 'L softmaxes', 5: 'L projection',
-            8: 'L END', 10: 'L start (warp per row)', 11: 'L acquired', 12: 'L END'},
+    'c51': {0: 'L-pre start', 1: 'L-pre acquired', 3: 'L softmaxes', 5: 'L projection',
+            8: 'L-pre END', 10: 'L-tail start', 11: 'L-tail acquired', 12: 'L-tail loss END',
+            9: 'L-tail tree END', 13: 'L-tail row scalars in', 14: 'L-tail log-softmax done'},
     'tree': {5: 'T tiny start', 6: 'T tiny acquired', 7: 'T tiny END', 12: 'P presort start',
              14: 'P presort END', 13: 'T apply start', 10: 'T leaf deltas published',
              11: 'T levels released', 15: 'T apply END'},

@@ -91,8 +91,8 @@ def _check_step(gpu, mem, tree, cols, cap, horizon, got, out, online, target):
   ref = c51_port.rainbow_update(want[2], want[6], want[1], probs, online, target,
                                 update_horizon=horizon)
   for key in ('loss', 'priorities', 'weights'):
-    np.testing.assert_allclose(out[key].cpu().numpy(), ref[key], rtol=2e-6,
-                               atol=1e-6, err_msg=key)
+    np.testing.assert_allclose(out[key].cpu().numpy(), ref[key], rtol=1e-6,
+                               atol=1e-7, err_msg=key)
   pr = out['priorities'].cpu().numpy()
   tree.set_seq(idx, pr.astype(np.float64))
   return idx
@@ -154,6 +154,46 @@ def test_fused_step_equals_separate_calls(gpu, batch):
               out_b[key].cpu().numpy().tobytes()), key
   for la, lb in zip(mem_a.sum_tree.nodes, mem_b.sum_tree.nodes):
     assert np.array_equal(la.view(np.uint64), lb.view(np.uint64))
+
+
+@pytest.mark.parametrize('batch', [32, 600])
+def test_deferred_frame_copies_equal_joined_steps(gpu, batch):
+  """b2r_set_deferred_frames: the frame copies of a step are joined by b2r_join_frames
+  (or by the next flush of staged adds) instead of by the call itself, so the next
+  step's chain runs beside them.  Twin buffers, same seed: every step's batch — frames
+  included, read after the join at the END of the run — losses and the final tree are
+  bit-identical to the joined mode; an add() between two steps joins by itself."""
+  torch, native = gpu.torch, gpu.native
+  lib = native.lib()
+  cap = 100000
+  mem_a, _, _ = _filled(gpu, cap, batch, seed=12)
+  mem_b, _, _ = _filled(gpu, cap, batch, seed=12)
+  native.check(lib.b2r_set_deferred_frames(mem_a._h, 1))
+  rng = np.random.RandomState(3)
+  support = gpu.ra.make_support(10., ATOMS)
+  got_a, got_b = [], []
+  for step in range(5):
+    online = torch.as_tensor(rng.randn(batch, ACTIONS, ATOMS).astype(np.float32),
+                             device='cuda')
+    target = torch.as_tensor(rng.randn(batch, ACTIONS, ATOMS).astype(np.float32),
+                             device='cuda')
+    got_a.append(gpu.ra.train_step(mem_a, online, target, support, 0.99 ** 3))
+    got_b.append(gpu.ra.train_step(mem_b, online, target, support, 0.99 ** 3))
+    if step == 2:  # staged adds: their flush waits for the copies still in flight
+      for mem in (mem_a, mem_b):
+        for k in range(3):
+          mem.add(np.full((84, 84), 10 * step + k, np.uint8), k, 0.5, 0, 1.0)
+  native.check(lib.b2r_join_frames(mem_a._h, native.current_stream()))
+  torch.cuda.synchronize()
+  for (batch_a, out_a), (batch_b, out_b) in zip(got_a, got_b):
+    for a, b in zip(batch_a, batch_b):
+      assert a.cpu().numpy().tobytes() == b.cpu().numpy().tobytes()
+    for key in ('loss', 'priorities', 'weights'):
+      assert out_a[key].cpu().numpy().tobytes() == out_b[key].cpu().numpy().tobytes()
+  for la, lb in zip(mem_a.sum_tree.nodes, mem_b.sum_tree.nodes):
+    assert np.array_equal(la.view(np.uint64), lb.view(np.uint64))
+  native.check(lib.b2r_check(mem_a._h, native.current_stream()))
+  native.check(lib.b2r_set_deferred_frames(mem_a._h, 0))
 
 
 def test_fused_step_in_cuda_graph(gpu):
@@ -372,12 +412,14 @@ def test_peer_exchange_times_out_instead_of_hanging(gpu):
   assert 'did not publish' in gpu.native.last_error()
 
 
-@pytest.mark.parametrize('global_batch', [256, 2048])
-def test_sharded_fused_step_matches_oracles(gpu, global_batch):
+@pytest.mark.parametrize('global_batch,bounded', [(256, False), (2048, False),
+                                                  (256, True), (2048, True)])
+def test_sharded_fused_step_matches_oracles(gpu, global_batch, bounded):
   """b2r_train_step_sharded_device on 4 emulated ranks (one sampling CTA up to a
   global batch of 256, tiles over each rank's stratum range above): each rank's rows
   (batch columns at its indices, losses, write-back) against the oracles, the rows of
-  all ranks partitioning the global batch."""
+  all ranks partitioning the global batch.  bounded: outputs, logits and launches sized
+  by a bound on the rank's share (max_rows) instead of the global batch."""
   import ctypes
   from dopamine_b200.replay_memory import sharded_replay
   torch, native = gpu.torch, gpu.native
@@ -388,18 +430,20 @@ def test_sharded_fused_step_matches_oracles(gpu, global_batch):
   rng = np.random.RandomState(8)
   support = gpu.ra.make_support(10., ATOMS)
   outs = []
+  # (shard 1 is "hot": it serves well over its even share)
+  rows = global_batch * 5 // 8 if bounded else global_batch
   for g in range(num_shards):
     mem = shards[g][0]
-    _, arrays, batch = mem._alloc_outputs(global_batch, True)
+    _, arrays, batch = mem._alloc_outputs(rows, True)
     outs.append(dict(
         arrays=arrays, batch=batch,
-        loss={k: torch.zeros(global_batch, dtype=torch.float32, device='cuda')
+        loss={k: torch.zeros(rows, dtype=torch.float32, device='cuda')
               for k in ('loss', 'priorities', 'weights')},
-        slots=torch.zeros(global_batch, dtype=torch.int32, device='cuda'),
+        slots=torch.zeros(rows, dtype=torch.int32, device='cuda'),
         count=torch.zeros(1, dtype=torch.int32, device='cuda')))
   for step in range(3):
-    online = rng.randn(global_batch, ACTIONS, ATOMS).astype(np.float32)
-    target = rng.randn(global_batch, ACTIONS, ATOMS).astype(np.float32)
+    online = rng.randn(rows, ACTIONS, ATOMS).astype(np.float32)
+    target = rng.randn(rows, ACTIONS, ATOMS).astype(np.float32)
     d_online = torch.as_tensor(online, device='cuda')
     d_target = torch.as_tensor(target, device='cuda')
     for g in range(num_shards):
@@ -419,9 +463,10 @@ def test_sharded_fused_step_matches_oracles(gpu, global_batch):
       native.check(lib.b2r_train_step_sharded_device(
           mem._h, exchanges[g]._h, global_batch, 77, step, ctypes.byref(o['batch']),
           ctypes.byref(args), o['slots'].data_ptr(), o['count'].data_ptr(),
-          native.current_stream()))
+          rows if bounded else 0, native.current_stream()))
       torch.cuda.synchronize()
       n = int(o['count'].cpu()[0])
+      assert n <= rows
       served += o['slots'][:n].cpu().numpy().tolist()
       if n == 0:
         continue
@@ -433,6 +478,58 @@ def test_sharded_fused_step_matches_oracles(gpu, global_batch):
   for mem, tree, _ in shards:
     for l, level in enumerate(mem.sum_tree.nodes):
       assert np.array_equal(level.view(np.uint64), tree.level(l).view(np.uint64)), l
+
+
+@pytest.mark.parametrize('global_batch', [64, 1024, 16384])
+def test_sharded_step_share_beyond_max_rows_is_latched(gpu, global_batch):
+  """A rank whose share of the global batch exceeds max_rows serves exactly max_rows
+  rows (its first strata), writes nothing beyond its buffers (canary rows stay) and
+  latches B2R_ERR_UNSUPPORTED.  64: one sampling CTA; 1024: warp sampler over the rank's
+  range; 16384: tiled thread sampler."""
+  import ctypes
+  from dopamine_b200.replay_memory import sharded_replay
+  torch, native = gpu.torch, gpu.native
+  lib = native.lib()
+  world, cap = 2, 20000
+  shards = [_filled(gpu, cap, 32, seed=70 + g, hot=False) for g in range(world)]
+  exchanges = sharded_replay.PeerExchange.emulated(world)
+  rows = global_batch // 4  # each rank's share is about half of the batch
+  support = gpu.ra.make_support(10., ATOMS)
+  for g in range(world):
+    exchanges[g].publish(shards[g][0])
+  for g in range(world):
+    mem = shards[g][0]
+    _, arrays, batch = mem._alloc_outputs(rows + 8, True)
+    canary = torch.full((rows + 8,), -7, dtype=torch.int32, device='cuda')
+    arrays[7].copy_(canary)  # indices
+    slots = canary.clone()
+    count = torch.zeros(1, dtype=torch.int32, device='cuda')
+    logits = torch.zeros(rows + 8, ACTIONS, ATOMS, dtype=torch.float32, device='cuda')
+    loss = {k: torch.full((rows + 8,), -7., dtype=torch.float32, device='cuda')
+            for k in ('loss', 'priorities', 'weights')}
+    args = native.C51Args()
+    args.batch, args.num_actions, args.num_atoms = global_batch, ACTIONS, ATOMS
+    args.cumulative_gamma = float(np.float32(0.99 ** 3))
+    args.support = support.data_ptr()
+    args.online_logits = args.target_logits = logits.data_ptr()
+    args.loss = loss['loss'].data_ptr()
+    args.priorities = loss['priorities'].data_ptr()
+    args.weights = loss['weights'].data_ptr()
+    native.check(lib.b2r_train_step_sharded_device(
+        mem._h, exchanges[g]._h, global_batch, 5, 0, ctypes.byref(batch),
+        ctypes.byref(args), slots.data_ptr(), count.data_ptr(), rows,
+        native.current_stream()))
+    torch.cuda.synchronize()
+    assert int(count.cpu()[0]) == rows
+    got_slots = slots.cpu().numpy()
+    first = 0 if g == 0 else int(got_slots[0])
+    assert np.array_equal(got_slots[:rows], np.arange(first, first + rows))
+    assert (got_slots[rows:] == -7).all()
+    assert (arrays[7].cpu().numpy()[rows:] == -7).all()
+    assert (loss['loss'].cpu().numpy()[rows:] == -7.).all()
+    assert (loss['loss'].cpu().numpy()[:rows] > 0.).all()
+    status = lib.b2r_check(mem._h, native.current_stream())
+    assert status == native.ERR_UNSUPPORTED, (status, native.last_error())
 
 
 def test_tma_gather_variant_passes_the_gather_parity_suite():

@@ -113,12 +113,12 @@ def test_c51_kernel_matches_reference_code(cuda, case):
   np.testing.assert_allclose(got['target'].cpu().numpy(), g[p + 'target'], rtol=1e-6,
                              atol=1e-6)
   weighted = (got['weights'] * got['loss']).cpu().numpy()
-  np.testing.assert_allclose(weighted, g[p + 'weighted_loss'], rtol=2e-6, atol=1e-6)
+  np.testing.assert_allclose(weighted, g[p + 'weighted_loss'], rtol=1e-6, atol=1e-7)
   np.testing.assert_allclose(float(got['mean_weighted_loss']), g[p + 'mean_loss'],
                              rtol=1e-5)
   if prioritized:
     np.testing.assert_allclose(got['priorities'].cpu().numpy(), g[p + 'priorities'],
-                               rtol=2e-6, atol=1e-6)
+                               rtol=1e-6, atol=1e-7)
   else:
     assert (got['weights'].cpu().numpy() == 1.0).all()
 
