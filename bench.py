@@ -1071,7 +1071,8 @@ def main():
   # N = 1, fused step: the frame copies of step n run beside the chain of step n + 1 and
   # are joined once per timed group of steps (b2r_set_deferred_frames), up to the batch
   # where the copies saturate HBM and anything beside them only slows both down.
-  defer = lambda b: world == 1 and wl.fused and not args.no_defer and b <= DEFER_MAX_BATCH
+  defer = lambda b: (wl.fused and not args.no_defer and b <= DEFER_MAX_BATCH and
+                     (world == 1 or args.exchange == 'p2p'))
   finish_of = lambda b: wl.join if defer(b) else None
   wl.set_deferred(defer(args.batch))
 
@@ -1092,7 +1093,7 @@ def main():
     ms = float(t.item())
   _native.check(_native.lib().b2r_check(wl.h, _native.current_stream()))
   shard_check = None
-  if world > 1:
+  if world > 1 and not os.environ.get('B2R_DEBUG_XCHG_NOWAIT'):
     # every rank has run the same steps: the last one's rows must partition the global
     # batch across the ranks (asserts; see ShardedStep.check_partition)
     counts = sharded.check_partition()
@@ -1127,6 +1128,10 @@ def main():
                   if world > 1 and args.exchange == 'p2p' else
                   '; NCCL all-gather of shard totals' if world > 1 else ''),
           'rng': 'device Philox4x32-10',
+          'logits': 'inputs of the step (random, resident in HBM): the path is timed '
+                    'without a network between gather and loss, as the metric names it; '
+                    'full_train_step is the same kernels with the cuDNN networks between '
+                    'them',
           'cpu_affinity': ('GPU-local NUMA node (%d cores per rank)' % numa_cpus
                            if numa_cpus else 'unbound'),
       },
@@ -1146,13 +1151,16 @@ def main():
       st = sharded_replay.ShardedStep(wl, b * world, world, rank, dist,
                                       exchange=exchange)
       k = max(20, min(args.steps, 300))
+      wl.set_deferred(defer(b))
       ms_b = time_graph_or_eager(torch, st.step, k, 5, use_graph, dist,
                                  per_graph=steps_per_graph(k, args.steps_per_graph),
-                                 min_ms=MIN_TIMED_MS)
+                                 min_ms=MIN_TIMED_MS, finish=finish_of(b))
+      wl.set_deferred(False)
       t = torch.tensor([ms_b], device='cuda')
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
       ms_b = float(t.item())
-      sweep_multi[str(b)] = {'global_batch': b * world,
+      sweep_multi[str(b)] = {'global_batch': b * world, 'rows_per_rank_bound': st.max_rows,
+                             'frame_copies': 'deferred' if defer(b) else 'joined every step',
                              'value': round(b * world * k / (ms_b * 1e-3), 1),
                              'ms_per_step': round(ms_b / k, 5)}
   # N > 1: the end-to-end loop and the full train step run on every rank together

@@ -132,6 +132,7 @@ class TrainerConfig(ctypes.Structure):
 
 
 P = ctypes.POINTER
+c_size_t = ctypes.c_size_t
 
 # name -> (restype, argtypes); must list every symbol of include/b200_replay.h.
 class IqnArgs(ctypes.Structure):
@@ -225,6 +226,12 @@ SIGNATURES = {
     'b2r_dqn_loss': (c_int, [P(DqnArgs), c_void_p]),
     'b2r_train_step_device': (c_int, [c_void_p, c_int32, c_uint64, c_uint64,
                                       P(Batch), P(C51Args), c_void_p]),
+    'b2r_stack_to_planes_device': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32,
+                                           c_int32, c_void_p]),
+    'b2r_add_batch': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                              P(c_void_p), c_void_p, c_int, P(c_int64), c_void_p]),
+    'b2r_gather_slab': (c_int, [c_void_p, c_int32, c_void_p, c_int32, P(Batch), c_void_p,
+                                c_size_t, P(Batch), P(c_size_t), c_void_p]),
     'b2r_set_deferred_frames': (c_int, [c_void_p, c_int32]),
     'b2r_join_frames': (c_int, [c_void_p, c_void_p]),
     'b2r_train_step_sharded_device': (c_int, [

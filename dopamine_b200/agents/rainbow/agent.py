@@ -39,6 +39,24 @@ def _same_pad(size, kernel, stride):
   return total // 2, total - total // 2
 
 
+def network_input(state, half=False):
+  """uint8 (B, H, W, stack) CUDA frame stacks -> (B, stack, H, W) float32 (or float16)
+  planes of value / 255: the reference's `tf.cast(state, tf.float32)`, `tf.div(net,
+  255.)` (atari_lib.py:124-125) and the layout of the first cuDNN convolution in ONE
+  hand-written pass (b2r_stack_to_planes_device) instead of permute + cast + division."""
+  torch = _torch()
+  from dopamine_b200 import _native  # pylint: disable=g-import-not-at-top
+  assert state.is_cuda and state.dtype == torch.uint8 and state.dim() == 4
+  state = state.contiguous()
+  b, h, w, stack = state.shape
+  out = torch.empty((b, stack, h, w), device=state.device,
+                    dtype=torch.float16 if half else torch.float32)
+  _native.check(_native.lib().b2r_stack_to_planes_device(
+      state.data_ptr(), out.data_ptr(), b, h * w, stack, int(bool(half)),
+      _native.current_stream()))
+  return out
+
+
 def make_rainbow_network(num_actions, num_atoms, observation_shape=(84, 84),
                          stack_size=4):
   """atari_lib.rainbow_network (atari_lib.py:108-144): uint8 (B, H, W, stack) in,
@@ -72,7 +90,7 @@ def make_rainbow_network(num_actions, num_atoms, observation_shape=(84, 84),
         nn.init.zeros_(m.bias)
 
     def forward(self, state):
-      x = state.permute(0, 3, 1, 2).to(torch.float32).div_(255.)  # atari_lib.py:124-125
+      x = network_input(state)  # atari_lib.py:124-125 (cast, / 255) + NCHW, one kernel
       for pad, conv in zip(self.pads, self.convs):
         x = torch.relu(conv(torch.nn.functional.pad(x, pad)))
       # slim.flatten works on NHWC; keep that ordering of the 7 744 features
@@ -81,6 +99,70 @@ def make_rainbow_network(num_actions, num_atoms, observation_shape=(84, 84),
       return self.fc2(x).view(-1, num_actions, num_atoms)
 
   return RainbowNetwork()
+
+
+def make_tf_adam(params, lr, beta1=0.9, beta2=0.999, epsilon=1e-8, capturable=False):
+  """tf.train.AdamOptimizer as the reference configures it (rainbow_agent.py:69-71,
+  rainbow.gin:21-25: learning_rate 6.25e-5, epsilon 1.5e-4).
+
+  TensorFlow 1.x applies   lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t),
+                           theta -= lr_t * m_t / (sqrt(v_t) + epsilon)
+  — its `epsilon` is the "epsilon hat" of Kingma & Ba, added to the UNcorrected sqrt(v_t).
+  torch.optim.Adam adds eps to the bias-corrected sqrt(v_t / (1 - beta2^t)) instead, which
+  with Rainbow's large epsilon makes the first thousands of updates up to 30x larger
+  (t = 1: sqrt(1 - beta2) = 0.032).  This optimizer implements TensorFlow's form with
+  multi-tensor (`_foreach`) ops; with `capturable` the step count lives on the device so
+  that the update can be captured in a CUDA graph, otherwise lr_t is a host float."""
+  torch = _torch()
+
+  class TFAdam(torch.optim.Optimizer):
+
+    def __init__(self):
+      super().__init__(list(params), dict(lr=lr, beta1=beta1, beta2=beta2,
+                                          epsilon=epsilon))
+      self._t = None
+      self._host_t = 0
+
+    @torch.no_grad()
+    def step(self, closure=None):
+      assert closure is None
+      for group in self.param_groups:
+        ps = [p for p in group['params'] if p.grad is not None]
+        if not ps:
+          continue
+        grads = [p.grad for p in ps]
+        ms, vs = [], []
+        for p in ps:
+          state = self.state[p]
+          if not state:
+            state['m'] = torch.zeros_like(p)
+            state['v'] = torch.zeros_like(p)
+          ms.append(state['m'])
+          vs.append(state['v'])
+        b1, b2 = group['beta1'], group['beta2']
+        if capturable:
+          if self._t is None:
+            self._t = torch.zeros((), dtype=torch.float64, device=ps[0].device)
+          self._t += 1
+          # lr_t in float64 on the device, applied as a float32 scalar tensor
+          lr_t = (group['lr'] * torch.sqrt(1.0 - b2 ** self._t) /
+                  (1.0 - b1 ** self._t)).to(torch.float32)
+        else:
+          self._host_t += 1
+          lr_t = float(np.float32(group['lr'] * math.sqrt(1.0 - b2 ** self._host_t) /
+                                  (1.0 - b1 ** self._host_t)))
+        torch._foreach_mul_(ms, b1)
+        torch._foreach_add_(ms, grads, alpha=1.0 - b1)
+        torch._foreach_mul_(vs, b2)
+        torch._foreach_addcmul_(vs, grads, grads, value=1.0 - b2)
+        denom = torch._foreach_sqrt(vs)
+        torch._foreach_add_(denom, group['epsilon'])
+        update = torch._foreach_div(ms, denom)
+        torch._foreach_mul_(update, lr_t)
+        torch._foreach_sub_(ps, update)
+      return None
+
+  return TFAdam()
 
 
 class RainbowLearner(object):
@@ -130,9 +212,9 @@ class RainbowLearner(object):
     self._cuda_graph = bool(cuda_graph)
     self._graph = None
     self._static_loss = None
-    self.optimizer = torch.optim.Adam(self.online.parameters(), lr=learning_rate,
-                                      eps=adam_epsilon,  # rainbow.gin:21-25
-                                      capturable=self._cuda_graph)
+    self.optimizer = make_tf_adam(self.online.parameters(), lr=learning_rate,
+                                  epsilon=adam_epsilon,  # rainbow.gin:21-25
+                                  capturable=self._cuda_graph)
     self.training_steps = 0
     self.updates = 0
 

@@ -248,6 +248,17 @@ def train_step(memory, online_logits, target_logits, support, cumulative_gamma,
   stream beside the loss and the write-back (they rejoin the current stream
   before this returns).
 
+  NOTE — what this call is for.  The logits are INPUTS: row b of both tensors is paired
+  with whatever transition the sampler draws for row b, so they cannot be the networks'
+  outputs ON that transition (the reference runs the networks on the sampled batch,
+  rainbow_agent.py:253-305).  This is the replay-and-update path of north_star measured
+  without a network in the middle (bench.py's `value` / `e2e`, and the parity tests, which
+  only need the arithmetic); priorities written by it are meaningful only if the caller's
+  logits do not depend on the batch.  A learner uses the same kernels in the reference's
+  order — `memory.sample_transition_batch()` -> networks -> `c51_loss` ->
+  `memory.set_priority` — as `agent.RainbowLearner._update` does; bench.py reports that
+  loop as `full_train_step`.
+
   Args:
     memory: OutOfGraphPrioritizedReplayBuffer (uint8 terminals, f32 rewards,
       scalar int32 actions).
@@ -303,6 +314,10 @@ class ReplayTrainer(object):
   `memory.add()`s, runs sample -> C51 loss -> priority write-back on the device and
   hands back the per-row losses of the step queued `pipeline_depth` calls earlier,
   so the host never waits for the step it has just queued.
+
+  Like `train_step`, this takes the logits as inputs BEFORE the batch is sampled: it is
+  the host-facing harness of the replay-and-update path (bench.py's `e2e`), not a
+  learner — see the note in `train_step`; `agent.RainbowLearner` is the learner.
   """
 
   def __init__(self, memory, num_actions, num_atoms=51, vmax=10.,

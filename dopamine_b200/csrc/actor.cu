@@ -12,6 +12,8 @@
 // host.  Latency-bound (one small launch); the point is what it removes from the host.
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cstring>
 #include <new>
 
@@ -71,6 +73,74 @@ struct b2r_actor {
 
 using b2r::as_stream;
 using b2r::fail;
+
+namespace b2r {
+
+// Network input: uint8 frame stacks (B, pixels, S) with the stack axis innermost — what
+// the replay gather and the actor state hold, the layout the reference feeds its
+// network — to (B, S, pixels) planes of float(u8) / 255 (atari_lib.py:124-125:
+// tf.cast(state, tf.float32) then tf.div(net, 255.), true division), the layout cuDNN's
+// first convolution reads.  One pass, 16-byte loads and stores: 4 B read and
+// 4 x sizeof(T) B written per pixel, where the eager tensor ops (permute, to, div_) move
+// about three times as much.  T = float (the reference's arithmetic, bit for bit) or
+// __half (the f32 quotient rounded once to nearest: the input of a half-precision conv).
+template <typename T>
+struct Quad;
+template <>
+struct Quad<float> {
+  using type = float4;
+  static __device__ __forceinline__ float4 make(float a, float b, float c, float d) {
+    return make_float4(a, b, c, d);
+  }
+};
+template <>
+struct Quad<__half> {
+  using type = uint2;
+  static __device__ __forceinline__ uint2 make(float a, float b, float c, float d) {
+    const __half2 lo = __halves2half2(__float2half_rn(a), __float2half_rn(b));
+    const __half2 hi = __halves2half2(__float2half_rn(c), __float2half_rn(d));
+    uint2 o;
+    o.x = *reinterpret_cast<const unsigned int *>(&lo);
+    o.y = *reinterpret_cast<const unsigned int *>(&hi);
+    return o;
+  }
+};
+
+__device__ __forceinline__ float unit_byte(uint32_t word, int k) {
+  return __fdiv_rn((float)((word >> (8 * k)) & 0xffu), 255.0f);
+}
+
+// S == 4, pixels % 4 == 0: thread = 4 pixels (one 16-byte load, four 4-element stores).
+template <typename T>
+__global__ void __launch_bounds__(256)
+stack4_to_planes_kernel(const uint4 *__restrict__ in, T *__restrict__ out, int64_t quads,
+                        int64_t pixels) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= quads) return;
+  const uint4 v = __ldg(in + q);
+  const int64_t per_image = pixels / 4;
+  const int64_t image = q / per_image, p0 = (q - image * per_image) * 4;
+  T *base = out + image * 4 * pixels + p0;
+  using Q = Quad<T>;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)  // plane k = stack position k of the 4 pixels
+    *reinterpret_cast<typename Q::type *>(base + k * pixels) =
+        Q::make(unit_byte(v.x, k), unit_byte(v.y, k), unit_byte(v.z, k), unit_byte(v.w, k));
+}
+
+template <typename T>
+__global__ void stack_to_planes_generic_kernel(const uint8_t *__restrict__ in,
+                                               T *__restrict__ out, int64_t total,
+                                               int64_t pixels, int stack) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // output element
+  if (e >= total) return;
+  const int64_t image = e / (pixels * stack), r = e - image * pixels * stack;
+  const int64_t k = r / pixels, p = r - k * pixels;
+  const float v = __fdiv_rn((float)in[(image * pixels + p) * stack + k], 255.0f);
+  out[e] = (T)v;
+}
+
+}  // namespace b2r
 
 extern "C" {
 
@@ -166,6 +236,41 @@ int b2r_actor_record(b2r_actor *a, void *state, const void *observation,
   B2R_CUDA(cudaEventRecord(a->done[k], s));
   a->pending[k] = true;
   ++a->recorded;
+  return B2R_OK;
+}
+
+int b2r_stack_to_planes_device(const void *stacks, void *planes, int64_t images,
+                                int64_t pixels, int32_t stack_size, int32_t half_out,
+                                b2r_stream stream) {
+  if (!stacks || !planes || images < 0 || pixels <= 0 || stack_size <= 0)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "stack_to_planes: bad argument");
+  if (images == 0) return B2R_OK;
+  cudaStream_t s = as_stream(stream);
+  const bool aligned = (reinterpret_cast<uintptr_t>(stacks) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(planes) & 15) == 0;
+  if (stack_size == 4 && pixels % 4 == 0 && aligned) {
+    const int64_t quads = images * pixels / 4;
+    const unsigned grid = (unsigned)((quads + 255) / 256);
+    if (half_out)
+      b2r::stack4_to_planes_kernel<__half><<<grid, 256, 0, s>>>(
+          static_cast<const uint4 *>(stacks), static_cast<__half *>(planes), quads, pixels);
+    else
+      b2r::stack4_to_planes_kernel<float><<<grid, 256, 0, s>>>(
+          static_cast<const uint4 *>(stacks), static_cast<float *>(planes), quads, pixels);
+  } else {
+    const int64_t total = images * pixels * stack_size;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (half_out)
+      b2r::stack_to_planes_generic_kernel<__half><<<grid, 256, 0, s>>>(
+          static_cast<const uint8_t *>(stacks), static_cast<__half *>(planes), total, pixels,
+          stack_size);
+    else
+      b2r::stack_to_planes_generic_kernel<float><<<grid, 256, 0, s>>>(
+          static_cast<const uint8_t *>(stacks), static_cast<float *>(planes), total, pixels,
+          stack_size);
+  }
+  B2R_CUDA(cudaGetLastError());
+  B2R_LAUNCHED();
   return B2R_OK;
 }
 

@@ -100,6 +100,7 @@ struct LossArgs {
   int fuse_tree;
   UpdateArgs<int32_t, float> tree;
   int64_t *err;  // nullable: asynchronous error latch (an action outside [0, A))
+  int32_t *count_copy;  // nullable: receives the row count (c51_post_kernel)
 };
 
 // One CTA per batch row, one warp per action (rainbow_agent.py:200-293):
@@ -974,6 +975,8 @@ c51_post_kernel(LossArgs a, const float *__restrict__ scratch, int have_stats) {
   pdl_acquire();
   B2R_MARK(11);
   const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
+  if (a.count_copy != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
+    *a.count_copy = a.u.batch_count ? *a.u.batch_count : a.u.batch;
   if ((int)blockIdx.x * kRowWarps >= rows) return;  // (no mean loss with batch_count)
   const int b = blockIdx.x * kRowWarps + warp;
   const bool row_ok = b < rows;
@@ -1355,7 +1358,7 @@ int c51_pre_launch(const b2r_c51_args *args, int rows, float *scratch, const Pre
 
 // The tail over the sampled rows.
 int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_stats,
-                    cudaStream_t s, int64_t *err) {
+                    cudaStream_t s, int64_t *err, int32_t *count_copy) {
   if (!args || args->batch <= 0 || !scratch)
     return fail(B2R_ERR_INVALID_ARGUMENT, "bad C51 shape");
   if (args->batch_count && args->mean_weighted_loss)
@@ -1368,6 +1371,7 @@ int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_sta
   a.u = *args;
   a.fuse_tree = 0;
   a.err = err;
+  a.count_copy = count_copy;
   a.warps = 0;
   B2R_TRY(ensure_loss_scratch(args->batch));
   a.weighted = g_weighted;
@@ -1394,6 +1398,7 @@ int c51_loss_launch(const b2r_c51_args *args, cudaStream_t s, b2r_tree *tree,
   a.u = *args;
   a.fuse_tree = 0;
   a.err = nullptr;
+  a.count_copy = nullptr;
   if (tree != nullptr) {
     if (!c51_can_fuse_writeback(args, tree))
       return fail(B2R_ERR_INVALID_ARGUMENT, "this batch cannot fuse its write-back");

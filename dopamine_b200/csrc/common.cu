@@ -71,7 +71,18 @@ int fail(int code, const char *fmt, ...) {
   return code;
 }
 
+int Bounce::mark_busy(cudaStream_t stream) {
+  if (!busy) B2R_CUDA(cudaEventCreateWithFlags(&busy, cudaEventDisableTiming));
+  B2R_CUDA(cudaEventRecord(busy, stream));
+  pending = true;
+  return B2R_OK;
+}
+
 int Bounce::reserve(size_t bytes) {
+  if (pending) {
+    B2R_CUDA(cudaEventSynchronize(busy));
+    pending = false;
+  }
   if (bytes <= cap) return B2R_OK;
   size_t want = cap ? cap : 4096;
   while (want < bytes) want *= 2;
@@ -83,6 +94,8 @@ int Bounce::reserve(size_t bytes) {
 }
 
 void Bounce::release() {
+  if (pending && busy) cudaEventSynchronize(busy);
+  pending = false;
   if (host) cudaFreeHost(host);
   if (dev) cudaFree(dev);
   host = dev = nullptr;

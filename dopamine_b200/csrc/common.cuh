@@ -49,7 +49,12 @@ struct Bounce {
   uint8_t *host = nullptr;
   uint8_t *dev = nullptr;
   size_t cap = 0;
+  // A caller that returns before its copy out of `host` has run (b2r_set_priority with
+  // host-validated inputs) marks the buffer busy; reserve() waits for that copy.
+  cudaEvent_t busy = nullptr;
+  bool pending = false;
   int reserve(size_t bytes);
+  int mark_busy(cudaStream_t stream);
   void release();
 };
 

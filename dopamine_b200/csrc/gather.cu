@@ -307,21 +307,32 @@ __global__ void get_priority_kernel(const double *__restrict__ leaves, int64_t n
 
 }  // namespace
 
-// 0: register path (LDG.128 -> PRMT -> STG.128), 1: TMA-staged path.  Chosen once
-// from B2R_GATHER (default set from measurements).
-int gather_variant() {
-  static const int v = [] {
+// 0: register path (LDG.128 -> PRMT -> STG.128), 1: TMA-staged path (cp.async.bulk into
+// shared memory on an mbarrier), for a launch of `batch` rows.  B2R_GATHER = reg | tma
+// forces one; the default follows the measurements (profiles/r2/README.md: CUDA-event
+// times of the fused step and ncu --set full of both kernels at 32 / 256 / 1024 / 4096):
+// the TMA kernel issues half the instructions and reaches 67 % of DRAM throughput at
+// batch 4096 against 56 % (fused step 100 us against 111 us; 24.5 against 26.0 at 256);
+// between those sizes, where the copies run beside the next step's chain, the register
+// kernel with its occupancy cap is the faster one (37.2 against 39.8 us at 1024).
+int gather_variant(int batch) {
+  static const int forced = [] {
     const char *e = std::getenv("B2R_GATHER");
-    if (e != nullptr) return std::strcmp(e, "tma") == 0 ? 1 : 0;
-    return 0;
+    if (e == nullptr || std::strcmp(e, "auto") == 0) return -1;
+    return std::strcmp(e, "tma") == 0 ? 1 : 0;
   }();
-  return v;
+  if (forced >= 0) return forced;
+  return batch <= 512 || batch >= 2048 ? 1 : 0;
 }
 
 // Will launch_gather(frames_only) run the kernel that understands RowFlags?
 bool gather_takes_row_flags(const b2r_buffer *b) {
+  static const bool reg_forced = [] {
+    const char *e = std::getenv("B2R_GATHER");
+    return e != nullptr && std::strcmp(e, "reg") == 0;
+  }();
   return b->cfg.stack_size == 4 && b->cfg.obs_itemsize == 1 &&
-         (b->cfg.obs_bytes & 15) == 0 && gather_variant() == 0;
+         (b->cfg.obs_bytes & 15) == 0 && reg_forced;
 }
 
 void fill_scalar_args(const b2r_buffer *b, const b2r_batch *out, ScalarArgs *sc) {
@@ -387,7 +398,7 @@ int launch_gather(b2r_buffer *b, int32_t batch, const int32_t *indices_dev,
   if (frames_only && !a.state && !a.next_state) return B2R_OK;
   const bool fast = a.stack == 4 && a.obs_itemsize == 1 && (a.obs_bytes & 15) == 0;
   const size_t tma_bytes = (size_t)kTmaMaxFrames * (size_t)a.obs_bytes;
-  if (fast && gather_variant() == 1 && tma_bytes <= 200 * 1024) {
+  if (fast && gather_variant(batch) == 1 && tma_bytes <= 200 * 1024) {
     static bool ready = false;
     if (!ready) {
       B2R_CUDA(cudaFuncSetAttribute(gather_stack4_u8_tma_kernel<true>,
@@ -474,65 +485,138 @@ int b2r_gather_device_counted(b2r_buffer *b, int32_t max_batch,
   return b2r::launch_gather(b, max_batch, indices, out, as_stream(stream), count);
 }
 
+namespace {
+
+// Layout of every requested output column in ONE slab, 256-byte aligned segments in a
+// fixed order, the indices the kernel reads first.  `want`: a non-null field = the
+// column is wanted.  Fills `at` with pointers into `base` and returns the slab size.
+size_t slab_layout(const b2r_buffer *b, int32_t batch, const b2r_batch *want,
+                   uint8_t *base, b2r_batch *at, size_t *indices_off) {
+  size_t total = 0;
+  auto seg = [&](size_t bytes) -> uint8_t * {
+    uint8_t *p = base + total;
+    total += (bytes + 255) & ~(size_t)255;
+    return p;
+  };
+  const size_t B = (size_t)batch;
+  const size_t stack_bytes = (size_t)b->cfg.obs_bytes * b->cfg.stack_size;
+  memset(at, 0, sizeof(*at));
+  *indices_off = total;
+  uint8_t *idx = seg(B * 4);
+  if (want->state) at->state = seg(B * stack_bytes);
+  if (want->action) at->action = seg(B * b->cfg.action_bytes);
+  if (want->reward) at->reward = seg(B * b->cfg.reward_itemsize);
+  if (want->next_state) at->next_state = seg(B * stack_bytes);
+  if (want->next_action) at->next_action = seg(B * b->cfg.action_bytes);
+  if (want->next_reward) at->next_reward = seg(B * b->cfg.reward_itemsize);
+  if (want->terminal) at->terminal = seg(B * b->cfg.terminal_itemsize);
+  // the kernel's index input doubles as the `indices` output column
+  if (want->indices) at->indices = reinterpret_cast<int32_t *>(idx);
+  for (int e = 0; e < b->cfg.num_extras; ++e)
+    if (want->extras[e]) at->extras[e] = seg(B * b->cfg.extra_bytes[e]);
+  if (want->sampling_probabilities)
+    at->sampling_probabilities = reinterpret_cast<float *>(seg(B * 4));
+  return total;
+}
+
+int ensure_out_scratch(b2r_buffer *b, size_t total) {
+  if (total <= b->out_scratch_cap) return B2R_OK;
+  if (b->out_scratch) cudaFree(b->out_scratch);
+  b->out_scratch = nullptr;
+  b->out_scratch_cap = 0;
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->out_scratch), total));
+  b->out_scratch_cap = total;
+  return B2R_OK;
+}
+
+}  // namespace
+
 int b2r_gather(b2r_buffer *b, int32_t batch, const int32_t *indices,
                const b2r_batch *out, b2r_stream stream) {
   if (batch <= 0 || batch > 60000)
     return fail(B2R_ERR_INVALID_ARGUMENT, "batch must be in [1, 60000]");
   cudaStream_t s = as_stream(stream);
   B2R_TRY(b2r::flush_queue(b, s));
-  // Device scratch for every requested output, 256-byte aligned segments.
-  struct Seg { void *host; size_t bytes; size_t off; };
-  Seg segs[8 + B2R_MAX_EXTRAS + 2];
-  int nseg = 0;
-  size_t total = 0;
-  auto seg = [&](void *host, size_t bytes) -> size_t {
-    segs[nseg] = {host, bytes, total};
-    total += (bytes + 255) & ~(size_t)255;
-    return segs[nseg++].off;
+  // Device scratch for every requested output, then one copy per column into the
+  // caller's (pageable) arrays.  b2r_gather_slab is the fast form of this call.
+  b2r_batch d;
+  size_t off_idx = 0;
+  const size_t total = slab_layout(b, batch, out, nullptr, &d, &off_idx);
+  B2R_TRY(ensure_out_scratch(b, total));
+  uint8_t *base = b->out_scratch;
+  auto dev = [&](const void *p) -> uint8_t * {  // (offsets were laid out against nullptr)
+    return base + reinterpret_cast<size_t>(p);
   };
   const size_t B = (size_t)batch;
   const size_t stack_bytes = (size_t)b->cfg.obs_bytes * b->cfg.stack_size;
-  const size_t off_idx = seg(nullptr, B * 4);
-  b2r_batch d;
-  memset(&d, 0, sizeof(d));
-  size_t o_state = out->state ? seg(out->state, B * stack_bytes) : 0;
-  size_t o_action = out->action ? seg(out->action, B * b->cfg.action_bytes) : 0;
-  size_t o_reward = out->reward ? seg(out->reward, B * b->cfg.reward_itemsize) : 0;
-  size_t o_nstate = out->next_state ? seg(out->next_state, B * stack_bytes) : 0;
-  size_t o_naction = out->next_action ? seg(out->next_action, B * b->cfg.action_bytes) : 0;
-  size_t o_nreward = out->next_reward ? seg(out->next_reward, B * b->cfg.reward_itemsize) : 0;
-  size_t o_term = out->terminal ? seg(out->terminal, B * b->cfg.terminal_itemsize) : 0;
-  size_t o_ind = out->indices ? seg(out->indices, B * 4) : 0;
-  size_t o_extra[B2R_MAX_EXTRAS] = {0};
-  for (int e = 0; e < b->cfg.num_extras; ++e)
-    if (out->extras[e]) o_extra[e] = seg(out->extras[e], B * b->cfg.extra_bytes[e]);
-  size_t o_prio = out->sampling_probabilities ? seg(out->sampling_probabilities, B * 4) : 0;
-  if (total > b->out_scratch_cap) {
-    if (b->out_scratch) cudaFree(b->out_scratch);
-    b->out_scratch = nullptr;
-    b->out_scratch_cap = 0;
-    B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->out_scratch), total));
-    b->out_scratch_cap = total;
+  struct Copy { void *host; const uint8_t *dev; size_t bytes; };
+  Copy copies[8 + B2R_MAX_EXTRAS + 2];
+  int n = 0;
+  b2r_batch k;
+  memset(&k, 0, sizeof(k));
+  auto col = [&](void *host, const void *at, size_t bytes) -> void * {
+    if (!host) return nullptr;
+    copies[n++] = {host, dev(at), bytes};
+    return dev(at);
+  };
+  k.state = col(out->state, d.state, B * stack_bytes);
+  k.action = col(out->action, d.action, B * b->cfg.action_bytes);
+  k.reward = col(out->reward, d.reward, B * b->cfg.reward_itemsize);
+  k.next_state = col(out->next_state, d.next_state, B * stack_bytes);
+  k.next_action = col(out->next_action, d.next_action, B * b->cfg.action_bytes);
+  k.next_reward = col(out->next_reward, d.next_reward, B * b->cfg.reward_itemsize);
+  k.terminal = col(out->terminal, d.terminal, B * b->cfg.terminal_itemsize);
+  if (out->indices) {
+    copies[n++] = {out->indices, base + off_idx, B * 4};
+    k.indices = nullptr;  // (the kernel's input already is that column)
   }
-  uint8_t *base = b->out_scratch;
-  if (out->state) d.state = base + o_state;
-  if (out->action) d.action = base + o_action;
-  if (out->reward) d.reward = base + o_reward;
-  if (out->next_state) d.next_state = base + o_nstate;
-  if (out->next_action) d.next_action = base + o_naction;
-  if (out->next_reward) d.next_reward = base + o_nreward;
-  if (out->terminal) d.terminal = base + o_term;
-  if (out->indices) d.indices = reinterpret_cast<int32_t *>(base + o_ind);
   for (int e = 0; e < b->cfg.num_extras; ++e)
-    if (out->extras[e]) d.extras[e] = base + o_extra[e];
-  if (out->sampling_probabilities)
-    d.sampling_probabilities = reinterpret_cast<float *>(base + o_prio);
+    k.extras[e] = col(out->extras[e], d.extras[e], B * b->cfg.extra_bytes[e]);
+  k.sampling_probabilities = static_cast<float *>(
+      col(out->sampling_probabilities, d.sampling_probabilities, B * 4));
   B2R_CUDA(cudaMemcpyAsync(base + off_idx, indices, B * 4, cudaMemcpyHostToDevice, s));
   B2R_TRY(b2r::launch_gather(b, batch,
-                             reinterpret_cast<const int32_t *>(base + off_idx), &d, s));
-  for (int k = 1; k < nseg; ++k)
-    B2R_CUDA(cudaMemcpyAsync(segs[k].host, base + segs[k].off, segs[k].bytes,
+                             reinterpret_cast<const int32_t *>(base + off_idx), &k, s));
+  for (int c = 0; c < n; ++c)
+    B2R_CUDA(cudaMemcpyAsync(copies[c].host, copies[c].dev, copies[c].bytes,
                              cudaMemcpyDeviceToHost, s));
+  B2R_CUDA(cudaStreamSynchronize(s));
+  return B2R_OK;
+}
+
+int b2r_gather_slab(b2r_buffer *b, int32_t batch, const int32_t *indices,
+                    int32_t indices_on_device, const b2r_batch *want, void *host_slab,
+                    size_t slab_bytes, b2r_batch *host_out, size_t *needed,
+                    b2r_stream stream) {
+  if (!b || !want || !host_out || !needed)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
+  if (batch <= 0 || batch > 60000)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "batch must be in [1, 60000]");
+  size_t off_idx = 0;
+  const size_t total =
+      slab_layout(b, batch, want, static_cast<uint8_t *>(host_slab), host_out, &off_idx);
+  *needed = total;
+  if (host_slab == nullptr) return B2R_OK;  // (size query: *host_out holds the offsets)
+  if (slab_bytes < total) {
+    memset(host_out, 0, sizeof(*host_out));
+    return fail(B2R_ERR_INVALID_ARGUMENT, "the slab holds %zu bytes, the batch needs %zu",
+                slab_bytes, total);
+  }
+  if (!indices) return fail(B2R_ERR_INVALID_ARGUMENT, "indices is NULL");
+  cudaStream_t s = as_stream(stream);
+  B2R_TRY(b2r::flush_queue(b, s));
+  B2R_TRY(ensure_out_scratch(b, total));
+  uint8_t *base = b->out_scratch;
+  b2r_batch d;
+  size_t unused = 0;
+  slab_layout(b, batch, want, base, &d, &unused);
+  d.indices = nullptr;  // (the kernel's input already is that column)
+  B2R_CUDA(cudaMemcpyAsync(base + off_idx, indices, (size_t)batch * 4,
+                           indices_on_device ? cudaMemcpyDeviceToDevice
+                                             : cudaMemcpyHostToDevice, s));
+  B2R_TRY(b2r::launch_gather(b, batch,
+                             reinterpret_cast<const int32_t *>(base + off_idx), &d, s));
+  B2R_CUDA(cudaMemcpyAsync(host_slab, base, total, cudaMemcpyDeviceToHost, s));
   B2R_CUDA(cudaStreamSynchronize(s));
   return B2R_OK;
 }

@@ -529,6 +529,38 @@ int b2r_add_atari(b2r_buffer *b, const void *observation, int32_t action,
                  priority_mode, stream);
 }
 
+int b2r_add_batch(b2r_buffer *b, int64_t n, const void *observations,
+                  const void *actions, const void *rewards, const void *terminals,
+                  const void *const *extras, const double *priorities, int priority_mode,
+                  int64_t *added, b2r_stream stream) {
+  if (added) *added = 0;
+  if (!b || n < 0 || (n > 0 && (!observations || !actions || !rewards || !terminals)))
+    return fail(B2R_ERR_INVALID_ARGUMENT, "add_batch: bad argument");
+  if (stream == B2R_STREAM_NONE)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "add_batch needs a stream: it may have to flush");
+  if (b->tree && priority_mode == B2R_PRIORITY_EXPLICIT && n > 0 && !priorities)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "add_batch: explicit priorities are NULL");
+  const uint8_t *col[4] = {static_cast<const uint8_t *>(observations),
+                           static_cast<const uint8_t *>(actions),
+                           static_cast<const uint8_t *>(rewards),
+                           static_cast<const uint8_t *>(terminals)};
+  const size_t stride[4] = {(size_t)b->cfg.obs_bytes, (size_t)b->cfg.action_bytes,
+                            (size_t)b->cfg.reward_itemsize,
+                            (size_t)b->cfg.terminal_itemsize};
+  const void *extra_rows[B2R_MAX_EXTRAS] = {nullptr};
+  for (int64_t k = 0; k < n; ++k) {
+    for (int e = 0; e < b->cfg.num_extras; ++e)
+      extra_rows[e] = static_cast<const uint8_t *>(extras[e]) +
+                      (size_t)k * (size_t)b->cfg.extra_bytes[e];
+    B2R_TRY(b2r_add(b, col[0] + k * stride[0], col[1] + k * stride[1],
+                    col[2] + k * stride[2], col[3] + k * stride[3],
+                    b->cfg.num_extras ? extra_rows : nullptr,
+                    priorities ? priorities[k] : 0.0, priority_mode, stream));
+    if (added) *added = k + 1;
+  }
+  return B2R_OK;
+}
+
 int b2r_flush(b2r_buffer *b, b2r_stream stream) {
   return b2r::flush_queue(b, as_stream(stream));
 }
@@ -677,6 +709,13 @@ int b2r_set_priority(b2r_buffer *b, int64_t n, const int32_t *indices,
   B2R_TRY((b2r::tree_apply<int32_t, double>(
       t, n, reinterpret_cast<const int32_t *>(b->bounce.dev + (size_t)n * 8),
       reinterpret_cast<const double *>(b->bounce.dev), nullptr, s)));
+  // What the device could refuse — a negative value (sum_tree.py:191-193), an index
+  // outside the tree — is visible on the host: when there is nothing of the kind the
+  // update cannot fail and the call returns without waiting for it.
+  bool clean = true;
+  for (int64_t k = 0; k < n && clean; ++k)
+    clean = priorities[k] >= 0.0 && indices[k] >= 0 && (int64_t)indices[k] < t->leaves;
+  if (clean) return b->bounce.mark_busy(s);
   int64_t st[2];
   B2R_CUDA(cudaMemcpyAsync(st, t->status, 16, cudaMemcpyDeviceToHost, s));
   B2R_CUDA(cudaStreamSynchronize(s));

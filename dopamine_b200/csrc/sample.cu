@@ -123,7 +123,7 @@ __device__ __forceinline__ void exchange_collect(const ExchangeArgs &x, int worl
   const int g = threadIdx.x;
   if (g >= world) return;
   double got = local_total;
-  if (g != rank) {
+  if (g != rank && x.timeout_ns > 0) {
     const uint32_t tag = (uint32_t)seq;
     const uint64_t *src = x.local + ((size_t)(seq & 1) * world + g) * 2;
     const bool broken = latched != nullptr && latched[0] == B2R_ERR_EXCHANGE;
@@ -757,7 +757,45 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
   // stratum index and the rank-order scan is monotone) the range [lo, hi) found by two
   // simultaneous k-ary searches, blockDim candidates per round.
   int range_lo = 0, range_hi = a.batch;
+  bool ranges_found = false;
   if (a.shard_ranges) {
+    // Both ends sit within a stratum or two of (totals before this rank) / total * batch
+    // and (totals through this rank) / total * batch: every warp tests a window of 16
+    // candidates around each estimate — lanes 0..15 the lower end, 16..31 the upper — with
+    // the exact owner rule, one draw per lane and no block barrier.  A window that does
+    // not bracket its boundary (never seen; the estimates are off by rounding only) falls
+    // back to the search below, so the result is the search's in every case.
+    double before = 0.0;
+    for (int g = 0; g < a.rank; ++g) before = __dadd_rn(before, shard_totals[g]);
+    const double through = __dadd_rn(before, shard_totals[a.rank]);
+    // (an estimate: single precision is plenty, and an fp64 division is a ~500-cycle
+    // subroutine)
+    const int which = lane >> 4;
+    const float est = __fdividef((float)(which == 0 ? before : through), (float)grand_total) *
+                      (float)a.batch;
+    const int win_base = (est < (float)a.batch ? (int)est : a.batch) - 7;
+    const int cand = win_base + (lane & 15);
+    bool pred = cand >= a.batch;  // at or past the end
+    if (cand >= 0 && cand < a.batch) {
+      double unused;
+      const int owner = stratum_owner(
+          cand, philox_uniform53_fast(a.seed, draw_offset, (uint64_t)cand), &unused);
+      pred = which == 0 ? owner >= a.rank : owner > a.rank;
+    }
+    const unsigned votes = __ballot_sync(full, pred);
+    const unsigned v_lo = votes & 0xffffu, v_hi = votes >> 16;
+    const int base_lo = __shfl_sync(full, win_base, 0), base_hi = __shfl_sync(full, win_base, 16);
+    const bool ok_lo = (v_lo & 0x8000u) != 0 && ((v_lo & 1u) == 0 || base_lo <= 0);
+    const bool ok_hi = (v_hi & 0x8000u) != 0 && ((v_hi & 1u) == 0 || base_hi <= 0);
+    if (ok_lo && ok_hi) {
+      range_lo = base_lo + __ffs(v_lo) - 1;
+      range_hi = base_hi + __ffs(v_hi) - 1;
+      if (range_lo < 0) range_lo = 0;
+      if (range_hi < range_lo) range_hi = range_lo;
+      ranges_found = true;
+    }
+  }
+  if (a.shard_ranges && !ranges_found) {
     const int fan = blockDim.x;
     int base[2] = {0, 0}, limit[2] = {a.batch, a.batch};
     while (base[0] < limit[0] || base[1] < limit[1]) {
@@ -1394,6 +1432,12 @@ void fill_exchange_args(const b2r_exchange *x, ExchangeArgs *out) {
   for (int g = 0; g < kMaxShards; ++g) out->peer[g] = x->peer[g];
   out->seq = x->seq;
   out->timeout_ns = x->timeout_ns;
+  // Profiling switch (never set in production): B2R_DEBUG_XCHG_NOWAIT=1 takes this rank's
+  // own total for every peer instead of waiting for theirs — the step time without the
+  // cross-GPU coupling, i.e. the bound of what any change to the exchange can gain.  The
+  // ranks' strata then no longer partition the batch.
+  static const bool nowait = std::getenv("B2R_DEBUG_XCHG_NOWAIT") != nullptr;
+  if (nowait) out->timeout_ns = 0;
 }
 
 int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shards,

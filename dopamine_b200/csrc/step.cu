@@ -95,7 +95,7 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
                 "are required");
   if (shard && (!shard->exchange || !shard->out_count))
     return fail(B2R_ERR_INVALID_ARGUMENT, "exchange and out_count are required");
-  const int32_t *count = shard ? shard->out_count : nullptr;
+  const int32_t *count = shard ? shard->out_count : nullptr;  // (deferred: a ring slot)
   // rows behind the sampler: the batch, or the capacity of a shard's outputs
   const int32_t rows_cap =
       shard && shard->max_rows > 0 && shard->max_rows < batch ? shard->max_rows : batch;
@@ -142,23 +142,31 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   g_host_trace.lap(2);
   // Deferred frame copies: the copies read their indices from a private ring slot (the
   // next step's sampler overwrites out->indices while they may still be running).
-  const bool deferred = b->deferred_frames && !shard;
+  // (A shard's copies also read its row count: that lives in the ring slot as well, and
+  // the loss tail hands it on to the caller's out_count.)
+  const bool deferred = b->deferred_frames && (!shard || split_loss);
+  if (b->deferred_frames && !deferred) B2R_TRY(join_frames(b, s));
   int32_t *sample_idx = out->indices;
   int ring_slot = 0;
   if (deferred) {
-    if (b->idx_ring_cap < batch) {
+    if (b->idx_ring_cap < rows_cap) {
       B2R_TRY(join_frames(b, s));
       B2R_CUDA(cudaStreamSynchronize(b->side));
       if (b->idx_ring) cudaFree(b->idx_ring);
       b->idx_ring = nullptr;
       b->idx_ring_cap = 0;
       int64_t cap = 256;
-      while (cap < batch) cap *= 2;
-      B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->idx_ring), (size_t)cap * 2 * 4));
+      while (cap < rows_cap) cap *= 2;
+      // [2][cap] indices, then the two row counts
+      B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->idx_ring), (size_t)(cap * 2 + 2) * 4));
       b->idx_ring_cap = cap;
     }
     ring_slot = b->frame_parity & 1;
     sample_idx = b->idx_ring + (size_t)ring_slot * b->idx_ring_cap;
+    if (shard) {
+      count = b->idx_ring + 2 * b->idx_ring_cap + ring_slot;
+      loss.batch_count = count;
+    }
     b->frame_parity ^= 1;
     // the copies of two steps ago read this slot
     if (b->slot_busy[ring_slot])
@@ -176,8 +184,8 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
     B2R_TRY(launch_sample_sharded(
         b, batch, shard->exchange->world, shard->exchange->rank, nullptr,
         shard->exchange, nullptr, b->cfg.max_sample_attempts, nullptr, seed, offset,
-        shard->out_slots, out->indices, shard->out_count, s, out, b->min_prob, rows_cap,
-        split_loss ? &pre_sync : nullptr));
+        shard->out_slots, sample_idx, const_cast<int32_t *>(count), s, out, b->min_prob,
+        rows_cap, split_loss ? &pre_sync : nullptr));
   else
     B2R_TRY(launch_sample(b, batch, true, seed, offset, nullptr, nullptr, 0,
                           sample_idx, b->info, s, out, b->min_prob,
@@ -224,7 +232,8 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   const bool tail_writeback =
       !split_loss && !shard && !debug_skip() && c51_can_fuse_writeback(&loss, b->tree);
   if (split_loss)
-    B2R_TRY(c51_post_launch(&loss, b->c51_bestp, have_stats, s, b->status));
+    B2R_TRY(c51_post_launch(&loss, b->c51_bestp, have_stats, s, b->status,
+                            shard && count != shard->out_count ? shard->out_count : nullptr));
   else if (tail_writeback)
     B2R_TRY(c51_loss_launch(&loss, s, b->tree, out->indices));
   else if (!(debug_skip() & 1))
@@ -267,7 +276,11 @@ struct b2r_trainer {
   // sharded mode
   b2r_exchange *exchange = nullptr;
   int32_t *slots = nullptr;   // device [batch]: stratum of every local row
-  int32_t *count = nullptr;   // device: local rows of the step (lives behind `loss`)
+  // Per-row losses (+ the shard's row count behind them), one buffer per logits set:
+  // step n's result copy reads its buffer on the result-copy stream while step n + 1's
+  // loss kernel is already writing the other one.
+  float *loss_buf[2] = {nullptr, nullptr};
+  int32_t *count_buf[2] = {nullptr, nullptr};
   int32_t last_rows = 0;
   // graph mode: the step's kernels captured once per logits set
   cudaStream_t cap = nullptr;
@@ -287,6 +300,7 @@ int capture_step(b2r_trainer *t, int set) {
   b2r_c51_args c51 = t->c51;
   c51.online_logits = t->logits[set][0];
   c51.target_logits = t->logits[set][1];
+  c51.loss = t->loss_buf[set];
   cudaGraph_t graph = nullptr;
   B2R_CUDA(cudaStreamBeginCapture(t->cap, cudaStreamCaptureModeThreadLocal));
   const int status = b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch,
@@ -402,8 +416,8 @@ int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
   };
   const size_t o_action = seg(B * 4), o_reward = seg(B * 4), o_naction = seg(B * 4),
                o_nreward = seg(B * 4), o_term = seg(B), o_idx = seg(B * 4),
-               o_prob = seg(B * 4), o_loss = seg((B + 1) * 4), o_prio = seg(B * 4),
-               o_w = seg(B * 4), o_slots = seg(B * 4);
+               o_prob = seg(B * 4), o_loss = seg((B + 1) * 4), o_loss1 = seg((B + 1) * 4),
+               o_prio = seg(B * 4), o_w = seg(B * 4), o_slots = seg(B * 4);
   size_t o_extra[B2R_MAX_EXTRAS];
   for (int e = 0; e < b->cfg.num_extras; ++e)
     o_extra[e] = seg(B * (size_t)b->cfg.extra_bytes[e]);
@@ -430,7 +444,10 @@ int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
   t->c51.priorities = reinterpret_cast<float *>(t->scalars + o_prio);
   t->c51.weights = reinterpret_cast<float *>(t->scalars + o_w);
   t->slots = reinterpret_cast<int32_t *>(t->scalars + o_slots);
-  t->count = reinterpret_cast<int32_t *>(t->c51.loss + B);  // copied back with the losses
+  t->loss_buf[0] = t->c51.loss;
+  t->loss_buf[1] = reinterpret_cast<float *>(t->scalars + o_loss1);
+  for (int k = 0; k < 2; ++k)  // copied back with the losses
+    t->count_buf[k] = reinterpret_cast<int32_t *>(t->loss_buf[k] + B);
 
   B2R_CUDA(cudaStreamCreateWithFlags(&t->copy, cudaStreamNonBlocking));
   B2R_CUDA(cudaStreamCreateWithFlags(&t->copy_out, cudaStreamNonBlocking));
@@ -506,11 +523,17 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   B2R_CUDA(cudaMemcpyAsync(t->logits[set][1], target_logits, logit_bytes,
                            cudaMemcpyHostToDevice, t->copy));
   B2R_CUDA(cudaEventRecord(t->ev_in[set], t->copy));
+  // The loss buffer of this set was last read by the result copy of step n - 2.  With a
+  // pipeline of depth <= 1 the host has already waited for that copy (collect); deeper
+  // pipelines order the step behind it on the device.
+  if (n >= 2 && t->cfg.pipeline_depth >= 2)
+    B2R_CUDA(cudaStreamWaitEvent(s, t->ev_done[(size_t)((n - 2) % t->ring)], 0));
   if (t->exchange) {
     b2r_c51_args c51 = t->c51;
     c51.online_logits = t->logits[set][0];
     c51.target_logits = t->logits[set][1];
-    b2r::ShardSpec shard = {t->exchange, t->slots, t->count, t->cfg.logit_rows};
+    c51.loss = t->loss_buf[set];
+    b2r::ShardSpec shard = {t->exchange, t->slots, t->count_buf[set], t->cfg.logit_rows};
     B2R_TRY(b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch, &c51, s,
                             t->ev_in[set], t->ev_loss[set], &shard));
   } else if (t->cfg.use_graph && n >= 2) {
@@ -527,6 +550,7 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
     b2r_c51_args c51 = t->c51;
     c51.online_logits = t->logits[set][0];
     c51.target_logits = t->logits[set][1];
+    c51.loss = t->loss_buf[set];
     B2R_TRY(b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch, &c51, s,
                             t->ev_in[set], t->ev_loss[set]));
   }
@@ -534,7 +558,7 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   const int slot = (int)(n % t->ring);
   B2R_CUDA(cudaStreamWaitEvent(t->copy_out, t->ev_loss[set], 0));
   B2R_CUDA(cudaMemcpyAsync(t->ring_host + (size_t)slot * (t->cfg.logit_rows + 1),
-                           t->c51.loss, (size_t)(t->cfg.logit_rows + 1) * sizeof(float),
+                           t->loss_buf[set], (size_t)(t->cfg.logit_rows + 1) * sizeof(float),
                            cudaMemcpyDeviceToHost, t->copy_out));
   B2R_CUDA(cudaEventRecord(t->ev_done[slot], t->copy_out));
   t->submitted = n + 1;
@@ -572,6 +596,7 @@ int b2r_trainer_views(b2r_trainer *t, b2r_batch *batch, b2r_c51_args *c51) {
     const int set = (int)((t->submitted + 1) & 1);  // set of the last queued step
     c51->online_logits = t->logits[set][0];
     c51->target_logits = t->logits[set][1];
+    c51->loss = t->loss_buf[set];
     c51->actions = static_cast<const int32_t *>(t->batch.action);
     c51->rewards = static_cast<const float *>(t->batch.reward);
     c51->terminals = static_cast<const uint8_t *>(t->batch.terminal);

@@ -721,7 +721,7 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t *keys, int padded, in
 // the internal levels is a __syncthreads.  Each warp sorts its own (node, k) keys
 // with shuffled-free warp-synchronous bitonic steps while the leaf warp resolves
 // the leaf chains; internal warps prefetch their node values before the barrier.
-template <typename I, typename V>
+template <bool PDL = true, typename I, typename V>
 __device__ __forceinline__ void tree_update_small_body(const UpdateArgs<I, V> &a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -733,10 +733,12 @@ __device__ __forceinline__ void tree_update_small_body(const UpdateArgs<I, V> &a
   double *sorted_delta = all_sorted + (size_t)warp * a.padded;
   __shared__ int s_stop, s_stop_code;
 
-  B2R_MARK(0);
-  pdl_release();
-  pdl_acquire();
-  B2R_MARK(1);
+  if (PDL) {
+    B2R_MARK(0);
+    pdl_release();
+    pdl_acquire();
+    B2R_MARK(1);
+  }
   int n = a.n;
   if (a.n_dev) n = min(n, max(*a.n_dev, 0));
   const int64_t latched = a.status[0];
@@ -867,14 +869,33 @@ __device__ __forceinline__ void tree_update_small_body(const UpdateArgs<I, V> &a
   B2R_MARK(7);
 }
 
+// tiny_ok: when the device-side count (a sharded step's rows: the launch is sized for the
+// bound on the share, the rows are usually far fewer) turns out to be at most 32, the
+// match-based body runs instead — the decision the host makes from n when it knows n.
 template <typename I, typename V>
-__global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V> a) {
-  tree_update_small_body(a);
+__global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V> a,
+                                                                 int tiny_ok) {
+  B2R_MARK(0);
+  pdl_release();
+  pdl_acquire();
+  B2R_MARK(1);
+  if (tiny_ok) {
+    int n = a.n;
+    if (a.n_dev) n = min(n, max(*a.n_dev, 0));
+    if (n <= kTinyBatch) {
+      tree_update_tiny_body<false>(a);
+      B2R_MARK_END(7);
+      return;
+    }
+  }
+  tree_update_small_body<false>(a);
 }
 
 template <typename I, typename V>
 __global__ void __launch_bounds__(1024) tree_update_tiny_kernel(UpdateArgs<I, V> a) {
+  B2R_MARK(30);
   tree_update_tiny_body<true>(a);
+  B2R_MARK_END(7);
 }
 
 // The flush of staged adds as ONE launch: CTA 0 applies the priorities of the new
@@ -1076,7 +1097,10 @@ bool tree_can_presort(int64_t n, int64_t expected_n) {
     const char *e = std::getenv("B2R_TREE_PRESORT_MAX");
     return e ? (int64_t)std::atoi(e) : (int64_t)BigCfg1024::kChunk;
   }();
-  return on && n <= BigCfg4096::kChunk && n <= presort_max;
+  // (A launch sized for more entries than are expected — a sharded step's bound on its
+  // share — presorts its first chunk, where the expected entries are; chunks behind it,
+  // normally empty, run unsplit.)
+  return on && likely <= BigCfg4096::kChunk && likely <= presort_max;
 }
 
 static int ensure_sorted(b2r_tree *t) {
@@ -1124,15 +1148,17 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
                       0, stream, a));
     else
       B2R_CUDA(launch(tree_update_small_kernel<I, V>, dim3(1),
-                      dim3(32 * (t->depth + 1)), smem, stream, a));
+                      dim3(32 * (t->depth + 1)), smem, stream, a,
+                      (int)(n_dev != nullptr && tree_tiny_enabled() && t->depth + 1 <= 32)));
     B2R_LAUNCHED();
     return B2R_OK;
   }
   // Up to 1024 entries (known on the host): the 256 x 4 geometry; above, chunks of
   // 4096 through the 1024 x 4 one.
-  const bool compact = n <= BigCfg1024::kChunk;
+  const bool compact = likely <= BigCfg1024::kChunk;
   const int64_t chunk = compact ? BigCfg1024::kChunk : BigCfg4096::kChunk;
   for (int64_t base = 0; base < n; base += chunk) {
+    if (phase == kPresort && base > 0) break;  // (only the first chunk is grouped ahead)
     const int len = (int)((n - base) < chunk ? (n - base) : chunk);
     UpdateArgs<I, V> a;
     a.heap = t->heap;
@@ -1149,7 +1175,7 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     a.status = t->status;
     a.n_dev = n_dev;
     a.scan_min_chain = tree_scan_min_chain();
-    a.phase = phase;
+    a.phase = base == 0 ? phase : kFull;
     a.sorted = t->sorted;
     a.sync_words = t->sync_words;
     if (compact)

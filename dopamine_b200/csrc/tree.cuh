@@ -474,6 +474,6 @@ int c51_pre_launch(const b2r_c51_args *args, int rows, float *scratch, const Pre
                    cudaStream_t stream, int *have_stats);
 // ... and the tail over the sampled rows.  err (nullable): asynchronous error latch.
 int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_stats,
-                    cudaStream_t stream, int64_t *err);
+                    cudaStream_t stream, int64_t *err, int32_t *count_copy = nullptr);
 
 }  // namespace b2r

@@ -24,6 +24,7 @@ import gzip
 import math
 import os
 import pickle
+import sys
 
 import numpy as np
 
@@ -166,6 +167,10 @@ class OutOfGraphReplayBuffer(object):
     # batch size instead: no allocation on the sampling path.
     self._reuse_outputs = bool(reuse_outputs)
     self._output_cache = {}
+    self._slab_pool = {}   # (batch, bytes) -> page-locked numpy slabs (output='numpy')
+    self._slab_plans = {}
+    self._slab_at = _native.Batch()
+    self._slab_needed = ctypes.c_size_t(0)
     self._lib = _native.lib()
     # add() fast path: Atari layout and plain scalars -> one native call.
     self._fast_add = (
@@ -356,6 +361,49 @@ class OutOfGraphReplayBuffer(object):
     self._check_add_types(observation, action, reward, terminal, *args)
     self._native_add((observation, action, reward, terminal) + tuple(args), 0.0,
                      _native.PRIORITY_EXPLICIT)
+
+  def add_batch(self, observations, actions, rewards, terminals, *args):
+    """n consecutive `add`s of one trajectory stream in ONE native call (b2r_add_batch).
+
+    Every argument is an array whose leading axis counts the steps; values are cast to
+    the storage dtypes as `add` casts them (CRB:280-282).  Same buffer state afterwards
+    as the loop `for k: add(observations[k], ...)` — zero padding after terminals,
+    invalid_range — with the rows staged together.  (No counterpart in the reference,
+    whose agents add one step at a time: DQ:444-458, RA:307-337.)"""
+    self._native_add_batch((observations, actions, rewards, terminals) + tuple(args),
+                           None, _native.PRIORITY_EXPLICIT)
+
+  def _native_add_batch(self, columns, priorities, priority_mode):
+    signature = self.get_storage_signature()
+    if len(columns) != len(signature):
+      raise ValueError('Add expects {} elements, received {}'.format(
+          len(signature), len(columns)))
+    n = len(columns[0])
+    arrays = []
+    for values, element in zip(columns, signature):
+      array = np.ascontiguousarray(values, dtype=element.type)
+      if array.shape != (n,) + tuple(element.shape):
+        raise ValueError('arg {} has shape {}, expected {}'.format(
+            element.name, array.shape, (n,) + tuple(element.shape)))
+      arrays.append(array)
+    extras = (ctypes.c_void_p * _native.MAX_EXTRAS)()
+    for k, array in enumerate(arrays[4:]):
+      extras[k] = array.ctypes.data
+    prio_ptr = None
+    if priorities is not None:
+      priorities = np.ascontiguousarray(priorities, dtype=np.float64)
+      if priorities.shape != (n,):
+        raise ValueError('priorities has shape {}, expected {}'.format(
+            priorities.shape, (n,)))
+      prio_ptr = priorities.ctypes.data
+    added = ctypes.c_int64(0)
+    status = self._lib.b2r_add_batch(
+        self._h, n, arrays[0].ctypes.data, arrays[1].ctypes.data, arrays[2].ctypes.data,
+        arrays[3].ctypes.data, extras, prio_ptr, priority_mode, ctypes.byref(added),
+        self._stream())
+    if status == _native.ERR_NEGATIVE_PRIORITY:
+      raise ValueError(_native.last_error())
+    _native.check(status)
 
   def _try_fast_add(self, observation, action, reward, terminal, priority, mode):
     """One native call when the arguments are what an Atari agent passes: a
@@ -570,6 +618,74 @@ class OutOfGraphReplayBuffer(object):
         assert i + 1 <= cursor, 'Index {} has not been added.'.format(
             i - self._stack_size + 1)
 
+  def _pinned_slab(self, batch_size, nbytes):
+    """A page-locked slab of `nbytes` that no array handed out earlier still views.
+
+    The reference returns FRESH arrays on every call (CRB:416-434, 516): a caller may
+    keep as many batches as it likes.  The slabs of a pool are therefore reused only
+    once every numpy view over them has been dropped (their reference count says so);
+    while views are alive the pool grows.  Page-locked memory is what lets the whole
+    batch travel in ONE copy at PCIe speed; allocating it is slow, hence the pool."""
+    pool = self._slab_pool.setdefault((batch_size, nbytes), [])
+    for slab in pool:
+      if sys.getrefcount(slab) == 3:  # the pool's list, `slab`, getrefcount's argument
+        return slab
+    torch = _torch()
+    keep = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    slab = keep.numpy()  # (holds `keep` alive as its base)
+    pool.append(slab)
+    return slab
+
+  def _host_batch_plan(self, batch_size):
+    """Per batch size, once: which columns are wanted, how large the slab is and where
+    each returned array sits in it."""
+    plan = self._slab_plans.get(batch_size)
+    if plan is not None:
+      return plan
+    elements = self.get_transition_elements(batch_size)
+    want = _native.Batch()
+    fields = []
+    extra = 0
+    for e in elements:
+      if hasattr(want, e.name) and e.name != 'extras':
+        setattr(want, e.name, 1)
+        fields.append(e.name)
+      else:
+        want.extras[extra] = 1
+        fields.append(extra)
+        extra += 1
+    needed = ctypes.c_size_t(0)
+    at = _native.Batch()  # with a NULL slab the pointers come back as offsets
+    _native.check(self._lib.b2r_gather_slab(
+        self._h, batch_size, None, 0, ctypes.byref(want), None, 0, ctypes.byref(at),
+        ctypes.byref(needed), self._stream()))
+    views = []
+    for e, f in zip(elements, fields):
+      offset = int((at.extras[f] if isinstance(f, int) else getattr(at, f)) or 0)
+      count = int(np.prod(e.shape, dtype=np.int64)) * np.dtype(e.type).itemsize
+      views.append((offset, offset + count, np.dtype(e.type), tuple(e.shape)))
+    plan = (want, int(needed.value), views)
+    self._slab_plans[batch_size] = plan
+    return plan
+
+  def _gather_to_host(self, batch_size, indices, device_indices):
+    """output='numpy': the batch as host arrays (the reference's return convention),
+    built on the device and shipped in one copy into a page-locked slab; the arrays are
+    views over it (b2r_gather_slab)."""
+    want, nbytes, views = self._host_batch_plan(batch_size)
+    slab = self._pinned_slab(batch_size, nbytes)
+    if device_indices is not None:
+      idx_ptr, on_device = device_indices.data_ptr(), 1
+    else:
+      host_idx = np.ascontiguousarray(indices, dtype=np.int32)
+      idx_ptr, on_device = host_idx.ctypes.data, 0
+    _native.check(self._lib.b2r_gather_slab(
+        self._h, batch_size, idx_ptr, on_device, ctypes.byref(want), slab.ctypes.data,
+        nbytes, ctypes.byref(self._slab_at), ctypes.byref(self._slab_needed),
+        self._stream()))
+    return tuple(slab[lo:hi].view(dtype).reshape(shape)
+                 for lo, hi, dtype, shape in views)
+
   def sample_transition_batch(self, batch_size=None, indices=None):
     """Batch of transitions in get_transition_elements() order (CRB:479-558).
 
@@ -587,8 +703,8 @@ class OutOfGraphReplayBuffer(object):
     else:
       self._check_explicit_indices(indices)
     assert len(indices) == batch_size
-    _, arrays, batch = self._alloc_outputs(batch_size, on_device)
     if on_device:
+      _, arrays, batch = self._alloc_outputs(batch_size, on_device)
       torch = _torch()
       if torch_indices is None:
         torch_indices = torch.as_tensor(
@@ -597,13 +713,7 @@ class OutOfGraphReplayBuffer(object):
           self._h, batch_size, torch_indices.data_ptr(), ctypes.byref(batch),
           self._stream()))
     else:
-      if torch_indices is not None:
-        host_idx = torch_indices.cpu().numpy()
-      else:
-        host_idx = np.ascontiguousarray(indices, dtype=np.int32)
-      _native.check(self._lib.b2r_gather(
-          self._h, batch_size, _native.ptr(host_idx), ctypes.byref(batch),
-          self._stream()))
+      return self._gather_to_host(batch_size, indices, torch_indices)
     return tuple(arrays)
 
   # -- checkpointing (CRB:593-687) -----------------------------------------------------------

@@ -170,6 +170,21 @@ class OutOfGraphPrioritizedReplayBuffer(
         ctypes.byref(used), ctypes.byref(fail_slot), self._stream())
     return status, out, used.value, fail_slot.value
 
+  def add_batch(self, observations, actions, rewards, terminals, *args):
+    """add_batch(observations, actions, rewards, terminals, *extras, priorities): n
+    consecutive `add`s in one native call.  `priorities` is an array of n values or
+    MAX_RECORDED_PRIORITY (every row takes sum_tree.max_recorded_priority as it stands
+    when the row is applied, RA:330-334)."""
+    if not args:
+      raise ValueError('add_batch expects the priorities as its last argument')
+    last = args[-1]
+    if last is MAX_RECORDED_PRIORITY:
+      self._native_add_batch((observations, actions, rewards, terminals) + tuple(args[:-1]),
+                             None, _native.PRIORITY_MAX_RECORDED)
+    else:
+      self._native_add_batch((observations, actions, rewards, terminals) + tuple(args[:-1]),
+                             last, _native.PRIORITY_EXPLICIT)
+
   def sample_index_batch(self, batch_size):
     """Stratified prioritized indices with in-order retries (PRB:142-171).
 

@@ -164,6 +164,20 @@ int b2r_add(b2r_buffer *buf, const void *observation, const void *action,
 int b2r_add_atari(b2r_buffer *buf, const void *observation, int32_t action,
                   float reward, uint8_t terminal, double priority,
                   int priority_mode, b2r_stream stream);
+/* n consecutive add()s of ONE trajectory stream in one call (the loop of
+ * DQNAgent._store_transition over a chunk of steps: an actor that hands over the steps of
+ * an environment in blocks, a vectorised environment with one replay shard per
+ * environment — the frame stacks of a buffer are built from CONSECUTIVE slots, so the
+ * steps of different environments never share one).  Column arrays hold n rows each in
+ * the storage dtypes, HOST.  Exactly the effects of n b2r_add calls in array order
+ * (zero transitions after every terminal == 1, invalid_range, PER priorities;
+ * priorities == NULL with B2R_PRIORITY_MAX_RECORDED), staged together and applied by as
+ * few flush kernels as the staging buffer allows.  A negative explicit priority stops at
+ * its row like the reference's loop would (*added = rows committed before it). */
+int b2r_add_batch(b2r_buffer *buf, int64_t n, const void *observations,
+                  const void *actions, const void *rewards, const void *terminals,
+                  const void *const *extras, const double *priorities, int priority_mode,
+                  int64_t *added, b2r_stream stream);
 int b2r_flush(b2r_buffer *buf, b2r_stream stream);
 
 /* add_count (CRB:177), cursor() (CRB:334-336), invalid_range (CRB:53-77, 285-287). */
@@ -239,6 +253,20 @@ int b2r_gather_device(b2r_buffer *buf, int32_t batch, const int32_t *indices,
 /* Same with HOST indices and HOST outputs (copies inside); synchronises. */
 int b2r_gather(b2r_buffer *buf, int32_t batch, const int32_t *indices,
                const b2r_batch *out, b2r_stream stream);
+/* The OutOfGraph return convention (host arrays, CRB:479-558) at PCIe speed: the batch
+ * is built in a device slab and shipped with ONE copy into `host_slab`, which the
+ * caller allocates page-locked (b2r_gather moves every column into pageable memory with
+ * a copy of its own).  `want`: a non-NULL field means the column is wanted, its value is
+ * ignored.  *host_out receives pointers INTO host_slab for the wanted columns (256-byte
+ * aligned segments); *needed the bytes the slab must hold — call with host_slab == NULL
+ * to ask for the size and the layout only (*host_out then holds the columns' OFFSETS in
+ * the slab; nothing is sampled or copied).  indices: HOST, or DEVICE when indices_on_device != 0 (a
+ * batch sampled by b2r_sample_indices_device never visits the host before the copy).
+ * Synchronises: the arrays are ready when the call returns. */
+int b2r_gather_slab(b2r_buffer *buf, int32_t batch, const int32_t *indices,
+                    int32_t indices_on_device, const b2r_batch *want, void *host_slab,
+                    size_t slab_bytes, b2r_batch *host_out, size_t *needed,
+                    b2r_stream stream);
 /* Device-RNG sampling + gather in one call (two launches). DEVICE; asynchronous. */
 int b2r_sample_transition_batch_device(b2r_buffer *buf, int32_t batch,
                                        uint64_t seed, uint64_t offset,
@@ -412,7 +440,11 @@ int b2r_dqn_loss(const b2r_dqn_args *args, b2r_stream stream);
  * min_probability and batch are taken from `out` (whatever the caller put there is
  * ignored).  out->indices, reward, terminal, action and (prioritized buffers)
  * sampling_probabilities are required.  DEVICE pointers; asynchronous; can be
- * captured in a CUDA graph. */
+ * captured in a CUDA graph.
+ * The logits in `c51` are inputs that exist before the batch is sampled: row r of them
+ * meets whatever transition the sampler draws for row r.  This is the path measured
+ * without a network in the middle; a learner runs b2r_sample_transition_batch_device,
+ * its networks, b2r_c51_loss and b2r_set_priority_device in that order (RA:253-305). */
 int b2r_train_step_device(b2r_buffer *buf, int32_t batch, uint64_t seed,
                           uint64_t offset, const b2r_batch *out,
                           const b2r_c51_args *c51, b2r_stream stream);
@@ -520,6 +552,17 @@ int b2r_actor_destroy(b2r_actor *actor);
 int b2r_actor_reset(b2r_actor *actor, void *state, b2r_stream stream);
 int b2r_actor_record(b2r_actor *actor, void *state, const void *observation,
                      b2r_stream stream);
+
+/* The network's input cast (atari_lib.py:124-125: tf.cast(state, tf.float32) followed by
+ * tf.div(net, 255.)) fused with the layout change the first convolution needs: uint8
+ * frame stacks (images, pixels, stack_size), stack axis innermost — the replay batch's
+ * `state` / `next_state`, the actor's state — to (images, stack_size, pixels) planes of
+ * float32 (half_out == 0: float(u8) / 255 by true division, the reference's values bit
+ * for bit) or float16 (the same quotient rounded once).  One pass over the data instead
+ * of a permute, a cast and a division.  DEVICE pointers; asynchronous. */
+int b2r_stack_to_planes_device(const void *stacks, void *planes, int64_t images,
+                                int64_t pixels, int32_t stack_size, int32_t half_out,
+                                b2r_stream stream);
 
 /* IQN (implicit_quantile_agent.py:166-315): greedy next action from the action
  * network's K quantile samples (:176-188), target quantile values

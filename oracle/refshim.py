@@ -34,6 +34,16 @@ import types
 _TRAVELLING_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
 
 
+
+def _stub_module(name):
+  """An empty module with a real __spec__: importlib.util.find_spec (torch._dynamo probes
+  'tensorflow' with it) raises on modules in sys.modules whose __spec__ is None."""
+  import importlib.machinery
+  mod = types.ModuleType(name)
+  mod.__spec__ = importlib.machinery.ModuleSpec(name, None)
+  return mod
+
+
 def _default_root():
   """/root/reference in the authoring container; on the GPU box the byte-for-byte
   copy of the three replay files that `make -C oracle _ref` made (git-ignored, shipped
@@ -54,7 +64,7 @@ def reference_available():
 
 def _install_stubs():
   if 'tensorflow' not in sys.modules:
-    tf = types.ModuleType('tensorflow')
+    tf = _stub_module('tensorflow')
     tf.logging = types.SimpleNamespace(
         info=lambda *a, **k: None, warning=lambda *a, **k: None)
 
@@ -75,7 +85,7 @@ def _install_stubs():
         Exists=os.path.exists, Open=open, Remove=_remove)
     sys.modules['tensorflow'] = tf
   if 'gin' not in sys.modules:
-    gin = types.ModuleType('gin')
+    gin = _stub_module('gin')
 
     def configurable(*args, **kwargs):
       if len(args) == 1 and callable(args[0]) and not kwargs:
@@ -83,7 +93,7 @@ def _install_stubs():
       return lambda obj: obj
 
     gin.configurable = configurable
-    gin_tf = types.ModuleType('gin.tf')
+    gin_tf = _stub_module('gin.tf')
     gin.tf = gin_tf
     sys.modules['gin'] = gin
     sys.modules['gin.tf'] = gin_tf
@@ -133,7 +143,7 @@ def load_reference_agents():
     tf.__getattr__ = _module_fallback(anything)  # PEP 562: tf.contrib, tf.train, ...
   for name in ('atari_py', 'gym', 'gym.spaces', 'gym.spaces.box', 'cv2'):
     if name not in sys.modules:
-      mod = types.ModuleType(name)
+      mod = _stub_module(name)
       mod.__getattr__ = _module_fallback(anything)
       sys.modules[name] = mod
   gin = sys.modules['gin']

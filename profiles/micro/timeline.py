@@ -21,7 +21,9 @@ NAMES = {
     'c51': {0: 'L-pre start', 1: 'L-pre acquired', 3: 'L softmaxes', 5: 'L projection',
             8: 'L-pre END', 10: 'L-tail start', 11: 'L-tail acquired', 12: 'L-tail loss END',
             9: 'L-tail tree END', 13: 'L-tail row scalars in', 14: 'L-tail log-softmax done'},
-    'tree': {5: 'T tiny start', 6: 'T tiny acquired', 7: 'T tiny END', 12: 'P presort start',
+    'tree': {30: 'T tiny start', 7: 'T tiny / one-CTA END',
+             0: 'T one-CTA start', 1: 'T one-CTA acquired', 5: 'T one-CTA leaf level done',
+             12: 'P presort start',
              14: 'P presort END', 13: 'T apply start', 10: 'T leaf deltas published',
              11: 'T levels released', 15: 'T apply END'},
 }

@@ -236,6 +236,50 @@ def test_gairl_usage_of_the_uniform_buffer_matches_port(gpu):
     assert any(terminals) and not all(terminals)
 
 
+def test_host_batches_are_fresh_arrays_over_pinned_slabs(gpu):
+  """output='numpy' ships the batch in one copy into a page-locked slab and returns views
+  over it (b2r_gather_slab).  The reference returns fresh arrays per call (CRB:416-434):
+  a batch the caller keeps is never overwritten by later calls, and slabs whose views
+  were dropped are reused instead of allocated again."""
+  shape, stack, cap, batch = (12, 10), 4, 300, 16
+  ours = gpu.crb.OutOfGraphReplayBuffer(shape, stack, cap, batch, update_horizon=2)
+  port = PortReplay(shape, stack, cap, batch, update_horizon=2)
+  rng = np.random.RandomState(5)
+  for _ in range(450):
+    row = (rng.randint(0, 256, size=shape).astype(np.uint8), rng.randint(4),
+           np.float32(rng.randn()), int(rng.rand() < 0.1))
+    ours.add(*row)
+    port.add(*row)
+  kept, want = [], []
+  for seed in range(6):
+    np.random.seed(seed)
+    want.append(port.sample_transition_batch())
+    np.random.seed(seed)
+    kept.append(ours.sample_transition_batch())
+  for got, ref in zip(kept, want):  # nothing was overwritten by the later calls
+    for g, w in zip(got, ref):
+      assert g.dtype == w.dtype and g.shape == w.shape
+      assert g.tobytes() == w.tobytes()
+  slabs = sum(len(v) for v in ours._slab_pool.values())
+  assert slabs == 6
+  del kept, got, g
+  for seed in range(6, 12):  # dropped batches: their slabs come round again
+    np.random.seed(seed)
+    ref = port.sample_transition_batch()
+    np.random.seed(seed)
+    got = ours.sample_transition_batch()
+    for g, w in zip(got, ref):
+      assert g.tobytes() == w.tobytes()
+    del got, g
+  assert sum(len(v) for v in ours._slab_pool.values()) == 6
+  # explicit indices and another batch size go through the same path
+  idx = [int(i) for i in want[0][7][:5]]
+  a = ours.sample_transition_batch(batch_size=5, indices=idx)
+  b = port.sample_transition_batch(batch_size=5, indices=idx)
+  for g, w in zip(a, b):
+    assert g.tobytes() == w.tobytes()
+
+
 # ------------------------------------------------------ prioritized buffer ----
 def test_prioritized_reference_known_answers(gpu):
   reference_kats.prioritized_kats(gpu.prb.OutOfGraphPrioritizedReplayBuffer)
@@ -439,6 +483,53 @@ def test_prioritized_full_size_step_matches_oracles(gpu):
   assert retried > 0
   for l, level in enumerate(mem.sum_tree.nodes):
     assert np.array_equal(level.view(np.uint64), want_tree.level(l).view(np.uint64))
+
+
+@pytest.mark.parametrize('prioritized', [False, True])
+def test_add_batch_equals_the_loop_of_adds(gpu, prioritized):
+  """b2r_add_batch: n consecutive adds in one native call leave the buffer exactly as
+  the loop of add() calls does — stores, zero padding after terminals, add_count,
+  invalid_range and (prioritized) every fp64 tree node, for explicit priorities and for
+  the max-recorded sentinel — also when n exceeds the staging queue and the ring wraps.
+  The loop itself is held to the reference elsewhere (fixtures, known answers)."""
+  shape, stack, cap = (9, 7), 4, 257
+  rng = np.random.RandomState(17)
+  n = 700
+  obs = rng.randint(0, 256, size=(n,) + shape).astype(np.uint8)
+  act = rng.randint(0, 6, size=n).astype(np.int32)
+  rew = rng.randn(n).astype(np.float32)
+  term = (rng.rand(n) < 0.07).astype(np.uint8)
+  prio = np.abs(rng.randn(n)) + 0.1
+  make = (gpu.prb.OutOfGraphPrioritizedReplayBuffer if prioritized
+          else gpu.crb.OutOfGraphReplayBuffer)
+  one, many = make(shape, stack, cap, 8), make(shape, stack, cap, 8)
+  chunks = [(0, 1), (1, 40), (40, 41), (41, 400), (400, 700)]
+  for lo, hi in chunks:
+    sentinel = prioritized and lo == 40
+    for k in range(lo, hi):
+      row = (obs[k], int(act[k]), float(rew[k]), int(term[k]))
+      if prioritized:
+        one.add(*row, gpu.prb.MAX_RECORDED_PRIORITY if sentinel else float(prio[k]))
+      else:
+        one.add(*row)
+    cols = (obs[lo:hi], act[lo:hi], rew[lo:hi], term[lo:hi])
+    if prioritized:
+      many.add_batch(*cols, gpu.prb.MAX_RECORDED_PRIORITY if sentinel else prio[lo:hi])
+    else:
+      many.add_batch(*cols)
+    assert one.add_count == many.add_count
+    assert list(one.invalid_range) == list(many.invalid_range)
+  for name in ('observation', 'action', 'reward', 'terminal'):
+    assert one._store[name].tobytes() == many._store[name].tobytes(), name
+  if prioritized:
+    for la, lb in zip(one.sum_tree.nodes, many.sum_tree.nodes):
+      assert np.array_equal(la.view(np.uint64), lb.view(np.uint64))
+    assert one.sum_tree.max_recorded_priority == many.sum_tree.max_recorded_priority
+    with pytest.raises(ValueError, match='nonnegative'):
+      many.add_batch(obs[:3], act[:3], rew[:3], term[:3], np.array([1.0, -2.0, 1.0]))
+    assert many.add_count >= one.add_count + 1  # the row before the bad one was added
+  with pytest.raises(ValueError):
+    many.add_batch(obs[:3, :5], act[:3], rew[:3], term[:3], *([prio[:3]] * prioritized))
 
 
 # ------------------------------------------------------------------- C51 ----

@@ -412,14 +412,16 @@ def test_peer_exchange_times_out_instead_of_hanging(gpu):
   assert 'did not publish' in gpu.native.last_error()
 
 
-@pytest.mark.parametrize('global_batch,bounded', [(256, False), (2048, False),
-                                                  (256, True), (2048, True)])
-def test_sharded_fused_step_matches_oracles(gpu, global_batch, bounded):
+@pytest.mark.parametrize('global_batch,bounded,deferred', [
+    (256, False, False), (2048, False, False), (256, True, False), (2048, True, False),
+    (256, True, True), (2048, True, True)])
+def test_sharded_fused_step_matches_oracles(gpu, global_batch, bounded, deferred):
   """b2r_train_step_sharded_device on 4 emulated ranks (one sampling CTA up to a
   global batch of 256, tiles over each rank's stratum range above): each rank's rows
   (batch columns at its indices, losses, write-back) against the oracles, the rows of
   all ranks partitioning the global batch.  bounded: outputs, logits and launches sized
-  by a bound on the rank's share (max_rows) instead of the global batch."""
+  by a bound on the rank's share (max_rows) instead of the global batch.  deferred: frame
+  copies joined by b2r_join_frames (the row count then travels through the ring slot)."""
   import ctypes
   from dopamine_b200.replay_memory import sharded_replay
   torch, native = gpu.torch, gpu.native
@@ -429,6 +431,8 @@ def test_sharded_fused_step_matches_oracles(gpu, global_batch, bounded):
   exchanges = sharded_replay.PeerExchange.emulated(num_shards)
   rng = np.random.RandomState(8)
   support = gpu.ra.make_support(10., ATOMS)
+  for mem, _, _ in shards:
+    native.check(lib.b2r_set_deferred_frames(mem._h, 1 if deferred else 0))
   outs = []
   # (shard 1 is "hot": it serves well over its even share)
   rows = global_batch * 5 // 8 if bounded else global_batch
@@ -464,6 +468,7 @@ def test_sharded_fused_step_matches_oracles(gpu, global_batch, bounded):
           mem._h, exchanges[g]._h, global_batch, 77, step, ctypes.byref(o['batch']),
           ctypes.byref(args), o['slots'].data_ptr(), o['count'].data_ptr(),
           rows if bounded else 0, native.current_stream()))
+      native.check(lib.b2r_join_frames(mem._h, native.current_stream()))
       torch.cuda.synchronize()
       n = int(o['count'].cpu()[0])
       assert n <= rows
@@ -532,22 +537,25 @@ def test_sharded_step_share_beyond_max_rows_is_latched(gpu, global_batch):
     assert status == native.ERR_UNSUPPORTED, (status, native.last_error())
 
 
-def test_tma_gather_variant_passes_the_gather_parity_suite():
-  """B2R_GATHER=tma selects the kernel that stages frames through cp.async.bulk into
-  shared memory; the variant is fixed per process, so the gather parity tests are
-  re-run in a child process with it (bit-exact batches at 100k / 1M, wrap-around,
-  terminals inside trajectories, fused step)."""
+@pytest.mark.parametrize('variant', ['tma', 'reg'])
+def test_each_gather_variant_passes_the_gather_parity_suite(variant):
+  """The frame copies have two kernels: the TMA-staged one (cp.async.bulk into shared
+  memory on an mbarrier) and the register one (LDG.128 -> PRMT -> STG.128); by default
+  the batch size picks (gather.cu: gather_variant).  B2R_GATHER forces one for a whole
+  process, so the gather parity tests are re-run in a child process with each (bit-exact
+  batches at 100k / 1M, wrap-around, terminals inside trajectories, fused and sharded
+  steps) — every size goes through both kernels."""
   import os
   import subprocess
   import sys
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-  env = dict(os.environ, B2R_GATHER='tma')
+  env = dict(os.environ, B2R_GATHER=variant)
   out = subprocess.run(
       [sys.executable, '-m', 'pytest', '-q', '-x', '-m', 'gpu',
        'tests/test_gpu_parity.py', 'tests/test_gpu_step.py', '-k',
        'gather_full_size or prioritized_full_size or uniform_reference_fixture or '
        'prioritized_reference_fixture or fused_step_matches_oracles or '
-       'sharded_fused_step'],
+       'sharded_fused_step or deferred_frame_copies or host_batches'],
       cwd=root, env=env, capture_output=True, text=True, timeout=900)
   assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
   assert ' passed' in out.stdout
