@@ -64,6 +64,8 @@ def parse_args():
                       'divisor of --steps up to this is used); 1 = one graph launch '
                       'per step')
   p.add_argument('--no-sweep', action='store_true')
+  p.add_argument('--no-early-publish', action='store_true',
+                 help='N > 1: publish shard totals from the sampler only')
   p.add_argument('--no-defer', action='store_true',
                  help='join the frame copies into the stream after every step')
   p.add_argument('--no-cpu-baseline', action='store_true')
@@ -498,7 +500,9 @@ def measure_e2e(torch, wl, batch, steps, update_period=4, pipeline_depth=2,
                              logit_rows=logit_rows)
   if world > 1:
     from dopamine_b200.replay_memory import sharded_replay
-    trainer.set_exchange(sharded_replay.PeerExchange(rank=rank, world_size=world))
+    e2e_exchange = sharded_replay.PeerExchange(rank=rank, world_size=world)
+    e2e_exchange.set_early_publish(True)
+    trainer.set_exchange(e2e_exchange)
   rng = np.random.RandomState(3)
   frames = rng.randint(0, 256, size=(64, 84, 84)).astype(np.uint8)
   online_h = wl.online[:logit_rows].cpu().pin_memory()
@@ -1060,6 +1064,9 @@ def main():
     exchange = None
     if args.exchange == 'p2p':
       exchange = sharded_replay.PeerExchange(rank=rank, world_size=world)
+      # the write-back publishes the shard total for the next step the moment the root
+      # is written (one-CTA tree kernels): the wire latency hides behind its tail
+      exchange.set_early_publish(not args.no_early_publish)
     sharded = sharded_replay.ShardedStep(wl, args.batch * world, world, rank, dist,
                                          exchange=exchange)
     step_fn = sharded.step

@@ -237,6 +237,7 @@ SIGNATURES = {
     'b2r_train_step_sharded_device': (c_int, [
         c_void_p, c_void_p, c_int32, c_uint64, c_uint64, P(Batch), P(C51Args),
         c_void_p, c_void_p, c_int32, c_void_p]),
+    'b2r_exchange_set_early_publish': (c_int, [c_void_p, c_int32]),
     'b2r_exchange_create': (c_int, [c_int32, c_int32, P(c_void_p)]),
     'b2r_exchange_destroy': (c_int, [c_void_p]),
     'b2r_exchange_local_handle': (c_int, [c_void_p, c_void_p]),

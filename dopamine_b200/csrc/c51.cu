@@ -16,6 +16,8 @@
 // read, <= 204 B target + 12 B scalars written (+3 672 B if grad_logits is asked).
 #include "replay.cuh"
 
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 namespace b2r {
@@ -101,6 +103,10 @@ struct LossArgs {
   UpdateArgs<int32_t, float> tree;
   int64_t *err;  // nullable: asynchronous error latch (an action outside [0, A))
   int32_t *count_copy;  // nullable: receives the row count (c51_post_kernel)
+  // c51_post_tree_kernel with a device-side row count (a shard's step): set to 1 when the
+  // kernel has applied the write-back itself (at most 32 rows), so that the one-CTA tree
+  // kernel launched behind it returns at once; left alone otherwise.
+  unsigned int *tree_done;
 };
 
 // One CTA per batch row, one warp per action (rainbow_agent.py:200-293):
@@ -954,12 +960,224 @@ __global__ void __launch_bounds__(kRowWarps * 32) c51_pre_rows_kernel(PreArgs a)
   pre_sync_signal(a.sync);
 }
 
+constexpr int kProjTerms = 6;  // Bellman atoms within dz of an output atom, with slack
+
+// One row of the tail by one warp.  bestp_row / sup_row: this warp's shared-memory rows
+// ([kRowAtoms] floats each).  Writes the row's outputs and returns its new priority.
+__device__ __forceinline__ float c51_post_row(const LossArgs &a,
+                                              const float *__restrict__ scratch,
+                                              int have_stats, int b, int rows, int lane,
+                                              float pmin, float *bestp_row, float *sup_row) {
+  const int N = a.u.num_atoms, A = a.u.num_actions;
+  const float *__restrict__ z = a.u.support;
+  float prio_out = 0.f;
+  // ---- round trip 1
+  int chosen = a.u.actions[b];
+  const float r = a.u.rewards[b];
+  const float term = (float)a.u.terminals[b];
+  const float my_prob = a.u.sampling_probabilities ? a.u.sampling_probabilities[b] : 1.f;
+  float zl[2], bp[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int i = lane + 32 * t;
+    zl[t] = i < N ? z[i] : 0.f;
+    bp[t] = i < N ? scratch[(size_t)b * kPreRow + i] : 0.f;
+  }
+  float2 st = make_float2(0.f, 0.f);  // lane = action: (max, log denominator)
+  if (have_stats && lane < A)
+    st = *reinterpret_cast<const float2 *>(scratch + (size_t)b * kPreRow + kRowAtoms + 2 * lane);
+  B2R_MARK(13);
+  // an action outside [0, A) (tf.gather_nd raises): evaluated for action 0, zero loss,
+  // B2R_ERR_INDEX_RANGE latched
+  const bool bad_action = chosen < 0 || chosen >= A;
+  if (bad_action) chosen = 0;
+  // ---- round trip 2
+  const float *__restrict__ orow = a.u.online_logits + ((size_t)b * A + chosen) * N;
+  float xo[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) xo[t] = lane + 32 * t < N ? orow[lane + 32 * t] : kLogitPad;
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+    if (lane + 32 * t < N) bestp_row[lane + 32 * t] = bp[t];
+  // Bellman support (rainbow_agent.py:229-235)
+  const float live = __fsub_rn(1.0f, term);
+  const float gwt = __fmul_rn(a.u.cumulative_gamma, live);
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+    if (lane + 32 * t < N) sup_row[lane + 32 * t] = __fadd_rn(r, __fmul_rn(gwt, zl[t]));
+  __syncwarp();
+  // log_softmax of the chosen action's online logits (rainbow_agent.py:262-271)
+  float mo, lse, eo0 = 0.f, eo1 = 0.f, den_o = 1.f;
+  if (have_stats && chosen < 32) {
+    mo = __shfl_sync(0xffffffffu, st.x, chosen);
+    lse = __shfl_sync(0xffffffffu, st.y, chosen);
+    if (a.u.grad_logits) {
+      eo0 = expf(__fsub_rn(xo[0], mo));
+      eo1 = expf(__fsub_rn(xo[1], mo));
+      den_o = group_sum<32>(__fadd_rn(eo0, eo1));
+    }
+  } else {
+    mo = group_max<32>(fmaxf(xo[0], xo[1]));
+    eo0 = expf(__fsub_rn(xo[0], mo));
+    eo1 = expf(__fsub_rn(xo[1], mo));
+    den_o = group_sum<32>(__fadd_rn(eo0, eo1));  // pads add exactly 0
+    lse = logf(den_o);
+  }
+  const float lgp[2] = {__fsub_rn(__fsub_rn(xo[0], mo), lse),
+                        __fsub_rn(__fsub_rn(xo[1], mo), lse)};
+  B2R_MARK(14);
+
+  // projection (RA:381-494): see c51_loss_rows_kernel for the interval argument
+  const float *sup = sup_row, *next_p = bestp_row;
+  const float z0 = __shfl_sync(0xffffffffu, zl[0], 0);
+  const float z1 = __shfl_sync(0xffffffffu, zl[0], 1);
+  const float zlast = __shfl_sync(0xffffffffu, N > 32 ? zl[1] : zl[0], (N - 1) & 31);
+  const float dz = __fsub_rn(z1, z0);
+  float tg[2] = {0.f, 0.f};
+  if (gwt == 0.f) {
+    // terminal row: every s_j is r, so hat(i, .) is one number, and it is 0 for all but
+    // the (at most two) atoms next to clip(r)
+    const float clipped = fminf(fmaxf(sup[0], z0), zlast);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int i = lane + 32 * t;
+      const float gap = fabsf(__fsub_rn(clipped, zl[t]));
+      if (i < N && gap < dz) {
+        float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
+        hat = fminf(fmaxf(hat, 0.f), 1.f);
+        float acc = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < N; ++j) acc = __fadd_rn(acc, __fmul_rn(hat, next_p[j]));
+        tg[t] = acc;
+      }
+    }
+  } else {
+    int jl[2], jh[2];
+    const float inv = __fdividef(1.0f, gwt * dz);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int i = lane + 32 * t;
+      jl[t] = 0;
+      jh[t] = i < N ? N - 1 : -1;
+      if (gwt > 0.f && i < N) {
+        const float lo = (zl[t] - dz - r - gwt * z0) * inv;
+        const float hi = (zl[t] + dz - r - gwt * z0) * inv;
+        if (i > 0 && lo > 0.f) jl[t] = min(N - 1, (int)fminf(lo, 1e6f));
+        if (i < N - 1 && hi < (float)(N - 2)) jh[t] = max(0, (int)fmaxf(hi, -1e6f) + 1);
+      }
+    }
+    const bool narrow = jh[0] - jl[0] < kProjTerms && jh[1] - jl[1] < kProjTerms;
+    if (__all_sync(0xffffffffu, narrow)) {
+      float term_v[2][kProjTerms];
+      bool term_on[2][kProjTerms];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+#pragma unroll
+        for (int k = 0; k < kProjTerms; ++k) {
+          const int j = jl[t] + k;
+          const bool in = j <= jh[t];
+          const int jj = in ? j : 0;
+          const float clipped = fminf(fmaxf(sup[jj], z0), zlast);
+          const float gap = fabsf(__fsub_rn(clipped, zl[t]));
+          float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
+          hat = fminf(fmaxf(hat, 0.f), 1.f);
+          term_v[t][k] = __fmul_rn(hat, next_p[jj]);
+          term_on[t][k] = in && gap < dz;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < kProjTerms; ++k)
+          if (term_on[t][k]) acc = __fadd_rn(acc, term_v[t][k]);
+        tg[t] = acc;
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        float acc = 0.f;
+#pragma unroll 1
+        for (int j = jl[t]; j <= jh[t]; ++j) {
+          const float clipped = fminf(fmaxf(sup[j], z0), zlast);
+          const float gap = fabsf(__fsub_rn(clipped, zl[t]));
+          if (gap < dz) {
+            float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
+            hat = fminf(fmaxf(hat, 0.f), 1.f);
+            acc = __fadd_rn(acc, __fmul_rn(hat, next_p[j]));
+          }
+        }
+        tg[t] = acc;
+      }
+    }
+  }
+  float ce_part = 0.f, tsum_part = 0.f;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int i = lane + 32 * t;
+    if (i < N) {
+      if (a.u.target) a.u.target[(size_t)b * N + i] = tg[t];
+      ce_part = __fadd_rn(ce_part, __fmul_rn(tg[t], lgp[t]));
+      tsum_part = __fadd_rn(tsum_part, tg[t]);
+    }
+  }
+
+  // cross entropy (RA:262-271), priority (RA:290), weight (RA:279-280)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ce_part = __fadd_rn(ce_part, __shfl_xor_sync(0xffffffffu, ce_part, o));
+    tsum_part = __fadd_rn(tsum_part, __shfl_xor_sync(0xffffffffu, tsum_part, o));
+  }
+  float ce = -ce_part;
+  const float tsum = tsum_part;
+  if (bad_action) {
+    ce = 0.f;
+    if (lane == 0 && a.err != nullptr && a.err[0] == 0) {
+      a.err[0] = B2R_ERR_INDEX_RANGE;
+      a.err[1] = b;
+    }
+  }
+  float w = 1.f;
+  if (a.u.sampling_probabilities) {
+    const float wmax = __fdiv_rn(1.0f, sqrtf(__fadd_rn(pmin, 1e-10f)));
+    const float raw = __fdiv_rn(1.0f, sqrtf(__fadd_rn(my_prob, 1e-10f)));
+    w = __fdiv_rn(raw, wmax);
+  }
+  prio_out = sqrtf(__fadd_rn(ce, 1e-10f));
+  if (lane == 0) {
+    a.u.loss[b] = ce;
+    a.u.priorities[b] = prio_out;
+    if (a.u.weights) a.u.weights[b] = w;
+    a.weighted[b] = __fmul_rn(w, ce);
+  }
+  if (a.u.grad_logits) {
+    const float scale = __fmul_rn(w, __fdiv_rn(1.0f, (float)rows));
+    float *g = a.u.grad_logits + (size_t)b * A * N;
+    float v[2] = {0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int i = lane + 32 * t;
+      if (i < N) {
+        const float p = __fdiv_rn(t == 0 ? eo0 : eo1, den_o);
+        v[t] = __fmul_rn(__fsub_rn(__fmul_rn(p, tsum), tg[t]), scale);
+      }
+    }
+    for (int act = 0; act < A; ++act) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int i = lane + 32 * t;
+        if (i < N) g[act * N + i] = act == chosen ? v[t] : 0.f;
+      }
+    }
+  }
+  return prio_out;
+}
+
 // The tail: one warp per row, kRowWarps rows per CTA, lanes own atoms lane and lane + 32.
 // Everything a row needs arrives in two memory round trips (the row's scalars, the
 // greedy action's probabilities and the statistics of all actions; then the chosen
 // action's online logits); the candidate terms of a projected atom are evaluated side by
 // side and added in ascending j, as the dense form adds them.
-constexpr int kProjTerms = 6;  // Bellman atoms within dz of an output atom, with slack
 
 __global__ void __launch_bounds__(kRowWarps * 32)
 c51_post_kernel(LossArgs a, const float *__restrict__ scratch, int have_stats) {
@@ -968,8 +1186,6 @@ c51_post_kernel(LossArgs a, const float *__restrict__ scratch, int have_stats) {
   __shared__ float s_red[kRowWarps];
   __shared__ bool s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N = a.u.num_atoms, A = a.u.num_actions;
-  const float *__restrict__ z = a.u.support;
   B2R_MARK(10);
   pdl_release();
   pdl_acquire();
@@ -998,206 +1214,8 @@ c51_post_kernel(LossArgs a, const float *__restrict__ scratch, int have_stats) {
     }
   }
 
-  if (row_ok) {
-    // ---- round trip 1
-    int chosen = a.u.actions[b];
-    const float r = a.u.rewards[b];
-    const float term = (float)a.u.terminals[b];
-    const float my_prob = a.u.sampling_probabilities ? a.u.sampling_probabilities[b] : 1.f;
-    float zl[2], bp[2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int i = lane + 32 * t;
-      zl[t] = i < N ? z[i] : 0.f;
-      bp[t] = i < N ? scratch[(size_t)b * kPreRow + i] : 0.f;
-    }
-    float2 st = make_float2(0.f, 0.f);  // lane = action: (max, log denominator)
-    if (have_stats && lane < A)
-      st = *reinterpret_cast<const float2 *>(scratch + (size_t)b * kPreRow + kRowAtoms + 2 * lane);
-    B2R_MARK(13);
-    // an action outside [0, A) (tf.gather_nd raises): evaluated for action 0, zero loss,
-    // B2R_ERR_INDEX_RANGE latched
-    const bool bad_action = chosen < 0 || chosen >= A;
-    if (bad_action) chosen = 0;
-    // ---- round trip 2
-    const float *__restrict__ orow = a.u.online_logits + ((size_t)b * A + chosen) * N;
-    float xo[2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t) xo[t] = lane + 32 * t < N ? orow[lane + 32 * t] : kLogitPad;
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-      if (lane + 32 * t < N) s_bestp[warp][lane + 32 * t] = bp[t];
-    // Bellman support (rainbow_agent.py:229-235)
-    const float live = __fsub_rn(1.0f, term);
-    const float gwt = __fmul_rn(a.u.cumulative_gamma, live);
-#pragma unroll
-    for (int t = 0; t < 2; ++t)
-      if (lane + 32 * t < N) s_sup[warp][lane + 32 * t] = __fadd_rn(r, __fmul_rn(gwt, zl[t]));
-    __syncwarp();
-    // log_softmax of the chosen action's online logits (rainbow_agent.py:262-271)
-    float mo, lse, eo0 = 0.f, eo1 = 0.f, den_o = 1.f;
-    if (have_stats && chosen < 32) {
-      mo = __shfl_sync(0xffffffffu, st.x, chosen);
-      lse = __shfl_sync(0xffffffffu, st.y, chosen);
-      if (a.u.grad_logits) {
-        eo0 = expf(__fsub_rn(xo[0], mo));
-        eo1 = expf(__fsub_rn(xo[1], mo));
-        den_o = group_sum<32>(__fadd_rn(eo0, eo1));
-      }
-    } else {
-      mo = group_max<32>(fmaxf(xo[0], xo[1]));
-      eo0 = expf(__fsub_rn(xo[0], mo));
-      eo1 = expf(__fsub_rn(xo[1], mo));
-      den_o = group_sum<32>(__fadd_rn(eo0, eo1));  // pads add exactly 0
-      lse = logf(den_o);
-    }
-    const float lgp[2] = {__fsub_rn(__fsub_rn(xo[0], mo), lse),
-                          __fsub_rn(__fsub_rn(xo[1], mo), lse)};
-    B2R_MARK(14);
-
-    // projection (RA:381-494): see c51_loss_rows_kernel for the interval argument
-    const float *sup = s_sup[warp], *next_p = s_bestp[warp];
-    const float z0 = __shfl_sync(0xffffffffu, zl[0], 0);
-    const float z1 = __shfl_sync(0xffffffffu, zl[0], 1);
-    const float zlast = __shfl_sync(0xffffffffu, N > 32 ? zl[1] : zl[0], (N - 1) & 31);
-    const float dz = __fsub_rn(z1, z0);
-    float tg[2] = {0.f, 0.f};
-    if (gwt == 0.f) {
-      // terminal row: every s_j is r, so hat(i, .) is one number, and it is 0 for all but
-      // the (at most two) atoms next to clip(r)
-      const float clipped = fminf(fmaxf(sup[0], z0), zlast);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int i = lane + 32 * t;
-        const float gap = fabsf(__fsub_rn(clipped, zl[t]));
-        if (i < N && gap < dz) {
-          float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
-          hat = fminf(fmaxf(hat, 0.f), 1.f);
-          float acc = 0.f;
-#pragma unroll 1
-          for (int j = 0; j < N; ++j) acc = __fadd_rn(acc, __fmul_rn(hat, next_p[j]));
-          tg[t] = acc;
-        }
-      }
-    } else {
-      int jl[2], jh[2];
-      const float inv = __fdividef(1.0f, gwt * dz);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int i = lane + 32 * t;
-        jl[t] = 0;
-        jh[t] = i < N ? N - 1 : -1;
-        if (gwt > 0.f && i < N) {
-          const float lo = (zl[t] - dz - r - gwt * z0) * inv;
-          const float hi = (zl[t] + dz - r - gwt * z0) * inv;
-          if (i > 0 && lo > 0.f) jl[t] = min(N - 1, (int)fminf(lo, 1e6f));
-          if (i < N - 1 && hi < (float)(N - 2)) jh[t] = max(0, (int)fmaxf(hi, -1e6f) + 1);
-        }
-      }
-      const bool narrow = jh[0] - jl[0] < kProjTerms && jh[1] - jl[1] < kProjTerms;
-      if (__all_sync(0xffffffffu, narrow)) {
-        float term_v[2][kProjTerms];
-        bool term_on[2][kProjTerms];
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-#pragma unroll
-          for (int k = 0; k < kProjTerms; ++k) {
-            const int j = jl[t] + k;
-            const bool in = j <= jh[t];
-            const int jj = in ? j : 0;
-            const float clipped = fminf(fmaxf(sup[jj], z0), zlast);
-            const float gap = fabsf(__fsub_rn(clipped, zl[t]));
-            float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
-            hat = fminf(fmaxf(hat, 0.f), 1.f);
-            term_v[t][k] = __fmul_rn(hat, next_p[jj]);
-            term_on[t][k] = in && gap < dz;
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          float acc = 0.f;
-#pragma unroll
-          for (int k = 0; k < kProjTerms; ++k)
-            if (term_on[t][k]) acc = __fadd_rn(acc, term_v[t][k]);
-          tg[t] = acc;
-        }
-      } else {
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          float acc = 0.f;
-#pragma unroll 1
-          for (int j = jl[t]; j <= jh[t]; ++j) {
-            const float clipped = fminf(fmaxf(sup[j], z0), zlast);
-            const float gap = fabsf(__fsub_rn(clipped, zl[t]));
-            if (gap < dz) {
-              float hat = __fsub_rn(1.0f, __fdiv_rn(gap, dz));
-              hat = fminf(fmaxf(hat, 0.f), 1.f);
-              acc = __fadd_rn(acc, __fmul_rn(hat, next_p[j]));
-            }
-          }
-          tg[t] = acc;
-        }
-      }
-    }
-    float ce_part = 0.f, tsum_part = 0.f;
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int i = lane + 32 * t;
-      if (i < N) {
-        if (a.u.target) a.u.target[(size_t)b * N + i] = tg[t];
-        ce_part = __fadd_rn(ce_part, __fmul_rn(tg[t], lgp[t]));
-        tsum_part = __fadd_rn(tsum_part, tg[t]);
-      }
-    }
-
-    // cross entropy (RA:262-271), priority (RA:290), weight (RA:279-280)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ce_part = __fadd_rn(ce_part, __shfl_xor_sync(0xffffffffu, ce_part, o));
-      tsum_part = __fadd_rn(tsum_part, __shfl_xor_sync(0xffffffffu, tsum_part, o));
-    }
-    float ce = -ce_part;
-    const float tsum = tsum_part;
-    if (bad_action) {
-      ce = 0.f;
-      if (lane == 0 && a.err != nullptr && a.err[0] == 0) {
-        a.err[0] = B2R_ERR_INDEX_RANGE;
-        a.err[1] = b;
-      }
-    }
-    float w = 1.f;
-    if (a.u.sampling_probabilities) {
-      const float wmax = __fdiv_rn(1.0f, sqrtf(__fadd_rn(pmin, 1e-10f)));
-      const float raw = __fdiv_rn(1.0f, sqrtf(__fadd_rn(my_prob, 1e-10f)));
-      w = __fdiv_rn(raw, wmax);
-    }
-    if (lane == 0) {
-      a.u.loss[b] = ce;
-      a.u.priorities[b] = sqrtf(__fadd_rn(ce, 1e-10f));
-      if (a.u.weights) a.u.weights[b] = w;
-      a.weighted[b] = __fmul_rn(w, ce);
-    }
-    if (a.u.grad_logits) {
-      const float scale = __fmul_rn(w, __fdiv_rn(1.0f, (float)rows));
-      float *g = a.u.grad_logits + (size_t)b * A * N;
-      float v[2] = {0.f, 0.f};
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int i = lane + 32 * t;
-        if (i < N) {
-          const float p = __fdiv_rn(t == 0 ? eo0 : eo1, den_o);
-          v[t] = __fmul_rn(__fsub_rn(__fmul_rn(p, tsum), tg[t]), scale);
-        }
-      }
-      for (int act = 0; act < A; ++act) {
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int i = lane + 32 * t;
-          if (i < N) g[act * N + i] = act == chosen ? v[t] : 0.f;
-        }
-      }
-    }
-  }
+  if (row_ok)
+    c51_post_row(a, scratch, have_stats, b, rows, lane, pmin, s_bestp[warp], s_sup[warp]);
   B2R_MARK_END(12);
 
   // ---- mean weighted loss: the last CTA to finish reduces in a fixed order.
@@ -1222,6 +1240,71 @@ c51_post_kernel(LossArgs a, const float *__restrict__ scratch, int have_stats) {
     for (int k = 0; k < kRowWarps; ++k) total = __fadd_rn(total, s_red[k]);
     *a.u.mean_weighted_loss = __fdiv_rn(total, (float)a.u.batch);
     *a.ticket = 0u;  // ready for the next launch
+  }
+}
+
+// The agent's batch (<= 32 rows): the tail and the priority write-back
+// (prioritized_replay_buffer.py:203-214) as ONE thread-block cluster of 8 CTAs.  CTAs 1..7
+// compute five rows each (one warp per row); CTA 0 is the tree's: its warp l owns tree
+// level l, and what that needs from the sampled indices alone — node loads, grouping of
+// the entries by node — runs while the rows are projected (tree_update_tiny_issue).  The
+// new priorities go from the row warps' registers into CTA 0's shared memory (distributed
+// shared memory), one cluster barrier replaces the kernel boundary, and CTA 0 finishes
+// the update (tree_update_tiny_finish).  Measured (profiles/r2/README.md): 15.3 us per
+// step at batch 32 against 16.3 us with the tail and the write-back as two kernels.
+constexpr int kPostClusterCtas = 8;
+constexpr int kPostRowWarps = 5;  // rows per row CTA: 7 row CTAs x 5 >= 32 rows
+
+__global__ void __launch_bounds__(1024)
+c51_post_tree_kernel(LossArgs a, const float *__restrict__ scratch, int have_stats) {
+  __shared__ float s_bestp[kPostRowWarps][kRowAtoms];
+  __shared__ float s_sup[kPostRowWarps][kRowAtoms];
+  __shared__ float s_prio[kTinyBatch];      // (CTA 0's copy is the one that is used)
+  __shared__ float s_weighted[kTinyBatch];
+  namespace cg = cooperative_groups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  cg::cluster_group cluster = cg::this_cluster();
+  B2R_MARK(10);
+  pdl_release();
+  pdl_acquire();
+  B2R_MARK(11);
+  // (a shard's step: the row count is on the device, and the write-back rides along only
+  // when it turns out to be at most 32 rows — else the tree kernel behind this one does it)
+  const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
+  const bool with_tree = rows <= kTinyBatch;
+  // CTA 0 is the tree's: warp l owns level l, loads its nodes and groups its entries now.
+  // CTAs 1..7 are the rows': warps 0..4 compute one row each (and stride on).
+  TinyLoads tl;
+  const bool tree_cta = blockIdx.x == 0;
+  if (tree_cta) {
+    if (a.count_copy != nullptr && threadIdx.x == 0) *a.count_copy = rows;
+    if (with_tree) tree_update_tiny_issue(a.tree, warp, lane, &tl);
+  } else if (warp < kPostRowWarps) {
+    const float pmin = a.u.sampling_probabilities ? *a.u.min_probability : INFINITY;
+    for (int b = ((int)blockIdx.x - 1) * kPostRowWarps + warp; b < rows;
+         b += (kPostClusterCtas - 1) * kPostRowWarps) {
+      __syncwarp();  // (this warp's shared rows are free again)
+      const float prio = c51_post_row(a, scratch, have_stats, b, rows, lane, pmin,
+                                      s_bestp[warp], s_sup[warp]);
+      if (lane == 0 && with_tree) {
+        cluster.map_shared_rank(s_prio, 0)[b] = prio;
+        if (a.u.mean_weighted_loss != nullptr)
+          cluster.map_shared_rank(s_weighted, 0)[b] = a.weighted[b];
+      }
+    }
+  }
+  B2R_MARK_END(12);
+  cluster_sync_relacq();  // the rows' priorities are in CTA 0's shared memory
+  if (!tree_cta || !with_tree) return;
+  const double v = (tl.in && !tl.use_max) ? (double)s_prio[lane] : 0.0;
+  tree_update_tiny_finish(a.tree, warp, lane, tl, v);
+  if (a.tree_done != nullptr && threadIdx.x == 0) *a.tree_done = 1u;
+  B2R_MARK_END(9);
+  if (a.u.mean_weighted_loss != nullptr && warp == 0) {
+    // fixed order: row k in lane k, butterfly, as the other instances reduce
+    float acc = lane < rows ? s_weighted[lane] : 0.f;
+    acc = group_sum<32>(acc);
+    if (lane == 0) *a.u.mean_weighted_loss = __fdiv_rn(acc, (float)rows);
   }
 }
 
@@ -1357,8 +1440,27 @@ int c51_pre_launch(const b2r_c51_args *args, int rows, float *scratch, const Pre
 }
 
 // The tail over the sampled rows.
+// expected_rows < 0: the host knows the rows (args->batch); else a shard's step, whose
+// device-side count is expected to be about that many.
+bool c51_post_takes_tree(const b2r_c51_args *args, const b2r_tree *tree,
+                         int64_t expected_rows) {
+  // B2R_POST_TREE=0: tail and write-back as two kernels (comparison runs)
+  static const bool on = [] {
+    const char *e = std::getenv("B2R_POST_TREE");
+    return e == nullptr || std::atoi(e) != 0;
+  }();
+  const bool counted = args->batch_count != nullptr;
+  const bool small = counted ? (expected_rows >= 0 && expected_rows <= kTinyBatch &&
+                                args->batch <= 256 && args->mean_weighted_loss == nullptr)
+                             : args->batch <= kTinyBatch;
+  return on && tree != nullptr && small && tree_tiny_enabled() && tree->depth + 1 <= 32 &&
+         (args->sampling_probabilities == nullptr || args->min_probability != nullptr);
+}
+
 int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_stats,
-                    cudaStream_t s, int64_t *err, int32_t *count_copy) {
+                    cudaStream_t s, int64_t *err, int32_t *count_copy, b2r_tree *tree,
+                    const int32_t *indices, unsigned int *tree_done,
+                    const b2r_exchange *publish) {
   if (!args || args->batch <= 0 || !scratch)
     return fail(B2R_ERR_INVALID_ARGUMENT, "bad C51 shape");
   if (args->batch_count && args->mean_weighted_loss)
@@ -1372,10 +1474,43 @@ int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_sta
   a.fuse_tree = 0;
   a.err = err;
   a.count_copy = count_copy;
+  a.tree_done = nullptr;
   a.warps = 0;
   B2R_TRY(ensure_loss_scratch(args->batch));
   a.weighted = g_weighted;
   a.ticket = g_ticket;
+  if (tree != nullptr) {
+    if (args->batch_count != nullptr && tree_done == nullptr)
+      return fail(B2R_ERR_INVALID_ARGUMENT, "a counted batch needs the tree_done flag");
+    set_tree_window(tree->heap, (size_t)tree->leaves * 16);
+    a.fuse_tree = 1;
+    a.tree_done = tree_done;
+    a.tree.heap = tree->heap;
+    a.tree.depth = tree->depth;
+    a.tree.leaves = tree->leaves;
+    a.tree.n = args->batch < kTinyBatch ? args->batch : kTinyBatch;
+    a.tree.padded = 32;
+    a.tree.indices = indices;
+    a.tree.values = args->priorities;
+    a.tree.mode = nullptr;
+    a.tree.k_base = 0;
+    a.tree.delta = tree->delta;
+    a.tree.max_rec = tree->max_rec;
+    a.tree.status = tree->status;
+    a.tree.n_dev = args->batch_count;
+    if (publish != nullptr && publish->world > 1 && publish->connected) {
+      a.tree.publish = publish->args_dev;
+      a.tree.publish_world = publish->world;
+      a.tree.publish_rank = publish->rank;
+    }
+    int warps = tree->depth + 1;
+    if (warps < kPostRowWarps) warps = kPostRowWarps;
+    B2R_CUDA(launch_prio_cluster(c51_post_tree_kernel, dim3(kPostClusterCtas),
+                                 dim3(warps * 32), 0, s, chain_priority(),
+                                 kPostClusterCtas, a, scratch, have_stats));
+    B2R_LAUNCHED();
+    return B2R_OK;
+  }
   const dim3 grid((args->batch + kRowWarps - 1) / kRowWarps), block(kRowWarps * 32);
   B2R_CUDA(launch(c51_post_kernel, grid, block, 0, s, a, scratch, have_stats));
   B2R_LAUNCHED();
@@ -1399,6 +1534,7 @@ int c51_loss_launch(const b2r_c51_args *args, cudaStream_t s, b2r_tree *tree,
   a.fuse_tree = 0;
   a.err = nullptr;
   a.count_copy = nullptr;
+  a.tree_done = nullptr;
   if (tree != nullptr) {
     if (!c51_can_fuse_writeback(args, tree))
       return fail(B2R_ERR_INVALID_ARGUMENT, "this batch cannot fuse its write-back");

@@ -144,6 +144,17 @@ cudaError_t launch(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem
                      static_cast<Args &&>(args)...);
 }
 
+// Barrier over the CTAs of a thread-block cluster with release / acquire semantics at
+// cluster scope: what the threads of the cluster wrote before it (shared memory of any
+// CTA of the cluster, global memory) is visible to all of them after it.
+// (SASS: MEMBAR.ALL.GPU, UCGABAR_ARV, UCGABAR_WAIT, CCTL.IVALL — the release is a
+// GPU-wide fence, as in cooperative_groups' cluster.sync(); a cheaper hand-over would
+// send the few words through st.async onto an mbarrier of the receiving CTA.)
+__device__ __forceinline__ void cluster_sync_relacq() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
 __device__ __forceinline__ void pdl_release() {
   asm volatile("griddepcontrol.launch_dependents;");
 }

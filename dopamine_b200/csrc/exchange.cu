@@ -14,6 +14,16 @@ namespace {
 constexpr size_t kMailboxBytes = 2 * b2r::kMaxShards * 2 * sizeof(uint64_t);
 }
 
+namespace {
+// The kernel arguments as the tree kernels' publish hook reads them (device memory).
+int upload_args(b2r_exchange *x) {
+  b2r::ExchangeArgs a;
+  b2r::fill_exchange_args(x, &a);
+  B2R_CUDA(cudaMemcpy(x->args_dev, &a, sizeof(a), cudaMemcpyHostToDevice));
+  return B2R_OK;
+}
+}  // namespace
+
 extern "C" {
 
 int b2r_exchange_create(int32_t world, int32_t rank, b2r_exchange **out) {
@@ -34,10 +44,13 @@ int b2r_exchange_create(int32_t world, int32_t rank, b2r_exchange **out) {
   B2R_CUDA(cudaMemset(x->mailbox, 0, kMailboxBytes));
   B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&x->seq), 8));
   B2R_CUDA(cudaMemset(x->seq, 0, 8));
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&x->pub), 16));
+  B2R_CUDA(cudaMemset(x->pub, 0, 16));
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&x->args_dev), sizeof(b2r::ExchangeArgs)));
   B2R_CUDA(cudaDeviceSynchronize());
   x->connected = world == 1;
   *out = x;
-  return B2R_OK;
+  return world == 1 ? upload_args(x) : B2R_OK;
 }
 
 int b2r_exchange_destroy(b2r_exchange *x) {
@@ -47,6 +60,8 @@ int b2r_exchange_destroy(b2r_exchange *x) {
     if (x->opened[g] && x->peer[g]) cudaIpcCloseMemHandle(x->peer[g]);
   cudaFree(x->mailbox);
   cudaFree(x->seq);
+  cudaFree(x->pub);
+  cudaFree(x->args_dev);
   delete x;
   return B2R_OK;
 }
@@ -77,7 +92,7 @@ int b2r_exchange_connect(b2r_exchange *x, const void *handles) {
     x->opened[g] = true;
   }
   x->connected = true;
-  return B2R_OK;
+  return upload_args(x);
 }
 
 int b2r_exchange_connect_pointers(b2r_exchange *x, void *const *mailboxes) {
@@ -85,7 +100,7 @@ int b2r_exchange_connect_pointers(b2r_exchange *x, void *const *mailboxes) {
   for (int g = 0; g < x->world; ++g)
     x->peer[g] = g == x->rank ? x->mailbox : static_cast<uint64_t *>(mailboxes[g]);
   x->connected = true;
-  return B2R_OK;
+  return upload_args(x);
 }
 
 void *b2r_exchange_mailbox(b2r_exchange *x) { return x ? x->mailbox : nullptr; }
@@ -94,6 +109,12 @@ int b2r_exchange_set_timeout(b2r_exchange *x, double seconds) {
   if (!x || !(seconds > 0.0))
     return fail(B2R_ERR_INVALID_ARGUMENT, "timeout must be positive");
   x->timeout_ns = (int64_t)(seconds * 1e9);
+  return x->connected ? upload_args(x) : B2R_OK;
+}
+
+int b2r_exchange_set_early_publish(b2r_exchange *x, int32_t on) {
+  if (!x) return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
+  x->early_publish = on != 0;
   return B2R_OK;
 }
 

@@ -132,7 +132,8 @@ int join_frames(b2r_buffer *b, cudaStream_t stream) {
   return B2R_OK;
 }
 
-int flush_queue(b2r_buffer *b, cudaStream_t stream, bool split) {
+int flush_queue(b2r_buffer *b, cudaStream_t stream, bool split,
+                const b2r_exchange *publish) {
   if (b->q_entries == 0) return B2R_OK;
   // the new rows overwrite ring slots that deferred frame copies may still be reading
   B2R_TRY(join_frames(b, stream));
@@ -173,7 +174,7 @@ int flush_queue(b2r_buffer *b, cudaStream_t stream, bool split) {
     if (per_entry < 1) per_entry = 1;
     if (per_entry > 8) per_entry = 8;
     B2R_TRY(flush_fused(b->tree, b->q_entries, hh.slots, hh.prio, hh.mode, p, per_entry,
-                        stream));
+                        stream, publish));
     b->ctx_dirty = false;
     B2R_CUDA(cudaEventRecord(s->done, stream));
     s->in_flight = true;
@@ -198,7 +199,7 @@ int flush_queue(b2r_buffer *b, cudaStream_t stream, bool split) {
     // prioritized_replay_buffer.py:139-140: sum_tree.set(cursor, priority) per row,
     // in add order (zero transitions carry priority 0).
     B2R_TRY((tree_apply<int64_t, double>(b->tree, b->q_entries, hd.slots, hd.prio,
-                                         hd.mode, stream)));
+                                         hd.mode, stream, nullptr, -1, 0, publish)));
   }
   AddParams p;
   p.n_entries = b->q_entries;

@@ -65,16 +65,6 @@ __device__ __forceinline__ int block_scan_flag(bool flag, int *warp_counts,
   return before + within;
 }
 
-// Shard totals exchanged through peer memory (see exchange_totals in sample.cu).
-constexpr int kMaxShards = 16;
-struct ExchangeArgs {
-  uint64_t *local;             // this rank's mailbox [2 parities][world][2 words];
-                               // nullptr: no exchange
-  uint64_t *peer[kMaxShards];  // the peers' mailboxes (peer-mapped device pointers)
-  uint64_t *seq;               // device step counter, in lockstep on all ranks
-  int64_t timeout_ns;
-};
-
 // Completion hand-shake between the first half of the C51 loss (c51.cu: c51_pre_*,
 // launched on a forked stream beside the sampler because it needs the network outputs
 // only) and the sampler of the same step.  The loss tail must follow BOTH; a kernel node
@@ -349,13 +339,23 @@ struct b2r_exchange {
   bool opened[b2r::kMaxShards] = {false};  // peer[g] came from cudaIpcOpenMemHandle
   bool connected = false;
   int64_t timeout_ns = 2000000000ll;
+  uint64_t *pub = nullptr;              // device [2]: ExchangeArgs::pub
+  b2r::ExchangeArgs *args_dev = nullptr;  // device copy of the kernel arguments (the tree
+                                          // kernels' publish hook reads it from there)
+  // b2r_exchange_set_early_publish: the kernel that leaves the tree final for the next
+  // sharded step publishes the shard total itself, and the staged adds of a step call are
+  // flushed at the END of that call (they become visible to the next step's sampler).
+  bool early_publish = false;
 };
 
 namespace b2r {
 // Applies the staged adds.  split: the staged rows are copied and written to the
 // ring on the buffer's side stream while the priorities go into the tree on
 // `stream`; `stream` then waits for the rows, so callers see no difference.
-int flush_queue(b2r_buffer *buf, cudaStream_t stream, bool split = false);
+// publish (nullable): the flush leaves the tree final for the next sharded step (see
+// tree_apply).
+int flush_queue(b2r_buffer *buf, cudaStream_t stream, bool split = false,
+                const b2r_exchange *publish = nullptr);
 // Makes `stream` wait for every deferred frame copy queued so far (no-op otherwise).
 int join_frames(b2r_buffer *buf, cudaStream_t stream);
 void fill_exchange_args(const b2r_exchange *x, ExchangeArgs *out);
@@ -382,7 +382,7 @@ int ensure_ctx(b2r_buffer *buf, cudaStream_t stream);
 int tree_small_max();
 int flush_fused(b2r_tree *tree, int n, const int64_t *slots, const double *prio,
                 const uint8_t *mode, const AddParams &rows, int row_blocks_per_entry,
-                cudaStream_t stream);
+                cudaStream_t stream, const b2r_exchange *publish = nullptr);
 int ensure_inv_slots(b2r_buffer *buf, int64_t n);
 // Row flags for `rows` rows (RowFlags; all fields nullptr when the hand-over is off:
 // B2R_ROW_FLAGS=0, the thread sampler).

@@ -81,39 +81,32 @@ struct PerSampleArgs {
   int out_cap;
 };
 
-__device__ __forceinline__ void st_sys_u64(uint64_t *p, uint64_t v) {
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ uint64_t ld_sys_u64(const uint64_t *p) {
-  uint64_t v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
 
-// All-gather of one fp64 per rank through peer memory (NVLink / NVSwitch): thread g
-// stores this rank's root total straight into rank g's mailbox and then polls its
-// own mailbox for rank g's.  Each total travels as two 8-byte words that carry half
-// of the payload and the step number in their low 32 bits (the flag is in-band, as
-// in NCCL's LL protocol), so no fence or ordering between the stores is needed.
-// Mailbox slots alternate with the parity of the step: a rank can only be one step
-// ahead of a peer, which has then finished reading the other parity.
-// A peer that does not answer within the timeout latches B2R_ERR_EXCHANGE (and
-// later launches skip the wait), so a lost rank cannot hang the GPU.
-__device__ __forceinline__ void exchange_publish(const ExchangeArgs &x, int world,
-                                                 int rank, double local_total,
-                                                 uint64_t seq) {
-  const int g = threadIdx.x;
-  if (g >= world || g == rank) return;
-  const uint32_t tag = (uint32_t)seq;
-  const uint64_t bits = (uint64_t)__double_as_longlong(local_total);
-  uint64_t *dst = x.peer[g] + ((size_t)(seq & 1) * world + rank) * 2;
-  st_sys_u64(dst, (bits & 0xffffffff00000000ull) | tag);
-  st_sys_u64(dst + 1, (bits << 32) | tag);
+// Receiving half of the all-gather of shard totals (tree.cuh: exchange_publish): thread g
+// polls this rank's mailbox for rank g's total of step `seq`.  A peer that does not answer
+// within the timeout latches B2R_ERR_EXCHANGE (and later launches skip the wait), so a
+// lost rank cannot hang the GPU.
+// The sampler's sending half: nothing to do when the kernel that last changed the tree
+// has published this step's total already (its bits must then be the root's: anything
+// else changed the tree behind the publisher's back, and the ranks would apportion the
+// batch from different totals — latched as B2R_ERR_EXCHANGE, peer number -1).
+__device__ __forceinline__ void exchange_publish_if_needed(const ExchangeArgs &x, int world,
+                                                           int rank, double local_total,
+                                                           uint64_t seq, int64_t *latched) {
+  if (x.pub != nullptr && x.pub[0] == seq) {
+    if ((threadIdx.x & 31) == rank && x.pub[1] != (uint64_t)__double_as_longlong(local_total) &&
+        latched != nullptr && latched[0] == 0) {
+      latched[0] = B2R_ERR_EXCHANGE;
+      latched[1] = -1;
+    }
+    return;
+  }
+  exchange_publish(x, world, rank, local_total, seq);
 }
 
 __device__ __forceinline__ void exchange_collect(const ExchangeArgs &x, int world,
@@ -207,7 +200,8 @@ __global__ void __launch_bounds__(MAX_THREADS) per_sample_kernel(const __grid_co
   uint64_t xseq = 0;
   if (exchange) {
     xseq = *a.xchg.seq + 1;
-    exchange_publish(a.xchg, a.num_shards, a.rank, a.heap[1], xseq);
+    if (blockIdx.x == 0 && threadIdx.x < 32)
+      exchange_publish_if_needed(a.xchg, a.num_shards, a.rank, a.heap[1], xseq, a.latched);
   }
   const int top_depth = stage_top_levels(a.heap, a.depth, top);
   B2R_MARK(2);
@@ -697,8 +691,8 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
   const double local_total = a.heap[1];  // root of the 1-based heap
   double c_top = warp_candidate(a.heap, 1, a.depth < 5 ? a.depth : 5, lane);
   const uint64_t draw_offset = a.offset + draws_before;
-  if (exchange && blockIdx.x == 0)
-    exchange_publish(a.xchg, a.num_shards, a.rank, local_total, xseq);
+  if (exchange && blockIdx.x == 0 && threadIdx.x < 32)
+    exchange_publish_if_needed(a.xchg, a.num_shards, a.rank, local_total, xseq, a.latched);
   const double *shard_totals = a.shard_totals;
   if (exchange) {
     exchange_collect(a.xchg, a.num_shards, a.rank, local_total, xseq, s_totals,
@@ -910,7 +904,7 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
 
   // ---- only the last CTA to finish goes on (CLUSTER: CTA 0, after the barrier)
   if (CLUSTER) {
-    cg::this_cluster().sync();
+    cluster_sync_relacq();
     if (blockIdx.x != 0) return;
     ws.inv_flag = s_flag;
     ws.spec_idx = s_cl_spec_idx;
@@ -1432,6 +1426,7 @@ void fill_exchange_args(const b2r_exchange *x, ExchangeArgs *out) {
   for (int g = 0; g < kMaxShards; ++g) out->peer[g] = x->peer[g];
   out->seq = x->seq;
   out->timeout_ns = x->timeout_ns;
+  out->pub = x->pub;
   // Profiling switch (never set in production): B2R_DEBUG_XCHG_NOWAIT=1 takes this rank's
   // own total for every peer instead of waiting for theirs — the step time without the
   // cross-GPU coupling, i.e. the bound of what any change to the exchange can gain.  The
@@ -1542,7 +1537,7 @@ int launch_sample_sharded(b2r_buffer *b, int32_t global_batch, int32_t num_shard
 // Publishes a rank's total for the next exchange step without consuming it.
 __global__ void exchange_publish_kernel(ExchangeArgs x, int world, int rank,
                                         const double *heap) {
-  exchange_publish(x, world, rank, heap[1], *x.seq + 1);
+  exchange_publish(x, world, rank, heap[1], *x.seq + 1);  // (also records x.pub)
 }
 
 int launch_exchange_publish(const b2r_exchange *x, const b2r_buffer *b,

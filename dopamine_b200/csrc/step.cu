@@ -138,7 +138,16 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
     B2R_CUDA(cudaEventRecord(b->ev_c51_pre, b->side3));
   }
   // Staged adds (rows on the side stream beside the tree update at larger batches).
-  B2R_TRY(flush_queue(b, s, batch > split_min()));
+  // Early publish (b2r_exchange_set_early_publish): whichever kernel of this call writes
+  // the tree LAST publishes the shard total for the next step — so the adds staged before
+  // this call are applied behind the write-back, at the end of the call, and are seen by
+  // the next step's sampler: the order of effects on the tree stays the reference's
+  // add, sample, set_priority, add, ... with the adds one call later.
+  const b2r_exchange *early =
+      shard && shard->exchange->early_publish && shard->exchange->world > 1 ? shard->exchange
+                                                                           : nullptr;
+  if (!early) B2R_TRY(flush_queue(b, s, batch > split_min()));
+  const bool flush_behind = early != nullptr && b->q_entries > 0;
   g_host_trace.lap(2);
   // Deferred frame copies: the copies read their indices from a private ring slot (the
   // next step's sampler overwrites out->indices while they may still be running).
@@ -229,11 +238,21 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   // early launch.  Its stream rejoins below, with the frame copies.)
   if (!split_loss && wait_before_loss) B2R_CUDA(cudaStreamWaitEvent(s, wait_before_loss, 0));
   // (B2R_FUSE_WRITEBACK=1, unsplit loss only: write-back at the tail of the loss kernel)
+  // (split loss, at most 32 rows: tail and write-back as one thread-block cluster)
+  // A shard's step (row count on the device): the cluster applies the write-back when
+  // the count turns out to be at most 32 and the one-CTA tree kernel launched behind it
+  // then returns at once (`tree_done`).
+  const bool tail_counted = split_loss && shard != nullptr && !flush_behind &&
+                            c51_post_takes_tree(&loss, b->tree, expected_rows);
   const bool tail_writeback =
-      !split_loss && !shard && !debug_skip() && c51_can_fuse_writeback(&loss, b->tree);
+      split_loss ? (!shard && c51_post_takes_tree(&loss, b->tree))
+                 : (!shard && !debug_skip() && c51_can_fuse_writeback(&loss, b->tree));
+  unsigned int *tree_done = tail_counted ? b->pre_sync + 3 : nullptr;
   if (split_loss)
     B2R_TRY(c51_post_launch(&loss, b->c51_bestp, have_stats, s, b->status,
-                            shard && count != shard->out_count ? shard->out_count : nullptr));
+                            shard && count != shard->out_count ? shard->out_count : nullptr,
+                            tail_writeback || tail_counted ? b->tree : nullptr,
+                            out->indices, tree_done, tail_counted ? early : nullptr));
   else if (tail_writeback)
     B2R_TRY(c51_loss_launch(&loss, s, b->tree, out->indices));
   else if (!(debug_skip() & 1))
@@ -244,7 +263,9 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   if (!(debug_skip() & 2) && !tail_writeback)
     B2R_TRY((tree_apply<int32_t, float>(b->tree, rows_cap, out->indices, loss.priorities,
                                         nullptr, s, count, expected_rows,
-                                        presort ? 2 : 0)));
+                                        presort ? 2 : 0, flush_behind ? nullptr : early,
+                                        tree_done)));
+  if (flush_behind) B2R_TRY(flush_queue(b, s, false, early));
   if (frames && !deferred) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join, 0));
   if (split_loss && !(deferred && frames)) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_c51_pre, 0));
   g_host_trace.lap(6);

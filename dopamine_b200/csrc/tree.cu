@@ -866,6 +866,7 @@ __device__ __forceinline__ void tree_update_small_body(const UpdateArgs<I, V> &a
     B2R_MARK(10);
     a.heap[base + node] = acc;
   }
+  if (level == 0) publish_root(a);
   B2R_MARK(7);
 }
 
@@ -879,6 +880,14 @@ __global__ void __launch_bounds__(1024) tree_update_small_kernel(UpdateArgs<I, V
   pdl_release();
   pdl_acquire();
   B2R_MARK(1);
+  if (a.skip_flag != nullptr) {
+    const unsigned int done = *a.skip_flag;
+    __syncthreads();  // (every thread has read the flag before it is re-armed)
+    if (done != 0u) {
+      if (threadIdx.x == 0) *a.skip_flag = 0u;
+      return;
+    }
+  }
   if (tiny_ok) {
     int n = a.n;
     if (a.n_dev) n = min(n, max(*a.n_dev, 0));
@@ -1056,7 +1065,7 @@ static int allow_small_smem() {
 
 int flush_fused(b2r_tree *t, int n, const int64_t *slots, const double *prio,
                 const uint8_t *mode, const AddParams &rows, int row_blocks_per_entry,
-                cudaStream_t stream) {
+                cudaStream_t stream, const b2r_exchange *publish) {
   set_tree_window(t->heap, (size_t)t->leaves * 16);
   B2R_TRY(allow_small_smem());
   const int padded = padded_size(n);
@@ -1075,6 +1084,11 @@ int flush_fused(b2r_tree *t, int n, const int64_t *slots, const double *prio,
   a.max_rec = t->max_rec;
   a.status = t->status;
   a.n_dev = nullptr;
+  if (publish != nullptr && publish->world > 1 && publish->connected) {
+    a.publish = publish->args_dev;
+    a.publish_world = publish->world;
+    a.publish_rank = publish->rank;
+  }
   B2R_CUDA(launch(flush_fused_kernel, dim3(1 + n * row_blocks_per_entry),
                   dim3(32 * (t->depth + 1)), smem, stream, a, rows,
                   row_blocks_per_entry, (int)(n <= kTinyBatch && tree_tiny_enabled())));
@@ -1113,7 +1127,8 @@ static int ensure_sorted(b2r_tree *t) {
 template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
                const uint8_t *mode, cudaStream_t stream, const int32_t *n_dev,
-               int64_t expected_n, int phase) {
+               int64_t expected_n, int phase, const b2r_exchange *publish,
+               unsigned int *skip_flag) {
   set_tree_window(t->heap, (size_t)t->leaves * 16);
   if (phase != kFull) {
     if (!tree_can_presort(n, expected_n) || mode != nullptr)
@@ -1143,7 +1158,13 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     a.max_rec = t->max_rec;
     a.status = t->status;
     a.n_dev = n_dev;
-    if (n <= kTinyBatch && tree_tiny_enabled())
+    if (publish != nullptr && publish->world > 1 && publish->connected) {
+      a.publish = publish->args_dev;
+      a.publish_world = publish->world;
+      a.publish_rank = publish->rank;
+    }
+    a.skip_flag = skip_flag;
+    if (n <= kTinyBatch && tree_tiny_enabled() && skip_flag == nullptr)
       B2R_CUDA(launch(tree_update_tiny_kernel<I, V>, dim3(1), dim3(32 * (t->depth + 1)),
                       0, stream, a));
     else
@@ -1188,13 +1209,16 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
 
 template int tree_apply<int64_t, double>(b2r_tree *, int64_t, const int64_t *,
                                          const double *, const uint8_t *,
-                                         cudaStream_t, const int32_t *, int64_t, int);
+                                         cudaStream_t, const int32_t *, int64_t, int,
+    const b2r_exchange *, unsigned int *);
 template int tree_apply<int32_t, float>(b2r_tree *, int64_t, const int32_t *,
                                         const float *, const uint8_t *,
-                                        cudaStream_t, const int32_t *, int64_t, int);
+                                        cudaStream_t, const int32_t *, int64_t, int,
+    const b2r_exchange *, unsigned int *);
 template int tree_apply<int32_t, double>(b2r_tree *, int64_t, const int32_t *,
                                          const double *, const uint8_t *,
-                                         cudaStream_t, const int32_t *, int64_t, int);
+                                         cudaStream_t, const int32_t *, int64_t, int,
+    const b2r_exchange *, unsigned int *);
 
 }  // namespace b2r
 

@@ -24,6 +24,8 @@ struct b2r_tree {
   b2r::Bounce bounce;
 };
 
+struct b2r_exchange;
+
 namespace b2r {
 
 constexpr int kTreeChunk = 4096;   // elements sorted per CTA (64 KB of smem)
@@ -266,6 +268,60 @@ __device__ __forceinline__ int stage_top_levels(const double *__restrict__ heap,
   return top_depth;
 }
 
+// Shard totals exchanged through peer memory (sample.cu: exchange_collect; exchange.cu).
+constexpr int kMaxShards = 16;
+struct ExchangeArgs {
+  uint64_t *local;             // this rank's mailbox [2 parities][world][2 words];
+                               // nullptr: no exchange
+  uint64_t *peer[kMaxShards];  // the peers' mailboxes (peer-mapped device pointers)
+  uint64_t *seq;               // device step counter, in lockstep on all ranks
+  int64_t timeout_ns;
+  // [0] the step number this rank's total has been published for, [1] the published
+  // bits.  A kernel that leaves the tree in its final state for the next sharded step
+  // (the write-back, or the flush of staged adds behind it) publishes the new root right
+  // away — the wire latency then hides behind the rest of that kernel, the kernel
+  // boundary and the next sampler's prologue — and the sampler publishes only if nobody
+  // has (pub[0] != its step number).
+  uint64_t *pub;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void st_sys_u64(uint64_t *p, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_sys_u64(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// All-gather of one fp64 per rank through peer memory (NVLink / NVSwitch), sending half:
+// thread g (= threadIdx.x & 31 < world) stores this rank's root total straight into rank
+// g's mailbox.  Each total travels as two 8-byte words that carry half of the payload and
+// the step number in their low 32 bits (the flag is in-band, as in NCCL's LL protocol), so
+// no fence or ordering between the stores is needed.  Mailbox slots alternate with the
+// parity of the step: a rank can only be one step ahead of a peer, which has then
+// finished reading the other parity.  The lane of this rank's own index records what was
+// published (x.pub).
+__device__ __forceinline__ void exchange_publish(const ExchangeArgs &x, int world,
+                                                 int rank, double local_total,
+                                                 uint64_t seq) {
+  const int g = threadIdx.x & 31;
+  if (g >= world) return;
+  const uint64_t bits = (uint64_t)__double_as_longlong(local_total);
+  if (g == rank) {
+    if (x.pub != nullptr) {
+      x.pub[1] = bits;
+      x.pub[0] = seq;
+    }
+    return;
+  }
+  const uint32_t tag = (uint32_t)seq;
+  uint64_t *dst = x.peer[g] + ((size_t)(seq & 1) * world + rank) * 2;
+  st_sys_u64(dst, (bits & 0xffffffff00000000ull) | tag);
+  st_sys_u64(dst + 1, (bits << 32) | tag);
+}
+#endif  // __CUDACC__
+
 #ifdef __CUDACC__
 // Arguments of the batched-set kernels (tree.cu; the tiny body below also runs at the
 // tail of the C51 loss kernel, c51.cu).
@@ -297,7 +353,24 @@ struct UpdateArgs {
   uint32_t *sorted = nullptr;
   // role ticket, barrier flag, barrier arrivals (see tree_update_kernel)
   unsigned int *sync_words = nullptr;
+  // Sharded replay: this launch leaves the tree final for the next sharded step, so the
+  // warp that writes the root publishes it to the peers (ExchangeArgs::pub; one-CTA
+  // kernels only).  nullptr: nothing to publish.
+  const ExchangeArgs *publish = nullptr;
+  int publish_world = 0, publish_rank = 0;
+  // One-CTA kernels: *skip_flag != 0 — the update has been applied already (the loss tail
+  // of a shard's step did it, c51.cu) — means return at once, re-arming the flag.
+  unsigned int *skip_flag = nullptr;
 };
+
+// Called by every lane of the warp that owns tree level 0, after its store of the root.
+template <typename I, typename V>
+__device__ __forceinline__ void publish_root(const UpdateArgs<I, V> &a) {
+  if (a.publish == nullptr) return;
+  __syncwarp();
+  const double root = *reinterpret_cast<volatile double *>(a.heap + 1);
+  exchange_publish(*a.publish, a.publish_world, a.publish_rank, root, *a.publish->seq + 1);
+}
 constexpr int kFull = 0, kPresort = 1, kApply = 2;
 
 // At most 32 sets (the agent's batch, an add flush): entry k lives in lane k of every
@@ -318,6 +391,9 @@ struct TinyLoads {
   int64_t latched, idx, node;
   bool in, use_max, idx_ok;
   double node_val;
+  double recorded;    // max_recorded_priority as stored (leaf warp)
+  unsigned same_all;  // lanes whose entries share this lane's node, all in-range entries
+                      // taken as applied (the usual case; else regrouped in the finish)
 };
 
 template <typename I, typename V>
@@ -335,6 +411,9 @@ __device__ __forceinline__ void tree_update_tiny_issue(const UpdateArgs<I, V> &a
   // every lane fetches the node its entry sits under (group mates fetch the same word)
   t->node = t->idx_ok ? (t->idx >> shift) : 0;
   t->node_val = t->idx_ok ? a.heap[base + t->node] : 0.0;
+  t->recorded = (level == a.depth && lane == 0) ? *a.max_rec : 0.0;
+  // grouping needs the indices only: done here, off the path that waits for the values
+  t->same_all = __match_any_sync(0xffffffffu, t->idx_ok ? (long long)t->node : -1ll - lane);
 }
 
 // Every warp of the block must call this (one block barrier inside); warps whose level
@@ -354,31 +433,36 @@ __device__ __forceinline__ void tree_update_tiny_finish(const UpdateArgs<I, V> &
   const bool in = t.in, use_max = t.use_max, idx_ok = t.idx_ok;
   const int64_t idx = t.idx, node = t.node;
   const double node_val = t.node_val;
+  // (leaf warp, kept for after the barrier: what the other levels do not wait for)
+  double v = explicit_v, recorded = 0.0;
+  int n_eff_leaf = n;
+  unsigned bad_mask = 0;
 
   if (is_leaf && !skip) {
     // v_k = mode ? max(max_recorded, explicit values before k) : value_k
     // (stage_mode_values), the first entry the reference would raise on, and
     // max_recorded_priority over the applied prefix.
-    const double recorded = *a.max_rec;
-    double x = (in && !use_max) ? explicit_v : -INFINITY;  // inclusive prefix max
+    recorded = __shfl_sync(full, t.recorded, 0);
+    if (a.mode != nullptr) {
+      double x = (in && !use_max) ? explicit_v : -INFINITY;  // inclusive prefix max
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double y = __shfl_up_sync(full, x, o);
-      if (lane >= o) x = fmax(x, y);
+      for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(full, x, o);
+        if (lane >= o) x = fmax(x, y);
+      }
+      double before = __shfl_up_sync(full, x, 1);
+      if (lane == 0) before = -INFINITY;
+      v = use_max ? fmax(recorded, before) : explicit_v;
     }
-    double before = __shfl_up_sync(full, x, 1);
-    if (lane == 0) before = -INFINITY;
-    const double v = use_max ? fmax(recorded, before) : explicit_v;
     const bool bad = in && (v < 0.0 || !idx_ok);
-    const unsigned bad_mask = __ballot_sync(full, bad);
+    bad_mask = __ballot_sync(full, bad);
     const int n_eff = bad_mask ? __ffs(bad_mask) - 1 : n;
+    n_eff_leaf = n_eff;
     const bool live = lane < n_eff;
-    double vmax = live ? v : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(full, vmax, o));
     // lanes that share a leaf: the lowest walks the group in batch order
-    const long long key = live ? (long long)idx : -1ll - lane;
-    const unsigned same = __match_any_sync(full, key);
+    unsigned same = t.same_all;
+    if (bad_mask != 0)  // (entries from the first refused one on are not applied)
+      same = __match_any_sync(full, live ? (long long)idx : -1ll - lane);
     double delta = __dsub_rn(v, node_val);
     double leaf = __dadd_rn(node_val, delta);
     if (__any_sync(full, live && (same & (same - 1)) != 0)) {
@@ -399,24 +483,33 @@ __device__ __forceinline__ void tree_update_tiny_finish(const UpdateArgs<I, V> &
       s_delta[lane] = delta;
       if (lane == __ffs(same) - 1) a.heap[base + idx] = leaf;
     }
-    // the code of the failure: value first (sum_tree.py:191-193), else the index
-    const double bad_v = __shfl_sync(full, v, bad_mask ? __ffs(bad_mask) - 1 : 0);
-    if (lane == 0) {
-      s_stop = n_eff;
-      if (n_eff > 0 && vmax > recorded) *a.max_rec = vmax;
-      if (n_eff < n) {
-        a.status[0] = bad_v < 0.0 ? B2R_ERR_NEGATIVE_PRIORITY : B2R_ERR_INDEX_RANGE;
-        a.status[1] = a.k_base + n_eff;
-      }
-    }
+    if (lane == 0) s_stop = n_eff;
   }
   __syncthreads();  // deltas and n_eff are in shared memory
-  if (is_leaf || skip) return;
+  if (skip) return;
+  if (is_leaf) {
+    // max_recorded_priority over the applied prefix and the code of the failure: value
+    // first (sum_tree.py:191-193), else the index — nobody waits for these
+    const bool live = lane < n_eff_leaf;
+    double vmax = live ? v : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(full, vmax, o));
+    const double bad_v = __shfl_sync(full, v, bad_mask ? __ffs(bad_mask) - 1 : 0);
+    if (lane == 0) {
+      if (n_eff_leaf > 0 && vmax > recorded) *a.max_rec = vmax;
+      if (n_eff_leaf < n) {
+        a.status[0] = bad_v < 0.0 ? B2R_ERR_NEGATIVE_PRIORITY : B2R_ERR_INDEX_RANGE;
+        a.status[1] = a.k_base + n_eff_leaf;
+      }
+    }
+    return;
+  }
   const int n_eff = s_stop;
   const bool live = lane < n_eff;
   const double d = live ? s_delta[lane] : 0.0;
-  const long long key = live ? (long long)node : -1ll - lane;
-  const unsigned same = __match_any_sync(full, key);
+  unsigned same = t.same_all;
+  if (n_eff < n)  // a refused entry: regroup over the applied prefix
+    same = __match_any_sync(full, live ? (long long)node : -1ll - lane);
   double acc = __dadd_rn(node_val, d);
   if (__any_sync(full, live && (same & (same - 1)) != 0)) {
     acc = node_val;
@@ -427,6 +520,7 @@ __device__ __forceinline__ void tree_update_tiny_finish(const UpdateArgs<I, V> &
     }
   }
   if (live && lane == __ffs(same) - 1) a.heap[base + node] = acc;
+  if (level == 0) publish_root(a);
 }
 
 // PDL: the body opens a kernel of its own (programmatic dependent launch hand-shake);
@@ -454,10 +548,13 @@ __device__ __forceinline__ void tree_update_tiny_body(const UpdateArgs<I, V> &a)
 // phase: 0 = the whole update; 1 = only group the entries by node (needs the indices,
 // not the values: tree_can_presort says whether this batch can); 2 = apply the values
 // over the lists of a phase-1 launch with the same n / indices / n_dev / expected_n.
+// publish (nullable, one-CTA kernels only): the launch leaves the tree final for the next
+// sharded step and publishes the new root to the exchange's peers.
 template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
                const uint8_t *mode, cudaStream_t stream,
-               const int32_t *n_dev = nullptr, int64_t expected_n = -1, int phase = 0);
+               const int32_t *n_dev = nullptr, int64_t expected_n = -1, int phase = 0,
+               const b2r_exchange *publish = nullptr, unsigned int *skip_flag = nullptr);
 bool tree_can_presort(int64_t n, int64_t expected_n);
 bool tree_tiny_enabled();
 // c51.cu: the C51 loss with the write-back of its priorities at the kernel's tail.
@@ -473,7 +570,17 @@ int c51_scratch_floats_per_row();
 int c51_pre_launch(const b2r_c51_args *args, int rows, float *scratch, const PreSync &sync,
                    cudaStream_t stream, int *have_stats);
 // ... and the tail over the sampled rows.  err (nullable): asynchronous error latch.
+// tree != nullptr (c51_post_takes_tree: batches of at most 32 rows): the tail and
+// set_priority(indices, priorities) as one thread-block cluster.
+// (expected_rows >= 0: a shard's step with a device-side row count — the cluster applies
+// the write-back when the count turns out to be at most 32 and says so in *tree_done; the
+// one-CTA tree kernel launched behind it with the same flag then returns at once.)
+bool c51_post_takes_tree(const b2r_c51_args *args, const b2r_tree *tree,
+                         int64_t expected_rows = -1);
 int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_stats,
-                    cudaStream_t stream, int64_t *err, int32_t *count_copy = nullptr);
+                    cudaStream_t stream, int64_t *err, int32_t *count_copy = nullptr,
+                    b2r_tree *tree = nullptr, const int32_t *indices = nullptr,
+                    unsigned int *tree_done = nullptr,
+                    const b2r_exchange *publish = nullptr);
 
 }  // namespace b2r

@@ -87,6 +87,12 @@ class PeerExchange(object):
       _native.check(lib.b2r_exchange_connect_pointers(x._h, boxes))
     return out
 
+  def set_early_publish(self, on=True):
+    """The kernel that leaves the tree final for the next sharded step (write-back, or
+    the flush of staged adds behind it) publishes the shard total itself; see
+    b2r_exchange_set_early_publish for what the caller accepts with it."""
+    _native.check(self._lib.b2r_exchange_set_early_publish(self._h, 1 if on else 0))
+
   def publish(self, memory):
     """Publishes `memory`'s total for the next step ahead of the sampling call
     (needed only when the ranks are emulated by sequential launches)."""

@@ -338,6 +338,21 @@ int b2r_exchange_connect(b2r_exchange *exchange, const void *handles);
 int b2r_exchange_connect_pointers(b2r_exchange *exchange, void *const *mailboxes);
 void *b2r_exchange_mailbox(b2r_exchange *exchange);
 int b2r_exchange_set_timeout(b2r_exchange *exchange, double seconds);
+/* Early publish.  By default a rank publishes its shard total at the start of the
+ * sampling kernel that needs the peers' totals, so every step waits one NVLink store
+ * latency inside that kernel.  With on != 0 the kernel that leaves the tree in its final
+ * state for the NEXT sharded step — the priority write-back of
+ * b2r_train_step_sharded_device, or the flush of staged add()s when there is one —
+ * publishes the new root the moment it is written (one-CTA tree kernels: shares of up
+ * to 256 rows; larger write-backs keep publishing from the sampler).  Consequences the
+ * caller accepts with the switch: (i) add()s staged before a step call are applied at the
+ * END of that call, behind its write-back, and become visible to the next step's sampler
+ * (the order of effects on the tree stays add, sample, set_priority, add, ...); (ii)
+ * between two sharded steps nothing else may change the tree (set_priority, a flush
+ * forced by another call): the next sampler finds the root different from what was
+ * published and latches B2R_ERR_EXCHANGE (peer -1) instead of letting the ranks apportion
+ * the batch from different totals.  Every rank of an exchange must use the same setting. */
+int b2r_exchange_set_early_publish(b2r_exchange *exchange, int32_t on);
 /* Publishes this rank's total for the NEXT step without consuming the step (the
  * sampling call publishes again, identically).  Only needed when ranks are
  * emulated by sequential launches on one device, where a launch cannot wait for a

@@ -412,16 +412,26 @@ def test_peer_exchange_times_out_instead_of_hanging(gpu):
   assert 'did not publish' in gpu.native.last_error()
 
 
-@pytest.mark.parametrize('global_batch,bounded,deferred', [
-    (256, False, False), (2048, False, False), (256, True, False), (2048, True, False),
-    (256, True, True), (2048, True, True)])
-def test_sharded_fused_step_matches_oracles(gpu, global_batch, bounded, deferred):
+@pytest.mark.parametrize('global_batch,bounded,deferred,early', [
+    (256, False, False, False), (2048, False, False, False), (256, True, False, False),
+    (2048, True, False, False), (256, True, True, False), (2048, True, True, False),
+    (128, True, True, True), (96, True, False, True), (64, True, True, True),
+    (96, True, False, False), (128, False, False, False)])
+def test_sharded_fused_step_matches_oracles(gpu, global_batch, bounded, deferred, early):
   """b2r_train_step_sharded_device on 4 emulated ranks (one sampling CTA up to a
   global batch of 256, tiles over each rank's stratum range above): each rank's rows
   (batch columns at its indices, losses, write-back) against the oracles, the rows of
   all ranks partitioning the global batch.  bounded: outputs, logits and launches sized
   by a bound on the rank's share (max_rows) instead of the global batch.  deferred: frame
-  copies joined by b2r_join_frames (the row count then travels through the ring slot)."""
+  copies joined by b2r_join_frames (the row count then travels through the ring slot).
+  early: the write-back publishes the shard total for the next step itself
+  (b2r_exchange_set_early_publish): only the first step needs the totals published ahead
+  (the ranks are emulated one after the other), and the later steps must still see the
+  partition of the global batch — i.e. every rank read the totals its peers left behind
+  at the end of their previous step.  (Expected shares of at most 32 rows: the one-CTA
+  tree kernels — and the loss tail's cluster, which applies the write-back of such a
+  step itself — carry the publish hook; larger write-backs leave publishing to the
+  sampler, which ranks emulated one after the other cannot wait for.)"""
   import ctypes
   from dopamine_b200.replay_memory import sharded_replay
   torch, native = gpu.torch, gpu.native
@@ -429,6 +439,8 @@ def test_sharded_fused_step_matches_oracles(gpu, global_batch, bounded, deferred
   num_shards, cap = 4, 50000
   shards = [_filled(gpu, cap, 32, seed=40 + g, hot=(g == 1)) for g in range(num_shards)]
   exchanges = sharded_replay.PeerExchange.emulated(num_shards)
+  for x in exchanges:
+    x.set_early_publish(early)
   rng = np.random.RandomState(8)
   support = gpu.ra.make_support(10., ATOMS)
   for mem, _, _ in shards:
@@ -451,7 +463,8 @@ def test_sharded_fused_step_matches_oracles(gpu, global_batch, bounded, deferred
     d_online = torch.as_tensor(online, device='cuda')
     d_target = torch.as_tensor(target, device='cuda')
     for g in range(num_shards):
-      exchanges[g].publish(shards[g][0])
+      if not early or step == 0:
+        exchanges[g].publish(shards[g][0])
     served = []
     for g in range(num_shards):
       mem, tree, cols = shards[g]
