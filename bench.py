@@ -43,7 +43,10 @@ STACK = 4
 METRIC = ('sampled transitions/sec (PER sample+gather+C51 target+priority '
           'update)')
 UNIT = 'transitions/s'
-# largest batch whose frame copies are deferred (see main)
+# batches whose frame copies are deferred (see main): below, the chain bounds the step and
+# the copies hide behind it either way (measured: 14.5 us joined, 15.0 deferred at 32);
+# above, the copies saturate HBM and slow the chain beside them
+DEFER_MIN_BATCH = 128
 DEFER_MAX_BATCH = 2048
 # shortest timed work the headline number may rest on (see time_graph_or_eager)
 MIN_TIMED_MS = 50.0
@@ -455,16 +458,20 @@ def measure_gather_roofline(torch, wl, batch, peak_gbs, launches=200):
   ms = time_graph_or_eager(torch, body, reps, 3, True)
   sec_per_launch = ms * 1e-3 / (reps * nbuf)
   achieved = bytes_per_launch / sec_per_launch / 1e9
+  # which of the two frame-copy kernels a launch of this size takes (gather.cu)
+  variant = int(wl.lib.b2r_gather_variant(wl.h, batch))
+  kernel = {0: 'gather_stack4_u8_kernel', 1: 'gather_stack4_u8_tma_kernel'}.get(
+      variant, 'gather_generic_kernel')
   traffic, traffic_note = None, None
   try:  # per-launch DRAM bytes of this kernel from the committed ncu capture
-    t = json.load(open(os.path.join(ROOT, 'profiles', 'r1', 'traffic.json')))
-    t = t['gather_stack4_u8_kernel'].get(str(batch))
+    t = json.load(open(os.path.join(ROOT, 'profiles', 'r2', 'traffic.json')))
+    t = t[kernel].get(str(batch))
     if t:
       traffic, traffic_note = t['traffic_bytes'], t['note']
   except Exception:  # pylint: disable=broad-except
     pass
   return {
-      'bound': 'hbm', 'kernel': 'gather_stack4_u8_kernel',
+      'bound': 'hbm', 'kernel': kernel,
       'achieved': round(achieved, 1), 'peak': peak_gbs, 'unit': 'GB/s',
       'frac': round(achieved / peak_gbs, 4), 'traffic': traffic,
       'traffic_note': traffic_note,
@@ -1075,10 +1082,10 @@ def main():
   else:
     step_fn = lambda: wl.step(args.batch)
     use_graph = not args.no_graph
-  # N = 1, fused step: the frame copies of step n run beside the chain of step n + 1 and
-  # are joined once per timed group of steps (b2r_set_deferred_frames), up to the batch
-  # where the copies saturate HBM and anything beside them only slows both down.
-  defer = lambda b: (wl.fused and not args.no_defer and b <= DEFER_MAX_BATCH and
+  # Fused step, batches 128..2048: the frame copies of step n run beside the chain of
+  # step n + 1 and are joined once per timed group of steps (b2r_set_deferred_frames).
+  defer = lambda b: (wl.fused and not args.no_defer and
+                     DEFER_MIN_BATCH <= b <= DEFER_MAX_BATCH and
                      (world == 1 or args.exchange == 'p2p'))
   finish_of = lambda b: wl.join if defer(b) else None
   wl.set_deferred(defer(args.batch))

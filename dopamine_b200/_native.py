@@ -23,6 +23,7 @@ ERR_TOO_FEW_TRANSITIONS = 6
 ERR_INDEX_RANGE = 7
 ERR_UNSUPPORTED = 8
 ERR_EXCHANGE = 9
+ERR_STALE_TOTAL = 11
 QUEUE_FULL = 10
 STREAM_NONE = ctypes.c_void_p(-1)
 IPC_HANDLE_BYTES = 64
@@ -230,6 +231,7 @@ SIGNATURES = {
                                            c_int32, c_void_p]),
     'b2r_add_batch': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                               P(c_void_p), c_void_p, c_int, P(c_int64), c_void_p]),
+    'b2r_gather_variant': (c_int32, [c_void_p, c_int32]),
     'b2r_gather_slab': (c_int, [c_void_p, c_int32, c_void_p, c_int32, P(Batch), c_void_p,
                                 c_size_t, P(Batch), P(c_size_t), c_void_p]),
     'b2r_set_deferred_frames': (c_int, [c_void_p, c_int32]),
@@ -265,6 +267,11 @@ SIGNATURES = {
 }
 
 _lib = None
+# The version of include/b200_replay.h this table of signatures (and the ctypes mirrors of
+# b2r_config, b2r_batch, b2r_c51_args, ...) was written against; b2r_abi_version() of the
+# loaded binary must agree, so that a stale libb200replay.so is an error at load time and
+# not a silent layout mismatch.  Bump both together.
+ABI_VERSION = 3
 
 
 class NativeError(RuntimeError):
@@ -287,6 +294,19 @@ def lib():
     if not os.path.exists(LIB_PATH):
       build()
     handle = ctypes.CDLL(LIB_PATH)
+    handle.b2r_abi_version.restype = c_int
+    found = handle.b2r_abi_version()
+    if found != ABI_VERSION and os.environ.get('B2R_LIB') is None:
+      # a binary built from older sources: rebuild once, then insist
+      build()
+      handle = ctypes.CDLL(LIB_PATH)
+      handle.b2r_abi_version.restype = c_int
+      found = handle.b2r_abi_version()
+    if found != ABI_VERSION:
+      raise NativeError(ERR_INVALID_ARGUMENT,
+                        '{} implements ABI version {}, this package needs {}: rebuild it '
+                        '(python -m dopamine_b200.csrc.build --force)'.format(
+                            LIB_PATH, found, ABI_VERSION))
     for name, (restype, argtypes) in SIGNATURES.items():
       fn = getattr(handle, name)  # AttributeError if the ABI is incomplete
       fn.restype = restype

@@ -108,7 +108,7 @@ extern "C" {
 
 const char *b2r_last_error(void) { return b2r::last_error_slot().c_str(); }
 
-int b2r_abi_version(void) { return 2; }
+int b2r_abi_version(void) { return B2R_ABI_VERSION; }
 
 int64_t b2r_launch_count(void) {
   return b2r::g_launches.load(std::memory_order_relaxed);

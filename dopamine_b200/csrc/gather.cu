@@ -468,6 +468,16 @@ using b2r::fail;
 
 extern "C" {
 
+int32_t b2r_gather_variant(const b2r_buffer *b, int32_t batch) {
+  if (!b) return -1;
+  const bool fast = b->cfg.stack_size == 4 && b->cfg.obs_itemsize == 1 &&
+                    (b->cfg.obs_bytes & 15) == 0;
+  if (!fast) return 2;
+  return b2r::gather_variant(batch) == 1 &&
+                 (size_t)b2r::kTmaMaxFrames * (size_t)b->cfg.obs_bytes <= 200 * 1024
+             ? 1 : 0;
+}
+
 int b2r_gather_device(b2r_buffer *b, int32_t batch, const int32_t *indices,
                       const b2r_batch *out, b2r_stream stream) {
   if (batch <= 0 || batch > 60000)

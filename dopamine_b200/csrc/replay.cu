@@ -672,6 +672,10 @@ int b2r_check(b2r_buffer *b, b2r_stream stream) {
     B2R_CUDA(cudaMemsetAsync(b->status, 0, 16, s));
     if (st[0] == B2R_ERR_EMPTY_TREE)
       return fail(B2R_ERR_EMPTY_TREE, "Cannot sample from an empty sum tree.");
+    if (st[0] == B2R_ERR_STALE_TOTAL)
+      return fail(B2R_ERR_STALE_TOTAL,
+                  "the sum tree changed between the early publish of this shard's total "
+                  "and the next sharded step (b2r_exchange_set_early_publish)");
     if (st[0] == B2R_ERR_EXCHANGE)
       return fail(B2R_ERR_EXCHANGE,
                   "shard %lld did not publish its priority total in time",

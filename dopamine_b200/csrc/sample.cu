@@ -94,15 +94,15 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // The sampler's sending half: nothing to do when the kernel that last changed the tree
 // has published this step's total already (its bits must then be the root's: anything
 // else changed the tree behind the publisher's back, and the ranks would apportion the
-// batch from different totals — latched as B2R_ERR_EXCHANGE, peer number -1).
+// batch from different totals — latched as B2R_ERR_STALE_TOTAL).
 __device__ __forceinline__ void exchange_publish_if_needed(const ExchangeArgs &x, int world,
                                                            int rank, double local_total,
                                                            uint64_t seq, int64_t *latched) {
   if (x.pub != nullptr && x.pub[0] == seq) {
     if ((threadIdx.x & 31) == rank && x.pub[1] != (uint64_t)__double_as_longlong(local_total) &&
         latched != nullptr && latched[0] == 0) {
-      latched[0] = B2R_ERR_EXCHANGE;
-      latched[1] = -1;
+      latched[0] = B2R_ERR_STALE_TOTAL;
+      latched[1] = rank;
     }
     return;
   }

@@ -46,7 +46,9 @@ typedef enum {
   B2R_ERR_INDEX_RANGE = 7,
   B2R_ERR_UNSUPPORTED = 8,
   B2R_ERR_EXCHANGE = 9,          /* a peer shard did not publish its total in time */
-  B2R_QUEUE_FULL = 10            /* b2r_add with B2R_STREAM_NONE: flush, then retry */
+  B2R_QUEUE_FULL = 10,           /* b2r_add with B2R_STREAM_NONE: flush, then retry */
+  B2R_ERR_STALE_TOTAL = 11       /* early publish: the tree changed after the shard's total
+                                    for the next step had been given to the peers        */
 } b2r_status;
 
 /* Stream argument of b2r_add / b2r_add_atari meaning "never launch from this call":
@@ -56,6 +58,9 @@ typedef enum {
 #define B2R_STREAM_NONE ((b2r_stream)(intptr_t)-1)
 
 const char *b2r_last_error(void);
+/* Version of this header's structs and signatures; a binding compares it with the
+ * version it was written against when it loads the library (dopamine_b200/_native.py). */
+#define B2R_ABI_VERSION 3
 int b2r_abi_version(void);
 /* Number of kernels this library has launched in this process (for bench.py's
  * gpu_launches claim). */
@@ -250,6 +255,10 @@ typedef struct {
  * DEVICE pointers; asynchronous. */
 int b2r_gather_device(b2r_buffer *buf, int32_t batch, const int32_t *indices,
                       const b2r_batch *out, b2r_stream stream);
+/* Which frame-copy kernel a launch of `batch` rows takes: 0 gather_stack4_u8_kernel
+ * (registers: LDG.128 -> PRMT -> STG.128), 1 gather_stack4_u8_tma_kernel (frames staged
+ * through cp.async.bulk into shared memory), 2 gather_generic_kernel (other layouts). */
+int32_t b2r_gather_variant(const b2r_buffer *buf, int32_t batch);
 /* Same with HOST indices and HOST outputs (copies inside); synchronises. */
 int b2r_gather(b2r_buffer *buf, int32_t batch, const int32_t *indices,
                const b2r_batch *out, b2r_stream stream);
@@ -350,7 +359,7 @@ int b2r_exchange_set_timeout(b2r_exchange *exchange, double seconds);
  * (the order of effects on the tree stays add, sample, set_priority, add, ...); (ii)
  * between two sharded steps nothing else may change the tree (set_priority, a flush
  * forced by another call): the next sampler finds the root different from what was
- * published and latches B2R_ERR_EXCHANGE (peer -1) instead of letting the ranks apportion
+ * published and latches B2R_ERR_STALE_TOTAL instead of letting the ranks apportion
  * the batch from different totals.  Every rank of an exchange must use the same setting. */
 int b2r_exchange_set_early_publish(b2r_exchange *exchange, int32_t on);
 /* Publishes this rank's total for the NEXT step without consuming the step (the

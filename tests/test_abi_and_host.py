@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
   for name in names:
     assert hasattr(lib, name), name
   assert sorted(_native.SIGNATURES) == names
-  assert lib.b2r_abi_version() == 2
+  assert lib.b2r_abi_version() == _native.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_the_header(tmp_path):

@@ -550,6 +550,134 @@ def test_sharded_step_share_beyond_max_rows_is_latched(gpu, global_batch):
     assert status == native.ERR_UNSUPPORTED, (status, native.last_error())
 
 
+def _sharded_step_args(gpu, mem, rows, support, logits):
+  import ctypes
+  torch, native = gpu.torch, gpu.native
+  _, arrays, batch = mem._alloc_outputs(rows, True)
+  loss = {k: torch.zeros(rows, dtype=torch.float32, device='cuda')
+          for k in ('loss', 'priorities', 'weights')}
+  args = native.C51Args()
+  args.num_actions, args.num_atoms = ACTIONS, ATOMS
+  args.cumulative_gamma = float(np.float32(0.99 ** 3))
+  args.support = support.data_ptr()
+  args.online_logits = args.target_logits = logits.data_ptr()
+  args.loss = loss['loss'].data_ptr()
+  args.priorities = loss['priorities'].data_ptr()
+  args.weights = loss['weights'].data_ptr()
+  return dict(arrays=arrays, batch=batch, loss=loss, args=args,
+              slots=torch.zeros(rows, dtype=torch.int32, device='cuda'),
+              count=torch.zeros(1, dtype=torch.int32, device='cuda'), ctypes=ctypes)
+
+
+def test_early_publish_applies_staged_adds_behind_the_write_back(gpu):
+  """b2r_exchange_set_early_publish: the kernel that writes the tree last in a step call
+  publishes the shard total for the next step, so add()s staged before a call are
+  applied at the END of that call, behind its write-back.  Twin shards, two emulated
+  ranks each: A (early) stages its adds and THEN steps; B (default) steps, then adds the
+  same rows and flushes.  The effects on the tree are the same sequence — sample,
+  set_priority, add, sample, ... — so every step samples the same indices, the rings hold
+  the same rows and every fp64 tree node is equal; in A only the first step's totals are
+  published ahead (ranks emulated one after the other: the later steps find the totals
+  their peers' write-backs / flushes left behind)."""
+  from dopamine_b200.replay_memory import sharded_replay
+  torch, native = gpu.torch, gpu.native
+  lib = native.lib()
+  world, cap, global_batch, rows = 2, 20000, 64, 64
+  support = gpu.ra.make_support(10., ATOMS)
+  logits = torch.as_tensor(np.random.RandomState(1).randn(rows, ACTIONS, ATOMS)
+                           .astype(np.float32), device='cuda')
+  runs = {}
+  for name, early in (('A', True), ('B', False)):
+    shards = [_filled(gpu, cap, 32, seed=80 + g, hot=False)[0] for g in range(world)]
+    xs = sharded_replay.PeerExchange.emulated(world)
+    for x in xs:
+      x.set_early_publish(early)
+    state = [_sharded_step_args(gpu, m, rows, support, logits) for m in shards]
+    picked = []
+    rng = np.random.RandomState(9)
+    for step in range(4):
+      new_rows = [(rng.randint(0, 256, size=(84, 84)).astype(np.uint8), int(rng.randint(18)),
+                   0.25, int(rng.rand() < 0.2), float(1.0 + rng.rand())) for _ in range(6)]
+      for g in range(world):
+        if not early or step == 0:
+          xs[g].publish(shards[g])
+      if early:  # staged now, applied behind this call's write-back
+        for m in shards:
+          for row in new_rows:
+            m.add(*row)
+      for g in range(world):
+        st = state[g]
+        st['args'].batch = global_batch
+        native.check(lib.b2r_train_step_sharded_device(
+            shards[g]._h, xs[g]._h, global_batch, 31, step, st['ctypes'].byref(st['batch']),
+            st['ctypes'].byref(st['args']), st['slots'].data_ptr(), st['count'].data_ptr(),
+            rows, native.current_stream()))
+        torch.cuda.synchronize()
+        n = int(st['count'].cpu()[0])
+        picked.append(st['arrays'][7][:n].cpu().numpy().copy())
+      if not early:
+        for m in shards:
+          for row in new_rows:
+            m.add(*row)
+          m._flush()
+    for m in shards:
+      native.check(lib.b2r_check(m._h, native.current_stream()))
+    runs[name] = (shards, picked)
+  (shards_a, picked_a), (shards_b, picked_b) = runs['A'], runs['B']
+  assert len(picked_a) == len(picked_b) == 8
+  for ia, ib in zip(picked_a, picked_b):
+    assert np.array_equal(ia, ib)
+  for ma, mb in zip(shards_a, shards_b):
+    assert ma.add_count == mb.add_count
+    assert list(ma.invalid_range) == list(mb.invalid_range)
+    for la, lb in zip(ma.sum_tree.nodes, mb.sum_tree.nodes):
+      assert np.array_equal(la.view(np.uint64), lb.view(np.uint64))
+    lo = int(mb.cursor()) - 40
+    assert (ma._read_column('observation', lo, 40).tobytes() ==
+            mb._read_column('observation', lo, 40).tobytes())
+
+
+def test_early_publish_latches_a_tree_change_behind_its_back(gpu):
+  """With early publish, nothing but the sharded steps may change a shard's tree between
+  two steps: a set_priority in between makes the next sampler find a root different from
+  the total its peers were given, and it latches B2R_ERR_STALE_TOTAL instead of letting
+  the ranks apportion the batch from different totals."""
+  from dopamine_b200.replay_memory import sharded_replay
+  torch, native = gpu.torch, gpu.native
+  lib = native.lib()
+  world, cap, global_batch, rows = 2, 20000, 64, 64
+  support = gpu.ra.make_support(10., ATOMS)
+  logits = torch.zeros(rows, ACTIONS, ATOMS, dtype=torch.float32, device='cuda')
+  shards = [_filled(gpu, cap, 32, seed=90 + g, hot=False)[0] for g in range(world)]
+  xs = sharded_replay.PeerExchange.emulated(world)
+  for x in xs:
+    x.set_early_publish(True)
+  state = [_sharded_step_args(gpu, m, rows, support, logits) for m in shards]
+
+  def step_all(k):
+    for g in range(world):
+      st = state[g]
+      st['args'].batch = global_batch
+      native.check(lib.b2r_train_step_sharded_device(
+          shards[g]._h, xs[g]._h, global_batch, 31, k, st['ctypes'].byref(st['batch']),
+          st['ctypes'].byref(st['args']), st['slots'].data_ptr(), st['count'].data_ptr(),
+          rows, native.current_stream()))
+    torch.cuda.synchronize()
+
+  for g in range(world):
+    xs[g].publish(shards[g])
+  step_all(0)
+  step_all(1)
+  for m in shards:
+    native.check(lib.b2r_check(m._h, native.current_stream()))
+  shards[0].set_priority(np.array([5, 6], np.int32), np.array([3.0, 4.0], np.float32))
+  step_all(2)
+  status = lib.b2r_check(shards[0]._h, native.current_stream())
+  assert status == native.ERR_STALE_TOTAL
+  assert 'changed between the early publish' in native.last_error()
+  native.check(lib.b2r_check(shards[1]._h, native.current_stream()))
+
+
 @pytest.mark.parametrize('variant', ['tma', 'reg'])
 def test_each_gather_variant_passes_the_gather_parity_suite(variant):
   """The frame copies have two kernels: the TMA-staged one (cp.async.bulk into shared
