@@ -107,6 +107,10 @@ struct LossArgs {
   // kernel has applied the write-back itself (at most 32 rows), so that the one-CTA tree
   // kernel launched behind it returns at once; left alone otherwise.
   unsigned int *tree_done;
+  // nullable: a second copy of the per-row losses (and of the row count behind them, at
+  // [batch]) in the caller's page-locked memory: the host-facing trainer's result slot,
+  // written by the kernel instead of copied by a call.
+  float *loss_host;
 };
 
 // One CTA per batch row, one warp per action (rainbow_agent.py:200-293):
@@ -756,6 +760,11 @@ struct PreArgs {
   float *scratch;  // [rows][kPreRow]
   int rows, num_actions, num_atoms, warps;
   PreSync sync;
+  // nullable: device copy of the online logits, written as they are read.  The host-facing
+  // trainer lets this kernel read both logits tensors straight from the caller's
+  // page-locked memory (no copy calls on the host); the tail then reads its one row of
+  // online logits per transition from this copy instead of crossing PCIe again.
+  float *online_copy;
 };
 
 // CTA per row, warp per action (rows below 128: latency-bound).
@@ -781,6 +790,8 @@ __global__ void __launch_bounds__(1024) c51_pre_kernel(PreArgs a) {
     xo[t] = (i < N && warp < A) ? orow[warp * N + i] : -INFINITY;
     bp[t] = 0.f;
   }
+  float *__restrict__ ocopy =
+      a.online_copy != nullptr ? a.online_copy + (size_t)b * A * N : nullptr;
   float best_q = 0.f;
   int best_a = -1;
   for (int act = warp; act < A; act += W) {
@@ -791,6 +802,11 @@ __global__ void __launch_bounds__(1024) c51_pre_kernel(PreArgs a) {
         xt[t] = i < N ? trow[act * N + i] : -INFINITY;
         xo[t] = i < N ? orow[act * N + i] : -INFINITY;
       }
+    }
+    if (ocopy != nullptr) {
+#pragma unroll
+      for (int t = 0; t < PL; ++t)
+        if (lane + 32 * t < N) ocopy[act * N + lane + 32 * t] = xo[t];
     }
     // the two softmaxes interleave: their reductions do not depend on each other
     float m = -INFINITY, mo = -INFINITY;
@@ -887,6 +903,11 @@ __global__ void __launch_bounds__(kRowWarps * 32) c51_pre_rows_kernel(PreArgs a)
   B2R_MARK(1);
   const int b = blockIdx.x * kRowWarps + warp;
   if (b < a.rows) {
+    if (a.online_copy != nullptr) {
+      const float *__restrict__ src = a.online_logits + (size_t)b * A * N;
+      float *__restrict__ dst = a.online_copy + (size_t)b * A * N;
+      for (int k = lane; k < A * N; k += 32) dst[k] = src[k];
+    }
     const float *__restrict__ trow = a.target_logits + (size_t)b * A * N;
     float zl[PL], xn[PL];
 #pragma unroll
@@ -1146,6 +1167,7 @@ __device__ __forceinline__ float c51_post_row(const LossArgs &a,
   prio_out = sqrtf(__fadd_rn(ce, 1e-10f));
   if (lane == 0) {
     a.u.loss[b] = ce;
+    if (a.loss_host != nullptr) a.loss_host[b] = ce;
     a.u.priorities[b] = prio_out;
     if (a.u.weights) a.u.weights[b] = w;
     a.weighted[b] = __fmul_rn(w, ce);
@@ -1191,8 +1213,11 @@ c51_post_kernel(LossArgs a, const float *__restrict__ scratch, int have_stats) {
   pdl_acquire();
   B2R_MARK(11);
   const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
-  if (a.count_copy != nullptr && blockIdx.x == 0 && threadIdx.x == 0)
-    *a.count_copy = a.u.batch_count ? *a.u.batch_count : a.u.batch;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int all = a.u.batch_count ? *a.u.batch_count : a.u.batch;
+    if (a.count_copy != nullptr) *a.count_copy = all;
+    if (a.loss_host != nullptr) reinterpret_cast<int32_t *>(a.loss_host)[a.u.batch] = all;
+  }
   if ((int)blockIdx.x * kRowWarps >= rows) return;  // (no mean loss with batch_count)
   const int b = blockIdx.x * kRowWarps + warp;
   const bool row_ok = b < rows;
@@ -1278,6 +1303,8 @@ c51_post_tree_kernel(LossArgs a, const float *__restrict__ scratch, int have_sta
   const bool tree_cta = blockIdx.x == 0;
   if (tree_cta) {
     if (a.count_copy != nullptr && threadIdx.x == 0) *a.count_copy = rows;
+    if (a.loss_host != nullptr && threadIdx.x == 0)
+      reinterpret_cast<int32_t *>(a.loss_host)[a.u.batch] = rows;
     if (with_tree) tree_update_tiny_issue(a.tree, warp, lane, &tl);
   } else if (warp < kPostRowWarps) {
     const float pmin = a.u.sampling_probabilities ? *a.u.min_probability : INFINITY;
@@ -1410,13 +1437,15 @@ int c51_scratch_floats_per_row() { return kPreRow; }
 // First half over `rows` rows of logits; scratch: device [rows][kPreRow] floats.  Sets
 // *have_stats when the launch leaves the online softmax statistics in the scratch.
 int c51_pre_launch(const b2r_c51_args *args, int rows, float *scratch, const PreSync &sync,
-                   cudaStream_t s, int *have_stats) {
+                   cudaStream_t s, int *have_stats, const float *online_src,
+                   float *online_copy) {
   if (!args || rows <= 0 || !scratch || !args->target_logits || !args->online_logits ||
       !args->support)
     return fail(B2R_ERR_INVALID_ARGUMENT, "bad C51 arguments");
   PreArgs a;
   a.target_logits = args->target_logits;
-  a.online_logits = args->online_logits;
+  a.online_logits = online_src != nullptr ? online_src : args->online_logits;
+  a.online_copy = online_copy;
   a.support = args->support;
   a.scratch = scratch;
   a.rows = rows;
@@ -1460,7 +1489,7 @@ bool c51_post_takes_tree(const b2r_c51_args *args, const b2r_tree *tree,
 int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_stats,
                     cudaStream_t s, int64_t *err, int32_t *count_copy, b2r_tree *tree,
                     const int32_t *indices, unsigned int *tree_done,
-                    const b2r_exchange *publish) {
+                    const b2r_exchange *publish, float *loss_host) {
   if (!args || args->batch <= 0 || !scratch)
     return fail(B2R_ERR_INVALID_ARGUMENT, "bad C51 shape");
   if (args->batch_count && args->mean_weighted_loss)
@@ -1475,6 +1504,7 @@ int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_sta
   a.err = err;
   a.count_copy = count_copy;
   a.tree_done = nullptr;
+  a.loss_host = loss_host;
   a.warps = 0;
   B2R_TRY(ensure_loss_scratch(args->batch));
   a.weighted = g_weighted;
@@ -1535,6 +1565,7 @@ int c51_loss_launch(const b2r_c51_args *args, cudaStream_t s, b2r_tree *tree,
   a.err = nullptr;
   a.count_copy = nullptr;
   a.tree_done = nullptr;
+  a.loss_host = nullptr;
   if (tree != nullptr) {
     if (!c51_can_fuse_writeback(args, tree))
       return fail(B2R_ERR_INVALID_ARGUMENT, "this batch cannot fuse its write-back");

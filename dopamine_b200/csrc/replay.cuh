@@ -299,8 +299,9 @@ struct b2r_buffer {
   // beside the sampler (c51.cu: c51_pre_kernel)
   cudaStream_t side3 = nullptr;
   cudaEvent_t ev_c51_fork = nullptr, ev_c51_pre = nullptr;
-  float *c51_bestp = nullptr;  // device [c51_bestp_rows][64 probabilities | 64 stats]
+  float *c51_bestp = nullptr;  // device [2 halves][c51_bestp_rows][64 probabilities | 64 stats]
   int64_t c51_bestp_rows = 0;
+  int c51_half = 0;            // half the next step's first half writes
   unsigned int *pre_sync = nullptr;  // device [4]: PreSync done, seen, ticket
   // Deferred frame copies (b2r_set_deferred_frames): the copies of a fused step are not
   // joined into the caller's stream when the call returns but when b2r_join_frames is

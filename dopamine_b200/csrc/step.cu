@@ -74,11 +74,22 @@ struct ShardSpec {
   int32_t max_rows;
 };
 
+// The host-facing trainer without copy calls: the first half of the loss reads both
+// logits tensors straight from the caller's page-locked memory (and leaves a device copy
+// of the online logits for the tail), the tail writes the per-row losses into the
+// trainer's page-locked result slot.  Only with the loss in two halves.
+struct DirectIO {
+  const float *online_src;   // device-visible address of the caller's online logits
+  float *online_copy;        // device buffer the tail reads (c51->online_logits)
+  float *loss_host;          // device-visible address of the result slot
+  cudaEvent_t first_half_after;  // nullable: what last read online_copy / the scratch half
+};
+
 // wait_before_loss / loss_done (nullable): events of the trainer's copy stream.
 static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offset,
                       const b2r_batch *out, const b2r_c51_args *c51, cudaStream_t s,
                       cudaEvent_t wait_before_loss, cudaEvent_t loss_done,
-                      const ShardSpec *shard = nullptr) {
+                      const ShardSpec *shard = nullptr, const DirectIO *direct = nullptr) {
   if (!b || !out || !c51) return fail(B2R_ERR_INVALID_ARGUMENT, "NULL argument");
   if (!b->tree) return fail(B2R_ERR_UNSUPPORTED, "not a prioritized buffer");
   if (batch <= 0 || batch > 60000)
@@ -115,26 +126,47 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   // (A shard does not know its row count before it has sampled: the first half covers
   // every row its logits hold.)
   const bool split_loss = !debug_skip() && c51_can_split(&loss);
+  if (direct != nullptr && !split_loss)
+    return fail(B2R_ERR_INVALID_ARGUMENT, "direct logits need the loss in two halves");
   PreSync pre_sync = {nullptr, nullptr, nullptr};
   int have_stats = 0;
+  float *scratch = nullptr;
   if (split_loss) {
+    // (two halves of scratch: with direct I/O the first half of step n + 1 is not
+    // ordered behind the tail of step n, which may still be reading its rows)
     if (b->c51_bestp_rows < rows_cap) {
-      if (b->c51_bestp) cudaFree(b->c51_bestp);
+      if (b->c51_bestp) {
+        B2R_CUDA(cudaStreamSynchronize(b->side3));
+        B2R_CUDA(cudaStreamSynchronize(s));
+        cudaFree(b->c51_bestp);
+      }
       b->c51_bestp = nullptr;
       b->c51_bestp_rows = 0;
       int64_t cap = 256;
       while (cap < rows_cap) cap *= 2;
       B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&b->c51_bestp),
-                          (size_t)cap * c51_scratch_floats_per_row() * sizeof(float)));
+                          2 * (size_t)cap * c51_scratch_floats_per_row() * sizeof(float)));
       b->c51_bestp_rows = cap;
     }
+    scratch = b->c51_bestp + (size_t)(b->c51_half & 1) * (size_t)b->c51_bestp_rows *
+                                 c51_scratch_floats_per_row();
+    b->c51_half ^= 1;
     pre_sync.done = b->pre_sync;
     pre_sync.seen = b->pre_sync + 1;
     pre_sync.ticket = b->pre_sync + 2;
-    B2R_CUDA(cudaEventRecord(b->ev_c51_fork, s));
-    B2R_CUDA(cudaStreamWaitEvent(b->side3, b->ev_c51_fork, 0));
-    if (wait_before_loss) B2R_CUDA(cudaStreamWaitEvent(b->side3, wait_before_loss, 0));
-    B2R_TRY(c51_pre_launch(&loss, rows_cap, b->c51_bestp, pre_sync, b->side3, &have_stats));
+    if (direct != nullptr) {
+      // nothing on `s` feeds the first half: it waits only for whoever last read the
+      // buffers it writes (the tail two steps back)
+      if (direct->first_half_after)
+        B2R_CUDA(cudaStreamWaitEvent(b->side3, direct->first_half_after, 0));
+      B2R_TRY(c51_pre_launch(&loss, rows_cap, scratch, pre_sync, b->side3, &have_stats,
+                             direct->online_src, direct->online_copy));
+    } else {
+      B2R_CUDA(cudaEventRecord(b->ev_c51_fork, s));
+      B2R_CUDA(cudaStreamWaitEvent(b->side3, b->ev_c51_fork, 0));
+      if (wait_before_loss) B2R_CUDA(cudaStreamWaitEvent(b->side3, wait_before_loss, 0));
+      B2R_TRY(c51_pre_launch(&loss, rows_cap, scratch, pre_sync, b->side3, &have_stats));
+    }
     B2R_CUDA(cudaEventRecord(b->ev_c51_pre, b->side3));
   }
   // Staged adds (rows on the side stream beside the tree update at larger batches).
@@ -249,10 +281,11 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
                  : (!shard && !debug_skip() && c51_can_fuse_writeback(&loss, b->tree));
   unsigned int *tree_done = tail_counted ? b->pre_sync + 3 : nullptr;
   if (split_loss)
-    B2R_TRY(c51_post_launch(&loss, b->c51_bestp, have_stats, s, b->status,
+    B2R_TRY(c51_post_launch(&loss, scratch, have_stats, s, b->status,
                             shard && count != shard->out_count ? shard->out_count : nullptr,
                             tail_writeback || tail_counted ? b->tree : nullptr,
-                            out->indices, tree_done, tail_counted ? early : nullptr));
+                            out->indices, tree_done, tail_counted ? early : nullptr,
+                            direct ? direct->loss_host : nullptr));
   else if (tail_writeback)
     B2R_TRY(c51_loss_launch(&loss, s, b->tree, out->indices));
   else if (!(debug_skip() & 1))
@@ -306,6 +339,18 @@ struct b2r_trainer {
   // graph mode: the step's kernels captured once per logits set
   cudaStream_t cap = nullptr;
   cudaGraphExec_t exec[2] = {nullptr, nullptr};
+  // Direct I/O: logits read by the kernels from the caller's page-locked memory, losses
+  // written by the kernels into the result ring — no copy calls, no copy streams (see
+  // DirectIO).  Decided per call: it needs page-locked logits (checked once per pointer
+  // pair) and the loss in two halves.  Default: only for the synchronous trainer
+  // (pipeline_depth 0), where the host waits for every step and the saved calls count
+  // (48.7 against 57.2 us per update with adds); a pipelined trainer is bound by the
+  // device, whose first half of the loss then reads 235 KB over PCIe beside the flush
+  // kernel's zero-copy reads (33.5 against 29.5 us).  B2R_TRAINER_DIRECT=0|1 forces it.
+  bool direct_ok = true;
+  const float *probed[2] = {nullptr, nullptr};  // last pointer pair looked up ...
+  const float *probed_dev[2] = {nullptr, nullptr};  // ... and their device addresses
+  float *ring_dev = nullptr;  // the result ring as the device sees it
   // results
   int ring = 1;
   float *ring_host = nullptr;  // pinned [ring][batch]
@@ -483,6 +528,16 @@ int b2r_trainer_create(b2r_buffer *b, const b2r_trainer_config *cfg,
   t->ev_done.resize(t->ring);
   for (int k = 0; k < t->ring; ++k)
     B2R_CUDA(cudaEventCreateWithFlags(&t->ev_done[k], cudaEventDisableTiming));
+  {
+    void *as_device = nullptr;
+    if (cudaHostGetDevicePointer(&as_device, t->ring_host, 0) == cudaSuccess)
+      t->ring_dev = static_cast<float *>(as_device);
+    else
+      cudaGetLastError();
+    const char *e = std::getenv("B2R_TRAINER_DIRECT");
+    t->direct_ok = t->ring_dev != nullptr &&
+                   (e != nullptr ? std::atoi(e) != 0 : cfg->pipeline_depth == 0);
+  }
   *out = t;
   return B2R_OK;
 }
@@ -534,6 +589,45 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   b2r::g_host_trace.start();
   const int64_t n = t->submitted;
   const int set = (int)(n & 1);
+  // ---- direct I/O: no copies, the kernels reach into the caller's page-locked memory
+  if (t->direct_ok && !t->cfg.use_graph) {
+    if (t->probed[0] != online_logits || t->probed[1] != target_logits) {
+      void *d0 = nullptr, *d1 = nullptr;
+      const bool mapped =
+          cudaHostGetDevicePointer(&d0, const_cast<float *>(online_logits), 0) == cudaSuccess &&
+          cudaHostGetDevicePointer(&d1, const_cast<float *>(target_logits), 0) == cudaSuccess;
+      if (!mapped) cudaGetLastError();  // pageable memory: the copy path below
+      t->probed[0] = online_logits;
+      t->probed[1] = target_logits;
+      t->probed_dev[0] = mapped ? static_cast<const float *>(d0) : nullptr;
+      t->probed_dev[1] = mapped ? static_cast<const float *>(d1) : nullptr;
+    }
+    b2r_c51_args c51 = t->c51;
+    c51.batch = t->exchange ? t->cfg.logit_rows : t->cfg.batch;
+    if (t->probed_dev[0] != nullptr && b2r::c51_can_split(&c51)) {
+      const int slot = (int)(n % t->ring);
+      c51.online_logits = t->logits[set][0];   // device copy left by the first half
+      c51.target_logits = t->probed_dev[1];
+      c51.loss = t->loss_buf[set];
+      b2r::DirectIO io;
+      io.online_src = t->probed_dev[0];
+      io.online_copy = t->logits[set][0];
+      io.loss_host = t->ring_dev + (size_t)slot * (t->cfg.logit_rows + 1);
+      // the buffers of this set were last read by the tail of step n - 2
+      io.first_half_after = n >= 2 ? t->ev_done[(size_t)((n - 2) % t->ring)] : nullptr;
+      b2r::ShardSpec shard = {t->exchange, t->slots, t->count_buf[set], t->cfg.logit_rows};
+      // (the result slot of step n is read by the host after ev_done[slot], recorded
+      // behind the tail; with ring = depth + 1 slots it was collected before this call)
+      B2R_TRY(b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch, &c51, s,
+                              nullptr, t->ev_done[slot], t->exchange ? &shard : nullptr, &io));
+      t->submitted = n + 1;
+      b2r::g_host_trace.lap(7);
+      const int status = collect(t, n - t->cfg.pipeline_depth, loss_out, loss_step);
+      b2r::g_host_trace.lap(0);
+      b2r::g_host_trace.calls += 1;
+      return status;
+    }
+  }
   const size_t logit_bytes = (size_t)t->cfg.logit_rows * t->cfg.num_actions *
                              t->cfg.num_atoms * sizeof(float);
   // inputs: on the copy stream, beside the sampler; set `set` was last read by the

@@ -567,8 +567,11 @@ int c51_loss_launch(const b2r_c51_args *args, cudaStream_t stream, b2r_tree *tre
 struct PreSync;
 bool c51_can_split(const b2r_c51_args *args);
 int c51_scratch_floats_per_row();
+// online_src / online_copy (nullable): read the online logits from there (the caller's
+// page-locked host memory) and leave a device copy for the tail.
 int c51_pre_launch(const b2r_c51_args *args, int rows, float *scratch, const PreSync &sync,
-                   cudaStream_t stream, int *have_stats);
+                   cudaStream_t stream, int *have_stats, const float *online_src = nullptr,
+                   float *online_copy = nullptr);
 // ... and the tail over the sampled rows.  err (nullable): asynchronous error latch.
 // tree != nullptr (c51_post_takes_tree: batches of at most 32 rows): the tail and
 // set_priority(indices, priorities) as one thread-block cluster.
@@ -581,6 +584,6 @@ int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_sta
                     cudaStream_t stream, int64_t *err, int32_t *count_copy = nullptr,
                     b2r_tree *tree = nullptr, const int32_t *indices = nullptr,
                     unsigned int *tree_done = nullptr,
-                    const b2r_exchange *publish = nullptr);
+                    const b2r_exchange *publish = nullptr, float *loss_host = nullptr);
 
 }  // namespace b2r

@@ -236,23 +236,42 @@ def test_fused_step_in_cuda_graph(gpu):
     assert np.array_equal(la.view(np.uint64), lb.view(np.uint64))
 
 
-@pytest.mark.parametrize('depth,graph', [(0, False), (2, False), (2, True)])
-def test_trainer_host_steps_match_oracles(gpu, depth, graph):
+@pytest.mark.parametrize('depth,graph,pinned,batch', [
+    (0, False, False, 32), (2, False, False, 32), (2, True, False, 32),
+    (0, False, True, 32), (1, False, True, 32), (2, False, True, 32), (3, False, True, 200)])
+def test_trainer_host_steps_match_oracles(gpu, depth, graph, pinned, batch):
   """The pipelined host-facing trainer: adds between steps, logits from host
   memory, losses handed back `depth` calls later; batch, losses and tree checked
-  against the oracles step by step."""
+  against the oracles step by step.  pinned: the logits live in page-locked memory —
+  the kernels then read them in place and write the losses into the result ring
+  themselves (no copy calls: DirectIO in step.cu; default only at depth 0, forced here
+  for every depth); pageable logits take the copies."""
+  import os
   torch = gpu.torch
-  cap, batch = 50000, 32
+  if pinned:
+    os.environ['B2R_TRAINER_DIRECT'] = '1'
+  else:
+    os.environ.pop('B2R_TRAINER_DIRECT', None)
+  cap = 50000
   mem, tree, cols = _filled(gpu, cap, batch, seed=21, hot=False)
   trainer = gpu.ra.ReplayTrainer(mem, ACTIONS, ATOMS, 10., pipeline_depth=depth,
                                  seed=21, use_graph=graph)
   rng = np.random.RandomState(4)
   inputs, losses = [], {}
+  # (page-locked buffers are the caller's until the step has run: one pair per step)
+  pin = [(torch.empty(batch, ACTIONS, ATOMS, dtype=torch.float32).pin_memory(),
+          torch.empty(batch, ACTIONS, ATOMS, dtype=torch.float32).pin_memory())
+         for _ in range(6)] if pinned else None
   for step in range(6):
     online = rng.randn(batch, ACTIONS, ATOMS).astype(np.float32)
     target = rng.randn(batch, ACTIONS, ATOMS).astype(np.float32)
     inputs.append((online, target))
-    loss, done = trainer.step(online, target)
+    if pinned:
+      pin[step][0].copy_(torch.from_numpy(online))
+      pin[step][1].copy_(torch.from_numpy(target))
+      loss, done = trainer.step(pin[step][0], pin[step][1])
+    else:
+      loss, done = trainer.step(online, target)
     assert done == step - depth if step >= depth else done == -1
     if done >= 0:
       losses[done] = loss
@@ -271,6 +290,7 @@ def test_trainer_host_steps_match_oracles(gpu, depth, graph):
     if step in losses:
       assert losses[step].tobytes() == losses[('device', step)].tobytes(), step
   assert 5 - depth in losses
+  os.environ.pop('B2R_TRAINER_DIRECT', None)
   for l, level in enumerate(mem.sum_tree.nodes):
     assert np.array_equal(level.view(np.uint64), tree.level(l).view(np.uint64)), l
 
