@@ -83,6 +83,10 @@ struct DirectIO {
   float *online_copy;        // device buffer the tail reads (c51->online_logits)
   float *loss_host;          // device-visible address of the result slot
   cudaEvent_t first_half_after;  // nullable: what last read online_copy / the scratch half
+  // online_src == nullptr: no direct I/O, only the trainer's EAGER launch order — the
+  // logits are ready at `wait_before_loss`, nothing on `s` feeds them and nothing is being
+  // captured, so the first half is neither forked from `s` nor joined back into it (its
+  // hand-shake with the sampler goes through memory): four driver calls less per update.
 };
 
 // wait_before_loss / loss_done (nullable): events of the trainer's copy stream.
@@ -126,8 +130,9 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   // (A shard does not know its row count before it has sampled: the first half covers
   // every row its logits hold.)
   const bool split_loss = !debug_skip() && c51_can_split(&loss);
-  if (direct != nullptr && !split_loss)
+  if (direct != nullptr && direct->online_src != nullptr && !split_loss)
     return fail(B2R_ERR_INVALID_ARGUMENT, "direct logits need the loss in two halves");
+  const bool unjoined = direct != nullptr && split_loss;  // (see DirectIO)
   PreSync pre_sync = {nullptr, nullptr, nullptr};
   int have_stats = 0;
   float *scratch = nullptr;
@@ -154,11 +159,12 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
     pre_sync.done = b->pre_sync;
     pre_sync.seen = b->pre_sync + 1;
     pre_sync.ticket = b->pre_sync + 2;
-    if (direct != nullptr) {
+    if (unjoined) {
       // nothing on `s` feeds the first half: it waits only for whoever last read the
-      // buffers it writes (the tail two steps back)
+      // buffers it writes (the tail two steps back) and for the logits
       if (direct->first_half_after)
         B2R_CUDA(cudaStreamWaitEvent(b->side3, direct->first_half_after, 0));
+      if (wait_before_loss) B2R_CUDA(cudaStreamWaitEvent(b->side3, wait_before_loss, 0));
       B2R_TRY(c51_pre_launch(&loss, rows_cap, scratch, pre_sync, b->side3, &have_stats,
                              direct->online_src, direct->online_copy));
     } else {
@@ -166,8 +172,8 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
       B2R_CUDA(cudaStreamWaitEvent(b->side3, b->ev_c51_fork, 0));
       if (wait_before_loss) B2R_CUDA(cudaStreamWaitEvent(b->side3, wait_before_loss, 0));
       B2R_TRY(c51_pre_launch(&loss, rows_cap, scratch, pre_sync, b->side3, &have_stats));
+      B2R_CUDA(cudaEventRecord(b->ev_c51_pre, b->side3));
     }
-    B2R_CUDA(cudaEventRecord(b->ev_c51_pre, b->side3));
   }
   // Staged adds (rows on the side stream beside the tree update at larger batches).
   // Early publish (b2r_exchange_set_early_publish): whichever kernel of this call writes
@@ -251,7 +257,8 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
     B2R_CUDA(cudaStreamWaitEvent(b->side, b->ev_fork, 0));
     // (deferred: the first half of the loss rejoins through the copies' stream, so that
     // the next sampler's only parent in a captured graph is this step's write-back)
-    if (deferred && split_loss) B2R_CUDA(cudaStreamWaitEvent(b->side, b->ev_c51_pre, 0));
+    if (deferred && split_loss && !unjoined)
+      B2R_CUDA(cudaStreamWaitEvent(b->side, b->ev_c51_pre, 0));
     B2R_TRY(launch_gather(b, rows_cap, sample_idx, out, b->side, count, true,
                           flags.desc ? &flags : nullptr));
     B2R_CUDA(cudaEventRecord(b->ev_join, b->side));
@@ -285,7 +292,7 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
                             shard && count != shard->out_count ? shard->out_count : nullptr,
                             tail_writeback || tail_counted ? b->tree : nullptr,
                             out->indices, tree_done, tail_counted ? early : nullptr,
-                            direct ? direct->loss_host : nullptr));
+                            direct && direct->online_src ? direct->loss_host : nullptr));
   else if (tail_writeback)
     B2R_TRY(c51_loss_launch(&loss, s, b->tree, out->indices));
   else if (!(debug_skip() & 1))
@@ -300,7 +307,8 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
                                         tree_done)));
   if (flush_behind) B2R_TRY(flush_queue(b, s, false, early));
   if (frames && !deferred) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join, 0));
-  if (split_loss && !(deferred && frames)) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_c51_pre, 0));
+  if (split_loss && !unjoined && !(deferred && frames))
+    B2R_CUDA(cudaStreamWaitEvent(s, b->ev_c51_pre, 0));
   g_host_trace.lap(6);
   return B2R_OK;
 }
@@ -640,8 +648,15 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   B2R_CUDA(cudaEventRecord(t->ev_in[set], t->copy));
   // The loss buffer of this set was last read by the result copy of step n - 2.  With a
   // pipeline of depth <= 1 the host has already waited for that copy (collect); deeper
-  // pipelines order the step behind it on the device.
-  if (n >= 2 && t->cfg.pipeline_depth >= 2)
+  // pipelines order the step behind it on the device: the eager path through the first
+  // half of the loss (which the sampler of this step waits for: `hints` below), the
+  // graph-replayed path on `s`.
+  const bool behind_copy = n >= 2 && t->cfg.pipeline_depth >= 2;
+  b2r::DirectIO hints = {nullptr, nullptr, nullptr,
+                         n >= 2 ? t->ev_done[(size_t)((n - 2) % t->ring)] : nullptr};
+  b2r_c51_args probe = t->c51;  // (c51.batch is the rows behind the sampler)
+  const bool through_first_half = !t->cfg.use_graph && b2r::c51_can_split(&probe);
+  if (behind_copy && !through_first_half)
     B2R_CUDA(cudaStreamWaitEvent(s, t->ev_done[(size_t)((n - 2) % t->ring)], 0));
   if (t->exchange) {
     b2r_c51_args c51 = t->c51;
@@ -650,7 +665,7 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
     c51.loss = t->loss_buf[set];
     b2r::ShardSpec shard = {t->exchange, t->slots, t->count_buf[set], t->cfg.logit_rows};
     B2R_TRY(b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch, &c51, s,
-                            t->ev_in[set], t->ev_loss[set], &shard));
+                            t->ev_in[set], t->ev_loss[set], &shard, &hints));
   } else if (t->cfg.use_graph && n >= 2) {
     // Everything host-dependent (staged adds, validity context) goes first, eagerly;
     // the replayed graph reads it from HBM.
@@ -667,7 +682,7 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
     c51.target_logits = t->logits[set][1];
     c51.loss = t->loss_buf[set];
     B2R_TRY(b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch, &c51, s,
-                            t->ev_in[set], t->ev_loss[set]));
+                            t->ev_in[set], t->ev_loss[set], nullptr, &hints));
   }
   // result: per-row losses into this step's pinned slot (copy stream, after the loss)
   const int slot = (int)(n % t->ring);
