@@ -292,7 +292,7 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
                             shard && count != shard->out_count ? shard->out_count : nullptr,
                             tail_writeback || tail_counted ? b->tree : nullptr,
                             out->indices, tree_done, tail_counted ? early : nullptr,
-                            direct && direct->online_src ? direct->loss_host : nullptr));
+                            direct ? direct->loss_host : nullptr));
   else if (tail_writeback)
     B2R_TRY(c51_loss_launch(&loss, s, b->tree, out->indices));
   else if (!(debug_skip() & 1))
@@ -640,7 +640,17 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
                              t->cfg.num_atoms * sizeof(float);
   // inputs: on the copy stream, beside the sampler; set `set` was last read by the
   // loss kernel of step n - 2.
-  if (n >= 2) B2R_CUDA(cudaStreamWaitEvent(t->copy, t->ev_loss[set], 0));
+  // (step n - 2's loss is done: ev_loss[set] in the copy path, the event behind its tail
+  // — ev_done of its slot — when the kernel wrote the losses; waiting for the later of the
+  // two records covers both)
+  b2r_c51_args probe = t->c51;  // (c51.batch is the rows behind the sampler)
+  const bool through_first_half = !t->cfg.use_graph && b2r::c51_can_split(&probe);
+  static const bool loss_copy = std::getenv("B2R_TRAINER_LOSS_COPY") != nullptr;
+  const bool kernel_writes_losses = through_first_half && t->ring_dev != nullptr && !loss_copy;
+  if (n >= 2)
+    B2R_CUDA(cudaStreamWaitEvent(
+        t->copy, kernel_writes_losses ? t->ev_done[(size_t)((n - 2) % t->ring)]
+                                      : t->ev_loss[set], 0));
   B2R_CUDA(cudaMemcpyAsync(t->logits[set][0], online_logits, logit_bytes,
                            cudaMemcpyHostToDevice, t->copy));
   B2R_CUDA(cudaMemcpyAsync(t->logits[set][1], target_logits, logit_bytes,
@@ -654,8 +664,13 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
   const bool behind_copy = n >= 2 && t->cfg.pipeline_depth >= 2;
   b2r::DirectIO hints = {nullptr, nullptr, nullptr,
                          n >= 2 ? t->ev_done[(size_t)((n - 2) % t->ring)] : nullptr};
-  b2r_c51_args probe = t->c51;  // (c51.batch is the rows behind the sampler)
-  const bool through_first_half = !t->cfg.use_graph && b2r::c51_can_split(&probe);
+  // ... and then the tail writes the per-row losses into this step's page-locked result
+  // slot itself (33 words over PCIe): no result copy, no result-copy stream; the event
+  // the host collects on is recorded behind the tail.  B2R_TRAINER_LOSS_COPY=1: the copy.
+  const int slot = (int)(n % t->ring);
+  if (kernel_writes_losses)
+    hints.loss_host = t->ring_dev + (size_t)slot * (t->cfg.logit_rows + 1);
+  cudaEvent_t after_loss = kernel_writes_losses ? t->ev_done[slot] : t->ev_loss[set];
   if (behind_copy && !through_first_half)
     B2R_CUDA(cudaStreamWaitEvent(s, t->ev_done[(size_t)((n - 2) % t->ring)], 0));
   if (t->exchange) {
@@ -665,7 +680,7 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
     c51.loss = t->loss_buf[set];
     b2r::ShardSpec shard = {t->exchange, t->slots, t->count_buf[set], t->cfg.logit_rows};
     B2R_TRY(b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch, &c51, s,
-                            t->ev_in[set], t->ev_loss[set], &shard, &hints));
+                            t->ev_in[set], after_loss, &shard, &hints));
   } else if (t->cfg.use_graph && n >= 2) {
     // Everything host-dependent (staged adds, validity context) goes first, eagerly;
     // the replayed graph reads it from HBM.
@@ -682,15 +697,17 @@ int b2r_trainer_step_host(b2r_trainer *t, const float *online_logits,
     c51.target_logits = t->logits[set][1];
     c51.loss = t->loss_buf[set];
     B2R_TRY(b2r::train_step(t->buf, t->cfg.batch, t->cfg.seed, 0, &t->batch, &c51, s,
-                            t->ev_in[set], t->ev_loss[set], nullptr, &hints));
+                            t->ev_in[set], after_loss, nullptr, &hints));
   }
-  // result: per-row losses into this step's pinned slot (copy stream, after the loss)
-  const int slot = (int)(n % t->ring);
-  B2R_CUDA(cudaStreamWaitEvent(t->copy_out, t->ev_loss[set], 0));
-  B2R_CUDA(cudaMemcpyAsync(t->ring_host + (size_t)slot * (t->cfg.logit_rows + 1),
-                           t->loss_buf[set], (size_t)(t->cfg.logit_rows + 1) * sizeof(float),
-                           cudaMemcpyDeviceToHost, t->copy_out));
-  B2R_CUDA(cudaEventRecord(t->ev_done[slot], t->copy_out));
+  if (!kernel_writes_losses) {
+    // result: per-row losses into this step's pinned slot (copy stream, after the loss)
+    B2R_CUDA(cudaStreamWaitEvent(t->copy_out, t->ev_loss[set], 0));
+    B2R_CUDA(cudaMemcpyAsync(t->ring_host + (size_t)slot * (t->cfg.logit_rows + 1),
+                             t->loss_buf[set],
+                             (size_t)(t->cfg.logit_rows + 1) * sizeof(float),
+                             cudaMemcpyDeviceToHost, t->copy_out));
+    B2R_CUDA(cudaEventRecord(t->ev_done[slot], t->copy_out));
+  }
   t->submitted = n + 1;
   b2r::g_host_trace.lap(7);
   const int status = collect(t, n - t->cfg.pipeline_depth, loss_out, loss_step);
