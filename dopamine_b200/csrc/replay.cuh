@@ -144,6 +144,28 @@ __device__ __forceinline__ void pre_sync_consume(const PreSync &p) {
     if (clock64() - t0 > 4000000000ll) break;
   *p.seen = seen + 1u;
 }
+// The same in two steps, so that the two loads are in flight long before the closing
+// thread needs their answer (the first half is normally done by then: no spin at all).
+struct PreSyncPeek {
+  unsigned int seen, done;
+};
+__device__ __forceinline__ PreSyncPeek pre_sync_peek(const PreSync &p) {
+  PreSyncPeek k = {0u, 1u};
+  if (p.done != nullptr) {
+    k.seen = *p.seen;
+    k.done = ld_acquire_u32(p.done);
+  }
+  return k;
+}
+__device__ __forceinline__ void pre_sync_consume(const PreSync &p, const PreSyncPeek &k) {
+  if (p.done == nullptr) return;
+  if (k.done == k.seen) {  // not yet when we looked: wait now
+    const long long t0 = clock64();
+    while (ld_acquire_u32(p.done) == k.seen)
+      if (clock64() - t0 > 4000000000ll) break;
+  }
+  *p.seen = k.seen + 1u;
+}
 // 24-bit form of the step tag, never 0 (a descriptor that was never written is 0)
 __device__ __forceinline__ uint32_t row_tag24(uint32_t tag) { return tag % 0xffffffu + 1u; }
 __device__ __forceinline__ uint64_t row_descriptor(uint32_t tag, int length, int64_t idx) {

@@ -904,12 +904,49 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
 
   // ---- only the last CTA to finish goes on (CLUSTER: CTA 0, after the barrier)
   if (CLUSTER) {
+    // (the closing thread's look at the first half of the loss travels with the barrier)
+    PreSyncPeek peek = {0u, 1u};
+    if (blockIdx.x == 0 && threadIdx.x == 0) peek = pre_sync_peek(a.pre);
     cluster_sync_relacq();
     if (blockIdx.x != 0) return;
     ws.inv_flag = s_flag;
     ws.spec_idx = s_cl_spec_idx;
     ws.spec_valid = s_cl_spec_valid;
     ws.cta_min = s_cl_min;
+    // The usual case at the agent's batch — every stratified pick valid, nothing to
+    // replace — is closed by warp 0 alone: a vote over the flags, a shuffle minimum over
+    // the CTAs' minima, the launch's counters; no block scan, no list, one barrier.
+    __shared__ int s_slow;
+    if (warp == 0) {
+      bool bad = false;
+      for (int p = lane; p < n_mine; p += 32) bad = bad || s_flag[p] != 0;
+      const bool slow = __any_sync(full, bad) || n_all > n_mine;
+      if (lane == 0) s_slow = slow ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_slow == 0) {
+      if (warp != 0) return;
+      float m = INFINITY;
+      if (want_min) {
+        for (int c = lane; c < (int)gridDim.x; c += 32) m = fminf(m, s_cl_min[c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(full, m, o));
+      }
+      if (lane == 0) {
+        if (a.counter) *a.counter = draws_before + 1;
+        if (exchange) *a.xchg.seq = xseq;
+        a.info[0] = B2R_OK;
+        a.info[1] = 0;
+        a.info[2] = 0;
+        a.info[3] = n_mine;
+        if (a.count_out) *a.count_out = n_mine;
+        if (want_min) *a.min_prob_out = m;
+        if (hand_over) st_release_u32(a.flags.final_word, row_tag);
+        pre_sync_consume(a.pre, peek);
+      }
+      B2R_MARK_ANY(20);
+      return;
+    }
   } else if (gridDim.x > 1) {
     __threadfence();
     __syncthreads();
