@@ -1286,10 +1286,12 @@ c51_post_tree_kernel(LossArgs a, const float *__restrict__ scratch, int have_sta
   __shared__ float s_sup[kPostRowWarps][kRowAtoms];
   __shared__ float s_prio[kTinyBatch];      // (CTA 0's copy is the one that is used)
   __shared__ float s_weighted[kTinyBatch];
-  namespace cg = cooperative_groups;
+  __shared__ __align__(8) uint64_t s_arrived;  // mbarrier: the rows' words have landed
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  cg::cluster_group cluster = cg::this_cluster();
+  const bool tree_cta = blockIdx.x == 0;
   B2R_MARK(10);
+  if (tree_cta && threadIdx.x == 0) mbar_init(&s_arrived, 1);
+  cluster_arrive_relaxed();  // (nobody sends before the mbarrier exists: waited for below)
   pdl_release();
   pdl_acquire();
   B2R_MARK(11);
@@ -1297,37 +1299,50 @@ c51_post_tree_kernel(LossArgs a, const float *__restrict__ scratch, int have_sta
   // when it turns out to be at most 32 rows — else the tree kernel behind this one does it)
   const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
   const bool with_tree = rows <= kTinyBatch;
+  const bool want_mean = a.u.mean_weighted_loss != nullptr;
   // CTA 0 is the tree's: warp l owns level l, loads its nodes and groups its entries now.
   // CTAs 1..7 are the rows': warps 0..4 compute one row each (and stride on).
   TinyLoads tl;
-  const bool tree_cta = blockIdx.x == 0;
+  float prio = 0.f, weighted = 0.f;
+  int my_row = -1;
   if (tree_cta) {
     if (a.count_copy != nullptr && threadIdx.x == 0) *a.count_copy = rows;
     if (a.loss_host != nullptr && threadIdx.x == 0)
       reinterpret_cast<int32_t *>(a.loss_host)[a.u.batch] = rows;
-    if (with_tree) tree_update_tiny_issue(a.tree, warp, lane, &tl);
+    if (with_tree) {
+      // one word per row (two with the mean loss) will arrive
+      if (threadIdx.x == 0) mbar_arrive_expect(&s_arrived, (uint32_t)rows * (want_mean ? 8u : 4u));
+      tree_update_tiny_issue(a.tree, warp, lane, &tl);
+    }
   } else if (warp < kPostRowWarps) {
     const float pmin = a.u.sampling_probabilities ? *a.u.min_probability : INFINITY;
     for (int b = ((int)blockIdx.x - 1) * kPostRowWarps + warp; b < rows;
          b += (kPostClusterCtas - 1) * kPostRowWarps) {
       __syncwarp();  // (this warp's shared rows are free again)
-      const float prio = c51_post_row(a, scratch, have_stats, b, rows, lane, pmin,
-                                      s_bestp[warp], s_sup[warp]);
-      if (lane == 0 && with_tree) {
-        cluster.map_shared_rank(s_prio, 0)[b] = prio;
-        if (a.u.mean_weighted_loss != nullptr)
-          cluster.map_shared_rank(s_weighted, 0)[b] = a.weighted[b];
-      }
+      prio = c51_post_row(a, scratch, have_stats, b, rows, lane, pmin, s_bestp[warp],
+                          s_sup[warp]);
+      my_row = b;  // (with the tree riding along there are at most 32 rows: one per warp)
+      if (want_mean) weighted = a.weighted[b];
     }
   }
   B2R_MARK_END(12);
-  cluster_sync_relacq();  // the rows' priorities are in CTA 0's shared memory
-  if (!tree_cta || !with_tree) return;
+  cluster_wait();
+  if (!with_tree) return;
+  if (!tree_cta) {
+    // the row's priority (and weighted loss) into CTA 0's shared memory, counted on its
+    // mbarrier: no fence, no second barrier
+    if (my_row >= 0 && lane == 0) {
+      st_async_u32(&s_prio[my_row], __float_as_uint(prio), &s_arrived, 0);
+      if (want_mean) st_async_u32(&s_weighted[my_row], __float_as_uint(weighted), &s_arrived, 0);
+    }
+    return;
+  }
+  mbar_wait(&s_arrived, 0);
   const double v = (tl.in && !tl.use_max) ? (double)s_prio[lane] : 0.0;
   tree_update_tiny_finish(a.tree, warp, lane, tl, v);
   if (a.tree_done != nullptr && threadIdx.x == 0) *a.tree_done = 1u;
   B2R_MARK_END(9);
-  if (a.u.mean_weighted_loss != nullptr && warp == 0) {
+  if (want_mean && warp == 0) {
     // fixed order: row k in lane k, butterfly, as the other instances reduce
     float acc = lane < rows ? s_weighted[lane] : 0.f;
     acc = group_sum<32>(acc);

@@ -155,6 +155,55 @@ __device__ __forceinline__ void cluster_sync_relacq() {
                "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
+// ---- hand-over of a few words between the CTAs of a cluster without a fence ------------
+// The receiving CTA owns an mbarrier; a sender stores its word into the receiver's shared
+// memory with st.async, which completes `bytes` on that mbarrier when the word has landed;
+// the receiver waits for the byte count it expects.  No release fence (barrier.cluster
+// .arrive.release is a MEMBAR.ALL.GPU in SASS), only a relaxed cluster barrier at the
+// start of the kernel so that nobody sends before the mbarrier exists.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// word -> the same shared-memory location in CTA `rank` of the cluster, counted on that
+// CTA's mbarrier (both given as THIS CTA's addresses of the corresponding variables)
+__device__ __forceinline__ void st_async_u32(void *local_dst, uint32_t value, uint64_t *local_bar,
+                                             int rank) {
+  uint32_t dst, bar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(smem_u32(local_dst)), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(bar) : "r"(smem_u32(local_bar)), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst),
+               "r"(value), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void pdl_release() {
   asm volatile("griddepcontrol.launch_dependents;");
 }
