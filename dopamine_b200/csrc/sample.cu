@@ -639,16 +639,19 @@ __global__ void __launch_bounds__(256, MIN_CTAS)
 per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
                        const __grid_constant__ WarpScratch ws_in) {
   __shared__ __align__(16) uint8_t s_flag[CLUSTER ? kClusterCap : 16];
+  __shared__ uint32_t s_flag32[CLUSTER ? kClusterCap : 1];  // as the words arrive
   __shared__ int s_cl_spec_idx[kSpecMax], s_cl_spec_valid[kSpecMax];
   __shared__ float s_cl_min[16];
+  __shared__ __align__(8) uint64_t s_arrived;  // CLUSTER: mbarrier of CTA 0
   WarpScratch ws = ws_in;
   if (CLUSTER) {
-    // where everybody writes: CTA 0's arrays (generic addresses into its shared memory)
-    cg::cluster_group cluster = cg::this_cluster();
-    ws.inv_flag = cluster.map_shared_rank(s_flag, 0);
-    ws.spec_idx = cluster.map_shared_rank(s_cl_spec_idx, 0);
-    ws.spec_valid = cluster.map_shared_rank(s_cl_spec_valid, 0);
-    ws.cta_min = cluster.map_shared_rank(s_cl_min, 0);
+    // Everybody's flags, speculative draws and minima go into CTA 0's shared memory as
+    // 32-bit words sent with st.async and counted on CTA 0's mbarrier: CTA 0 waits for the
+    // bytes it expects, nobody fences (common.cuh).  The relaxed barrier only keeps the
+    // senders behind the mbarrier's initialisation; it is waited for where the first
+    // word is sent, a microsecond later.
+    if (blockIdx.x == 0 && threadIdx.x == 0) mbar_init(&s_arrived, 1);
+    cluster_arrive_relaxed();
   }
   __shared__ double s_totals[kMaxShards];
   __shared__ int s_first[2];
@@ -724,6 +727,7 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
       if (hand_over) st_release_u32(a.flags.final_word, row_tag);
       pre_sync_consume(a.pre);
     }
+    if (CLUSTER) cluster_wait();
     return;
   }
 
@@ -849,6 +853,13 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
   // query = random.random() * total), whether or not they will be needed
   float my_min = INFINITY;
   bool first_item = true;
+  if (CLUSTER) {
+    cluster_wait();
+    // one word per stratum, two per speculative draw, one minimum per CTA
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      mbar_arrive_expect(&s_arrived,
+                         4u * (uint32_t)(n_mine + 2 * n_spec + (want_min ? (int)gridDim.x : 0)));
+  }
 #pragma unroll 1
   for (int pos = blockIdx.x * warps + warp; pos < n_mine + n_spec;
        pos += gridDim.x * warps) {
@@ -875,7 +886,8 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
       if (stratum) {
         a.out_idx[pos] = (int32_t)idx;
         if (a.out_slots) a.out_slots[pos] = range_lo + pos;
-        ws.inv_flag[pos] = valid ? 0 : 1;
+        if (CLUSTER) st_async_u32(&s_flag32[pos], valid ? 0u : 1u, &s_arrived, 0);
+        else ws.inv_flag[pos] = valid ? 0 : 1;
         if (valid) {
           float p = INFINITY;
           int length = 0;
@@ -885,6 +897,9 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
           if (hand_over)
             st_release_u64(a.flags.desc + pos, row_descriptor(row_tag, length, idx));
         }
+      } else if (CLUSTER) {
+        st_async_u32(&s_cl_spec_idx[pos - n_mine], (uint32_t)(int32_t)idx, &s_arrived, 0);
+        st_async_u32(&s_cl_spec_valid[pos - n_mine], valid ? 1u : 0u, &s_arrived, 0);
       } else {
         ws.spec_idx[pos - n_mine] = (int32_t)idx;
         ws.spec_valid[pos - n_mine] = valid ? 1 : 0;
@@ -898,17 +913,18 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
     if (threadIdx.x == 0) {
       float m = s_wmin[0];
       for (int w = 1; w < warps; ++w) m = fminf(m, s_wmin[w]);
-      ws.cta_min[blockIdx.x] = m;
+      if (CLUSTER) st_async_u32(&s_cl_min[blockIdx.x], __float_as_uint(m), &s_arrived, 0);
+      else ws.cta_min[blockIdx.x] = m;
     }
   }
 
   // ---- only the last CTA to finish goes on (CLUSTER: CTA 0, after the barrier)
   if (CLUSTER) {
-    // (the closing thread's look at the first half of the loss travels with the barrier)
+    if (blockIdx.x != 0) return;  // (its words are on their way to CTA 0)
+    // (the closing thread's look at the first half of the loss travels with the wait)
     PreSyncPeek peek = {0u, 1u};
-    if (blockIdx.x == 0 && threadIdx.x == 0) peek = pre_sync_peek(a.pre);
-    cluster_sync_relacq();
-    if (blockIdx.x != 0) return;
+    if (threadIdx.x == 0) peek = pre_sync_peek(a.pre);
+    mbar_wait(&s_arrived, 0);
     ws.inv_flag = s_flag;
     ws.spec_idx = s_cl_spec_idx;
     ws.spec_valid = s_cl_spec_valid;
@@ -919,7 +935,7 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
     __shared__ int s_slow;
     if (warp == 0) {
       bool bad = false;
-      for (int p = lane; p < n_mine; p += 32) bad = bad || s_flag[p] != 0;
+      for (int p = lane; p < n_mine; p += 32) bad = bad || s_flag32[p] != 0u;
       const bool slow = __any_sync(full, bad) || n_all > n_mine;
       if (lane == 0) s_slow = slow ? 1 : 0;
     }
@@ -947,6 +963,9 @@ per_sample_warp_kernel(const __grid_constant__ PerSampleArgs a,
       B2R_MARK_ANY(20);
       return;
     }
+    // the slow path below reads the flags as bytes
+    for (int p = threadIdx.x; p < n_mine; p += blockDim.x) s_flag[p] = (uint8_t)s_flag32[p];
+    __syncthreads();
   } else if (gridDim.x > 1) {
     __threadfence();
     __syncthreads();
