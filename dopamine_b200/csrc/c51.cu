@@ -981,7 +981,8 @@ __global__ void __launch_bounds__(kRowWarps * 32) c51_pre_rows_kernel(PreArgs a)
   pre_sync_signal(a.sync);
 }
 
-constexpr int kProjTerms = 6;  // Bellman atoms within dz of an output atom, with slack
+constexpr int kProjTerms = 5;  // Bellman atoms within dz of an output atom, with slack
+                              // (gamma^n >= 2/3: 2 / (gamma^n) + 2 <= 5; wider: the loop)
 
 // One row of the tail by one warp.  bestp_row / sup_row: this warp's shared-memory rows
 // ([kRowAtoms] floats each).  Writes the row's outputs and returns its new priority.
@@ -1007,6 +1008,14 @@ __device__ __forceinline__ float c51_post_row(const LossArgs &a,
   float2 st = make_float2(0.f, 0.f);  // lane = action: (max, log denominator)
   if (have_stats && lane < A)
     st = *reinterpret_cast<const float2 *>(scratch + (size_t)b * kPreRow + kRowAtoms + 2 * lane);
+  // importance weight (RA:279-280): needs the probabilities only — two square roots and
+  // three divisions that are in flight while the second round trip and the projection run
+  float w = 1.f;
+  if (a.u.sampling_probabilities) {
+    const float wmax = __fdiv_rn(1.0f, sqrtf(__fadd_rn(pmin, 1e-10f)));
+    const float raw = __fdiv_rn(1.0f, sqrtf(__fadd_rn(my_prob, 1e-10f)));
+    w = __fdiv_rn(raw, wmax);
+  }
   B2R_MARK(13);
   // an action outside [0, A) (tf.gather_nd raises): evaluated for action 0, zero loss,
   // B2R_ERR_INDEX_RANGE latched
@@ -1157,12 +1166,6 @@ __device__ __forceinline__ float c51_post_row(const LossArgs &a,
       a.err[0] = B2R_ERR_INDEX_RANGE;
       a.err[1] = b;
     }
-  }
-  float w = 1.f;
-  if (a.u.sampling_probabilities) {
-    const float wmax = __fdiv_rn(1.0f, sqrtf(__fadd_rn(pmin, 1e-10f)));
-    const float raw = __fdiv_rn(1.0f, sqrtf(__fadd_rn(my_prob, 1e-10f)));
-    w = __fdiv_rn(raw, wmax);
   }
   prio_out = sqrtf(__fadd_rn(ce, 1e-10f));
   if (lane == 0) {
