@@ -151,8 +151,10 @@ c51_loss_kernel(LossArgs a) {
   __shared__ bool s_last;
   const float *z = a.u.support;
   B2R_MARK(0);
-  pdl_release();
+  // (wait, then release: a dependent that starts early — the tree write-back — may read
+  // what this kernel's own predecessor, the sampler, wrote: tree.cu, kEarly)
   pdl_acquire();
+  pdl_release();
   B2R_MARK(1);
   const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
   if (b >= rows) return;  // (mean_weighted_loss is not supported with batch_count)
@@ -482,8 +484,10 @@ c51_loss_rows_kernel(LossArgs a) {
   const int N = NC ? NC : a.u.num_atoms, A = a.u.num_actions;
   const float *__restrict__ z = a.u.support;
   B2R_MARK(10);
-  pdl_release();
+  // (wait, then release: a dependent that starts early — the tree write-back — may read
+  // what this kernel's own predecessor, the sampler, wrote: tree.cu, kEarly)
   pdl_acquire();
+  pdl_release();
   B2R_MARK(11);
   const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
   if ((int)blockIdx.x * kRowWarps >= rows) return;  // (no mean loss with batch_count)
@@ -1212,8 +1216,10 @@ c51_post_kernel(LossArgs a, const float *__restrict__ scratch, int have_stats) {
   __shared__ bool s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   B2R_MARK(10);
-  pdl_release();
+  // (wait, then release: a dependent that starts early — the tree write-back — may read
+  // what this kernel's own predecessor, the sampler, wrote: tree.cu, kEarly)
   pdl_acquire();
+  pdl_release();
   B2R_MARK(11);
   const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
   if (blockIdx.x == 0 && threadIdx.x == 0) {

@@ -236,6 +236,11 @@ __device__ __forceinline__ long long b2r_now() { return clock64(); }
     if ((int)blockIdx.x == (blk) && threadIdx.x == 0)        \
       g_trace[i] = b2r_now();                                \
   } while (0)
+// mark from thread 0 of the CTA for which `cond` holds
+#define B2R_MARK_IF(i, cond)                                 \
+  do {                                                       \
+    if ((cond) && threadIdx.x == 0) g_trace[i] = b2r_now();  \
+  } while (0)
 // mark from thread 0 of whichever CTA gets there (e.g. the last one to finish)
 #define B2R_MARK_ANY(i)                        \
   do {                                         \
@@ -260,6 +265,9 @@ __device__ __forceinline__ long long b2r_now() { return clock64(); }
   do {                  \
   } while (0)
 #define B2R_MARK_CTA(i, blk) \
+  do {                       \
+  } while (0)
+#define B2R_MARK_IF(i, cond) \
   do {                       \
   } while (0)
 #endif

@@ -245,7 +245,15 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   int64_t expected_rows =
       shard ? (batch + shard->exchange->world - 1) / shard->exchange->world : -1;
   if (expected_rows > rows_cap) expected_rows = rows_cap;
-  const bool presort = tree_can_presort(rows_cap, expected_rows) && !(debug_skip() & 6);
+  // B2R_TREE_EARLY=0 (comparison runs): grouping as a kernel of its own on a forked
+  // stream, joined in front of the write-back proper.  Default: ONE write-back kernel
+  // behind the loss kernel that groups ahead of its wait for it (tree.cu, kEarly).
+  static const bool tree_early = [] {
+    const char *e = std::getenv("B2R_TREE_EARLY");
+    return e == nullptr || std::atoi(e) != 0;
+  }();
+  const bool groupable = tree_can_presort(rows_cap, expected_rows) && !(debug_skip() & 6);
+  const bool presort = groupable && !tree_early;
   if (frames || presort) B2R_CUDA(cudaEventRecord(b->ev_fork, s));
   if (presort) {
     B2R_CUDA(cudaStreamWaitEvent(b->side2, b->ev_fork, 0));
@@ -303,8 +311,8 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   if (!(debug_skip() & 2) && !tail_writeback)
     B2R_TRY((tree_apply<int32_t, float>(b->tree, rows_cap, out->indices, loss.priorities,
                                         nullptr, s, count, expected_rows,
-                                        presort ? 2 : 0, flush_behind ? nullptr : early,
-                                        tree_done)));
+                                        presort ? 2 : (groupable ? 3 : 0),
+                                        flush_behind ? nullptr : early, tree_done)));
   if (flush_behind) B2R_TRY(flush_queue(b, s, false, early));
   if (frames && !deferred) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join, 0));
   if (split_loss && !unjoined && !(deferred && frames))

@@ -34,6 +34,39 @@ B2R_TRACE_DECL
 
 constexpr uint64_t kPadKey = ~0ull;
 
+// (trace builds) a mark by the CTA that took tree level `lv` in tree_update_kernel
+#define B2R_MARK_LVL(i, lv) B2R_MARK_IF(i, level == (lv))
+// (trace builds) per-level times of the write-back: [what][level]
+#ifdef B2R_TRACE
+static __device__ unsigned long long g_trace_count[8];
+#define B2R_TRACE_COUNT(i, cond)                                          \
+  do {                                                                    \
+    if ((cond) && threadIdx.x == 0) atomicAdd(&g_trace_count[i], 1ull);  \
+  } while (0)
+static __device__ long long g_level_trace[4][32];
+static __device__ long long g_phase_trace[2][16];
+// who: 0 = the leaf CTA, 1 = the CTA of level 10, else not traced
+#define B2R_PHASE(who, i)                                                          \
+  do {                                                                             \
+    if (threadIdx.x == 0 && (unsigned)(who) < 2u) g_phase_trace[who][i] = b2r_now(); \
+  } while (0)
+#define B2R_LEVEL_TIME(what, lv)                                      \
+  do {                                                                \
+    if (threadIdx.x == 0) g_level_trace[what][(lv) & 31] = b2r_now(); \
+  } while (0)
+#else
+#define B2R_LEVEL_TIME(what, lv) \
+  do {                           \
+  } while (0)
+#define B2R_TRACE_COUNT(i, cond) \
+  do {                           \
+  } while (0)
+#define B2R_PHASE(who, i) \
+  do {                    \
+  } while (0)
+#endif
+
+
 
 
 // Add-path batches may ask for "whatever max_recorded_priority is when this entry
@@ -119,10 +152,18 @@ struct BigCfg {
       HashSmem h;           // leaf CTA only, before (instead of) the sort
     };
     double vals[kChunk];    // value -> leaf delta (leaf CTA) / deltas in group order
+    uint32_t place[kChunk]; // kEarly: entry k -> its place in the list of duplicate leaves
+    double leafv[kChunk];   // kEarly: entry k -> its leaf's value before the batch
+    double nodev[kChunk];   // kEarly: entry k -> its node's value on the CTA's level
   };
 };
 using BigCfg4096 = BigCfg<1024, 4>;
 using BigCfg1024 = BigCfg<256, 4>;
+// kEarly, up to 1024 entries: one entry per thread.  These kernels are chains of dependent
+// instructions (ncu: 13 cycles per instruction and warp, 2 warps per scheduler with
+// 256 x 4); a thread with one entry runs a quarter of them and the schedulers have eight
+// warps to pick from (B2R_TREE_WIDE=0: 256 x 4).
+using BigCfgWide = BigCfg<1024, 1>;
 static_assert(BigCfg4096::kChunk == kTreeChunk, "chunk size");
 
 // Leaf pass without sorting.  The leaf deltas gate every other level (the root's
@@ -373,6 +414,131 @@ __device__ __forceinline__ bool chains_by_verified_scan(double *__restrict__ lev
   return true;
 }
 
+// ---- the one-way barrier between the leaf CTA and the level CTAs ---------------------
+// A failure is latched by the LAST level to pass (every CTA has read the latch by
+// then: CTAs start whenever an SM has room, and one that started after the latch was
+// set would skip the launch — and the barrier).
+template <typename I, typename V>
+__device__ __forceinline__ void leaf_publishes(const UpdateArgs<I, V> &a, int n, int n_eff,
+                                               int stop_code) {
+  long long *pending = reinterpret_cast<long long *>(a.sync_words + 4);
+  if (threadIdx.x == 0) {
+    pending[0] = n_eff < n ? stop_code : 0;
+    pending[1] = a.k_base + n_eff;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.sync_words + 1), "r"(1u)
+                 : "memory");
+  }
+  B2R_MARK_ANY(10);
+}
+
+// Returns (to every thread) the number of entries the leaf CTA applied.
+template <typename I, typename V>
+__device__ __forceinline__ int levels_wait_for_leaf(const UpdateArgs<I, V> &a) {
+  long long *pending = reinterpret_cast<long long *>(a.sync_words + 4);
+  __shared__ int s_applied;
+  if (threadIdx.x == 0) {
+    unsigned seen = 0;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
+                   : "=r"(seen)
+                   : "l"(a.sync_words + 1)
+                   : "memory");
+    } while (seen == 0 && clock64() - t0 < 4000000000ll);  // (2 s: never hang the GPU)
+    if (seen == 0 && a.status[0] == 0) a.status[0] = B2R_ERR_CUDA;
+    s_applied = seen ? (int)(pending[1] - a.k_base) : 0;
+    // the last level to leave re-arms the flag for the next launch
+    if (atomicInc(a.sync_words + 2, (unsigned)a.depth - 1) == (unsigned)a.depth - 1) {
+      a.sync_words[1] = 0u;
+      if (pending[0] != 0 && a.status[0] == 0) {
+        a.status[0] = pending[0];
+        a.status[1] = pending[1];
+      }
+    }
+  }
+  __syncthreads();
+  return s_applied;
+}
+
+// ---- an internal level behind the barrier: deltas in group order, then one ordered
+// chain per node (sm.g.node / sm.g.elem hold the level's grouping, node_val the stored
+// values of the nodes whose groups start at this thread's positions).
+template <typename C, typename I, typename V>
+__device__ __forceinline__ void internal_level_chains(const UpdateArgs<I, V> &a, int level,
+                                                      int n_eff, typename C::Smem &sm,
+                                                      const double *node_val) {
+  constexpr int kBigItems = C::kItems;
+  const int64_t base = ((int64_t)1) << level;
+  double *vals = sm.vals;
+  double *sorted_delta = vals;
+  {
+    double d[kBigItems];
+#pragma unroll
+    for (int j = 0; j < kBigItems; ++j) {
+      const int p = threadIdx.x + j * C::kThreads;
+      d[j] = p < n_eff ? __ldcg(a.delta + sm.g.elem[p]) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < kBigItems; ++j) {
+      const int p = threadIdx.x + j * C::kThreads;
+      if (p < n_eff) sorted_delta[p] = d[j];
+    }
+  }
+  __syncthreads();
+  B2R_MARK_LVL(3, 0);
+  B2R_MARK_LVL(20, 1);
+  B2R_MARK_LVL(26, a.depth - 1);
+  // long chains (the upper levels): verified scan; it declines when adds round
+  if (a.scan_min_chain > 0 && (n_eff >> level) >= a.scan_min_chain &&
+      chains_by_verified_scan<C>(a.heap + base, node_val, sm.g.node, sorted_delta,
+                                 n_eff)) {
+    B2R_MARK_LVL(4, 0);
+    B2R_MARK_LVL(21, 1);
+    B2R_MARK_LVL(27, a.depth - 1);
+    B2R_MARK_END(15);
+    return;
+  }
+  // serial chains: the thread that owns a group's first position walks the group
+  int seg_end[kBigItems];
+#pragma unroll
+  for (int j = 0; j < kBigItems; ++j) {
+    const int p = threadIdx.x * kBigItems + j;
+    seg_end[j] = p;  // (empty: not a group start)
+    if (p < n_eff) {
+      const uint32_t node = sm.g.node[p];
+      if (p == 0 || sm.g.node[p - 1] != node) {
+        // first position whose node is larger: the neighbour, else a binary search
+        int lo = p + 1, hi = n_eff;
+        if (lo < hi && sm.g.node[lo] > node) hi = lo;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (sm.g.node[mid] > node) hi = mid; else lo = mid + 1;
+        }
+        seg_end[j] = lo;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kBigItems; ++j) {
+    const int p = threadIdx.x * kBigItems + j;
+    if (seg_end[j] > p) {
+      double acc = node_val[j];
+#pragma unroll 8
+      for (int q = p; q < seg_end[j]; ++q) acc = __dadd_rn(acc, sorted_delta[q]);
+      a.heap[base + sm.g.node[p]] = acc;
+    }
+  }
+  B2R_MARK_LVL(4, 0);
+  B2R_MARK_LVL(21, 1);
+  B2R_MARK_LVL(27, a.depth - 1);
+  B2R_MARK_END(15);
+}
+
+
 template <typename I, typename V, typename C>
 __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, V> a) {
   constexpr int kBigItems = C::kItems;
@@ -397,9 +563,9 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
   __syncthreads();
   const int level = s_role == 0 ? a.depth : s_role - 1;
   const bool is_leaf = level == a.depth;
-  B2R_MARK_CTA(0, 0);
-  B2R_MARK_CTA(16, a.depth);
-  B2R_MARK_CTA(22, a.depth - 1);
+  B2R_MARK_LVL(0, 0);
+  B2R_MARK_LVL(16, a.depth);
+  B2R_MARK_LVL(22, a.depth - 1);
   int n = a.n;
   if (a.n_dev) {
     const int64_t left = (int64_t)*a.n_dev - a.k_base;
@@ -469,9 +635,9 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
                                       : B2R_ERR_INDEX_RANGE;
 
   // 2. leaf CTA: the sort-free pass when duplicates are few (the usual case)
-  B2R_MARK_CTA(17, a.depth);
-  B2R_MARK_CTA(23, a.depth - 1);
-  B2R_MARK_CTA(29, 0);
+  B2R_MARK_LVL(17, a.depth);
+  B2R_MARK_LVL(23, a.depth - 1);
+  B2R_MARK_LVL(29, 0);
   bool leaf_done = false;
   // kApply: the presorted lists hold all n entries; they serve iff all n are applied
   const bool presorted = a.phase == kApply && n_eff == n;
@@ -515,7 +681,7 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
     }
   }
   __syncthreads();
-  B2R_MARK_CTA(18, a.depth);
+  B2R_MARK_LVL(18, a.depth);
 
   if (is_leaf) {
     if (!leaf_done) {
@@ -564,52 +730,19 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
     }
   }
 
-  B2R_MARK_CTA(1, 0);
-  B2R_MARK_CTA(19, a.depth);
-  B2R_MARK_CTA(24, a.depth - 1);
+  B2R_MARK_LVL(1, 0);
+  B2R_MARK_LVL(19, a.depth);
+  B2R_MARK_LVL(24, a.depth - 1);
   // ---- one-way barrier: the leaf CTA's deltas (and leaf writes) are published
-  // A failure is latched by the LAST level to pass (every CTA has read the latch by
-  // then: CTAs start whenever an SM has room, and one that started after the latch was
-  // set would skip the launch — and the barrier).
-  long long *pending = reinterpret_cast<long long *>(a.sync_words + 4);
   if (is_leaf) {
-    if (threadIdx.x == 0) {
-      pending[0] = n_eff < n ? s_stop_code : 0;
-      pending[1] = a.k_base + n_eff;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.sync_words + 1), "r"(1u)
-                   : "memory");
-    }
-    B2R_MARK_ANY(10);
+    leaf_publishes(a, n, n_eff, s_stop_code);
   } else {
-    if (threadIdx.x == 0) {
-      unsigned seen = 0;
-      const long long t0 = clock64();
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
-                     : "=r"(seen)
-                     : "l"(a.sync_words + 1)
-                     : "memory");
-      } while (seen == 0 && clock64() - t0 < 4000000000ll);  // (2 s: never hang the GPU)
-      if (seen == 0 && a.status[0] == 0) a.status[0] = B2R_ERR_CUDA;
-      // the last level to leave re-arms the flag for the next launch
-      if (atomicInc(a.sync_words + 2, (unsigned)a.depth - 1) == (unsigned)a.depth - 1) {
-        a.sync_words[1] = 0u;
-        if (pending[0] != 0 && a.status[0] == 0) {
-          a.status[0] = pending[0];
-          a.status[1] = pending[1];
-        }
-      }
-    }
-    __syncthreads();
+    levels_wait_for_leaf(a);
     B2R_MARK_END(11);
   }
-  B2R_MARK_CTA(2, 0);
-  B2R_MARK_CTA(25, a.depth - 1);
-  B2R_MARK_CTA(28, a.depth);
+  B2R_MARK_LVL(2, 0);
+  B2R_MARK_LVL(25, a.depth - 1);
+  B2R_MARK_LVL(28, a.depth);
 
   if (is_leaf) {
     if (threadIdx.x == 0) {
@@ -627,68 +760,953 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
   }
 
   // 3. internal level: deltas in group order, then one ordered chain per node.
-  double *sorted_delta = vals;
-  {
-    double d[kBigItems];
+  internal_level_chains<C>(a, level, n_eff, sm, node_val);
+}
+
+// ---- the same update with everything that needs only the INDICES done ahead of the
+// values, and no hand-over between the CTAs behind them (kEarly).
+//
+// In the fused step the indices are final when the sampler ends and the values are what
+// the loss kernel between the sampler and this kernel produces; the loss kernel lets its
+// dependents start once it has seen the sampler's end (griddepcontrol: wait, then
+// launch_dependents), so this kernel runs BESIDE it.  Ahead of its own
+// griddepcontrol.wait:
+//   * every level CTA groups the batch by node (the radix sort that used to sit between
+//     the loss and the write-back, or in a side stream with a second kernel and a join),
+//     finds the ends of its groups, and fetches the nodes it will change AND the leaves
+//     its entries point at;
+//   * the leaf CTA builds its hash set, ranks the entries that share a leaf with another
+//     entry (by leaf, then batch position) and hands that list to the level CTAs through
+//     HBM and a flag — a hand-over nobody is waiting for yet.
+// Behind the wait a level CTA needs nothing from any other CTA: an entry's delta is
+// value - leaf (sum_tree.py:196-202) with the leaf it fetched itself; the few entries that
+// share leaves are chains  delta = value - leaf; leaf += delta  that every CTA walks for
+// itself from the leaf CTA's list.  One round trip for the values, the deltas, the ordered
+// chains (or the verified scan), the stores.  (The plain kernel's leaf CTA publishes the
+// deltas through HBM behind a fence and a flag: 4-5 us of this kernel's 11 at 1024.)
+// When the list does not serve — more duplicates than it holds, or an entry the
+// reference's loop would have raised on (negative priority, index out of range), so that
+// only a prefix is applied — every CTA sees that for itself and the kernel goes on as the
+// plain one does: leaf pass over the prefix, deltas through HBM, flag, regrouped levels.
+// Only for callers that can promise the first sentence (phase == kEarly, train_step).
+template <typename C>
+struct LeafDupSmem {
+  uint32_t d_idx[C::kMaxDup], d_k[C::kMaxDup], ds_idx[C::kMaxDup], ds_k[C::kMaxDup];
+  int ndup;
+};
+
+// What the leaf CTA leaves in HBM for the level CTAs (words of UpdateArgs::sorted).
+template <typename C>
+struct DupInfo {
+  static constexpr uint32_t kOverflow = 0xffffffffu;
+  static constexpr int kCount = 0;                     // [1]: entries in the list / kOverflow
+  static constexpr int kIdx = 16;                      // [kMaxDup]: leaf, in chain order
+  static constexpr int kK = kIdx + C::kMaxDup;         // [kMaxDup]: batch position
+  static constexpr int kOf = kK + C::kMaxDup;          // [chunk]: k -> place in the list / -1
+  static constexpr int kLeaf = kOf + C::kChunk;        // [chunk] doubles: k -> its leaf's value
+  static constexpr int kWords = kLeaf + 2 * C::kChunk;
+  static_assert(kLeaf % 2 == 0, "doubles");
+};
+
+template <typename C>
+struct LeafPrep {
+  uint32_t idx[C::kItems];  // leaf index / 0xffffffff (pad, out of range)
+  uint32_t k[C::kItems];    // batch position
+  double leaf[C::kItems];   // the leaf's value
+  bool single[C::kItems];   // no other entry of the batch has this leaf
+};
+
+// ---- a batch that is ALREADY grouped, but for a few entries.  The fused step's batch
+// is: stratified queries grow with the stratum (sum_tree.py:162-166), the descent is
+// monotone in the query, so row k's leaf — and with it its node on every level — never
+// decreases with k; the exceptions are the rows whose pick was invalid and was drawn
+// again (prioritized_replay_buffer.py:155-170), ~0.3 % of them.  Grouping by (node, k)
+// is then the identity with a handful of entries moved, and costs two block scans and a
+// few binary searches instead of a radix sort (5 passes at the deepest levels: what made
+// the index-only half of this kernel longer than the loss kernel it runs beside).
+//   * suspects: every entry that is larger than its right neighbour or smaller than its
+//     left one (both ends of every descent: the culprit and, possibly, an innocent);
+//   * the rest must be non-decreasing — checked against its running maximum, else (or
+//     with more than kMaxMoved suspects) the caller sorts;
+//   * a suspect's place: entries of the rest that sort before (key, k) — two binary
+//     searches in the rest with the suspects' slots filled by the running maximum — plus
+//     the suspects that do; an entry of the rest moves by the suspects that cross it.
+constexpr int kMaxMoved = 64;
+
+struct ScanSmem {
+  uint32_t wmax[32];
+  int wsum[32];
+};
+
+// Exclusive block scan of (max, sum) over thread totals; *total = the sum of all.
+template <int T>
+__device__ __forceinline__ void block_scan_max_sum(uint32_t tm, int ts, ScanSmem &ss,
+                                                   uint32_t *pm, int *ps, int *total) {
+  constexpr int WARPS = T / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t im = tm;
+  int is = ts;
 #pragma unroll
-    for (int j = 0; j < kBigItems; ++j) {
-      const int p = threadIdx.x + j * C::kThreads;
-      d[j] = p < n_eff ? __ldcg(a.delta + sm.g.elem[p]) : 0.0;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t um = __shfl_up_sync(0xffffffffu, im, o);
+    const int us = __shfl_up_sync(0xffffffffu, is, o);
+    if (lane >= o) {
+      im = max(im, um);
+      is += us;
     }
+  }
+  uint32_t em = __shfl_up_sync(0xffffffffu, im, 1);
+  int es = __shfl_up_sync(0xffffffffu, is, 1);
+  if (lane == 0) {
+    em = 0u;
+    es = 0;
+  }
+  __syncthreads();  // (the arrays may still be read from an earlier scan)
+  if (lane == 31) {
+    ss.wmax[warp] = im;
+    ss.wsum[warp] = is;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t wm = lane < WARPS ? ss.wmax[lane] : 0u;
+    int ws = lane < WARPS ? ss.wsum[lane] : 0;
 #pragma unroll
-    for (int j = 0; j < kBigItems; ++j) {
-      const int p = threadIdx.x + j * C::kThreads;
-      if (p < n_eff) sorted_delta[p] = d[j];
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t um = __shfl_up_sync(0xffffffffu, wm, o);
+      const int us = __shfl_up_sync(0xffffffffu, ws, o);
+      if (lane >= o) {
+        wm = max(wm, um);
+        ws += us;
+      }
+    }
+    ss.wmax[lane] = wm;
+    ss.wsum[lane] = ws;
+  }
+  __syncthreads();
+  *pm = warp > 0 ? max(ss.wmax[warp - 1], em) : em;
+  *ps = warp > 0 ? ss.wsum[warp - 1] + es : es;
+  *total = ss.wsum[31];
+}
+
+// What a thread keeps of the analysis for its entries kItems * t + j.
+template <typename C>
+struct NearlySorted {
+  bool moved[C::kItems];
+  int before_moved[C::kItems];  // suspects in front of the entry
+  int n_moved;
+};
+
+// key[j]: the key of entry kItems * t + j (pads: all ones, behind every real entry).
+// True: the batch is of that kind; `scratch` (at least kChunk + 2 * kMaxMoved words of
+// shared memory) then holds the rest's keys with the suspects' slots filled, and the
+// suspects.
+template <typename C>
+__device__ __forceinline__ bool nearly_sorted_analyse(const uint32_t *key, uint32_t *scratch,
+                                                      ScanSmem &ss, NearlySorted<C> *ns) {
+  constexpr int kItems = C::kItems, T = C::kThreads, kChunk = C::kChunk;
+  uint32_t *c = scratch, *moved_k = scratch + kChunk, *moved_key = moved_k + kMaxMoved;
+  const int k0 = threadIdx.x * kItems;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) c[k0 + j] = key[j];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int k = k0 + j;
+    const uint32_t left = j > 0 ? key[j - 1] : (k > 0 ? c[k - 1] : 0u);
+    const uint32_t right = j + 1 < kItems ? key[j + 1] : (k + 1 < kChunk ? c[k + 1] : 0xffffffffu);
+    ns->moved[j] = key[j] < left || key[j] > right;
+  }
+  // running maximum of the rest, running count of the suspects
+  uint32_t before_max[kItems];
+  uint32_t tm = 0u;
+  int ts = 0;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    before_max[j] = tm;
+    ns->before_moved[j] = ts;
+    if (ns->moved[j]) ++ts; else tm = max(tm, key[j]);
+  }
+  uint32_t pm;
+  int ps;
+  block_scan_max_sum<T>(tm, ts, ss, &pm, &ps, &ns->n_moved);  // (its barriers: c[] is read)
+  bool unsorted = false;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    before_max[j] = max(before_max[j], pm);
+    ns->before_moved[j] += ps;
+    unsorted |= !ns->moved[j] && key[j] < before_max[j];
+  }
+  if (__syncthreads_or(unsorted || ns->n_moved > kMaxMoved)) return false;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    if (ns->moved[j]) {
+      c[k0 + j] = before_max[j];
+      moved_k[ns->before_moved[j]] = (uint32_t)(k0 + j);
+      moved_key[ns->before_moved[j]] = key[j];
     }
   }
   __syncthreads();
-  B2R_MARK_CTA(3, 0);
-  B2R_MARK_CTA(20, 1);
-  B2R_MARK_CTA(26, a.depth - 1);
-  // long chains (the upper levels): verified scan; it declines when adds round
-  if (a.scan_min_chain > 0 && (n_eff >> level) >= a.scan_min_chain &&
-      chains_by_verified_scan<C>(a.heap + base, node_val, sm.g.node, sorted_delta,
-                                 n_eff)) {
-    B2R_MARK_CTA(4, 0);
-    B2R_MARK_CTA(21, 1);
-    B2R_MARK_CTA(27, a.depth - 1);
-    B2R_MARK_END(15);
-    return;
-  }
-  // serial chains: the thread that owns a group's first position walks the group
-  int seg_end[kBigItems];
+  return true;
+}
+
+// Where the entries go when the batch is ordered by (key >> shift, k): the rest is in
+// that order for every shift, and any superset of a level's suspects will do for it.
+// A suspect's INSERTION POINT is the first slot of the batch that sorts behind it (slots
+// of the rest carry their keys, the suspects' slots the running maximum: one monotone
+// predicate, one binary search); an entry of the rest at slot k has exactly the suspects
+// with an insertion point <= k in front of it, and a suspect the rest in front of its
+// insertion point plus the suspects that sort before it.
+// Two shifts at once (the leaves and the CTA's own level; the searches interleave):
+// first nearly_sorted_insertions by every thread (a block barrier inside), then
+// nearly_sorted_positions for either shift.
+template <typename C>
+__device__ __forceinline__ void nearly_sorted_insertions(const uint32_t *key, int shift_a,
+                                                         int shift_b,
+                                                         const NearlySorted<C> &ns,
+                                                         uint32_t *scratch) {
+  constexpr int kItems = C::kItems, kChunk = C::kChunk;
+  const uint32_t *c = scratch;
+  uint32_t *ip_a = scratch + kChunk + 2 * kMaxMoved, *ip_b = ip_a + kMaxMoved;
+  const int k0 = threadIdx.x * kItems;
 #pragma unroll
-  for (int j = 0; j < kBigItems; ++j) {
-    const int p = threadIdx.x * kBigItems + j;
-    seg_end[j] = p;  // (empty: not a group start)
-    if (p < n_eff) {
-      const uint32_t node = sm.g.node[p];
-      if (p == 0 || sm.g.node[p - 1] != node) {
-        // first position whose node is larger: the neighbour, else a binary search
-        int lo = p + 1, hi = n_eff;
-        if (lo < hi && sm.g.node[lo] > node) hi = lo;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (sm.g.node[mid] > node) hi = mid; else lo = mid + 1;
-        }
-        seg_end[j] = lo;
+  for (int j = 0; j < kItems; ++j) {
+    if (!ns.moved[j]) continue;
+    const int k = k0 + j;
+    const uint32_t xa = key[j] >> shift_a, xb = key[j] >> shift_b;
+    int lo_a = 0, hi_a = kChunk, lo_b = 0, hi_b = kChunk;
+    while (lo_a < hi_a || lo_b < hi_b) {  // (same number of steps: same range)
+      const int mid_a = (lo_a + hi_a) >> 1, mid_b = (lo_b + hi_b) >> 1;
+      const uint32_t ca = c[mid_a < kChunk ? mid_a : kChunk - 1] >> shift_a;
+      const uint32_t cb = c[mid_b < kChunk ? mid_b : kChunk - 1] >> shift_b;
+      if (lo_a < hi_a) {
+        if (ca > xa || (ca == xa && mid_a > k)) hi_a = mid_a; else lo_a = mid_a + 1;
+      }
+      if (lo_b < hi_b) {
+        if (cb > xb || (cb == xb && mid_b > k)) hi_b = mid_b; else lo_b = mid_b + 1;
       }
     }
+    ip_a[ns.before_moved[j]] = (uint32_t)lo_a;
+    ip_b[ns.before_moved[j]] = (uint32_t)lo_b;
   }
+  __syncthreads();
+}
+
+// pos[j]: where entry kItems * t + j goes (which = 0: shift_a's order, 1: shift_b's).
+template <typename C>
+__device__ __forceinline__ void nearly_sorted_positions(const uint32_t *key, int shift,
+                                                        int which,
+                                                        const NearlySorted<C> &ns,
+                                                        const uint32_t *scratch, int *pos) {
+  constexpr int kItems = C::kItems, kChunk = C::kChunk;
+  const uint32_t *moved_k = scratch + kChunk, *moved_key = moved_k + kMaxMoved;
+  const uint32_t *ip = scratch + kChunk + 2 * kMaxMoved + which * kMaxMoved;
+  const int k0 = threadIdx.x * kItems;
+  const int n_moved = ns.n_moved;
+  bool any_moved = false;
 #pragma unroll
-  for (int j = 0; j < kBigItems; ++j) {
-    const int p = threadIdx.x * kBigItems + j;
-    if (seg_end[j] > p) {
-      double acc = node_val[j];
-#pragma unroll 8
-      for (int q = p; q < seg_end[j]; ++q) acc = __dadd_rn(acc, sorted_delta[q]);
-      a.heap[base + sm.g.node[p]] = acc;
+  for (int j = 0; j < kItems; ++j) {
+    pos[j] = k0 + j - ns.before_moved[j];
+    any_moved |= ns.moved[j];
+  }
+  for (int o = 0; o < n_moved; ++o) {  // (one load per suspect for the thread's entries)
+    const int at = (int)ip[o];
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) pos[j] += at <= k0 + j ? 1 : 0;
+  }
+  if (any_moved) {
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      if (!ns.moved[j]) continue;
+      const uint32_t k = (uint32_t)(k0 + j), mine = key[j] >> shift;
+      const int at = (int)ip[ns.before_moved[j]];
+      int p = at;
+      for (int o = 0; o < n_moved; ++o) {
+        const uint32_t ok = moved_key[o] >> shift, kk = moved_k[o];
+        p -= (int)kk < at ? 1 : 0;  // (a suspect's slot in front of the insertion point)
+        p += (ok < mine || (ok == mine && kk < k)) ? 1 : 0;
+      }
+      pos[j] = p;
     }
   }
-  B2R_MARK_CTA(4, 0);
-  B2R_MARK_CTA(21, 1);
-  B2R_MARK_CTA(27, a.depth - 1);
+}
+
+// Leaves the entries in sm.g.node / sm.g.elem at the given positions (a block barrier
+// behind the stores).
+template <typename C>
+__device__ __forceinline__ void nearly_sorted_store(const uint32_t *key, int shift,
+                                                    const int *pos, typename C::Smem &sm) {
+  constexpr int kItems = C::kItems;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    sm.g.node[pos[j]] = key[j] >> shift;
+    sm.g.elem[pos[j]] = (uint32_t)(threadIdx.x * kItems + j);
+  }
+  __syncthreads();
+}
+
+template <typename C>
+__device__ __forceinline__ bool group_nearly_sorted(const uint32_t *key,
+                                                    typename C::Smem &sm, uint32_t *scratch,
+                                                    ScanSmem &ss) {
+  NearlySorted<C> ns;
+  if (!nearly_sorted_analyse<C>(key, scratch, ss, &ns)) return false;
+  int pos[C::kItems];
+  nearly_sorted_insertions<C>(key, 0, 0, ns, scratch);
+  nearly_sorted_positions<C>(key, 0, 0, ns, scratch, pos);
+  nearly_sorted_store<C>(key, 0, pos, sm);
+  return true;
+}
+
+// The leaf CTA ahead of the values (first half of leaf_deltas_hashed): needs a.indices
+// and the tree only.  Entries whose index is out of range lower *s_stop (initialised by
+// the caller) and stay out of the set.  Leaves dup.ds_idx / ds_k / ndup in shared memory
+// and the same, plus every entry's place in the list, in `info`.  False: more duplicates
+// than the list holds (info says so too).
+template <typename C, typename I, typename V>
+__device__ __forceinline__ bool leaf_hashed_prepare(const UpdateArgs<I, V> &a, int n,
+                                                    typename C::HashSmem &h,
+                                                    LeafDupSmem<C> &dup, LeafPrep<C> *r,
+                                                    int *s_stop, uint32_t *info) {
+  constexpr int kItems = C::kItems, T = C::kThreads;
+  constexpr int kHashSlots = C::kHashSlots, kHashBits = C::kHashBits;
+  constexpr int kMaxDup = C::kMaxDup;
+  constexpr uint32_t kEmpty = 0xffffffffu;
+  using Info = DupInfo<C>;
+  uint32_t slot_of[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int k = threadIdx.x + j * T;
+    r->idx[j] = kEmpty;
+    r->k[j] = (uint32_t)k;
+    if (k < n) {
+      const int64_t ix = (int64_t)a.indices[k];
+      if (ix >= 0 && ix < a.leaves) r->idx[j] = (uint32_t)ix;
+      else atomicMin(s_stop, k);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {  // (first used behind the values)
+    r->leaf[j] = 0.0;
+    slot_of[j] = 0;
+    if (r->idx[j] != kEmpty) r->leaf[j] = a.heap[a.leaves + r->idx[j]];
+  }
+  for (int i = threadIdx.x; i < kHashSlots; i += blockDim.x) {
+    h.key[i] = kEmpty;
+    h.count[i] = 0;
+  }
+  if (threadIdx.x == 0) dup.ndup = 0;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    if (r->idx[j] != kEmpty) {
+      const uint32_t idx = r->idx[j];
+      uint32_t slot = (idx * 2654435761u) >> (32 - kHashBits);
+      while (true) {
+        const uint32_t old = atomicCAS(&h.key[slot], kEmpty, idx);
+        if (old == kEmpty || old == idx) break;
+        slot = (slot + 1) & (kHashSlots - 1);
+      }
+      atomicAdd(&h.count[slot], 1u);
+      slot_of[j] = slot;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int k = threadIdx.x + j * T;
+    r->single[j] = r->idx[j] != kEmpty && h.count[slot_of[j]] == 1;
+    if (r->idx[j] != kEmpty && h.count[slot_of[j]] > 1) {
+      const int pos = atomicAdd(&dup.ndup, 1);
+      if (pos < kMaxDup) {
+        dup.d_idx[pos] = r->idx[j];
+        dup.d_k[pos] = (uint32_t)k;
+      }
+    } else if (k < n) {
+      info[Info::kOf + k] = 0xffffffffu;  // its leaf is its alone
+    }
+    // (the level CTAs take the leaves from here, not from the tree: this CTA may be
+    // writing the new ones while a level CTA that got an SM late is still fetching)
+    if (k < n) reinterpret_cast<double *>(info + Info::kLeaf)[k] = r->leaf[j];
+  }
+  __syncthreads();
+  const int ndup = dup.ndup;
+  if (ndup > kMaxDup) {
+    if (threadIdx.x == 0) info[Info::kCount] = Info::kOverflow;
+    return false;
+  }
+  // duplicates: order by (leaf, batch position), one chain per leaf
+  if ((int)threadIdx.x < ndup) {
+    const uint64_t me = ((uint64_t)dup.d_idx[threadIdx.x] << 32) | dup.d_k[threadIdx.x];
+    int rank = 0;
+    for (int j = 0; j < ndup; ++j)
+      rank += ((((uint64_t)dup.d_idx[j] << 32) | dup.d_k[j]) < me) ? 1 : 0;
+    dup.ds_idx[rank] = dup.d_idx[threadIdx.x];
+    dup.ds_k[rank] = dup.d_k[threadIdx.x];
+    info[Info::kIdx + rank] = dup.d_idx[threadIdx.x];
+    info[Info::kK + rank] = dup.d_k[threadIdx.x];
+    info[Info::kOf + dup.d_k[threadIdx.x]] = (uint32_t)rank;
+  }
+  if (threadIdx.x == 0) info[Info::kCount] = (uint32_t)ndup;
+  __syncthreads();
+  return true;
+}
+
+// What a level CTA holds for the grouped positions kItems * t .. kItems * t + kItems - 1
+// of thread t (sm.g.node / sm.g.elem hold the grouping itself).
+template <typename C>
+struct LevelPrep {
+  double node_val[C::kItems];  // group starts here: the node's stored value
+  double leaf[C::kItems];      // the leaf the entry points at (from the leaf CTA's list)
+  uint32_t k[C::kItems];       // the entry's batch position
+  uint32_t dup_of[C::kItems];  // its place in the leaf CTA's list / 0xffffffff
+};
+
+// What LevelPrep holds, but for leaf and dup_of, from the grouping in sm.g (behind a block
+// barrier).
+template <typename C, typename I, typename V>
+__device__ __forceinline__ void level_prefetch(const UpdateArgs<I, V> &a, int level,
+                                               int count, typename C::Smem &sm,
+                                               LevelPrep<C> *r, bool staged = false) {
+  constexpr int kItems = C::kItems;
+  const int64_t base = ((int64_t)1) << level;
+  uint32_t key[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    key[j] = sm.g.node[threadIdx.x * kItems + j];
+    r->k[j] = sm.g.elem[threadIdx.x * kItems + j];
+  }
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int p = threadIdx.x * kItems + j;
+    r->node_val[j] = 0.0;
+    r->leaf[j] = 0.0;
+    r->dup_of[j] = 0xffffffffu;
+    if (p >= count || (int64_t)key[j] >= base) continue;
+    // (staged: every entry fetched its node's value when its index arrived, sm.nodev)
+    if (p == 0 || sm.g.node[p - 1] != key[j])
+      r->node_val[j] = staged ? sm.nodev[r->k[j]] : a.heap[base + key[j]];
+  }
+}
+
+// Groups the first `count` entries by their node on `level` into sm.g (as a batch that is
+// grouped already but for a few entries, else by a stable radix sort on the level's bits;
+// entries that are pads or out of range sort as all-ones keys and lower *s_stop) and
+// fetches what LevelPrep holds, but for leaf and dup_of.  sm.vals is scratch here.
+template <typename C, typename I, typename V>
+__device__ __forceinline__ void group_level(const UpdateArgs<I, V> &a, int level, int count,
+                                            typename C::Smem &sm, LevelPrep<C> *r,
+                                            int *s_stop, ScanSmem &ss) {
+  constexpr int kItems = C::kItems;
+  using Sort = typename C::Sort;
+  const int shift = a.depth - level;
+  uint32_t key[kItems], val[kItems];
+  int64_t ix[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int k = threadIdx.x * kItems + j;
+    ix[j] = k < count ? (int64_t)a.indices[k] : 0;
+  }
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int k = threadIdx.x * kItems + j;
+    key[j] = 0xffffffffu;
+    if (k < count) {
+      if (ix[j] >= 0 && ix[j] < a.leaves) key[j] = (uint32_t)(ix[j] >> shift);
+      else atomicMin(s_stop, k);
+    }
+    val[j] = (uint32_t)k;
+  }
+  if (level != 0 &&
+      !group_nearly_sorted<C>(key, sm, reinterpret_cast<uint32_t *>(sm.vals), ss)) {
+    Sort(sm.g.sort).Sort(key, val, 0, level);
+    __syncthreads();  // (the sort's storage overlaps nothing below, but keep the order)
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      sm.g.node[threadIdx.x * kItems + j] = key[j];
+      sm.g.elem[threadIdx.x * kItems + j] = val[j];
+    }
+  } else if (level == 0) {
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      sm.g.node[threadIdx.x * kItems + j] = key[j];
+      sm.g.elem[threadIdx.x * kItems + j] = val[j];
+    }
+  }
+  __syncthreads();
+  level_prefetch<C>(a, level, count, sm, r);
+}
+
+// EVERY CTA ahead of the values when the batch is grouped by leaf already, but for a few
+// entries (nearly_sorted_analyse): entries that share a leaf are neighbours then, and the
+// list of them is what is left of the grouped batch without the leaves that occur once —
+// no hash set, and nothing to hand from the leaf CTA to the others: each CTA makes the
+// list for itself.  idx[j]: leaf of entry kItems * t + j / all ones (pads, out of range).
+// 1: dup.ds_idx / ds_k / ndup and sm.place hold the list, own_pos the entries' places in
+// the order of the CTA's own level (keys >> own_shift; for nearly_sorted_store); 0: the
+// batch is not of that kind; -1: more duplicates than the list holds.  (sm.g is
+// overwritten.)
+template <typename C, typename I, typename V>
+__device__ __forceinline__ int leaf_list_from_sorted(const UpdateArgs<I, V> &a, int n,
+                                                     typename C::Smem &sm,
+                                                     LeafDupSmem<C> &dup,
+                                                     const uint32_t *idx,
+                                                     NearlySorted<C> *ns, uint32_t *scratch,
+                                                     ScanSmem &ss, int own_shift,
+                                                     int *own_pos, int who = -1) {
+  constexpr int kItems = C::kItems, T = C::kThreads;
+  constexpr int kMaxDup = C::kMaxDup;
+  constexpr uint32_t kEmpty = 0xffffffffu;
+  (void)who;
+  B2R_PHASE(who, 1);
+  if (!nearly_sorted_analyse<C>(idx, scratch, ss, ns)) return 0;
+  B2R_PHASE(who, 2);
+  // (own_pos: the entries' places on the CTA's own level, for nearly_sorted_store later)
+  int pos[kItems];
+  nearly_sorted_insertions<C>(idx, 0, own_shift, *ns, scratch);
+  nearly_sorted_positions<C>(idx, 0, 0, *ns, scratch, pos);
+  nearly_sorted_positions<C>(idx, own_shift, 1, *ns, scratch, own_pos);
+  nearly_sorted_store<C>(idx, 0, pos, sm);
+  B2R_PHASE(who, 3);
+  // entries that share their leaf with a neighbour, compacted in (leaf, k) order
+  bool shares[kItems];
+  int mine = 0;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int p = threadIdx.x * kItems + j;
+    const uint32_t node = sm.g.node[p];
+    shares[j] = p < n && node != kEmpty &&
+                ((p > 0 && sm.g.node[p - 1] == node) || (p + 1 < n && sm.g.node[p + 1] == node));
+    mine += shares[j] ? 1 : 0;
+  }
+  uint32_t unused;
+  int at, ndup;
+  block_scan_max_sum<T>(0u, mine, ss, &unused, &at, &ndup);
+  B2R_PHASE(who, 4);
+  if (ndup > kMaxDup) return -1;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int p = threadIdx.x * kItems + j;
+    if (p >= n) continue;
+    const uint32_t k = sm.g.elem[p];
+    if (shares[j]) {
+      dup.ds_idx[at] = sm.g.node[p];
+      dup.ds_k[at] = k;
+      sm.place[k] = (uint32_t)at;
+      ++at;
+    } else {
+      sm.place[k] = kEmpty;
+    }
+  }
+  if (threadIdx.x == 0) dup.ndup = ndup;
+  __syncthreads();
+  return 1;
+}
+
+// The ordered chains of one level over deltas that are in shared memory already
+// (sm.vals, in group order, behind a block barrier).
+template <typename C, typename I, typename V>
+__device__ __forceinline__ void level_chains_grouped(const UpdateArgs<I, V> &a, int level,
+                                                     int n, typename C::Smem &sm,
+                                                     const LevelPrep<C> &r) {
+  constexpr int kItems = C::kItems;
+  const int64_t base = ((int64_t)1) << level;
+  const double *sorted_delta = sm.vals;
+  // long chains (the upper levels): verified scan; it declines when adds round
+  if (a.scan_min_chain > 0 && (n >> level) >= a.scan_min_chain &&
+      chains_by_verified_scan<C>(a.heap + base, r.node_val, sm.g.node, sorted_delta, n))
+    return;
+  // serial chains: the thread that owns a group's first position walks the group
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int p = threadIdx.x * kItems + j;
+    if (p >= n) continue;
+    const uint32_t node = sm.g.node[p];
+    if ((int64_t)node >= base || (p > 0 && sm.g.node[p - 1] == node)) continue;
+    double acc = r.node_val[j];
+    for (int q = p; q < n && sm.g.node[q] == node; ++q) acc = __dadd_rn(acc, sorted_delta[q]);
+    a.heap[base + node] = acc;
+  }
+}
+
+template <typename I, typename V, typename C>
+__global__ void __launch_bounds__(C::kThreads) tree_update_early_kernel(UpdateArgs<I, V> a) {
+  constexpr int kItems = C::kItems, T = C::kThreads;
+  constexpr uint32_t kEmpty = 0xffffffffu;
+  using Sort = typename C::Sort;
+  using Info = DupInfo<C>;
+  static_assert(Info::kWords <= DupInfo<BigCfg4096>::kWords, "scratch (ensure_sorted)");
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  typename C::Smem &sm = *reinterpret_cast<typename C::Smem *>(smem_raw);
+  double *vals = sm.vals;
+  __shared__ LeafDupSmem<C> s_dup;
+  __shared__ double s_dupd[C::kMaxDup];  // deltas of the entries that share leaves
+  __shared__ int s_stop;                 // first position that must not be applied
+  __shared__ int s_stop_code;
+  __shared__ double s_max[32];
+  __shared__ int s_role;
+  __shared__ uint32_t s_listed;
+  __shared__ ScanSmem s_scan;
+  uint32_t *info = a.sorted;
+  unsigned int *list_flag = a.sync_words + 8, *ended = a.sync_words + 9;
+  unsigned int *fetched = a.sync_words + 10;  // level CTAs that have their leaves
+  B2R_MARK(13);
+  pdl_release();
+  // (the level counter and the flags belong to this launch: the launch before it ended
+  // before the kernel that produced the indices did)
+  if (threadIdx.x == 0) s_role = (int)atomicInc(a.sync_words, (unsigned)a.depth);
+  int n = a.n;
+  if (a.n_dev) {
+    const int64_t left = (int64_t)*a.n_dev - a.k_base;
+    n = left < n ? (left > 0 ? (int)left : 0) : n;
+  }
+  if (threadIdx.x == 0) {
+    s_stop = n;
+    s_stop_code = 0;
+  }
+  __syncthreads();
+  // Levels are handed out in order of arrival, the leaf level first: the CTA the others
+  // wait for (its list ahead of the values; its deltas when the list does not serve) is
+  // always one that is already running.
+  const int level = s_role == 0 ? a.depth : s_role - 1;
+  const bool is_leaf = level == a.depth;
+  B2R_MARK_LVL(0, 0);
+  B2R_MARK_LVL(16, a.depth);
+  B2R_MARK_LVL(22, a.depth - 1);
+  if (n <= 0) {  // (every CTA sees the same n)
+    pdl_acquire();
+    return;
+  }
+  // The last CTA to leave re-arms the list's flag and the count of level CTAs that have
+  // their leaves (everybody is past both then).
+  auto leave = [&]() {
+    if (threadIdx.x == 0 && atomicInc(ended, (unsigned)a.depth) == (unsigned)a.depth) {
+      *list_flag = 0u;
+      *fetched = 0u;
+    }
+  };
+
+  // ---- ahead of the values
+  LeafPrep<C> leaf_prep;
+  LevelPrep<C> prep;
+  bool listed = false;  // a list of the duplicate leaves serves
+  int ndup = 0;
+  double chain_leaf = 0.0;
+  uint32_t *scratch = reinterpret_cast<uint32_t *>(sm.vals);
+  uint32_t lidx[kItems];
+  NearlySorted<C> ns;
+  // own_list: the batch is grouped by leaf already but for a few entries — every CTA makes
+  // the list for itself and takes its leaves from the tree; else the leaf CTA makes it
+  // with a hash set and hands it (and the leaves) to the others.
+  const int who = is_leaf ? 0 : (level == 10 ? 1 : -1);
+  (void)who;
+  B2R_PHASE(who, 0);
+  // The indices; then, at once and for every entry, the loads that need nothing else: its
+  // leaf and (level CTAs) its node on this level — they fly while the batch is analysed.
+  int first_bad = n;
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int k = threadIdx.x * kItems + j;
+    lidx[j] = kEmpty;
+    if (k < n) {
+      const int64_t ix = (int64_t)a.indices[k];
+      if (ix >= 0 && ix < a.leaves) lidx[j] = (uint32_t)ix;
+      else first_bad = min(first_bad, k);
+    }
+  }
+  double leaf_k[kItems], node_k[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    leaf_k[j] = node_k[j] = 0.0;
+    if (lidx[j] == kEmpty) continue;
+    leaf_k[j] = a.heap[a.leaves + lidx[j]];
+    if (!is_leaf)
+      node_k[j] = a.heap[(((int64_t)1) << level) + (lidx[j] >> (a.depth - level))];
+  }
+  if (first_bad < n) atomicMin(&s_stop, first_bad);
+  int own_pos[kItems];
+  const bool own_list =
+      a.own_lists != 0 && leaf_list_from_sorted<C>(a, n, sm, s_dup, lidx, &ns, scratch, s_scan,
+                                                   a.depth - level, own_pos, who) == 1;
+  B2R_PHASE(who, 5);
+  B2R_TRACE_COUNT(0, is_leaf);
+  B2R_TRACE_COUNT(1, is_leaf && own_list);
+  if (own_list) {
+    listed = true;
+    ndup = s_dup.ndup;
+    // (the grouping by leaf has been read by everybody: leaf_list_from_sorted ends on a
+    // barrier; the one behind these stores is the one below)
+    if (!is_leaf) {
+#pragma unroll
+      for (int j = 0; j < kItems; ++j) {
+        sm.g.node[own_pos[j]] = lidx[j] >> (a.depth - level);
+        sm.g.elem[own_pos[j]] = (uint32_t)(threadIdx.x * kItems + j);
+      }
+    }
+    B2R_PHASE(who, 6);
+    // The leaf CTA writes the new leaves only once every level CTA HAS the old ones: a
+    // value that is in shared memory has landed.
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      sm.leafv[threadIdx.x * kItems + j] = leaf_k[j];
+      if (!is_leaf) sm.nodev[threadIdx.x * kItems + j] = node_k[j];
+    }
+    B2R_PHASE(who, 8);
+    __syncthreads();
+    if (!is_leaf && threadIdx.x == 0) atomicAdd(fetched, 1u);
+    B2R_PHASE(who, 9);
+    const bool head = (int)threadIdx.x < ndup &&
+                      (threadIdx.x == 0 ||
+                       s_dup.ds_idx[threadIdx.x - 1] != s_dup.ds_idx[threadIdx.x]);
+    if (head) chain_leaf = sm.leafv[s_dup.ds_k[threadIdx.x]];
+    if (is_leaf) {
+#pragma unroll
+      for (int j = 0; j < kItems; ++j) {
+        const int k = threadIdx.x * kItems + j;
+        leaf_prep.idx[j] = lidx[j];
+        leaf_prep.k[j] = (uint32_t)k;
+        leaf_prep.single[j] = k < n && lidx[j] != kEmpty && sm.place[k] == kEmpty;
+        leaf_prep.leaf[j] = leaf_k[j];
+      }
+    } else {
+      level_prefetch<C>(a, level, n, sm, &prep, true);
+#pragma unroll
+      for (int j = 0; j < kItems; ++j)
+        if (threadIdx.x * kItems + j < n) prep.dup_of[j] = sm.place[prep.k[j]];
+      B2R_PHASE(who, 7);
+    }
+  } else if (is_leaf) {
+    listed = leaf_hashed_prepare<C>(a, n, sm.h, s_dup, &leaf_prep, &s_stop, info);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(list_flag), "r"(1u) : "memory");
+    ndup = listed ? s_dup.ndup : 0;
+  } else {
+    group_level<C>(a, level, n, sm, &prep, &s_stop, s_scan);
+    B2R_LEVEL_TIME(0, level);
+    if (threadIdx.x == 0) {
+      unsigned seen = 0;
+      const long long t0 = clock64();
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(list_flag)
+                     : "memory");
+      } while (seen == 0 && clock64() - t0 < 4000000000ll);  // (2 s: never hang the GPU)
+      s_listed = seen ? __ldcg(info + Info::kCount) : Info::kOverflow;
+    }
+    __syncthreads();
+    listed = s_listed != Info::kOverflow;
+    ndup = listed ? (int)s_listed : 0;
+    if (listed) {
+      for (int q = threadIdx.x; q < ndup; q += T) {
+        s_dup.ds_idx[q] = __ldcg(info + Info::kIdx + q);
+        s_dup.ds_k[q] = __ldcg(info + Info::kK + q);
+      }
+      const double *leaves_then = reinterpret_cast<const double *>(info + Info::kLeaf);
+#pragma unroll
+      for (int j = 0; j < kItems; ++j) {
+        if (threadIdx.x * kItems + j < n) {
+          prep.dup_of[j] = __ldcg(info + Info::kOf + prep.k[j]);
+          prep.leaf[j] = __ldcg(leaves_then + prep.k[j]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // heads of the duplicates' chains (every CTA walks them all): the leaf they start from
+  const bool chain_head = (int)threadIdx.x < ndup &&
+                          (threadIdx.x == 0 ||
+                           s_dup.ds_idx[threadIdx.x - 1] != s_dup.ds_idx[threadIdx.x]);
+  if (chain_head && !own_list)
+    chain_leaf = __ldcg(reinterpret_cast<const double *>(info + Info::kLeaf) +
+                        s_dup.ds_k[threadIdx.x]);
+  B2R_MARK_LVL(17, a.depth);
+  B2R_MARK_LVL(23, a.depth - 1);
+  B2R_MARK_LVL(29, 0);
+  B2R_LEVEL_TIME(1, level);
+  B2R_PHASE(who, 10);
+  pdl_acquire();
+  B2R_PHASE(who, 11);
+  B2R_LEVEL_TIME(2, level);
+  B2R_MARK_LVL(18, a.depth);
+  B2R_MARK_LVL(1, 0);
+  B2R_MARK_LVL(24, a.depth - 1);
+  // An earlier chunk (or the kernel that produced the values) failed: the reference's
+  // loop stopped there.  This kernel's own latch is only written once every level has
+  // passed the plain kernel's flag, so every CTA takes the same branch.
+  if (a.status[0] != 0) {
+    leave();
+    return;
+  }
+
+  // ---- the values: every CTA reads all of them, and finds the first entry the reference
+  // would have raised on for itself
+  double v[kItems];
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int k = threadIdx.x + j * T;
+    v[j] = k < n ? (double)a.values[k] : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < kItems; ++j) {
+    const int k = threadIdx.x + j * T;
+    if (k < n) {
+      vals[k] = v[j];
+      if (v[j] < 0.0) atomicMin(&s_stop, k);
+    }
+  }
+  __syncthreads();
+  const int n_eff = s_stop;
+
+  // (own lists: the level CTAs take the old leaves from the tree, so the new ones wait
+  // until all of them have theirs — which they have had since before the values came)
+  if (own_list && is_leaf) {
+    if (threadIdx.x == 0) {
+      unsigned have = 0;
+      const long long t0 = clock64();
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(have) : "l"(fetched)
+                     : "memory");
+      } while (have < (unsigned)a.depth && clock64() - t0 < 4000000000ll);
+      if (have < (unsigned)a.depth && a.status[0] == 0) a.status[0] = B2R_ERR_CUDA;
+    }
+    __syncthreads();
+  }
+  B2R_TRACE_COUNT(2, is_leaf && listed && n_eff == n);
+  if (listed && n_eff == n) {
+    // ---- nothing to wait for.  Chains of the entries that share leaves:
+    //   delta = value - leaf; leaf += delta   (sum_tree.py:196-202, last level)
+    if (chain_head) {
+      const uint32_t idx = s_dup.ds_idx[threadIdx.x];
+      double leaf = chain_leaf;
+      for (int q = threadIdx.x; q < ndup && s_dup.ds_idx[q] == idx; ++q) {
+        const double d = __dsub_rn(vals[s_dup.ds_k[q]], leaf);
+        leaf = __dadd_rn(leaf, d);
+        s_dupd[q] = d;
+      }
+      if (is_leaf) a.heap[a.leaves + idx] = leaf;
+    }
+    if (is_leaf) {
+#pragma unroll
+      for (int j = 0; j < kItems; ++j) {
+        if (leaf_prep.single[j]) {
+          const double d = __dsub_rn(vals[leaf_prep.k[j]], leaf_prep.leaf[j]);
+          a.heap[a.leaves + leaf_prep.idx[j]] = __dadd_rn(leaf_prep.leaf[j], d);
+        }
+      }
+      // max_recorded_priority = max(value, current)
+      double local_max = 0.0;
+#pragma unroll
+      for (int j = 0; j < kItems; ++j) local_max = fmax(local_max, v[j]);
+      for (int off = 16; off > 0; off >>= 1)
+        local_max = fmax(local_max, __shfl_xor_sync(0xffffffffu, local_max, off));
+      if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = local_max;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double m = *a.max_rec;
+        for (int w = 0; w < T / 32; ++w)
+          if (s_max[w] > m) m = s_max[w];
+        *a.max_rec = m;
+      }
+      B2R_LEVEL_TIME(3, level);
+      B2R_MARK_END(15);
+      leave();
+      return;
+    }
+    double vp[kItems];
+#pragma unroll
+    for (int j = 0; j < kItems; ++j)
+      vp[j] = threadIdx.x * kItems + j < n ? vals[prep.k[j]] : 0.0;
+    __syncthreads();  // (vals turns into the deltas in group order)
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      const int p = threadIdx.x * kItems + j;
+      if (p < n)
+        vals[p] = prep.dup_of[j] != kEmpty
+                      ? s_dupd[prep.dup_of[j]]
+                      : __dsub_rn(vp[j], own_list ? sm.leafv[prep.k[j]] : prep.leaf[j]);
+    }
+    __syncthreads();
+    B2R_MARK_LVL(3, 0);
+    B2R_MARK_LVL(20, 1);
+    B2R_MARK_LVL(26, a.depth - 1);
+    level_chains_grouped<C>(a, level, n, sm, prep);
+    B2R_MARK_LVL(4, 0);
+    B2R_MARK_LVL(21, 1);
+    B2R_MARK_LVL(27, a.depth - 1);
+    B2R_LEVEL_TIME(3, level);
+    B2R_MARK_END(15);
+    leave();
+    return;
+  }
+
+  // ---- the list does not serve: on as the plain kernel
+  if (!is_leaf) {
+    const int applied = levels_wait_for_leaf(a);
+    B2R_MARK_END(11);
+    if (applied != n) group_level<C>(a, level, applied, sm, &prep, &s_stop, s_scan);
+    if (applied > 0) internal_level_chains<C>(a, level, applied, sm, prep.node_val);
+    leave();
+    return;
+  }
+  if (n_eff < n && threadIdx.x == 0)
+    s_stop_code = (vals[n_eff] < 0.0) ? B2R_ERR_NEGATIVE_PRIORITY : B2R_ERR_INDEX_RANGE;
+  {
+    double local_max = 0.0;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j)
+      if (threadIdx.x + j * T < n_eff) local_max = fmax(local_max, v[j]);
+    for (int off = 16; off > 0; off >>= 1)
+      local_max = fmax(local_max, __shfl_xor_sync(0xffffffffu, local_max, off));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = local_max;
+  }
+  __syncthreads();
+  if (!leaf_deltas_hashed<C>(a, n_eff, sm.h, vals)) {
+    __syncthreads();
+    uint32_t key[kItems], val[kItems];
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      const int k = threadIdx.x * kItems + j;
+      key[j] = k < n_eff ? (uint32_t)a.indices[k] : 0xffffffffu;
+      val[j] = (uint32_t)k;
+    }
+    if (a.depth != 0) Sort(sm.g.sort).Sort(key, val, 0, a.depth);
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      sm.g.node[threadIdx.x * kItems + j] = key[j];
+      sm.g.elem[threadIdx.x * kItems + j] = val[j];
+    }
+    __syncthreads();
+    // one thread per distinct leaf walks its chain in batch order
+    for (int p = threadIdx.x; p < n_eff; p += T) {
+      if (p != 0 && sm.g.node[p - 1] == sm.g.node[p]) continue;
+      const uint32_t node = sm.g.node[p];
+      double leaf = a.heap[a.leaves + node];
+      for (int q = p; q < n_eff && sm.g.node[q] == node; ++q) {
+        const uint32_t k = sm.g.elem[q];
+        const double d = __dsub_rn(vals[k], leaf);
+        leaf = __dadd_rn(leaf, d);
+        vals[k] = d;
+      }
+      a.heap[a.leaves + node] = leaf;
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < n_eff; k += T) a.delta[k] = vals[k];
+  B2R_MARK_LVL(19, a.depth);
+  leaf_publishes(a, n, n_eff, s_stop_code);
+  B2R_MARK_LVL(28, a.depth);
+  if (threadIdx.x == 0) {
+    double m = *a.max_rec;
+    for (int w = 0; w < T / 32; ++w)
+      if (s_max[w] > m) m = s_max[w];
+    if (n_eff > 0) *a.max_rec = m;
+    if (n_eff < n && a.depth == 0) {  // (a one-node tree has no other level to latch)
+      a.status[0] = s_stop_code;
+      a.status[1] = a.k_base + n_eff;
+    }
+  }
   B2R_MARK_END(15);
+  leave();
 }
 
 constexpr int kSmallBatch = 256;  // largest batch the single-CTA kernel takes
@@ -961,9 +1979,9 @@ int padded_size(int n) {
   return p;
 }
 
-template <typename C, typename K>
+template <typename C, int WHICH, typename K>
 int allow_big_smem(K kernel) {
-  static bool done = false;  // per instantiation
+  static bool done = false;  // per instantiation (WHICH tells kernels of one type apart)
   if (!done) {
     B2R_CUDA(cudaFuncSetAttribute(kernel,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -976,7 +1994,8 @@ int allow_big_smem(K kernel) {
 // One chunk of the cooperative kernel with geometry C.
 template <typename C, typename I, typename V>
 int launch_big_chunk(const UpdateArgs<I, V> &a, int depth, cudaStream_t stream) {
-  B2R_TRY((allow_big_smem<C>(tree_update_kernel<I, V, C>)));
+  B2R_TRY((allow_big_smem<C, 0>(tree_update_kernel<I, V, C>)));
+  B2R_TRY((allow_big_smem<C, 1>(tree_update_early_kernel<I, V, C>)));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(depth + 1);
   cfg.blockDim = dim3(C::kThreads);
@@ -986,7 +2005,8 @@ int launch_big_chunk(const UpdateArgs<I, V> &a, int depth, cudaStream_t stream) 
   int n_attr = 0;
   // Launched early (programmatic dependent launch) only in the 256 x 4 geometry: 21
   // early CTAs of 1024 threads would sit on 21 SMs for the whole loss kernel.
-  if (pdl_enabled() && C::kThreads <= 256) {
+  // (kEarly: starting early is the point — its CTAs are sorting meanwhile.)
+  if (pdl_enabled() && (C::kThreads <= 256 || a.phase == kEarly)) {
     attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n_attr++].val.programmaticStreamSerializationAllowed = 1;
   }
@@ -1004,7 +2024,10 @@ int launch_big_chunk(const UpdateArgs<I, V> &a, int depth, cudaStream_t stream) 
   }
   cfg.attrs = attr;
   cfg.numAttrs = n_attr;
-  B2R_CUDA(cudaLaunchKernelEx(&cfg, tree_update_kernel<I, V, C>, a));
+  if (a.phase == kEarly)
+    B2R_CUDA(cudaLaunchKernelEx(&cfg, tree_update_early_kernel<I, V, C>, a));
+  else
+    B2R_CUDA(cudaLaunchKernelEx(&cfg, tree_update_kernel<I, V, C>, a));
   B2R_LAUNCHED();
   return B2R_OK;
 }
@@ -1119,8 +2142,10 @@ bool tree_can_presort(int64_t n, int64_t expected_n) {
 
 static int ensure_sorted(b2r_tree *t) {
   if (t->sorted) return B2R_OK;
-  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->sorted),
-                      (size_t)(t->depth + 1) * 2 * BigCfg4096::kChunk * sizeof(uint32_t)));
+  // (the presorted lists of every level; kEarly: the leaf CTA's list of duplicate leaves)
+  size_t words = (size_t)(t->depth + 1) * 2 * BigCfg4096::kChunk;
+  if (words < (size_t)DupInfo<BigCfg4096>::kWords) words = DupInfo<BigCfg4096>::kWords;
+  B2R_CUDA(cudaMalloc(reinterpret_cast<void **>(&t->sorted), words * sizeof(uint32_t)));
   return B2R_OK;
 }
 
@@ -1197,9 +2222,20 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
     a.n_dev = n_dev;
     a.scan_min_chain = tree_scan_min_chain();
     a.phase = base == 0 ? phase : kFull;
+    static const int own_lists = [] {
+      const char *e = std::getenv("B2R_TREE_OWN_LISTS");
+      return e == nullptr || std::atoi(e) != 0 ? 1 : 0;
+    }();
+    a.own_lists = own_lists;
     a.sorted = t->sorted;
     a.sync_words = t->sync_words;
-    if (compact)
+    static const bool wide = [] {
+      const char *e = std::getenv("B2R_TREE_WIDE");
+      return e == nullptr || std::atoi(e) != 0;
+    }();
+    if (compact && a.phase == kEarly && wide)
+      B2R_TRY((launch_big_chunk<BigCfgWide>(a, t->depth, stream)));
+    else if (compact)
       B2R_TRY((launch_big_chunk<BigCfg1024>(a, t->depth, stream)));
     else
       B2R_TRY((launch_big_chunk<BigCfg4096>(a, t->depth, stream)));
@@ -1302,10 +2338,18 @@ int b2r_tree_set(b2r_tree *t, int64_t n, const int64_t *indices,
   memcpy(t->bounce.host + (size_t)n * 8, values, (size_t)n * 8);
   B2R_CUDA(cudaMemcpyAsync(t->bounce.dev, t->bounce.host, (size_t)n * 16,
                            cudaMemcpyHostToDevice, s));
+  // (tests: B2R_TREE_SET_PHASE=3 sends this call through the kernel that groups ahead of
+  // its values, as the fused step does; indices and values come from a copy here, so its
+  // promise holds trivially)
+  const char *phase_env = std::getenv("B2R_TREE_SET_PHASE");
+  const int phase = phase_env != nullptr && std::atoi(phase_env) == b2r::kEarly &&
+                            b2r::tree_can_presort(n, -1)
+                        ? b2r::kEarly
+                        : b2r::kFull;
   B2R_TRY((b2r::tree_apply<int64_t, double>(
       t, n, reinterpret_cast<const int64_t *>(t->bounce.dev),
       reinterpret_cast<const double *>(t->bounce.dev + (size_t)n * 8), nullptr,
-      s)));
+      s, nullptr, -1, phase)));
   int64_t st[2];
   B2R_CUDA(cudaMemcpyAsync(st, t->status, 16, cudaMemcpyDeviceToHost, s));
   B2R_CUDA(cudaStreamSynchronize(s));
@@ -1426,5 +2470,17 @@ int b2r_tree_write_level(b2r_tree *t, int level, const double *in,
 #ifdef B2R_TRACE
 extern "C" int b2r_debug_trace_tree(long long *out) {
   return (int)cudaMemcpyFromSymbol(out, b2r::g_trace, sizeof(long long) * 32);
+}
+// [4][32]: per tree level — grouped, parent ended, released (leaf: deltas written), done
+extern "C" int b2r_debug_trace_tree_levels(long long *out) {
+  return (int)cudaMemcpyFromSymbol(out, b2r::g_level_trace, sizeof(long long) * 128);
+}
+// [8]: launches of the early write-back, ... with every CTA's own list, ... that needed no
+// hand-over behind the values
+extern "C" int b2r_debug_trace_tree_phases(long long *out) {
+  return (int)cudaMemcpyFromSymbol(out, b2r::g_phase_trace, sizeof(long long) * 32);
+}
+extern "C" int b2r_debug_trace_tree_counts(unsigned long long *out) {
+  return (int)cudaMemcpyFromSymbol(out, b2r::g_trace_count, sizeof(unsigned long long) * 8);
 }
 #endif

@@ -349,7 +349,14 @@ struct UpdateArgs {
   // those lists instead of sorting — unless an entry must not be applied (negative value,
   // index out of range), in which case the lists are ignored and the kernel sorts the
   // applied prefix itself, as kFull always does.
+  // kEarly (tree_update_early_kernel): ONE launch that does the index-only work ahead of
+  // its griddepcontrol.wait, beside the kernel that produces the values.  The caller
+  // promises that the indices (and n_dev) were final before that kernel let its
+  // dependents start.
   int phase = 0;
+  // kEarly: 0 = never take the path for batches that are grouped by leaf already
+  // (B2R_TREE_OWN_LISTS=0, comparison runs)
+  int own_lists = 1;
   uint32_t *sorted = nullptr;
   // role ticket, barrier flag, barrier arrivals (see tree_update_kernel)
   unsigned int *sync_words = nullptr;
@@ -371,7 +378,7 @@ __device__ __forceinline__ void publish_root(const UpdateArgs<I, V> &a) {
   const double root = *reinterpret_cast<volatile double *>(a.heap + 1);
   exchange_publish(*a.publish, a.publish_world, a.publish_rank, root, *a.publish->seq + 1);
 }
-constexpr int kFull = 0, kPresort = 1, kApply = 2;
+constexpr int kFull = 0, kPresort = 1, kApply = 2, kEarly = 3;
 
 // At most 32 sets (the agent's batch, an add flush): entry k lives in lane k of every
 // warp, warp l owns tree level l, and nothing is sorted.  __match_any_sync groups the

@@ -108,6 +108,101 @@ def test_tree_long_chains_verified_scan_bit_exact(gpu, batch, odd):
   assert tree.max_recorded_priority == float(want.max_recorded[0])
 
 
+@pytest.fixture
+def early_tree_sets(monkeypatch):
+  """Batched sets through the write-back that groups ahead of its values (tree.cu:
+  tree_update_early_kernel, the fused step's kernel)."""
+  monkeypatch.setenv('B2R_TREE_SET_PHASE', '3')
+
+
+def _early_batch(rng, cap, batch, dups, order):
+  """Indices of one batch: 'random'; 'sorted' (a stratified sample: rows in leaf order);
+  'nearly' (the same with ~1 % of the rows drawn again, as invalid picks are);
+  'shuffled-tail' (sorted but for a stretch of 100 rows: too many to move, so the kernel
+  sorts)."""
+  idx = rng.randint(0, cap, size=batch).astype(np.int64)
+  if dups:
+    idx[rng.choice(batch, size=dups, replace=False)] = idx[0]
+  if order != 'random':
+    idx = np.sort(idx)
+  if order == 'nearly':
+    again = rng.choice(batch, size=max(1, batch // 100), replace=False)
+    idx[again] = rng.randint(0, cap, size=len(again))
+    if batch > 8:  # two neighbours drawn again, one of them onto an existing leaf
+      idx[5] = idx[batch - 2]
+      idx[6] = rng.randint(0, cap)
+  if order == 'shuffled-tail' and batch > 200:
+    rng.shuffle(idx[batch - 150:batch - 50])
+  return idx
+
+
+@pytest.mark.parametrize('order', ['random', 'sorted', 'nearly', 'shuffled-tail'])
+@pytest.mark.parametrize('cap,batch,dups', [(2, 33, 0), (1000, 256, 32), (4096, 1024, 128),
+                                            (1 << 20, 1024, 2), (1 << 20, 700, 600),
+                                            (1 << 20, 64, 0)])
+def test_tree_early_grouping_bit_exact(gpu, early_tree_sets, cap, batch, dups, order):
+  """Same contract as test_tree_batched_sets_bit_exact; `dups` entries share one leaf
+  (600 of 700: more than the list of duplicate leaves takes, so the plain leaf pass
+  runs)."""
+  rng = np.random.RandomState(cap % 1000 + batch + dups + len(order))
+  tree = gpu.st.SumTree(cap)
+  want = fast.FastTree(cap)
+  if cap > 4096:
+    fill_idx = np.arange(cap, dtype=np.int64)
+    fill = (0.5 + rng.rand(cap)).astype(np.float32).astype(np.float64)
+    for lo in range(0, cap, 4096 * 16):
+      tree.set_batch(fill_idx[lo:lo + 4096 * 16], fill[lo:lo + 4096 * 16])
+    assert want.set_seq(fill_idx, fill) == 0
+  for rep in range(5):
+    idx = _early_batch(rng, cap, batch, dups, order)
+    val = np.sqrt(np.abs(rng.randn(batch)) + 1e-10).astype(np.float32).astype(
+        np.float64) * (10.0 ** rng.randint(-3, 3))
+    val[rng.rand(batch) < 0.05] = 0.0
+    if rep == 3:
+      val[rng.choice(batch, size=3, replace=False)] = rng.rand(3) * np.pi  # adds that round
+    tree.set_batch(idx, val)
+    assert want.set_seq(idx, val) == 0
+    for l, level in enumerate(tree.nodes):
+      assert np.array_equal(level.view(np.uint64), want.level(l).view(np.uint64)), (
+          'level %d differs after batch %d' % (l, rep))
+  assert tree.max_recorded_priority == float(want.max_recorded[0])
+
+
+@pytest.mark.parametrize('order', ['random', 'nearly'])
+@pytest.mark.parametrize('bad', ['negative', 'index'])
+def test_tree_early_grouping_stops_where_the_reference_raises(gpu, early_tree_sets, bad,
+                                                              order):
+  """sum_tree.py:178-205 in a loop (prioritized_replay_buffer.py:213-214): the entries
+  before the offending one are applied, nothing behind it is."""
+  cap, batch, stop = 5000, 600, 417
+  rng = np.random.RandomState(11)
+  tree = gpu.st.SumTree(cap)
+  want = fast.FastTree(cap)
+  idx = rng.randint(0, cap, size=batch).astype(np.int64)
+  idx[5] = idx[500] = idx[100]
+  val = (0.1 + rng.rand(batch)).astype(np.float32).astype(np.float64)
+  tree.set_batch(idx, val)
+  assert want.set_seq(idx, val) == 0
+  idx2 = _early_batch(rng, cap, batch, 4, order)
+  val2 = (0.1 + rng.rand(batch)).astype(np.float32).astype(np.float64)
+  if bad == 'negative':
+    val2[stop] = -1.5
+    with pytest.raises(ValueError, match='nonnegative. Got -1.5'):
+      tree.set_batch(idx2, val2)
+  else:
+    idx2[stop] = cap + (1 << 32)  # (its low 32 bits are a valid leaf)
+    with pytest.raises((ValueError, IndexError, RuntimeError)):
+      tree.set_batch(idx2, val2)
+  assert want.set_seq(idx2[:stop], val2[:stop]) == 0
+  for l, level in enumerate(tree.nodes):
+    assert np.array_equal(level.view(np.uint64), want.level(l).view(np.uint64)), (
+        'level %d differs' % l)
+  assert tree.max_recorded_priority == float(want.max_recorded[0])
+  tree.set_batch(idx, val)  # the latch is cleared; the next batch applies in full
+  assert want.set_seq(idx, val) == 0
+  assert np.array_equal(tree.nodes[0].view(np.uint64), want.level(0).view(np.uint64))
+
+
 def test_tree_negative_value_stops_the_batch(gpu):
   tree = gpu.st.SumTree(64)
   with pytest.raises(ValueError, match='nonnegative. Got -2.0'):
