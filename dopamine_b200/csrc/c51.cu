@@ -111,6 +111,9 @@ struct LossArgs {
   // [batch]) in the caller's page-locked memory: the host-facing trainer's result slot,
   // written by the kernel instead of copied by a call.
   float *loss_host;
+  // The write-back behind this kernel is resident already and waits to hear that the
+  // sampled indices are final (tree.cuh: TreeGo); go.go == nullptr: nobody does.
+  TreeGo go;
 };
 
 // One CTA per batch row, one warp per action (rainbow_agent.py:200-293):
@@ -151,10 +154,10 @@ c51_loss_kernel(LossArgs a) {
   __shared__ bool s_last;
   const float *z = a.u.support;
   B2R_MARK(0);
-  // (wait, then release: a dependent that starts early — the tree write-back — may read
-  // what this kernel's own predecessor, the sampler, wrote: tree.cu, kEarly)
-  pdl_acquire();
   pdl_release();
+  pdl_acquire();
+  // (the sampler has ended: the write-back behind this kernel may read its indices)
+  if (blockIdx.x == 0 && threadIdx.x == 0) tree_go_signal(a.go);
   B2R_MARK(1);
   const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
   if (b >= rows) return;  // (mean_weighted_loss is not supported with batch_count)
@@ -484,10 +487,10 @@ c51_loss_rows_kernel(LossArgs a) {
   const int N = NC ? NC : a.u.num_atoms, A = a.u.num_actions;
   const float *__restrict__ z = a.u.support;
   B2R_MARK(10);
-  // (wait, then release: a dependent that starts early — the tree write-back — may read
-  // what this kernel's own predecessor, the sampler, wrote: tree.cu, kEarly)
-  pdl_acquire();
   pdl_release();
+  pdl_acquire();
+  // (the sampler has ended: the write-back behind this kernel may read its indices)
+  if (blockIdx.x == 0 && threadIdx.x == 0) tree_go_signal(a.go);
   B2R_MARK(11);
   const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
   if ((int)blockIdx.x * kRowWarps >= rows) return;  // (no mean loss with batch_count)
@@ -1216,10 +1219,10 @@ c51_post_kernel(LossArgs a, const float *__restrict__ scratch, int have_stats) {
   __shared__ bool s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   B2R_MARK(10);
-  // (wait, then release: a dependent that starts early — the tree write-back — may read
-  // what this kernel's own predecessor, the sampler, wrote: tree.cu, kEarly)
-  pdl_acquire();
   pdl_release();
+  pdl_acquire();
+  // (the sampler has ended: the write-back behind this kernel may read its indices)
+  if (blockIdx.x == 0 && threadIdx.x == 0) tree_go_signal(a.go);
   B2R_MARK(11);
   const int rows = a.u.batch_count ? min(*a.u.batch_count, a.u.batch) : a.u.batch;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1513,7 +1516,7 @@ bool c51_post_takes_tree(const b2r_c51_args *args, const b2r_tree *tree,
 int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_stats,
                     cudaStream_t s, int64_t *err, int32_t *count_copy, b2r_tree *tree,
                     const int32_t *indices, unsigned int *tree_done,
-                    const b2r_exchange *publish, float *loss_host) {
+                    const b2r_exchange *publish, float *loss_host, const TreeGo *go) {
   if (!args || args->batch <= 0 || !scratch)
     return fail(B2R_ERR_INVALID_ARGUMENT, "bad C51 shape");
   if (args->batch_count && args->mean_weighted_loss)
@@ -1529,6 +1532,7 @@ int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_sta
   a.count_copy = count_copy;
   a.tree_done = nullptr;
   a.loss_host = loss_host;
+  if (go != nullptr) a.go = *go;
   a.warps = 0;
   B2R_TRY(ensure_loss_scratch(args->batch));
   a.weighted = g_weighted;

@@ -245,15 +245,24 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   int64_t expected_rows =
       shard ? (batch + shard->exchange->world - 1) / shard->exchange->world : -1;
   if (expected_rows > rows_cap) expected_rows = rows_cap;
-  // B2R_TREE_EARLY=0 (comparison runs): grouping as a kernel of its own on a forked
-  // stream, joined in front of the write-back proper.  Default: ONE write-back kernel
-  // behind the loss kernel that groups ahead of its wait for it (tree.cu, kEarly).
-  static const bool tree_early = [] {
-    const char *e = std::getenv("B2R_TREE_EARLY");
-    return e == nullptr || std::atoi(e) != 0;
+  // Up to B2R_TREE_EARLY_MAX rows (default 512; 0: never): ONE write-back kernel behind
+  // the loss tail that is resident early and groups the batch ahead of its values
+  // (tree.cu, kEarly; the loss tail tells it when the indices are final — TreeGo).  Above,
+  // the frame copies bound the step and what they want from the chain is to be left
+  // alone: the grouping runs as a small kernel of its own on a forked stream and is
+  // joined in front of the write-back proper (measured at 1024: 36.8 us against 40.1 with
+  // the 21 early CTAs of 1024 threads resident beside the copies).
+  static const int tree_early_max = [] {
+    const char *e = std::getenv("B2R_TREE_EARLY_MAX");
+    const char *off = std::getenv("B2R_TREE_EARLY");
+    if (off != nullptr && std::atoi(off) == 0) return 0;
+    return e != nullptr ? std::atoi(e) : 512;
   }();
   const bool groupable = tree_can_presort(rows_cap, expected_rows) && !(debug_skip() & 6);
-  const bool presort = groupable && !tree_early;
+  const int64_t likely_rows = expected_rows >= 0 ? expected_rows : rows_cap;
+  const bool early_tree = groupable && split_loss && likely_rows <= tree_early_max;
+  const bool presort = groupable && !early_tree;
+  const TreeGo tree_go = early_tree ? tree_go_of(b->tree) : TreeGo();
   if (frames || presort) B2R_CUDA(cudaEventRecord(b->ev_fork, s));
   if (presort) {
     B2R_CUDA(cudaStreamWaitEvent(b->side2, b->ev_fork, 0));
@@ -300,7 +309,8 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
                             shard && count != shard->out_count ? shard->out_count : nullptr,
                             tail_writeback || tail_counted ? b->tree : nullptr,
                             out->indices, tree_done, tail_counted ? early : nullptr,
-                            direct ? direct->loss_host : nullptr));
+                            direct ? direct->loss_host : nullptr,
+                            early_tree ? &tree_go : nullptr));
   else if (tail_writeback)
     B2R_TRY(c51_loss_launch(&loss, s, b->tree, out->indices));
   else if (!(debug_skip() & 1))
@@ -311,8 +321,9 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   if (!(debug_skip() & 2) && !tail_writeback)
     B2R_TRY((tree_apply<int32_t, float>(b->tree, rows_cap, out->indices, loss.priorities,
                                         nullptr, s, count, expected_rows,
-                                        presort ? 2 : (groupable ? 3 : 0),
-                                        flush_behind ? nullptr : early, tree_done)));
+                                        presort ? 2 : (early_tree ? 3 : 0),
+                                        flush_behind ? nullptr : early, tree_done,
+                                        early_tree)));
   if (flush_behind) B2R_TRY(flush_queue(b, s, false, early));
   if (frames && !deferred) B2R_CUDA(cudaStreamWaitEvent(s, b->ev_join, 0));
   if (split_loss && !unjoined && !(deferred && frames))

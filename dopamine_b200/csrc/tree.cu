@@ -834,14 +834,18 @@ struct LeafPrep {
 constexpr int kMaxMoved = 64;
 
 struct ScanSmem {
-  uint32_t wmax[32];
-  int wsum[32];
+  // two sets, used in turn: a scan may start while slow warps still read the one before
+  uint32_t wmax[2][32];
+  int wsum[2][32];
 };
 
-// Exclusive block scan of (max, sum) over thread totals; *total = the sum of all.
+// Exclusive block scan of (max, sum) over thread totals; *total = the sum of all.  ONE
+// block barrier: every warp scans the 32 warp totals for itself.  `which`: 0, 1, 0, ...
+// on successive calls of a kernel.
 template <int T>
 __device__ __forceinline__ void block_scan_max_sum(uint32_t tm, int ts, ScanSmem &ss,
-                                                   uint32_t *pm, int *ps, int *total) {
+                                                   int which, uint32_t *pm, int *ps,
+                                                   int *total) {
   constexpr int WARPS = T / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t im = tm;
@@ -861,31 +865,27 @@ __device__ __forceinline__ void block_scan_max_sum(uint32_t tm, int ts, ScanSmem
     em = 0u;
     es = 0;
   }
-  __syncthreads();  // (the arrays may still be read from an earlier scan)
   if (lane == 31) {
-    ss.wmax[warp] = im;
-    ss.wsum[warp] = is;
+    ss.wmax[which][warp] = im;
+    ss.wsum[which][warp] = is;
   }
   __syncthreads();
-  if (warp == 0) {
-    uint32_t wm = lane < WARPS ? ss.wmax[lane] : 0u;
-    int ws = lane < WARPS ? ss.wsum[lane] : 0;
+  uint32_t wm = lane < WARPS ? ss.wmax[which][lane] : 0u;
+  int ws = lane < WARPS ? ss.wsum[which][lane] : 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t um = __shfl_up_sync(0xffffffffu, wm, o);
-      const int us = __shfl_up_sync(0xffffffffu, ws, o);
-      if (lane >= o) {
-        wm = max(wm, um);
-        ws += us;
-      }
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t um = __shfl_up_sync(0xffffffffu, wm, o);
+    const int us = __shfl_up_sync(0xffffffffu, ws, o);
+    if (lane >= o) {
+      wm = max(wm, um);
+      ws += us;
     }
-    ss.wmax[lane] = wm;
-    ss.wsum[lane] = ws;
   }
-  __syncthreads();
-  *pm = warp > 0 ? max(ss.wmax[warp - 1], em) : em;
-  *ps = warp > 0 ? ss.wsum[warp - 1] + es : es;
-  *total = ss.wsum[31];
+  const uint32_t before_m = __shfl_sync(0xffffffffu, wm, warp > 0 ? warp - 1 : 0);
+  const int before_s = __shfl_sync(0xffffffffu, ws, warp > 0 ? warp - 1 : 0);
+  *pm = warp > 0 ? max(before_m, em) : em;
+  *ps = warp > 0 ? before_s + es : es;
+  *total = __shfl_sync(0xffffffffu, ws, 31);
 }
 
 // What a thread keeps of the analysis for its entries kItems * t + j.
@@ -928,7 +928,7 @@ __device__ __forceinline__ bool nearly_sorted_analyse(const uint32_t *key, uint3
   }
   uint32_t pm;
   int ps;
-  block_scan_max_sum<T>(tm, ts, ss, &pm, &ps, &ns->n_moved);  // (its barriers: c[] is read)
+  block_scan_max_sum<T>(tm, ts, ss, 0, &pm, &ps, &ns->n_moved);  // (its barrier: c[] is read)
   bool unsorted = false;
 #pragma unroll
   for (int j = 0; j < kItems; ++j) {
@@ -1280,7 +1280,7 @@ __device__ __forceinline__ int leaf_list_from_sorted(const UpdateArgs<I, V> &a, 
   }
   uint32_t unused;
   int at, ndup;
-  block_scan_max_sum<T>(0u, mine, ss, &unused, &at, &ndup);
+  block_scan_max_sum<T>(0u, mine, ss, 1, &unused, &at, &ndup);
   B2R_PHASE(who, 4);
   if (ndup > kMaxDup) return -1;
 #pragma unroll
@@ -1350,10 +1350,45 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_early_kernel(UpdateAr
   unsigned int *list_flag = a.sync_words + 8, *ended = a.sync_words + 9;
   unsigned int *fetched = a.sync_words + 10;  // level CTAs that have their leaves
   B2R_MARK(13);
+  // The last CTA to leave re-arms the list's flag and the count of level CTAs that have
+  // their leaves (everybody is past both then), and counts the launch (TreeGo).
+  auto leave = [&]() {
+    if (threadIdx.x == 0 && atomicInc(ended, (unsigned)a.depth) == (unsigned)a.depth) {
+      *list_flag = 0u;
+      *fetched = 0u;
+      atomicAdd(a.sync_words + 15, 1u);
+    }
+  };
+  // A ticket first, dependents second: the next early write-back can only start once
+  // every CTA of this one has its ticket, so ticket / CTAs is the launch's number and
+  // ticket % CTAs the order of arrival within it.  Dependents only when the indices are
+  // final, too: released at once, the kernels of the NEXT steps would all become resident
+  // behind each other (each lets the next start from its first instruction) and sit on
+  // the SMs waiting — bounded to one step ahead this way.
+  if (threadIdx.x == 0) {
+    const unsigned long long ticket = atomicAdd(a.tickets, 1ull);
+    const unsigned int ctas = (unsigned)a.depth + 1u;
+    s_role = (int)(ticket % ctas);
+    s_listed = 1u;
+    if (a.go != nullptr) {
+      // resident ahead of the indices: wait to hear that they are final (TreeGo)
+      const unsigned int launch = (unsigned int)(ticket / ctas) + 1u;
+      unsigned int seen = 0;
+      const long long t0 = clock64();
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.go) : "memory");
+      } while (seen != launch && clock64() - t0 < 4000000000ll);  // (2 s: never hang)
+      s_listed = seen == launch ? 1u : 0u;
+    }
+  }
+  __syncthreads();
   pdl_release();
-  // (the level counter and the flags belong to this launch: the launch before it ended
-  // before the kernel that produced the indices did)
-  if (threadIdx.x == 0) s_role = (int)atomicInc(a.sync_words, (unsigned)a.depth);
+  if (s_listed == 0u) {  // (nobody said go: touch nothing, say so)
+    pdl_acquire();
+    if (threadIdx.x == 0 && a.status[0] == 0) a.status[0] = B2R_ERR_CUDA;
+    leave();
+    return;
+  }
   int n = a.n;
   if (a.n_dev) {
     const int64_t left = (int64_t)*a.n_dev - a.k_base;
@@ -1374,16 +1409,9 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_early_kernel(UpdateAr
   B2R_MARK_LVL(22, a.depth - 1);
   if (n <= 0) {  // (every CTA sees the same n)
     pdl_acquire();
+    leave();
     return;
   }
-  // The last CTA to leave re-arms the list's flag and the count of level CTAs that have
-  // their leaves (everybody is past both then).
-  auto leave = [&]() {
-    if (threadIdx.x == 0 && atomicInc(ended, (unsigned)a.depth) == (unsigned)a.depth) {
-      *list_flag = 0u;
-      *fetched = 0u;
-    }
-  };
 
   // ---- ahead of the values
   LeafPrep<C> leaf_prep;
@@ -2153,7 +2181,7 @@ template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
                const uint8_t *mode, cudaStream_t stream, const int32_t *n_dev,
                int64_t expected_n, int phase, const b2r_exchange *publish,
-               unsigned int *skip_flag) {
+               unsigned int *skip_flag, bool go_by_flag) {
   set_tree_window(t->heap, (size_t)t->leaves * 16);
   if (phase != kFull) {
     if (!tree_can_presort(n, expected_n) || mode != nullptr)
@@ -2227,6 +2255,8 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
       return e == nullptr || std::atoi(e) != 0 ? 1 : 0;
     }();
     a.own_lists = own_lists;
+    a.tickets = reinterpret_cast<unsigned long long *>(t->sync_words + 12);
+    a.go = go_by_flag && a.phase == kEarly ? t->sync_words + 14 : nullptr;
     a.sorted = t->sorted;
     a.sync_words = t->sync_words;
     static const bool wide = [] {
@@ -2246,15 +2276,22 @@ int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
 template int tree_apply<int64_t, double>(b2r_tree *, int64_t, const int64_t *,
                                          const double *, const uint8_t *,
                                          cudaStream_t, const int32_t *, int64_t, int,
-    const b2r_exchange *, unsigned int *);
+    const b2r_exchange *, unsigned int *, bool);
 template int tree_apply<int32_t, float>(b2r_tree *, int64_t, const int32_t *,
                                         const float *, const uint8_t *,
                                         cudaStream_t, const int32_t *, int64_t, int,
-    const b2r_exchange *, unsigned int *);
+    const b2r_exchange *, unsigned int *, bool);
 template int tree_apply<int32_t, double>(b2r_tree *, int64_t, const int32_t *,
                                          const double *, const uint8_t *,
                                          cudaStream_t, const int32_t *, int64_t, int,
-    const b2r_exchange *, unsigned int *);
+    const b2r_exchange *, unsigned int *, bool);
+
+TreeGo tree_go_of(b2r_tree *t) {
+  TreeGo g;
+  g.completed = t->sync_words + 15;
+  g.go = t->sync_words + 14;
+  return g;
+}
 
 }  // namespace b2r
 

@@ -322,6 +322,28 @@ __device__ __forceinline__ void exchange_publish(const ExchangeArgs &x, int worl
 }
 #endif  // __CUDACC__
 
+// "The sampled indices are final": what the kernel in front of the early write-back
+// (tree.cu, kEarly) tells it through memory, so that the write-back can be resident and
+// start on the indices the moment they are — a programmatic dependent launch would only
+// START it then, 1.5 us later.  Every early write-back counts itself in `completed` when
+// its last CTA leaves; the kernel in front — which runs when the write-back before this
+// one has ended and this one cannot have — stores completed + 1, the number of the coming
+// launch, in `go`; the CTAs of that launch know their number from the tickets they take
+// (each before it lets ITS dependents start, so launches never interleave) and wait for
+// exactly it.
+struct TreeGo {
+  const unsigned int *completed = nullptr;
+  unsigned int *go = nullptr;  // nullptr: nothing to signal
+};
+#ifdef __CUDACC__
+// (by one thread of the kernel in front, behind its griddepcontrol.wait)
+__device__ __forceinline__ void tree_go_signal(const TreeGo &g) {
+  if (g.go == nullptr) return;
+  const unsigned int launch = *reinterpret_cast<const volatile unsigned int *>(g.completed) + 1u;
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(g.go), "r"(launch) : "memory");
+}
+#endif
+
 #ifdef __CUDACC__
 // Arguments of the batched-set kernels (tree.cu; the tiny body below also runs at the
 // tail of the C51 loss kernel, c51.cu).
@@ -357,6 +379,10 @@ struct UpdateArgs {
   // kEarly: 0 = never take the path for batches that are grouped by leaf already
   // (B2R_TREE_OWN_LISTS=0, comparison runs)
   int own_lists = 1;
+  // kEarly: the launch's tickets (always) and, when the kernel in front signals "indices
+  // final" through memory instead of through its end, the word to wait on (TreeGo)
+  unsigned long long *tickets = nullptr;
+  unsigned int *go = nullptr;
   uint32_t *sorted = nullptr;
   // role ticket, barrier flag, barrier arrivals (see tree_update_kernel)
   unsigned int *sync_words = nullptr;
@@ -561,7 +587,10 @@ template <typename I, typename V>
 int tree_apply(b2r_tree *t, int64_t n, const I *indices, const V *values,
                const uint8_t *mode, cudaStream_t stream,
                const int32_t *n_dev = nullptr, int64_t expected_n = -1, int phase = 0,
-               const b2r_exchange *publish = nullptr, unsigned int *skip_flag = nullptr);
+               const b2r_exchange *publish = nullptr, unsigned int *skip_flag = nullptr,
+               bool go_by_flag = false);
+// What the kernel in front of an early write-back of `t` signals (go_by_flag).
+TreeGo tree_go_of(b2r_tree *t);
 bool tree_can_presort(int64_t n, int64_t expected_n);
 bool tree_tiny_enabled();
 // c51.cu: the C51 loss with the write-back of its priorities at the kernel's tail.
@@ -591,6 +620,7 @@ int c51_post_launch(const b2r_c51_args *args, const float *scratch, int have_sta
                     cudaStream_t stream, int64_t *err, int32_t *count_copy = nullptr,
                     b2r_tree *tree = nullptr, const int32_t *indices = nullptr,
                     unsigned int *tree_done = nullptr,
-                    const b2r_exchange *publish = nullptr, float *loss_host = nullptr);
+                    const b2r_exchange *publish = nullptr, float *loss_host = nullptr,
+                    const TreeGo *go = nullptr);
 
 }  // namespace b2r
