@@ -13,7 +13,7 @@ timeout 300 python bench.py --steps 20 --warmup 5 > $O/${T}_n1_k20.json 2> $O/${
 timeout 200 python bench.py --impl reference --steps 5 --warmup 3 > $O/${T}_ref.json 2> $O/${T}_ref.err; echo "ref rc=$?"
 timeout 200 python profiles/micro/kernel_times.py --per-graph 10 > $O/${T}_kernel_times.jsonl 2>&1; cat $O/${T}_kernel_times.jsonl
 [ "${2:-}" = "no-ncu" ] && exit 0
-for B in 32 4096; do
+for B in 32 256 4096; do
   timeout 100 python profiles/profile_step.py --batch $B --steps 3 > $O/${T}_plain_$B.log 2>&1 || continue
   timeout 200 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none \
     --csv --log-file $O/${T}_launches_b${B}.csv python profiles/profile_step.py --batch $B --steps 3 > $O/${T}_ncu_$B.log 2>&1

@@ -14,7 +14,15 @@ COLUMNS = [
     'sm__throughput.avg.pct_of_peak_sustained_elapsed',
     'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
     'smsp__issue_active.avg.pct_of_peak_sustained_active',
-    'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct']
+    'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct',
+    # stalls per issued instruction (the latency-bound kernels of the chain)
+    'sm__cycles_elapsed.max',
+    'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio']
 
 
 def main():
