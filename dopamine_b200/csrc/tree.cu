@@ -152,9 +152,12 @@ struct BigCfg {
       HashSmem h;           // leaf CTA only, before (instead of) the sort
     };
     double vals[kChunk];    // value -> leaf delta (leaf CTA) / deltas in group order
-    uint32_t place[kChunk]; // kEarly: entry k -> its place in the list of duplicate leaves
-    double leafv[kChunk];   // kEarly: entry k -> its leaf's value before the batch
-    double nodev[kChunk];   // kEarly: entry k -> its node's value on the CTA's level
+  };
+  // tree_update_early_kernel: what it stages ahead of the values, per entry k
+  struct EarlySmem : Smem {
+    uint32_t place[kChunk]; // its place in the list of duplicate leaves / all ones
+    double leafv[kChunk];   // its leaf's value before the batch
+    double nodev[kChunk];   // its node's value on the CTA's level
   };
 };
 using BigCfg4096 = BigCfg<1024, 4>;
@@ -1165,7 +1168,7 @@ struct LevelPrep {
 // barrier).
 template <typename C, typename I, typename V>
 __device__ __forceinline__ void level_prefetch(const UpdateArgs<I, V> &a, int level,
-                                               int count, typename C::Smem &sm,
+                                               int count, typename C::EarlySmem &sm,
                                                LevelPrep<C> *r, bool staged = false) {
   constexpr int kItems = C::kItems;
   const int64_t base = ((int64_t)1) << level;
@@ -1194,7 +1197,7 @@ __device__ __forceinline__ void level_prefetch(const UpdateArgs<I, V> &a, int le
 // fetches what LevelPrep holds, but for leaf and dup_of.  sm.vals is scratch here.
 template <typename C, typename I, typename V>
 __device__ __forceinline__ void group_level(const UpdateArgs<I, V> &a, int level, int count,
-                                            typename C::Smem &sm, LevelPrep<C> *r,
+                                            typename C::EarlySmem &sm, LevelPrep<C> *r,
                                             int *s_stop, ScanSmem &ss) {
   constexpr int kItems = C::kItems;
   using Sort = typename C::Sort;
@@ -1247,7 +1250,7 @@ __device__ __forceinline__ void group_level(const UpdateArgs<I, V> &a, int level
 // overwritten.)
 template <typename C, typename I, typename V>
 __device__ __forceinline__ int leaf_list_from_sorted(const UpdateArgs<I, V> &a, int n,
-                                                     typename C::Smem &sm,
+                                                     typename C::EarlySmem &sm,
                                                      LeafDupSmem<C> &dup,
                                                      const uint32_t *idx,
                                                      NearlySorted<C> *ns, uint32_t *scratch,
@@ -1336,7 +1339,7 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_early_kernel(UpdateAr
   using Info = DupInfo<C>;
   static_assert(Info::kWords <= DupInfo<BigCfg4096>::kWords, "scratch (ensure_sorted)");
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  typename C::Smem &sm = *reinterpret_cast<typename C::Smem *>(smem_raw);
+  typename C::EarlySmem &sm = *reinterpret_cast<typename C::EarlySmem *>(smem_raw);
   double *vals = sm.vals;
   __shared__ LeafDupSmem<C> s_dup;
   __shared__ double s_dupd[C::kMaxDup];  // deltas of the entries that share leaves
@@ -2011,9 +2014,9 @@ template <typename C, int WHICH, typename K>
 int allow_big_smem(K kernel) {
   static bool done = false;  // per instantiation (WHICH tells kernels of one type apart)
   if (!done) {
-    B2R_CUDA(cudaFuncSetAttribute(kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)sizeof(typename C::Smem)));
+    B2R_CUDA(cudaFuncSetAttribute(
+        kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        (int)(WHICH == 1 ? sizeof(typename C::EarlySmem) : sizeof(typename C::Smem))));
     done = true;
   }
   return B2R_OK;
@@ -2027,7 +2030,8 @@ int launch_big_chunk(const UpdateArgs<I, V> &a, int depth, cudaStream_t stream) 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(depth + 1);
   cfg.blockDim = dim3(C::kThreads);
-  cfg.dynamicSmemBytes = sizeof(typename C::Smem);
+  cfg.dynamicSmemBytes =
+      a.phase == kEarly ? sizeof(typename C::EarlySmem) : sizeof(typename C::Smem);
   cfg.stream = stream;
   cudaLaunchAttribute attr[3];
   int n_attr = 0;
