@@ -770,28 +770,31 @@ __global__ void __launch_bounds__(C::kThreads) tree_update_kernel(UpdateArgs<I, 
 // values, and no hand-over between the CTAs behind them (kEarly).
 //
 // In the fused step the indices are final when the sampler ends and the values are what
-// the loss kernel between the sampler and this kernel produces; the loss kernel lets its
-// dependents start once it has seen the sampler's end (griddepcontrol: wait, then
-// launch_dependents), so this kernel runs BESIDE it.  Ahead of its own
-// griddepcontrol.wait:
-//   * every level CTA groups the batch by node (the radix sort that used to sit between
-//     the loss and the write-back, or in a side stream with a second kernel and a join),
-//     finds the ends of its groups, and fetches the nodes it will change AND the leaves
-//     its entries point at;
-//   * the leaf CTA builds its hash set, ranks the entries that share a leaf with another
-//     entry (by leaf, then batch position) and hands that list to the level CTAs through
-//     HBM and a flag — a hand-over nobody is waiting for yet.
+// the loss tail between the sampler and this kernel produces.  This kernel is launched
+// programmatically from the tail's first instruction, so it is RESIDENT while the tail
+// works; the tail's first thread tells it through memory when the sampler has ended
+// (TreeGo, tree.cuh).  Ahead of its own griddepcontrol.wait every CTA
+//   * reads the indices and at once, per entry, its leaf and its node on the CTA's level;
+//   * finds the entries that share a leaf with another entry, ordered by leaf and batch
+//     position (the "list"), and groups the batch by node on its level.
+//     The usual batch is grouped by leaf already but for a few entries
+//     (nearly_sorted_analyse): two block scans and a binary search per moved entry, and
+//     every CTA makes the list for itself (leaf_list_from_sorted).  Any other batch: the
+//     leaf CTA makes the list with a hash set and hands it to the level CTAs through HBM
+//     and a flag — a hand-over nobody is waiting for yet — while they group by radix sort.
 // Behind the wait a level CTA needs nothing from any other CTA: an entry's delta is
-// value - leaf (sum_tree.py:196-202) with the leaf it fetched itself; the few entries that
-// share leaves are chains  delta = value - leaf; leaf += delta  that every CTA walks for
-// itself from the leaf CTA's list.  One round trip for the values, the deltas, the ordered
+// value - leaf (sum_tree.py:196-202) with the leaf as it was before the batch; the few
+// entries that share leaves are chains  delta = value - leaf; leaf += delta  that every CTA
+// walks for itself from the list.  One round trip for the values, the deltas, the ordered
 // chains (or the verified scan), the stores.  (The plain kernel's leaf CTA publishes the
-// deltas through HBM behind a fence and a flag: 4-5 us of this kernel's 11 at 1024.)
+// deltas through HBM behind a fence and a flag: 4-5 us of that kernel's 11 at 1024.)
 // When the list does not serve — more duplicates than it holds, or an entry the
 // reference's loop would have raised on (negative priority, index out of range), so that
 // only a prefix is applied — every CTA sees that for itself and the kernel goes on as the
 // plain one does: leaf pass over the prefix, deltas through HBM, flag, regrouped levels.
-// Only for callers that can promise the first sentence (phase == kEarly, train_step).
+// Only for callers that can promise that the indices are final when they say so
+// (phase == kEarly: train_step, whose loss tail signals; or a predecessor that is not a
+// programmatic launch at all, such as the copy in front of b2r_tree_set's test hook).
 template <typename C>
 struct LeafDupSmem {
   uint32_t d_idx[C::kMaxDup], d_k[C::kMaxDup], ds_idx[C::kMaxDup], ds_k[C::kMaxDup];
