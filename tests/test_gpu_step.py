@@ -98,13 +98,16 @@ def _check_step(gpu, mem, tree, cols, cap, horizon, got, out, online, target):
   return idx
 
 
-@pytest.mark.parametrize('cap,batch', [(100000, 32), (100000, 300), (200000, 1024),
-                                       (1000000, 4096)])
+@pytest.mark.parametrize('cap,batch', [(100000, 32), (100000, 48), (100000, 300),
+                                       (200000, 512), (200000, 1024), (1000000, 4096)])
 def test_fused_step_matches_oracles(gpu, cap, batch):
   """sample -> scalars -> C51 -> write-back in one call (frames on the forked
   stream): every batch column bit-exact against the C restatement at the sampled
   indices, loss / priorities / weights within 1e-6 of the numpy restatement, every
-  fp64 tree node bit-exact after the write-backs."""
+  fp64 tree node bit-exact after the write-backs.  (32: tail + write-back as one cluster;
+  48: cluster sampler, write-back that groups ahead of its values; 300, 512: that
+  write-back behind the many-CTA sampler; 1024: grouping on a side stream; 4096: thread
+  sampler, unsplit loss, plain write-back.)"""
   torch = gpu.torch
   mem, tree, cols = _filled(gpu, cap, batch, seed=cap // 1000 + batch)
   rng = np.random.RandomState(5)
