@@ -17,6 +17,11 @@
 // The root's chain of n dependent DADDs used to be the critical path (25 us at
 // n = 4096); with the verified scan it is the deepest levels' radix sort before the
 // barrier.  Bandwidth is irrelevant here (n * depth * 16 bytes).
+//
+// The fused step's write-back of 33 .. 512 rows is a second kernel over the same pieces
+// (tree_update_early_kernel, further down): resident beside the loss kernel, it does
+// everything that needs the indices only ahead of the values and nothing that needs
+// another CTA behind them.
 #include "replay.cuh"
 
 #include <cooperative_groups.h>
