@@ -312,9 +312,13 @@ __global__ void get_priority_kernel(const double *__restrict__ leaves, int64_t n
 // forces one; the default follows the measurements (profiles/r2/README.md: CUDA-event
 // times of the fused step and ncu --set full of both kernels at 32 / 256 / 1024 / 4096):
 // the TMA kernel issues half the instructions and reaches 67 % of DRAM throughput at
-// batch 4096 against 56 % (fused step 100 us against 111 us; 24.5 against 26.0 at 256);
-// between those sizes, where the copies run beside the next step's chain, the register
-// kernel with its occupancy cap is the faster one (37.2 against 39.8 us at 1024).
+// batch 4096 against 56 % (fused step 100 us against 111 us; 24.5 against 26.0 at 256).
+// Between those sizes, where the copies run beside the next step's chain, the register
+// kernel with its occupancy cap used to be the faster one (37.2 against 39.8 us at 1024)
+// — while the write-back sorted on a side stream and needed the room.  With the
+// write-back that groups ahead of its values (tree.cu, kEarly) the TMA kernel wins there
+// too: 28.6 / 33.2 / 50.3 us at 768 / 1024 / 1536 rows against 33.5 / 36.8 / 57.2
+// (profiles/r2/out/run71.txt .. run73.txt), so it is the default at every size.
 int gather_variant(int batch) {
   static const int forced = [] {
     const char *e = std::getenv("B2R_GATHER");
@@ -322,7 +326,8 @@ int gather_variant(int batch) {
     return std::strcmp(e, "tma") == 0 ? 1 : 0;
   }();
   if (forced >= 0) return forced;
-  return batch <= 512 || batch >= 2048 ? 1 : 0;
+  (void)batch;
+  return 1;
 }
 
 // Will launch_gather(frames_only) run the kernel that understands RowFlags?

@@ -245,18 +245,20 @@ static int train_step(b2r_buffer *b, int32_t batch, uint64_t seed, uint64_t offs
   int64_t expected_rows =
       shard ? (batch + shard->exchange->world - 1) / shard->exchange->world : -1;
   if (expected_rows > rows_cap) expected_rows = rows_cap;
-  // Up to B2R_TREE_EARLY_MAX rows (default 512; 0: never): ONE write-back kernel behind
-  // the loss tail that is resident early and groups the batch ahead of its values
-  // (tree.cu, kEarly; the loss tail tells it when the indices are final — TreeGo).  Above,
-  // the frame copies bound the step and what they want from the chain is to be left
-  // alone: the grouping runs as a small kernel of its own on a forked stream and is
-  // joined in front of the write-back proper (measured at 1024: 36.8 us against 40.1 with
-  // the 21 early CTAs of 1024 threads resident beside the copies).
+  // Up to B2R_TREE_EARLY_MAX rows (default 1024, the kernel's largest batch; 0: never):
+  // ONE write-back kernel behind the loss tail that is resident early and groups the batch
+  // ahead of its values (tree.cu, kEarly; the loss tail tells it when the indices are
+  // final — TreeGo).  Above (and with B2R_TREE_EARLY=0) the grouping runs as a small kernel
+  // of its own on a forked stream and is joined in front of the write-back proper.
+  // (At 1024 rows, where the frame copies bound the step: 33.2 us with the TMA copies,
+  // 36.8 us with the side-stream grouping and the register copies under their occupancy
+  // cap, 40.1 us with this kernel beside the capped register copies —
+  // profiles/r2/out/run63.txt, run71.txt, run72.txt.)
   static const int tree_early_max = [] {
     const char *e = std::getenv("B2R_TREE_EARLY_MAX");
     const char *off = std::getenv("B2R_TREE_EARLY");
     if (off != nullptr && std::atoi(off) == 0) return 0;
-    return e != nullptr ? std::atoi(e) : 512;
+    return e != nullptr ? std::atoi(e) : 1024;
   }();
   const bool groupable = tree_can_presort(rows_cap, expected_rows) && !(debug_skip() & 6);
   const int64_t likely_rows = expected_rows >= 0 ? expected_rows : rows_cap;
