@@ -439,7 +439,10 @@ def test_peer_exchange_times_out_instead_of_hanging(gpu):
     (256, False, False, False), (2048, False, False, False), (256, True, False, False),
     (2048, True, False, False), (256, True, True, False), (2048, True, True, False),
     (128, True, True, True), (96, True, False, True), (64, True, True, True),
-    (96, True, False, False), (128, False, False, False)])
+    (96, True, False, False), (128, False, False, False),
+    # expected share 1024 rows, the hot rank's beyond it: the early write-back takes the
+    # first 1024 entries, the plain kernel behind it the rest
+    (4096, True, False, False), (4096, True, True, False)])
 def test_sharded_fused_step_matches_oracles(gpu, global_batch, bounded, deferred, early):
   """b2r_train_step_sharded_device on 4 emulated ranks (one sampling CTA up to a
   global batch of 256, tiles over each rank's stratum range above): each rank's rows
