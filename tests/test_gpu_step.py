@@ -707,8 +707,8 @@ def test_early_publish_latches_a_tree_change_behind_its_back(gpu):
 @pytest.mark.parametrize('variant', ['tma', 'reg'])
 def test_each_gather_variant_passes_the_gather_parity_suite(variant):
   """The frame copies have two kernels: the TMA-staged one (cp.async.bulk into shared
-  memory on an mbarrier) and the register one (LDG.128 -> PRMT -> STG.128); by default
-  the batch size picks (gather.cu: gather_variant).  B2R_GATHER forces one for a whole
+  memory on an mbarrier, the default) and the register one (LDG.128 -> PRMT -> STG.128;
+  gather.cu: gather_variant).  B2R_GATHER forces one for a whole
   process, so the gather parity tests are re-run in a child process with each (bit-exact
   batches at 100k / 1M, wrap-around, terminals inside trajectories, fused and sharded
   steps) — every size goes through both kernels."""
